@@ -1,0 +1,207 @@
+/*
+ * trust4_b200 -- C ABI of the B200-native stage-1 assembly hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI; its
+ * boundary is the C++ class SeqSet as used by the stage-1 driver.  Every entry
+ * point below names the reference interface it replaces (file:line under the
+ * reference tree).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * One `t4_seqset` is one novel-contig set (reference: `SeqSet seqSet(k)`,
+ * main.cpp:642) and, on the device, one *stream*: a persistent CTA owns its
+ * contigs, posWeight columns and k-mer postings in HBM and executes the reads
+ * submitted to it strictly in order (the reference's AddRead loop is serial,
+ * main.cpp:1583-1880).  Many seqsets run concurrently, one CTA each.
+ *
+ * Return conventions follow the reference: AddRead >= 0 contig slot, -1 not
+ * added, -2 overlapped but could not extend (SeqSet.hpp:3422-3425, 4463-4467).
+ * Errors of this library are < T4_E_BASE and never abort the process.
+ */
+#ifndef TRUST4_B200_H
+#define TRUST4_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T4_OK 0
+#define T4_E_BASE (-16)
+#define T4_E_CUDA (-17)        /* CUDA runtime error (see t4_last_error) */
+#define T4_E_NOMEM (-18)       /* device arena exhausted */
+#define T4_E_INVAL (-19)       /* bad argument */
+#define T4_E_UNSUPPORTED (-20) /* e.g. isLongSeqSet, read longer than T4_MAX_READ_LEN */
+#define T4_E_NODEVICE (-21)    /* no CUDA device: there is NO CPU fallback */
+#define T4_E_INTERNAL (-22)    /* device-side invariant violated */
+
+#define T4_MAX_READ_LEN 1000
+
+typedef struct t4_seqset t4_seqset;
+
+/* ---- library / device ------------------------------------------------- */
+/* Select the device and size the device arena (bytes; 0 = 1/2 of free HBM).
+ * Optional: the first t4_seqset_create() calls t4_init(current device, 0). */
+int t4_init(int device, size_t arena_bytes);
+int t4_shutdown(void);
+const char *t4_last_error(void);
+const char *t4_version(void);
+/* Bytes of device arena in use / capacity (diagnostics). */
+int t4_arena_stats(size_t *used, size_t *capacity);
+
+/* ---- SeqSet mirror ---------------------------------------------------- */
+/* SeqSet::SeqSet(int kl), SeqSet.hpp:2558-2576 (radius 10, hitLenRequired 31,
+ * novelSeqSimilarity 0.9, nomatchGapLimit from k). */
+t4_seqset *t4_seqset_create(int kmer_length);
+void t4_seqset_destroy(t4_seqset *s);
+/* SeqSet::SetHitLenRequired, SeqSet.hpp:2601 */
+int t4_seqset_set_hit_len_required(t4_seqset *s, int l);
+/* SeqSet::SetNovelSeqSimilarity, SeqSet.hpp:2606 */
+int t4_seqset_set_novel_seq_similarity(t4_seqset *s, double v);
+/* SeqSet::SetConsiderBarcodeInIndexHash, SeqSet.hpp:2611 */
+int t4_seqset_set_consider_barcode_in_hash(t4_seqset *s, int on);
+/* SeqSet::SetIsLongSeqSet, SeqSet.hpp:11082 -- only `0` is supported (reads <= 200 bp). */
+int t4_seqset_set_is_long(t4_seqset *s, int on);
+/* SeqSet::Size, SeqSet.hpp:2591 (counts released slots) */
+int t4_seqset_size(t4_seqset *s);
+int t4_seqset_kmer_length(t4_seqset *s);
+
+/* int SeqSet::AddRead(char *read, char *geneName, int &strand, int barcode,
+ *   int minKmerCount, bool repetitiveData, double similarityThreshold), SeqSet.hpp:3426 */
+int t4_seqset_add_read(t4_seqset *s, const char *read, const char *gene_name, int *strand_inout,
+                       int barcode, int min_kmer_count, int repetitive, double sim_threshold);
+/* int SeqSet::RepeatAddRead(char *read), SeqSet.hpp:4477 */
+int t4_seqset_repeat_add_read(t4_seqset *s, const char *read);
+/* int SeqSet::InputNovelRead(const char *id, char *read, int strand, int barcode), SeqSet.hpp:3028 */
+int t4_seqset_input_novel_read(t4_seqset *s, const char *id, const char *read, int strand, int barcode);
+/* void SeqSet::UpdateAllConsensus(), SeqSet.hpp:4525 */
+int t4_seqset_update_all_consensus(t4_seqset *s);
+/* void SeqSet::ChangeKmerLength(int kl), SeqSet.hpp:4624 (compacts slots, rebuilds the index) */
+int t4_seqset_change_kmer_length(t4_seqset *s, int kmer_length);
+/* void SeqSet::Output(FILE*, std::vector<std::string>*), SeqSet.hpp:10939 */
+int t4_seqset_output(t4_seqset *s, FILE *fp, const char *const *barcode_names, int n_barcode_names);
+/* Same text into a malloc'ed buffer (caller frees with t4_free). */
+int t4_seqset_output_mem(t4_seqset *s, char **buf, size_t *len);
+void t4_free(void *p);
+
+/* Contig accessors (hand contigs back to the CPU mate-extension code,
+ * SeqSet::InputSeqSet consumer, SeqSet.hpp:3108).  Buffers may be NULL to query sizes.
+ * Returns consensus length, or -1 for a released slot. */
+int t4_seqset_get_contig(t4_seqset *s, int slot, char *consensus, int consensus_cap,
+                         int32_t *pos_weight /* 4*len, [pos][ACGT] */, char *name, int name_cap,
+                         int *barcode, int *num_read, int *min_left_ext_anchor, int *min_right_ext_anchor);
+
+/* int SeqSet::HasMotif(char *read, int strand), SeqSet.hpp:5029 (host utility) */
+int t4_has_motif(const char *read, int strand);
+/* void SeqSet::ReverseComplementInPlace(char*, int), SeqSet.hpp:2629 (host utility) */
+void t4_reverse_complement_in_place(char *seq, int len);
+
+/* ---- read-only probes over a frozen set (parity / roofline entry points) -- */
+/* SeqSet::GetHitsFromRead + SortHits, SeqSet.hpp:1341, 1306.
+ * Writes up to cap hits as int32[5] = {seqIdx, seqOffset, readOffset, strand, repeats},
+ * ordered by (strand, seqIdx, readOffset, seqOffset).  Returns the hit count. */
+int t4_seqset_get_hits(t4_seqset *s, const char *read, int strand, int barcode, int allow_total_skip,
+                       int32_t *hits, int cap);
+/* SeqSet::GetOverlapsFromRead (readType 0), SeqSet.hpp:1508: scored overlaps as
+ * int32[8] = {seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, indelCnt}
+ * plus similarity[i].  Returns the overlap count (or -1 when the read is shorter than k). */
+int t4_seqset_get_overlaps(t4_seqset *s, const char *read, int strand, int barcode, int skip_repeats,
+                           int32_t *overlaps, double *similarity, int cap);
+/* AlignAlgo::GlobalAlignment_PosWeight, AlignAlgo.hpp:57: n independent problems on the device.
+ * t_weights: concatenated int32[4] columns, p: concatenated chars; offsets arrays have n+1 entries.
+ * align_out: concatenated edit strings, problem i at align_off[i] (capacity lent+lenp+1 each),
+ * terminated by -1.  score_out[i] is the returned score. */
+int t4_dp_pos_weight_batch(int n, const int32_t *t_weights, const int64_t *t_off, const char *p,
+                           const int64_t *p_off, int8_t *align_out, const int64_t *align_off,
+                           int32_t *score_out);
+
+/* ---- batch / multi-stream entry (the throughput path) ------------------ */
+/* One element per iteration of the reference's AddRead loop (main.cpp:1583-1880):
+ * everything the loop derives from the pre-processing (rough annotation, k-mer
+ * counts, sort) is precomputed by the host into this record; everything that
+ * depends on the evolving contig set is decided on the device. */
+typedef struct t4_read_desc {
+    uint64_t seq_off;        /* offset of the read (ASCII ACGTN) in the read pool */
+    int32_t len;             /* read length */
+    int32_t barcode;         /* sortedReads[i].barcode, -1 = none */
+    int32_t min_cnt;         /* sortedReads[i].minCnt (rescue threshold, main.cpp:1914-1923) */
+    int32_t min_kmer_count;  /* AddRead argument (main.cpp:1700-1701) */
+    double sim_threshold;    /* main.cpp:1676-1694 */
+    int32_t name_id;         /* InputNovelRead name on failure (index into names), -1 = none */
+    int32_t mate_idx;        /* sortedReads[i].mateIdx as an index into this array, -1 = none */
+    int32_t eq_lo, eq_hi;    /* [eq_lo,eq_hi): maximal run of records with this read string (main.cpp:1814-1835) */
+    uint32_t flags;          /* T4_RD_* */
+    int8_t strand_in;        /* strand passed to AddRead (0 = unknown) */
+    int8_t novel_strand;     /* strand passed to InputNovelRead (main.cpp:1743) */
+    char gene4[4];           /* 4-char gene prefix passed as geneName, zero padded */
+    int8_t pad_[2];
+} t4_read_desc;
+
+#define T4_RD_DUP (1u << 0)           /* same read+barcode as the previous record (main.cpp:1596) */
+#define T4_RD_FILTERED (1u << 1)      /* V/D/J/C order or C-gene filter hit (main.cpp:1609-1654) */
+#define T4_RD_NOVEL_ON_FAIL (1u << 2) /* anchored: InputNovelRead(names[name_id]) if AddRead<0 (main.cpp:1706-1745) */
+#define T4_RD_MOTIF (1u << 3)         /* HasMotif(read, +-1) != 0 (main.cpp:1752) */
+#define T4_RD_GOOD_PLUS (1u << 4)     /* main.cpp:1782-1808 evaluates to good when strand==+1 */
+#define T4_RD_GOOD_MINUS (1u << 5)    /* ... when strand==-1 */
+#define T4_RD_MOTIF_FORCED (1u << 6)  /* replay mode: take the motif path with strand = novel_strand */
+
+typedef struct t4_run_cfg {
+    int32_t has_barcode;           /* main.cpp hasBarcode: no periodic UpdateAllConsensus / k change */
+    int32_t repetitive;            /* trimLevel > 1 (AddRead repetitiveData) */
+    int32_t change_k_threshold;    /* changeKmerLengthThreshold, main.cpp:641,1567 (0 = never) */
+    int32_t update_consensus_every;/* main.cpp:1862 (10000; 0 = never) */
+    int32_t do_rescue;             /* run the rescue pass main.cpp:1897-1940 */
+    int32_t first_read_len;        /* firstReadLen (rescue is skipped when > 200) */
+    int32_t final_update;          /* UpdateAllConsensus after each pass (main.cpp:1881,1939) */
+    int32_t reserved_;
+} t4_run_cfg;
+
+/* Observationally equal to running the reference loop (main.cpp:1583-1881, and
+ * 1897-1940 when cfg->do_rescue) over descs[0..n) on this seqset.
+ * ret_codes[i]: addRet of iteration i; strands[i]: sortedReads[i].strand afterwards;
+ * rescue_ret (may be NULL): n entries, addRet of the rescue pass or INT32_MIN if not rescued. */
+int t4_seqset_add_reads_batch(t4_seqset *s, const t4_run_cfg *cfg, const t4_read_desc *descs, int n,
+                              const char *read_pool, size_t read_pool_bytes,
+                              const char *const *names, int n_names,
+                              int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
+
+/* The same over many independent seqsets at once: one CTA per stream, one launch.
+ * Stream j consumes descs[desc_off[j] .. desc_off[j+1]) (mate_idx / eq_* are
+ * relative to desc_off[j]).  Host buffers; H2D/D2H are part of the call. */
+int t4_streams_run(t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg,
+                   const t4_read_desc *descs, const int64_t *desc_off,
+                   const char *read_pool, size_t read_pool_bytes,
+                   const char *const *names, int n_names,
+                   int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
+
+/* Device-resident variant used by bench.py's `value` leg: the workload is
+ * uploaded once (t4_workload_upload), then t4_streams_run_resident() only
+ * launches kernels on `cuda_stream` (a cudaStream_t cast to void*, NULL = default). */
+typedef struct t4_workload t4_workload;
+t4_workload *t4_workload_upload(const t4_read_desc *descs, int64_t n_descs, const char *read_pool,
+                                size_t read_pool_bytes, const char *const *names, int n_names);
+void t4_workload_free(t4_workload *w);
+int t4_streams_run_resident(t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg,
+                            t4_workload *w, const int64_t *desc_off, void *cuda_stream);
+/* Copy results of the last resident run back. */
+int t4_workload_results(t4_workload *w, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
+
+/* Per-launch device counters of the last run (summed over streams):
+ * [0] reads processed, [1] AddRead executed, [2] k-mer lookups executed, [3] postings read (sum c_j),
+ * [4] hits emitted (sum c_j'), [5] read bytes, [6] overlaps scored, [7] full banded DPs,
+ * [8] probe-phase clock cycles (sum over CTAs), [9] total clock cycles (sum over CTAs),
+ * [10..15] per-phase cycles: sort, chain, score, decide, commit, other. */
+#define T4_N_COUNTERS 16
+int t4_last_counters(uint64_t *counters /* T4_N_COUNTERS */);
+
+/* Standalone probe kernel over frozen sets (roofline measurement):
+ * reads of the workload are probed against the set of their stream, hits written to HBM.
+ * Returns 0; kernel time is measured by the caller with CUDA events on cuda_stream. */
+int t4_probe_resident(t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off,
+                      void *cuda_stream, uint64_t *algorithmic_bytes, uint64_t *hits_emitted);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,445 @@
+// TEST INFRASTRUCTURE (oracle) -- not part of the product.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load the library built from this file.
+//
+// Library-level oracle: a thin C ABI over the UNMODIFIED
+// reference classes, compiled from the sources where they lie in /root/reference
+// (see oracle/Makefile; output oracle/_ref/libt4ref.so).  `#define private public`
+// gives the stage dumps (hits, chains, overlaps, index) access to SeqSet's
+// private helpers.  Nothing of the reference is copied into this repository.
+//
+// Besides the per-call wrappers, t4ref_run_descs() restates the stage-1 driver
+// loop rules (main.cpp:1583-1880, rescue pass 1897-1940) over t4_read_desc
+// records -- the oracle for the batch entry t4_seqset_add_reads_batch().  That
+// restatement is pinned against the stock binary by tests/test_oracle_pin.py
+// (call-trace replay must reproduce trust4's own _raw.out byte for byte).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <time.h>
+#include <assert.h>
+#include <limits.h>
+#include <map>
+#include <vector>
+#include <string>
+
+#define private public
+#include "SeqSet.hpp"
+#undef private
+
+#include "../include/trust4_b200.h"
+
+// Each reference executable defines these (main.cpp:39-44); values restated from defs.h's contract.
+int nucToNum[26] = { 0, -1, 1, -1, -1, -1, 2,
+	-1, -1, -1, -1, -1, -1, 0,
+	-1, -1, -1, -1, -1, 3,
+	-1, -1, -1, -1, -1, -1 } ;
+char numToNuc[26] = {'A', 'C', 'G', 'T'} ;
+
+extern "C" {
+
+void *t4ref_create( int k ) { return new SeqSet( k ) ; }
+void t4ref_destroy( void *h ) { delete (SeqSet *)h ; }
+int t4ref_set_hit_len_required( void *h, int l ) { return ((SeqSet *)h)->SetHitLenRequired( l ) ; }
+double t4ref_set_novel_seq_similarity( void *h, double v ) { return ((SeqSet *)h)->SetNovelSeqSimilarity( v ) ; }
+void t4ref_set_consider_barcode_in_hash( void *h, int on ) { ((SeqSet *)h)->SetConsiderBarcodeInIndexHash( on != 0 ) ; }
+void t4ref_set_is_long( void *h, int on ) { ((SeqSet *)h)->SetIsLongSeqSet( on != 0 ) ; }
+int t4ref_size( void *h ) { return ((SeqSet *)h)->Size() ; }
+int t4ref_kmer_length( void *h ) { return ((SeqSet *)h)->kmerLength ; }
+
+int t4ref_add_read( void *h, const char *read, const char *geneName, int *strand, int barcode, int minKmerCount,
+	int repetitive, double thr )
+{
+	char *r = strdup( read ) ;
+	char name[64] ;
+	strncpy( name, geneName, 63 ) ; name[63] = '\0' ;
+	int s = *strand ;
+	int ret = ((SeqSet *)h)->AddRead( r, name, s, barcode, minKmerCount, repetitive != 0, thr ) ;
+	*strand = s ;
+	free( r ) ;
+	return ret ;
+}
+
+int t4ref_repeat_add_read( void *h, const char *read )
+{
+	char *r = strdup( read ) ;
+	int ret = ((SeqSet *)h)->RepeatAddRead( r ) ;
+	free( r ) ;
+	return ret ;
+}
+
+int t4ref_input_novel_read( void *h, const char *id, const char *read, int strand, int barcode )
+{
+	char *r = strdup( read ) ;
+	int ret = ((SeqSet *)h)->InputNovelRead( id, r, strand, barcode ) ;
+	free( r ) ;
+	return ret ;
+}
+
+void t4ref_update_all_consensus( void *h ) { ((SeqSet *)h)->UpdateAllConsensus() ; }
+void t4ref_change_kmer_length( void *h, int kl ) { ((SeqSet *)h)->ChangeKmerLength( kl ) ; }
+
+int t4ref_has_motif( void *h, const char *read, int strand )
+{
+	char *r = strdup( read ) ;
+	int ret = ((SeqSet *)h)->HasMotif( r, strand ) ;
+	free( r ) ;
+	return ret ;
+}
+
+void t4ref_reverse_complement_in_place( void *h, char *seq, int len ) { ((SeqSet *)h)->ReverseComplementInPlace( seq, len ) ; }
+
+// SeqSet::Output into a malloc'ed buffer; caller frees with t4ref_free.
+int t4ref_output_mem( void *h, char **buf, size_t *len )
+{
+	FILE *fp = open_memstream( buf, len ) ;
+	if ( fp == NULL )
+		return -1 ;
+	((SeqSet *)h)->Output( fp, NULL ) ;
+	fclose( fp ) ;
+	return 0 ;
+}
+void t4ref_free( void *p ) { free( p ) ; }
+
+// Contig accessors.
+int t4ref_get_contig( void *h, int slot, char *consensus, int consensusCap, int32_t *posWeight, char *name, int nameCap,
+	int *barcode, int *numRead, int *minLeft, int *minRight )
+{
+	SeqSet *s = (SeqSet *)h ;
+	if ( slot < 0 || slot >= (int)s->seqs.size() || s->seqs[slot].consensus == NULL )
+		return -1 ;
+	struct _seqWrapper &seq = s->seqs[slot] ;
+	int len = seq.consensusLen ;
+	if ( consensus != NULL && consensusCap > len )
+	{
+		memcpy( consensus, seq.consensus, len ) ;
+		consensus[len] = '\0' ;
+	}
+	if ( posWeight != NULL )
+		for ( int i = 0 ; i < len ; ++i )
+			for ( int j = 0 ; j < 4 ; ++j )
+				posWeight[4 * i + j] = seq.posWeight[i].count[j] ;
+	if ( name != NULL && nameCap > 0 )
+	{
+		strncpy( name, seq.name, nameCap - 1 ) ;
+		name[nameCap - 1] = '\0' ;
+	}
+	if ( barcode ) *barcode = seq.barcode ;
+	if ( numRead ) *numRead = seq.numRead ;
+	if ( minLeft ) *minLeft = seq.minLeftExtAnchor ;
+	if ( minRight ) *minRight = seq.minRightExtAnchor ;
+	return len ;
+}
+
+// ---- stage dumps ----------------------------------------------------------
+// GetHitsFromRead + SortHits (SeqSet.hpp:1341, 1306): int32[5] per hit.
+int t4ref_get_hits( void *h, const char *read, int strand, int barcode, int allowTotalSkip, int32_t *out, int cap )
+{
+	SeqSet *s = (SeqSet *)h ;
+	int len = strlen( read ) ;
+	if ( len < s->kmerLength )
+		return 0 ;
+	char *r = strdup( read ) ;
+	char *rc = new char[len + 1] ;
+	SimpleVector<struct _hit> hits ;
+	s->GetHitsFromRead( r, rc, strand, barcode, allowTotalSkip != 0, hits, NULL ) ;
+	s->SortHits( hits, true ) ;
+	int n = hits.Size() ;
+	for ( int i = 0 ; i < n && i < cap ; ++i )
+	{
+		out[5 * i] = hits[i].indexHit.idx ;
+		out[5 * i + 1] = hits[i].indexHit.offset ;
+		out[5 * i + 2] = hits[i].readOffset ;
+		out[5 * i + 3] = hits[i].strand ;
+		out[5 * i + 4] = hits[i].repeats ;
+	}
+	delete[] rc ;
+	free( r ) ;
+	return n ;
+}
+
+// GetHitsFromRead + SortHits + GetOverlapsFromHits (SeqSet.hpp:763) as AddRead's
+// full pass runs it (filter 1, conservativeChain false): int32[8] per chain =
+// {seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, nHitCoords}; the
+// hitCoords (a,b) pairs are appended to coords (2 ints each) in chain order.
+int t4ref_get_chains( void *h, const char *read, int strand, int barcode, int allowTotalSkip, int filter,
+	int32_t *out, int cap, int32_t *coords, int coordCap, int *nCoords )
+{
+	SeqSet *s = (SeqSet *)h ;
+	int len = strlen( read ) ;
+	*nCoords = 0 ;
+	if ( len < s->kmerLength )
+		return 0 ;
+	char *r = strdup( read ) ;
+	char *rc = new char[len + 1] ;
+	SimpleVector<struct _hit> hits ;
+	std::vector<struct _overlap> overlaps ;
+	s->GetHitsFromRead( r, rc, strand, barcode, allowTotalSkip != 0, hits, NULL ) ;
+	s->SortHits( hits, true ) ;
+	int n = s->GetOverlapsFromHits( hits, s->hitLenRequired, filter, false, overlaps ) ;
+	int c = 0 ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		int m = overlaps[i].hitCoords->Size() ;
+		if ( i < cap )
+		{
+			out[8 * i] = overlaps[i].seqIdx ;
+			out[8 * i + 1] = overlaps[i].readStart ;
+			out[8 * i + 2] = overlaps[i].readEnd ;
+			out[8 * i + 3] = overlaps[i].seqStart ;
+			out[8 * i + 4] = overlaps[i].seqEnd ;
+			out[8 * i + 5] = overlaps[i].strand ;
+			out[8 * i + 6] = overlaps[i].matchCnt ;
+			out[8 * i + 7] = m ;
+		}
+		for ( int j = 0 ; j < m ; ++j )
+		{
+			if ( c + j < coordCap )
+			{
+				coords[2 * ( c + j )] = (*overlaps[i].hitCoords)[j].a ;
+				coords[2 * ( c + j ) + 1] = (*overlaps[i].hitCoords)[j].b ;
+			}
+		}
+		c += m ;
+		delete overlaps[i].hitCoords ;
+	}
+	*nCoords = c ;
+	delete[] rc ;
+	free( r ) ;
+	return n ;
+}
+
+// GetOverlapsFromRead (SeqSet.hpp:1508) with readType 0: int32[8] per overlap + similarity.
+int t4ref_get_overlaps( void *h, const char *read, int strand, int barcode, int skipRepeats, int32_t *out, double *sim, int cap )
+{
+	SeqSet *s = (SeqSet *)h ;
+	char *r = strdup( read ) ;
+	std::vector<struct _overlap> overlaps ;
+	int n = s->GetOverlapsFromRead( r, strand, barcode, 0, skipRepeats != 0, overlaps ) ;
+	for ( int i = 0 ; i < n && i < cap ; ++i )
+	{
+		out[8 * i] = overlaps[i].seqIdx ;
+		out[8 * i + 1] = overlaps[i].readStart ;
+		out[8 * i + 2] = overlaps[i].readEnd ;
+		out[8 * i + 3] = overlaps[i].seqStart ;
+		out[8 * i + 4] = overlaps[i].seqEnd ;
+		out[8 * i + 5] = overlaps[i].strand ;
+		out[8 * i + 6] = overlaps[i].matchCnt ;
+		out[8 * i + 7] = overlaps[i].indelCnt ;
+		sim[i] = overlaps[i].similarity ;
+	}
+	free( r ) ;
+	return n ;
+}
+
+// AlignAlgo::GlobalAlignment_PosWeight (AlignAlgo.hpp:57).  align must hold lent+lenp+2 entries.
+int t4ref_dp_pos_weight( const int32_t *tWeights, int lent, const char *p, int lenp, signed char *align )
+{
+	struct _posWeight *w = new struct _posWeight[lent + 1] ;
+	for ( int i = 0 ; i < lent ; ++i )
+		for ( int j = 0 ; j < 4 ; ++j )
+			w[i].count[j] = tWeights[4 * i + j] ;
+	char *pp = (char *)malloc( lenp + 1 ) ;
+	memcpy( pp, p, lenp ) ;
+	pp[lenp] = '\0' ;
+	int ret = (int)AlignAlgo::GlobalAlignment_PosWeight( w, lent, pp, lenp, align ) ;
+	free( pp ) ;
+	delete[] w ;
+	return ret ;
+}
+
+// Postings of one k-mer (KmerIndex::Search, KmerIndex.hpp:104), in the reference's list order.
+int t4ref_index_lookup( void *h, uint64_t code, int barcode, int32_t *out, int cap )
+{
+	SeqSet *s = (SeqSet *)h ;
+	KmerCode kc( s->kmerLength ) ;
+	kc.SetCode( code ) ;
+	SimpleVector<struct _indexInfo> &l = *s->seqIndex.Search( kc, barcode ) ;
+	int n = l.Size() ;
+	for ( int i = 0 ; i < n && i < cap ; ++i )
+	{
+		out[2 * i] = l[i].idx ;
+		out[2 * i + 1] = l[i].offset ;
+	}
+	return n ;
+}
+
+// Total number of postings and an order-independent checksum of the whole index.
+int64_t t4ref_index_checksum( void *h, uint64_t *checksum )
+{
+	SeqSet *s = (SeqSet *)h ;
+	int64_t total = 0 ;
+	uint64_t sum = 0 ;
+	for ( int b = 0 ; b < KINDEX_HASH_MAX ; ++b )
+	{
+		for ( std::map<uint64_t, SimpleVector<struct _indexInfo> >::iterator it = s->seqIndex.index[b].begin() ;
+			it != s->seqIndex.index[b].end() ; ++it )
+		{
+			int n = it->second.Size() ;
+			total += n ;
+			for ( int i = 0 ; i < n ; ++i )
+			{
+				uint64_t x = it->first * 0x9E3779B97F4A7C15ull ^ ( (uint64_t)(uint32_t)it->second[i].idx << 32 | (uint32_t)it->second[i].offset ) ;
+				x ^= x >> 31 ; x *= 0xBF58476D1CE4E5B9ull ; x ^= x >> 29 ;
+				sum += x ;
+			}
+		}
+	}
+	*checksum = sum ;
+	return total ;
+}
+
+int t4ref_nomatch_gap_limit( void *h ) { return ((SeqSet *)h)->nomatchGapLimit ; }
+
+// ---- restated driver loop over read descriptors ---------------------------
+// Follows main.cpp:1583-1880 (main pass) and 1897-1940 (rescue pass).  The static
+// per-read quantities (filter, gene prefix, strand, thresholds, anchoring) arrive
+// precomputed in t4_read_desc; see include/trust4_b200.h.
+static double RescueThreshold( int minCnt ) // main.cpp:1913-1923
+{
+	double t = 0.9 ;
+	if ( minCnt >= 20 )
+		t = 0.97 ;
+	else if ( minCnt >= 2 )
+		t = 0.95 ;
+	return t ;
+}
+
+int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, int n, const char *pool,
+	const char *const *names, int nNames, int32_t *retCodes, int8_t *strands, int32_t *rescueRet )
+{
+	SeqSet *s = (SeqSet *)h ;
+	int i, j ;
+	int assembledReadCnt = 0 ;
+	int prevAddRet = -1 ;
+	int indexKmerLength = s->kmerLength ;
+	int changeKmerLengthThreshold = cfg->change_k_threshold ;
+	std::vector<char> goodCandidate( n, 0 ) ;
+	std::vector<int> info( n, -1 ) ;
+	std::vector<int> rescue ;
+	char *buf = (char *)malloc( T4_MAX_READ_LEN + 2 ) ;
+	for ( i = 0 ; i < n ; ++i )
+	{
+		const t4_read_desc &d = descs[i] ;
+		int addRet = -1 ;
+		memcpy( buf, pool + d.seq_off, d.len ) ;
+		buf[d.len] = '\0' ;
+		if ( !( d.flags & T4_RD_DUP ) )
+		{
+			int strand = 0 ;
+			if ( d.flags & T4_RD_FILTERED )
+				addRet = -1 ;
+			else
+			{
+				char name[5] ;
+				memcpy( name, d.gene4, 4 ) ;
+				name[4] = '\0' ;
+				strand = d.strand_in ;
+				addRet = s->AddRead( buf, name, strand, d.barcode, d.min_kmer_count, cfg->repetitive != 0, d.sim_threshold ) ;
+				if ( addRet < 0 )
+				{
+					if ( d.flags & T4_RD_NOVEL_ON_FAIL )
+						addRet = s->InputNovelRead( names[d.name_id], buf, d.novel_strand, d.barcode ) ;
+					else if ( d.flags & T4_RD_MOTIF_FORCED )
+					{
+						if ( s->HasMotif( buf, d.novel_strand ) )
+							addRet = s->InputNovelRead( "Novel", buf, d.novel_strand, d.barcode ) ;
+					}
+					else if ( goodCandidate[i] )
+					{
+						int ms = -strands[ info[i] ] ;
+						if ( ms != 0 && ( d.flags & T4_RD_MOTIF ) )
+							addRet = s->InputNovelRead( "Novel", buf, ms, d.barcode ) ;
+					}
+				}
+				strands[i] = strand ;
+			}
+			if ( d.flags & T4_RD_FILTERED )
+				strands[i] = 0 ; // sortedReads[i].strand keeps its rough-annotation value; not observable downstream
+		}
+		else
+		{
+			if ( prevAddRet != -1 && prevAddRet != -3 )
+				addRet = s->RepeatAddRead( buf ) ;
+			else if ( prevAddRet == -3 )
+				addRet = -3 ;
+			strands[i] = i > 0 ? strands[i - 1] : 0 ;
+		}
+
+		if ( addRet == -2 )
+			rescue.push_back( i ) ;
+		else if ( addRet >= 0 )
+		{
+			++assembledReadCnt ;
+			if ( d.mate_idx > i )
+			{
+				bool good = false ;
+				if ( strands[i] == 1 && ( d.flags & T4_RD_GOOD_PLUS ) )
+					good = true ;
+				if ( strands[i] == -1 && ( d.flags & T4_RD_GOOD_MINUS ) )
+					good = true ;
+				if ( good && !goodCandidate[ d.mate_idx ] )
+				{
+					int tag = d.mate_idx ;
+					const t4_read_desc &m = descs[tag] ;
+					for ( j = tag - 1 ; j > 0 && j >= m.eq_lo ; --j )
+					{
+						goodCandidate[j] = 1 ;
+						info[j] = i ;
+					}
+					for ( j = tag + 1 ; j < n && j < m.eq_hi ; ++j )
+					{
+						goodCandidate[j] = 1 ;
+						info[j] = i ;
+					}
+				}
+				if ( good )
+				{
+					goodCandidate[ d.mate_idx ] = 1 ;
+					info[ d.mate_idx ] = i ;
+				}
+			}
+		}
+		retCodes[i] = addRet ;
+
+		if ( assembledReadCnt > 0 && cfg->update_consensus_every > 0 && assembledReadCnt % cfg->update_consensus_every == 0
+			&& !cfg->has_barcode )
+			s->UpdateAllConsensus() ;
+		prevAddRet = addRet ;
+		if ( changeKmerLengthThreshold > 0 && s->Size() > changeKmerLengthThreshold && indexKmerLength < 16 && !cfg->has_barcode )
+		{
+			changeKmerLengthThreshold *= 4 ;
+			indexKmerLength += 2 ;
+			s->ChangeKmerLength( indexKmerLength ) ;
+		}
+	}
+	if ( cfg->final_update )
+		s->UpdateAllConsensus() ;
+
+	if ( rescueRet != NULL )
+		for ( i = 0 ; i < n ; ++i )
+			rescueRet[i] = INT_MIN ;
+	if ( cfg->do_rescue && cfg->first_read_len <= 200 )
+	{
+		int cnt = rescue.size() ;
+		for ( i = 0 ; i < cnt ; ++i )
+		{
+			const t4_read_desc &d = descs[ rescue[i] ] ;
+			memcpy( buf, pool + d.seq_off, d.len ) ;
+			buf[d.len] = '\0' ;
+			char name[2] = "" ;
+			int strand = 0 ;
+			int addRet = s->AddRead( buf, name, strand, d.barcode, 1, cfg->repetitive != 0, RescueThreshold( d.min_cnt ) ) ;
+			strands[ rescue[i] ] = strand ;
+			if ( rescueRet != NULL )
+				rescueRet[ rescue[i] ] = addRet ;
+		}
+		if ( cfg->final_update )
+			s->UpdateAllConsensus() ;
+	}
+	free( buf ) ;
+	return assembledReadCnt ;
+}
+
+} // extern "C"
