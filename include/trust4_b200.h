@@ -49,11 +49,15 @@ const char *t4_last_error(void);
 const char *t4_version(void);
 /* Bytes of device arena in use / capacity (diagnostics). */
 int t4_arena_stats(size_t *used, size_t *capacity);
+/* Drop every seqset at once (the arena is a bump allocator; all t4_seqset handles become stale). */
+int t4_reset(void);
 
 /* ---- SeqSet mirror ---------------------------------------------------- */
 /* SeqSet::SeqSet(int kl), SeqSet.hpp:2558-2576 (radius 10, hitLenRequired 31,
  * novelSeqSimilarity 0.9, nomatchGapLimit from k). */
 t4_seqset *t4_seqset_create(int kmer_length);
+/* n sets with one device launch (read-sharded runs create thousands of streams). */
+int t4_seqsets_create(int n, int kmer_length, t4_seqset **handles);
 void t4_seqset_destroy(t4_seqset *s);
 /* SeqSet::SetHitLenRequired, SeqSet.hpp:2601 */
 int t4_seqset_set_hit_len_required(t4_seqset *s, int l);
@@ -186,6 +190,11 @@ int t4_streams_run_resident(t4_seqset *const *sets, int n_sets, const t4_run_cfg
                             t4_workload *w, const int64_t *desc_off, void *cuda_stream);
 /* Copy results of the last resident run back. */
 int t4_workload_results(t4_workload *w, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
+
+/* First device-side error among the streams (0 = none); details in t4_last_error(). */
+int t4_streams_error(t4_seqset *const *sets, int n_sets);
+/* Test hook: number of postings in the k-mer index and an order-independent checksum of them. */
+int64_t t4_seqset_index_checksum(t4_seqset *s, uint64_t *checksum);
 
 /* Per-launch device counters of the last run (summed over streams):
  * [0] reads processed, [1] AddRead executed, [2] k-mer lookups executed, [3] postings read (sum c_j),

@@ -1,0 +1,165 @@
+"""Parity checks shared by the emulation (CPU, tests/emu) and GPU test modules.  `lib` is an api.Lib."""
+import gzip
+import os
+
+import numpy as np
+
+from trust4_b200 import api, synth
+import tracereplay as tr
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold_trace(name):
+    return tr.load_trace(os.path.join(GOLD, name + ".trace.gz"))
+
+
+def gold_raw(name):
+    return gzip.open(os.path.join(GOLD, name + "_raw.out.gz")).read()
+
+
+def check_trace_replay(lib, name):
+    """Every SeqSet call of a real trust4 run, one C-ABI call each: return values, strand outputs and the
+    final Output text must equal what the reference binary produced."""
+    lib.check(lib.reset())
+    s, bad = tr.replay(gold_trace(name), lambda k: api.SeqSet(k, lib))
+    assert not bad, bad[:1]
+    assert s.output() == gold_raw(name)
+
+
+def small_workload(seed, nclones=25, npairs=400, L=150):
+    cl = synth.make_clones(nclones, seed)
+    rd = synth.sample_pairs(cl, npairs, L, seed)
+    return synth.build_workload(cl, rd)
+
+
+def check_batch_vs_ref(lib, ref, seed, n_shards, nclones=25, npairs=400, cfg=None):
+    """t4_streams_run over read shards == the reference SeqSet driven by the restated loop, per shard."""
+    lib.check(lib.reset())
+    w = small_workload(seed, nclones, npairs)
+    cfg = cfg if cfg is not None else synth.run_cfg()
+    off, descs = synth.shard_workload(w, n_shards)
+    k = 9
+    sets = api.SeqSet.create_many(n_shards, k, lib)
+    ret, strands, resc = api.streams_run(sets, cfg, descs, off, w.pool, w.names, lib)
+    for j in range(n_shards):
+        lo, hi = int(off[j]), int(off[j + 1])
+        r = ref.RefSeqSet(k)
+        _, rret, rstr, rresc = r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)
+        assert (rret == ret[lo:hi]).all(), ("ret", j, np.flatnonzero(rret != ret[lo:hi])[:5])
+        assert (rstr == strands[lo:hi]).all(), ("strand", j)
+        assert (rresc == resc[lo:hi]).all(), ("rescue", j)
+        assert r.output() == sets[j].output(), ("contigs", j)
+        assert r.index_checksum() == sets[j].index_checksum(), ("index", j)
+        assert r.size() == sets[j].size()
+    return int((ret >= 0).sum())
+
+
+def check_stage_parity(lib, ref, name="synth2k", every=97, max_checks=60):
+    """k-mer hits (after SortHits) and scored overlaps of individual reads against a frozen snapshot:
+    replay the golden trace on both sides and compare the stage outputs at sampled AddRead calls."""
+    lib.check(lib.reset())
+    ops = gold_trace(name)
+    g = None
+    r = None
+    checks = 0
+    for i, t in enumerate(ops):
+        if t[0] == "A" and i % every == 0 and checks < max_checks:
+            read, sin = t[1], int(t[3])
+            hr = canon_hits(r.get_hits(read, sin))
+            hg = g.get_hits(read, sin)
+            assert hr.shape == hg.shape and (hr == hg).all(), ("hits", i)
+            n1, o1, s1 = r.get_overlaps(read, sin)
+            n2, o2, s2 = g.get_overlaps(read, sin)
+            assert n1 == n2, ("overlap count", i, n1, n2)
+            if n1 > 0:
+                assert (o1 == o2).all(), ("overlaps", i)
+                assert (s1 == s2).all(), ("similarity", i)   # IEEE doubles, bit-equal
+            assert r.index_checksum() == g.index_checksum(), ("index", i)
+            checks += 1
+        if t[0] == "C":
+            g = api.SeqSet(int(t[1]), lib)
+            r = ref.RefSeqSet(int(t[1]))
+        elif t[0] == "O":
+            break
+        else:
+            tr.replay([t], lambda k: None) if False else None
+            _apply(t, r)
+            _apply(t, g)
+    assert checks > 5
+
+
+def canon_hits(h):
+    """The reference's SortHits (SeqSet.hpp:1306) orders hits by (strand, seqIdx, readOffset) and leaves hits of
+    one k-mer on one contig in postings (insertion) order, which nothing downstream observes
+    (GetOverlapsFromHits re-sorts every group by diagonal).  Compare in the canonical order
+    (strand, seqIdx, readOffset, seqOffset) the C ABI documents."""
+    if len(h) == 0:
+        return h
+    order = np.lexsort((h[:, 1], h[:, 2], h[:, 0], h[:, 3]))
+    return h[order]
+
+
+def _apply(t, s):
+    c = t[0]
+    if c == "A":
+        s.add_read(t[1], "" if t[2] == "." else t[2], int(t[3]), int(t[4]), int(t[5]), int(t[6]), float(t[7]))
+    elif c == "R":
+        s.repeat_add_read(t[1])
+    elif c == "N":
+        s.input_novel_read(t[1], t[2], int(t[3]), int(t[4]))
+    elif c == "U":
+        s.update_all_consensus()
+    elif c == "K":
+        s.change_kmer_length(int(t[1]))
+    elif c == "H":
+        s.set_hit_len_required(int(t[1]))
+
+
+def dp_cases(seed, n=300):
+    """Random GlobalAlignment_PosWeight problems: equal and unequal lengths, clean / noisy / indel inputs."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        lent = int(rng.integers(0, 70))
+        kind = rng.integers(0, 5)
+        t = rng.integers(0, 4, size=lent)
+        p = list(t)
+        if kind == 0:
+            pass
+        elif kind == 1:                      # substitutions
+            for _ in range(int(rng.integers(1, 6))):
+                if p:
+                    p[int(rng.integers(len(p)))] = int(rng.integers(4))
+        elif kind == 2:                      # an indel
+            if len(p) > 3:
+                x = int(rng.integers(1, len(p) - 1))
+                if rng.random() < 0.5:
+                    del p[x]
+                else:
+                    p.insert(x, int(rng.integers(4)))
+        elif kind == 3:                      # unrelated, maybe other length
+            p = list(rng.integers(0, 4, size=max(0, lent + int(rng.integers(-4, 5)))))
+        else:                                # indel + substitutions, N's
+            if len(p) > 6:
+                x = int(rng.integers(2, len(p) - 2))
+                del p[x:x + int(rng.integers(1, 3))]
+                p[int(rng.integers(len(p)))] = 4
+        tw = np.zeros((lent, 4), dtype=np.int32)
+        for j in range(lent):
+            tw[j, t[j]] = int(rng.integers(1, 30))
+            if rng.random() < 0.3:
+                tw[j, int(rng.integers(4))] += int(rng.integers(0, 12))
+            if rng.random() < 0.03:
+                tw[j] = 0
+        ps = "".join("ACGTN"[c] for c in p)
+        out.append((tw, ps))
+    return out
+
+
+def check_dp(lib, ref, seed=5):
+    cases = dp_cases(seed)
+    got = api.dp_pos_weight_batch(cases, lib)
+    for (tw, p), (sc, ed) in zip(cases, got):
+        rs, re_ = ref.dp_pos_weight(tw, p)
+        assert (sc, ed) == (rs, re_), (tw.tolist(), p, sc, rs, ed, re_)

@@ -1,0 +1,24 @@
+"""CPU checks of the engine's bit-exact logic through the TEST-ONLY emulation build (tests/emu): the same
+t4_engine.h compiled by g++ with one emulated thread per stream.  The product path is exercised by
+test_gpu_parity.py on the B200; this module only guards the logic while developing without a GPU."""
+import pytest
+
+import parity_cases as pc
+
+
+@pytest.mark.parametrize("name", ["example", "synth2k"])
+def test_emu_trace_replay(emu_lib, name):
+    pc.check_trace_replay(emu_lib, name)
+
+
+@pytest.mark.parametrize("seed,shards", [(1, 1), (2, 3), (3, 8)])
+def test_emu_batch_vs_reference(emu_lib, ref, seed, shards):
+    assert pc.check_batch_vs_ref(emu_lib, ref, seed, shards) > 100
+
+
+def test_emu_stage_parity(emu_lib, ref):
+    pc.check_stage_parity(emu_lib, ref, "synth2k", every=131, max_checks=25)
+
+
+def test_emu_dp(emu_lib, ref):
+    pc.check_dp(emu_lib, ref)

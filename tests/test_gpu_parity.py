@@ -1,0 +1,70 @@
+"""Parity tests proper: the CUDA engine through the C ABI (libtrust4_b200.so) against the oracle --
+the reference's own classes compiled into oracle/_ref/libt4ref.so (travels to the GPU box prebuilt) and the
+golden call traces / outputs of the stock trust4 binary in tests/golden/."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from trust4_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["example", "synth2k", "synth6k"])
+def test_gpu_trace_replay(gpu_lib, name):
+    """BASELINE.json configs[0] (shipped example) and two synthetic sets: every AddRead / RepeatAddRead /
+    InputNovelRead / UpdateAllConsensus call of the real stage-1 run, bit-exact returns and _raw.out."""
+    pc.check_trace_replay(gpu_lib, name)
+
+
+@pytest.mark.parametrize("seed,shards", [(1, 1), (2, 3), (3, 8), (4, 64)])
+def test_gpu_batch_vs_reference(gpu_lib, ref, seed, shards):
+    assert pc.check_batch_vs_ref(gpu_lib, ref, seed, shards, nclones=40, npairs=1500) > 100
+
+
+def test_gpu_batch_larger_single_stream(gpu_lib, ref):
+    """One stream, enough contigs for the periodic UpdateAllConsensus (every 10000 assembled reads)."""
+    assert pc.check_batch_vs_ref(gpu_lib, ref, 9, 1, nclones=300, npairs=6000) > 10000
+
+
+def test_gpu_stage_parity(gpu_lib, ref):
+    """k-mer hits, chains -> scored overlaps (similarity doubles bit-equal), index multiset."""
+    pc.check_stage_parity(gpu_lib, ref, "synth2k", every=37, max_checks=80)
+
+
+def test_gpu_dp(gpu_lib, ref):
+    for seed in (5, 6, 7):
+        pc.check_dp(gpu_lib, ref, seed)
+
+
+def test_gpu_change_kmer_length(gpu_lib, ref):
+    """ChangeKmerLength (slot compaction + full re-index) in the middle of a stream."""
+    gpu_lib.check(gpu_lib.reset())
+    w = pc.small_workload(21, 60, 1500)
+    cfg = synth.run_cfg(change_k_threshold=20)     # force k: 9 -> 11 -> 13 early
+    g = api.SeqSet(9, gpu_lib)
+    r = ref.RefSeqSet(9)
+    _, gret, gstr, gres = g.run_descs(cfg, w.descs, w.pool, w.names)
+    _, rret, rstr, rres = r.run_descs(cfg, w.descs, w.pool, w.names)
+    assert g.kmer_length() == r.kmer_length() and g.kmer_length() > 9
+    assert (gret == rret).all() and (gstr == rstr).all() and (gres == rres).all()
+    assert g.output() == r.output()
+    assert g.index_checksum() == r.index_checksum()
+
+
+def test_gpu_empty_and_short_inputs(gpu_lib, ref):
+    gpu_lib.check(gpu_lib.reset())
+    g = api.SeqSet(9, gpu_lib)
+    r = ref.RefSeqSet(9)
+    assert g.output() == r.output() == b""
+    for read in ("ACGT", "ACGTACGTA", "A" * 60, "ACGTNACGTACGTTTGACCANNACGATCGATCGATTTACGACGGGATCTAGCAGGACTTT"):
+        assert g.add_read(read, "", 0, -1, 1, 0, 0.9) == r.add_read(read, "", 0, -1, 1, 0, 0.9)
+        assert g.repeat_add_read(read) == r.repeat_add_read(read)
+        assert g.input_novel_read("IGHV1-2*01", read, -1, -1) == r.input_novel_read("IGHV1-2*01", read, -1, -1)
+        assert g.add_read(read, "IGHV", 0, -1, 1, 0, 0.9) == r.add_read(read, "IGHV", 0, -1, 1, 0, 0.9)
+        assert g.repeat_add_read(read) == r.repeat_add_read(read)
+    assert g.output() == r.output()
+    assert g.index_checksum() == r.index_checksum()
+    # zero-length batch
+    e = synth.READ_DESC
+    assert g.run_descs(synth.run_cfg(), np.zeros(0, dtype=e), np.zeros(16, dtype=np.uint8), [])[0] == 0

@@ -1,0 +1,284 @@
+"""ctypes mirror of include/trust4_b200.h (host side, Python).
+
+`SeqSet` mirrors the reference class of the same name for the stage-1 path
+(SeqSet.hpp: AddRead :3426, RepeatAddRead :4477, InputNovelRead :3028,
+UpdateAllConsensus :4525, ChangeKmerLength :4624, Output :10939) with the same
+argument meaning and return codes; everything executes on the GPU through
+libtrust4_b200.so.  There is no CPU fallback: loading fails loudly when the
+extension is missing, and every call fails with T4_E_NODEVICE without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrust4_b200.so")
+
+T4_E_BASE = -16
+T4_E_CUDA, T4_E_NOMEM, T4_E_INVAL, T4_E_UNSUPPORTED, T4_E_NODEVICE, T4_E_INTERNAL = -17, -18, -19, -20, -21, -22
+N_COUNTERS = 16
+
+EXPORTS = [
+    "init", "shutdown", "last_error", "version", "arena_stats", "reset",
+    "seqset_create", "seqsets_create", "seqset_destroy", "seqset_set_hit_len_required",
+    "seqset_set_novel_seq_similarity", "seqset_set_consider_barcode_in_hash", "seqset_set_is_long",
+    "seqset_size", "seqset_kmer_length", "seqset_add_read", "seqset_repeat_add_read",
+    "seqset_input_novel_read", "seqset_update_all_consensus", "seqset_change_kmer_length",
+    "seqset_output", "seqset_output_mem", "free", "seqset_get_contig", "has_motif",
+    "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch",
+    "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
+    "streams_run_resident", "workload_results", "last_counters", "probe_resident", "streams_error",
+    "seqset_index_checksum",
+]
+
+
+class T4Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("trust4_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Lib:
+    """One loaded C-ABI library.  prefix is 't4_' for the product and 't4emu_' for the test emulation."""
+
+    def __init__(self, path=LIB_PATH, prefix="t4_"):
+        if not os.path.exists(path):
+            raise ImportError(
+                "%s not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "trust4_b200 has no CPU fallback." % path)
+        self.path = path
+        self.prefix = prefix
+        self.dll = C.CDLL(path)
+        f = self._f
+        vp, ci, cd, cs = C.c_void_p, C.c_int, C.c_double, C.c_char_p
+        f("init", ci, [ci, C.c_size_t])
+        f("shutdown", ci, [])
+        f("reset", ci, [])
+        f("last_error", cs, [])
+        f("version", cs, [])
+        f("arena_stats", ci, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)])
+        f("seqset_create", vp, [ci])
+        f("seqsets_create", ci, [ci, ci, C.POINTER(vp)])
+        f("seqset_destroy", None, [vp])
+        f("seqset_set_hit_len_required", ci, [vp, ci])
+        f("seqset_set_novel_seq_similarity", ci, [vp, cd])
+        f("seqset_set_consider_barcode_in_hash", ci, [vp, ci])
+        f("seqset_set_is_long", ci, [vp, ci])
+        f("seqset_size", ci, [vp])
+        f("seqset_kmer_length", ci, [vp])
+        f("seqset_add_read", ci, [vp, cs, cs, C.POINTER(ci), ci, ci, ci, cd])
+        f("seqset_repeat_add_read", ci, [vp, cs])
+        f("seqset_input_novel_read", ci, [vp, cs, cs, ci, ci])
+        f("seqset_update_all_consensus", ci, [vp])
+        f("seqset_change_kmer_length", ci, [vp, ci])
+        f("seqset_output_mem", ci, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)])
+        f("free", None, [vp])
+        f("seqset_get_contig", ci, [vp, ci, cs, ci, vp, cs, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)])
+        f("has_motif", ci, [cs, ci])
+        f("reverse_complement_in_place", None, [cs, ci])
+        f("seqset_get_hits", ci, [vp, cs, ci, ci, ci, vp, ci])
+        f("seqset_get_overlaps", ci, [vp, cs, ci, ci, ci, vp, vp, ci])
+        f("dp_pos_weight_batch", ci, [ci, vp, vp, vp, vp, vp, vp, vp])
+        f("seqset_add_reads_batch", ci, [vp, vp, vp, ci, vp, C.c_size_t, C.POINTER(cs), ci, vp, vp, vp])
+        f("streams_run", ci, [C.POINTER(vp), ci, vp, vp, vp, vp, C.c_size_t, C.POINTER(cs), ci, vp, vp, vp])
+        f("workload_upload", vp, [vp, C.c_int64, vp, C.c_size_t, C.POINTER(cs), ci])
+        f("workload_free", None, [vp])
+        f("streams_run_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, vp])
+        f("workload_results", ci, [vp, vp, vp, vp])
+        f("last_counters", ci, [vp])
+        f("probe_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+        f("streams_error", ci, [C.POINTER(vp), ci])
+        f("seqset_index_checksum", C.c_int64, [vp, C.POINTER(C.c_uint64)])
+
+    def _f(self, name, restype, argtypes):
+        fn = getattr(self.dll, self.prefix + name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+        setattr(self, name, fn)
+
+    def err(self):
+        return (self.last_error() or b"").decode()
+
+    def check(self, r):
+        if r < T4_E_BASE:
+            raise T4Error(r, self.err())
+        return r
+
+
+_default = None
+
+
+def default_lib() -> Lib:
+    global _default
+    if _default is None:
+        _default = Lib()
+    return _default
+
+
+def _names_array(names):
+    arr = (C.c_char_p * max(1, len(names)))(*[n if isinstance(n, bytes) else n.encode() for n in names])
+    return arr
+
+
+class SeqSet:
+    """GPU-resident novel-contig set; method names follow the reference's SeqSet."""
+
+    def __init__(self, k=9, lib: Lib | None = None, handle=None):
+        self.lib = lib or default_lib()
+        if handle is None:
+            handle = self.lib.seqset_create(k)
+            if not handle:
+                raise T4Error(T4_E_CUDA, self.lib.err())
+        self.h = C.c_void_p(handle)
+
+    @classmethod
+    def create_many(cls, n, k=9, lib: Lib | None = None):
+        lib = lib or default_lib()
+        arr = (C.c_void_p * n)()
+        lib.check(lib.seqsets_create(n, k, arr))
+        return [cls(k, lib, arr[i]) for i in range(n)]
+
+    def close(self):
+        if self.h:
+            self.lib.seqset_destroy(self.h)
+            self.h = None
+
+    def set_hit_len_required(self, v):
+        return self.lib.check(self.lib.seqset_set_hit_len_required(self.h, v))
+
+    def set_novel_seq_similarity(self, v):
+        return self.lib.check(self.lib.seqset_set_novel_seq_similarity(self.h, v))
+
+    def set_consider_barcode_in_hash(self, on):
+        return self.lib.check(self.lib.seqset_set_consider_barcode_in_hash(self.h, int(on)))
+
+    def set_is_long(self, on):
+        return self.lib.check(self.lib.seqset_set_is_long(self.h, int(on)))
+
+    def size(self):
+        return self.lib.check(self.lib.seqset_size(self.h))
+
+    def kmer_length(self):
+        return self.lib.check(self.lib.seqset_kmer_length(self.h))
+
+    def add_read(self, read, name, strand, barcode, min_kmer_count, repetitive, thr):
+        s = C.c_int(strand)
+        r = self.lib.seqset_add_read(self.h, read.encode(), name.encode(), C.byref(s), barcode, min_kmer_count, int(repetitive), thr)
+        self.lib.check(r)
+        return r, s.value
+
+    def repeat_add_read(self, read):
+        return self.lib.check(self.lib.seqset_repeat_add_read(self.h, read.encode()))
+
+    def input_novel_read(self, name, read, strand, barcode):
+        return self.lib.check(self.lib.seqset_input_novel_read(self.h, name.encode(), read.encode(), strand, barcode))
+
+    def update_all_consensus(self):
+        self.lib.check(self.lib.seqset_update_all_consensus(self.h))
+
+    def change_kmer_length(self, k):
+        self.lib.check(self.lib.seqset_change_kmer_length(self.h, k))
+
+    def output(self) -> bytes:
+        buf = C.c_void_p()
+        n = C.c_size_t()
+        self.lib.check(self.lib.seqset_output_mem(self.h, C.byref(buf), C.byref(n)))
+        s = C.string_at(buf, n.value)
+        self.lib.free(buf)
+        return s
+
+    def get_hits(self, read, strand=0, barcode=-1, allow_total_skip=False, cap=1 << 20):
+        out = np.zeros((cap, 5), dtype=np.int32)
+        n = self.lib.check(self.lib.seqset_get_hits(self.h, read.encode(), strand, barcode, int(allow_total_skip), out.ctypes.data, cap))
+        assert n <= cap
+        return out[:n]
+
+    def get_overlaps(self, read, strand=0, barcode=-1, skip_repeats=False, cap=1 << 14):
+        out = np.zeros((cap, 8), dtype=np.int32)
+        sim = np.zeros(cap, dtype=np.float64)
+        n = self.lib.check(self.lib.seqset_get_overlaps(self.h, read.encode(), strand, barcode, int(skip_repeats), out.ctypes.data, sim.ctypes.data, cap))
+        if n < 0:
+            return n, None, None
+        return n, out[:n], sim[:n]
+
+    def index_checksum(self):
+        cs = C.c_uint64()
+        n = self.lib.seqset_index_checksum(self.h, C.byref(cs))
+        self.lib.check(int(n))
+        return int(n), cs.value
+
+    def get_contig(self, slot):
+        ln = self.lib.seqset_get_contig(self.h, slot, None, 0, None, None, 0, None, None, None, None)
+        if ln < 0:
+            return None
+        cons = C.create_string_buffer(ln + 1)
+        pw = np.zeros((ln, 4), dtype=np.int32)
+        name = C.create_string_buffer(4096)
+        bc, nr, ml, mr = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.seqset_get_contig(self.h, slot, cons, ln + 1, pw.ctypes.data, name, 4096, C.byref(bc), C.byref(nr), C.byref(ml), C.byref(mr))
+        return dict(consensus=cons.value.decode(), pos_weight=pw, name=name.value.decode(), barcode=bc.value,
+                    num_read=nr.value, min_left=ml.value, min_right=mr.value)
+
+    def run_descs(self, cfg, descs, pool, names):
+        """t4_seqset_add_reads_batch: the reference's AddRead loop over read descriptors."""
+        n = len(descs)
+        ret = np.zeros(n, dtype=np.int32)
+        strands = np.zeros(n, dtype=np.int8)
+        resc = np.zeros(n, dtype=np.int32)
+        descs = np.ascontiguousarray(descs)
+        pool = np.ascontiguousarray(pool)
+        r = self.lib.seqset_add_reads_batch(self.h, cfg.ctypes.data, descs.ctypes.data, n, pool.ctypes.data, pool.nbytes,
+                                            _names_array(names), len(names), ret.ctypes.data, strands.ctypes.data, resc.ctypes.data)
+        self.lib.check(r)
+        return int((ret >= 0).sum()), ret, strands, resc
+
+
+def streams_run(sets, cfg, descs, desc_off, pool, names, lib: Lib | None = None):
+    """t4_streams_run: one CTA per seqset, host buffers in and out."""
+    lib = lib or sets[0].lib
+    n = len(descs)
+    ret = np.zeros(n, dtype=np.int32)
+    strands = np.zeros(n, dtype=np.int8)
+    resc = np.zeros(n, dtype=np.int32)
+    descs = np.ascontiguousarray(descs)
+    pool = np.ascontiguousarray(pool)
+    desc_off = np.ascontiguousarray(desc_off, dtype=np.int64)
+    hs = (C.c_void_p * len(sets))(*[s.h for s in sets])
+    r = lib.streams_run(hs, len(sets), cfg.ctypes.data, descs.ctypes.data, desc_off.ctypes.data, pool.ctypes.data, pool.nbytes,
+                        _names_array(names), len(names), ret.ctypes.data, strands.ctypes.data, resc.ctypes.data)
+    lib.check(r)
+    return ret, strands, resc
+
+
+def dp_pos_weight_batch(problems, lib: Lib | None = None):
+    """problems: list of (int32[lent,4], str).  Returns [(score, [edit ops])]."""
+    lib = lib or default_lib()
+    n = len(problems)
+    t_off = np.zeros(n + 1, dtype=np.int64)
+    p_off = np.zeros(n + 1, dtype=np.int64)
+    a_off = np.zeros(n + 1, dtype=np.int64)
+    for i, (tw, p) in enumerate(problems):
+        t_off[i + 1] = t_off[i] + len(tw)
+        p_off[i + 1] = p_off[i] + len(p)
+        a_off[i + 1] = a_off[i] + len(tw) + len(p) + 2
+    tw_all = np.zeros((max(1, t_off[n]), 4), dtype=np.int32)
+    for i, (tw, p) in enumerate(problems):
+        if len(tw):
+            tw_all[t_off[i]:t_off[i + 1]] = tw
+    p_all = np.frombuffer(("".join(p for _, p in problems) + "\0").encode(), dtype=np.uint8).copy()
+    align = np.zeros(a_off[n] + 16, dtype=np.int8)
+    score = np.zeros(n, dtype=np.int32)
+    lib.check(lib.dp_pos_weight_batch(n, tw_all.ctypes.data, t_off.ctypes.data, p_all.ctypes.data, p_off.ctypes.data,
+                                      align.ctypes.data, a_off.ctypes.data, score.ctypes.data))
+    out = []
+    for i in range(n):
+        e = []
+        for v in align[a_off[i]:a_off[i + 1]]:
+            if v == -1:
+                break
+            e.append(int(v))
+        out.append((int(score[i]), e))
+    return out

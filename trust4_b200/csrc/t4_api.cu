@@ -1,0 +1,1288 @@
+// C ABI of include/trust4_b200.h over the stream engine (t4_engine.h).
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a -> libtrust4_b200.so.  The hot path runs
+// only on the GPU; every entry point fails with T4_E_NODEVICE when no device is present.
+// Test-only emulation build (tests/emu, g++ -x c++ -DT4_EMU -DT4_PREFIX=t4emu_): the same host logic with
+// the "device" being host memory and one emulated thread per stream; it exports t4emu_* symbols only.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+#include <vector>
+#include <string>
+#include <mutex>
+
+#include "t4_engine.h"
+
+#if T4_CUDA
+#include <cuda_runtime.h>
+#endif
+
+#ifdef T4_EMU
+#define T4_CAT2( a, b ) a##b
+#define T4_CAT( a, b ) T4_CAT2( a, b )
+#define T4_API( name ) T4_CAT( t4emu_, name )
+#else
+#define T4_API( name ) t4_##name
+#endif
+
+// ---------------------------------------------------------------------------
+// backend
+// ---------------------------------------------------------------------------
+static std::string g_err ;
+static void set_err( const std::string &s ) { g_err = s ; }
+
+#if T4_CUDA
+#define CK( call )                                                                 \
+	do                                                                             \
+	{                                                                              \
+		cudaError_t e_ = ( call ) ;                                                \
+		if ( e_ != cudaSuccess )                                                   \
+		{                                                                          \
+			set_err( std::string( #call ) + ": " + cudaGetErrorString( e_ ) ) ;    \
+			return T4_E_CUDA ;                                                     \
+		}                                                                          \
+	} while ( 0 )
+
+__global__ void t4_stream_kernel( char *A, T4Op *ops, const int *gapTable )
+{
+	__shared__ T4Smem sm ;
+	T4Op *op = ops + blockIdx.x ;
+	T4Ctx cx ;
+	cx.A = A ;
+	cx.g = (T4Global *)A ;
+	cx.st = (T4Stream *)( A + op->streamOff ) ;
+	cx.sm = &sm ;
+	cx.tid = threadIdx.x ;
+	cx.nt = blockDim.x ;
+	c_run_op( cx, op, gapTable ) ;
+}
+
+__global__ void t4_init_kernel( char *A, u64 base, T4InitParams ip )
+{
+	__shared__ T4Smem sm ;
+	T4Ctx cx ;
+	cx.A = A ;
+	cx.g = (T4Global *)A ;
+	cx.st = 0 ;
+	cx.sm = &sm ;
+	cx.tid = threadIdx.x ;
+	cx.nt = blockDim.x ;
+	c_init_stream( cx, base + (u64)blockIdx.x * ip.footprint, ip ) ;
+}
+
+// copy contig payloads into one contiguous buffer: per contig [consensus len][posWeight 16*len][name nameLen]
+__global__ void t4_gather_kernel( char *A, const T4Contig *ct, const u64 *outOff, char *out, int n )
+{
+	int c = blockIdx.x ;
+	if ( c >= n || ct[c].consOff == 0 )
+		return ;
+	const T4Contig &k = ct[c] ;
+	char *o = out + outOff[c] ;
+	const char *cons = A + k.consOff + k.lead ;
+	const char *pw = A + k.pwOff + 16ull * k.lead ;
+	const char *nm = A + k.nameOff ;
+	for ( int i = threadIdx.x ; i < k.len ; i += blockDim.x )
+		o[i] = cons[i] ;
+	for ( int i = threadIdx.x ; i < 16 * k.len ; i += blockDim.x )
+		o[k.len + i] = pw[i] ;
+	for ( int i = threadIdx.x ; i < k.nameLen ; i += blockDim.x )
+		o[17 * k.len + i] = nm[i] ;
+}
+
+// AlignAlgo::GlobalAlignment_PosWeight for n independent problems, one thread each.
+__global__ void t4_dp_kernel( int n, const int *tw, const i64 *tOff, const char *p, const i64 *pOff, signed char *align,
+	const i64 *alignOff, int *score, char *scratch, const i64 *scratchOff )
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x ;
+	if ( i >= n )
+		return ;
+	int lent = (int)( tOff[i + 1] - tOff[i] ) ;
+	int lenp = (int)( pOff[i + 1] - pOff[i] ) ;
+	int d = lent > lenp ? lent - lenp : lenp - lent ;
+	int W = 2 * T4_DP_BAND + 3 + d ;
+	char *s = scratch + scratchOff[i] ;
+	score[i] = t4_dp_posweight( tw + 4 * tOff[i], lent, p + pOff[i], lenp, align + alignOff[i], (int *)s,
+		(unsigned char *)( s + 8 * W ), 0 ) ;
+}
+#else
+#define CK( call ) do { } while ( 0 )
+#endif
+
+struct Engine
+{
+	bool up ;
+	int device ;
+	char *A ;          // arena base (device or, in the emulation, host)
+	size_t cap ;
+	int nt ;
+	int *gapTable ;    // device int[40]
+	int hostGap[40] ;
+	// staging (device)
+	char *stage ;
+	size_t stageCap ;
+	Engine() : up( false ), device( 0 ), A( 0 ), cap( 0 ), nt( 32 ), gapTable( 0 ), stage( 0 ), stageCap( 0 ) {}
+} ;
+static Engine E ;
+static std::mutex g_mu ;
+
+static int dmalloc( void **p, size_t n )
+{
+#if T4_CUDA
+	CK( cudaMalloc( p, n ) ) ;
+#else
+	*p = malloc( n ) ;
+	if ( !*p ) return T4_E_NOMEM ;
+#endif
+	return 0 ;
+}
+static void dfree( void *p )
+{
+#if T4_CUDA
+	cudaFree( p ) ;
+#else
+	free( p ) ;
+#endif
+}
+static int h2d( void *d, const void *h, size_t n )
+{
+	if ( n == 0 ) return 0 ;
+#if T4_CUDA
+	CK( cudaMemcpy( d, h, n, cudaMemcpyHostToDevice ) ) ;
+#else
+	memcpy( d, h, n ) ;
+#endif
+	return 0 ;
+}
+static int d2h( void *h, const void *d, size_t n )
+{
+	if ( n == 0 ) return 0 ;
+#if T4_CUDA
+	CK( cudaMemcpy( h, d, n, cudaMemcpyDeviceToHost ) ) ;
+#else
+	memcpy( h, d, n ) ;
+#endif
+	return 0 ;
+}
+static int dzero( void *d, size_t n )
+{
+#if T4_CUDA
+	CK( cudaMemset( d, 0, n ) ) ;
+#else
+	memset( d, 0, n ) ;
+#endif
+	return 0 ;
+}
+
+// SeqSet::ComputeNomatchGapLimit (SeqSet.hpp:2476-2482): host pow/log, like the reference
+static int nomatch_gap_limit( int kl )
+{
+	double readAccuracy = 0.8 ;
+	double kmerHitProb = pow( readAccuracy, kl ) ;
+	int ret = int( kl * ( log( 0.01 ) / log( 1 - kmerHitProb ) ) ) + 1 ;
+	return ret ;
+}
+
+static int launch_ops( T4Op *dOps, int n, void *stream )
+{
+#if T4_CUDA
+	t4_stream_kernel<<<n, E.nt, 0, (cudaStream_t)stream>>>( E.A, dOps, E.gapTable ) ;
+	CK( cudaGetLastError() ) ;
+#else
+	T4Smem *sm = new T4Smem ;
+	for ( int b = 0 ; b < n ; ++b )
+	{
+		T4Ctx cx ;
+		cx.A = E.A ;
+		cx.g = (T4Global *)E.A ;
+		cx.st = (T4Stream *)( E.A + dOps[b].streamOff ) ;
+		cx.sm = sm ;
+		cx.tid = 0 ;
+		cx.nt = 1 ;
+		c_run_op( cx, dOps + b, E.gapTable ) ;
+	}
+	delete sm ;
+#endif
+	return 0 ;
+}
+
+static int dsync()
+{
+#if T4_CUDA
+	CK( cudaDeviceSynchronize() ) ;
+#endif
+	return 0 ;
+}
+
+static int ensure_stage( size_t n )
+{
+	if ( n <= E.stageCap )
+		return 0 ;
+	if ( E.stage )
+		dfree( E.stage ) ;
+	size_t c = E.stageCap ? E.stageCap : ( 1 << 20 ) ;
+	while ( c < n )
+		c *= 2 ;
+	void *p = 0 ;
+	int r = dmalloc( &p, c ) ;
+	if ( r )
+	{
+		E.stage = 0 ;
+		E.stageCap = 0 ;
+		return r ;
+	}
+	E.stage = (char *)p ;
+	E.stageCap = c ;
+	return 0 ;
+}
+
+// host-side bump allocation (only between launches)
+static int arena_alloc( size_t bytes, u64 *off )
+{
+	T4Global g ;
+	int r = d2h( &g, E.A, sizeof( u64 ) * 2 ) ;
+	if ( r ) return r ;
+	bytes = ( bytes + 255 ) & ~(size_t)255 ;
+	u64 top = ( g.top + 255 ) & ~255ull ;
+	if ( top + bytes > g.cap )
+	{
+		set_err( "device arena exhausted" ) ;
+		return T4_E_NOMEM ;
+	}
+	*off = top ;
+	top += bytes ;
+	return h2d( E.A, &top, sizeof( u64 ) ) ;
+}
+
+struct t4_seqset
+{
+	u64 off ;
+	int k ;
+	bool alive ;
+	uint32_t gen ;
+} ;
+static uint32_t g_gen = 1 ;
+
+struct t4_workload
+{
+	char *buf ;            // one device allocation
+	size_t bytes ;
+	i64 nDescs ;
+	size_t poolBytes ;
+	int nNames ;
+	// device pointers into buf
+	t4_read_desc *descs ;
+	char *pool ;
+	T4Names *names ;
+	int32_t *ret ;
+	int8_t *strands ;
+	int32_t *rescue ;
+	int32_t *rescueList ;
+	int8_t *good ;
+	int32_t *info ;
+	T4Op *ops ;
+	int opCap ;
+} ;
+
+extern "C" {
+
+const char *T4_API( last_error )( void ) { return g_err.c_str() ; }
+const char *T4_API( version )( void )
+{
+#if T4_CUDA
+	return "trust4_b200 0.1.0 (sm_100a)" ;
+#else
+	return "trust4_b200 0.1.0 (TEST EMULATION - not a product build)" ;
+#endif
+}
+
+int T4_API( shutdown )( void )
+{
+	std::lock_guard<std::mutex> lk( g_mu ) ;
+	if ( !E.up )
+		return 0 ;
+	dsync() ;
+	dfree( E.A ) ;
+	if ( E.gapTable )
+#if T4_CUDA
+		dfree( E.gapTable ) ;
+#else
+		free( E.gapTable ) ;
+#endif
+	if ( E.stage )
+		dfree( E.stage ) ;
+	E = Engine() ;
+	++g_gen ;
+	return 0 ;
+}
+
+int T4_API( init )( int device, size_t arena_bytes )
+{
+	std::lock_guard<std::mutex> lk( g_mu ) ;
+	if ( E.up )
+		return 0 ;
+#if T4_CUDA
+	int nd = 0 ;
+	if ( cudaGetDeviceCount( &nd ) != cudaSuccess || nd == 0 )
+	{
+		set_err( "no CUDA device: trust4_b200 has no CPU fallback" ) ;
+		return T4_E_NODEVICE ;
+	}
+	if ( device < 0 )
+		CK( cudaGetDevice( &device ) ) ;
+	CK( cudaSetDevice( device ) ) ;
+	if ( arena_bytes == 0 )
+	{
+		size_t fr = 0, tot = 0 ;
+		CK( cudaMemGetInfo( &fr, &tot ) ) ;
+		arena_bytes = fr / 2 ;
+	}
+#else
+	if ( arena_bytes == 0 )
+		arena_bytes = 1ull << 30 ;
+#endif
+	const char *env = getenv( "T4_ARENA_MB" ) ;
+	if ( env )
+		arena_bytes = (size_t)atoll( env ) << 20 ;
+	env = getenv( "T4_NT" ) ;
+	if ( env )
+		E.nt = atoi( env ) ;
+	if ( E.nt < 1 || E.nt > T4_MAX_NT || ( E.nt & ( E.nt - 1 ) ) )
+	{
+		set_err( "T4_NT must be a power of two <= 128" ) ;
+		return T4_E_INVAL ;
+	}
+#if !T4_CUDA
+	E.nt = 1 ;
+#endif
+	void *p = 0 ;
+	int r = dmalloc( &p, arena_bytes ) ;
+	if ( r )
+		return r ;
+	E.A = (char *)p ;
+	E.cap = arena_bytes ;
+	E.device = device ;
+	T4Global g ;
+	memset( &g, 0, sizeof( g ) ) ;
+	g.top = ( sizeof( T4Global ) + 255 ) & ~255ull ;
+	g.cap = arena_bytes ;
+	r = h2d( E.A, &g, sizeof( g ) ) ;
+	if ( r )
+		return r ;
+	for ( int k = 0 ; k < 40 ; ++k )
+		E.hostGap[k] = ( k >= 2 && k <= 32 ) ? nomatch_gap_limit( k ) : 0 ;
+	r = dmalloc( &p, sizeof( E.hostGap ) ) ;
+	if ( r )
+		return r ;
+	E.gapTable = (int *)p ;
+	r = h2d( E.gapTable, E.hostGap, sizeof( E.hostGap ) ) ;
+	if ( r )
+		return r ;
+	E.up = true ;
+	return 0 ;
+}
+
+static int ensure_up()
+{
+	if ( E.up )
+		return 0 ;
+	return T4_API( init )( -1, 0 ) ;
+}
+
+// Release every seqset and workload-independent allocation of the arena (all t4_seqset handles die).
+int T4_API( reset )( void )
+{
+	if ( !E.up )
+		return 0 ;
+	int r = dsync() ;
+	if ( r ) return r ;
+	T4Global g ;
+	memset( &g, 0, sizeof( g ) ) ;
+	g.top = ( sizeof( T4Global ) + 255 ) & ~255ull ;
+	g.cap = E.cap ;
+	++g_gen ;
+	return h2d( E.A, &g, sizeof( g ) ) ;
+}
+
+int T4_API( arena_stats )( size_t *used, size_t *capacity )
+{
+	if ( !E.up )
+		return T4_E_INVAL ;
+	T4Global g ;
+	int r = d2h( &g, E.A, 16 ) ;
+	if ( r ) return r ;
+	if ( used ) *used = g.top ;
+	if ( capacity ) *capacity = g.cap ;
+	return 0 ;
+}
+
+int T4_API( last_counters )( uint64_t *c )
+{
+	if ( !E.up )
+		return T4_E_INVAL ;
+	T4Global g ;
+	int r = d2h( &g, E.A, sizeof( g ) ) ;
+	if ( r ) return r ;
+	memcpy( c, g.counters, sizeof( g.counters ) ) ;
+	return 0 ;
+}
+
+static int reset_counters()
+{
+	u64 z[T4_N_COUNTERS] ;
+	memset( z, 0, sizeof( z ) ) ;
+	return h2d( E.A + offsetof( T4Global, counters ), z, sizeof( z ) ) ;
+}
+
+// Create n seqsets in one go (one init launch).  handles[i] receives the new set.
+int T4_API( seqsets_create )( int n, int kmer_length, t4_seqset **handles )
+{
+	int r = ensure_up() ;
+	if ( r ) return r ;
+	if ( n <= 0 || kmer_length < 2 || kmer_length > 31 )
+	{
+		set_err( "bad k-mer length / count" ) ;
+		return T4_E_INVAL ;
+	}
+	T4InitParams ip ;
+	ip.kmerLength = kmer_length ;
+	ip.nomatchGapLimit = E.hostGap[kmer_length] ;
+	ip.nThreads = E.nt ;
+	ip.seqCap = 64 ;
+	ip.dirCap = 2048 ;
+	ip.hitCap = 2048 ;
+	ip.ovlCap = 64 ;
+	ip.footprint = 0 ;
+	u64 fp = ( t4_stream_footprint( ip ) + 255 ) & ~255ull ;
+	ip.footprint = (u32)fp ;
+	u64 base ;
+	r = arena_alloc( fp * n, &base ) ;
+	if ( r ) return r ;
+#if T4_CUDA
+	t4_init_kernel<<<n, 128>>>( E.A, base, ip ) ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaDeviceSynchronize() ) ;
+#else
+	T4Smem *sm = new T4Smem ;
+	for ( int b = 0 ; b < n ; ++b )
+	{
+		T4Ctx cx ;
+		cx.A = E.A ; cx.g = (T4Global *)E.A ; cx.st = 0 ; cx.sm = sm ; cx.tid = 0 ; cx.nt = 1 ;
+		c_init_stream( cx, base + (u64)b * fp, ip ) ;
+	}
+	delete sm ;
+#endif
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		t4_seqset *s = new t4_seqset ;
+		s->off = base + (u64)i * fp ;
+		s->k = kmer_length ;
+		s->alive = true ;
+		s->gen = g_gen ;
+		handles[i] = s ;
+	}
+	return 0 ;
+}
+
+t4_seqset *T4_API( seqset_create )( int kmer_length )
+{
+	t4_seqset *s = 0 ;
+	if ( T4_API( seqsets_create )( 1, kmer_length, &s ) )
+		return 0 ;
+	return s ;
+}
+
+void T4_API( seqset_destroy )( t4_seqset *s )
+{
+	// arena memory is reclaimed by t4_reset() / t4_shutdown() (bump allocator)
+	delete s ;
+}
+
+static int check( t4_seqset *s )
+{
+	if ( !s || !E.up || s->gen != g_gen )
+	{
+		set_err( "stale or null seqset handle" ) ;
+		return T4_E_INVAL ;
+	}
+	return 0 ;
+}
+
+static int get_stream( t4_seqset *s, T4Stream *st )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	return d2h( st, E.A + s->off, sizeof( T4Stream ) ) ;
+}
+
+static int put_field( t4_seqset *s, size_t fieldOff, const void *v, size_t n )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	return h2d( E.A + s->off + fieldOff, v, n ) ;
+}
+
+int T4_API( seqset_set_hit_len_required )( t4_seqset *s, int l ) { return put_field( s, offsetof( T4Stream, hitLenRequired ), &l, sizeof( int ) ) ; }
+int T4_API( seqset_set_novel_seq_similarity )( t4_seqset *s, double v ) { return put_field( s, offsetof( T4Stream, novelSeqSimilarity ), &v, sizeof( double ) ) ; }
+int T4_API( seqset_set_consider_barcode_in_hash )( t4_seqset *s, int on )
+{
+	int v = on ? 1 : 0 ;
+	return put_field( s, offsetof( T4Stream, considerBarcode ), &v, sizeof( int ) ) ;
+}
+int T4_API( seqset_set_is_long )( t4_seqset *s, int on )
+{
+	if ( on )
+	{
+		set_err( "isLongSeqSet (reads > 200 bp as the first read) is not supported" ) ;
+		return T4_E_UNSUPPORTED ;
+	}
+	return check( s ) ;
+}
+int T4_API( seqset_size )( t4_seqset *s )
+{
+	T4Stream st ;
+	int r = get_stream( s, &st ) ;
+	if ( r ) return r ;
+	return st.nSeqs ;
+}
+int T4_API( seqset_kmer_length )( t4_seqset *s )
+{
+	T4Stream st ;
+	int r = get_stream( s, &st ) ;
+	if ( r ) return r ;
+	return st.kmerLength ;
+}
+
+// run one op on one stream through the staging buffer.  extra: bytes copied in after the op record;
+// outBytes: bytes copied back from stage + outAt.
+static int run_single( T4Op &op, const void *extra, size_t extraBytes, size_t outAt, void *outHost, size_t outBytes, size_t totalStage )
+{
+	int r = ensure_stage( totalStage ) ;
+	if ( r ) return r ;
+	// patch relative pointers: callers fill read/name/out as offsets from the stage start
+	u64 b = (u64)(uintptr_t)E.stage ;
+	if ( op.read ) op.read += b ;
+	if ( op.name ) op.name += b ;
+	if ( op.out ) op.out += b ;
+	if ( op.out2 ) op.out2 += b ;
+	r = h2d( E.stage, &op, sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	if ( extraBytes )
+	{
+		r = h2d( E.stage + sizeof( T4Op ), extra, extraBytes ) ;
+		if ( r ) return r ;
+	}
+	r = launch_ops( (T4Op *)E.stage, 1, 0 ) ;
+	if ( r ) return r ;
+	r = dsync() ;
+	if ( r ) return r ;
+	r = d2h( &op, E.stage, sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	if ( outBytes )
+		r = d2h( outHost, E.stage + outAt, outBytes ) ;
+	if ( op.ret < T4_E_BASE )
+		set_err( "device-side error " + std::to_string( op.ret ) ) ;
+	return r ;
+}
+
+static int read_ok( const char *read, int *len )
+{
+	size_t n = strlen( read ) ;
+	if ( n > T4_DEV_MAX_READ )
+	{
+		set_err( "read longer than the device limit" ) ;
+		return T4_E_UNSUPPORTED ;
+	}
+	*len = (int)n ;
+	return 0 ;
+}
+
+int T4_API( seqset_add_read )( t4_seqset *s, const char *read, const char *gene_name, int *strand_inout, int barcode,
+	int min_kmer_count, int repetitive, double sim_threshold )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	int len ;
+	r = read_ok( read, &len ) ;
+	if ( r ) return r ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_ADD_READ ;
+	op.read = sizeof( T4Op ) ;
+	op.len = len ;
+	op.strand = *strand_inout ;
+	op.barcode = barcode ;
+	op.minKmerCount = min_kmer_count ;
+	op.repetitive = repetitive ;
+	op.thr = sim_threshold ;
+	strncpy( op.gene, gene_name ? gene_name : "", 7 ) ;
+	r = run_single( op, read, len + 1, 0, 0, 0, sizeof( T4Op ) + len + 16 ) ;
+	if ( r ) return r ;
+	*strand_inout = op.strandOut ;
+	return op.ret ;
+}
+
+int T4_API( seqset_repeat_add_read )( t4_seqset *s, const char *read )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	int len ;
+	r = read_ok( read, &len ) ;
+	if ( r ) return r ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_REPEAT ;
+	op.read = sizeof( T4Op ) ;
+	op.len = len ;
+	r = run_single( op, read, len + 1, 0, 0, 0, sizeof( T4Op ) + len + 16 ) ;
+	if ( r ) return r ;
+	return op.ret ;
+}
+
+int T4_API( seqset_input_novel_read )( t4_seqset *s, const char *id, const char *read, int strand, int barcode )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	int len ;
+	r = read_ok( read, &len ) ;
+	if ( r ) return r ;
+	int nl = (int)strlen( id ) ;
+	std::vector<char> extra( len + 1 + nl + 1 ) ;
+	memcpy( extra.data(), read, len + 1 ) ;
+	memcpy( extra.data() + len + 1, id, nl + 1 ) ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_INPUT_NOVEL ;
+	op.read = sizeof( T4Op ) ;
+	op.name = sizeof( T4Op ) + len + 1 ;
+	op.nameLen = nl ;
+	op.len = len ;
+	op.strand = strand ;
+	op.barcode = barcode ;
+	r = run_single( op, extra.data(), extra.size(), 0, 0, 0, sizeof( T4Op ) + extra.size() + 16 ) ;
+	if ( r ) return r ;
+	return op.ret ;
+}
+
+int T4_API( seqset_update_all_consensus )( t4_seqset *s )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_UPDATE_ALL ;
+	r = run_single( op, 0, 0, 0, 0, 0, sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	return op.ret < T4_E_BASE ? op.ret : 0 ;
+}
+
+int T4_API( seqset_change_kmer_length )( t4_seqset *s, int kl )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	if ( kl < 2 || kl > 31 )
+		return T4_E_INVAL ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_CHANGE_K ;
+	op.kl = kl ;
+	r = run_single( op, 0, 0, 0, 0, 0, sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	s->k = kl ;
+	return op.ret < T4_E_BASE ? op.ret : 0 ;
+}
+
+int T4_API( seqset_get_hits )( t4_seqset *s, const char *read, int strand, int barcode, int allow_total_skip, int32_t *hits, int cap )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	int len ;
+	r = read_ok( read, &len ) ;
+	if ( r ) return r ;
+	size_t outAt = ( sizeof( T4Op ) + len + 1 + 63 ) & ~(size_t)63 ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_GET_HITS ;
+	op.read = sizeof( T4Op ) ;
+	op.len = len ;
+	op.strand = strand ;
+	op.barcode = barcode ;
+	op.repetitive = allow_total_skip ;
+	op.out = outAt ;
+	op.outCap = cap ;
+	// two-step: the count first (cap may be too small), then the copy of min(count, cap)
+	r = run_single( op, read, len + 1, 0, 0, 0, outAt + (size_t)cap * 20 + 64 ) ;
+	if ( r ) return r ;
+	if ( op.ret > 0 )
+	{
+		int n = op.ret < cap ? op.ret : cap ;
+		r = d2h( hits, E.stage + outAt, (size_t)n * 20 ) ;
+		if ( r ) return r ;
+	}
+	return op.ret ;
+}
+
+int T4_API( seqset_get_overlaps )( t4_seqset *s, const char *read, int strand, int barcode, int skip_repeats, int32_t *overlaps,
+	double *similarity, int cap )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	int len ;
+	r = read_ok( read, &len ) ;
+	if ( r ) return r ;
+	size_t outAt = ( sizeof( T4Op ) + len + 1 + 63 ) & ~(size_t)63 ;
+	size_t out2At = outAt + (size_t)cap * 32 ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_GET_OVERLAPS ;
+	op.read = sizeof( T4Op ) ;
+	op.len = len ;
+	op.strand = strand ;
+	op.barcode = barcode ;
+	op.repetitive = skip_repeats ;
+	op.out = outAt ;
+	op.out2 = out2At ;
+	op.outCap = cap ;
+	r = run_single( op, read, len + 1, 0, 0, 0, out2At + (size_t)cap * 8 + 64 ) ;
+	if ( r ) return r ;
+	if ( op.ret > 0 )
+	{
+		int n = op.ret < cap ? op.ret : cap ;
+		r = d2h( overlaps, E.stage + outAt, (size_t)n * 32 ) ;
+		if ( r ) return r ;
+		r = d2h( similarity, E.stage + out2At, (size_t)n * 8 ) ;
+		if ( r ) return r ;
+	}
+	return op.ret ;
+}
+
+// ---- contigs back to the host -------------------------------------------------
+struct HostContigs
+{
+	T4Stream st ;
+	std::vector<T4Contig> ct ;
+	std::vector<u64> off ;
+	std::vector<char> data ;
+} ;
+
+static int fetch_contigs( t4_seqset *s, HostContigs &hc )
+{
+	int r = get_stream( s, &hc.st ) ;
+	if ( r ) return r ;
+	int n = hc.st.nSeqs ;
+	hc.ct.resize( n ) ;
+	hc.off.assign( n + 1, 0 ) ;
+	if ( n == 0 )
+		return 0 ;
+	r = d2h( hc.ct.data(), E.A + hc.st.seqsOff, (size_t)n * sizeof( T4Contig ) ) ;
+	if ( r ) return r ;
+	u64 tot = 0 ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		hc.off[i] = tot ;
+		if ( hc.ct[i].consOff )
+			tot += ( 17ull * hc.ct[i].len + hc.ct[i].nameLen + 15 ) & ~15ull ;
+	}
+	hc.off[n] = tot ;
+	hc.data.resize( tot ) ;
+	if ( tot == 0 )
+		return 0 ;
+#if T4_CUDA
+	size_t need = (size_t)n * sizeof( T4Contig ) + ( n + 1 ) * 8 + tot + 256 ;
+	r = ensure_stage( need ) ;
+	if ( r ) return r ;
+	char *dct = E.stage ;
+	char *doff = dct + ( ( (size_t)n * sizeof( T4Contig ) + 63 ) & ~(size_t)63 ) ;
+	char *dout = doff + ( ( ( n + 1 ) * 8 + 63 ) & ~(size_t)63 ) ;
+	r = ensure_stage( ( dout - E.stage ) + tot ) ;
+	if ( r ) return r ;
+	dct = E.stage ;
+	doff = dct + ( ( (size_t)n * sizeof( T4Contig ) + 63 ) & ~(size_t)63 ) ;
+	dout = doff + ( ( ( n + 1 ) * 8 + 63 ) & ~(size_t)63 ) ;
+	r = h2d( dct, hc.ct.data(), (size_t)n * sizeof( T4Contig ) ) ;
+	if ( r ) return r ;
+	r = h2d( doff, hc.off.data(), ( n + 1 ) * 8 ) ;
+	if ( r ) return r ;
+	t4_gather_kernel<<<n, 128>>>( E.A, (const T4Contig *)dct, (const u64 *)doff, dout, n ) ;
+	CK( cudaGetLastError() ) ;
+	r = d2h( hc.data.data(), dout, tot ) ;
+	if ( r ) return r ;
+#else
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		const T4Contig &k = hc.ct[i] ;
+		if ( !k.consOff )
+			continue ;
+		char *o = hc.data.data() + hc.off[i] ;
+		memcpy( o, E.A + k.consOff + k.lead, k.len ) ;
+		memcpy( o + k.len, E.A + k.pwOff + 16ull * k.lead, 16ull * k.len ) ;
+		memcpy( o + 17ull * k.len, E.A + k.nameOff, k.nameLen ) ;
+	}
+#endif
+	return 0 ;
+}
+
+// SeqSet::Output (SeqSet.hpp:10939-10994)
+static int output_to( t4_seqset *s, FILE *fp, const char *const *barcode_names, int n_barcode_names )
+{
+	HostContigs hc ;
+	int r = fetch_contigs( s, hc ) ;
+	if ( r ) return r ;
+	int n = hc.st.nSeqs ;
+	std::string line ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		const T4Contig &k = hc.ct[i] ;
+		if ( !k.consOff )
+			continue ;
+		const char *o = hc.data.data() + hc.off[i] ;
+		std::string cons( o, k.len ) ;
+		std::string name( o + 17ull * k.len, k.nameLen ) ;
+		const int32_t *pw = (const int32_t *)( o + k.len ) ;
+		// posWeight columns start at byte k.len: may be unaligned in the packed buffer -> copy
+		std::vector<int32_t> w( 4 * (size_t)k.len ) ;
+		memcpy( w.data(), (const void *)pw, 16ull * k.len ) ;
+		if ( barcode_names == NULL || k.barcode == -1 || k.barcode >= n_barcode_names )
+			fprintf( fp, ">assemble%d %s\n%s\n", i, name.c_str(), cons.c_str() ) ;
+		else
+			fprintf( fp, ">%s_%d %s\n%s\n", barcode_names[k.barcode], i, name.c_str(), cons.c_str() ) ;
+		for ( int c = 0 ; c < 4 ; ++c )
+		{
+			line.clear() ;
+			char buf[16] ;
+			for ( int j = 0 ; j < k.len ; ++j )
+			{
+				int m = snprintf( buf, sizeof( buf ), "%d ", w[4 * j + c] ) ;
+				line.append( buf, m ) ;
+			}
+			line.push_back( '\n' ) ;
+			fwrite( line.data(), 1, line.size(), fp ) ;
+		}
+	}
+	return 0 ;
+}
+
+int T4_API( seqset_output )( t4_seqset *s, FILE *fp, const char *const *barcode_names, int n ) { return output_to( s, fp, barcode_names, n ) ; }
+
+int T4_API( seqset_output_mem )( t4_seqset *s, char **buf, size_t *len )
+{
+	FILE *fp = open_memstream( buf, len ) ;
+	if ( !fp )
+		return T4_E_NOMEM ;
+	int r = output_to( s, fp, NULL, 0 ) ;
+	fclose( fp ) ;
+	return r ;
+}
+
+void T4_API( free )( void *p ) { free( p ) ; }
+
+int T4_API( seqset_get_contig )( t4_seqset *s, int slot, char *consensus, int consensus_cap, int32_t *pos_weight, char *name,
+	int name_cap, int *barcode, int *num_read, int *min_left, int *min_right )
+{
+	T4Stream st ;
+	int r = get_stream( s, &st ) ;
+	if ( r ) return r ;
+	if ( slot < 0 || slot >= st.nSeqs )
+		return -1 ;
+	T4Contig k ;
+	r = d2h( &k, E.A + st.seqsOff + (size_t)slot * sizeof( T4Contig ), sizeof( k ) ) ;
+	if ( r ) return r ;
+	if ( !k.consOff )
+		return -1 ;
+	if ( consensus && consensus_cap > k.len )
+	{
+		r = d2h( consensus, E.A + k.consOff + k.lead, k.len ) ;
+		if ( r ) return r ;
+		consensus[k.len] = '\0' ;
+	}
+	if ( pos_weight )
+	{
+		r = d2h( pos_weight, E.A + k.pwOff + 16ull * k.lead, 16ull * k.len ) ;
+		if ( r ) return r ;
+	}
+	if ( name && name_cap > 0 )
+	{
+		int m = k.nameLen < name_cap - 1 ? k.nameLen : name_cap - 1 ;
+		r = d2h( name, E.A + k.nameOff, m ) ;
+		if ( r ) return r ;
+		name[m] = '\0' ;
+	}
+	if ( barcode ) *barcode = k.barcode ;
+	if ( num_read ) *num_read = k.numRead ;
+	if ( min_left ) *min_left = k.minLeftExtAnchor ;
+	if ( min_right ) *min_right = k.minRightExtAnchor ;
+	return k.len ;
+}
+
+// Order-independent checksum + count of all postings (test hook, mirrors oracle t4ref_index_checksum)
+int64_t T4_API( seqset_index_checksum )( t4_seqset *s, uint64_t *checksum )
+{
+	T4Stream st ;
+	int r = get_stream( s, &st ) ;
+	if ( r ) return r ;
+	std::vector<T4Dir> dir( st.dirCap ) ;
+	r = d2h( dir.data(), E.A + st.dirOff, (size_t)st.dirCap * sizeof( T4Dir ) ) ;
+	if ( r ) return r ;
+	int64_t total = 0 ;
+	uint64_t sum = 0 ;
+	std::vector<u64> l ;
+	u64 saltMask = ( st.kmerLength < 32 ) ? ( ( 1ull << ( 2 * st.kmerLength ) ) - 1 ) : ~0ull ;
+	for ( u32 i = 0 ; i < st.dirCap ; ++i )
+	{
+		if ( dir[i].key == 0 || dir[i].cnt == 0 )
+			continue ;
+		l.resize( dir[i].cnt ) ;
+		r = d2h( l.data(), E.A + dir[i].listOff, (size_t)dir[i].cnt * 8 ) ;
+		if ( r ) return r ;
+		u64 code = ( dir[i].key - 1 ) & saltMask ;
+		for ( u32 j = 0 ; j < dir[i].cnt ; ++j )
+		{
+			uint64_t x = code * 0x9E3779B97F4A7C15ull ^ l[j] ;
+			x ^= x >> 31 ; x *= 0xBF58476D1CE4E5B9ull ; x ^= x >> 29 ;
+			sum += x ;
+		}
+		total += dir[i].cnt ;
+	}
+	*checksum = sum ;
+	return total ;
+}
+
+// ---- host utilities -----------------------------------------------------------
+// SeqSet::DnaToAa (SeqSet.hpp:638): standard code, '-' for codons with N
+static char dna_to_aa( char a, char b, char c )
+{
+	if ( a == 'N' || b == 'N' || c == 'N' )
+		return '-' ;
+	static const char *tab = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV_Y_YSSSS_CWCLFLF" ;
+	return tab[16 * t4_nuc( a ) + 4 * t4_nuc( b ) + t4_nuc( c )] ;
+}
+
+// SeqSet::HasMotif (SeqSet.hpp:5029): note that the reference translates `read` itself for either strand
+int T4_API( has_motif )( const char *read, int strand )
+{
+	if ( strand == 0 )
+		return 0 ;
+	int len = (int)strlen( read ) ;
+	std::vector<char> aa( len + 1 ) ;
+	int ret = 0 ;
+	for ( int k = 0 ; k <= 2 ; ++k )
+	{
+		int i, j ;
+		for ( i = k, j = 0 ; i + 2 < len ; i += 3, ++j )
+			aa[j] = dna_to_aa( read[i], read[i + 1], read[i + 2] ) ;
+		for ( i = 0 ; i + 2 < j ; ++i )
+			if ( aa[i] == 'Y' && aa[i + 1] == 'Y' && aa[i + 2] == 'C' )
+			{
+				ret |= 2 ;
+				break ;
+			}
+		for ( i = 0 ; i + 3 < j ; ++i )
+			if ( ( aa[i] == 'F' || aa[i] == 'W' ) && aa[i + 1] == 'G' && aa[i + 3] == 'G' )
+			{
+				ret |= 1 ;
+				break ;
+			}
+	}
+	return ret ;
+}
+
+// SeqSet::ReverseComplementInPlace (SeqSet.hpp:2629)
+void T4_API( reverse_complement_in_place )( char *seq, int len )
+{
+	int i, j ;
+	for ( i = 0, j = len - 1 ; i < j ; ++i, --j )
+	{
+		char tmp = seq[j] ;
+		seq[j] = ( seq[i] != 'N' ) ? t4_numToNuc( 3 - t4_nuc( seq[i] ) ) : 'N' ;
+		seq[i] = ( tmp != 'N' ) ? t4_numToNuc( 3 - t4_nuc( tmp ) ) : 'N' ;
+	}
+	if ( i == j )
+		seq[i] = ( seq[i] != 'N' ) ? t4_numToNuc( 3 - t4_nuc( seq[i] ) ) : 'N' ;
+}
+
+// ---- DP batch -------------------------------------------------------------------
+int T4_API( dp_pos_weight_batch )( int n, const int32_t *t_weights, const int64_t *t_off, const char *p, const int64_t *p_off,
+	int8_t *align_out, const int64_t *align_off, int32_t *score_out )
+{
+	int r = ensure_up() ;
+	if ( r ) return r ;
+	if ( n <= 0 )
+		return 0 ;
+	std::vector<i64> so( n + 1 ) ;
+	i64 tot = 0 ;
+	i64 alignTot = 0 ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		i64 lent = t_off[i + 1] - t_off[i], lenp = p_off[i + 1] - p_off[i] ;
+		i64 d = lent > lenp ? lent - lenp : lenp - lent ;
+		i64 W = 2 * T4_DP_BAND + 3 + d ;
+		so[i] = tot ;
+		tot += ( 8 * W + ( lenp + 1 ) * W + 15 ) & ~15ll ;
+		i64 e = align_off[i] + lent + lenp + 2 ;
+		if ( e > alignTot )
+			alignTot = e ;
+	}
+	so[n] = tot ;
+	size_t szT = (size_t)t_off[n] * 16, szP = (size_t)p_off[n], szO = ( n + 1 ) * 8 ;
+	void *dT = 0, *dP = 0, *dTo = 0, *dPo = 0, *dA = 0, *dAo = 0, *dS = 0, *dScr = 0, *dSo = 0 ;
+	if ( dmalloc( &dT, szT + 16 ) || dmalloc( &dP, szP + 16 ) || dmalloc( &dTo, szO ) || dmalloc( &dPo, szO ) || dmalloc( &dA, alignTot + 16 )
+		|| dmalloc( &dAo, szO ) || dmalloc( &dS, n * 4 ) || dmalloc( &dScr, tot + 16 ) || dmalloc( &dSo, szO ) )
+		return T4_E_NOMEM ;
+	h2d( dT, t_weights, szT ) ;
+	h2d( dP, p, szP ) ;
+	h2d( dTo, t_off, szO ) ;
+	h2d( dPo, p_off, szO ) ;
+	h2d( dAo, align_off, szO ) ;
+	h2d( dSo, so.data(), szO ) ;
+#if T4_CUDA
+	t4_dp_kernel<<<( n + 63 ) / 64, 64>>>( n, (const int *)dT, (const i64 *)dTo, (const char *)dP, (const i64 *)dPo, (signed char *)dA,
+		(const i64 *)dAo, (int *)dS, (char *)dScr, (const i64 *)dSo ) ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaDeviceSynchronize() ) ;
+#else
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		int lent = (int)( t_off[i + 1] - t_off[i] ), lenp = (int)( p_off[i + 1] - p_off[i] ) ;
+		int d = lent > lenp ? lent - lenp : lenp - lent ;
+		int W = 2 * T4_DP_BAND + 3 + d ;
+		char *sc = (char *)dScr + so[i] ;
+		( (int *)dS )[i] = t4_dp_posweight( (const int *)dT + 4 * t_off[i], lent, (const char *)dP + p_off[i], lenp,
+			(signed char *)dA + align_off[i], (int *)sc, (unsigned char *)( sc + 8 * W ), 0 ) ;
+	}
+#endif
+	d2h( align_out, dA, alignTot ) ;
+	d2h( score_out, dS, n * 4 ) ;
+	dfree( dT ) ; dfree( dP ) ; dfree( dTo ) ; dfree( dPo ) ; dfree( dA ) ; dfree( dAo ) ; dfree( dS ) ; dfree( dScr ) ; dfree( dSo ) ;
+	return 0 ;
+}
+
+// ---- workloads / batch -------------------------------------------------------------
+t4_workload *T4_API( workload_upload )( const t4_read_desc *descs, int64_t n, const char *read_pool, size_t pool_bytes,
+	const char *const *names, int n_names )
+{
+	if ( ensure_up() )
+		return 0 ;
+	std::vector<u32> noff( n_names + 1 ) ;
+	std::string npool ;
+	for ( int i = 0 ; i < n_names ; ++i )
+	{
+		noff[i] = (u32)npool.size() ;
+		npool += names[i] ;
+	}
+	noff[n_names] = (u32)npool.size() ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	size_t oDesc = 0 ;
+	size_t oPool = oDesc + al( (size_t)n * sizeof( t4_read_desc ) ) ;
+	size_t oNames = oPool + al( pool_bytes + 16 ) ;
+	size_t oNoff = oNames + al( sizeof( T4Names ) ) ;
+	size_t oNpool = oNoff + al( ( n_names + 1 ) * 4 ) ;
+	size_t oRet = oNpool + al( npool.size() + 16 ) ;
+	size_t oStr = oRet + al( (size_t)n * 4 ) ;
+	size_t oResc = oStr + al( (size_t)n ) ;
+	size_t oRl = oResc + al( (size_t)n * 4 ) ;
+	size_t oGood = oRl + al( (size_t)n * 4 ) ;
+	size_t oInfo = oGood + al( (size_t)n ) ;
+	size_t total = oInfo + al( (size_t)n * 4 ) ;
+	void *p = 0 ;
+	if ( dmalloc( &p, total ) )
+		return 0 ;
+	t4_workload *w = new t4_workload ;
+	memset( w, 0, sizeof( *w ) ) ;
+	w->buf = (char *)p ;
+	w->bytes = total ;
+	w->nDescs = n ;
+	w->poolBytes = pool_bytes ;
+	w->nNames = n_names ;
+	w->descs = (t4_read_desc *)( w->buf + oDesc ) ;
+	w->pool = w->buf + oPool ;
+	w->names = (T4Names *)( w->buf + oNames ) ;
+	w->ret = (int32_t *)( w->buf + oRet ) ;
+	w->strands = (int8_t *)( w->buf + oStr ) ;
+	w->rescue = (int32_t *)( w->buf + oResc ) ;
+	w->rescueList = (int32_t *)( w->buf + oRl ) ;
+	w->good = (int8_t *)( w->buf + oGood ) ;
+	w->info = (int32_t *)( w->buf + oInfo ) ;
+	T4Names hn ;
+	hn.pool = (u64)(uintptr_t)( w->buf + oNpool ) ;
+	hn.off = (u64)(uintptr_t)( w->buf + oNoff ) ;
+	hn.n = n_names ;
+	hn.pad = 0 ;
+	if ( h2d( w->descs, descs, (size_t)n * sizeof( t4_read_desc ) ) || h2d( w->pool, read_pool, pool_bytes ) || h2d( w->names, &hn, sizeof( hn ) )
+		|| h2d( w->buf + oNoff, noff.data(), ( n_names + 1 ) * 4 ) || h2d( w->buf + oNpool, npool.data(), npool.size() ) )
+	{
+		dfree( p ) ;
+		delete w ;
+		return 0 ;
+	}
+	return w ;
+}
+
+void T4_API( workload_free )( t4_workload *w )
+{
+	if ( !w )
+		return ;
+	if ( w->ops )
+		dfree( w->ops ) ;
+	dfree( w->buf ) ;
+	delete w ;
+}
+
+static int build_ops( t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg, t4_workload *w, const int64_t *desc_off, int opcode,
+	std::vector<T4Op> &ops )
+{
+	ops.resize( n_sets ) ;
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		int r = check( sets[j] ) ;
+		if ( r ) return r ;
+		T4Op &op = ops[j] ;
+		memset( &op, 0, sizeof( op ) ) ;
+		i64 lo = desc_off[j], hi = desc_off[j + 1] ;
+		if ( lo < 0 || hi < lo || hi > w->nDescs )
+		{
+			set_err( "desc_off out of range" ) ;
+			return T4_E_INVAL ;
+		}
+		op.streamOff = sets[j]->off ;
+		op.op = opcode ;
+		op.n = (int)( hi - lo ) ;
+		op.desc = (u64)(uintptr_t)( w->descs + lo ) ;
+		op.pool = (u64)(uintptr_t)w->pool ;
+		op.names = (u64)(uintptr_t)w->names ;
+		op.retCodes = (u64)(uintptr_t)( w->ret + lo ) ;
+		op.strands = (u64)(uintptr_t)( w->strands + lo ) ;
+		op.rescueRet = (u64)(uintptr_t)( w->rescue + lo ) ;
+		op.rescueList = (u64)(uintptr_t)( w->rescueList + lo ) ;
+		op.good = (u64)(uintptr_t)( w->good + lo ) ;
+		op.info = (u64)(uintptr_t)( w->info + lo ) ;
+		if ( cfg )
+			op.cfg = *cfg ;
+	}
+	return 0 ;
+}
+
+static int ensure_ops( t4_workload *w, int n )
+{
+	if ( n <= w->opCap )
+		return 0 ;
+	if ( w->ops )
+		dfree( w->ops ) ;
+	void *p = 0 ;
+	int r = dmalloc( &p, (size_t)n * sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	w->ops = (T4Op *)p ;
+	w->opCap = n ;
+	return 0 ;
+}
+
+int T4_API( streams_run_resident )( t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg, t4_workload *w, const int64_t *desc_off,
+	void *cuda_stream )
+{
+	if ( !w || n_sets <= 0 )
+		return T4_E_INVAL ;
+	std::vector<T4Op> ops ;
+	int r = build_ops( sets, n_sets, cfg, w, desc_off, T4_OP_RUN_LOOP, ops ) ;
+	if ( r ) return r ;
+	r = ensure_ops( w, n_sets ) ;
+	if ( r ) return r ;
+#if T4_CUDA
+	CK( cudaMemcpyAsync( w->ops, ops.data(), (size_t)n_sets * sizeof( T4Op ), cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream ) ) ;
+#else
+	memcpy( w->ops, ops.data(), (size_t)n_sets * sizeof( T4Op ) ) ;
+#endif
+	return launch_ops( w->ops, n_sets, cuda_stream ) ;
+}
+
+int T4_API( probe_resident )( t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off, void *cuda_stream,
+	uint64_t *algorithmic_bytes, uint64_t *hits_emitted )
+{
+	if ( !w || n_sets <= 0 )
+		return T4_E_INVAL ;
+	std::vector<T4Op> ops ;
+	int r = build_ops( sets, n_sets, NULL, w, desc_off, T4_OP_PROBE_ONLY, ops ) ;
+	if ( r ) return r ;
+	r = ensure_ops( w, n_sets ) ;
+	if ( r ) return r ;
+	r = dsync() ;
+	if ( r ) return r ;
+	r = reset_counters() ;
+	if ( r ) return r ;
+	r = h2d( w->ops, ops.data(), (size_t)n_sets * sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	r = launch_ops( w->ops, n_sets, cuda_stream ) ;
+	if ( r ) return r ;
+	if ( algorithmic_bytes || hits_emitted )
+	{
+		r = dsync() ;
+		if ( r ) return r ;
+		u64 c[T4_N_COUNTERS] ;
+		r = T4_API( last_counters )( c ) ;
+		if ( r ) return r ;
+		// B_probe = ceil(L/4) + sum_j (8 + 8 c_j) + 16 sum_j c_j'
+		if ( algorithmic_bytes ) *algorithmic_bytes = c[5] + 8 * c[2] + 8 * c[3] + 16 * c[4] ;
+		if ( hits_emitted ) *hits_emitted = c[4] ;
+	}
+	return 0 ;
+}
+
+int T4_API( workload_results )( t4_workload *w, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret )
+{
+	int r = dsync() ;
+	if ( r ) return r ;
+	if ( ret_codes && ( r = d2h( ret_codes, w->ret, (size_t)w->nDescs * 4 ) ) ) return r ;
+	if ( strands && ( r = d2h( strands, w->strands, (size_t)w->nDescs ) ) ) return r ;
+	if ( rescue_ret && ( r = d2h( rescue_ret, w->rescue, (size_t)w->nDescs * 4 ) ) ) return r ;
+	return 0 ;
+}
+
+// first device-side error among the given streams (0 if none)
+int T4_API( streams_error )( t4_seqset *const *sets, int n_sets )
+{
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		T4Stream st ;
+		int r = get_stream( sets[j], &st ) ;
+		if ( r ) return r ;
+		if ( st.error )
+		{
+			set_err( "stream " + std::to_string( j ) + ": device error " + std::to_string( st.error ) + " aux " + std::to_string( st.errorAux ) ) ;
+			return st.error ;
+		}
+	}
+	return 0 ;
+}
+
+int T4_API( streams_run )( t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg, const t4_read_desc *descs, const int64_t *desc_off,
+	const char *read_pool, size_t read_pool_bytes, const char *const *names, int n_names, int32_t *ret_codes, int8_t *strands,
+	int32_t *rescue_ret )
+{
+	if ( n_sets <= 0 )
+		return T4_E_INVAL ;
+	t4_workload *w = T4_API( workload_upload )( descs, desc_off[n_sets], read_pool, read_pool_bytes, names, n_names ) ;
+	if ( !w )
+		return T4_E_NOMEM ;
+	int r = T4_API( streams_run_resident )( sets, n_sets, cfg, w, desc_off, 0 ) ;
+	if ( !r )
+		r = T4_API( workload_results )( w, ret_codes, strands, rescue_ret ) ;
+	if ( !r )
+		r = T4_API( streams_error )( sets, n_sets ) ;
+	T4_API( workload_free )( w ) ;
+	return r ;
+}
+
+int T4_API( seqset_add_reads_batch )( t4_seqset *s, const t4_run_cfg *cfg, const t4_read_desc *descs, int n, const char *read_pool,
+	size_t read_pool_bytes, const char *const *names, int n_names, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret )
+{
+	int64_t off[2] = { 0, n } ;
+	return T4_API( streams_run )( &s, 1, cfg, descs, off, read_pool, read_pool_bytes, names, n_names, ret_codes, strands, rescue_ret ) ;
+}
+
+} // extern "C"

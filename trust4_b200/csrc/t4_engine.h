@@ -1,0 +1,2938 @@
+// Stream engine: the per-read k-mer-seeded overlap-and-extend assembly hot path
+// (KmerIndex lookup -> hit chaining -> banded DP extension -> posWeight update)
+// as device code executed by ONE CTA PER STREAM (= per SeqSet).
+//
+// Written against T4Ctx{tid, nt} + T4_SYNC(): compiled by nvcc for sm_100a
+// (product) and by g++ with nt = 1 for the test-only emulation (tests/emu).
+// Function prefixes:  c_  collective (every thread of the CTA calls it; contains
+// barriers),  s_  serial (thread 0 only),  no prefix: pure / any thread.
+//
+// Every function cites the reference code whose observable behaviour it
+// reproduces (paths relative to the reference tree).  This is a re-design, not a
+// translation: hits are single 64-bit keys sorted by a CTA radix sort, chains are
+// diagonal runs of the sorted key array, contigs live in slack-padded HBM arrays
+// so a left extension is a pointer move, postings are unordered multisets
+// (their order is unobservable: GetOverlapsFromHits re-sorts every group).
+#ifndef T4_ENGINE_H
+#define T4_ENGINE_H
+
+#include "t4_common.h"
+
+#if !T4_CUDA
+#include <algorithm>
+#endif
+
+#define T4_MAX_NT 128
+#define T4_RADIX_BITS 4
+#define T4_RADIX (1 << T4_RADIX_BITS)
+#define T4_DP_BAND 5
+#define T4_DP_W (2 * T4_DP_BAND + 3)
+
+#define EDIT_MATCH 0
+#define EDIT_MISMATCH 1
+#define EDIT_INSERT 2
+#define EDIT_DELETE 3
+#define SCORE_MATCH 2
+#define SCORE_MISMATCH (-2)
+#define SCORE_INDEL (-4)
+
+struct T4Smem
+{
+	char read[T4_DEV_MAX_READ + 8] ;
+	char rc[T4_DEV_MAX_READ + 8] ;
+	u32 radix[T4_RADIX * T4_MAX_NT] ;
+	u32 scan[T4_MAX_NT + 4] ;
+	u64 bu[4] ;
+	int bi[8] ;
+	u64 red[2] ;
+} ;
+
+struct T4Ctx
+{
+	char *A ;          // arena base
+	T4Global *g ;
+	T4Stream *st ;
+	T4Smem *sm ;
+	int tid, nt ;
+
+	template <class T> T4_HD T *P( u64 off ) const { return (T *)( A + off ) ; }
+} ;
+
+#define T4_PAR_FOR( i, n ) for ( int i = cx.tid ; i < (int)( n ) ; i += cx.nt )
+
+// ---------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------
+T4_HD inline int t4_nuc( char c ) // nucToNum[c - 'A'] & 3 (main.cpp:39-42): A0 C1 G2 T3, N -> 0, anything else -> 3
+{
+	switch ( c )
+	{
+		case 'A': return 0 ;
+		case 'C': return 1 ;
+		case 'G': return 2 ;
+		case 'T': return 3 ;
+		case 'N': return 0 ;
+		default: return 3 ;
+	}
+}
+T4_HD inline char t4_numToNuc( int x ) { return "ACGT"[x & 3] ; }
+
+T4_HD inline int t4_abs( int x ) { return x < 0 ? -x : x ; }
+T4_HD inline int t4_min( int a, int b ) { return a < b ? a : b ; }
+T4_HD inline int t4_max( int a, int b ) { return a > b ? a : b ; }
+
+T4_D inline u64 t4_atomic_add( u64 *p, u64 v )
+{
+#if T4_CUDA
+	return atomicAdd( (unsigned long long *)p, (unsigned long long)v ) ;
+#else
+	u64 o = *p ; *p += v ; return o ;
+#endif
+}
+
+T4_D inline void t4_raise( T4Ctx &cx, int code, int aux )
+{
+	if ( cx.st->error == 0 )
+	{
+		cx.st->error = code ;
+		cx.st->errorAux = aux ;
+	}
+}
+
+// Serial bump allocation from the arena.  Returns 0 (and raises T4_E_NOMEM) when exhausted.
+T4_D inline u64 s_alloc( T4Ctx &cx, u64 bytes )
+{
+	bytes = ( bytes + ( T4_ALIGN - 1 ) ) & ~(u64)( T4_ALIGN - 1 ) ;
+	u64 off = t4_atomic_add( &cx.g->top, bytes ) ;
+	if ( off + bytes > cx.g->cap )
+	{
+		t4_raise( cx, T4_E_NOMEM, (int)( bytes >> 10 ) ) ;
+		return 0 ;
+	}
+	return off ;
+}
+
+T4_D inline T4Contig *t4_seq( T4Ctx &cx, int idx ) { return cx.P<T4Contig>( cx.st->seqsOff ) + idx ; }
+T4_D inline char *t4_cons( T4Ctx &cx, T4Contig *c ) { return cx.P<char>( c->consOff ) + c->lead ; }
+T4_D inline int *t4_pw( T4Ctx &cx, T4Contig *c ) { return cx.P<int>( c->pwOff ) + 4 * c->lead ; }
+
+T4_D inline u64 t4_key_of( int strand, int idx, int a, int b, int bigRepeat )
+{
+	return ( (u64)( strand == 1 ? 1 : 0 ) << T4_KEY_STRAND_SHIFT ) | ( (u64)(u32)idx << T4_KEY_IDX_SHIFT )
+		| ( (u64)(u32)( a - b + T4_KEY_C_BIAS ) << T4_KEY_C_SHIFT ) | ( (u64)(u32)b << T4_KEY_B_SHIFT ) | (u64)( bigRepeat ? 1 : 0 ) ;
+}
+T4_HD inline int t4_key_strand( u64 k ) { return ( k >> T4_KEY_STRAND_SHIFT ) ? 1 : -1 ; }
+T4_HD inline int t4_key_idx( u64 k ) { return (int)( ( k >> T4_KEY_IDX_SHIFT ) & ( ( 1u << T4_KEY_IDX_BITS ) - 1 ) ) ; }
+T4_HD inline int t4_key_b( u64 k ) { return (int)( ( k >> T4_KEY_B_SHIFT ) & T4_KEY_B_MASK ) ; }
+T4_HD inline int t4_key_c( u64 k ) { return (int)( ( k >> T4_KEY_C_SHIFT ) & T4_KEY_C_MASK ) - T4_KEY_C_BIAS ; }
+T4_HD inline int t4_key_a( u64 k ) { return t4_key_b( k ) + t4_key_c( k ) ; }
+T4_HD inline int t4_key_big( u64 k ) { return (int)( k & 1 ) ; }
+
+// ---------------------------------------------------------------------------
+// k-mer directory + postings (KmerIndex.hpp).  Open addressing, 32-byte slots.
+// ---------------------------------------------------------------------------
+T4_D inline u64 t4_index_key( T4Stream *st, u64 code, int barcode )
+{
+	// KmerIndex::GetHash salts the bucket with barcode + 1 when considerBarcode is set (KmerIndex.hpp:29-33);
+	// the postings lists are then effectively per (k-mer, barcode).
+	u64 key = code ;
+	if ( st->considerBarcode )
+		key += (u64)(u32)( barcode + 1 ) << ( 2 * st->kmerLength ) ;
+	return key + 1 ;
+}
+
+T4_D inline u32 t4_dir_slot( u64 key, u32 cap ) { return (u32)( ( key * 0x9E3779B97F4A7C15ull ) >> 32 ) & ( cap - 1 ) ; }
+
+T4_D inline T4Dir *t4_dir_find( T4Ctx &cx, u64 key )
+{
+	T4Stream *st = cx.st ;
+	T4Dir *dir = cx.P<T4Dir>( st->dirOff ) ;
+	u32 cap = st->dirCap ;
+	u32 s = t4_dir_slot( key, cap ) ;
+	while ( 1 )
+	{
+		u64 kk = dir[s].key ;
+		if ( kk == key )
+			return dir + s ;
+		if ( kk == 0 )
+			return 0 ;
+		s = ( s + 1 ) & ( cap - 1 ) ;
+	}
+}
+
+T4_D inline void s_dir_grow( T4Ctx &cx )
+{
+	T4Stream *st = cx.st ;
+	u32 oldCap = st->dirCap ;
+	u32 newCap = oldCap * 2 ;
+	u64 off = s_alloc( cx, (u64)newCap * sizeof( T4Dir ) ) ;
+	if ( !off )
+		return ;
+	T4Dir *nd = cx.P<T4Dir>( off ) ;
+	T4Dir *od = cx.P<T4Dir>( st->dirOff ) ;
+	for ( u32 i = 0 ; i < newCap ; ++i )
+		nd[i].key = 0 ;
+	for ( u32 i = 0 ; i < oldCap ; ++i )
+	{
+		if ( od[i].key == 0 )
+			continue ;
+		u32 s = t4_dir_slot( od[i].key, newCap ) ;
+		while ( nd[s].key != 0 )
+			s = ( s + 1 ) & ( newCap - 1 ) ;
+		nd[s] = od[i] ;
+	}
+	st->dirOff = off ;
+	st->dirCap = newCap ;
+}
+
+T4_D inline T4Dir *s_dir_get( T4Ctx &cx, u64 key )
+{
+	T4Stream *st = cx.st ;
+	if ( ( st->dirUsed + 1 ) * 2 > st->dirCap )
+	{
+		s_dir_grow( cx ) ;
+		if ( st->error )
+			return 0 ;
+	}
+	T4Dir *dir = cx.P<T4Dir>( st->dirOff ) ;
+	u32 cap = st->dirCap ;
+	u32 s = t4_dir_slot( key, cap ) ;
+	while ( 1 )
+	{
+		u64 kk = dir[s].key ;
+		if ( kk == key )
+			return dir + s ;
+		if ( kk == 0 )
+		{
+			dir[s].key = key ;
+			dir[s].listOff = 0 ;
+			dir[s].cnt = 0 ;
+			dir[s].cap = 0 ;
+			dir[s].lock = 0 ;
+			++st->dirUsed ;
+			return dir + s ;
+		}
+		s = ( s + 1 ) & ( cap - 1 ) ;
+	}
+}
+
+// KmerIndex::Insert (KmerIndex.hpp:66).  Postings are an unordered multiset.
+T4_D inline void s_index_insert( T4Ctx &cx, u64 code, int idx, int offset, int barcode )
+{
+	T4Dir *d = s_dir_get( cx, t4_index_key( cx.st, code, barcode ) ) ;
+	if ( !d )
+		return ;
+	if ( d->cnt == d->cap )
+	{
+		u32 nc = d->cap ? d->cap * 2 : 4 ;
+		u64 off = s_alloc( cx, (u64)nc * 8 ) ;
+		if ( !off )
+			return ;
+		u64 *nl = cx.P<u64>( off ) ;
+		u64 *ol = cx.P<u64>( d->listOff ) ;
+		for ( u32 i = 0 ; i < d->cnt ; ++i )
+			nl[i] = ol[i] ;
+		d->listOff = off ;
+		d->cap = nc ;
+	}
+	cx.P<u64>( d->listOff )[d->cnt] = ( (u64)(u32)idx << 32 ) | (u32)offset ;
+	++d->cnt ;
+}
+
+// KmerIndex::Remove (KmerIndex.hpp:81): delete one posting equal to (idx, offset) if present.
+T4_D inline void s_index_remove( T4Ctx &cx, u64 code, int idx, int offset, int barcode )
+{
+	T4Dir *d = t4_dir_find( cx, t4_index_key( cx.st, code, barcode ) ) ;
+	if ( !d )
+		return ;
+	u64 v = ( (u64)(u32)idx << 32 ) | (u32)offset ;
+	u64 *l = cx.P<u64>( d->listOff ) ;
+	for ( u32 i = 0 ; i < d->cnt ; ++i )
+		if ( l[i] == v )
+		{
+			l[i] = l[d->cnt - 1] ;
+			--d->cnt ;
+			return ;
+		}
+}
+
+// Rolling 2-bit k-mer with N tracking (KmerCode.hpp:94-109).
+struct T4Kmer
+{
+	u64 code, mask ;
+	int k, sinceN ;    // sinceN: bases appended since the last 'N' (saturating), valid iff >= k
+	T4_D inline void init( int kl )
+	{
+		k = kl ;
+		mask = kl < 32 ? ( ( 1ull << ( 2 * kl ) ) - 1ull ) : ~0ull ;
+		code = 0 ;
+		sinceN = 1 << 20 ;
+	}
+	T4_D inline void restart() { code = 0 ; sinceN = 1 << 20 ; }
+	T4_D inline void append( char c )
+	{
+		code = ( ( code << 2 ) & mask ) | (u64)t4_nuc( c ) ;
+		if ( c == 'N' )
+			sinceN = 0 ;
+		else if ( sinceN < ( 1 << 20 ) )
+			++sinceN ;
+	}
+	T4_D inline bool valid() const { return sinceN >= k ; }
+} ;
+
+// KmerIndex::BuildIndexFromRead (KmerIndex.hpp:118-141), including its first-k-mer rule (i == kl, not kl-1).
+T4_D inline void s_build_index( T4Ctx &cx, const char *s, int len, int id, int barcode, int shift )
+{
+	int kl = cx.st->kmerLength ;
+	if ( len < kl )
+		return ;
+	T4Kmer km ;
+	km.init( kl ) ;
+	u64 prev = 0 ;
+	int i ;
+	for ( i = 0 ; i < kl - 1 ; ++i )
+		km.append( s[i] ) ;
+	for ( ; i < len ; ++i )
+	{
+		km.append( s[i] ) ;
+		if ( km.valid() && ( i == kl || km.code != prev ) )
+			s_index_insert( cx, km.code, id, i - kl + 1 + shift, barcode ) ;
+		prev = km.code ;
+	}
+}
+
+// KmerIndex::UpdateIndexFromRead (KmerIndex.hpp:144-181): literal, position by position.
+T4_D inline void s_update_index( T4Ctx &cx, const char *s, int len, int barcode, int shift, int oldId, int id )
+{
+	int kl = cx.st->kmerLength ;
+	if ( len < kl )
+		return ;
+	T4Kmer km ;
+	km.init( kl ) ;
+	int i ;
+	for ( i = 0 ; i < kl - 1 ; ++i )
+		km.append( s[i] ) ;
+	for ( ; i < len ; ++i )
+	{
+		km.append( s[i] ) ;
+		if ( !km.valid() )
+			continue ;
+		T4Dir *d = t4_dir_find( cx, t4_index_key( cx.st, km.code, barcode ) ) ;
+		if ( !d )
+			continue ;
+		u64 v = ( (u64)(u32)oldId << 32 ) | (u32)( i - kl + 1 ) ;
+		u64 *l = cx.P<u64>( d->listOff ) ;
+		for ( u32 j = 0 ; j < d->cnt ; ++j )
+			if ( l[j] == v )
+			{
+				l[j] = ( (u64)(u32)id << 32 ) | (u32)( i - kl + 1 + shift ) ;
+				break ;
+			}
+	}
+}
+
+// KmerIndex::RemoveIndexFromRead (KmerIndex.hpp:183-201).
+T4_D inline void s_remove_index( T4Ctx &cx, const char *s, int len, int id, int barcode, int offset )
+{
+	int kl = cx.st->kmerLength ;
+	if ( len < kl )
+		return ;
+	T4Kmer km ;
+	km.init( kl ) ;
+	int i ;
+	for ( i = 0 ; i < kl - 1 ; ++i )
+		km.append( s[i] ) ;
+	for ( ; i < len ; ++i )
+	{
+		km.append( s[i] ) ;
+		if ( km.valid() )
+			s_index_remove( cx, km.code, id, i - kl + 1 + offset, barcode ) ;
+	}
+}
+
+// ---------------------------------------------------------------------------
+// contig storage
+// ---------------------------------------------------------------------------
+// Append a contig slot (seqs.push_back).  Serial.
+T4_D inline int s_new_contig( T4Ctx &cx, int len )
+{
+	T4Stream *st = cx.st ;
+	if ( st->nSeqs == st->seqCap )
+	{
+		int nc = st->seqCap * 2 ;
+		u64 off = s_alloc( cx, (u64)nc * sizeof( T4Contig ) ) ;
+		if ( !off )
+			return -1 ;
+		T4Contig *n = cx.P<T4Contig>( off ) ;
+		T4Contig *o = cx.P<T4Contig>( st->seqsOff ) ;
+		for ( int i = 0 ; i < st->nSeqs ; ++i )
+			n[i] = o[i] ;
+		st->seqsOff = off ;
+		st->seqCap = nc ;
+	}
+	if ( st->nSeqs >= ( 1 << T4_KEY_IDX_BITS ) - 1 )
+	{
+		t4_raise( cx, T4_E_UNSUPPORTED, 1 ) ;
+		return -1 ;
+	}
+	int idx = st->nSeqs ;
+	T4Contig *c = t4_seq( cx, idx ) ;
+	int cap = 2 * len + 128 ;
+	c->consOff = s_alloc( cx, cap ) ;
+	c->pwOff = s_alloc( cx, (u64)cap * 16 ) ;
+	if ( !c->consOff || !c->pwOff )
+		return -1 ;
+	c->cap = cap ;
+	c->lead = ( cap - len ) / 2 ;
+	c->len = len ;
+	c->nameOff = 0 ;
+	c->nameLen = 0 ;
+	c->minLeftExtAnchor = c->minRightExtAnchor = 0 ;
+	c->barcode = -1 ;
+	c->numRead = 0 ;
+	++st->nSeqs ;
+	return idx ;
+}
+
+// Make room for `left` new bases in front and `right` behind; old bases keep their values,
+// new cells are uninitialised.  Serial.
+T4_D inline bool s_contig_grow( T4Ctx &cx, T4Contig *c, int left, int right )
+{
+	int newLen = c->len + left + right ;
+	if ( newLen > (int)T4_KEY_B_MASK )
+	{
+		t4_raise( cx, T4_E_UNSUPPORTED, 2 ) ;
+		return false ;
+	}
+	if ( c->lead >= left && c->lead + c->len + right <= c->cap )
+	{
+		c->lead -= left ;
+		c->len = newLen ;
+		return true ;
+	}
+	int cap = 2 * newLen + 128 ;
+	u64 co = s_alloc( cx, cap ) ;
+	u64 po = s_alloc( cx, (u64)cap * 16 ) ;
+	if ( !co || !po )
+		return false ;
+	int lead = ( cap - newLen ) / 2 ;
+	char *oc = t4_cons( cx, c ) ;
+	int *op = t4_pw( cx, c ) ;
+	char *nc = cx.P<char>( co ) + lead + left ;
+	int *np = cx.P<int>( po ) + 4 * ( lead + left ) ;
+	for ( int i = 0 ; i < c->len ; ++i )
+		nc[i] = oc[i] ;
+	for ( int i = 0 ; i < 4 * c->len ; ++i )
+		np[i] = op[i] ;
+	c->consOff = co ;
+	c->pwOff = po ;
+	c->cap = cap ;
+	c->lead = lead ;
+	c->len = newLen ;
+	return true ;
+}
+
+T4_D inline void s_set_name( T4Ctx &cx, T4Contig *c, const char *s, int n )
+{
+	u64 off = s_alloc( cx, n + 1 ) ;
+	if ( !off )
+		return ;
+	char *d = cx.P<char>( off ) ;
+	for ( int i = 0 ; i < n ; ++i )
+		d[i] = s[i] ;
+	d[n] = '\0' ;
+	c->nameOff = off ;
+	c->nameLen = n ;
+}
+
+// SeqSet::SetPrevAddInfo (SeqSet.hpp:627)
+T4_D inline void t4_set_prev( T4Stream *st, int seqIdx, int readStart, int readEnd, int seqStart, int strand )
+{
+	st->prevSeqIdx = seqIdx ;
+	st->prevReadStart = readStart ;
+	st->prevReadEnd = readEnd ;
+	st->prevSeqStart = seqStart ;
+	st->prevStrand = strand ;
+}
+
+// SeqSet::ReverseComplement (SeqSet.hpp:2616)
+T4_D inline void t4_revcomp( char *rc, const char *s, int len )
+{
+	for ( int i = 0 ; i < len ; ++i )
+	{
+		char c = s[len - 1 - i] ;
+		rc[i] = ( c != 'N' ) ? t4_numToNuc( 3 - t4_nuc( c ) ) : 'N' ;
+	}
+	rc[len] = '\0' ;
+}
+
+// ---------------------------------------------------------------------------
+// collective primitives
+// ---------------------------------------------------------------------------
+// Grow the hit scratch buffers to hold n keys.
+T4_D inline void c_ensure_hits( T4Ctx &cx, u32 n )
+{
+	T4Stream *st = cx.st ;
+	if ( n + 1 > st->hitCap )
+	{
+		if ( cx.tid == 0 )
+		{
+			u32 nc = st->hitCap ;
+			while ( nc < n + 1 )
+				nc *= 2 ;
+			u64 a = s_alloc( cx, (u64)nc * 8 ) ;
+			u64 b = s_alloc( cx, (u64)nc * 8 ) ;
+			u64 g = s_alloc( cx, (u64)( nc + 1 ) * 4 ) ;
+			u64 r = s_alloc( cx, (u64)( nc + 1 ) * 4 ) ;
+			if ( a && b && g && r )
+			{
+				st->keysAOff = a ; st->keysBOff = b ; st->grpOff = g ; st->runOff = r ;
+				st->hitCap = nc ;
+			}
+		}
+		T4_SYNC() ;
+	}
+}
+
+T4_D inline void c_ensure_ovl( T4Ctx &cx, u32 n )
+{
+	T4Stream *st = cx.st ;
+	if ( n + 1 > st->ovlCap )
+	{
+		if ( cx.tid == 0 )
+		{
+			u32 nc = st->ovlCap ;
+			while ( nc < n + 1 )
+				nc *= 2 ;
+			u64 a = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
+			u64 b = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
+			u64 c = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
+			u64 d = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
+			u64 e = s_alloc( cx, (u64)nc * 8 ) ;
+			if ( a && b && c && d && e )
+			{
+				// the live overlaps (if any) stay valid: callers only grow before filling
+				st->ovlOff = a ; st->ovlTmpOff = b ; st->extOff = c ; st->failOff = d ; st->anchorOff = e ;
+				st->ovlCap = nc ;
+			}
+		}
+		T4_SYNC() ;
+	}
+}
+
+// Exclusive scan of one value per thread; returns this thread's offset and the total.
+T4_D inline u32 c_scan_threads( T4Ctx &cx, u32 v, u32 &total )
+{
+	T4_SYNC() ;
+	cx.sm->scan[cx.tid] = v ;
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+	{
+		u32 s = 0 ;
+		for ( int t = 0 ; t < cx.nt ; ++t )
+		{
+			u32 x = cx.sm->scan[t] ;
+			cx.sm->scan[t] = s ;
+			s += x ;
+		}
+		cx.sm->scan[cx.nt] = s ;
+	}
+	T4_SYNC() ;
+	total = cx.sm->scan[cx.nt] ;
+	return cx.sm->scan[cx.tid] ;
+}
+
+// Sort n keys ascending.  Returns the buffer (a or b) holding the result.
+T4_D inline u64 *c_sort_keys( T4Ctx &cx, u64 *a, u64 *b, u32 n )
+{
+#if !T4_CUDA
+	std::sort( a, a + n ) ;
+	return a ;
+#else
+	if ( n <= 1 )
+		return a ;
+	// which bits vary at all?
+	u64 vo = 0, va = ~0ull ;
+	for ( u32 i = cx.tid ; i < n ; i += cx.nt )
+	{
+		u64 k = a[i] ;
+		vo |= k ;
+		va &= k ;
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+	{
+		cx.sm->red[0] = 0 ;
+		cx.sm->red[1] = ~0ull ;
+	}
+	T4_SYNC() ;
+	atomicOr( (unsigned long long *)&cx.sm->red[0], (unsigned long long)vo ) ;
+	atomicAnd( (unsigned long long *)&cx.sm->red[1], (unsigned long long)va ) ;
+	T4_SYNC() ;
+	u64 vary = cx.sm->red[0] ^ cx.sm->red[1] ;
+	u32 chunk = ( n + cx.nt - 1 ) / cx.nt ;
+	u32 lo = cx.tid * chunk ;
+	u32 hi = lo + chunk < n ? lo + chunk : n ;
+	if ( lo > n )
+		lo = n ;
+	u64 *src = a, *dst = b ;
+	for ( int shift = 0 ; shift < 64 ; shift += T4_RADIX_BITS )
+	{
+		if ( ( ( vary >> shift ) & ( T4_RADIX - 1 ) ) == 0 )
+			continue ;
+		u32 *cnt = cx.sm->radix ;
+		for ( int d = 0 ; d < T4_RADIX ; ++d )
+			cnt[d * cx.nt + cx.tid] = 0 ;
+		for ( u32 i = lo ; i < hi ; ++i )
+			++cnt[( ( src[i] >> shift ) & ( T4_RADIX - 1 ) ) * cx.nt + cx.tid] ;
+		T4_SYNC() ;
+		// exclusive scan over (digit major, thread minor)
+		if ( cx.tid < T4_RADIX )
+		{
+			u32 s = 0 ;
+			for ( int t = 0 ; t < cx.nt ; ++t )
+				s += cnt[cx.tid * cx.nt + t] ;
+			cx.sm->scan[cx.tid] = s ;
+		}
+		T4_SYNC() ;
+		if ( cx.tid == 0 )
+		{
+			u32 s = 0 ;
+			for ( int d = 0 ; d < T4_RADIX ; ++d )
+			{
+				u32 x = cx.sm->scan[d] ;
+				cx.sm->scan[d] = s ;
+				s += x ;
+			}
+		}
+		T4_SYNC() ;
+		if ( cx.tid < T4_RADIX )
+		{
+			u32 s = cx.sm->scan[cx.tid] ;
+			for ( int t = 0 ; t < cx.nt ; ++t )
+			{
+				u32 x = cnt[cx.tid * cx.nt + t] ;
+				cnt[cx.tid * cx.nt + t] = s ;
+				s += x ;
+			}
+		}
+		T4_SYNC() ;
+		for ( u32 i = lo ; i < hi ; ++i )
+		{
+			u64 k = src[i] ;
+			u32 d = ( k >> shift ) & ( T4_RADIX - 1 ) ;
+			dst[cnt[d * cx.nt + cx.tid]++] = k ;
+		}
+		T4_SYNC() ;
+		u64 *t = src ; src = dst ; dst = t ;
+	}
+	return src ;
+#endif
+}
+
+// Positions p in [0,n) where (keys[p] >> shift) differs from its predecessor's, in order; out[count] = n.
+T4_D inline u32 c_heads( T4Ctx &cx, const u64 *keys, u32 n, int shift, u32 *out )
+{
+	u32 chunk = ( n + cx.nt - 1 ) / cx.nt ;
+	u32 lo = cx.tid * chunk ;
+	u32 hi = lo + chunk < n ? lo + chunk : n ;
+	if ( lo > n )
+		lo = n ;
+	u32 c = 0 ;
+	for ( u32 i = lo ; i < hi ; ++i )
+		if ( i == 0 || ( keys[i] >> shift ) != ( keys[i - 1] >> shift ) )
+			++c ;
+	u32 total ;
+	u32 o = c_scan_threads( cx, c, total ) ;
+	for ( u32 i = lo ; i < hi ; ++i )
+		if ( i == 0 || ( keys[i] >> shift ) != ( keys[i - 1] >> shift ) )
+			out[o++] = i ;
+	if ( cx.tid == 0 )
+		out[total] = n ;
+	T4_SYNC() ;
+	return total ;
+}
+
+// ---------------------------------------------------------------------------
+// banded global alignment against posWeight columns
+// ---------------------------------------------------------------------------
+// AlignAlgo::IsBaseEqual (AlignAlgo.hpp:49-55)
+T4_HD inline bool t4_base_equal( const int *w, char c )
+{
+	int sum = w[0] + w[1] + w[2] + w[3] ;
+	if ( sum == 0 || c == 'N' || sum < 3 * w[t4_nuc( c )] )
+		return true ;
+	return false ;
+}
+
+// AlignAlgo::GlobalAlignment_PosWeight (AlignAlgo.hpp:57-216).  tw: lent columns of int[4]; p: lenp chars.
+// rows: 2*W ints, act: (lenp+1)*W bytes with W = leftBand + rightBand + 3.  Scores are kept for two rows only;
+// the traceback decision of every band cell (a pure function of the cell and its three neighbours,
+// AlignAlgo.hpp:177-193) is taken while filling and stored as one byte.
+T4_HD inline int t4_dp_posweight( const int *tw, int lent, const char *p, int lenp, signed char *align, int *rows,
+	unsigned char *act, int *usedFullDp )
+{
+	if ( usedFullDp )
+		*usedFullDp = 0 ;
+	if ( lent == 0 || lenp == 0 )
+	{
+		align[0] = -1 ;
+		return 0 ;
+	}
+	else if ( lent == 1 && lenp == 1 )
+	{
+		if ( t4_base_equal( tw, p[0] ) )
+		{
+			align[0] = EDIT_MATCH ;
+			align[1] = -1 ;
+			return SCORE_MATCH ;
+		}
+		align[0] = EDIT_MISMATCH ;
+		align[1] = -1 ;
+		return SCORE_MISMATCH ;
+	}
+	int i, j ;
+	if ( lent == lenp )
+	{
+		int score = 0 ;
+		for ( i = 0 ; i < lent ; ++i )
+		{
+			if ( t4_base_equal( tw + 4 * i, p[i] ) )
+			{
+				align[i] = EDIT_MATCH ;
+				score += SCORE_MATCH ;
+			}
+			else
+			{
+				align[i] = EDIT_MISMATCH ;
+				score += SCORE_MISMATCH ;
+			}
+		}
+		align[i] = -1 ;
+		if ( score >= lent * SCORE_MATCH + 2 * SCORE_INDEL )
+			return score ;
+	}
+	if ( usedFullDp )
+		*usedFullDp = 1 ;
+	int leftBand = T4_DP_BAND, rightBand = T4_DP_BAND ;
+	if ( lent > lenp )
+		rightBand += lent - lenp ;
+	else if ( lent < lenp )
+		leftBand += lenp - lent ;
+	const int W = leftBand + rightBand + 3 ;
+	const int negInf = ( lent + 1 ) * ( lenp + 1 ) * SCORE_INDEL ;
+	int *prev = rows, *cur = rows + W ;
+	// row 0: m[0][j] = j ? -4 - 4j : 0 (AlignAlgo.hpp:120-129)
+	{
+		int wlo = 0 - leftBand - 1 ;
+		for ( int l = 0 ; l < W ; ++l )
+		{
+			j = wlo + l ;
+			prev[l] = ( j == 0 ) ? 0 : ( SCORE_INDEL + j * SCORE_INDEL ) ;
+		}
+	}
+	for ( i = 1 ; i <= lenp ; ++i )
+	{
+		int wlo = i - leftBand - 1 ;
+		int start = ( i - leftBand < 1 ) ? 1 : ( i - leftBand ) ;
+		int end = ( i + rightBand > lent ) ? lent : ( i + rightBand ) ;
+		if ( 0 >= wlo )
+			cur[0 - wlo] = SCORE_INDEL + i * SCORE_INDEL ;
+		if ( start > 1 )
+			cur[start - 1 - wlo] = negInf ;
+		if ( end < lent )
+			cur[end + 1 - wlo] = negInf ;
+		unsigned char *arow = act + (size_t)i * W ;
+		char pc = p[i - 1] ;
+		for ( j = start ; j <= end ; ++j )
+		{
+			int l = j - wlo ;
+			int diff = t4_base_equal( tw + 4 * ( j - 1 ), pc ) ? SCORE_MATCH : SCORE_MISMATCH ;
+			int dg = prev[l] + diff ;          // (i-1, j-1)
+			int lf = cur[l - 1] + SCORE_INDEL ; // (i, j-1)
+			int up = prev[l + 1] + SCORE_INDEL ; // (i-1, j)
+			int score = dg ;
+			if ( lf > score ) score = lf ;
+			if ( up > score ) score = up ;
+			cur[l] = score ;
+			int a = 0 ;
+			if ( lf == score ) a = EDIT_DELETE ;
+			if ( up == score ) a = EDIT_INSERT ;
+			if ( dg == score ) a = ( diff == SCORE_MATCH ) ? EDIT_MATCH : EDIT_MISMATCH ;
+			arow[l] = (unsigned char)a ;
+		}
+		int *t = prev ; prev = cur ; cur = t ;
+	}
+	int ret = prev[lent - ( lenp - leftBand - 1 )] ;
+	// trace back (AlignAlgo.hpp:168-214)
+	int tagi = lenp, tagj = lent, tag = 0 ;
+	while ( tagi > 0 || tagj > 0 )
+	{
+		int a ;
+		if ( tagi > 0 && tagj > 0 )
+			a = act[(size_t)tagi * W + ( tagj - ( tagi - leftBand - 1 ) )] ;
+		else if ( tagj > 0 ) // row 0: m[0][j-1] - 4 == m[0][j] holds iff j >= 2
+			a = ( tagj >= 2 ) ? EDIT_DELETE : EDIT_MATCH ;
+		else // column 0
+			a = ( tagi >= 2 ) ? EDIT_INSERT : EDIT_MATCH ;
+		align[tag] = (signed char)a ;
+		++tag ;
+		if ( a == EDIT_DELETE )
+			--tagj ;
+		else if ( a == EDIT_INSERT )
+			--tagi ;
+		else
+		{
+			--tagi ;
+			--tagj ;
+		}
+	}
+	align[tag] = -1 ;
+	for ( i = 0, j = tag - 1 ; i < j ; ++i, --j )
+	{
+		signed char tmp = align[i] ;
+		align[i] = align[j] ;
+		align[j] = tmp ;
+	}
+	return ret ;
+}
+
+// SeqSet::GetAlignStats (SeqSet.hpp:570)
+T4_HD inline void t4_align_stats( const signed char *align, bool update, int &matchCnt, int &mismatchCnt, int &indelCnt )
+{
+	if ( !update )
+		matchCnt = mismatchCnt = indelCnt = 0 ;
+	for ( int k = 0 ; align[k] != -1 ; ++k )
+	{
+		if ( align[k] == EDIT_MATCH )
+			++matchCnt ;
+		else if ( align[k] == EDIT_MISMATCH )
+			++mismatchCnt ;
+		else
+			++indelCnt ;
+	}
+}
+
+struct T4DpScratch
+{
+	int *rows ;
+	unsigned char *act ;
+	signed char *align ;
+} ;
+
+T4_D inline T4DpScratch t4_dp_scratch( T4Ctx &cx )
+{
+	char *b = cx.P<char>( cx.st->dpOff ) + (size_t)cx.tid * cx.st->dpStride ;
+	T4DpScratch s ;
+	s.rows = (int *)b ;
+	s.act = (unsigned char *)( b + 2 * T4_DP_W * 4 + 8 ) ;
+	s.align = (signed char *)( b + 2 * T4_DP_W * 4 + 8 + ( T4_DEV_MAX_READ + 1 ) * T4_DP_W + 8 ) ;
+	return s ;
+}
+#define T4_DP_STRIDE ( ( 2 * T4_DP_W * 4 + 8 + ( T4_DEV_MAX_READ + 1 ) * T4_DP_W + 8 + 2 * T4_DEV_MAX_READ + 16 + 15 ) & ~15 )
+
+// ---------------------------------------------------------------------------
+// seeds: SeqSet::GetHitsFromRead (SeqSet.hpp:1341-1501), emitted as keys
+// ---------------------------------------------------------------------------
+// Reads cx.sm->read / rc.  Returns the number of keys written to keysA (invalid keys included,
+// they sort last); *nValid receives the number of hits that survive the barcode filter.
+T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool allowTotalSkip, int *anyBig )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	const int k = st->kmerLength ;
+	T4Pos *pos = cx.P<T4Pos>( st->posOff ) ;
+	const int m = len - k + 1 ; // positions per pass, index q = i - (k-1)
+	// directory probes for every k-mer of both strand passes, in parallel.  Whether a probe "counts"
+	// (SeqSet.hpp:1376: first k-mer, or code differs from prevKmerCode) is decided by the serial pass below,
+	// because the reference's `continue` statements skip the prevKmerCode update.
+	for ( int x = cx.tid ; x < 2 * m ; x += cx.nt )
+	{
+		int pass = x >= m ;
+		int q = pass ? x - m : x ;
+		T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+		po->cnt = 0 ;
+		po->listOff = 0 ;
+		po->base = 0xffffffffu ;
+		if ( ( pass == 0 && strand == -1 ) || ( pass == 1 && strand == 1 ) )
+			continue ;
+		const char *r = pass ? sm->rc : sm->read ;
+		u64 code = 0 ;
+		bool valid = true ;
+		for ( int j = 0 ; j < k ; ++j )
+		{
+			char c = r[q + j] ;
+			code = ( code << 2 ) | (u64)t4_nuc( c ) ;
+			if ( c == 'N' )
+				valid = false ;
+		}
+		po->code = code ;
+		if ( valid )
+		{
+			T4Dir *d = t4_dir_find( cx, t4_index_key( st, code, barcode ) ) ;
+			if ( d )
+			{
+				po->cnt = d->cnt ;
+				po->listOff = d->listOff ;
+			}
+		}
+	}
+	T4_SYNC() ;
+	// sequential scan along the read: equal-to-previous rule with the stale prevKmerCode semantics and the
+	// >=100-postings skip rule (SeqSet.hpp:1376-1392, 1441-1455)
+	if ( cx.tid == 0 )
+	{
+		int skipLimit = k / 2 ;
+		u32 total = 0 ;
+		int big = 0 ;
+		u64 lookups = 0, postings = 0 ;
+		u64 prev = 0 ; // KmerCode prevKmerCode( kmerLength ): code 0, carried from the forward into the reverse pass
+		for ( int pass = 0 ; pass < 2 ; ++pass )
+		{
+			if ( ( pass == 0 && strand == -1 ) || ( pass == 1 && strand == 1 ) )
+				continue ;
+			int skipCnt = 0 ;
+			for ( int q = 0 ; q < m ; ++q )
+			{
+				T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+				int i = q + k - 1 ;
+				if ( i == k - 1 || po->code != prev )
+				{
+					++lookups ;
+					int size = po->cnt ;
+					if ( size >= 100 && i != k - 1 && i != len - 1 )
+					{
+						if ( skipCnt < skipLimit )
+						{
+							++skipCnt ;
+							continue ;
+						}
+					}
+					if ( size >= 100 && allowTotalSkip )
+						continue ;
+					skipCnt = 0 ;
+					if ( size > 0 )
+					{
+						po->base = total ;
+						total += size ;
+						postings += size ;
+						if ( barcode == -1 && size > T4_BIG_REPEAT )
+							big = 1 ;
+					}
+				}
+				prev = po->code ;
+			}
+		}
+		sm->bi[0] = (int)total ;
+		sm->bi[1] = big ;
+		t4_atomic_add( &cx.g->counters[2], lookups ) ;
+		t4_atomic_add( &cx.g->counters[3], postings ) ;
+		t4_atomic_add( &cx.g->counters[4], (u64)total ) ;
+		t4_atomic_add( &cx.g->counters[5], (u64)( ( len + 3 ) / 4 ) ) ;
+	}
+	T4_SYNC() ;
+	u32 H = (u32)sm->bi[0] ;
+	*anyBig = sm->bi[1] ;
+	c_ensure_hits( cx, H ) ;
+	if ( st->error )
+		return 0 ;
+	u64 *keys = cx.P<u64>( st->keysAOff ) ;
+	// emit: one lookup after the other, postings spread over the threads (coalesced 8-byte loads)
+	for ( int pass = 0 ; pass < 2 ; ++pass )
+		for ( int q = 0 ; q < m ; ++q )
+		{
+			T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+			u32 base = po->base ;
+			if ( base == 0xffffffffu )
+				continue ;
+			u32 cnt = po->cnt ;
+			const u64 *l = cx.P<u64>( po->listOff ) ;
+			int big = ( barcode == -1 && cnt > T4_BIG_REPEAT ) ;
+			for ( u32 j = cx.tid ; j < cnt ; j += cx.nt )
+			{
+				u64 v = l[j] ;
+				int idx = (int)( v >> 32 ) ;
+				int off = (int)(u32)v ;
+				u64 key = t4_key_of( pass ? -1 : 1, idx, q, off, big ) ;
+				if ( barcode != -1 && t4_seq( cx, idx )->barcode != barcode )
+					key = T4_KEY_INVALID ;
+				keys[base + j] = key ;
+			}
+		}
+	T4_SYNC() ;
+	return H ;
+}
+
+// ---------------------------------------------------------------------------
+// chains: SeqSet::SortHits + GetOverlapsFromHits (SeqSet.hpp:1306, 763-1063) for novel contigs
+// ---------------------------------------------------------------------------
+// For novel contigs adjustRadius is 0 (SeqSet.hpp:902-904), so a candidate is a maximal run of hits on one
+// diagonal; on one diagonal b and a increase together, hence LongestIncreasingSubsequence (SeqSet.hpp:342)
+// returns its input unchanged and the chain IS the run.  GetVJOverlapsFromHits only ever sees isRef hits.
+//
+// keys: sorted, H valid hits.  tmp: spare u64[H].  keysR (may be 0): the same hits sorted in SortHits order
+// (strand, idx, a, b) -- only needed to reproduce the `hits[k].repeats` indexing of SeqSet.hpp:931-947 when
+// some k-mer has more than 10000 postings.
+T4_D inline int c_overlaps_from_hits( T4Ctx &cx, const u64 *keys, u32 H, u64 *tmp, const u64 *keysR, int hitLenRequired,
+	int filter )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	const int k = st->kmerLength ;
+	u32 *grp = cx.P<u32>( st->grpOff ) ;
+	u32 *run = cx.P<u32>( st->runOff ) ;
+	u32 nG = c_heads( cx, keys, H, T4_KEY_IDX_SHIFT, grp ) ;
+	u32 nR = c_heads( cx, keys, H, T4_KEY_C_SHIFT, run ) ;
+	// pre-pass (SeqSet.hpp:781-824), including its group-skipping loop increment
+	if ( cx.tid == 0 )
+	{
+		int novelMin[2] = {3, 3} ;
+		int removeOnlyRepeats[2] = {0, 0} ;
+		if ( filter == 1 )
+		{
+			int possible[2] = {0, 0} ;
+			int longest[2] = {0, 0} ;
+			u32 g = 0 ;
+			u32 i = 0 ;
+			while ( i < H )
+			{
+				while ( grp[g + 1] <= i )
+					++g ;
+				u32 j = grp[g + 1] ;
+				int plus = (int)( keys[i] >> T4_KEY_STRAND_SHIFT ) ;
+				int sz = (int)( j - i ) ;
+				if ( sz > novelMin[plus] )
+					++possible[plus] ;
+				if ( sz > longest[plus] )
+					longest[plus] = sz ;
+				if ( !removeOnlyRepeats[plus] )
+				{
+					int cnt = 0 ;
+					if ( keysR == 0 )
+						cnt = sz ;
+					else
+						for ( u32 x = i ; x < j ; ++x )
+							if ( !t4_key_big( keysR[x] ) )
+								++cnt ;
+					if ( cnt >= novelMin[plus] )
+						removeOnlyRepeats[plus] = 1 ;
+				}
+				i = j + 1 ; // `i = j` followed by the for-loop's ++i (SeqSet.hpp:784, 810)
+			}
+			for ( int s = 0 ; s <= 1 ; ++s )
+			{
+				if ( possible[s] > 100000 )
+					novelMin[s] = (int)( longest[s] * 0.75 ) ;
+				else if ( possible[s] > 10000 )
+					novelMin[s] = longest[s] / 2 ;
+				else if ( possible[s] > 1000 )
+					novelMin[s] = longest[s] / 3 ;
+				else if ( possible[s] > 100 )
+					novelMin[s] = longest[s] / 4 ;
+			}
+		}
+		sm->bi[0] = novelMin[0] ;
+		sm->bi[1] = novelMin[1] ;
+		sm->bi[2] = removeOnlyRepeats[0] ;
+		sm->bi[3] = removeOnlyRepeats[1] ;
+	}
+	T4_SYNC() ;
+	int novelMin[2] = { sm->bi[0], sm->bi[1] } ;
+	int removeOnlyRepeats[2] = { sm->bi[2], sm->bi[3] } ;
+	T4_SYNC() ;
+	// one candidate per diagonal run (SeqSet.hpp:906-1057)
+	for ( u32 r = cx.tid ; r < nR ; r += cx.nt )
+	{
+		u32 s = run[r], e = run[r + 1] ;
+		u64 k0 = keys[s] ;
+		int plus = (int)( k0 >> T4_KEY_STRAND_SHIFT ) ;
+		int minHit = novelMin[plus] ;
+		tmp[r] = 0 ;
+		// group [gi, gj) containing this run
+		u32 lo = 0, hi = nG ;
+		while ( hi - lo > 1 )
+		{
+			u32 mid = ( lo + hi ) / 2 ;
+			if ( grp[mid] <= s )
+				lo = mid ;
+			else
+				hi = mid ;
+		}
+		u32 gi = grp[lo], gj = grp[lo + 1] ;
+		if ( (int)( gj - gi ) < minHit )
+			continue ;
+		if ( removeOnlyRepeats[plus] && keysR != 0 )
+		{
+			bool hasUnique = false ;
+			for ( u32 x = gi ; x < gj ; ++x )
+				if ( !t4_key_big( keysR[x] ) )
+				{
+					hasUnique = true ;
+					break ;
+				}
+			if ( !hasUnique )
+				continue ;
+		}
+		int n = (int)( e - s ) ;
+		if ( n < minHit || n * k < hitLenRequired )
+			continue ;
+		if ( removeOnlyRepeats[plus] && keysR != 0 )
+		{
+			// SeqSet.hpp:931-947 indexes hits[] with the run-local range [s - gi, e - gi)
+			bool hasUnique = false ;
+			for ( u32 x = s - gi ; x < e - gi ; ++x )
+				if ( !t4_key_big( keysR[x] ) )
+				{
+					hasUnique = true ;
+					break ;
+				}
+			if ( !hasUnique )
+				continue ;
+		}
+		if ( n * k < hitLenRequired ) // lisSize * kmerLength (SeqSet.hpp:966)
+			continue ;
+		// GetTotalHitLengthOnRead / OnSeq (SeqSet.hpp:3330, 3352): identical on a single diagonal
+		int hitLen = 0 ;
+		{
+			u32 x = s ;
+			while ( x < e )
+			{
+				u32 y ;
+				int bx = t4_key_b( keys[x] ) ;
+				int last = bx ;
+				for ( y = x + 1 ; y < e ; ++y )
+				{
+					int by = t4_key_b( keys[y] ) ;
+					if ( by > last + k - 1 )
+						break ;
+					last = by ;
+				}
+				hitLen += last - bx + k ;
+				x = y ;
+			}
+		}
+		if ( hitLen < hitLenRequired )
+			continue ;
+		int seqStart = t4_key_b( k0 ) ;
+		int seqEnd = t4_key_b( keys[e - 1] ) + k - 1 ;
+		if ( hitLen * 2 < seqEnd - seqStart + 1 )
+			continue ;
+		tmp[r] = (u64)hitLen ;
+	}
+	T4_SYNC() ;
+	// compact the kept runs, in key order, into overlaps
+	u32 chunk = ( nR + cx.nt - 1 ) / cx.nt ;
+	u32 lo = cx.tid * chunk ;
+	u32 hi = lo + chunk < nR ? lo + chunk : nR ;
+	if ( lo > nR )
+		lo = nR ;
+	u32 c = 0 ;
+	for ( u32 r = lo ; r < hi ; ++r )
+		if ( tmp[r] )
+			++c ;
+	u32 total ;
+	u32 o = c_scan_threads( cx, c, total ) ;
+	c_ensure_ovl( cx, total ) ;
+	if ( st->error )
+		return 0 ;
+	T4Ovl *ovl = cx.P<T4Ovl>( st->ovlOff ) ;
+	for ( u32 r = lo ; r < hi ; ++r )
+	{
+		if ( !tmp[r] )
+			continue ;
+		u32 s = run[r], e = run[r + 1] ;
+		int hitLen = (int)tmp[r] ;
+		T4Ovl no ;
+		no.seqIdx = t4_key_idx( keys[s] ) ;
+		no.readStart = t4_key_a( keys[s] ) ;
+		no.readEnd = t4_key_a( keys[e - 1] ) + k - 1 ;
+		no.strand = t4_key_strand( keys[s] ) ;
+		no.seqStart = t4_key_b( keys[s] ) ;
+		no.seqEnd = t4_key_b( keys[e - 1] ) + k - 1 ;
+		no.matchCnt = 2 * hitLen ;
+		no.indelCnt = 0 ;
+		no.similarity = 0 ;
+		no.hcStart = (int)s ;
+		no.hcCnt = (int)( e - s ) ;
+		no.preMatchCnt = no.matchCnt ;
+		no.infoFromHits = 0 ;
+		ovl[o++] = no ;
+	}
+	T4_SYNC() ;
+	return (int)total ;
+}
+
+// `_overlap::operator<` (SeqSet.hpp:104-128)
+T4_HD inline bool t4_ovl_less( const T4Ovl &a, const T4Ovl &b )
+{
+	if ( a.matchCnt != b.matchCnt )
+		return a.matchCnt > b.matchCnt ;
+	else if ( a.similarity != b.similarity )
+		return a.similarity > b.similarity ;
+	else if ( a.readEnd - a.readStart != b.readEnd - b.readStart )
+		return a.readEnd - a.readStart > b.readEnd - b.readStart ;
+	else if ( a.seqIdx != b.seqIdx )
+		return a.seqIdx < b.seqIdx ;
+	else if ( a.strand != b.strand )
+		return a.strand < b.strand ;
+	else if ( a.readStart != b.readStart )
+		return a.readStart < b.readStart ;
+	else if ( a.readEnd != b.readEnd )
+		return a.readEnd < b.readEnd ;
+	else if ( a.seqStart != b.seqStart )
+		return a.seqStart < b.seqStart ;
+	else
+		return a.seqEnd < b.seqEnd ;
+}
+
+// std::sort( overlaps ) with operator< (a strict total order on distinct overlaps, so any correct sort
+// yields the reference's sequence).  Rank sort: n is small (tens, rarely hundreds).
+T4_D inline void c_sort_overlaps( T4Ctx &cx, int n )
+{
+	if ( n <= 1 )
+		return ;
+	T4Ovl *ovl = cx.P<T4Ovl>( cx.st->ovlOff ) ;
+	T4Ovl *tmp = cx.P<T4Ovl>( cx.st->ovlTmpOff ) ;
+	T4_PAR_FOR( i, n )
+	{
+		T4Ovl me = ovl[i] ;
+		int rank = 0 ;
+		for ( int j = 0 ; j < n ; ++j )
+		{
+			if ( j == i )
+				continue ;
+			if ( t4_ovl_less( ovl[j], me ) || ( j < i && !t4_ovl_less( me, ovl[j] ) ) )
+				++rank ;
+		}
+		tmp[rank] = me ;
+	}
+	T4_SYNC() ;
+	T4_PAR_FOR( i, n )
+		ovl[i] = tmp[i] ;
+	T4_SYNC() ;
+}
+
+// SeqSet::IsOverlapLowComplex (SeqSet.hpp:590)
+T4_D inline bool t4_low_complex( const char *r, const T4Ovl &o )
+{
+	int cnt[4] = {0, 0, 0, 0} ;
+	for ( int i = o.readStart ; i <= o.readEnd ; ++i )
+	{
+		if ( r[i] == 'N' )
+			continue ;
+		++cnt[t4_nuc( r[i] )] ;
+	}
+	int lowCnt = 0, lowTotalCnt = 0 ;
+	for ( int i = 0 ; i < 4 ; ++i )
+		if ( cnt[i] <= 2 )
+		{
+			++lowCnt ;
+			lowTotalCnt += cnt[i] ;
+		}
+	if ( lowTotalCnt * 7 >= o.readEnd - o.readStart + 1 )
+		return false ;
+	return lowCnt >= 2 ;
+}
+
+// ---------------------------------------------------------------------------
+// SeqSet::GetOverlapsFromRead (SeqSet.hpp:1508-2124), readType 0, novel contigs
+// ---------------------------------------------------------------------------
+// Returns the number of overlaps left in ovl[] (-1 when the read is shorter than k).
+T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, bool skipRepeats )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	const int k = st->kmerLength ;
+	if ( len < k )
+		return -1 ;
+	int overlapCnt = 0 ;
+	const u64 *keys = 0 ;
+	for ( int pass = skipRepeats ? 0 : 1 ; pass < 2 && overlapCnt == 0 ; ++pass )
+	{
+		int anyBig = 0 ;
+		u32 H = c_get_hits( cx, len, strand, barcode, pass == 0, &anyBig ) ;
+		if ( st->error )
+			return 0 ;
+		u64 *a = cx.P<u64>( st->keysAOff ) ;
+		u64 *b = cx.P<u64>( st->keysBOff ) ;
+		const u64 *keysR = 0 ;
+		if ( anyBig )
+		{
+			// rare: reproduce SortHits order (strand, idx, a, b) in a second array.  Not supported yet.
+			if ( cx.tid == 0 )
+				t4_raise( cx, T4_E_UNSUPPORTED, 3 ) ;
+			T4_SYNC() ;
+			return 0 ;
+		}
+		u64 *sorted = c_sort_keys( cx, a, b, H ) ;
+		// invalid keys (barcode filter) sorted to the end
+		if ( barcode != -1 )
+		{
+			u32 c = 0 ;
+			for ( u32 i = cx.tid ; i < H ; i += cx.nt )
+				if ( sorted[i] != T4_KEY_INVALID )
+					++c ;
+			u32 total ;
+			c_scan_threads( cx, c, total ) ;
+			H = total ;
+		}
+		keys = sorted ;
+		u64 *tmp = ( sorted == a ) ? b : a ;
+		overlapCnt = c_overlaps_from_hits( cx, sorted, H, tmp, keysR, st->hitLenRequired, pass == 0 ? 0 : 1 ) ;
+		if ( st->error )
+			return 0 ;
+	}
+	if ( overlapCnt == 0 )
+		return 0 ;
+	c_sort_overlaps( cx, overlapCnt ) ;
+	T4Ovl *ovl = cx.P<T4Ovl>( st->ovlOff ) ;
+	// keep the strand of the best overlap (SeqSet.hpp:1601-1616)
+	if ( cx.tid == 0 )
+	{
+		int kk = 1 ;
+		for ( int i = 1 ; i < overlapCnt ; ++i )
+		{
+			if ( ovl[i].strand != ovl[0].strand )
+				continue ;
+			if ( i != kk )
+				ovl[kk] = ovl[i] ;
+			++kk ;
+		}
+		sm->bi[0] = kk ;
+	}
+	T4_SYNC() ;
+	overlapCnt = sm->bi[0] ;
+	T4_SYNC() ;
+	// score every overlap independently (SeqSet.hpp:1832-2020); the order-dependent pre-filters are replayed below
+	T4DpScratch ds = t4_dp_scratch( cx ) ;
+	u64 fullDps = 0 ;
+	T4_PAR_FOR( i, overlapCnt )
+	{
+		T4Ovl &o = ovl[i] ;
+		const char *r = ( o.strand == 1 ) ? sm->read : sm->rc ;
+		const u64 *hc = keys + o.hcStart ;
+		int hitCnt = o.hcCnt ;
+		int matchCnt = 2 * k, mismatchCnt = 0, indelCnt = 0 ;
+		double similarity = 1 ;
+		int *pw = t4_pw( cx, t4_seq( cx, o.seqIdx ) ) ;
+		for ( int j = 1 ; j < hitCnt ; ++j )
+		{
+			int a0 = t4_key_a( hc[j - 1] ), a1 = t4_key_a( hc[j] ) ;
+			int b0 = t4_key_b( hc[j - 1] ) ;
+			// same diagonal always (see c_overlaps_from_hits)
+			if ( a0 + k - 1 >= a1 )
+				matchCnt += 2 * ( a1 - a0 ) ;
+			else
+			{
+				matchCnt += 2 * k ;
+				int gap = a1 - ( a0 + k ) ;
+				if ( gap > st->nomatchGapLimit )
+				{
+					similarity = 0 ;
+					break ;
+				}
+				int full = 0 ;
+				t4_dp_posweight( pw + 4 * ( b0 + k ), gap, r + a0 + k, gap, ds.align, ds.rows, ds.act, &full ) ;
+				fullDps += full ;
+				int cnt0, cnt1, cnt2 ;
+				t4_align_stats( ds.align, false, cnt0, cnt1, cnt2 ) ;
+				matchCnt += 2 * cnt0 ;
+				mismatchCnt += cnt1 ;
+				indelCnt += cnt2 ;
+				if ( indelCnt > 0 )
+				{
+					similarity = 0 ;
+					break ;
+				}
+			}
+		}
+		o.preMatchCnt = o.matchCnt ;
+		o.matchCnt = matchCnt ;
+		o.indelCnt = indelCnt ;
+		if ( similarity == 1 )
+			o.similarity = (double)matchCnt / ( o.seqEnd - o.seqStart + 1 + o.readEnd - o.readStart + 1 ) ;
+		else
+			o.similarity = 0 ;
+		if ( t4_low_complex( r, o ) )
+			o.similarity = 0 ;
+	}
+	if ( fullDps )
+		t4_atomic_add( &cx.g->counters[7], fullDps ) ;
+	t4_atomic_add( &cx.g->counters[6], cx.tid == 0 ? (u64)overlapCnt : 0 ) ;
+	T4_SYNC() ;
+	// sequential replay of the loop's bookkeeping: infoFromHits, bestNovelOverlap pre-filters (only when
+	// overlapCnt > 50), final similarity filter (SeqSet.hpp:1673-1794, 2024-2118)
+	if ( cx.tid == 0 )
+	{
+		int best = -1 ;
+		int radius = st->radius ;
+		for ( int i = 0 ; i < overlapCnt ; ++i )
+		{
+			T4Ovl &o = ovl[i] ;
+			o.infoFromHits = i ;
+			bool filtered = false ;
+			if ( best != -1 && overlapCnt > 50 )
+			{
+				T4Ovl &bo = ovl[best] ;
+				int pm = o.preMatchCnt ;
+				if ( bo.readStart == 0 && bo.readEnd == len - 1 )
+				{
+					if ( bo.similarity == 1 )
+						filtered = true ;
+					else if ( bo.similarity > st->repeatSimilarity && pm < 0.9 * bo.matchCnt )
+						filtered = true ;
+				}
+				if ( !filtered && bo.readStart + len - 1 - bo.readEnd < radius )
+				{
+					if ( bo.similarity == 1 && pm < 0.9 * bo.matchCnt )
+						filtered = true ;
+					else if ( ( bo.similarity > st->repeatSimilarity || st->isLongSeqSet ) && pm < 0.8 * bo.matchCnt )
+						filtered = true ;
+				}
+				if ( !filtered && o.seqStart - o.readStart >= radius
+					&& o.seqEnd + ( len - 1 - o.readEnd ) + radius < t4_seq( cx, o.seqIdx )->len
+					&& bo.matchCnt > 0.97 * ( 2 * len )
+					&& bo.similarity > st->repeatSimilarity
+					&& pm < 0.9 * bo.matchCnt )
+					filtered = true ;
+				if ( !filtered && pm < 0.4 * bo.matchCnt )
+					filtered = true ;
+				if ( !filtered && overlapCnt > 1000 && pm < 0.9 * bo.matchCnt )
+					filtered = true ;
+			}
+			if ( filtered )
+			{
+				o.similarity = 0 ;
+				o.matchCnt = o.preMatchCnt ;
+				o.indelCnt = 0 ;
+				continue ;
+			}
+			if ( o.similarity > 0 )
+			{
+				if ( best == -1 || t4_ovl_less( o, ovl[best] ) )
+					best = i ;
+			}
+		}
+		int kk = 0 ;
+		for ( int i = 0 ; i < overlapCnt ; ++i )
+		{
+			if ( ovl[i].similarity < st->novelSeqSimilarity )
+				continue ;
+			if ( kk != i )
+				ovl[kk] = ovl[i] ;
+			++kk ;
+		}
+		sm->bi[0] = kk ;
+	}
+	T4_SYNC() ;
+	overlapCnt = sm->bi[0] ;
+	T4_SYNC() ;
+	return overlapCnt ;
+}
+
+// ---------------------------------------------------------------------------
+// SeqSet::ExtendOverlap (SeqSet.hpp:1165-1277).  Pure function of (read, contig, overlap).
+// ---------------------------------------------------------------------------
+T4_D inline int t4_extend_overlap( T4Ctx &cx, const char *r, int len, T4Contig *seq, double mismatchThresholdFactor,
+	T4DpScratch &ds, const T4Ovl &overlap, T4Ovl &ext )
+{
+	T4Stream *st = cx.st ;
+	int matchCnt, mismatchCnt, indelCnt ;
+	int leftOverhangSize = t4_min( overlap.readStart, overlap.seqStart ) ;
+	int ret = 1 ;
+	int i, k ;
+	int goodLeftOverhangSize = 0 ;
+	int *pw = t4_pw( cx, seq ) ;
+	signed char *align = ds.align ;
+	t4_dp_posweight( pw + 4 * ( overlap.seqStart - leftOverhangSize ), leftOverhangSize,
+		r + overlap.readStart - leftOverhangSize, leftOverhangSize, align, ds.rows, ds.act, 0 ) ;
+	t4_align_stats( align, false, matchCnt, mismatchCnt, indelCnt ) ;
+	if ( indelCnt > 0 )
+	{
+		leftOverhangSize = 0 ;
+		ret = 0 ;
+	}
+	for ( i = 0 ; align[i] != -1 ; ++i )
+		;
+	int tmpMatchCnt = 0 ;
+	for ( i = i - 1, k = 1 ; i >= 0 ; --i, ++k )
+	{
+		if ( align[i] == EDIT_MATCH )
+		{
+			++tmpMatchCnt ;
+			if ( tmpMatchCnt > 0.75 * k )
+				goodLeftOverhangSize = k ;
+		}
+		else if ( align[i] != EDIT_MISMATCH )
+			break ;
+	}
+	int rightOverhangSize = t4_min( len - 1 - overlap.readEnd, seq->len - 1 - overlap.seqEnd ) ;
+	int goodRightOverhangSize = 0 ;
+	t4_dp_posweight( pw + 4 * ( overlap.seqEnd + 1 ), rightOverhangSize, r + overlap.readEnd + 1, rightOverhangSize, align,
+		ds.rows, ds.act, 0 ) ;
+	int oldIndelCnt = indelCnt ;
+	t4_align_stats( align, true, matchCnt, mismatchCnt, indelCnt ) ;
+	if ( indelCnt > oldIndelCnt )
+	{
+		rightOverhangSize = 0 ;
+		ret = 0 ;
+	}
+	tmpMatchCnt = 0 ;
+	for ( i = 0 ; align[i] != -1 ; ++i )
+	{
+		if ( align[i] == EDIT_MATCH )
+		{
+			++tmpMatchCnt ;
+			if ( tmpMatchCnt > 0.75 * ( i + 1 ) )
+				goodRightOverhangSize = i + 1 ;
+		}
+		else if ( align[i] != EDIT_MISMATCH )
+			break ;
+	}
+	int mismatchThreshold = 2 ;
+	if ( leftOverhangSize >= 2 )
+		++mismatchThreshold ;
+	if ( rightOverhangSize >= 2 )
+		++mismatchThreshold ;
+	double densityThreshold = 1.5 / st->kmerLength ;
+	mismatchThreshold = (int)( mismatchThreshold * mismatchThresholdFactor ) ;
+	if ( mismatchCnt > mismatchThreshold && (double)mismatchCnt / ( leftOverhangSize + rightOverhangSize ) > densityThreshold )
+		ret = 0 ;
+	ext = overlap ;
+	ext.readStart = overlap.readStart - leftOverhangSize ;
+	ext.readEnd = overlap.readEnd + rightOverhangSize ;
+	ext.seqStart = overlap.seqStart - leftOverhangSize ;
+	ext.seqEnd = overlap.seqEnd + rightOverhangSize ;
+	ext.matchCnt = 2 * matchCnt + overlap.matchCnt ;
+	ext.similarity = (double)( 2 * matchCnt + overlap.matchCnt ) /
+		( ext.readEnd - ext.readStart + 1 + ext.seqEnd - ext.seqStart + 1 ) ;
+	// only seqIdx, coordinates, strand, matchCnt, similarity are assigned by the reference; the remaining
+	// fields of the destination keep whatever they held.  None of them is observable afterwards.
+	if ( ext.similarity < st->novelSeqSimilarity )
+	{
+		ext = overlap ;
+		ret = 0 ;
+	}
+	if ( ret == 0 )
+	{
+		ext.readStart = overlap.readStart - goodLeftOverhangSize ;
+		ext.readEnd = overlap.readEnd + goodRightOverhangSize ;
+		ext.seqStart = overlap.seqStart - goodLeftOverhangSize ;
+		ext.seqEnd = overlap.seqEnd + goodRightOverhangSize ;
+	}
+	return ret ;
+}
+
+// ---------------------------------------------------------------------------
+// gene names
+// ---------------------------------------------------------------------------
+// SeqSet::GetChainType (SeqSet.hpp:5132)
+T4_D inline int t4_chain_type( const char *name )
+{
+	if ( name[0] == 'I' )
+	{
+		if ( name[2] == 'H' ) return 0 ;
+		else if ( name[2] == 'K' ) return 1 ;
+		else if ( name[2] == 'L' ) return 2 ;
+	}
+	else if ( name[0] == 'T' )
+	{
+		if ( name[2] == 'A' ) return 3 ;
+		else if ( name[2] == 'B' ) return 4 ;
+		else if ( name[2] == 'G' ) return 5 ;
+		else if ( name[2] == 'D' ) return 6 ;
+	}
+	return 8 ;
+}
+
+// SeqSet::GetGeneType (SeqSet.hpp:5076) on name[0..n)
+T4_D inline int t4_gene_type( const char *name, int n )
+{
+	// the reference reads name[3], name[4] of a NUL-terminated string; positions past the end read as '\0'
+	char c0 = n > 0 ? name[0] : 0, c1 = n > 1 ? name[1] : 0, c3 = n > 3 ? name[3] : 0, c4 = n > 4 ? name[4] : 0 ;
+	if ( c0 == 'N' && c1 == 'o' )
+		return -1 ;
+	switch ( c3 )
+	{
+		case 'V': return 0 ;
+		case 'D': return ( c4 >= '0' && c4 <= '9' ) ? 1 : 3 ;
+		case 'J': return 2 ;
+		case 'L':
+		{
+			char tmp[3] = { c0, c1, n > 2 ? name[2] : (char)0 } ;
+			if ( t4_chain_type( tmp ) == 2 )
+				return -1 ;
+			return 3 ;
+		}
+		default: return 3 ;
+	}
+}
+
+// SeqSet::IsNameCompatible (SeqSet.hpp:3374): b comes after a
+T4_D inline bool t4_name_compatible( const char *a, int na, const char *b, int nb )
+{
+	int maxA = -1, minB = 10 ;
+	int i, j ;
+	for ( i = 0 ; i < na ; )
+	{
+		if ( a[i] == '+' )
+		{
+			++i ;
+			continue ;
+		}
+		for ( j = i ; j < na && a[j] != '+' ; ++j )
+			;
+		int gt = t4_gene_type( a + i, j - i ) ;
+		if ( gt > maxA )
+			maxA = gt ;
+		i = j ;
+	}
+	for ( i = 0 ; i < nb ; )
+	{
+		if ( b[i] == '+' )
+		{
+			++i ;
+			continue ;
+		}
+		for ( j = i ; j < nb && b[j] != '+' ; ++j )
+			;
+		int gt = t4_gene_type( b + i, j - i ) ;
+		if ( gt < minB && gt != -1 )
+			minB = gt ;
+		i = j ;
+	}
+	return maxA <= minB ;
+}
+
+T4_D inline bool t4_name_eq( const char *a, int na, const char *b, int nb )
+{
+	if ( na != nb )
+		return false ;
+	for ( int i = 0 ; i < na ; ++i )
+		if ( a[i] != b[i] )
+			return false ;
+	return true ;
+}
+
+// ---------------------------------------------------------------------------
+// consensus maintenance
+// ---------------------------------------------------------------------------
+// SeqSet::SubstituteConsensusPos (SeqSet.hpp:11058), updateIndex = true
+T4_D inline void s_substitute_consensus_pos( T4Ctx &cx, int seqIdx, int pos, char c )
+{
+	T4Contig *seq = t4_seq( cx, seqIdx ) ;
+	char *cons = t4_cons( cx, seq ) ;
+	if ( pos >= seq->len || cons[pos] == c )
+		return ;
+	int kl = cx.st->kmerLength ;
+	int start = pos - kl + 1 ;
+	int end = pos + kl - 1 ;
+	if ( start < 0 )
+		start = 0 ;
+	if ( end >= seq->len )
+		end = seq->len - 1 ;
+	s_remove_index( cx, cons + start, end - start + 1, seqIdx, seq->barcode, start ) ;
+	cons[pos] = c ;
+	s_build_index( cx, cons + start, end - start + 1, seqIdx, seq->barcode, start ) ;
+}
+
+// SeqSet::UpdateConsensus (SeqSet.hpp:4537-4588).  Serial.
+T4_D inline void s_update_consensus( T4Ctx &cx, int seqIdx, bool updateIndex )
+{
+	T4Contig *seq = t4_seq( cx, seqIdx ) ;
+	char *cons = t4_cons( cx, seq ) ;
+	int *pw = t4_pw( cx, seq ) ;
+	int changes = 0 ;
+	for ( int pass = 0 ; pass < 2 ; ++pass )
+	{
+		// pass 0 counts; pass 1 (after the index removal) applies -- the reference collects a change list first
+		for ( int i = 0 ; i < seq->len ; ++i )
+		{
+			int max = 0, maxTag = 0 ;
+			for ( int j = 0 ; j < 4 ; ++j )
+				if ( pw[4 * i + j] > max )
+				{
+					max = pw[4 * i + j] ;
+					maxTag = j ;
+				}
+			if ( max == 0 )
+				continue ;
+			int cur = t4_nuc( cons[i] ) ;
+			if ( cur != maxTag && pw[4 * i + cur] < max )
+			{
+				if ( pass == 0 )
+					++changes ;
+				else
+					cons[i] = t4_numToNuc( maxTag ) ;
+			}
+		}
+		if ( pass == 0 )
+		{
+			if ( changes == 0 )
+				return ;
+			if ( updateIndex )
+				s_remove_index( cx, cons, seq->len, seqIdx, seq->barcode, 0 ) ;
+		}
+	}
+	if ( updateIndex )
+		s_build_index( cx, cons, seq->len, seqIdx, seq->barcode, 0 ) ;
+}
+
+// SeqSet::UpdateAllConsensus (SeqSet.hpp:4525).  Collective: contigs are scanned in parallel, the rare
+// contigs that change are fixed up serially in slot order.
+T4_D inline void c_update_all_consensus( T4Ctx &cx )
+{
+	T4Stream *st = cx.st ;
+	T4_SYNC() ;
+	// Order matters only through the index multiset, which is order independent; changed contigs are
+	// processed by thread 0 in slot order like the reference.
+	u32 *flag = cx.P<u32>( st->grpOff ) ; // scratch, hitCap + 1 entries; fall back to serial when too small
+	bool useFlags = (u32)st->nSeqs <= st->hitCap ;
+	if ( useFlags )
+	{
+		T4_PAR_FOR( s, st->nSeqs )
+		{
+			T4Contig *seq = t4_seq( cx, s ) ;
+			u32 f = 0 ;
+			if ( seq->consOff != 0 )
+			{
+				const char *cons = t4_cons( cx, seq ) ;
+				const int *pw = t4_pw( cx, seq ) ;
+				for ( int i = 0 ; i < seq->len && !f ; ++i )
+				{
+					int max = 0, maxTag = 0 ;
+					for ( int j = 0 ; j < 4 ; ++j )
+						if ( pw[4 * i + j] > max )
+						{
+							max = pw[4 * i + j] ;
+							maxTag = j ;
+						}
+					if ( max == 0 )
+						continue ;
+					int cur = t4_nuc( cons[i] ) ;
+					if ( cur != maxTag && pw[4 * i + cur] < max )
+						f = 1 ;
+				}
+			}
+			flag[s] = f ;
+		}
+		T4_SYNC() ;
+	}
+	if ( cx.tid == 0 )
+	{
+		for ( int s = 0 ; s < st->nSeqs ; ++s )
+		{
+			if ( t4_seq( cx, s )->consOff == 0 )
+				continue ;
+			if ( useFlags && !flag[s] )
+				continue ;
+			s_update_consensus( cx, s, true ) ;
+		}
+	}
+	T4_SYNC() ;
+}
+
+// SeqSet::Clean(false) + ChangeKmerLength (SeqSet.hpp:4591-4629): compact the slots, rebuild the index.
+// nomatchGapLimit is computed on the host (pow/log) and passed in.
+T4_D inline void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
+{
+	T4Stream *st = cx.st ;
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+	{
+		st->kmerLength = kl ;
+		st->nomatchGapLimit = nomatchGapLimit ;
+		// seqIndex.Clear()
+		T4Dir *dir = cx.P<T4Dir>( st->dirOff ) ;
+		for ( u32 i = 0 ; i < st->dirCap ; ++i )
+			dir[i].key = 0 ;
+		st->dirUsed = 0 ;
+		int k = 0 ;
+		for ( int i = 0 ; i < st->nSeqs ; ++i )
+		{
+			T4Contig *c = t4_seq( cx, i ) ;
+			if ( c->consOff == 0 )
+				continue ;
+			if ( k != i )
+				*t4_seq( cx, k ) = *c ;
+			T4Contig *d = t4_seq( cx, k ) ;
+			s_build_index( cx, t4_cons( cx, d ), d->len, k, d->barcode, 0 ) ;
+			++k ;
+		}
+		t4_set_prev( st, -1, -1, -1, -1, 0 ) ;
+		st->nSeqs = k ;
+	}
+	T4_SYNC() ;
+}
+
+// SeqSet::ComputeNomatchGapLimit (SeqSet.hpp:2476) for the k values the driver can reach
+// (k = 9, 11, 13, 15, 17; main.cpp:1874-1879).  Values computed with the reference's own expression on the
+// host (see t4_api: nomatch_gap_limit()); the device only needs them when the loop changes k by itself.
+T4_D inline int t4_nomatch_gap_limit_table( int kl, const int *table )
+{
+	return table[kl] ;
+}
+
+// ---------------------------------------------------------------------------
+// SeqSet::InputNovelRead (SeqSet.hpp:3028-3073).  Serial; reads cx.sm->read.
+// ---------------------------------------------------------------------------
+T4_D inline int s_input_novel_read( T4Ctx &cx, const char *id, int idLen, int len, int strand, int barcode )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	int seqIdx = s_new_contig( cx, len ) ;
+	if ( seqIdx < 0 )
+		return T4_E_NOMEM ;
+	T4Contig *c = t4_seq( cx, seqIdx ) ;
+	s_set_name( cx, c, id, idLen ) ;
+	char *cons = t4_cons( cx, c ) ;
+	int *pw = t4_pw( cx, c ) ;
+	const char *src = ( strand == -1 ) ? sm->rc : sm->read ;
+	for ( int i = 0 ; i < len ; ++i )
+	{
+		cons[i] = src[i] ;
+		pw[4 * i] = pw[4 * i + 1] = pw[4 * i + 2] = pw[4 * i + 3] = 0 ;
+		if ( src[i] != 'N' )
+			pw[4 * i + t4_nuc( src[i] )] = 1 ;
+	}
+	c->barcode = barcode ;
+	c->numRead = 1 ;
+	s_build_index( cx, cons, len, seqIdx, barcode, 0 ) ;
+	t4_set_prev( st, seqIdx, 0, len - 1, 0, strand ) ;
+	return seqIdx ;
+}
+
+// SeqSet::RepeatAddRead (SeqSet.hpp:4477-4507).  Collective.
+T4_D inline int c_repeat_add_read( T4Ctx &cx, int len )
+{
+	T4Stream *st = cx.st ;
+	if ( st->prevSeqIdx < 0 )
+		return st->prevSeqIdx ;
+	const char *r = ( st->prevStrand == -1 ) ? cx.sm->rc : cx.sm->read ;
+	T4Contig *seq = t4_seq( cx, st->prevSeqIdx ) ;
+	int *pw = t4_pw( cx, seq ) ;
+	for ( int i = st->prevReadStart + cx.tid ; i <= st->prevReadEnd ; i += cx.nt )
+	{
+		if ( r[i] == 'N' )
+			continue ;
+		++pw[4 * ( i + st->prevSeqStart ) + t4_nuc( r[i] )] ;
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+		++seq->numRead ;
+	T4_SYNC() ;
+	return st->prevSeqIdx ;
+}
+
+// ---------------------------------------------------------------------------
+// SeqSet::AddRead (SeqSet.hpp:3426-4473), novel-contig set.  Collective; reads cx.sm->read / rc.
+// ---------------------------------------------------------------------------
+T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &strand, int barcode, int minKmerCount,
+	bool repetitiveData, double similarityThreshold )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	if ( cx.tid == 0 )
+		t4_set_prev( st, -1, -1, -1, -1, 0 ) ;
+	int overlapCnt = c_get_overlaps( cx, len, strand, barcode, repetitiveData ) ;
+	if ( st->error )
+		return st->error ;
+	if ( overlapCnt <= 0 )
+		return -1 ;
+	T4Ovl *overlaps = cx.P<T4Ovl>( st->ovlOff ) ;
+	// gene-name prefix filter (SeqSet.hpp:3445-3472)
+	if ( geneName[0] != '\0' )
+	{
+		if ( cx.tid == 0 )
+		{
+			int k = 0 ;
+			for ( int i = 0 ; i < overlapCnt ; ++i )
+			{
+				T4Contig *c = t4_seq( cx, overlaps[i].seqIdx ) ;
+				const char *nm = cx.P<char>( c->nameOff ) ;
+				int j = 3 ;
+				if ( nm[0] >= 'A' && nm[0] <= 'Z' )
+				{
+					for ( j = 0 ; j < 3 ; ++j )
+						if ( nm[j] != geneName[j] )
+							break ;
+				}
+				if ( j == 3 || t4_name_eq( nm, c->nameLen, "Novel", 5 ) )
+				{
+					if ( k != i )
+						overlaps[k] = overlaps[i] ;
+					++k ;
+				}
+			}
+			sm->bi[0] = k ;
+		}
+		T4_SYNC() ;
+		overlapCnt = sm->bi[0] ;
+		T4_SYNC() ;
+		if ( overlapCnt <= 0 )
+			return -1 ;
+	}
+	c_sort_overlaps( cx, overlapCnt ) ;
+
+	const char *r = ( overlaps[0].strand == 1 ) ? sm->read : sm->rc ;
+	const double factor = ( barcode == -1 && !repetitiveData ) ? 1.0 : 2.0 ;
+	// ExtendOverlap is a pure function of (overlap, read, contig): evaluate it for every overlap up front
+	T4Ovl *pre = cx.P<T4Ovl>( st->extOff ) ;
+	{
+		T4DpScratch ds = t4_dp_scratch( cx ) ;
+		T4_PAR_FOR( i, overlapCnt )
+		{
+			T4Ovl e ;
+			int ok = t4_extend_overlap( cx, r, len, t4_seq( cx, overlaps[i].seqIdx ), factor, ds, overlaps[i], e ) ;
+			e.infoFromHits = ok ; // aux: the return value
+			pre[i] = e ;
+		}
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+	{
+		// ---------------- decision + commit: serial, order dependent ----------------
+		T4Ovl *extendedOverlaps = cx.P<T4Ovl>( st->ovlTmpOff ) ;
+		T4Ovl *failedExtendedOverlaps = cx.P<T4Ovl>( st->failOff ) ;
+		int *oldMinExtAnchor = cx.P<int>( st->anchorOff ) ;
+		const int radius = st->radius ;
+		int i, j, k = 0 ;
+		int ret = -1 ;
+		int failedExtendedOverlapsCnt = 0 ;
+		T4Ovl goodExtendedOverlap ;
+		goodExtendedOverlap.seqIdx = -1 ;
+		int readInConsensusOffset = 0 ;
+		int seqIdx = -1 ;
+		int tag = 0 ;
+		bool sortExtendedOverlaps = true ;
+		bool added = false ;
+		bool bail = false ;
+
+		for ( i = 0 ; i < overlapCnt ; ++i )
+		{
+			T4Contig *seq = t4_seq( cx, overlaps[i].seqIdx ) ;
+			oldMinExtAnchor[2 * i] = seq->minLeftExtAnchor ;
+			oldMinExtAnchor[2 * i + 1] = seq->minRightExtAnchor ;
+			for ( j = 0 ; j < k ; ++j )
+			{
+				int leftRadius = radius, rightRadius = radius ;
+				if ( extendedOverlaps[j].seqStart == 0 )
+					leftRadius = 0 ;
+				if ( extendedOverlaps[j].seqEnd == t4_seq( cx, extendedOverlaps[j].seqIdx )->len - 1 )
+					rightRadius = 0 ;
+				if ( overlaps[i].readStart >= extendedOverlaps[j].readStart - leftRadius
+					&& overlaps[i].readEnd <= extendedOverlaps[j].readEnd + rightRadius
+					&& ( overlaps[i].seqStart >= radius || overlaps[i].seqEnd <= seq->len - radius - 1 ) )
+					break ;
+				leftRadius = radius ;
+				rightRadius = radius ;
+				if ( overlaps[i].seqStart == 0 )
+					leftRadius = 0 ;
+				if ( overlaps[i].seqEnd == seq->len - 1 )
+					rightRadius = 0 ;
+				if ( extendedOverlaps[j].readStart >= overlaps[i].readStart - leftRadius
+					&& extendedOverlaps[j].readEnd <= overlaps[i].readEnd + rightRadius )
+					break ;
+			}
+			if ( j < k )
+				continue ;
+			extendedOverlaps[k] = pre[i] ;
+			if ( pre[i].infoFromHits == 1 )
+			{
+				T4Ovl &eo = extendedOverlaps[k] ;
+				if ( eo.similarity < similarityThreshold )
+				{
+					if ( ( minKmerCount <= 1 || eo.similarity + 0.01 >= similarityThreshold ) && eo.readStart == 0
+						&& eo.readEnd == len - 1 )
+						goodExtendedOverlap = eo ;
+					continue ;
+				}
+				for ( j = 0 ; j < k ; ++j )
+				{
+					int leftRadius = radius, rightRadius = radius ;
+					if ( extendedOverlaps[j].seqStart == 0 )
+						leftRadius = 0 ;
+					if ( extendedOverlaps[j].seqEnd == t4_seq( cx, extendedOverlaps[j].seqIdx )->len - 1 )
+						rightRadius = 0 ;
+					if ( eo.readStart >= extendedOverlaps[j].readStart - leftRadius
+						&& eo.readEnd <= extendedOverlaps[j].readEnd + rightRadius
+						&& ( overlaps[i].seqStart > 0 || overlaps[i].seqEnd < seq->len - 1 ) )
+						break ;
+					if ( extendedOverlaps[j].readStart >= eo.readStart - radius && extendedOverlaps[j].readEnd <= eo.readEnd + radius )
+						break ;
+				}
+				if ( j < k )
+					continue ;
+				T4Contig *eseq = t4_seq( cx, eo.seqIdx ) ;
+				int span = eo.readEnd - eo.readStart + 1 ;
+				for ( j = 0 ; j < i ; ++j )
+				{
+					if ( eo.seqStart == 0 && eo.seqEnd == eseq->len - 1 )
+						continue ;
+					if ( eo.readStart >= overlaps[j].readStart && eo.readEnd <= overlaps[j].readEnd
+						&& ( overlaps[j].readEnd - overlaps[j].readStart >= eo.readEnd - eo.readStart + 10
+							|| overlaps[j].similarity + 0.02 >= eo.similarity ) )
+					{
+						if ( eo.readStart > 0 && eseq->minLeftExtAnchor < span )
+							eseq->minLeftExtAnchor = span ;
+						if ( eo.readEnd < len - 1 && eseq->minRightExtAnchor < span )
+							eseq->minRightExtAnchor = span ;
+						break ;
+					}
+				}
+				if ( j < i )
+					continue ;
+				for ( j = 0 ; j < failedExtendedOverlapsCnt ; ++j )
+				{
+					if ( eo.seqStart == 0 && eo.seqEnd == eseq->len - 1 )
+						continue ;
+					if ( eo.readStart >= failedExtendedOverlaps[j].readStart && eo.readEnd <= failedExtendedOverlaps[j].readEnd )
+					{
+						if ( eo.readStart > 0 && eseq->minLeftExtAnchor < span )
+							eseq->minLeftExtAnchor = span ;
+						if ( eo.readEnd < len - 1 && eseq->minRightExtAnchor < span )
+							eseq->minRightExtAnchor = span ;
+						break ;
+					}
+				}
+				if ( j < failedExtendedOverlapsCnt )
+					continue ;
+				if ( eo.readStart > 0 && eseq->minLeftExtAnchor >= span )
+					continue ;
+				if ( eo.readEnd < len - 1 && eseq->minRightExtAnchor >= span )
+					continue ;
+				tag = i ;
+				++k ;
+			}
+			else
+			{
+				failedExtendedOverlaps[failedExtendedOverlapsCnt] = extendedOverlaps[k] ;
+				++failedExtendedOverlapsCnt ;
+			}
+		}
+
+		if ( k == 1 && extendedOverlaps[0].readStart <= radius && extendedOverlaps[0].readEnd >= len - radius )
+		{
+			// could the read bridge to a second contig? (SeqSet.hpp:3732-3793)
+			for ( i = 0 ; i < overlapCnt ; ++i )
+			{
+				if ( tag == i )
+					continue ;
+				extendedOverlaps[k] = pre[i] ;
+				if ( pre[i].infoFromHits == 1 )
+				{
+					j = i ;
+					++k ;
+				}
+			}
+			if ( k > 2 )
+				k = 1 ;
+			else if ( k == 2 )
+			{
+				int span = extendedOverlaps[1].readEnd - extendedOverlaps[1].readStart + 1 ;
+				if ( extendedOverlaps[1].readStart > 0 && oldMinExtAnchor[2 * j] >= span )
+					k = 1 ;
+				if ( extendedOverlaps[1].readEnd < len - 1 && oldMinExtAnchor[2 * j + 1] >= span )
+					k = 1 ;
+				if ( k == 2 )
+				{
+					if ( extendedOverlaps[0].seqEnd == t4_seq( cx, extendedOverlaps[0].seqIdx )->len - 1
+						&& extendedOverlaps[1].seqStart == 0 )
+						sortExtendedOverlaps = false ;
+					else if ( extendedOverlaps[0].seqStart == 0
+						&& extendedOverlaps[1].seqEnd == t4_seq( cx, extendedOverlaps[1].seqIdx )->len - 1 )
+					{
+						sortExtendedOverlaps = false ;
+						T4Ovl tmp = extendedOverlaps[0] ;
+						extendedOverlaps[0] = extendedOverlaps[1] ;
+						extendedOverlaps[1] = tmp ;
+					}
+					else
+						k = 1 ;
+				}
+			}
+		}
+
+		if ( similarityThreshold > st->novelSeqSimilarity )
+		{
+			int cnt = 0 ;
+			for ( i = 0 ; i < k ; ++i )
+				if ( extendedOverlaps[i].similarity >= similarityThreshold )
+				{
+					extendedOverlaps[cnt] = extendedOverlaps[i] ;
+					++cnt ;
+				}
+			k = cnt ;
+		}
+		if ( k == 0 && goodExtendedOverlap.seqIdx != -1 )
+		{
+			extendedOverlaps[0] = goodExtendedOverlap ;
+			k = 1 ;
+		}
+		if ( k > 1 )
+		{
+			for ( i = 0 ; i < k ; ++i )
+				if ( extendedOverlaps[i].similarity >= 0.95 )
+					break ;
+			if ( i >= k )
+			{
+				int maxtag = 0 ;
+				for ( i = 1 ; i < k ; ++i )
+					if ( t4_ovl_less( extendedOverlaps[i], extendedOverlaps[maxtag] ) )
+						maxtag = i ;
+				extendedOverlaps[0] = extendedOverlaps[maxtag] ;
+				k = 1 ;
+			}
+		}
+		if ( k > 1 )
+		{
+			for ( i = 0 ; i < k - 1 ; ++i )
+				for ( j = i + 1 ; j < k ; ++j )
+					if ( extendedOverlaps[i].seqIdx == extendedOverlaps[j].seqIdx )
+					{
+						k = 0 ;
+						break ;
+					}
+		}
+
+		if ( k > 1 )
+		{
+			// ------------- merge contigs (SeqSet.hpp:3878-4130) -------------
+			int eOverlapCnt = k ;
+			added = true ;
+			if ( sortExtendedOverlaps )
+			{
+				// std::sort by readStart only; equal keys would make the order implementation defined, so keep the
+				// sort stable and flag ties (they need differing contigs with equal extended read starts)
+				for ( i = 1 ; i < eOverlapCnt ; ++i )
+				{
+					T4Ovl x = extendedOverlaps[i] ;
+					for ( j = i - 1 ; j >= 0 && extendedOverlaps[j].readStart > x.readStart ; --j )
+						extendedOverlaps[j + 1] = extendedOverlaps[j] ;
+					extendedOverlaps[j + 1] = x ;
+				}
+			}
+			for ( i = 0 ; i < k && !bail ; ++i )
+				for ( j = i + 1 ; j < k ; ++j )
+				{
+					T4Contig *ca = t4_seq( cx, extendedOverlaps[i].seqIdx ) ;
+					T4Contig *cb = t4_seq( cx, extendedOverlaps[j].seqIdx ) ;
+					if ( !t4_name_compatible( cx.P<char>( ca->nameOff ), ca->nameLen, cx.P<char>( cb->nameOff ), cb->nameLen ) )
+					{
+						bail = true ;
+						break ;
+					}
+				}
+			if ( bail )
+				ret = -1 ;
+			else
+			{
+				int sum = 0 ;
+				for ( i = 0 ; i < eOverlapCnt ; ++i )
+					sum += t4_seq( cx, extendedOverlaps[i].seqIdx )->len ;
+				// positions of the contigs in the merged contig; extOff (pre[]) is free from here on
+				int *seqOffset = (int *)pre ;
+				if ( extendedOverlaps[0].readStart > 0 )
+				{
+					for ( i = 0 ; i < eOverlapCnt ; ++i )
+						seqOffset[i] = extendedOverlaps[i].readStart ;
+				}
+				else
+				{
+					seqOffset[0] = 0 ;
+					for ( i = 1 ; i < eOverlapCnt ; ++i )
+						seqOffset[i] = seqOffset[i - 1] + t4_seq( cx, extendedOverlaps[i - 1].seqIdx )->len - 1
+							+ ( extendedOverlaps[i].readStart - extendedOverlaps[i - 1].readEnd ) ;
+				}
+				u64 ncOff = s_alloc( cx, (u64)( sum + len + 1 ) + 16 ) ;
+				if ( ncOff )
+				{
+					char *newConsensus = cx.P<char>( ncOff ) ;
+					if ( extendedOverlaps[0].readStart > 0 )
+						memcpy( newConsensus, r, len ) ;
+					else
+						memcpy( newConsensus + extendedOverlaps[0].seqStart, r, len ) ;
+					for ( i = eOverlapCnt - 1 ; i >= 0 ; --i )
+					{
+						T4Contig *c = t4_seq( cx, extendedOverlaps[i].seqIdx ) ;
+						memcpy( newConsensus + seqOffset[i], t4_cons( cx, c ), c->len ) ;
+					}
+					int newConsensusLen = 0 ;
+					int lastEndExtendedOverlapIdx = eOverlapCnt - 1 ;
+					k = 0 ;
+					for ( i = 0 ; i < eOverlapCnt ; ++i )
+					{
+						int e = seqOffset[i] + t4_seq( cx, extendedOverlaps[i].seqIdx )->len ;
+						if ( e > k )
+						{
+							k = e ;
+							lastEndExtendedOverlapIdx = i ;
+						}
+					}
+					if ( extendedOverlaps[lastEndExtendedOverlapIdx].readEnd < len )
+						newConsensusLen = k + ( len - extendedOverlaps[lastEndExtendedOverlapIdx].readEnd - 1 ) ;
+					else
+						newConsensusLen = k ;
+
+					int newSeqIdx = extendedOverlaps[0].seqIdx ;
+					k = 0 ;
+					for ( i = 1 ; i < eOverlapCnt ; ++i )
+						if ( extendedOverlaps[i].seqIdx < newSeqIdx )
+						{
+							newSeqIdx = extendedOverlaps[i].seqIdx ;
+							k = i ;
+						}
+					// index removal uses the OLD consensus of every participant
+					for ( i = 0 ; i < eOverlapCnt ; ++i )
+					{
+						T4Contig *c = t4_seq( cx, extendedOverlaps[i].seqIdx ) ;
+						s_remove_index( cx, t4_cons( cx, c ), c->len, extendedOverlaps[i].seqIdx, barcode, 0 ) ;
+					}
+					// new posWeight: old columns of newSeqIdx shifted by seqOffset[k], zero elsewhere, plus the others
+					T4Contig *ns = t4_seq( cx, newSeqIdx ) ;
+					int oldLen = ns->len ;
+					int cap = 2 * newConsensusLen + 128 ;
+					u64 co = s_alloc( cx, cap ) ;
+					u64 po = s_alloc( cx, (u64)cap * 16 ) ;
+					if ( co && po )
+					{
+						int lead = ( cap - newConsensusLen ) / 2 ;
+						int *npw = cx.P<int>( po ) + 4 * lead ;
+						int *opw = t4_pw( cx, ns ) ;
+						for ( i = 0 ; i < 4 * newConsensusLen ; ++i )
+							npw[i] = 0 ;
+						for ( i = 0 ; i < 4 * oldLen ; ++i )
+							npw[4 * seqOffset[k] + i] = opw[i] ;
+						for ( i = 0 ; i < eOverlapCnt ; ++i )
+						{
+							int sIdx = extendedOverlaps[i].seqIdx ;
+							if ( sIdx == newSeqIdx )
+								continue ;
+							T4Contig *c = t4_seq( cx, sIdx ) ;
+							ns->numRead += c->numRead ;
+							int *cpw = t4_pw( cx, c ) ;
+							for ( j = 0 ; j < 4 * c->len ; ++j )
+								npw[4 * seqOffset[i] + j] += cpw[j] ;
+						}
+						// name (SeqSet.hpp:4066-4096)
+						int nameIdx ;
+						for ( nameIdx = 0 ; nameIdx < eOverlapCnt ; ++nameIdx )
+						{
+							T4Contig *c = t4_seq( cx, extendedOverlaps[nameIdx].seqIdx ) ;
+							if ( !t4_name_eq( cx.P<char>( c->nameOff ), c->nameLen, "Novel", 5 ) )
+								break ;
+						}
+						if ( nameIdx >= eOverlapCnt )
+							nameIdx = 0 ;
+						int nameSum = 0 ;
+						for ( i = 0 ; i < eOverlapCnt ; ++i )
+							nameSum += t4_seq( cx, extendedOverlaps[i].seqIdx )->nameLen ;
+						u64 nbOff = s_alloc( cx, nameSum + eOverlapCnt + 1 ) ;
+						if ( nbOff )
+						{
+							char *nameBuffer = cx.P<char>( nbOff ) ;
+							T4Contig *c0 = t4_seq( cx, extendedOverlaps[nameIdx].seqIdx ) ;
+							memcpy( nameBuffer, cx.P<char>( c0->nameOff ), c0->nameLen ) ;
+							int nl = c0->nameLen ;
+							for ( i = 0 ; i < eOverlapCnt ; ++i )
+							{
+								if ( i == nameIdx )
+									continue ;
+								if ( i > 0 )
+								{
+									T4Contig *ci = t4_seq( cx, extendedOverlaps[i].seqIdx ) ;
+									T4Contig *cp = t4_seq( cx, extendedOverlaps[i - 1].seqIdx ) ;
+									if ( !t4_name_eq( cx.P<char>( ci->nameOff ), ci->nameLen, cx.P<char>( cp->nameOff ), cp->nameLen ) )
+									{
+										nameBuffer[nl] = '+' ;
+										memcpy( nameBuffer + nl + 1, cx.P<char>( ci->nameOff ), ci->nameLen ) ;
+										nl += 1 + ci->nameLen ;
+									}
+								}
+							}
+							nameBuffer[nl] = '\0' ;
+							int minLeft = t4_seq( cx, extendedOverlaps[0].seqIdx )->minLeftExtAnchor ;
+							int minRight = t4_seq( cx, extendedOverlaps[lastEndExtendedOverlapIdx].seqIdx )->minRightExtAnchor ;
+							// release the merged-away contigs (SeqSet::ReleaseSeq: the slot stays, NULL consensus)
+							for ( i = 0 ; i < eOverlapCnt ; ++i )
+							{
+								int sIdx = extendedOverlaps[i].seqIdx ;
+								if ( sIdx == newSeqIdx )
+									continue ;
+								T4Contig *c = t4_seq( cx, sIdx ) ;
+								c->consOff = 0 ;
+								c->pwOff = 0 ;
+								c->nameOff = 0 ;
+								c->len = 0 ;
+							}
+							ns->nameOff = nbOff ;
+							ns->nameLen = nl ;
+							ns->consOff = co ;
+							ns->pwOff = po ;
+							ns->cap = cap ;
+							ns->lead = lead ;
+							ns->len = newConsensusLen ;
+							memcpy( t4_cons( cx, ns ), newConsensus, newConsensusLen ) ;
+							s_update_consensus( cx, newSeqIdx, false ) ;
+							s_build_index( cx, t4_cons( cx, ns ), newConsensusLen, newSeqIdx, barcode, 0 ) ;
+							ns->minLeftExtAnchor = minLeft ;
+							ns->minRightExtAnchor = minRight ;
+							readInConsensusOffset = 0 ;
+							if ( extendedOverlaps[0].seqStart > 0 )
+								readInConsensusOffset = extendedOverlaps[0].seqStart ;
+							seqIdx = newSeqIdx ;
+						}
+					}
+				}
+			}
+		}
+		else if ( k == 1 )
+		{
+			// ------------- extend / inside a contig (SeqSet.hpp:4131-4316) -------------
+			added = true ;
+			const T4Ovl e0 = extendedOverlaps[0] ;
+			seqIdx = e0.seqIdx ;
+			T4Contig *seq = t4_seq( cx, seqIdx ) ;
+			++seq->numRead ;
+			if ( e0.readStart > 0 || e0.readEnd < len - 1 )
+			{
+				int shift = e0.readStart ;
+				int rightAdd = ( e0.readEnd < len - 1 ) ? ( len - 1 - e0.readEnd ) : 0 ;
+				int oldLen = seq->len ;
+				// index first, exactly in the reference's order: new left k-mers, shift old postings, new right k-mers.
+				// The old consensus is still in place; build the (short) new flanks in a temporary buffer.
+				char *oldCons = t4_cons( cx, seq ) ;
+				int kl = st->kmerLength ;
+				if ( shift > 0 )
+				{
+					// newConsensus[0 .. shift + kl - 1) = read prefix + first kl-1 old bases
+					char *tmpc = (char *)pre ; // scratch
+					int n = shift + kl - 1 ;
+					for ( i = 0 ; i < n ; ++i )
+						tmpc[i] = ( i < shift ) ? r[i] : ( ( i - shift < oldLen ) ? oldCons[i - shift] : '\0' ) ;
+					// BuildIndexFromRead(newConsensus, readStart + k - 1) -- if the old contig is shorter than k-1 the reference
+					// reads into the appended right part; mirror that
+					for ( i = shift + oldLen ; i < n ; ++i )
+					{
+						int ri = e0.readEnd + 1 + ( i - shift - oldLen ) ;
+						tmpc[i] = ( ri < len ) ? r[ri] : '\0' ;
+					}
+					s_build_index( cx, tmpc, n, seqIdx, barcode, 0 ) ;
+					s_update_index( cx, oldCons, oldLen, barcode, shift, seqIdx, seqIdx ) ;
+				}
+				if ( !s_contig_grow( cx, seq, shift, rightAdd ) )
+				{
+					ret = T4_E_NOMEM ;
+					bail = true ;
+				}
+				else
+				{
+					char *newConsensus = t4_cons( cx, seq ) ;
+					int *pw = t4_pw( cx, seq ) ;
+					int newConsensusLen = seq->len ;
+					for ( i = 0 ; i < shift ; ++i )
+						newConsensus[i] = r[i] ;
+					for ( i = e0.readEnd + 1, j = shift + oldLen ; i < len ; ++i, ++j )
+						newConsensus[j] = r[i] ;
+					if ( e0.readEnd < len - 1 )
+					{
+						int start = e0.readStart + e0.seqEnd - kl + 2 ;
+						if ( start < 0 )
+						{
+							// contig shorter than k-2: pointer before the buffer in the reference; never seen
+							t4_raise( cx, T4_E_INTERNAL, 11 ) ;
+							start = 0 ;
+						}
+						s_build_index( cx, newConsensus + start, newConsensusLen - start, seqIdx, barcode, start ) ;
+					}
+					// posWeight: old columns already sit at [shift, shift + oldLen)
+					int nrep = 0 ;
+					int repPos[4] ;
+					char repChar[4] ;
+					if ( shift > 0 )
+					{
+						if ( barcode == -1 || minKmerCount > 1 )
+						{
+							for ( i = 0 ; i < 2 ; ++i )
+							{
+								if ( i + shift >= len || r[i + shift] == 'N' )
+									continue ;
+								char nc = newConsensus[i + shift] ;
+								if ( r[i + shift] != nc && nc != 'N' && pw[4 * ( i + shift ) + t4_nuc( nc )] == 1 )
+								{
+									repPos[nrep] = i + shift ;
+									repChar[nrep] = r[i + shift] ;
+									++nrep ;
+								}
+								for ( j = 0 ; j < 4 ; ++j )
+									if ( r[i + shift] != t4_numToNuc( j ) && pw[4 * ( i + shift ) + j] > 1 )
+										--pw[4 * ( i + shift ) + j] ;
+							}
+						}
+						for ( i = 0 ; i < 4 * shift ; ++i )
+							pw[i] = 0 ;
+					}
+					if ( e0.readEnd < len - 1 )
+					{
+						int start = e0.readStart + oldLen ;
+						for ( i = 4 * start ; i < 4 * ( start + len - e0.readEnd - 1 ) ; ++i )
+							pw[i] = 0 ;
+						if ( barcode == -1 || minKmerCount > 1 )
+						{
+							for ( i = oldLen - 2 ; i < oldLen ; ++i )
+							{
+								int pos = i - e0.seqStart ;
+								int seqPos = i + shift ;
+								if ( pos < 0 || r[pos] == 'N' )
+									continue ;
+								if ( i < 0 )
+								{
+									t4_raise( cx, T4_E_INTERNAL, 12 ) ;
+									continue ;
+								}
+								char nc = newConsensus[seqPos] ;
+								if ( r[pos] != nc && nc != 'N' && pw[4 * seqPos + t4_nuc( nc )] == 1 )
+								{
+									repPos[nrep] = seqPos ;
+									repChar[nrep] = r[pos] ;
+									++nrep ;
+								}
+								for ( j = 0 ; j < 4 ; ++j )
+									if ( r[pos] != t4_numToNuc( j ) && pw[4 * seqPos + j] > 1 )
+										--pw[4 * seqPos + j] ;
+							}
+						}
+					}
+					if ( shift > 0 )
+						seq->minLeftExtAnchor = 0 ;
+					if ( e0.readEnd < len - 1 )
+						seq->minRightExtAnchor = 0 ;
+					// (the +GENE name adjustment needs isRef overlaps: never in the stage-1 novel set, SeqSet.hpp:4258-4296)
+					readInConsensusOffset = 0 ;
+					if ( e0.seqStart > 0 )
+						readInConsensusOffset = e0.seqStart ;
+					for ( i = 0 ; i < nrep ; ++i )
+						s_substitute_consensus_pos( cx, seqIdx, repPos[i], repChar[i] ) ;
+				}
+			}
+			else
+				readInConsensusOffset = e0.seqStart ;
+		}
+
+		// ------------- posWeight update (SeqSet.hpp:4318-4363) -------------
+		if ( added && !bail && seqIdx >= 0 && !st->error )
+		{
+			T4Contig *seq = t4_seq( cx, seqIdx ) ;
+			char *cons = t4_cons( cx, seq ) ;
+			int *pw = t4_pw( cx, seq ) ;
+			int kl = st->kmerLength ;
+			int *nPos = (int *)pre ;
+			int size = 0 ;
+			for ( i = 0 ; i < len ; ++i )
+			{
+				if ( r[i] == 'N' )
+					continue ;
+				++pw[4 * ( i + readInConsensusOffset ) + t4_nuc( r[i] )] ;
+				if ( cons[i + readInConsensusOffset] == 'N' )
+					nPos[size++] = i ;
+			}
+			t4_set_prev( st, seqIdx, 0, len - 1, readInConsensusOffset, overlaps[0].strand ) ;
+			for ( i = 0 ; i < size ; )
+			{
+				for ( j = i + 1 ; j < size ; ++j )
+					if ( nPos[j] > nPos[j - 1] + kl - 1 )
+						break ;
+				for ( int l = i ; l < j ; ++l )
+					cons[nPos[l] + readInConsensusOffset] = r[nPos[l]] ;
+				int start = nPos[i] - kl + 1 + readInConsensusOffset ;
+				if ( start < 0 )
+					start = 0 ;
+				int end = nPos[j - 1] + kl - 1 + readInConsensusOffset ;
+				if ( end >= seq->len )
+					end = seq->len - 1 ;
+				s_build_index( cx, cons + start, end - start + 1, seqIdx, barcode, start ) ;
+				i = j ;
+			}
+			ret = seqIdx ;
+		}
+		// addNew is only kept for isRef overlaps (SeqSet.hpp:4377-4391): never in the novel set
+		if ( ret == -1 && !bail )
+		{
+			t4_set_prev( st, -2, -1, -1, -1, 0 ) ;
+			ret = -2 ;
+		}
+		sm->bi[0] = ret ;
+		sm->bi[1] = ( ret >= 0 && strand == 0 ) ? overlaps[0].strand : strand ;
+	}
+	T4_SYNC() ;
+	int ret = sm->bi[0] ;
+	strand = sm->bi[1] ;
+	T4_SYNC() ;
+	if ( st->error )
+		return st->error ;
+	return ret ;
+}
+
+// ---------------------------------------------------------------------------
+// loading a read into shared memory
+// ---------------------------------------------------------------------------
+T4_D inline void c_load_read( T4Ctx &cx, const char *src, int len )
+{
+	T4Smem *sm = cx.sm ;
+	T4_SYNC() ;
+	T4_PAR_FOR( i, len )
+	{
+		char c = src[i] ;
+		sm->read[i] = c ;
+		sm->rc[len - 1 - i] = ( c != 'N' ) ? t4_numToNuc( 3 - t4_nuc( c ) ) : 'N' ;
+	}
+	if ( cx.tid == 0 )
+	{
+		sm->read[len] = '\0' ;
+		sm->rc[len] = '\0' ;
+	}
+	T4_SYNC() ;
+}
+
+// ---------------------------------------------------------------------------
+// the stage-1 driver loop (main.cpp:1583-1881) and rescue pass (main.cpp:1897-1940) over read descriptors
+// ---------------------------------------------------------------------------
+T4_D inline double t4_rescue_threshold( int minCnt )
+{
+	double t = 0.9 ;
+	if ( minCnt >= 20 )
+		t = 0.97 ;
+	else if ( minCnt >= 2 )
+		t = 0.95 ;
+	return t ;
+}
+
+T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	const t4_read_desc *descs = t4_x<t4_read_desc>( op->desc ) ;
+	const char *pool = t4_x<char>( op->pool ) ;
+	T4Names *names = t4_x<T4Names>( op->names ) ;
+	const char *namePool = t4_x<char>( names->pool ) ;
+	const u32 *nameOff = t4_x<u32>( names->off ) ;
+	int32_t *retCodes = t4_x<int32_t>( op->retCodes ) ;
+	int8_t *strands = t4_x<int8_t>( op->strands ) ;
+	int32_t *rescueRet = t4_x<int32_t>( op->rescueRet ) ;
+	int32_t *rescueList = t4_x<int32_t>( op->rescueList ) ;
+	int8_t *goodCandidate = t4_x<int8_t>( op->good ) ;
+	int32_t *info = t4_x<int32_t>( op->info ) ;
+	const t4_run_cfg cfg = op->cfg ;
+	const int n = op->n ;
+	T4_PAR_FOR( i, n )
+	{
+		goodCandidate[i] = 0 ;
+		info[i] = -1 ;
+		rescueRet[i] = INT32_MIN ;
+	}
+	T4_SYNC() ;
+	int assembledReadCnt = 0 ;
+	int prevAddRet = -1 ;
+	int indexKmerLength = st->kmerLength ;
+	int changeKmerLengthThreshold = cfg.change_k_threshold ;
+	int rescueCnt = 0 ;
+	for ( int i = 0 ; i < n && !st->error ; ++i )
+	{
+		const t4_read_desc d = descs[i] ;
+		int addRet = -1 ;
+		if ( d.len > T4_DEV_MAX_READ || d.len < 0 )
+		{
+			if ( cx.tid == 0 )
+				t4_raise( cx, T4_E_UNSUPPORTED, 4 ) ;
+			T4_SYNC() ;
+			break ;
+		}
+		c_load_read( cx, pool + d.seq_off, d.len ) ;
+		int finalStrand = 0 ;
+		if ( !( d.flags & T4_RD_DUP ) )
+		{
+			int strand = 0 ;
+			if ( !( d.flags & T4_RD_FILTERED ) )
+			{
+				char name[5] ;
+				name[0] = d.gene4[0] ; name[1] = d.gene4[1] ; name[2] = d.gene4[2] ; name[3] = d.gene4[3] ; name[4] = '\0' ;
+				strand = d.strand_in ;
+				addRet = c_add_read( cx, d.len, name, strand, d.barcode, d.min_kmer_count, cfg.repetitive != 0, d.sim_threshold ) ;
+				if ( st->error )
+					break ;
+				if ( addRet < 0 )
+				{
+					int novelStrand = 0 ;
+					const char *nm = 0 ;
+					int nmLen = 0 ;
+					if ( d.flags & T4_RD_NOVEL_ON_FAIL )
+					{
+						novelStrand = d.novel_strand ;
+						nm = namePool + nameOff[d.name_id] ;
+						nmLen = (int)( nameOff[d.name_id + 1] - nameOff[d.name_id] ) ;
+					}
+					else if ( d.flags & T4_RD_MOTIF_FORCED )
+					{
+						if ( d.novel_strand != 0 && ( d.flags & T4_RD_MOTIF ) )
+						{
+							novelStrand = d.novel_strand ;
+							nm = "Novel" ;
+							nmLen = 5 ;
+						}
+					}
+					else if ( goodCandidate[i] )
+					{
+						int ms = -strands[info[i]] ;
+						if ( ms != 0 && ( d.flags & T4_RD_MOTIF ) )
+						{
+							novelStrand = ms ;
+							nm = "Novel" ;
+							nmLen = 5 ;
+						}
+					}
+					if ( nm != 0 )
+					{
+						if ( cx.tid == 0 )
+							sm->bi[0] = s_input_novel_read( cx, nm, nmLen, d.len, novelStrand, d.barcode ) ;
+						T4_SYNC() ;
+						addRet = sm->bi[0] ;
+						T4_SYNC() ;
+					}
+				}
+			}
+			finalStrand = ( d.flags & T4_RD_FILTERED ) ? 0 : strand ;
+		}
+		else
+		{
+			if ( prevAddRet != -1 && prevAddRet != -3 )
+				addRet = c_repeat_add_read( cx, d.len ) ;
+			else if ( prevAddRet == -3 )
+				addRet = -3 ;
+			finalStrand = i > 0 ? strands[i - 1] : 0 ;
+		}
+		if ( cx.tid == 0 )
+		{
+			strands[i] = (int8_t)finalStrand ;
+			retCodes[i] = addRet ;
+			if ( addRet == -2 )
+				rescueList[rescueCnt] = i ;
+			else if ( addRet >= 0 && d.mate_idx > i )
+			{
+				bool good = false ;
+				if ( finalStrand == 1 && ( d.flags & T4_RD_GOOD_PLUS ) )
+					good = true ;
+				if ( finalStrand == -1 && ( d.flags & T4_RD_GOOD_MINUS ) )
+					good = true ;
+				if ( good && !goodCandidate[d.mate_idx] )
+				{
+					int tagm = d.mate_idx ;
+					const t4_read_desc &md = descs[tagm] ;
+					for ( int j = tagm - 1 ; j > 0 && j >= md.eq_lo ; --j )
+					{
+						goodCandidate[j] = 1 ;
+						info[j] = i ;
+					}
+					for ( int j = tagm + 1 ; j < n && j < md.eq_hi ; ++j )
+					{
+						goodCandidate[j] = 1 ;
+						info[j] = i ;
+					}
+				}
+				if ( good )
+				{
+					goodCandidate[d.mate_idx] = 1 ;
+					info[d.mate_idx] = i ;
+				}
+			}
+		}
+		if ( addRet == -2 )
+			++rescueCnt ;
+		else if ( addRet >= 0 )
+			++assembledReadCnt ;
+		T4_SYNC() ;
+		if ( assembledReadCnt > 0 && cfg.update_consensus_every > 0 && assembledReadCnt % cfg.update_consensus_every == 0
+			&& !cfg.has_barcode )
+			c_update_all_consensus( cx ) ;
+		prevAddRet = addRet ;
+		if ( changeKmerLengthThreshold > 0 && st->nSeqs > changeKmerLengthThreshold && indexKmerLength < 16 && !cfg.has_barcode )
+		{
+			changeKmerLengthThreshold *= 4 ;
+			indexKmerLength += 2 ;
+			c_change_kmer_length( cx, indexKmerLength, gapLimitTable[indexKmerLength] ) ;
+		}
+	}
+	if ( cfg.final_update && !st->error )
+		c_update_all_consensus( cx ) ;
+	if ( cfg.do_rescue && cfg.first_read_len <= 200 && !st->error )
+	{
+		for ( int x = 0 ; x < rescueCnt && !st->error ; ++x )
+		{
+			int i = rescueList[x] ;
+			const t4_read_desc d = descs[i] ;
+			c_load_read( cx, pool + d.seq_off, d.len ) ;
+			char name[2] = "" ;
+			int strand = 0 ;
+			int addRet = c_add_read( cx, d.len, name, strand, d.barcode, 1, cfg.repetitive != 0, t4_rescue_threshold( d.min_cnt ) ) ;
+			if ( cx.tid == 0 )
+			{
+				strands[i] = (int8_t)strand ;
+				rescueRet[i] = addRet ;
+			}
+			T4_SYNC() ;
+		}
+		if ( cfg.final_update && !st->error )
+			c_update_all_consensus( cx ) ;
+	}
+	if ( cx.tid == 0 )
+	{
+		st->assembledReadCnt = assembledReadCnt ;
+		st->prevAddRet = prevAddRet ;
+		t4_atomic_add( &cx.g->counters[0], (u64)n ) ;
+	}
+	T4_SYNC() ;
+}
+
+// ---------------------------------------------------------------------------
+// stream construction: SeqSet::SeqSet(int kl) (SeqSet.hpp:2558-2576)
+// ---------------------------------------------------------------------------
+T4_HD inline u64 t4_al( u64 x ) { return ( x + 63 ) & ~63ull ; }
+
+T4_HD inline u64 t4_stream_footprint( const T4InitParams &ip )
+{
+	u64 o = t4_al( sizeof( T4Stream ) ) ;
+	o += t4_al( (u64)ip.seqCap * sizeof( T4Contig ) ) ;
+	o += t4_al( (u64)ip.dirCap * sizeof( T4Dir ) ) ;
+	o += 2 * t4_al( (u64)ip.hitCap * 8 ) ;
+	o += 2 * t4_al( (u64)( ip.hitCap + 1 ) * 4 ) ;
+	o += t4_al( 2ull * T4_DEV_MAX_READ * sizeof( T4Pos ) ) ;
+	o += 4 * t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
+	o += t4_al( (u64)ip.ovlCap * 8 ) ;
+	o += t4_al( (u64)ip.nThreads * T4_DP_STRIDE ) ;
+	return o ;
+}
+
+T4_D inline void c_init_stream( T4Ctx &cx, u64 base, const T4InitParams &ip )
+{
+	T4Stream *st = cx.P<T4Stream>( base ) ;
+	if ( cx.tid == 0 )
+	{
+		u64 o = base + t4_al( sizeof( T4Stream ) ) ;
+		memset( st, 0, sizeof( T4Stream ) ) ;
+		st->kmerLength = ip.kmerLength ;
+		st->radius = 10 ;
+		st->hitLenRequired = 31 ;
+		st->nomatchGapLimit = ip.nomatchGapLimit ;
+		st->isLongSeqSet = 0 ;
+		st->considerBarcode = 0 ;
+		st->novelSeqSimilarity = 0.9 ;
+		st->repeatSimilarity = 0.95 ;
+		st->nSeqs = 0 ;
+		st->seqCap = (int)ip.seqCap ;
+		st->seqsOff = o ; o += t4_al( (u64)ip.seqCap * sizeof( T4Contig ) ) ;
+		st->dirOff = o ; o += t4_al( (u64)ip.dirCap * sizeof( T4Dir ) ) ;
+		st->dirCap = ip.dirCap ;
+		st->dirUsed = 0 ;
+		st->prevSeqIdx = -1 ;
+		st->prevReadStart = -1 ;
+		st->prevReadEnd = st->prevSeqStart = -1 ;
+		st->prevStrand = 0 ;
+		st->keysAOff = o ; o += t4_al( (u64)ip.hitCap * 8 ) ;
+		st->keysBOff = o ; o += t4_al( (u64)ip.hitCap * 8 ) ;
+		st->grpOff = o ; o += t4_al( (u64)( ip.hitCap + 1 ) * 4 ) ;
+		st->runOff = o ; o += t4_al( (u64)( ip.hitCap + 1 ) * 4 ) ;
+		st->hitCap = ip.hitCap ;
+		st->posOff = o ; o += t4_al( 2ull * T4_DEV_MAX_READ * sizeof( T4Pos ) ) ;
+		st->ovlOff = o ; o += t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
+		st->ovlTmpOff = o ; o += t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
+		st->extOff = o ; o += t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
+		st->failOff = o ; o += t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
+		st->anchorOff = o ; o += t4_al( (u64)ip.ovlCap * 8 ) ;
+		st->ovlCap = ip.ovlCap ;
+		st->dpOff = o ; o += t4_al( (u64)ip.nThreads * T4_DP_STRIDE ) ;
+		st->dpStride = T4_DP_STRIDE ;
+		st->nThreads = ip.nThreads ;
+		st->prevAddRet = -1 ;
+	}
+	T4Dir *dir = cx.P<T4Dir>( base + t4_al( sizeof( T4Stream ) ) + t4_al( (u64)ip.seqCap * sizeof( T4Contig ) ) ) ;
+	T4_PAR_FOR( i, ip.dirCap )
+	{
+		dir[i].key = 0 ;
+		dir[i].listOff = 0 ;
+		dir[i].cnt = dir[i].cap = dir[i].lock = dir[i].pad = 0 ;
+	}
+	T4_SYNC() ;
+}
+
+// Probe only: GetHitsFromRead of every read of the op against the (frozen) stream; the hits are written
+// to the stream's key buffer exactly as AddRead would.  Used for the probe-kernel roofline measurement.
+T4_D inline void c_probe_only( T4Ctx &cx, T4Op *op )
+{
+	const t4_read_desc *descs = t4_x<t4_read_desc>( op->desc ) ;
+	const char *pool = t4_x<char>( op->pool ) ;
+	for ( int i = 0 ; i < op->n && !cx.st->error ; ++i )
+	{
+		const t4_read_desc d = descs[i] ;
+		if ( d.len > T4_DEV_MAX_READ || d.len < cx.st->kmerLength )
+			continue ;
+		c_load_read( cx, pool + d.seq_off, d.len ) ;
+		int anyBig ;
+		c_get_hits( cx, d.len, d.strand_in, d.barcode, false, &anyBig ) ;
+	}
+	if ( cx.tid == 0 )
+		t4_atomic_add( &cx.g->counters[0], (u64)op->n ) ;
+}
+
+// ---------------------------------------------------------------------------
+// op dispatch: body of the stream kernel (one CTA = one T4Op)
+// ---------------------------------------------------------------------------
+T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	if ( st->error )
+	{
+		if ( cx.tid == 0 )
+			op->ret = st->error ;
+		return ;
+	}
+	switch ( op->op )
+	{
+		case T4_OP_RUN_LOOP:
+			c_run_loop( cx, op, gapLimitTable ) ;
+			if ( cx.tid == 0 )
+				op->ret = st->error ? st->error : st->assembledReadCnt ;
+			break ;
+		case T4_OP_ADD_READ:
+		{
+			c_load_read( cx, t4_x<char>( op->read ), op->len ) ;
+			int strand = op->strand ;
+			int ret = c_add_read( cx, op->len, op->gene, strand, op->barcode, op->minKmerCount, op->repetitive != 0, op->thr ) ;
+			if ( cx.tid == 0 )
+			{
+				op->ret = ret ;
+				op->strandOut = strand ;
+			}
+			break ;
+		}
+		case T4_OP_REPEAT:
+		{
+			c_load_read( cx, t4_x<char>( op->read ), op->len ) ;
+			int ret = c_repeat_add_read( cx, op->len ) ;
+			if ( cx.tid == 0 )
+				op->ret = ret ;
+			break ;
+		}
+		case T4_OP_INPUT_NOVEL:
+		{
+			c_load_read( cx, t4_x<char>( op->read ), op->len ) ;
+			if ( cx.tid == 0 )
+				op->ret = s_input_novel_read( cx, t4_x<char>( op->name ), op->nameLen, op->len, op->strand, op->barcode ) ;
+			break ;
+		}
+		case T4_OP_UPDATE_ALL:
+			c_update_all_consensus( cx ) ;
+			if ( cx.tid == 0 )
+				op->ret = 0 ;
+			break ;
+		case T4_OP_CHANGE_K:
+			c_change_kmer_length( cx, op->kl, gapLimitTable[op->kl] ) ;
+			if ( cx.tid == 0 )
+				op->ret = 0 ;
+			break ;
+		case T4_OP_GET_HITS:
+		{
+			// GetHitsFromRead + SortHits, reported in (strand, idx, a, b) order as int32[5]
+			c_load_read( cx, t4_x<char>( op->read ), op->len ) ;
+			int ret = 0 ;
+			if ( op->len >= st->kmerLength )
+			{
+				int anyBig = 0 ;
+				u32 H = c_get_hits( cx, op->len, op->strand, op->barcode, op->repetitive != 0, &anyBig ) ;
+				u64 *a = cx.P<u64>( st->keysAOff ) ;
+				u64 *b = cx.P<u64>( st->keysBOff ) ;
+				// re-key to SortHits order: (strand, idx, a, b)
+				const T4Pos *pos = cx.P<T4Pos>( st->posOff ) ;
+				const int m = op->len - st->kmerLength + 1 ;
+				T4_PAR_FOR( i, H )
+				{
+					u64 kx = a[i] ;
+					if ( kx == T4_KEY_INVALID )
+						continue ;
+					u64 aa = (u64)t4_key_a( kx ) ;
+					a[i] = ( kx & ( ~0ull << T4_KEY_IDX_SHIFT ) ) | ( aa << 30 ) | ( (u64)t4_key_b( kx ) << 1 ) | ( kx & 1 ) ;
+				}
+				T4_SYNC() ;
+				u64 *sorted = c_sort_keys( cx, a, b, H ) ;
+				int32_t *out = t4_x<int32_t>( op->out ) ;
+				T4_PAR_FOR( i, H )
+				{
+					u64 kx = sorted[i] ;
+					if ( kx == T4_KEY_INVALID || i >= op->outCap )
+						continue ;
+					int strand = t4_key_strand( kx ) ;
+					int aa = (int)( ( kx >> 30 ) & 0x7ff ) ;
+					int bb = (int)( ( kx >> 1 ) & T4_KEY_B_MASK ) ;
+					out[5 * i] = t4_key_idx( kx ) ;
+					out[5 * i + 1] = bb ;
+					out[5 * i + 2] = aa ;
+					out[5 * i + 3] = strand ;
+					int rep = (int)pos[( strand == 1 ? 0 : 1 ) * T4_DEV_MAX_READ + aa].cnt ;
+					out[5 * i + 4] = ( op->barcode != -1 ) ? 1 : rep ;
+				}
+				T4_SYNC() ;
+				u32 c = 0 ;
+				for ( u32 i = cx.tid ; i < H ; i += cx.nt )
+					if ( sorted[i] != T4_KEY_INVALID )
+						++c ;
+				u32 total ;
+				c_scan_threads( cx, c, total ) ;
+				ret = (int)total ;
+				(void)m ;
+			}
+			if ( cx.tid == 0 )
+				op->ret = ret ;
+			break ;
+		}
+		case T4_OP_GET_OVERLAPS:
+		{
+			c_load_read( cx, t4_x<char>( op->read ), op->len ) ;
+			int n = c_get_overlaps( cx, op->len, op->strand, op->barcode, op->repetitive != 0 ) ;
+			if ( n > 0 )
+			{
+				T4Ovl *ovl = cx.P<T4Ovl>( st->ovlOff ) ;
+				int32_t *out = t4_x<int32_t>( op->out ) ;
+				double *sim = t4_x<double>( op->out2 ) ;
+				T4_PAR_FOR( i, n )
+				{
+					if ( i >= op->outCap )
+						continue ;
+					out[8 * i] = ovl[i].seqIdx ;
+					out[8 * i + 1] = ovl[i].readStart ;
+					out[8 * i + 2] = ovl[i].readEnd ;
+					out[8 * i + 3] = ovl[i].seqStart ;
+					out[8 * i + 4] = ovl[i].seqEnd ;
+					out[8 * i + 5] = ovl[i].strand ;
+					out[8 * i + 6] = ovl[i].matchCnt ;
+					out[8 * i + 7] = ovl[i].indelCnt ;
+					sim[i] = ovl[i].similarity ;
+				}
+			}
+			if ( cx.tid == 0 )
+				op->ret = n ;
+			break ;
+		}
+		case T4_OP_PROBE_ONLY:
+			c_probe_only( cx, op ) ;
+			if ( cx.tid == 0 )
+				op->ret = 0 ;
+			break ;
+		default:
+			break ;
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 && st->error && op->ret >= T4_E_BASE )
+		op->ret = st->error ;
+	(void)sm ;
+}
+
+#endif
