@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py -- reads/sec assembled (150 bp PE) through the stage-1 AddRead loop on N B200s.
+
+Workload (BASELINE.json configs[1]): 1 M synthetic 150 bp pairs (2 M reads) per GPU against the IMGT gene
+set, k = 9, read-sharded into S independent streams (contiguous shards of the sorted read
+list, one SeqSet each; parity is per shard).  A step = one pass of the whole loop over the whole workload:
+fresh streams -> stream kernel -> results.
+
+  value      inputs resident in HBM, CUDA-event time over K steps (max over ranks)
+  e2e        the same through t4_streams_run with pinned HOST buffers: H2D of records + reads and D2H of
+             the per-read results inside the timed region
+  roofline   the stream kernel (the only hot kernel of a step): algorithmic bytes from the
+             device counters / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs;
+             roofline_probe: the standalone probe kernel (GetHitsFromRead only) over the final contig sets
+  cpu_baseline / --impl reference: the reference's own SeqSet (oracle/_ref/libt4ref.so, compiled from the
+             reference sources) driven over the same shards on the host cores, bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("T4_BENCH_PAIRS", 1000000)))
+    ap.add_argument("--clones", type=int, default=0, help="clonotypes (default pairs/50)")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("T4_BENCH_STREAMS", 4096)))
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--ref-seconds", type=float, default=20.0, help="CPU time budget of one reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-probe", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def make_workload(args, rank, device):
+    from trust4_b200 import synth
+    nclones = args.clones or max(20, args.pairs // 50)
+    cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
+    rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
+    w = synth.build_workload(cl, rd, device=device)
+    off, descs = synth.shard_workload(w, args.streams)
+    return w, off, descs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def reference_sample(args, w, off, descs, budget_s, cores):
+    """The reference's SeqSet over the first shards of the workload on `cores` host threads for ~budget_s."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refharness as rh
+    from trust4_b200 import synth
+    if not rh.available():
+        return None
+    cfg = synth.run_cfg()
+    n_shards = len(off) - 1
+    lock = threading.Lock()
+    state = {"next": 0, "reads": 0, "shards": 0}
+    t0 = time.perf_counter()
+
+    def worker():
+        while True:
+            with lock:
+                j = state["next"]
+                if j >= n_shards or time.perf_counter() - t0 > budget_s:
+                    return
+                state["next"] += 1
+            lo, hi = int(off[j]), int(off[j + 1])
+            r = rh.RefSeqSet(9)
+            r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)     # ctypes releases the GIL
+            r.close()
+            with lock:
+                state["reads"] += hi - lo
+                state["shards"] += 1
+
+    th = [threading.Thread(target=worker) for _ in range(cores)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    el = time.perf_counter() - t0
+    return {"value": state["reads"] / el, "unit": "reads/s", "cores": cores, "kind": "reference",
+            "sample": "first %d of %d read shards (%d reads) of the same workload, %.1f s wall on %d threads; "
+                      "oracle/_ref/libt4ref.so = reference SeqSet::AddRead/RepeatAddRead/InputNovelRead driven by the "
+                      "restated main.cpp loop" % (state["shards"], n_shards, state["reads"], el, cores)}
+
+
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    cores = os.cpu_count() or 1
+    config = {"workload": "configs[1]: %d synthetic 150bp PE pairs (%d reads) per GPU vs human_IMGT+C gene pool, k=9, "
+                          "read-sharded into %d streams per GPU (one SeqSet each, per-shard parity, SURVEY.md 8e)"
+                          % (args.pairs, 2 * args.pairs, args.streams),
+              "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150,
+              "l2": "inputs (>= 400 MB of reads + records, GBs of stream state) exceed the 126 MB L2",
+              "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w, off, descs = make_workload(args, 0, None)
+        per_step = max(2.0, min(args.ref_seconds, 150.0 / max(1, args.steps + args.warmup)))
+        vals = []
+        for it in range(args.warmup + args.steps):
+            s = reference_sample(args, w, off, descs, per_step, cores)
+            if s is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libt4ref.so not built"}))
+                return
+            if it >= args.warmup:
+                vals.append(s)
+        v = float(np.mean([x["value"] for x in vals]))
+        n_reads = len(descs)
+        line = {"impl": "reference", "metric": "reads/sec assembled (150bp PE)", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_reads / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "cpu_baseline": dict(vals[-1], value=v),
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from trust4_b200 import api, synth
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = api.default_lib()
+    lib.check(lib.init(local, 0))
+    dev = torch.device("cuda", local)
+
+    t_gen = time.perf_counter()
+    w, off, descs = make_workload(args, rank, dev)
+    t_gen = time.perf_counter() - t_gen
+    torch.cuda.empty_cache()
+    n_reads = len(descs)
+    S = args.streams
+    cfg = synth.run_cfg()
+    names_arr = api._names_array(w.names)
+    off64 = np.ascontiguousarray(off, dtype=np.int64)
+
+    # pinned host copies for the e2e leg
+    pin_descs = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).pin_memory()
+    pin_pool = torch.from_numpy(w.pool.copy()).pin_memory()
+    ret = torch.zeros(n_reads, dtype=torch.int32).pin_memory()
+    strands = torch.zeros(n_reads, dtype=torch.int8).pin_memory()
+    resc = torch.zeros(n_reads, dtype=torch.int32).pin_memory()
+    h2d_bytes = pin_descs.numel() + pin_pool.numel() + S * 256
+    d2h_bytes = n_reads * 9
+
+    wl = lib.workload_upload(pin_descs.data_ptr(), n_reads, pin_pool.data_ptr(), pin_pool.numel(), names_arr, len(w.names))
+    if not wl:
+        raise RuntimeError(lib.err())
+    handles = (C.c_void_p * S)()
+
+    def step_resident():
+        lib.check(lib.reset())
+        lib.check(lib.seqsets_create(S, 9, handles))
+        lib.check(lib.streams_run_resident(handles, S, cfg.ctypes.data, wl, off64.ctypes.data, None))
+
+    def step_e2e():
+        lib.check(lib.reset())
+        lib.check(lib.seqsets_create(S, 9, handles))
+        lib.check(lib.streams_run(handles, S, cfg.ctypes.data, pin_descs.data_ptr(), off64.ctypes.data, pin_pool.data_ptr(),
+                                  pin_pool.numel(), names_arr, len(w.names), ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    err = lib.streams_error(handles, S)
+    if err:
+        raise RuntimeError("device error after warm-up: " + lib.err())
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    counters = np.zeros(api.N_COUNTERS, dtype=np.uint64)
+    lib.check(lib.last_counters(counters.ctypes.data))
+    assembled = None
+    lib.check(lib.workload_results(wl, ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
+    assembled = int((ret >= 0).sum().item() + (resc >= 0).sum().item())
+
+    # kernel-only duration of the stream kernel (one launch per step) for the roofline
+    lib.check(lib.reset())
+    lib.check(lib.seqsets_create(S, 9, handles))
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0 = np.zeros(api.N_COUNTERS, dtype=np.uint64)
+    lib.check(lib.last_counters(c0.ctypes.data))
+    k0.record()
+    lib.check(lib.streams_run_resident(handles, S, cfg.ctypes.data, wl, off64.ctypes.data, None))
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1)
+    c1 = np.zeros(api.N_COUNTERS, dtype=np.uint64)
+    lib.check(lib.last_counters(c1.ctypes.data))
+    dc = (c1 - c0).astype(np.float64)
+    # probe ceil(L/4) + sum(8 + 8 c_j) + 16 sum c_j'; chain 2 x 16 sum c_j'; commit 8 L per assembled read
+    b_probe = dc[5] + 8 * dc[2] + 8 * dc[3] + 16 * dc[4]
+    b_chain = 32 * dc[4]
+    b_commit = 8.0 * 150 * assembled
+    alg_bytes = b_probe + b_chain + b_commit
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "t4_stream_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                "algorithmic_bytes": {"probe": b_probe, "chain": b_chain, "commit": b_commit},
+                "per_read": {"lookups": dc[2] / max(1.0, dc[1] if dc[1] else n_reads), "hits": dc[4] / n_reads}}
+
+    roofline_probe = None
+    if not args.no_probe:
+        pb, ph = C.c_uint64(), C.c_uint64()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib.check(lib.probe_resident(handles, S, wl, off64.ctypes.data, None, None, None))     # warm
+        torch.cuda.synchronize()
+        p0.record()
+        lib.check(lib.probe_resident(handles, S, wl, off64.ctypes.data, None, None, None))
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1)
+        lib.check(lib.probe_resident(handles, S, wl, off64.ctypes.data, None, C.byref(pb), C.byref(ph)))
+        a = pb.value / (pms * 1e-3) / 1e9
+        roofline_probe = {"bound": "hbm", "kernel": "t4_stream_kernel<PROBE_ONLY> (GetHitsFromRead over the final contig sets)",
+                          "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "kernel_ms": pms,
+                          "algorithmic_bytes": pb.value, "hits": ph.value, "reads_per_s": n_reads / (pms * 1e-3)}
+
+    # e2e leg
+    for _ in range(1):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_assembled = int((ret >= 0).sum().item() + (resc >= 0).sum().item())
+    assert e2e_assembled == assembled, (e2e_assembled, assembled)
+
+    value = world * n_reads * args.steps / (ms * 1e-3)
+    e2e = world * n_reads * args.steps / (ms_e2e * 1e-3)
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = reference_sample(args, w, off, descs, args.ref_seconds, cores)
+        line = {"metric": "reads/sec assembled (150bp PE)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": 2 * args.steps, "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
+                "assembled_reads": assembled, "reads_per_gpu": n_reads, "workload_gen_s": t_gen,
+                "threads_per_stream": int(os.environ.get("T4_NT", 32))}
+        print(json.dumps(line))
+    lib.workload_free(wl)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -207,11 +207,31 @@ def write_fastq(reads: Reads, prefix: str):
 # ---------------------------------------------------------------------------
 # pre-processing stand-in: k-mer statistics, sort, annotation from truth
 # ---------------------------------------------------------------------------
-def kmer_stats(codes: np.ndarray, k: int = 21):
+def kmer_stats(codes: np.ndarray, k: int = 21, device=None):
     """Canonical k-mer counts over all reads -> per-read (min, median, mean) like
-    KmerCount::GetCountStatsAndTrim (KmerCount.hpp:177) without trimming."""
+    KmerCount::GetCountStatsAndTrim (KmerCount.hpp:177) without trimming.  `device`: a torch device
+    to do the counting on (workload preparation only -- 260 M k-mers for 1 M pairs)."""
     n, L = codes.shape
     m = L - k + 1
+    if device is not None:
+        import torch
+        c = torch.from_numpy(np.ascontiguousarray(codes)).to(device).to(torch.int64)
+        fw = torch.zeros((n, m), dtype=torch.int64, device=device)
+        rc = torch.zeros((n, m), dtype=torch.int64, device=device)
+        for j in range(k):
+            fw = (fw << 2) | c[:, j:j + m]
+            rc = rc | ((3 - c[:, j:j + m]) << (2 * j))
+        canon = torch.minimum(fw, rc).reshape(-1)
+        del fw, rc, c
+        uniq, inv, cnt = torch.unique(canon, return_inverse=True, return_counts=True)
+        del canon, uniq
+        per = cnt[inv].reshape(n, m)
+        del inv, cnt
+        per_sorted, _ = torch.sort(per, dim=1)
+        mn = per_sorted[:, 0].to(torch.int32).cpu().numpy()
+        med = per_sorted[:, m // 2].to(torch.int32).cpu().numpy()
+        avg = per.to(torch.float64).mean(dim=1).to(torch.float32).cpu().numpy()
+        return mn, med, avg
     c64 = codes.astype(np.uint64)
     fw = np.zeros((n, m), dtype=np.uint64)
     rc = np.zeros((n, m), dtype=np.uint64)
@@ -265,10 +285,10 @@ class Workload:
         return self.pool[int(d["seq_off"]): int(d["seq_off"]) + int(d["len"])].tobytes().decode()
 
 
-def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17) -> Workload:
+def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=None) -> Workload:
     """Truth-annotated stand-in for main.cpp:981-1526 -> AddRead-loop records."""
     n, L = reads.codes.shape
-    mn, med, avg = kmer_stats(reads.codes)
+    mn, med, avg = kmer_stats(reads.codes, device=device)
     # sort: minCnt desc, medianCnt desc, avgCnt desc, len desc, read asc, id asc  (main.cpp:103-125)
     words = []
     nw = (L + 31) // 32
