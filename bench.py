@@ -253,8 +253,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
-    err = lib.streams_error(handles, S)
-    if err:
+    if args.warmup > 0 and lib.streams_error(handles, S):
         raise RuntimeError("device error after warm-up: " + lib.err())
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(step_resident, args.steps)
@@ -296,7 +295,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": "t4_stream_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes": {"probe": b_probe, "chain": b_chain, "commit": b_commit},
-                "per_read": {"lookups": dc[2] / max(1.0, dc[1] if dc[1] else n_reads), "hits": dc[4] / n_reads}}
+                "per_read": {"lookups": dc[2] / n_reads, "hits": dc[4] / n_reads, "overlaps_scored": dc[6] / n_reads, "gap_dps": dc[7] / n_reads,
+                             "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads},
+                "phase_share": dict(zip(["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"],
+                                        [round(float(x), 4) for x in (dc[8:16] / max(1.0, dc[8:16].sum()))]))}
 
     roofline_probe = None
     if not args.no_probe:
@@ -335,7 +337,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": 2 * args.steps, "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
                 "assembled_reads": assembled, "reads_per_gpu": n_reads, "workload_gen_s": t_gen,
-                "threads_per_stream": int(os.environ.get("T4_NT", 32))}
+                "threads_per_stream": int(os.environ.get("T4_NT", 64))}
         print(json.dumps(line))
     lib.workload_free(wl)
     if world > 1:

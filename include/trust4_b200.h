@@ -191,6 +191,13 @@ int t4_streams_run_resident(t4_seqset *const *sets, int n_sets, const t4_run_cfg
 /* Copy results of the last resident run back. */
 int t4_workload_results(t4_workload *w, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
 
+/* Merge step: pack every live contig of the given sets, in (set, slot) order, into ONE caller-provided
+ * DEVICE buffer (e.g. a torch tensor) ready for an NCCL all-gather.  Record = 32-byte header {u32 set, slot, len,
+ * nameLen; i32 barcode, numRead; u32 recordBytes, 0} + consensus[len] + posWeight int32[len][4] + name, padded to 16 B.
+ * With dev_buf == NULL only *bytes_needed / *n_contigs are computed. */
+int t4_streams_pack_contigs(t4_seqset *const *sets, int n_sets, void *dev_buf, size_t cap, size_t *bytes_needed,
+                            int64_t *n_contigs);
+
 /* First device-side error among the streams (0 = none); details in t4_last_error(). */
 int t4_streams_error(t4_seqset *const *sets, int n_sets);
 /* Test hook: number of postings in the k-mer index and an order-independent checksum of them. */
@@ -201,7 +208,7 @@ int64_t t4_seqset_index_checksum(t4_seqset *s, uint64_t *checksum);
  * [4] hits emitted (sum c_j'), [5] read bytes, [6] overlaps scored, [7] full banded DPs,
  * [8] probe-phase clock cycles (sum over CTAs), [9] total clock cycles (sum over CTAs),
  * [10..15] per-phase cycles: sort, chain, score, decide, commit, other. */
-#define T4_N_COUNTERS 16
+#define T4_N_COUNTERS 24
 int t4_last_counters(uint64_t *counters /* T4_N_COUNTERS */);
 
 /* Standalone probe kernel over frozen sets (roofline measurement):

@@ -1,0 +1,63 @@
+"""World-size-2 gloo test of the multi-GPU host logic (runs on CPU): read sharding by rank and stream, the
+merge-step all-gather of packed contigs, and per-shard parity of what rank 0 receives.  The device work is done by
+the TEST-ONLY emulation (tests/emu) here; on the B200 the same code path runs with NCCL (bench.py --gpus N)."""
+import os
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, emu_path, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch.distributed as dist
+    from trust4_b200 import api, synth, dist as tdist
+    import refharness as rh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = api.Lib(emu_path, "t4emu_")
+    lib.check(lib.init(0, 1 << 30))
+    S = 3
+    cl = synth.make_clones(20, 5)                               # shared repertoire
+    rd = synth.sample_pairs(cl, 300, 150, 5000 + rank)          # rank-specific reads
+    w = synth.build_workload(cl, rd)
+    off, descs = synth.shard_workload(w, S)
+    cfg = synth.run_cfg()
+    sets = api.SeqSet.create_many(S, 9, lib)
+    api.streams_run(sets, cfg, descs, off, w.pool, w.names, lib)
+    buf, n = tdist.pack_contigs(lib, sets)
+    gathered = tdist.allgather_contigs(buf)
+    assert len(gathered) == world
+    # every rank checks its own slice against the reference; rank 0 additionally checks what it received
+    mine = tdist.format_output(tdist.unpack_contigs(gathered[rank]))
+    for j in range(S):
+        r = rh.RefSeqSet(9)
+        r.run_descs(cfg, descs[int(off[j]):int(off[j + 1])].copy(), w.pool, w.names)
+        assert r.output() == mine.get(j, b""), (rank, j)
+    tot = sum(len(tdist.unpack_contigs(g)) for g in gathered)
+    cnt = np.array([n], dtype=np.int64)
+    import torch
+    t = torch.from_numpy(cnt)
+    dist.all_reduce(t)
+    assert int(t.item()) == tot
+    q.put((rank, tot))
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_allgather(emu_lib, ref):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib.path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = sorted(q.get() for _ in range(2))
+    assert res[0][1] == res[1][1] and res[0][1] > 0

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libtrust4_b200.so")
 
 T4_E_BASE = -16
 T4_E_CUDA, T4_E_NOMEM, T4_E_INVAL, T4_E_UNSUPPORTED, T4_E_NODEVICE, T4_E_INTERNAL = -17, -18, -19, -20, -21, -22
-N_COUNTERS = 16
+N_COUNTERS = 24
 
 EXPORTS = [
     "init", "shutdown", "last_error", "version", "arena_stats", "reset",
@@ -31,7 +31,7 @@ EXPORTS = [
     "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch",
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
     "streams_run_resident", "workload_results", "last_counters", "probe_resident", "streams_error",
-    "seqset_index_checksum",
+    "seqset_index_checksum", "streams_pack_contigs",
 ]
 
 
@@ -92,6 +92,7 @@ class Lib:
         f("probe_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
         f("streams_error", ci, [C.POINTER(vp), ci])
         f("seqset_index_checksum", C.c_int64, [vp, C.POINTER(C.c_uint64)])
+        f("streams_pack_contigs", ci, [C.POINTER(vp), ci, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64)])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)

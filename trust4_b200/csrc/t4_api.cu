@@ -45,7 +45,10 @@ static void set_err( const std::string &s ) { g_err = s ; }
 		}                                                                          \
 	} while ( 0 )
 
-__global__ void t4_stream_kernel( char *A, T4Op *ops, const int *gapTable )
+#ifndef T4_MIN_BLOCKS
+#define T4_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_stream_kernel( char *A, T4Op *ops, const int *gapTable )
 {
 	__shared__ T4Smem sm ;
 	T4Op *op = ops + blockIdx.x ;
@@ -54,6 +57,7 @@ __global__ void t4_stream_kernel( char *A, T4Op *ops, const int *gapTable )
 	cx.g = (T4Global *)A ;
 	cx.st = (T4Stream *)( A + op->streamOff ) ;
 	cx.sm = &sm ;
+	cx.cap = cx.g->cap ;
 	cx.tid = threadIdx.x ;
 	cx.nt = blockDim.x ;
 	c_run_op( cx, op, gapTable ) ;
@@ -67,6 +71,7 @@ __global__ void t4_init_kernel( char *A, u64 base, T4InitParams ip )
 	cx.g = (T4Global *)A ;
 	cx.st = 0 ;
 	cx.sm = &sm ;
+	cx.cap = cx.g->cap ;
 	cx.tid = threadIdx.x ;
 	cx.nt = blockDim.x ;
 	c_init_stream( cx, base + (u64)blockIdx.x * ip.footprint, ip ) ;
@@ -106,6 +111,54 @@ __global__ void t4_dp_kernel( int n, const int *tw, const i64 *tOff, const char 
 	score[i] = t4_dp_posweight( tw + 4 * tOff[i], lent, p + pOff[i], lenp, align + alignOff[i], (int *)s,
 		(unsigned char *)( s + 8 * W ), 0 ) ;
 }
+
+__global__ void t4_pack_size_kernel( char *A, const u64 *streamOff, u64 *sizes, u64 *counts )
+{
+	if ( threadIdx.x != 0 )
+		return ;
+	const T4Stream *st = (const T4Stream *)( A + streamOff[blockIdx.x] ) ;
+	const T4Contig *ct = (const T4Contig *)( A + st->seqsOff ) ;
+	u64 tot = 0, n = 0 ;
+	for ( int i = 0 ; i < st->nSeqs ; ++i )
+		if ( ct[i].consOff )
+		{
+			tot += t4_pack_record_bytes( ct[i] ) ;
+			++n ;
+		}
+	sizes[blockIdx.x] = tot ;
+	counts[blockIdx.x] = n ;
+}
+
+__global__ void t4_pack_kernel( char *A, const u64 *streamOff, const u64 *outOff, char *out )
+{
+	const T4Stream *st = (const T4Stream *)( A + streamOff[blockIdx.x] ) ;
+	const T4Contig *ct = (const T4Contig *)( A + st->seqsOff ) ;
+	u64 o = outOff[blockIdx.x] ;
+	for ( int i = 0 ; i < st->nSeqs ; ++i )
+	{
+		const T4Contig &k = ct[i] ;
+		if ( !k.consOff )
+			continue ;
+		u64 rb = t4_pack_record_bytes( k ) ;
+		char *rec = out + o ;
+		if ( threadIdx.x == 0 )
+		{
+			u32 *h = (u32 *)rec ;
+			h[0] = blockIdx.x ; h[1] = (u32)i ; h[2] = (u32)k.len ; h[3] = (u32)k.nameLen ;
+			h[4] = (u32)k.barcode ; h[5] = (u32)k.numRead ; h[6] = (u32)rb ; h[7] = 0 ;
+		}
+		const char *cons = A + k.consOff + k.lead ;
+		const char *pw = A + k.pwOff + 16ull * k.lead ;
+		const char *nm = A + k.nameOff ;
+		for ( int x = threadIdx.x ; x < k.len ; x += blockDim.x )
+			rec[32 + x] = cons[x] ;
+		for ( int x = threadIdx.x ; x < 16 * k.len ; x += blockDim.x )
+			rec[32 + k.len + x] = pw[x] ;
+		for ( int x = threadIdx.x ; x < k.nameLen ; x += blockDim.x )
+			rec[32 + 17 * k.len + x] = nm[x] ;
+		o += rb ;
+	}
+}
 #else
 #define CK( call ) do { } while ( 0 )
 #endif
@@ -122,7 +175,10 @@ struct Engine
 	// staging (device)
 	char *stage ;
 	size_t stageCap ;
-	Engine() : up( false ), device( 0 ), A( 0 ), cap( 0 ), nt( 32 ), gapTable( 0 ), stage( 0 ), stageCap( 0 ) {}
+	// grow-only device buffer reused by t4_streams_run for the uploaded workload (no cudaMalloc per call)
+	char *wl ;
+	size_t wlCap ;
+	Engine() : up( false ), device( 0 ), A( 0 ), cap( 0 ), nt( 64 ), gapTable( 0 ), stage( 0 ), stageCap( 0 ), wl( 0 ), wlCap( 0 ) {}
 } ;
 static Engine E ;
 static std::mutex g_mu ;
@@ -198,6 +254,7 @@ static int launch_ops( T4Op *dOps, int n, void *stream )
 		cx.g = (T4Global *)E.A ;
 		cx.st = (T4Stream *)( E.A + dOps[b].streamOff ) ;
 		cx.sm = sm ;
+		cx.cap = cx.g->cap ;
 		cx.tid = 0 ;
 		cx.nt = 1 ;
 		c_run_op( cx, dOps + b, E.gapTable ) ;
@@ -283,6 +340,7 @@ struct t4_workload
 	int32_t *info ;
 	T4Op *ops ;
 	int opCap ;
+	bool persistent ;
 } ;
 
 extern "C" {
@@ -312,6 +370,8 @@ int T4_API( shutdown )( void )
 #endif
 	if ( E.stage )
 		dfree( E.stage ) ;
+	if ( E.wl )
+		dfree( E.wl ) ;
 	E = Engine() ;
 	++g_gen ;
 	return 0 ;
@@ -468,7 +528,7 @@ int T4_API( seqsets_create )( int n, int kmer_length, t4_seqset **handles )
 	for ( int b = 0 ; b < n ; ++b )
 	{
 		T4Ctx cx ;
-		cx.A = E.A ; cx.g = (T4Global *)E.A ; cx.st = 0 ; cx.sm = sm ; cx.tid = 0 ; cx.nt = 1 ;
+		cx.A = E.A ; cx.g = (T4Global *)E.A ; cx.st = 0 ; cx.sm = sm ; cx.cap = cx.g->cap ; cx.tid = 0 ; cx.nt = 1 ;
 		c_init_stream( cx, base + (u64)b * fp, ip ) ;
 	}
 	delete sm ;
@@ -1065,8 +1125,8 @@ int T4_API( dp_pos_weight_batch )( int n, const int32_t *t_weights, const int64_
 }
 
 // ---- workloads / batch -------------------------------------------------------------
-t4_workload *T4_API( workload_upload )( const t4_read_desc *descs, int64_t n, const char *read_pool, size_t pool_bytes,
-	const char *const *names, int n_names )
+static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, const char *read_pool, size_t pool_bytes,
+	const char *const *names, int n_names, bool persistent )
 {
 	if ( ensure_up() )
 		return 0 ;
@@ -1090,12 +1150,30 @@ t4_workload *T4_API( workload_upload )( const t4_read_desc *descs, int64_t n, co
 	size_t oRl = oResc + al( (size_t)n * 4 ) ;
 	size_t oGood = oRl + al( (size_t)n * 4 ) ;
 	size_t oInfo = oGood + al( (size_t)n ) ;
-	size_t total = oInfo + al( (size_t)n * 4 ) ;
+	size_t oOps = oInfo + al( (size_t)n * 4 ) ;
+	size_t total = oOps ;
 	void *p = 0 ;
-	if ( dmalloc( &p, total ) )
+	if ( persistent )
+	{
+		if ( E.wlCap < total )
+		{
+			if ( E.wl )
+				dfree( E.wl ) ;
+			E.wl = 0 ;
+			E.wlCap = 0 ;
+			size_t c = total + total / 4 ;
+			if ( dmalloc( &p, c ) )
+				return 0 ;
+			E.wl = (char *)p ;
+			E.wlCap = c ;
+		}
+		p = E.wl ;
+	}
+	else if ( dmalloc( &p, total ) )
 		return 0 ;
 	t4_workload *w = new t4_workload ;
 	memset( w, 0, sizeof( *w ) ) ;
+	w->persistent = persistent ;
 	w->buf = (char *)p ;
 	w->bytes = total ;
 	w->nDescs = n ;
@@ -1118,11 +1196,18 @@ t4_workload *T4_API( workload_upload )( const t4_read_desc *descs, int64_t n, co
 	if ( h2d( w->descs, descs, (size_t)n * sizeof( t4_read_desc ) ) || h2d( w->pool, read_pool, pool_bytes ) || h2d( w->names, &hn, sizeof( hn ) )
 		|| h2d( w->buf + oNoff, noff.data(), ( n_names + 1 ) * 4 ) || h2d( w->buf + oNpool, npool.data(), npool.size() ) )
 	{
-		dfree( p ) ;
+		if ( !persistent )
+			dfree( p ) ;
 		delete w ;
 		return 0 ;
 	}
 	return w ;
+}
+
+t4_workload *T4_API( workload_upload )( const t4_read_desc *descs, int64_t n, const char *read_pool, size_t pool_bytes,
+	const char *const *names, int n_names )
+{
+	return workload_upload_impl( descs, n, read_pool, pool_bytes, names, n_names, false ) ;
 }
 
 void T4_API( workload_free )( t4_workload *w )
@@ -1131,7 +1216,8 @@ void T4_API( workload_free )( t4_workload *w )
 		return ;
 	if ( w->ops )
 		dfree( w->ops ) ;
-	dfree( w->buf ) ;
+	if ( !w->persistent )
+		dfree( w->buf ) ;
 	delete w ;
 }
 
@@ -1243,6 +1329,92 @@ int T4_API( workload_results )( t4_workload *w, int32_t *ret_codes, int8_t *stra
 	return 0 ;
 }
 
+int T4_API( streams_pack_contigs )( t4_seqset *const *sets, int n_sets, void *dev_buf, size_t cap, size_t *bytes_needed, int64_t *n_contigs )
+{
+	if ( n_sets <= 0 )
+		return T4_E_INVAL ;
+	std::vector<u64> so( n_sets ), sizes( n_sets ), counts( n_sets ), off( n_sets ) ;
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		int r = check( sets[j] ) ;
+		if ( r ) return r ;
+		so[j] = sets[j]->off ;
+	}
+	int r = dsync() ;
+	if ( r ) return r ;
+#if T4_CUDA
+	r = ensure_stage( (size_t)n_sets * 32 + 256 ) ;
+	if ( r ) return r ;
+	u64 *dSo = (u64 *)E.stage, *dSz = dSo + n_sets, *dCnt = dSz + n_sets, *dOff = dCnt + n_sets ;
+	r = h2d( dSo, so.data(), (size_t)n_sets * 8 ) ;
+	if ( r ) return r ;
+	t4_pack_size_kernel<<<n_sets, 32>>>( E.A, dSo, dSz, dCnt ) ;
+	CK( cudaGetLastError() ) ;
+	r = d2h( sizes.data(), dSz, (size_t)n_sets * 8 ) ;
+	if ( r ) return r ;
+	r = d2h( counts.data(), dCnt, (size_t)n_sets * 8 ) ;
+	if ( r ) return r ;
+#else
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		const T4Stream *st = (const T4Stream *)( E.A + so[j] ) ;
+		const T4Contig *ct = (const T4Contig *)( E.A + st->seqsOff ) ;
+		sizes[j] = counts[j] = 0 ;
+		for ( int i = 0 ; i < st->nSeqs ; ++i )
+			if ( ct[i].consOff )
+			{
+				sizes[j] += t4_pack_record_bytes( ct[i] ) ;
+				++counts[j] ;
+			}
+	}
+#endif
+	u64 tot = 0, n = 0 ;
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		off[j] = tot ;
+		tot += sizes[j] ;
+		n += counts[j] ;
+	}
+	if ( bytes_needed ) *bytes_needed = tot ;
+	if ( n_contigs ) *n_contigs = (int64_t)n ;
+	if ( !dev_buf )
+		return 0 ;
+	if ( cap < tot )
+	{
+		set_err( "pack buffer too small" ) ;
+		return T4_E_INVAL ;
+	}
+#if T4_CUDA
+	r = h2d( dOff, off.data(), (size_t)n_sets * 8 ) ;
+	if ( r ) return r ;
+	t4_pack_kernel<<<n_sets, 128>>>( E.A, dSo, dOff, (char *)dev_buf ) ;
+	CK( cudaGetLastError() ) ;
+#else
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		const T4Stream *st = (const T4Stream *)( E.A + so[j] ) ;
+		const T4Contig *ct = (const T4Contig *)( E.A + st->seqsOff ) ;
+		u64 o = off[j] ;
+		for ( int i = 0 ; i < st->nSeqs ; ++i )
+		{
+			const T4Contig &k = ct[i] ;
+			if ( !k.consOff )
+				continue ;
+			u64 rb = t4_pack_record_bytes( k ) ;
+			char *rec = (char *)dev_buf + o ;
+			memset( rec, 0, rb ) ;
+			u32 *h = (u32 *)rec ;
+			h[0] = j ; h[1] = (u32)i ; h[2] = (u32)k.len ; h[3] = (u32)k.nameLen ; h[4] = (u32)k.barcode ; h[5] = (u32)k.numRead ; h[6] = (u32)rb ;
+			memcpy( rec + 32, E.A + k.consOff + k.lead, k.len ) ;
+			memcpy( rec + 32 + k.len, E.A + k.pwOff + 16ull * k.lead, 16ull * k.len ) ;
+			memcpy( rec + 32 + 17ull * k.len, E.A + k.nameOff, k.nameLen ) ;
+			o += rb ;
+		}
+	}
+#endif
+	return 0 ;
+}
+
 // first device-side error among the given streams (0 if none)
 int T4_API( streams_error )( t4_seqset *const *sets, int n_sets )
 {
@@ -1266,7 +1438,7 @@ int T4_API( streams_run )( t4_seqset *const *sets, int n_sets, const t4_run_cfg 
 {
 	if ( n_sets <= 0 )
 		return T4_E_INVAL ;
-	t4_workload *w = T4_API( workload_upload )( descs, desc_off[n_sets], read_pool, read_pool_bytes, names, n_names ) ;
+	t4_workload *w = workload_upload_impl( descs, desc_off[n_sets], read_pool, read_pool_bytes, names, n_names, true ) ;
 	if ( !w )
 		return T4_E_NOMEM ;
 	int r = T4_API( streams_run_resident )( sets, n_sets, cfg, w, desc_off, 0 ) ;

@@ -76,6 +76,9 @@ struct T4Contig            // SeqSet.hpp:19 `_seqWrapper`, novel contigs only (i
 	int numRead ;
 } ;
 
+// bytes of one packed contig record (t4_streams_pack_contigs)
+T4_HD inline u64 t4_pack_record_bytes( const T4Contig &k ) { return ( 32ull + 17ull * k.len + k.nameLen + 15 ) & ~15ull ; }
+
 struct T4Ovl               // SeqSet.hpp:76 `_overlap`
 {
 	int seqIdx ;
@@ -114,6 +117,7 @@ struct T4Stream            // one SeqSet (SeqSet.hpp:189-230 private members) + 
 	u32 hitCap ;
 	u64 posOff ;                   // per read position scratch, see T4Pos
 	u64 ovlOff, ovlTmpOff, extOff, failOff, anchorOff ;
+	u64 bitsOff ;                  // u32[ovlCap * 32]: IsBaseEqual bit masks of the overhangs (ExtendOverlap)
 	u32 ovlCap ;
 	u64 dpOff ;                    // per-thread DP scratch, dpStride bytes each
 	u32 dpStride ;
@@ -124,6 +128,8 @@ struct T4Stream            // one SeqSet (SeqSet.hpp:189-230 private members) + 
 	int changeKThreshold ;
 	int error ;                    // first T4_E_* raised on the device
 	int errorAux ;
+	// stream-local slab carved out of the arena (keeps small allocations off the global bump pointer)
+	u64 slabTop, slabEnd ;
 	// stats
 	u64 nReads, nAddRead ;
 } ;

@@ -23,6 +23,7 @@
 #endif
 
 #define T4_MAX_NT 128
+#define T4_IDX_CHUNK 256
 #define T4_RADIX_BITS 4
 #define T4_RADIX (1 << T4_RADIX_BITS)
 #define T4_DP_BAND 5
@@ -43,8 +44,14 @@ struct T4Smem
 	u32 radix[T4_RADIX * T4_MAX_NT] ;
 	u32 scan[T4_MAX_NT + 4] ;
 	u64 bu[4] ;
-	int bi[8] ;
+	int bi[16] ;
 	u64 red[2] ;
+	u64 icode[T4_IDX_CHUNK] ; // c_index_op: k-mer codes of the current chunk of positions
+	unsigned char iact[T4_IDX_CHUNK] ;
+	T4Ovl e0 ;             // commit plan of c_add_read
+	long long ph[8] ;      // per-phase clock accumulators (thread 0)
+	long long phLast ;
+	int phCur ;
 } ;
 
 struct T4Ctx
@@ -53,12 +60,31 @@ struct T4Ctx
 	T4Global *g ;
 	T4Stream *st ;
 	T4Smem *sm ;
+	u64 cap ;          // arena capacity (copy of g->cap)
 	int tid, nt ;
 
 	template <class T> T4_HD T *P( u64 off ) const { return (T *)( A + off ) ; }
 } ;
 
 #define T4_PAR_FOR( i, n ) for ( int i = cx.tid ; i < (int)( n ) ; i += cx.nt )
+
+// phase accounting (thread 0): 0 other, 1 probe, 2 hit sort, 3 chains, 4 overlap sort + scoring, 5 ExtendOverlap,
+// 6 decision + commit, 7 InputNovelRead / RepeatAddRead / consensus maintenance
+#if T4_CUDA
+#define T4_PHASE( cx, id )                                       \
+	do                                                           \
+	{                                                            \
+		if ( ( cx ).tid == 0 )                                   \
+		{                                                        \
+			long long now_ = clock64() ;                         \
+			( cx ).sm->ph[( cx ).sm->phCur] += now_ - ( cx ).sm->phLast ; \
+			( cx ).sm->phLast = now_ ;                           \
+			( cx ).sm->phCur = ( id ) ;                          \
+		}                                                        \
+	} while ( 0 )
+#else
+#define T4_PHASE( cx, id ) ( (void)0 )
+#endif
 
 // ---------------------------------------------------------------------------
 // small utilities
@@ -90,6 +116,27 @@ T4_D inline u64 t4_atomic_add( u64 *p, u64 v )
 #endif
 }
 
+T4_D inline u64 t4_atomic_cas( u64 *p, u64 cmp, u64 val )
+{
+#if T4_CUDA
+	return atomicCAS( (unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)val ) ;
+#else
+	u64 o = *p ;
+	if ( o == cmp )
+		*p = val ;
+	return o ;
+#endif
+}
+
+T4_D inline u32 t4_atomic_add32( u32 *p, u32 v )
+{
+#if T4_CUDA
+	return atomicAdd( p, v ) ;
+#else
+	u32 o = *p ; *p += v ; return o ;
+#endif
+}
+
 T4_D inline void t4_raise( T4Ctx &cx, int code, int aux )
 {
 	if ( cx.st->error == 0 )
@@ -99,17 +146,49 @@ T4_D inline void t4_raise( T4Ctx &cx, int code, int aux )
 	}
 }
 
-// Serial bump allocation from the arena.  Returns 0 (and raises T4_E_NOMEM) when exhausted.
-T4_D inline u64 s_alloc( T4Ctx &cx, u64 bytes )
+// Bump allocation from the arena; callable by any thread.  Returns 0 (and raises T4_E_NOMEM) when exhausted.
+// Small requests are served from a stream-local slab (refilled by thread 0 between reads, c_refill_slab) so
+// that thousands of CTAs do not serialise on the one global bump pointer.
+#define T4_SLAB_BYTES ( 128u << 10 )
+#define T4_SLAB_MAX_REQ ( 8u << 10 )
+
+T4_D inline u64 t4_alloc_global( T4Ctx &cx, u64 bytes )
 {
-	bytes = ( bytes + ( T4_ALIGN - 1 ) ) & ~(u64)( T4_ALIGN - 1 ) ;
 	u64 off = t4_atomic_add( &cx.g->top, bytes ) ;
-	if ( off + bytes > cx.g->cap )
+	if ( off + bytes > cx.cap )
 	{
 		t4_raise( cx, T4_E_NOMEM, (int)( bytes >> 10 ) ) ;
 		return 0 ;
 	}
 	return off ;
+}
+
+T4_D inline u64 s_alloc( T4Ctx &cx, u64 bytes )
+{
+	bytes = ( bytes + ( T4_ALIGN - 1 ) ) & ~(u64)( T4_ALIGN - 1 ) ;
+	T4Stream *st = cx.st ;
+	if ( st != 0 && bytes <= T4_SLAB_MAX_REQ && st->slabTop + bytes <= st->slabEnd )
+	{
+		u64 off = t4_atomic_add( &st->slabTop, bytes ) ;
+		if ( off + bytes <= st->slabEnd )
+			return off ;
+	}
+	return t4_alloc_global( cx, bytes ) ;
+}
+
+// Thread 0, at a point where no other thread allocates: start a fresh slab when the current one runs low.
+T4_D inline void s_refill_slab( T4Ctx &cx )
+{
+	T4Stream *st = cx.st ;
+	if ( st->slabTop + ( T4_SLAB_BYTES / 4 ) > st->slabEnd )
+	{
+		u64 off = t4_alloc_global( cx, T4_SLAB_BYTES ) ;
+		if ( off )
+		{
+			st->slabTop = off ;
+			st->slabEnd = off + T4_SLAB_BYTES ;
+		}
+	}
 }
 
 T4_D inline T4Contig *t4_seq( T4Ctx &cx, int idx ) { return cx.P<T4Contig>( cx.st->seqsOff ) + idx ; }
@@ -183,6 +262,54 @@ T4_D inline void s_dir_grow( T4Ctx &cx )
 	}
 	st->dirOff = off ;
 	st->dirCap = newCap ;
+}
+
+// Collective variant: zero and re-insert in parallel (keys are unique, slots are claimed with a CAS).
+T4_D inline void c_dir_grow( T4Ctx &cx )
+{
+	T4Stream *st = cx.st ;
+	T4_SYNC() ;
+	u32 oldCap = st->dirCap ;
+	u32 newCap = oldCap * 2 ;
+	if ( cx.tid == 0 )
+	{
+		u64 off = s_alloc( cx, (u64)newCap * sizeof( T4Dir ) ) ;
+		cx.sm->bu[0] = off ;
+	}
+	T4_SYNC() ;
+	u64 off = cx.sm->bu[0] ;
+	T4_SYNC() ;
+	if ( !off )
+		return ;
+	T4Dir *nd = cx.P<T4Dir>( off ) ;
+	T4Dir *od = cx.P<T4Dir>( st->dirOff ) ;
+	for ( u32 i = cx.tid ; i < newCap ; i += cx.nt )
+		nd[i].key = 0 ;
+	T4_SYNC() ;
+	for ( u32 i = cx.tid ; i < oldCap ; i += cx.nt )
+	{
+		T4Dir e = od[i] ;
+		if ( e.key == 0 )
+			continue ;
+		u32 s = t4_dir_slot( e.key, newCap ) ;
+		while ( 1 )
+		{
+			if ( nd[s].key == 0 && t4_atomic_cas( &nd[s].key, 0ull, e.key ) == 0 )
+				break ;
+			s = ( s + 1 ) & ( newCap - 1 ) ;
+		}
+		nd[s].listOff = e.listOff ;
+		nd[s].cnt = e.cnt ;
+		nd[s].cap = e.cap ;
+		nd[s].lock = 0 ;
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+	{
+		st->dirOff = off ;
+		st->dirCap = newCap ;
+	}
+	T4_SYNC() ;
 }
 
 T4_D inline T4Dir *s_dir_get( T4Ctx &cx, u64 key )
@@ -351,6 +478,176 @@ T4_D inline void s_remove_index( T4Ctx &cx, const char *s, int len, int id, int 
 }
 
 // ---------------------------------------------------------------------------
+// collective index maintenance.  The three KmerIndex walkers (Build / Update / RemoveIndexFromRead,
+// KmerIndex.hpp:118-201) only interact through the postings list of ONE k-mer code, so positions are
+// processed in chunks, every distinct code of a chunk is owned by the thread of its first occurrence,
+// and the owner applies that code's positions in ascending order -- exactly the reference's sequence
+// restricted to that list.  Chunks run one after the other, so order across chunks is ascending too.
+// ---------------------------------------------------------------------------
+T4_D inline u32 c_scan_threads( T4Ctx &cx, u32 v, u32 &total ) ;
+
+#define T4_IDX_BUILD 0
+#define T4_IDX_REMOVE 1
+#define T4_IDX_UPDATE 2
+
+T4_D inline T4Dir *t4_dir_find_or_claim( T4Ctx &cx, u64 key )
+{
+	T4Stream *st = cx.st ;
+	T4Dir *dir = cx.P<T4Dir>( st->dirOff ) ;
+	u32 cap = st->dirCap ;
+	u32 s = t4_dir_slot( key, cap ) ;
+	while ( 1 )
+	{
+		u64 kk = dir[s].key ;
+		if ( kk == key )
+			return dir + s ;
+		if ( kk == 0 )
+		{
+			u64 old = t4_atomic_cas( &dir[s].key, 0ull, key ) ;
+			if ( old == 0 )
+			{
+				dir[s].listOff = 0 ;
+				dir[s].cnt = 0 ;
+				dir[s].cap = 0 ;
+				dir[s].lock = 0 ;
+				t4_atomic_add32( &st->dirUsed, 1 ) ;
+				return dir + s ;
+			}
+			if ( old == key )
+				return dir + s ;
+		}
+		s = ( s + 1 ) & ( cap - 1 ) ;
+	}
+}
+
+T4_D inline void t4_list_append( T4Ctx &cx, T4Dir *d, u64 v )
+{
+	if ( d->cnt == d->cap )
+	{
+		u32 nc = d->cap ? d->cap * 2 : 4 ;
+		u64 off = s_alloc( cx, (u64)nc * 8 ) ;
+		if ( !off )
+			return ;
+		u64 *nl = cx.P<u64>( off ) ;
+		u64 *ol = cx.P<u64>( d->listOff ) ;
+		for ( u32 i = 0 ; i < d->cnt ; ++i )
+			nl[i] = ol[i] ;
+		d->listOff = off ;
+		d->cap = nc ;
+	}
+	cx.P<u64>( d->listOff )[d->cnt] = v ;
+	++d->cnt ;
+}
+
+// mode BUILD:  BuildIndexFromRead( s, len, id, barcode, shift = arg )
+// mode REMOVE: RemoveIndexFromRead( s, len, id, barcode, offset = arg )
+// mode UPDATE: UpdateIndexFromRead( s, len, barcode, shift = arg, oldId, id )
+T4_D inline void c_index_op( T4Ctx &cx, const char *s, int len, int mode, int id, int barcode, int arg, int oldId )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	const int kl = st->kmerLength ;
+	T4_SYNC() ;
+	if ( len < kl )
+		return ;
+	const u64 mask = kl < 32 ? ( ( 1ull << ( 2 * kl ) ) - 1ull ) : ~0ull ;
+	for ( int c0 = kl - 1 ; c0 < len ; c0 += T4_IDX_CHUNK )
+	{
+		int cn = len - c0 < T4_IDX_CHUNK ? len - c0 : T4_IDX_CHUNK ;
+		u32 mine = 0 ;
+		T4_PAR_FOR( j, cn )
+		{
+			int i = c0 + j ;
+			u64 code = 0 ;
+			bool valid = true ;
+			for ( int x = i - kl + 1 ; x <= i ; ++x )
+			{
+				char c = s[x] ;
+				code = ( code << 2 ) | (u64)t4_nuc( c ) ;
+				if ( c == 'N' )
+					valid = false ;
+			}
+			bool act = valid ;
+			if ( mode == T4_IDX_BUILD && valid )
+			{
+				u64 prev = 0 ; // KmerCode prevKmerCode( kl ) starts at 0; afterwards the rolling code of position i-1
+				if ( i > kl - 1 )
+					prev = ( ( code >> 2 ) | ( (u64)t4_nuc( s[i - kl] ) << ( 2 * ( kl - 1 ) ) ) ) & mask ;
+				act = ( i == kl || code != prev ) ;
+			}
+			sm->icode[j] = code ;
+			sm->iact[j] = act ? 1 : 0 ;
+			if ( act )
+				++mine ;
+		}
+		if ( mode == T4_IDX_BUILD )
+		{
+			u32 total ;
+			c_scan_threads( cx, mine, total ) ;
+			while ( !st->error && ( st->dirUsed + total + 1 ) * 2 > st->dirCap )
+				c_dir_grow( cx ) ;
+		}
+		T4_SYNC() ;
+		if ( st->error )
+			return ;
+		T4_PAR_FOR( j, cn )
+		{
+			if ( !sm->iact[j] )
+				continue ;
+			u64 code = sm->icode[j] ;
+			// uniform scan of the chunk (same trip count in every lane, broadcast shared-memory reads)
+			int first = -1, nsame = 0 ;
+			for ( int x = 0 ; x < cn ; ++x )
+				if ( sm->icode[x] == code && sm->iact[x] )
+				{
+					if ( first < 0 )
+						first = x ;
+					++nsame ;
+				}
+			if ( first != j )
+				continue ;
+			u64 key = t4_index_key( st, code, barcode ) ;
+			T4Dir *d = ( mode == T4_IDX_BUILD ) ? t4_dir_find_or_claim( cx, key ) : t4_dir_find( cx, key ) ;
+			if ( !d )
+				continue ;
+			for ( int x = j ; x < cn && nsame > 0 ; ++x )
+			{
+				if ( !sm->iact[x] || sm->icode[x] != code )
+					continue ;
+				--nsame ;
+				int pos = c0 + x - kl + 1 ;
+				if ( mode == T4_IDX_BUILD )
+					t4_list_append( cx, d, ( (u64)(u32)id << 32 ) | (u32)( pos + arg ) ) ;
+				else if ( mode == T4_IDX_REMOVE )
+				{
+					u64 v = ( (u64)(u32)id << 32 ) | (u32)( pos + arg ) ;
+					u64 *l = cx.P<u64>( d->listOff ) ;
+					for ( u32 y = 0 ; y < d->cnt ; ++y )
+						if ( l[y] == v )
+						{
+							l[y] = l[d->cnt - 1] ;
+							--d->cnt ;
+							break ;
+						}
+				}
+				else
+				{
+					u64 v = ( (u64)(u32)oldId << 32 ) | (u32)pos ;
+					u64 *l = cx.P<u64>( d->listOff ) ;
+					for ( u32 y = 0 ; y < d->cnt ; ++y )
+						if ( l[y] == v )
+						{
+							l[y] = ( (u64)(u32)id << 32 ) | (u32)( pos + arg ) ;
+							break ;
+						}
+				}
+			}
+		}
+		T4_SYNC() ;
+	}
+}
+
+// ---------------------------------------------------------------------------
 // contig storage
 // ---------------------------------------------------------------------------
 // Append a contig slot (seqs.push_back).  Serial.
@@ -509,10 +806,11 @@ T4_D inline void c_ensure_ovl( T4Ctx &cx, u32 n )
 			u64 c = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
 			u64 d = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
 			u64 e = s_alloc( cx, (u64)nc * 8 ) ;
-			if ( a && b && c && d && e )
+			u64 f = s_alloc( cx, (u64)nc * 32 * 4 ) ;
+			if ( a && b && c && d && e && f )
 			{
 				// the live overlaps (if any) stay valid: callers only grow before filling
-				st->ovlOff = a ; st->ovlTmpOff = b ; st->extOff = c ; st->failOff = d ; st->anchorOff = e ;
+				st->ovlOff = a ; st->ovlTmpOff = b ; st->extOff = c ; st->failOff = d ; st->anchorOff = e ; st->bitsOff = f ;
 				st->ovlCap = nc ;
 			}
 		}
@@ -551,6 +849,39 @@ T4_D inline u64 *c_sort_keys( T4Ctx &cx, u64 *a, u64 *b, u32 n )
 #else
 	if ( n <= 1 )
 		return a ;
+	if ( n <= T4_RADIX * T4_MAX_NT / 2 )
+	{
+		// small inputs (the common case for sharded streams): bitonic sort entirely in shared memory,
+		// in the area the radix counters would use (u64[1024])
+		u64 *sk = (u64 *)cx.sm->radix ;
+		u32 np = 1 ;
+		while ( np < n )
+			np <<= 1 ;
+		for ( u32 i = cx.tid ; i < np ; i += cx.nt )
+			sk[i] = i < n ? a[i] : ~0ull ;
+		T4_SYNC() ;
+		for ( u32 size = 2 ; size <= np ; size <<= 1 )
+			for ( u32 stride = size >> 1 ; stride > 0 ; stride >>= 1 )
+			{
+				for ( u32 t = cx.tid ; t < np / 2 ; t += cx.nt )
+				{
+					u32 lo = 2 * t - ( t & ( stride - 1 ) ) ;
+					u32 hi = lo + stride ;
+					bool up = ( ( lo & size ) == 0 ) ;
+					u64 x = sk[lo], y = sk[hi] ;
+					if ( ( x > y ) == up )
+					{
+						sk[lo] = y ;
+						sk[hi] = x ;
+					}
+				}
+				T4_SYNC() ;
+			}
+		for ( u32 i = cx.tid ; i < n ; i += cx.nt )
+			a[i] = sk[i] ;
+		T4_SYNC() ;
+		return a ;
+	}
 	// which bits vary at all?
 	u64 vo = 0, va = ~0ull ;
 	for ( u32 i = cx.tid ; i < n ; i += cx.nt )
@@ -797,6 +1128,159 @@ T4_HD inline int t4_dp_posweight( const int *tw, int lent, const char *p, int le
 	return ret ;
 }
 
+// The same alignment for lent == lenp == n (every hot-path call: overhangs and same-diagonal gaps), band +-5.
+// Both score rows live in registers (the 13-wide window is fully unrolled), IsBaseEqual outcomes slide through a
+// 64-bit register as one nibble per column (bit b = "base b equals this column"), and the traceback decision of a
+// row is packed into one 32-bit word (2 bits per band cell).  act32: n + 1 words.
+T4_HD inline unsigned t4_eq_nibble( const int *w )
+{
+	int sum = w[0] + w[1] + w[2] + w[3] ;
+	if ( sum == 0 )
+		return 0xFu ;
+	return ( sum < 3 * w[0] ? 1u : 0u ) | ( sum < 3 * w[1] ? 2u : 0u ) | ( sum < 3 * w[2] ? 4u : 0u ) | ( sum < 3 * w[3] ? 8u : 0u ) ;
+}
+
+T4_HD inline int t4_dp_equal( const int *tw, const char *p, int n, signed char *align, u32 *act32, bool diagKnownBad, int *usedFullDp )
+{
+	if ( usedFullDp )
+		*usedFullDp = 0 ;
+	if ( n == 0 )
+	{
+		align[0] = -1 ;
+		return 0 ;
+	}
+	if ( n == 1 )
+	{
+		bool eq = t4_base_equal( tw, p[0] ) ;
+		align[0] = eq ? EDIT_MATCH : EDIT_MISMATCH ;
+		align[1] = -1 ;
+		return eq ? SCORE_MATCH : SCORE_MISMATCH ;
+	}
+	if ( !diagKnownBad )
+	{
+		int score = 0 ;
+		for ( int i = 0 ; i < n ; ++i )
+		{
+			if ( t4_base_equal( tw + 4 * i, p[i] ) )
+			{
+				align[i] = EDIT_MATCH ;
+				score += SCORE_MATCH ;
+			}
+			else
+			{
+				align[i] = EDIT_MISMATCH ;
+				score += SCORE_MISMATCH ;
+			}
+		}
+		align[n] = -1 ;
+		if ( score >= n * SCORE_MATCH + 2 * SCORE_INDEL )
+			return score ;
+	}
+	if ( usedFullDp )
+		*usedFullDp = 1 ;
+	const int negInf = ( n + 1 ) * ( n + 1 ) * SCORE_INDEL ;
+	int prev[13], cur[13] ;
+	// row 0, window columns j = l - 6
+#pragma unroll
+	for ( int l = 0 ; l < 13 ; ++l )
+	{
+		int j = l - 6 ;
+		prev[l] = ( j == 0 ) ? 0 : ( SCORE_INDEL + j * SCORE_INDEL ) ;
+	}
+	// eq nibble of window slot l (column j = wlo + l, posWeight index j - 1) at bits [4l, 4l+4)
+	unsigned long long eqw = 0 ;
+#pragma unroll
+	for ( int l = 1 ; l <= 11 ; ++l )
+	{
+		int c = l - 6 ; // posWeight index for row 1: j - 1 with j = (1 - 6) + l
+		if ( c >= 0 && c < n )
+			eqw |= (unsigned long long)t4_eq_nibble( tw + 4 * c ) << ( 4 * l ) ;
+	}
+	for ( int i = 1 ; i <= n ; ++i )
+	{
+		const int wlo = i - 6 ;
+		const int start = ( i - 5 < 1 ) ? 1 : ( i - 5 ) ;
+		const int end = ( i + 5 > n ) ? n : ( i + 5 ) ;
+		const char pc = p[i - 1] ;
+		const int pn = t4_nuc( pc ) ;
+		const bool pN = ( pc == 'N' ) ;
+		u32 arow = 0 ;
+#pragma unroll
+		for ( int l = 0 ; l < 13 ; ++l )
+			cur[l] = negInf ;
+		if ( wlo <= 0 )
+		{
+			// column 0 sits at slot -wlo (0..5)
+#pragma unroll
+			for ( int l = 0 ; l <= 5 ; ++l )
+				if ( l == -wlo )
+					cur[l] = SCORE_INDEL + i * SCORE_INDEL ;
+		}
+#pragma unroll
+		for ( int l = 1 ; l <= 11 ; ++l )
+		{
+			int j = wlo + l ;
+			if ( j >= start && j <= end )
+			{
+				bool eq = pN || ( ( (unsigned)( eqw >> ( 4 * l ) ) >> pn ) & 1u ) ;
+				int diff = eq ? SCORE_MATCH : SCORE_MISMATCH ;
+				int dg = prev[l] + diff ;
+				int lf = cur[l - 1] + SCORE_INDEL ;
+				int up = prev[l + 1] + SCORE_INDEL ;
+				int score = dg ;
+				if ( lf > score ) score = lf ;
+				if ( up > score ) score = up ;
+				cur[l] = score ;
+				u32 a = 0 ;
+				if ( lf == score ) a = EDIT_DELETE ;
+				if ( up == score ) a = EDIT_INSERT ;
+				if ( dg == score ) a = eq ? EDIT_MATCH : EDIT_MISMATCH ;
+				arow |= a << ( 2 * l ) ;
+			}
+		}
+		act32[i] = arow ;
+#pragma unroll
+		for ( int l = 0 ; l < 13 ; ++l )
+			prev[l] = cur[l] ;
+		// slide the eq window: slot l of row i+1 is slot l+1 of row i; new column at slot 11 has posWeight index i + 5
+		eqw >>= 4 ;
+		eqw &= ~( 0xFull << 44 ) ;
+		if ( i + 5 < n )
+			eqw |= (unsigned long long)t4_eq_nibble( tw + 4 * ( i + 5 ) ) << 44 ;
+	}
+	int ret = prev[6] ; // column n of row n: slot n - (n - 6)
+	int tagi = n, tagj = n, tag = 0 ;
+	while ( tagi > 0 || tagj > 0 )
+	{
+		int a ;
+		if ( tagi > 0 && tagj > 0 )
+			a = (int)( ( act32[tagi] >> ( 2 * ( tagj - ( tagi - 6 ) ) ) ) & 3u ) ;
+		else if ( tagj > 0 )
+			a = ( tagj >= 2 ) ? EDIT_DELETE : EDIT_MATCH ;
+		else
+			a = ( tagi >= 2 ) ? EDIT_INSERT : EDIT_MATCH ;
+		align[tag] = (signed char)a ;
+		++tag ;
+		if ( a == EDIT_DELETE )
+			--tagj ;
+		else if ( a == EDIT_INSERT )
+			--tagi ;
+		else
+		{
+			--tagi ;
+			--tagj ;
+		}
+	}
+	align[tag] = -1 ;
+	for ( int i = 0, j = tag - 1 ; i < j ; ++i, --j )
+	{
+		signed char tmp = align[i] ;
+		align[i] = align[j] ;
+		align[j] = tmp ;
+	}
+	return ret ;
+}
+
 // SeqSet::GetAlignStats (SeqSet.hpp:570)
 T4_HD inline void t4_align_stats( const signed char *align, bool update, int &matchCnt, int &mismatchCnt, int &indelCnt )
 {
@@ -844,8 +1328,11 @@ T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool al
 	T4Pos *pos = cx.P<T4Pos>( st->posOff ) ;
 	const int m = len - k + 1 ; // positions per pass, index q = i - (k-1)
 	// directory probes for every k-mer of both strand passes, in parallel.  Whether a probe "counts"
-	// (SeqSet.hpp:1376: first k-mer, or code differs from prevKmerCode) is decided by the serial pass below,
-	// because the reference's `continue` statements skip the prevKmerCode update.
+	// (SeqSet.hpp:1376: first k-mer, or code differs from prevKmerCode) is decided below, because the
+	// reference's `continue` statements skip the prevKmerCode update.
+	if ( cx.tid == 0 )
+		sm->bi[2] = 0 ;
+	T4_SYNC() ;
 	for ( int x = cx.tid ; x < 2 * m ; x += cx.nt )
 	{
 		int pass = x >= m ;
@@ -874,13 +1361,66 @@ T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool al
 			{
 				po->cnt = d->cnt ;
 				po->listOff = d->listOff ;
+				if ( d->cnt >= 100 )
+					sm->bi[2] = 1 ;
 			}
 		}
 	}
 	T4_SYNC() ;
+	const bool anyLarge = sm->bi[2] != 0 ;
+	T4_SYNC() ;
+	if ( !anyLarge )
+	{
+		// no list reaches 100 postings: neither skip rule can fire, prevKmerCode is always the previous k-mer,
+		// so "taken" is a per-position predicate and the hit slots are an exclusive prefix sum
+		int tot = 2 * m ;
+		int chunk = ( tot + cx.nt - 1 ) / cx.nt ;
+		int lo = cx.tid * chunk ;
+		int hi = lo + chunk < tot ? lo + chunk : tot ;
+		u32 cnt = 0, looks = 0 ;
+		for ( int x = lo ; x < hi ; ++x )
+		{
+			int pass = x >= m ;
+			int q = pass ? x - m : x ;
+			if ( ( pass == 0 && strand == -1 ) || ( pass == 1 && strand == 1 ) )
+				continue ;
+			T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+			if ( q == 0 || po->code != po[-1].code )
+			{
+				++looks ;
+				cnt += po->cnt ;
+			}
+		}
+		u32 total ;
+		u32 o = c_scan_threads( cx, cnt, total ) ;
+		for ( int x = lo ; x < hi ; ++x )
+		{
+			int pass = x >= m ;
+			int q = pass ? x - m : x ;
+			if ( ( pass == 0 && strand == -1 ) || ( pass == 1 && strand == 1 ) )
+				continue ;
+			T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+			if ( ( q == 0 || po->code != po[-1].code ) && po->cnt > 0 )
+			{
+				po->base = o ;
+				o += po->cnt ;
+			}
+		}
+		u32 ltot ;
+		c_scan_threads( cx, looks, ltot ) ;
+		if ( cx.tid == 0 )
+		{
+			sm->bi[0] = (int)total ;
+			sm->bi[1] = 0 ;
+			t4_atomic_add( &cx.g->counters[2], (u64)ltot ) ;
+			t4_atomic_add( &cx.g->counters[3], (u64)total ) ;
+			t4_atomic_add( &cx.g->counters[4], (u64)total ) ;
+			t4_atomic_add( &cx.g->counters[5], (u64)( ( len + 3 ) / 4 ) ) ;
+		}
+	}
 	// sequential scan along the read: equal-to-previous rule with the stale prevKmerCode semantics and the
 	// >=100-postings skip rule (SeqSet.hpp:1376-1392, 1441-1455)
-	if ( cx.tid == 0 )
+	else if ( cx.tid == 0 )
 	{
 		int skipLimit = k / 2 ;
 		u32 total = 0 ;
@@ -933,32 +1473,58 @@ T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool al
 	T4_SYNC() ;
 	u32 H = (u32)sm->bi[0] ;
 	*anyBig = sm->bi[1] ;
+	T4_SYNC() ;
 	c_ensure_hits( cx, H ) ;
 	if ( st->error )
 		return 0 ;
 	u64 *keys = cx.P<u64>( st->keysAOff ) ;
-	// emit: one lookup after the other, postings spread over the threads (coalesced 8-byte loads)
-	for ( int pass = 0 ; pass < 2 ; ++pass )
-		for ( int q = 0 ; q < m ; ++q )
+	// emit.  Short lists: one thread copies the list of its own position; long lists (>= 100 postings exist)
+	// are spread over the CTA with coalesced 8-byte loads.
+	for ( int x = cx.tid ; x < 2 * m ; x += cx.nt )
+	{
+		int pass = x >= m ;
+		int q = pass ? x - m : x ;
+		T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+		u32 base = po->base ;
+		if ( base == 0xffffffffu )
+			continue ;
+		u32 cnt = po->cnt ;
+		if ( anyLarge && cnt > 32 )
+			continue ;
+		const u64 *l = cx.P<u64>( po->listOff ) ;
+		for ( u32 j = 0 ; j < cnt ; ++j )
 		{
-			T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
-			u32 base = po->base ;
-			if ( base == 0xffffffffu )
-				continue ;
-			u32 cnt = po->cnt ;
-			const u64 *l = cx.P<u64>( po->listOff ) ;
-			int big = ( barcode == -1 && cnt > T4_BIG_REPEAT ) ;
-			for ( u32 j = cx.tid ; j < cnt ; j += cx.nt )
-			{
-				u64 v = l[j] ;
-				int idx = (int)( v >> 32 ) ;
-				int off = (int)(u32)v ;
-				u64 key = t4_key_of( pass ? -1 : 1, idx, q, off, big ) ;
-				if ( barcode != -1 && t4_seq( cx, idx )->barcode != barcode )
-					key = T4_KEY_INVALID ;
-				keys[base + j] = key ;
-			}
+			u64 v = l[j] ;
+			int idx = (int)( v >> 32 ) ;
+			int off = (int)(u32)v ;
+			u64 key = t4_key_of( pass ? -1 : 1, idx, q, off, 0 ) ;
+			if ( barcode != -1 && t4_seq( cx, idx )->barcode != barcode )
+				key = T4_KEY_INVALID ;
+			keys[base + j] = key ;
 		}
+	}
+	if ( anyLarge )
+		for ( int pass = 0 ; pass < 2 ; ++pass )
+			for ( int q = 0 ; q < m ; ++q )
+			{
+				T4Pos *po = pos + pass * T4_DEV_MAX_READ + q ;
+				u32 base = po->base ;
+				u32 cnt = po->cnt ;
+				if ( base == 0xffffffffu || cnt <= 32 )
+					continue ;
+				const u64 *l = cx.P<u64>( po->listOff ) ;
+				int big = ( barcode == -1 && cnt > T4_BIG_REPEAT ) ;
+				for ( u32 j = cx.tid ; j < cnt ; j += cx.nt )
+				{
+					u64 v = l[j] ;
+					int idx = (int)( v >> 32 ) ;
+					int off = (int)(u32)v ;
+					u64 key = t4_key_of( pass ? -1 : 1, idx, q, off, big ) ;
+					if ( barcode != -1 && t4_seq( cx, idx )->barcode != barcode )
+						key = T4_KEY_INVALID ;
+					keys[base + j] = key ;
+				}
+			}
 	T4_SYNC() ;
 	return H ;
 }
@@ -1250,7 +1816,9 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 	for ( int pass = skipRepeats ? 0 : 1 ; pass < 2 && overlapCnt == 0 ; ++pass )
 	{
 		int anyBig = 0 ;
+		T4_PHASE( cx, 1 ) ;
 		u32 H = c_get_hits( cx, len, strand, barcode, pass == 0, &anyBig ) ;
+		T4_PHASE( cx, 2 ) ;
 		if ( st->error )
 			return 0 ;
 		u64 *a = cx.P<u64>( st->keysAOff ) ;
@@ -1278,10 +1846,12 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 		}
 		keys = sorted ;
 		u64 *tmp = ( sorted == a ) ? b : a ;
+		T4_PHASE( cx, 3 ) ;
 		overlapCnt = c_overlaps_from_hits( cx, sorted, H, tmp, keysR, st->hitLenRequired, pass == 0 ? 0 : 1 ) ;
 		if ( st->error )
 			return 0 ;
 	}
+	T4_PHASE( cx, 4 ) ;
 	if ( overlapCnt == 0 )
 		return 0 ;
 	c_sort_overlaps( cx, overlapCnt ) ;
@@ -1332,7 +1902,7 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 					break ;
 				}
 				int full = 0 ;
-				t4_dp_posweight( pw + 4 * ( b0 + k ), gap, r + a0 + k, gap, ds.align, ds.rows, ds.act, &full ) ;
+				t4_dp_equal( pw + 4 * ( b0 + k ), r + a0 + k, gap, ds.align, (u32 *)ds.act, false, &full ) ;
 				fullDps += full ;
 				int cnt0, cnt1, cnt2 ;
 				t4_align_stats( ds.align, false, cnt0, cnt1, cnt2 ) ;
@@ -1433,61 +2003,137 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 // ---------------------------------------------------------------------------
 // SeqSet::ExtendOverlap (SeqSet.hpp:1165-1277).  Pure function of (read, contig, overlap).
 // ---------------------------------------------------------------------------
+struct T4AlignView      // an edit string either as an explicit array (full DP) or as match bits (all-diagonal alignment)
+{
+	const signed char *a ;
+	const u32 *bits ;
+	int n ;
+	int dp ;
+	T4_D inline int get( int i ) const
+	{
+		if ( a )
+			return a[i] ;
+		return ( ( bits[i >> 5] >> ( i & 31 ) ) & 1 ) ? EDIT_MATCH : EDIT_MISMATCH ;
+	}
+} ;
+
+// GlobalAlignment_PosWeight for an overhang of equal lengths n whose IsBaseEqual outcomes are given as bits:
+// the trivial cases and the <= 2 mismatch fast path (AlignAlgo.hpp:59-103) need no DP at all.
+T4_D inline T4AlignView t4_overhang_align( const int *tw, const char *p, int n, const u32 *bits, T4DpScratch &ds )
+{
+	T4AlignView v ;
+	v.a = 0 ;
+	v.bits = bits ;
+	v.n = n ;
+	v.dp = 0 ;
+	if ( n <= 1 )
+		return v ;
+	int matches = 0 ;
+	for ( int w = 0 ; w * 32 < n ; ++w )
+	{
+		u32 x = bits[w] ;
+		if ( ( w + 1 ) * 32 > n )
+			x &= ( 1u << ( n - w * 32 ) ) - 1u ;
+#if T4_CUDA
+		matches += __popc( x ) ;
+#else
+		matches += __builtin_popcount( x ) ;
+#endif
+	}
+	int score = SCORE_MATCH * matches + SCORE_MISMATCH * ( n - matches ) ;
+	if ( score >= n * SCORE_MATCH + 2 * SCORE_INDEL )
+		return v ;
+	t4_dp_equal( tw, p, n, ds.align, (u32 *)ds.act, true, 0 ) ;
+	v.dp = 1 ;
+	v.a = ds.align ;
+	v.bits = 0 ;
+	int l = 0 ;
+	while ( ds.align[l] != -1 )
+		++l ;
+	v.n = l ;
+	return v ;
+}
+
+// lbits / rbits: IsBaseEqual( posWeight column, read base ) for the left / right overhang, bit t = t-th overhang position
 T4_D inline int t4_extend_overlap( T4Ctx &cx, const char *r, int len, T4Contig *seq, double mismatchThresholdFactor,
-	T4DpScratch &ds, const T4Ovl &overlap, T4Ovl &ext )
+	T4DpScratch &ds, const T4Ovl &overlap, T4Ovl &ext, const u32 *lbits, const u32 *rbits )
 {
 	T4Stream *st = cx.st ;
-	int matchCnt, mismatchCnt, indelCnt ;
+	int matchCnt = 0, mismatchCnt = 0, indelCnt = 0 ;
 	int leftOverhangSize = t4_min( overlap.readStart, overlap.seqStart ) ;
 	int ret = 1 ;
 	int i, k ;
 	int goodLeftOverhangSize = 0 ;
 	int *pw = t4_pw( cx, seq ) ;
-	signed char *align = ds.align ;
-	t4_dp_posweight( pw + 4 * ( overlap.seqStart - leftOverhangSize ), leftOverhangSize,
-		r + overlap.readStart - leftOverhangSize, leftOverhangSize, align, ds.rows, ds.act, 0 ) ;
-	t4_align_stats( align, false, matchCnt, mismatchCnt, indelCnt ) ;
-	if ( indelCnt > 0 )
 	{
-		leftOverhangSize = 0 ;
-		ret = 0 ;
-	}
-	for ( i = 0 ; align[i] != -1 ; ++i )
-		;
-	int tmpMatchCnt = 0 ;
-	for ( i = i - 1, k = 1 ; i >= 0 ; --i, ++k )
-	{
-		if ( align[i] == EDIT_MATCH )
+		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqStart - leftOverhangSize ), r + overlap.readStart - leftOverhangSize,
+			leftOverhangSize, lbits, ds ) ;
+		if ( av.dp )
+			t4_atomic_add( &cx.g->counters[1], 1 ) ;
+		for ( i = 0 ; i < av.n ; ++i )
 		{
-			++tmpMatchCnt ;
-			if ( tmpMatchCnt > 0.75 * k )
-				goodLeftOverhangSize = k ;
+			int e = av.get( i ) ;
+			if ( e == EDIT_MATCH )
+				++matchCnt ;
+			else if ( e == EDIT_MISMATCH )
+				++mismatchCnt ;
+			else
+				++indelCnt ;
 		}
-		else if ( align[i] != EDIT_MISMATCH )
-			break ;
+		if ( indelCnt > 0 )
+		{
+			leftOverhangSize = 0 ;
+			ret = 0 ;
+		}
+		int tmpMatchCnt = 0 ;
+		for ( i = av.n - 1, k = 1 ; i >= 0 ; --i, ++k )
+		{
+			int e = av.get( i ) ;
+			if ( e == EDIT_MATCH )
+			{
+				++tmpMatchCnt ;
+				if ( tmpMatchCnt > 0.75 * k )
+					goodLeftOverhangSize = k ;
+			}
+			else if ( e != EDIT_MISMATCH )
+				break ;
+		}
 	}
 	int rightOverhangSize = t4_min( len - 1 - overlap.readEnd, seq->len - 1 - overlap.seqEnd ) ;
 	int goodRightOverhangSize = 0 ;
-	t4_dp_posweight( pw + 4 * ( overlap.seqEnd + 1 ), rightOverhangSize, r + overlap.readEnd + 1, rightOverhangSize, align,
-		ds.rows, ds.act, 0 ) ;
-	int oldIndelCnt = indelCnt ;
-	t4_align_stats( align, true, matchCnt, mismatchCnt, indelCnt ) ;
-	if ( indelCnt > oldIndelCnt )
 	{
-		rightOverhangSize = 0 ;
-		ret = 0 ;
-	}
-	tmpMatchCnt = 0 ;
-	for ( i = 0 ; align[i] != -1 ; ++i )
-	{
-		if ( align[i] == EDIT_MATCH )
+		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqEnd + 1 ), r + overlap.readEnd + 1, rightOverhangSize, rbits, ds ) ;
+		if ( av.dp )
+			t4_atomic_add( &cx.g->counters[1], 1 ) ;
+		int oldIndelCnt = indelCnt ;
+		for ( i = 0 ; i < av.n ; ++i )
 		{
-			++tmpMatchCnt ;
-			if ( tmpMatchCnt > 0.75 * ( i + 1 ) )
-				goodRightOverhangSize = i + 1 ;
+			int e = av.get( i ) ;
+			if ( e == EDIT_MATCH )
+				++matchCnt ;
+			else if ( e == EDIT_MISMATCH )
+				++mismatchCnt ;
+			else
+				++indelCnt ;
 		}
-		else if ( align[i] != EDIT_MISMATCH )
-			break ;
+		if ( indelCnt > oldIndelCnt )
+		{
+			rightOverhangSize = 0 ;
+			ret = 0 ;
+		}
+		int tmpMatchCnt = 0 ;
+		for ( i = 0 ; i < av.n ; ++i )
+		{
+			int e = av.get( i ) ;
+			if ( e == EDIT_MATCH )
+			{
+				++tmpMatchCnt ;
+				if ( tmpMatchCnt > 0.75 * ( i + 1 ) )
+					goodRightOverhangSize = i + 1 ;
+			}
+			else if ( e != EDIT_MISMATCH )
+				break ;
+		}
 	}
 	int mismatchThreshold = 2 ;
 	if ( leftOverhangSize >= 2 )
@@ -1636,6 +2282,30 @@ T4_D inline void s_substitute_consensus_pos( T4Ctx &cx, int seqIdx, int pos, cha
 	s_build_index( cx, cons + start, end - start + 1, seqIdx, seq->barcode, start ) ;
 }
 
+// SeqSet::SubstituteConsensusPos, collective variant
+T4_D inline void c_substitute_consensus_pos( T4Ctx &cx, int seqIdx, int pos, char c )
+{
+	T4Contig *seq = t4_seq( cx, seqIdx ) ;
+	char *cons = t4_cons( cx, seq ) ;
+	T4_SYNC() ;
+	bool skip = ( pos >= seq->len || cons[pos] == c ) ;
+	T4_SYNC() ;
+	if ( skip )
+		return ;
+	int kl = cx.st->kmerLength ;
+	int start = pos - kl + 1 ;
+	int end = pos + kl - 1 ;
+	if ( start < 0 )
+		start = 0 ;
+	if ( end >= seq->len )
+		end = seq->len - 1 ;
+	c_index_op( cx, cons + start, end - start + 1, T4_IDX_REMOVE, seqIdx, seq->barcode, start, 0 ) ;
+	if ( cx.tid == 0 )
+		cons[pos] = c ;
+	T4_SYNC() ;
+	c_index_op( cx, cons + start, end - start + 1, T4_IDX_BUILD, seqIdx, seq->barcode, start, 0 ) ;
+}
+
 // SeqSet::UpdateConsensus (SeqSet.hpp:4537-4588).  Serial.
 T4_D inline void s_update_consensus( T4Ctx &cx, int seqIdx, bool updateIndex )
 {
@@ -1718,16 +2388,41 @@ T4_D inline void c_update_all_consensus( T4Ctx &cx )
 		}
 		T4_SYNC() ;
 	}
-	if ( cx.tid == 0 )
+	if ( !useFlags )
 	{
-		for ( int s = 0 ; s < st->nSeqs ; ++s )
+		if ( cx.tid == 0 )
+			for ( int s = 0 ; s < st->nSeqs ; ++s )
+				if ( t4_seq( cx, s )->consOff != 0 )
+					s_update_consensus( cx, s, true ) ;
+		T4_SYNC() ;
+		return ;
+	}
+	for ( int s = 0 ; s < st->nSeqs ; ++s )
+	{
+		if ( !flag[s] )
+			continue ;
+		// UpdateConsensus( s, true ): drop the contig's k-mers, apply the changes, index it again
+		T4Contig *seq = t4_seq( cx, s ) ;
+		char *cons = t4_cons( cx, seq ) ;
+		int *pw = t4_pw( cx, seq ) ;
+		c_index_op( cx, cons, seq->len, T4_IDX_REMOVE, s, seq->barcode, 0, 0 ) ;
+		T4_PAR_FOR( i, seq->len )
 		{
-			if ( t4_seq( cx, s )->consOff == 0 )
+			int max = 0, maxTag = 0 ;
+			for ( int j = 0 ; j < 4 ; ++j )
+				if ( pw[4 * i + j] > max )
+				{
+					max = pw[4 * i + j] ;
+					maxTag = j ;
+				}
+			if ( max == 0 )
 				continue ;
-			if ( useFlags && !flag[s] )
-				continue ;
-			s_update_consensus( cx, s, true ) ;
+			int cur = t4_nuc( cons[i] ) ;
+			if ( cur != maxTag && pw[4 * i + cur] < max )
+				cons[i] = t4_numToNuc( maxTag ) ;
 		}
+		T4_SYNC() ;
+		c_index_op( cx, cons, seq->len, T4_IDX_BUILD, s, seq->barcode, 0, 0 ) ;
 	}
 	T4_SYNC() ;
 }
@@ -1738,14 +2433,13 @@ T4_D inline void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
 {
 	T4Stream *st = cx.st ;
 	T4_SYNC() ;
+	T4Dir *dir = cx.P<T4Dir>( st->dirOff ) ;
+	T4_PAR_FOR( i, st->dirCap ) // seqIndex.Clear()
+		dir[i].key = 0 ;
 	if ( cx.tid == 0 )
 	{
 		st->kmerLength = kl ;
 		st->nomatchGapLimit = nomatchGapLimit ;
-		// seqIndex.Clear()
-		T4Dir *dir = cx.P<T4Dir>( st->dirOff ) ;
-		for ( u32 i = 0 ; i < st->dirCap ; ++i )
-			dir[i].key = 0 ;
 		st->dirUsed = 0 ;
 		int k = 0 ;
 		for ( int i = 0 ; i < st->nSeqs ; ++i )
@@ -1755,12 +2449,16 @@ T4_D inline void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
 				continue ;
 			if ( k != i )
 				*t4_seq( cx, k ) = *c ;
-			T4Contig *d = t4_seq( cx, k ) ;
-			s_build_index( cx, t4_cons( cx, d ), d->len, k, d->barcode, 0 ) ;
 			++k ;
 		}
 		t4_set_prev( st, -1, -1, -1, -1, 0 ) ;
 		st->nSeqs = k ;
+	}
+	T4_SYNC() ;
+	for ( int i = 0 ; i < st->nSeqs ; ++i )
+	{
+		T4Contig *d = t4_seq( cx, i ) ;
+		c_index_op( cx, t4_cons( cx, d ), d->len, T4_IDX_BUILD, i, d->barcode, 0, 0 ) ;
 	}
 	T4_SYNC() ;
 }
@@ -1776,29 +2474,49 @@ T4_D inline int t4_nomatch_gap_limit_table( int kl, const int *table )
 // ---------------------------------------------------------------------------
 // SeqSet::InputNovelRead (SeqSet.hpp:3028-3073).  Serial; reads cx.sm->read.
 // ---------------------------------------------------------------------------
-T4_D inline int s_input_novel_read( T4Ctx &cx, const char *id, int idLen, int len, int strand, int barcode )
+T4_D inline int c_input_novel_read( T4Ctx &cx, const char *id, int idLen, int len, int strand, int barcode )
 {
 	T4Stream *st = cx.st ;
 	T4Smem *sm = cx.sm ;
-	int seqIdx = s_new_contig( cx, len ) ;
-	if ( seqIdx < 0 )
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+	{
+		int seqIdx = s_new_contig( cx, len ) ;
+		if ( seqIdx >= 0 )
+		{
+			T4Contig *c = t4_seq( cx, seqIdx ) ;
+			s_set_name( cx, c, id, idLen ) ;
+			c->barcode = barcode ;
+			c->numRead = 1 ;
+		}
+		sm->bi[0] = seqIdx ;
+	}
+	T4_SYNC() ;
+	int seqIdx = sm->bi[0] ;
+	T4_SYNC() ;
+	if ( seqIdx < 0 || st->error )
 		return T4_E_NOMEM ;
 	T4Contig *c = t4_seq( cx, seqIdx ) ;
-	s_set_name( cx, c, id, idLen ) ;
 	char *cons = t4_cons( cx, c ) ;
 	int *pw = t4_pw( cx, c ) ;
 	const char *src = ( strand == -1 ) ? sm->rc : sm->read ;
-	for ( int i = 0 ; i < len ; ++i )
+	T4_PAR_FOR( i, len )
 	{
-		cons[i] = src[i] ;
-		pw[4 * i] = pw[4 * i + 1] = pw[4 * i + 2] = pw[4 * i + 3] = 0 ;
-		if ( src[i] != 'N' )
-			pw[4 * i + t4_nuc( src[i] )] = 1 ;
+		char ch = src[i] ;
+		cons[i] = ch ;
+		int w0 = 0, w1 = 0, w2 = 0, w3 = 0 ;
+		if ( ch != 'N' )
+		{
+			int x = t4_nuc( ch ) ;
+			w0 = x == 0 ; w1 = x == 1 ; w2 = x == 2 ; w3 = x == 3 ;
+		}
+		pw[4 * i] = w0 ; pw[4 * i + 1] = w1 ; pw[4 * i + 2] = w2 ; pw[4 * i + 3] = w3 ;
 	}
-	c->barcode = barcode ;
-	c->numRead = 1 ;
-	s_build_index( cx, cons, len, seqIdx, barcode, 0 ) ;
-	t4_set_prev( st, seqIdx, 0, len - 1, 0, strand ) ;
+	T4_SYNC() ;
+	c_index_op( cx, cons, len, T4_IDX_BUILD, seqIdx, barcode, 0, 0 ) ;
+	if ( cx.tid == 0 )
+		t4_set_prev( st, seqIdx, 0, len - 1, 0, strand ) ;
+	T4_SYNC() ;
 	return seqIdx ;
 }
 
@@ -1835,6 +2553,7 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 	if ( cx.tid == 0 )
 		t4_set_prev( st, -1, -1, -1, -1, 0 ) ;
 	int overlapCnt = c_get_overlaps( cx, len, strand, barcode, repetitiveData ) ;
+	T4_PHASE( cx, 0 ) ;
 	if ( st->error )
 		return st->error ;
 	if ( overlapCnt <= 0 )
@@ -1877,18 +2596,55 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 	const char *r = ( overlaps[0].strand == 1 ) ? sm->read : sm->rc ;
 	const double factor = ( barcode == -1 && !repetitiveData ) ? 1.0 : 2.0 ;
 	// ExtendOverlap is a pure function of (overlap, read, contig): evaluate it for every overlap up front
+	T4_PHASE( cx, 5 ) ;
+	if ( cx.tid == 0 )
+		t4_atomic_add( &cx.g->counters[16], (u64)overlapCnt ) ;
 	T4Ovl *pre = cx.P<T4Ovl>( st->extOff ) ;
 	{
+		// IsBaseEqual of every overhang column, 32 positions per work item, spread over the CTA
+		u32 *bits = cx.P<u32>( st->bitsOff ) ;
+		T4_PAR_FOR( x, overlapCnt * 32 )
+		{
+			int oi = x >> 5, w = x & 15, right = ( x >> 4 ) & 1 ;
+			const T4Ovl &o = overlaps[oi] ;
+			T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+			int n, col0, rp0 ;
+			if ( !right )
+			{
+				n = t4_min( o.readStart, o.seqStart ) ;
+				col0 = o.seqStart - n ;
+				rp0 = o.readStart - n ;
+			}
+			else
+			{
+				n = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
+				col0 = o.seqEnd + 1 ;
+				rp0 = o.readEnd + 1 ;
+			}
+			u32 m = 0 ;
+			if ( w * 32 < n )
+			{
+				const int *pw = t4_pw( cx, seq ) ;
+				int hi = n - w * 32 < 32 ? n - w * 32 : 32 ;
+				for ( int t = 0 ; t < hi ; ++t )
+					if ( t4_base_equal( pw + 4 * ( col0 + w * 32 + t ), r[rp0 + w * 32 + t] ) )
+						m |= 1u << t ;
+			}
+			bits[x] = m ;
+		}
+		T4_SYNC() ;
 		T4DpScratch ds = t4_dp_scratch( cx ) ;
 		T4_PAR_FOR( i, overlapCnt )
 		{
 			T4Ovl e ;
-			int ok = t4_extend_overlap( cx, r, len, t4_seq( cx, overlaps[i].seqIdx ), factor, ds, overlaps[i], e ) ;
+			int ok = t4_extend_overlap( cx, r, len, t4_seq( cx, overlaps[i].seqIdx ), factor, ds, overlaps[i], e, bits + 32 * i,
+				bits + 32 * i + 16 ) ;
 			e.infoFromHits = ok ; // aux: the return value
 			pre[i] = e ;
 		}
 	}
 	T4_SYNC() ;
+	T4_PHASE( cx, 6 ) ;
 	if ( cx.tid == 0 )
 	{
 		// ---------------- decision + commit: serial, order dependent ----------------
@@ -1907,6 +2663,7 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		bool sortExtendedOverlaps = true ;
 		bool added = false ;
 		bool bail = false ;
+		int kind = 0 ;
 
 		for ( i = 0 ; i < overlapCnt ; ++i )
 		{
@@ -2097,9 +2854,10 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 
 		if ( k > 1 )
 		{
-			// ------------- merge contigs (SeqSet.hpp:3878-4130) -------------
+			// ------------- merge contigs (SeqSet.hpp:3878-4130); rare (0.7 % of AddReads), serial -------------
 			int eOverlapCnt = k ;
 			added = true ;
+			kind = 2 ;
 			if ( sortExtendedOverlaps )
 			{
 				// std::sort by readStart only; equal keys would make the order implementation defined, so keep the
@@ -2288,190 +3046,240 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		}
 		else if ( k == 1 )
 		{
-			// ------------- extend / inside a contig (SeqSet.hpp:4131-4316) -------------
 			added = true ;
-			const T4Ovl e0 = extendedOverlaps[0] ;
-			seqIdx = e0.seqIdx ;
-			T4Contig *seq = t4_seq( cx, seqIdx ) ;
+			kind = 1 ;
+			sm->e0 = extendedOverlaps[0] ;
+		}
+		sm->bi[2] = kind ;
+		sm->bi[3] = seqIdx ;
+		sm->bi[4] = readInConsensusOffset ;
+		sm->bi[5] = bail ? 1 : 0 ;
+		sm->bi[6] = ret ;
+		sm->bi[7] = added ? 1 : 0 ;
+	}
+	T4_SYNC() ;
+	int kind = sm->bi[2] ;
+	int seqIdx = sm->bi[3] ;
+	int readInConsensusOffset = sm->bi[4] ;
+	bool bail = sm->bi[5] != 0 ;
+	int ret = sm->bi[6] ;
+	bool added = sm->bi[7] != 0 ;
+	T4_SYNC() ;
+	if ( kind == 1 )
+	{
+		// ------------- extend / inside a contig (SeqSet.hpp:4131-4316); collective -------------
+		const T4Ovl e0 = sm->e0 ;
+		seqIdx = e0.seqIdx ;
+		T4Contig *seq = t4_seq( cx, seqIdx ) ;
+		if ( cx.tid == 0 )
 			++seq->numRead ;
-			if ( e0.readStart > 0 || e0.readEnd < len - 1 )
+		if ( e0.readStart > 0 || e0.readEnd < len - 1 )
+		{
+			const int shift = e0.readStart ;
+			const int rightAdd = ( e0.readEnd < len - 1 ) ? ( len - 1 - e0.readEnd ) : 0 ;
+			const int oldLen = seq->len ;
+			const int kl = st->kmerLength ;
+			// index first, in the reference's order: new left k-mers, shift the old postings, (later) new right k-mers
+			if ( shift > 0 )
 			{
-				int shift = e0.readStart ;
-				int rightAdd = ( e0.readEnd < len - 1 ) ? ( len - 1 - e0.readEnd ) : 0 ;
-				int oldLen = seq->len ;
-				// index first, exactly in the reference's order: new left k-mers, shift old postings, new right k-mers.
-				// The old consensus is still in place; build the (short) new flanks in a temporary buffer.
 				char *oldCons = t4_cons( cx, seq ) ;
-				int kl = st->kmerLength ;
-				if ( shift > 0 )
+				char *tmpc = (char *)pre ; // newConsensus[0 .. shift + kl - 1): read prefix + the first kl-1 old bases
+				int n = shift + kl - 1 ;
+				T4_PAR_FOR( i, n )
 				{
-					// newConsensus[0 .. shift + kl - 1) = read prefix + first kl-1 old bases
-					char *tmpc = (char *)pre ; // scratch
-					int n = shift + kl - 1 ;
-					for ( i = 0 ; i < n ; ++i )
-						tmpc[i] = ( i < shift ) ? r[i] : ( ( i - shift < oldLen ) ? oldCons[i - shift] : '\0' ) ;
-					// BuildIndexFromRead(newConsensus, readStart + k - 1) -- if the old contig is shorter than k-1 the reference
-					// reads into the appended right part; mirror that
-					for ( i = shift + oldLen ; i < n ; ++i )
+					char c ;
+					if ( i < shift )
+						c = r[i] ;
+					else if ( i - shift < oldLen )
+						c = oldCons[i - shift] ;
+					else
 					{
 						int ri = e0.readEnd + 1 + ( i - shift - oldLen ) ;
-						tmpc[i] = ( ri < len ) ? r[ri] : '\0' ;
+						c = ( ri < len ) ? r[ri] : '\0' ;
 					}
-					s_build_index( cx, tmpc, n, seqIdx, barcode, 0 ) ;
-					s_update_index( cx, oldCons, oldLen, barcode, shift, seqIdx, seqIdx ) ;
+					tmpc[i] = c ;
 				}
-				if ( !s_contig_grow( cx, seq, shift, rightAdd ) )
+				T4_SYNC() ;
+				c_index_op( cx, tmpc, n, T4_IDX_BUILD, seqIdx, barcode, 0, 0 ) ;
+				c_index_op( cx, oldCons, oldLen, T4_IDX_UPDATE, seqIdx, barcode, shift, seqIdx ) ;
+			}
+			T4_SYNC() ; // every thread has read the old length / pointers
+			if ( cx.tid == 0 )
+				sm->bi[0] = s_contig_grow( cx, seq, shift, rightAdd ) ? 1 : 0 ;
+			T4_SYNC() ;
+			bool grown = sm->bi[0] != 0 ;
+			T4_SYNC() ;
+			if ( !grown )
+			{
+				ret = T4_E_NOMEM ;
+				bail = true ;
+			}
+			else
+			{
+				char *newConsensus = t4_cons( cx, seq ) ;
+				int *pw = t4_pw( cx, seq ) ;
+				const int newConsensusLen = seq->len ;
+				T4_PAR_FOR( i, shift )
+					newConsensus[i] = r[i] ;
+				T4_PAR_FOR( x, rightAdd )
+					newConsensus[shift + oldLen + x] = r[e0.readEnd + 1 + x] ;
+				T4_PAR_FOR( i, 4 * shift )
+					pw[i] = 0 ;
+				T4_PAR_FOR( i, 4 * rightAdd )
+					pw[4 * ( shift + oldLen ) + i] = 0 ;
+				T4_SYNC() ;
+				if ( e0.readEnd < len - 1 )
 				{
-					ret = T4_E_NOMEM ;
-					bail = true ;
-				}
-				else
-				{
-					char *newConsensus = t4_cons( cx, seq ) ;
-					int *pw = t4_pw( cx, seq ) ;
-					int newConsensusLen = seq->len ;
-					for ( i = 0 ; i < shift ; ++i )
-						newConsensus[i] = r[i] ;
-					for ( i = e0.readEnd + 1, j = shift + oldLen ; i < len ; ++i, ++j )
-						newConsensus[j] = r[i] ;
-					if ( e0.readEnd < len - 1 )
+					int start = e0.readStart + e0.seqEnd - kl + 2 ;
+					if ( start < 0 )
 					{
-						int start = e0.readStart + e0.seqEnd - kl + 2 ;
-						if ( start < 0 )
-						{
-							// contig shorter than k-2: pointer before the buffer in the reference; never seen
+						if ( cx.tid == 0 )
 							t4_raise( cx, T4_E_INTERNAL, 11 ) ;
-							start = 0 ;
-						}
-						s_build_index( cx, newConsensus + start, newConsensusLen - start, seqIdx, barcode, start ) ;
+						start = 0 ;
 					}
-					// posWeight: old columns already sit at [shift, shift + oldLen)
+					c_index_op( cx, newConsensus + start, newConsensusLen - start, T4_IDX_BUILD, seqIdx, barcode, start, 0 ) ;
+				}
+				// end-weight decay and scheduled consensus substitutions (SeqSet.hpp:4192-4247): four columns, serial
+				if ( cx.tid == 0 )
+				{
 					int nrep = 0 ;
-					int repPos[4] ;
-					char repChar[4] ;
-					if ( shift > 0 )
+					if ( shift > 0 && ( barcode == -1 || minKmerCount > 1 ) )
 					{
-						if ( barcode == -1 || minKmerCount > 1 )
+						for ( int i = 0 ; i < 2 ; ++i )
 						{
-							for ( i = 0 ; i < 2 ; ++i )
+							if ( i + shift >= len || r[i + shift] == 'N' )
+								continue ;
+							char nc = newConsensus[i + shift] ;
+							if ( r[i + shift] != nc && nc != 'N' && pw[4 * ( i + shift ) + t4_nuc( nc )] == 1 )
 							{
-								if ( i + shift >= len || r[i + shift] == 'N' )
-									continue ;
-								char nc = newConsensus[i + shift] ;
-								if ( r[i + shift] != nc && nc != 'N' && pw[4 * ( i + shift ) + t4_nuc( nc )] == 1 )
-								{
-									repPos[nrep] = i + shift ;
-									repChar[nrep] = r[i + shift] ;
-									++nrep ;
-								}
-								for ( j = 0 ; j < 4 ; ++j )
-									if ( r[i + shift] != t4_numToNuc( j ) && pw[4 * ( i + shift ) + j] > 1 )
-										--pw[4 * ( i + shift ) + j] ;
+								sm->bi[2 + nrep] = i + shift ;
+								sm->bi[6 + nrep] = r[i + shift] ;
+								++nrep ;
 							}
+							for ( int j = 0 ; j < 4 ; ++j )
+								if ( r[i + shift] != t4_numToNuc( j ) && pw[4 * ( i + shift ) + j] > 1 )
+									--pw[4 * ( i + shift ) + j] ;
 						}
-						for ( i = 0 ; i < 4 * shift ; ++i )
-							pw[i] = 0 ;
 					}
-					if ( e0.readEnd < len - 1 )
+					if ( e0.readEnd < len - 1 && ( barcode == -1 || minKmerCount > 1 ) )
 					{
-						int start = e0.readStart + oldLen ;
-						for ( i = 4 * start ; i < 4 * ( start + len - e0.readEnd - 1 ) ; ++i )
-							pw[i] = 0 ;
-						if ( barcode == -1 || minKmerCount > 1 )
+						for ( int i = oldLen - 2 ; i < oldLen ; ++i )
 						{
-							for ( i = oldLen - 2 ; i < oldLen ; ++i )
+							int pos = i - e0.seqStart ;
+							int seqPos = i + shift ;
+							if ( pos < 0 || r[pos] == 'N' )
+								continue ;
+							if ( i < 0 )
 							{
-								int pos = i - e0.seqStart ;
-								int seqPos = i + shift ;
-								if ( pos < 0 || r[pos] == 'N' )
-									continue ;
-								if ( i < 0 )
-								{
-									t4_raise( cx, T4_E_INTERNAL, 12 ) ;
-									continue ;
-								}
-								char nc = newConsensus[seqPos] ;
-								if ( r[pos] != nc && nc != 'N' && pw[4 * seqPos + t4_nuc( nc )] == 1 )
-								{
-									repPos[nrep] = seqPos ;
-									repChar[nrep] = r[pos] ;
-									++nrep ;
-								}
-								for ( j = 0 ; j < 4 ; ++j )
-									if ( r[pos] != t4_numToNuc( j ) && pw[4 * seqPos + j] > 1 )
-										--pw[4 * seqPos + j] ;
+								t4_raise( cx, T4_E_INTERNAL, 12 ) ;
+								continue ;
 							}
+							char nc = newConsensus[seqPos] ;
+							if ( r[pos] != nc && nc != 'N' && pw[4 * seqPos + t4_nuc( nc )] == 1 )
+							{
+								sm->bi[2 + nrep] = seqPos ;
+								sm->bi[6 + nrep] = r[pos] ;
+								++nrep ;
+							}
+							for ( int j = 0 ; j < 4 ; ++j )
+								if ( r[pos] != t4_numToNuc( j ) && pw[4 * seqPos + j] > 1 )
+									--pw[4 * seqPos + j] ;
 						}
 					}
 					if ( shift > 0 )
 						seq->minLeftExtAnchor = 0 ;
 					if ( e0.readEnd < len - 1 )
 						seq->minRightExtAnchor = 0 ;
-					// (the +GENE name adjustment needs isRef overlaps: never in the stage-1 novel set, SeqSet.hpp:4258-4296)
-					readInConsensusOffset = 0 ;
-					if ( e0.seqStart > 0 )
-						readInConsensusOffset = e0.seqStart ;
-					for ( i = 0 ; i < nrep ; ++i )
-						s_substitute_consensus_pos( cx, seqIdx, repPos[i], repChar[i] ) ;
+					sm->bi[1] = nrep ;
+				}
+				T4_SYNC() ;
+				// (the +GENE name adjustment needs isRef overlaps: never in the stage-1 novel set, SeqSet.hpp:4258-4296)
+				readInConsensusOffset = 0 ;
+				if ( e0.seqStart > 0 )
+					readInConsensusOffset = e0.seqStart ;
+				int nrep = sm->bi[1] ;
+				int repPos[4], repChar[4] ;
+				for ( int i = 0 ; i < nrep ; ++i )
+				{
+					repPos[i] = sm->bi[2 + i] ;
+					repChar[i] = sm->bi[6 + i] ;
+				}
+				T4_SYNC() ;
+				for ( int i = 0 ; i < nrep ; ++i )
+					c_substitute_consensus_pos( cx, seqIdx, repPos[i], (char)repChar[i] ) ;
+			}
+		}
+		else
+			readInConsensusOffset = e0.seqStart ;
+	}
+
+	// ------------- posWeight update (SeqSet.hpp:4318-4363); collective -------------
+	if ( added && !bail && seqIdx >= 0 && !st->error )
+	{
+		T4Contig *seq = t4_seq( cx, seqIdx ) ;
+		char *cons = t4_cons( cx, seq ) ;
+		int *pw = t4_pw( cx, seq ) ;
+		if ( cx.tid == 0 )
+			sm->bi[0] = 0 ;
+		T4_SYNC() ;
+		T4_PAR_FOR( i, len )
+		{
+			if ( r[i] == 'N' )
+				continue ;
+			++pw[4 * ( i + readInConsensusOffset ) + t4_nuc( r[i] )] ;
+			if ( cons[i + readInConsensusOffset] == 'N' )
+				sm->bi[0] = 1 ;
+		}
+		T4_SYNC() ;
+		if ( cx.tid == 0 )
+		{
+			t4_set_prev( st, seqIdx, 0, len - 1, readInConsensusOffset, overlaps[0].strand ) ;
+			if ( sm->bi[0] )
+			{
+				// consensus N's under the read are filled and their k-mers indexed (SeqSet.hpp:4338-4360); rare
+				int kl = st->kmerLength ;
+				int *nPos = (int *)pre ;
+				int size = 0 ;
+				for ( int i = 0 ; i < len ; ++i )
+					if ( r[i] != 'N' && cons[i + readInConsensusOffset] == 'N' )
+						nPos[size++] = i ;
+				for ( int i = 0 ; i < size ; )
+				{
+					int j ;
+					for ( j = i + 1 ; j < size ; ++j )
+						if ( nPos[j] > nPos[j - 1] + kl - 1 )
+							break ;
+					for ( int l = i ; l < j ; ++l )
+						cons[nPos[l] + readInConsensusOffset] = r[nPos[l]] ;
+					int start = nPos[i] - kl + 1 + readInConsensusOffset ;
+					if ( start < 0 )
+						start = 0 ;
+					int end = nPos[j - 1] + kl - 1 + readInConsensusOffset ;
+					if ( end >= seq->len )
+						end = seq->len - 1 ;
+					s_build_index( cx, cons + start, end - start + 1, seqIdx, barcode, start ) ;
+					i = j ;
 				}
 			}
-			else
-				readInConsensusOffset = e0.seqStart ;
 		}
-
-		// ------------- posWeight update (SeqSet.hpp:4318-4363) -------------
-		if ( added && !bail && seqIdx >= 0 && !st->error )
-		{
-			T4Contig *seq = t4_seq( cx, seqIdx ) ;
-			char *cons = t4_cons( cx, seq ) ;
-			int *pw = t4_pw( cx, seq ) ;
-			int kl = st->kmerLength ;
-			int *nPos = (int *)pre ;
-			int size = 0 ;
-			for ( i = 0 ; i < len ; ++i )
-			{
-				if ( r[i] == 'N' )
-					continue ;
-				++pw[4 * ( i + readInConsensusOffset ) + t4_nuc( r[i] )] ;
-				if ( cons[i + readInConsensusOffset] == 'N' )
-					nPos[size++] = i ;
-			}
-			t4_set_prev( st, seqIdx, 0, len - 1, readInConsensusOffset, overlaps[0].strand ) ;
-			for ( i = 0 ; i < size ; )
-			{
-				for ( j = i + 1 ; j < size ; ++j )
-					if ( nPos[j] > nPos[j - 1] + kl - 1 )
-						break ;
-				for ( int l = i ; l < j ; ++l )
-					cons[nPos[l] + readInConsensusOffset] = r[nPos[l]] ;
-				int start = nPos[i] - kl + 1 + readInConsensusOffset ;
-				if ( start < 0 )
-					start = 0 ;
-				int end = nPos[j - 1] + kl - 1 + readInConsensusOffset ;
-				if ( end >= seq->len )
-					end = seq->len - 1 ;
-				s_build_index( cx, cons + start, end - start + 1, seqIdx, barcode, start ) ;
-				i = j ;
-			}
-			ret = seqIdx ;
-		}
-		// addNew is only kept for isRef overlaps (SeqSet.hpp:4377-4391): never in the novel set
-		if ( ret == -1 && !bail )
-		{
-			t4_set_prev( st, -2, -1, -1, -1, 0 ) ;
-			ret = -2 ;
-		}
-		sm->bi[0] = ret ;
-		sm->bi[1] = ( ret >= 0 && strand == 0 ) ? overlaps[0].strand : strand ;
+		ret = seqIdx ;
 	}
+	// addNew is only kept for isRef overlaps (SeqSet.hpp:4377-4391): never in the novel set
+	if ( ret == -1 && !bail )
+	{
+		if ( cx.tid == 0 )
+			t4_set_prev( st, -2, -1, -1, -1, 0 ) ;
+		ret = -2 ;
+	}
+	if ( ret >= 0 && strand == 0 )
+		strand = overlaps[0].strand ;
 	T4_SYNC() ;
-	int ret = sm->bi[0] ;
-	strand = sm->bi[1] ;
-	T4_SYNC() ;
+	T4_PHASE( cx, 0 ) ;
 	if ( st->error )
 		return st->error ;
 	return ret ;
 }
+
 
 // ---------------------------------------------------------------------------
 // loading a read into shared memory
@@ -2490,6 +3298,7 @@ T4_D inline void c_load_read( T4Ctx &cx, const char *src, int len )
 	{
 		sm->read[len] = '\0' ;
 		sm->rc[len] = '\0' ;
+		s_refill_slab( cx ) ;
 	}
 	T4_SYNC() ;
 }
@@ -2592,11 +3401,9 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 					}
 					if ( nm != 0 )
 					{
-						if ( cx.tid == 0 )
-							sm->bi[0] = s_input_novel_read( cx, nm, nmLen, d.len, novelStrand, d.barcode ) ;
-						T4_SYNC() ;
-						addRet = sm->bi[0] ;
-						T4_SYNC() ;
+						T4_PHASE( cx, 7 ) ;
+						addRet = c_input_novel_read( cx, nm, nmLen, d.len, novelStrand, d.barcode ) ;
+						T4_PHASE( cx, 0 ) ;
 					}
 				}
 			}
@@ -2604,10 +3411,12 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		}
 		else
 		{
+			T4_PHASE( cx, 7 ) ;
 			if ( prevAddRet != -1 && prevAddRet != -3 )
 				addRet = c_repeat_add_read( cx, d.len ) ;
 			else if ( prevAddRet == -3 )
 				addRet = -3 ;
+			T4_PHASE( cx, 0 ) ;
 			finalStrand = i > 0 ? strands[i - 1] : 0 ;
 		}
 		if ( cx.tid == 0 )
@@ -2652,7 +3461,11 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		T4_SYNC() ;
 		if ( assembledReadCnt > 0 && cfg.update_consensus_every > 0 && assembledReadCnt % cfg.update_consensus_every == 0
 			&& !cfg.has_barcode )
+		{
+			T4_PHASE( cx, 7 ) ;
 			c_update_all_consensus( cx ) ;
+			T4_PHASE( cx, 0 ) ;
+		}
 		prevAddRet = addRet ;
 		if ( changeKmerLengthThreshold > 0 && st->nSeqs > changeKmerLengthThreshold && indexKmerLength < 16 && !cfg.has_barcode )
 		{
@@ -2661,8 +3474,10 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			c_change_kmer_length( cx, indexKmerLength, gapLimitTable[indexKmerLength] ) ;
 		}
 	}
+	T4_PHASE( cx, 7 ) ;
 	if ( cfg.final_update && !st->error )
 		c_update_all_consensus( cx ) ;
+	T4_PHASE( cx, 0 ) ;
 	if ( cfg.do_rescue && cfg.first_read_len <= 200 && !st->error )
 	{
 		for ( int x = 0 ; x < rescueCnt && !st->error ; ++x )
@@ -2707,6 +3522,7 @@ T4_HD inline u64 t4_stream_footprint( const T4InitParams &ip )
 	o += t4_al( 2ull * T4_DEV_MAX_READ * sizeof( T4Pos ) ) ;
 	o += 4 * t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
 	o += t4_al( (u64)ip.ovlCap * 8 ) ;
+	o += t4_al( (u64)ip.ovlCap * 32 * 4 ) ;
 	o += t4_al( (u64)ip.nThreads * T4_DP_STRIDE ) ;
 	return o ;
 }
@@ -2747,6 +3563,7 @@ T4_D inline void c_init_stream( T4Ctx &cx, u64 base, const T4InitParams &ip )
 		st->extOff = o ; o += t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
 		st->failOff = o ; o += t4_al( (u64)ip.ovlCap * sizeof( T4Ovl ) ) ;
 		st->anchorOff = o ; o += t4_al( (u64)ip.ovlCap * 8 ) ;
+		st->bitsOff = o ; o += t4_al( (u64)ip.ovlCap * 32 * 4 ) ;
 		st->ovlCap = ip.ovlCap ;
 		st->dpOff = o ; o += t4_al( (u64)ip.nThreads * T4_DP_STRIDE ) ;
 		st->dpStride = T4_DP_STRIDE ;
@@ -2795,6 +3612,16 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			op->ret = st->error ;
 		return ;
 	}
+#if T4_CUDA
+	if ( cx.tid == 0 )
+	{
+		for ( int i = 0 ; i < 8 ; ++i )
+			sm->ph[i] = 0 ;
+		sm->phCur = 0 ;
+		sm->phLast = clock64() ;
+	}
+	T4_SYNC() ;
+#endif
 	switch ( op->op )
 	{
 		case T4_OP_RUN_LOOP:
@@ -2825,8 +3652,9 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		case T4_OP_INPUT_NOVEL:
 		{
 			c_load_read( cx, t4_x<char>( op->read ), op->len ) ;
+			int r0 = c_input_novel_read( cx, t4_x<char>( op->name ), op->nameLen, op->len, op->strand, op->barcode ) ;
 			if ( cx.tid == 0 )
-				op->ret = s_input_novel_read( cx, t4_x<char>( op->name ), op->nameLen, op->len, op->strand, op->barcode ) ;
+				op->ret = r0 ;
 			break ;
 		}
 		case T4_OP_UPDATE_ALL:
@@ -2932,6 +3760,12 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 	T4_SYNC() ;
 	if ( cx.tid == 0 && st->error && op->ret >= T4_E_BASE )
 		op->ret = st->error ;
+#if T4_CUDA
+	T4_PHASE( cx, 0 ) ;
+	if ( cx.tid == 0 )
+		for ( int i = 0 ; i < 8 ; ++i )
+			t4_atomic_add( &cx.g->counters[8 + i], (u64)sm->ph[i] ) ;
+#endif
 	(void)sm ;
 }
 
