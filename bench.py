@@ -296,7 +296,9 @@ def main():
                 "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes": {"probe": b_probe, "chain": b_chain, "commit": b_commit},
                 "per_read": {"lookups": dc[2] / n_reads, "hits": dc[4] / n_reads, "overlaps_scored": dc[6] / n_reads, "gap_dps": dc[7] / n_reads,
-                             "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads},
+                             "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads,
+                             "ext_cycles_stage_dp_tail_per_overlap": [dc[17] / max(1, dc[16]), dc[18] / max(1, dc[16]), dc[19] / max(1, dc[16])],
+                             "ext_dp_rows_per_overlap": dc[20] / max(1, dc[16])},
                 "phase_share": dict(zip(["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"],
                                         [round(float(x), 4) for x in (dc[8:16] / max(1.0, dc[8:16].sum()))]))}
 
@@ -337,7 +339,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": 2 * args.steps, "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
                 "assembled_reads": assembled, "reads_per_gpu": n_reads, "workload_gen_s": t_gen,
-                "threads_per_stream": int(os.environ.get("T4_NT", 64))}
+                "threads_per_stream": int(os.environ.get("T4_NT", 128))}
         print(json.dumps(line))
     lib.workload_free(wl)
     if world > 1:

@@ -46,7 +46,7 @@ static void set_err( const std::string &s ) { g_err = s ; }
 	} while ( 0 )
 
 #ifndef T4_MIN_BLOCKS
-#define T4_MIN_BLOCKS 8
+#define T4_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_stream_kernel( char *A, T4Op *ops, const int *gapTable )
 {
@@ -178,7 +178,7 @@ struct Engine
 	// grow-only device buffer reused by t4_streams_run for the uploaded workload (no cudaMalloc per call)
 	char *wl ;
 	size_t wlCap ;
-	Engine() : up( false ), device( 0 ), A( 0 ), cap( 0 ), nt( 64 ), gapTable( 0 ), stage( 0 ), stageCap( 0 ), wl( 0 ), wlCap( 0 ) {}
+	Engine() : up( false ), device( 0 ), A( 0 ), cap( 0 ), nt( 128 ), gapTable( 0 ), stage( 0 ), stageCap( 0 ), wl( 0 ), wlCap( 0 ) {}
 } ;
 static Engine E ;
 static std::mutex g_mu ;

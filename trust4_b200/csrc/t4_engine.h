@@ -24,6 +24,7 @@
 
 #define T4_MAX_NT 128
 #define T4_IDX_CHUNK 256
+#define T4_WACT_WORDS 12
 #define T4_RADIX_BITS 4
 #define T4_RADIX (1 << T4_RADIX_BITS)
 #define T4_DP_BAND 5
@@ -49,6 +50,10 @@ struct T4Smem
 	u64 icode[T4_IDX_CHUNK] ; // c_index_op: k-mer codes of the current chunk of positions
 	unsigned char iact[T4_IDX_CHUNK] ;
 	T4Ovl e0 ;             // commit plan of c_add_read
+	u32 wnib[T4_MAX_NT / 32][2][64] ;        // per warp, per overhang side: IsBaseEqual nibbles of up to 512 columns
+	u32 wbits[T4_MAX_NT / 32][2][16] ;       // ... and the match bits against the read
+	u32 wact[T4_MAX_NT / 32][2][13 * T4_WACT_WORDS] ; // ... traceback words of the half-warp DP (n <= 16*T4_WACT_WORDS - 1)
+	signed char wal[T4_MAX_NT / 32][2][2 * 16 * T4_WACT_WORDS + 8] ; // ... and its edit string (filled backwards: no reversal pass)
 	long long ph[8] ;      // per-phase clock accumulators (thread 0)
 	long long phLast ;
 	int phCur ;
@@ -1205,37 +1210,61 @@ T4_HD inline int t4_dp_equal( const int *tw, const char *p, int n, signed char *
 		const int pn = t4_nuc( pc ) ;
 		const bool pN = ( pc == 'N' ) ;
 		u32 arow = 0 ;
-#pragma unroll
-		for ( int l = 0 ; l < 13 ; ++l )
-			cur[l] = negInf ;
-		if ( wlo <= 0 )
+		if ( i >= 7 && i + 5 <= n )
 		{
-			// column 0 sits at slot -wlo (0..5)
+			// interior row: the whole 11-cell band is inside the matrix, both window edges are -inf
+			const unsigned long long rowEq = pN ? ~0ull : ( eqw >> pn ) ;
+			cur[0] = negInf ;
+			cur[12] = negInf ;
 #pragma unroll
-			for ( int l = 0 ; l <= 5 ; ++l )
-				if ( l == -wlo )
-					cur[l] = SCORE_INDEL + i * SCORE_INDEL ;
-		}
-#pragma unroll
-		for ( int l = 1 ; l <= 11 ; ++l )
-		{
-			int j = wlo + l ;
-			if ( j >= start && j <= end )
+			for ( int l = 1 ; l <= 11 ; ++l )
 			{
-				bool eq = pN || ( ( (unsigned)( eqw >> ( 4 * l ) ) >> pn ) & 1u ) ;
-				int diff = eq ? SCORE_MATCH : SCORE_MISMATCH ;
-				int dg = prev[l] + diff ;
+				bool eq = ( (unsigned)( rowEq >> ( 4 * l ) ) & 1u ) != 0 ;
+				int dg = prev[l] + ( eq ? SCORE_MATCH : SCORE_MISMATCH ) ;
 				int lf = cur[l - 1] + SCORE_INDEL ;
 				int up = prev[l + 1] + SCORE_INDEL ;
 				int score = dg ;
 				if ( lf > score ) score = lf ;
 				if ( up > score ) score = up ;
 				cur[l] = score ;
-				u32 a = 0 ;
-				if ( lf == score ) a = EDIT_DELETE ;
-				if ( up == score ) a = EDIT_INSERT ;
-				if ( dg == score ) a = eq ? EDIT_MATCH : EDIT_MISMATCH ;
+				u32 a = ( dg == score ) ? ( eq ? (u32)EDIT_MATCH : (u32)EDIT_MISMATCH ) : ( ( up == score ) ? (u32)EDIT_INSERT : (u32)EDIT_DELETE ) ;
 				arow |= a << ( 2 * l ) ;
+			}
+		}
+		else
+		{
+	#pragma unroll
+			for ( int l = 0 ; l < 13 ; ++l )
+				cur[l] = negInf ;
+			if ( wlo <= 0 )
+			{
+				// column 0 sits at slot -wlo (0..5)
+	#pragma unroll
+				for ( int l = 0 ; l <= 5 ; ++l )
+					if ( l == -wlo )
+						cur[l] = SCORE_INDEL + i * SCORE_INDEL ;
+			}
+	#pragma unroll
+			for ( int l = 1 ; l <= 11 ; ++l )
+			{
+				int j = wlo + l ;
+				if ( j >= start && j <= end )
+				{
+					bool eq = pN || ( ( (unsigned)( eqw >> ( 4 * l ) ) >> pn ) & 1u ) ;
+					int diff = eq ? SCORE_MATCH : SCORE_MISMATCH ;
+					int dg = prev[l] + diff ;
+					int lf = cur[l - 1] + SCORE_INDEL ;
+					int up = prev[l + 1] + SCORE_INDEL ;
+					int score = dg ;
+					if ( lf > score ) score = lf ;
+					if ( up > score ) score = up ;
+					cur[l] = score ;
+					u32 a = 0 ;
+					if ( lf == score ) a = EDIT_DELETE ;
+					if ( up == score ) a = EDIT_INSERT ;
+					if ( dg == score ) a = eq ? EDIT_MATCH : EDIT_MISMATCH ;
+					arow |= a << ( 2 * l ) ;
+				}
 			}
 		}
 		act32[i] = arow ;
@@ -1307,6 +1336,15 @@ struct T4DpScratch
 T4_D inline T4DpScratch t4_dp_scratch( T4Ctx &cx )
 {
 	char *b = cx.P<char>( cx.st->dpOff ) + (size_t)cx.tid * cx.st->dpStride ;
+	T4DpScratch s ;
+	s.rows = (int *)b ;
+	s.act = (unsigned char *)( b + 2 * T4_DP_W * 4 + 8 ) ;
+	s.align = (signed char *)( b + 2 * T4_DP_W * 4 + 8 + ( T4_DEV_MAX_READ + 1 ) * T4_DP_W + 8 ) ;
+	return s ;
+}
+T4_D inline T4DpScratch t4_dp_scratch_of( T4Ctx &cx, int tid )
+{
+	char *b = cx.P<char>( cx.st->dpOff ) + (size_t)tid * cx.st->dpStride ;
 	T4DpScratch s ;
 	s.rows = (int *)b ;
 	s.act = (unsigned char *)( b + 2 * T4_DP_W * 4 + 8 ) ;
@@ -1800,6 +1838,10 @@ T4_D inline bool t4_low_complex( const char *r, const T4Ovl &o )
 	return lowCnt >= 2 ;
 }
 
+#if T4_CUDA
+T4_D inline void c_score_all_warp( T4Ctx &cx, T4Ovl *ovl, int overlapCnt, const u64 *keys ) ;
+#endif
+
 // ---------------------------------------------------------------------------
 // SeqSet::GetOverlapsFromRead (SeqSet.hpp:1508-2124), readType 0, novel contigs
 // ---------------------------------------------------------------------------
@@ -1874,6 +1916,10 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 	overlapCnt = sm->bi[0] ;
 	T4_SYNC() ;
 	// score every overlap independently (SeqSet.hpp:1832-2020); the order-dependent pre-filters are replayed below
+#if T4_CUDA
+	u64 fullDps = 0 ;
+	c_score_all_warp( cx, ovl, overlapCnt, keys ) ;
+#else
 	T4DpScratch ds = t4_dp_scratch( cx ) ;
 	u64 fullDps = 0 ;
 	T4_PAR_FOR( i, overlapCnt )
@@ -1926,6 +1972,7 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 		if ( t4_low_complex( r, o ) )
 			o.similarity = 0 ;
 	}
+#endif
 	if ( fullDps )
 		t4_atomic_add( &cx.g->counters[7], fullDps ) ;
 	t4_atomic_add( &cx.g->counters[6], cx.tid == 0 ? (u64)overlapCnt : 0 ) ;
@@ -2054,87 +2101,61 @@ T4_D inline T4AlignView t4_overhang_align( const int *tw, const char *p, int n, 
 	return v ;
 }
 
-// lbits / rbits: IsBaseEqual( posWeight column, read base ) for the left / right overhang, bit t = t-th overhang position
-T4_D inline int t4_extend_overlap( T4Ctx &cx, const char *r, int len, T4Contig *seq, double mismatchThresholdFactor,
-	T4DpScratch &ds, const T4Ovl &overlap, T4Ovl &ext, const u32 *lbits, const u32 *rbits )
+struct T4SideStats { int m, x, ind, good ; } ;
+
+// Statistics ExtendOverlap takes from one overhang alignment (SeqSet.hpp:1176-1224): edit counts over the whole
+// string, and the longest prefix (seen from the anchor: fromEnd for the left overhang) of match/mismatch ops whose
+// running match fraction exceeds 0.75 at a match.
+T4_D inline T4SideStats t4_side_stats( const T4AlignView &av, bool fromEnd )
+{
+	T4SideStats r ;
+	r.m = r.x = r.ind = r.good = 0 ;
+	for ( int i = 0 ; i < av.n ; ++i )
+	{
+		int e = av.get( i ) ;
+		if ( e == EDIT_MATCH )
+			++r.m ;
+		else if ( e == EDIT_MISMATCH )
+			++r.x ;
+		else
+			++r.ind ;
+	}
+	int tmpMatchCnt = 0 ;
+	for ( int kk = 0 ; kk < av.n ; ++kk )
+	{
+		int e = av.get( fromEnd ? av.n - 1 - kk : kk ) ;
+		if ( e == EDIT_MATCH )
+		{
+			++tmpMatchCnt ;
+			if ( tmpMatchCnt > 0.75 * ( kk + 1 ) )
+				r.good = kk + 1 ;
+		}
+		else if ( e != EDIT_MISMATCH )
+			break ;
+	}
+	return r ;
+}
+
+// The rest of ExtendOverlap (SeqSet.hpp:1226-1277) given both sides' statistics.
+T4_D inline int t4_extend_finish( T4Ctx &cx, int len, T4Contig *seq, double mismatchThresholdFactor, const T4Ovl &overlap, T4Ovl &ext,
+	const T4SideStats &ls, const T4SideStats &rs )
 {
 	T4Stream *st = cx.st ;
-	int matchCnt = 0, mismatchCnt = 0, indelCnt = 0 ;
-	int leftOverhangSize = t4_min( overlap.readStart, overlap.seqStart ) ;
 	int ret = 1 ;
-	int i, k ;
-	int goodLeftOverhangSize = 0 ;
-	int *pw = t4_pw( cx, seq ) ;
-	{
-		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqStart - leftOverhangSize ), r + overlap.readStart - leftOverhangSize,
-			leftOverhangSize, lbits, ds ) ;
-		if ( av.dp )
-			t4_atomic_add( &cx.g->counters[1], 1 ) ;
-		for ( i = 0 ; i < av.n ; ++i )
-		{
-			int e = av.get( i ) ;
-			if ( e == EDIT_MATCH )
-				++matchCnt ;
-			else if ( e == EDIT_MISMATCH )
-				++mismatchCnt ;
-			else
-				++indelCnt ;
-		}
-		if ( indelCnt > 0 )
-		{
-			leftOverhangSize = 0 ;
-			ret = 0 ;
-		}
-		int tmpMatchCnt = 0 ;
-		for ( i = av.n - 1, k = 1 ; i >= 0 ; --i, ++k )
-		{
-			int e = av.get( i ) ;
-			if ( e == EDIT_MATCH )
-			{
-				++tmpMatchCnt ;
-				if ( tmpMatchCnt > 0.75 * k )
-					goodLeftOverhangSize = k ;
-			}
-			else if ( e != EDIT_MISMATCH )
-				break ;
-		}
-	}
+	int leftOverhangSize = t4_min( overlap.readStart, overlap.seqStart ) ;
 	int rightOverhangSize = t4_min( len - 1 - overlap.readEnd, seq->len - 1 - overlap.seqEnd ) ;
-	int goodRightOverhangSize = 0 ;
+	int matchCnt = ls.m + rs.m, mismatchCnt = ls.x + rs.x ;
+	if ( ls.ind > 0 )
 	{
-		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqEnd + 1 ), r + overlap.readEnd + 1, rightOverhangSize, rbits, ds ) ;
-		if ( av.dp )
-			t4_atomic_add( &cx.g->counters[1], 1 ) ;
-		int oldIndelCnt = indelCnt ;
-		for ( i = 0 ; i < av.n ; ++i )
-		{
-			int e = av.get( i ) ;
-			if ( e == EDIT_MATCH )
-				++matchCnt ;
-			else if ( e == EDIT_MISMATCH )
-				++mismatchCnt ;
-			else
-				++indelCnt ;
-		}
-		if ( indelCnt > oldIndelCnt )
-		{
-			rightOverhangSize = 0 ;
-			ret = 0 ;
-		}
-		int tmpMatchCnt = 0 ;
-		for ( i = 0 ; i < av.n ; ++i )
-		{
-			int e = av.get( i ) ;
-			if ( e == EDIT_MATCH )
-			{
-				++tmpMatchCnt ;
-				if ( tmpMatchCnt > 0.75 * ( i + 1 ) )
-					goodRightOverhangSize = i + 1 ;
-			}
-			else if ( e != EDIT_MISMATCH )
-				break ;
-		}
+		leftOverhangSize = 0 ;
+		ret = 0 ;
 	}
+	if ( rs.ind > 0 )
+	{
+		rightOverhangSize = 0 ;
+		ret = 0 ;
+	}
+	int goodLeftOverhangSize = ls.good, goodRightOverhangSize = rs.good ;
 	int mismatchThreshold = 2 ;
 	if ( leftOverhangSize >= 2 )
 		++mismatchThreshold ;
@@ -2168,6 +2189,417 @@ T4_D inline int t4_extend_overlap( T4Ctx &cx, const char *r, int len, T4Contig *
 	}
 	return ret ;
 }
+
+// lbits / rbits: IsBaseEqual( posWeight column, read base ) for the left / right overhang, bit t = t-th overhang position
+T4_D inline int t4_extend_overlap( T4Ctx &cx, const char *r, int len, T4Contig *seq, double mismatchThresholdFactor,
+	T4DpScratch &ds, const T4Ovl &overlap, T4Ovl &ext, const u32 *lbits, const u32 *rbits )
+{
+	int leftOverhangSize = t4_min( overlap.readStart, overlap.seqStart ) ;
+	int rightOverhangSize = t4_min( len - 1 - overlap.readEnd, seq->len - 1 - overlap.seqEnd ) ;
+	int *pw = t4_pw( cx, seq ) ;
+	T4SideStats ls, rs ;
+	{
+		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqStart - leftOverhangSize ), r + overlap.readStart - leftOverhangSize,
+			leftOverhangSize, lbits, ds ) ;
+		if ( av.dp )
+			t4_atomic_add( &cx.g->counters[1], 1 ) ;
+		ls = t4_side_stats( av, true ) ;
+	}
+	{
+		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqEnd + 1 ), r + overlap.readEnd + 1, rightOverhangSize, rbits, ds ) ;
+		if ( av.dp )
+			t4_atomic_add( &cx.g->counters[1], 1 ) ;
+		rs = t4_side_stats( av, false ) ;
+	}
+	return t4_extend_finish( cx, len, seq, mismatchThresholdFactor, overlap, ext, ls, rs ) ;
+}
+
+#if T4_CUDA
+// ---------------------------------------------------------------------------
+// warp-cooperative forms (product build only; the emulation uses the sequential forms above, and the GPU parity
+// tests compare these against the reference)
+// ---------------------------------------------------------------------------
+#define T4_FULL 0xffffffffu
+
+// Banded DP for equal lengths in a HALF warp: the 16 lanes own the 13 window slots, anti-diagonal schedule
+// T = 2 i + slot (cell (i, slot) needs (i-1, slot) at T-2 and (i, slot-1), (i-1, slot+1) at T-1, which are the
+// neighbours' most recent values, exchanged by shuffles).  All 32 lanes call; a half with n == 0 idles.
+// nib: the IsBaseEqual nibbles of the n target columns, 8 per word (staged in shared memory by w_stage_side), so the
+// loop touches no global memory.  actBase / actStride: traceback words of slot s at actBase + s * actStride.
+// Returns the score in every lane of the half; the half's lane 0 writes the edit string to `align`; *alignLen = its length.
+T4_D inline int w_dp_equal_half( T4Ctx &cx, const u32 *nib, const char *p, int n, signed char *alignBuf, int alignCap, int *alignLen,
+	u32 *actBase, int actStride )
+{
+	const int lane = cx.tid & 31, hl = lane & 15 ;
+	const int nmax = max( n, __shfl_xor_sync( T4_FULL, n, 16 ) ) ;
+	const int negInf = ( n + 1 ) * ( n + 1 ) * SCORE_INDEL ;
+	const int j0 = hl - 6 ;
+	int latest = ( j0 == 0 ) ? 0 : ( j0 > 0 ? SCORE_INDEL + j0 * SCORE_INDEL : negInf ) ;
+	u32 *myAct = actBase + hl * actStride ;
+	u32 aw = 0 ;
+	for ( int T = 2 ; T <= 2 * nmax + 12 ; ++T )
+	{
+		int vl = __shfl_up_sync( T4_FULL, latest, 1, 16 ) ;
+		int vu = __shfl_down_sync( T4_FULL, latest, 1, 16 ) ;
+		int i = ( T - hl ) >> 1 ;
+		if ( hl < 13 && ( ( T - hl ) & 1 ) == 0 && i >= 1 && i <= n )
+		{
+			int j = i - 6 + hl ;
+			int start = i - 5 < 1 ? 1 : i - 5 ;
+			int end = i + 5 > n ? n : i + 5 ;
+			int val ;
+			u32 a = 0 ;
+			if ( j == 0 )
+				val = SCORE_INDEL + i * SCORE_INDEL ;
+			else if ( j < start || j > end )
+				val = negInf ;
+			else
+			{
+				char pc = p[i - 1] ;
+				u32 nb = ( nib[( j - 1 ) >> 3] >> ( 4 * ( ( j - 1 ) & 7 ) ) ) & 15u ;
+				bool eq = ( pc == 'N' ) || ( ( nb >> t4_nuc( pc ) ) & 1u ) ;
+				int diff = eq ? SCORE_MATCH : SCORE_MISMATCH ;
+				int dg = latest + diff, lf = vl + SCORE_INDEL, up = vu + SCORE_INDEL ;
+				val = dg ;
+				if ( lf > val ) val = lf ;
+				if ( up > val ) val = up ;
+				if ( lf == val ) a = EDIT_DELETE ;
+				if ( up == val ) a = EDIT_INSERT ;
+				if ( dg == val ) a = eq ? EDIT_MATCH : EDIT_MISMATCH ;
+			}
+			aw |= a << ( 2 * ( i & 15 ) ) ;
+			if ( ( i & 15 ) == 15 || i == n )
+			{
+				myAct[i >> 4] = aw ;
+				aw = 0 ;
+			}
+			latest = val ;
+		}
+	}
+	int ret = __shfl_sync( T4_FULL, latest, 6, 16 ) ;
+	__syncwarp() ;
+	int tag = 0 ;
+	if ( hl == 0 && n > 0 )
+	{
+		// the edit string is written from the end of the buffer towards its start: it ends up in reading order at
+		// alignBuf + alignCap - 1 - tag without a reversal pass
+		signed char *align = alignBuf + alignCap - 1 ;
+		*align = -1 ;
+		int tagi = n, tagj = n ;
+		while ( tagi > 0 || tagj > 0 )
+		{
+			int a ;
+			if ( tagi > 0 && tagj > 0 )
+			{
+				int slot = tagj - ( tagi - 6 ) ;
+				a = (int)( ( actBase[slot * actStride + ( tagi >> 4 )] >> ( 2 * ( tagi & 15 ) ) ) & 3u ) ;
+			}
+			else if ( tagj > 0 )
+				a = ( tagj >= 2 ) ? EDIT_DELETE : EDIT_MATCH ;
+			else
+				a = ( tagi >= 2 ) ? EDIT_INSERT : EDIT_MATCH ;
+			++tag ;
+			align[-tag] = (signed char)a ;
+			if ( a == EDIT_DELETE )
+				--tagj ;
+			else if ( a == EDIT_INSERT )
+				--tagi ;
+			else
+			{
+				--tagi ;
+				--tagj ;
+			}
+		}
+	}
+	tag = __shfl_sync( T4_FULL, tag, 0, 16 ) ;
+	__syncwarp() ;
+	*alignLen = tag ;
+	return ret ;
+}
+
+// Stage one side for a warp: the n columns tw[0..n) against p[0..n): IsBaseEqual nibbles (8 per word) and the
+// match bits, into shared memory, with coalesced 16-byte column loads.  Returns the number of matches.
+T4_D inline int w_stage_side( const int *tw, const char *p, int n, u32 *nibOut, u32 *bitsOut, int lane )
+{
+	const int4 *tw4 = (const int4 *)tw ;
+	int matches = 0 ;
+	for ( int t0 = 0 ; t0 < n ; t0 += 32 )
+	{
+		int t = t0 + lane ;
+		u32 nb = 0 ;
+		bool eq = false ;
+		if ( t < n )
+		{
+			int4 w = tw4[t] ;
+			int sum = w.x + w.y + w.z + w.w ;
+			nb = ( sum == 0 ) ? 0xFu : ( ( sum < 3 * w.x ? 1u : 0u ) | ( sum < 3 * w.y ? 2u : 0u ) | ( sum < 3 * w.z ? 4u : 0u ) | ( sum < 3 * w.w ? 8u : 0u ) ) ;
+			char pc = p[t] ;
+			eq = ( pc == 'N' ) || ( ( nb >> t4_nuc( pc ) ) & 1u ) ;
+		}
+		u32 v = nb << ( 4 * ( lane & 7 ) ) ;
+		v |= __shfl_xor_sync( T4_FULL, v, 1 ) ;
+		v |= __shfl_xor_sync( T4_FULL, v, 2 ) ;
+		v |= __shfl_xor_sync( T4_FULL, v, 4 ) ;
+		if ( ( lane & 7 ) == 0 )
+			nibOut[( t0 >> 3 ) + ( lane >> 3 )] = v ;
+		u32 mb = __ballot_sync( T4_FULL, eq ) ;
+		if ( lane == 0 )
+			bitsOut[t0 >> 5] = mb ;
+		matches += __popc( mb ) ;
+	}
+	__syncwarp() ;
+	return matches ;
+}
+
+// t4_side_stats with all 32 lanes (ballots / popcounts).  Identical in every lane.
+T4_D inline T4SideStats w_side_stats( const T4AlignView &v, bool fromEnd, int lane )
+{
+	T4SideStats r ;
+	r.m = r.x = r.ind = r.good = 0 ;
+	int mbase = 0 ;
+	bool stopped = false ;
+	for ( int base = 0 ; base < v.n ; base += 32 )
+	{
+		int kk = base + lane ;
+		int e = -1 ;
+		if ( kk < v.n )
+			e = v.get( fromEnd ? v.n - 1 - kk : kk ) ;
+		unsigned mb = __ballot_sync( T4_FULL, e == EDIT_MATCH ) ;
+		unsigned xb = __ballot_sync( T4_FULL, e == EDIT_MISMATCH ) ;
+		unsigned ib = __ballot_sync( T4_FULL, e == EDIT_INSERT || e == EDIT_DELETE ) ;
+		r.m += __popc( mb ) ;
+		r.x += __popc( xb ) ;
+		r.ind += __popc( ib ) ;
+		if ( !stopped )
+		{
+			unsigned le = ( lane == 31 ) ? 0xffffffffu : ( ( 1u << ( lane + 1 ) ) - 1u ) ;
+			int mk = mbase + __popc( mb & le ) ;
+			bool cond = ( e == EDIT_MATCH ) && ( ( ib & le ) == 0 ) && ( mk > 0.75 * ( kk + 1 ) ) ;
+			unsigned cb = __ballot_sync( T4_FULL, cond ) ;
+			if ( cb )
+				r.good = base + ( 31 - __clz( cb ) ) + 1 ;
+			if ( ib )
+				stopped = true ;
+			mbase += __popc( mb ) ;
+		}
+	}
+	return r ;
+}
+
+T4_D inline signed char *t4_align_of_thread( T4Ctx &cx, int tid )
+{
+	return (signed char *)( cx.P<char>( cx.st->dpOff ) + (size_t)tid * cx.st->dpStride + 2 * T4_DP_W * 4 + 8
+		+ ( T4_DEV_MAX_READ + 1 ) * T4_DP_W + 8 ) ;
+}
+
+// number of matches among the first n bits
+T4_D inline int t4_bits_matches( const u32 *bits, int n )
+{
+	int m = 0 ;
+	for ( int w = 0 ; w * 32 < n ; ++w )
+	{
+		u32 x = bits[w] ;
+		if ( ( w + 1 ) * 32 > n )
+			x &= ( 1u << ( n - w * 32 ) ) - 1u ;
+		m += __popc( x ) ;
+	}
+	return m ;
+}
+
+// ExtendOverlap for every overlap: one warp per overlap (round robin), both overhang DPs at once in the two half warps.
+T4_D inline void c_extend_all_warp( T4Ctx &cx, const char *r, int len, double factor, const T4Ovl *overlaps, int overlapCnt,
+	T4Ovl *pre )
+{
+	T4Smem *sm = cx.sm ;
+	const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31 ;
+	for ( int i = warp ; i < overlapCnt ; i += nwarps )
+	{
+		long long tc0 = clock64() ;
+		const T4Ovl o = overlaps[i] ;
+		T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+		const int *pw = t4_pw( cx, seq ) ;
+		const int L = t4_min( o.readStart, o.seqStart ) ;
+		const int R = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
+		u32 *lb = sm->wbits[warp][0], *rb = sm->wbits[warp][1] ;
+		const int *twL = pw + 4 * ( o.seqStart - L ), *twR = pw + 4 * ( o.seqEnd + 1 ) ;
+		const char *pL = r + o.readStart - L, *pR = r + o.readEnd + 1 ;
+		const int mL = w_stage_side( twL, pL, L, sm->wnib[warp][0], lb, lane ) ;
+		const int mR = w_stage_side( twR, pR, R, sm->wnib[warp][1], rb, lane ) ;
+		const bool dpL = L >= 2 && ( SCORE_MATCH * mL + SCORE_MISMATCH * ( L - mL ) < L * SCORE_MATCH + 2 * SCORE_INDEL ) ;
+		const bool dpR = R >= 2 && ( SCORE_MATCH * mR + SCORE_MISMATCH * ( R - mR ) < R * SCORE_MATCH + 2 * SCORE_INDEL ) ;
+		long long tc1 = clock64() ;
+		signed char *alL = 0, *alR = 0 ;
+		int lenL = L, lenR = R ;
+		if ( dpL || dpR )
+		{
+			const bool left = lane < 16 ;
+			int n = left ? ( dpL ? L : 0 ) : ( dpR ? R : 0 ) ;
+			int nOther = __shfl_xor_sync( T4_FULL, n, 16 ) ;
+			bool small = ( n < 16 * T4_WACT_WORDS ) && ( nOther < 16 * T4_WACT_WORDS ) ;
+			T4DpScratch ds = t4_dp_scratch( cx ) ;
+			// traceback words: shared memory when both sides fit, else this thread-group's global scratch
+			u32 *actBase = small ? sm->wact[warp][left ? 0 : 1] : (u32 *)t4_dp_scratch_of( cx, ( cx.tid & ~15 ) ).act ;
+			int actStride = small ? T4_WACT_WORDS : (int)( T4_DP_STRIDE / 4 ) ;
+			int al = 0 ;
+			signed char *abuf = small ? sm->wal[warp][left ? 0 : 1] : t4_align_of_thread( cx, cx.tid & ~15 ) ;
+			int acap = small ? (int)sizeof( sm->wal[0][0] ) : 2 * T4_DEV_MAX_READ + 8 ;
+			w_dp_equal_half( cx, sm->wnib[warp][left ? 0 : 1], left ? pL : pR, n, abuf, acap, &al, actBase, actStride ) ;
+			int alOther = __shfl_xor_sync( T4_FULL, al, 16 ) ;
+			// start of each side's edit string (every lane needs both pointers)
+			signed char *bufL = small ? sm->wal[warp][0] : t4_align_of_thread( cx, warp * 32 ) ;
+			signed char *bufR = small ? sm->wal[warp][1] : t4_align_of_thread( cx, warp * 32 + 16 ) ;
+			if ( dpL )
+			{
+				lenL = left ? al : alOther ;
+				alL = bufL + acap - 1 - lenL ;
+			}
+			if ( dpR )
+			{
+				lenR = left ? alOther : al ;
+				alR = bufR + acap - 1 - lenR ;
+			}
+			if ( lane == 0 )
+				t4_atomic_add( &cx.g->counters[1], (u64)( ( dpL ? 1 : 0 ) + ( dpR ? 1 : 0 ) ) ) ;
+			(void)ds ;
+		}
+		long long tc2 = clock64() ;
+		T4AlignView vl, vr ;
+		vl.a = dpL ? alL : 0 ; vl.bits = lb ; vl.n = lenL ; vl.dp = dpL ;
+		vr.a = dpR ? alR : 0 ; vr.bits = rb ; vr.n = lenR ; vr.dp = dpR ;
+		T4SideStats ls = w_side_stats( vl, true, lane ) ;
+		T4SideStats rs = w_side_stats( vr, false, lane ) ;
+		if ( lane == 0 )
+		{
+			T4Ovl e ;
+			int ok = t4_extend_finish( cx, len, seq, factor, o, e, ls, rs ) ;
+			e.infoFromHits = ok ;
+			pre[i] = e ;
+			long long tc3 = clock64() ;
+			t4_atomic_add( &cx.g->counters[17], (u64)( tc1 - tc0 ) ) ;
+			t4_atomic_add( &cx.g->counters[18], (u64)( tc2 - tc1 ) ) ;
+			t4_atomic_add( &cx.g->counters[19], (u64)( tc3 - tc2 ) ) ;
+			t4_atomic_add( &cx.g->counters[20], (u64)( ( dpL || dpR ) ? ( ( dpL ? L : 0 ) > ( dpR ? R : 0 ) ? ( dpL ? L : 0 ) : ( dpR ? R : 0 ) ) : 0 ) ) ;
+		}
+		__syncwarp() ;
+	}
+}
+
+// Overlap scoring (SeqSet.hpp:1832-2020) for every overlap: one warp per overlap, lanes over consecutive hit pairs.
+// A failed overlap (gap over the limit, or an indel in a gap) gets similarity 0; its counts are unobservable.
+T4_D inline void c_score_all_warp( T4Ctx &cx, T4Ovl *ovl, int overlapCnt, const u64 *keys )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	const int k = st->kmerLength ;
+	const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31 ;
+	u64 fullDps = 0 ;
+	for ( int i = warp ; i < overlapCnt ; i += nwarps )
+	{
+		const T4Ovl o = ovl[i] ;
+		const char *r = ( o.strand == 1 ) ? sm->read : sm->rc ;
+		const u64 *hc = keys + o.hcStart ;
+		const int hitCnt = o.hcCnt ;
+		const int *pw = t4_pw( cx, t4_seq( cx, o.seqIdx ) ) ;
+		int acc = 0 ;           // per-lane partial of matchCnt
+		bool fail = false ;
+		for ( int base = 1 ; base < hitCnt && !fail ; base += 32 )
+		{
+			int j = base + lane ;
+			int a0 = 0, a1 = 0, b0 = 0 ;
+			bool gapHere = false ;
+			if ( j < hitCnt )
+			{
+				u64 k0 = hc[j - 1], k1 = hc[j] ;
+				a0 = t4_key_a( k0 ) ; a1 = t4_key_a( k1 ) ; b0 = t4_key_b( k0 ) ;
+				if ( a0 + k - 1 >= a1 )
+					acc += 2 * ( a1 - a0 ) ;
+				else
+				{
+					acc += 2 * k ;
+					gapHere = true ;
+				}
+			}
+			unsigned gb = __ballot_sync( T4_FULL, gapHere ) ;
+			while ( gb && !fail )
+			{
+				int src = __ffs( gb ) - 1 ;
+				gb &= gb - 1 ;
+				int ga0 = __shfl_sync( T4_FULL, a0, src ), ga1 = __shfl_sync( T4_FULL, a1, src ), gb0 = __shfl_sync( T4_FULL, b0, src ) ;
+				int gap = ga1 - ( ga0 + k ) ;
+				if ( gap > st->nomatchGapLimit )
+				{
+					fail = true ;
+					break ;
+				}
+				const int *tw = pw + 4 * ( gb0 + k ) ;
+				const char *p = r + ga0 + k ;
+				// IsBaseEqual along the diagonal of the gap (nibbles + match bits staged in shared memory)
+				int matches = w_stage_side( tw, p, gap, sm->wnib[warp][0], sm->wbits[warp][0], lane ) ;
+				int cnt0 = matches ;
+				if ( gap >= 2 && SCORE_MATCH * matches + SCORE_MISMATCH * ( gap - matches ) < gap * SCORE_MATCH + 2 * SCORE_INDEL )
+				{
+					int alen = 0 ;
+					bool small = gap < 16 * T4_WACT_WORDS ;
+					u32 *actBase = small ? sm->wact[warp][lane < 16 ? 0 : 1] : (u32 *)t4_dp_scratch_of( cx, ( cx.tid & ~15 ) ).act ;
+					int actStride = small ? T4_WACT_WORDS : (int)( T4_DP_STRIDE / 4 ) ;
+					signed char *abuf = small ? sm->wal[warp][lane < 16 ? 0 : 1] : t4_align_of_thread( cx, cx.tid & ~15 ) ;
+					int acap = small ? (int)sizeof( sm->wal[0][0] ) : 2 * T4_DEV_MAX_READ + 8 ;
+					w_dp_equal_half( cx, sm->wnib[warp][0], p, lane < 16 ? gap : 0, abuf, acap, &alen, actBase, actStride ) ;
+					alen = __shfl_sync( T4_FULL, alen, 0 ) ;
+					++fullDps ;
+					signed char *buf0 = small ? sm->wal[warp][0] : t4_align_of_thread( cx, warp * 32 ) ;
+					T4AlignView v ;
+					v.a = buf0 + acap - 1 - alen ; v.bits = 0 ; v.n = alen ; v.dp = 1 ;
+					T4SideStats ss = w_side_stats( v, false, lane ) ;
+					cnt0 = ss.m ;
+					if ( ss.ind > 0 )
+						fail = true ;
+				}
+				if ( lane == 0 )
+					acc += 2 * cnt0 ;
+			}
+		}
+		int matchCnt = 2 * k + __reduce_add_sync( T4_FULL, acc ) ;
+		// IsOverlapLowComplex (SeqSet.hpp:590)
+		int c0 = 0, c1 = 0, c2 = 0, c3 = 0 ;
+		for ( int t0 = o.readStart ; t0 <= o.readEnd ; t0 += 32 )
+		{
+			int t = t0 + lane ;
+			int x = -1 ;
+			if ( t <= o.readEnd && r[t] != 'N' )
+				x = t4_nuc( r[t] ) ;
+			c0 += __popc( __ballot_sync( T4_FULL, x == 0 ) ) ;
+			c1 += __popc( __ballot_sync( T4_FULL, x == 1 ) ) ;
+			c2 += __popc( __ballot_sync( T4_FULL, x == 2 ) ) ;
+			c3 += __popc( __ballot_sync( T4_FULL, x == 3 ) ) ;
+		}
+		if ( lane == 0 )
+		{
+			T4Ovl &w = ovl[i] ;
+			w.preMatchCnt = o.matchCnt ;
+			w.matchCnt = matchCnt ;
+			w.indelCnt = 0 ;
+			double sim = 0 ;
+			if ( !fail )
+				sim = (double)matchCnt / ( o.seqEnd - o.seqStart + 1 + o.readEnd - o.readStart + 1 ) ;
+			int cnt[4] = { c0, c1, c2, c3 } ;
+			int lowCnt = 0, lowTotalCnt = 0 ;
+			for ( int x = 0 ; x < 4 ; ++x )
+				if ( cnt[x] <= 2 )
+				{
+					++lowCnt ;
+					lowTotalCnt += cnt[x] ;
+				}
+			if ( !( lowTotalCnt * 7 >= o.readEnd - o.readStart + 1 ) && lowCnt >= 2 )
+				sim = 0 ;
+			w.similarity = sim ;
+		}
+		__syncwarp() ;
+	}
+	if ( lane == 0 && fullDps )
+		t4_atomic_add( &cx.g->counters[7], fullDps ) ;
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // gene names
@@ -2601,6 +3033,9 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		t4_atomic_add( &cx.g->counters[16], (u64)overlapCnt ) ;
 	T4Ovl *pre = cx.P<T4Ovl>( st->extOff ) ;
 	{
+#if 0
+		c_extend_all_warp( cx, r, len, factor, overlaps, overlapCnt, pre ) ;
+#else
 		// IsBaseEqual of every overhang column, 32 positions per work item, spread over the CTA
 		u32 *bits = cx.P<u32>( st->bitsOff ) ;
 		T4_PAR_FOR( x, overlapCnt * 32 )
@@ -2633,15 +3068,39 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 			bits[x] = m ;
 		}
 		T4_SYNC() ;
+		// one thread per (overlap, side): the two overhang alignments of an overlap are independent
 		T4DpScratch ds = t4_dp_scratch( cx ) ;
+		T4SideStats *sstats = (T4SideStats *)cx.P<char>( st->failOff ) ; // scratch: 2 per overlap (failOff is unused until the decision)
+		T4_PAR_FOR( x, 2 * overlapCnt )
+		{
+			int i = x >> 1, right = x & 1 ;
+			const T4Ovl &o = overlaps[i] ;
+			T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+			int *pw = t4_pw( cx, seq ) ;
+			T4AlignView av ;
+			if ( !right )
+			{
+				int L = t4_min( o.readStart, o.seqStart ) ;
+				av = t4_overhang_align( pw + 4 * ( o.seqStart - L ), r + o.readStart - L, L, bits + 32 * i, ds ) ;
+			}
+			else
+			{
+				int R = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
+				av = t4_overhang_align( pw + 4 * ( o.seqEnd + 1 ), r + o.readEnd + 1, R, bits + 32 * i + 16, ds ) ;
+			}
+			if ( av.dp )
+				t4_atomic_add( &cx.g->counters[1], 1 ) ;
+			sstats[x] = t4_side_stats( av, !right ) ;
+		}
+		T4_SYNC() ;
 		T4_PAR_FOR( i, overlapCnt )
 		{
 			T4Ovl e ;
-			int ok = t4_extend_overlap( cx, r, len, t4_seq( cx, overlaps[i].seqIdx ), factor, ds, overlaps[i], e, bits + 32 * i,
-				bits + 32 * i + 16 ) ;
+			int ok = t4_extend_finish( cx, len, t4_seq( cx, overlaps[i].seqIdx ), factor, overlaps[i], e, sstats[2 * i], sstats[2 * i + 1] ) ;
 			e.infoFromHits = ok ; // aux: the return value
 			pre[i] = e ;
 		}
+#endif
 	}
 	T4_SYNC() ;
 	T4_PHASE( cx, 6 ) ;
