@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="CPU time budget of one reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--contiguous", action="store_true", help="contiguous shards instead of dealing runs round-robin")
     return ap.parse_args()
 
 
@@ -60,7 +61,7 @@ def make_workload(args, rank, device):
     cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
     rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
     w = synth.build_workload(cl, rd, device=device)
-    off, descs = synth.shard_workload(w, args.streams)
+    off, descs = synth.shard_workload(w, args.streams, deal=not args.contiguous)
     return w, off, descs
 
 
@@ -155,8 +156,8 @@ def main():
         args.gpus = world
     cores = os.cpu_count() or 1
     config = {"workload": "configs[1]: %d synthetic 150bp PE pairs (%d reads) per GPU vs human_IMGT+C gene pool, k=9, "
-                          "read-sharded into %d streams per GPU (one SeqSet each, per-shard parity, SURVEY.md 8e)"
-                          % (args.pairs, 2 * args.pairs, args.streams),
+                          "read-sharded into %d streams per GPU (runs of identical reads %s; one SeqSet each, per-shard parity, SURVEY.md 8e)"
+                          % (args.pairs, 2 * args.pairs, args.streams, "in contiguous blocks" if args.contiguous else "dealt round-robin"),
               "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150,
               "l2": "inputs (>= 400 MB of reads + records, GBs of stream state) exceed the 126 MB L2",
               "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective"}
@@ -279,6 +280,12 @@ def main():
     c1 = np.zeros(api.N_COUNTERS, dtype=np.uint64)
     lib.check(lib.last_counters(c1.ctypes.data))
     dc = (c1 - c0).astype(np.float64)
+    cyc = np.zeros(S, dtype=np.uint64)
+    lib.check(lib.streams_cycles(handles, S, cyc.ctypes.data))
+    cycf = cyc.astype(np.float64)
+    balance = {"mean_ms": float(cycf.mean() / 1.965e6), "max_ms": float(cycf.max() / 1.965e6), "p50_ms": float(np.median(cycf) / 1.965e6),
+               "p99_ms": float(np.percentile(cycf, 99) / 1.965e6),
+               "by_decile_of_stream_index_ms": [float(x.mean() / 1.965e6) for x in np.array_split(cycf, 10)]}
     # probe ceil(L/4) + sum(8 + 8 c_j) + 16 sum c_j'; chain 2 x 16 sum c_j'; commit 8 L per assembled read
     b_probe = dc[5] + 8 * dc[2] + 8 * dc[3] + 16 * dc[4]
     b_chain = 32 * dc[4]
@@ -299,7 +306,7 @@ def main():
                              "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads,
                              "ext_cycles_stage_dp_tail_per_overlap": [dc[17] / max(1, dc[16]), dc[18] / max(1, dc[16]), dc[19] / max(1, dc[16])],
                              "ext_dp_rows_per_overlap": dc[20] / max(1, dc[16])},
-                "phase_share": dict(zip(["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"],
+                "stream_balance": balance, "phase_share": dict(zip(["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"],
                                         [round(float(x), 4) for x in (dc[8:16] / max(1.0, dc[8:16].sum()))]))}
 
     roofline_probe = None

@@ -200,6 +200,8 @@ int t4_streams_pack_contigs(t4_seqset *const *sets, int n_sets, void *dev_buf, s
 
 /* First device-side error among the streams (0 = none); details in t4_last_error(). */
 int t4_streams_error(t4_seqset *const *sets, int n_sets);
+/* Diagnostics: SM clock cycles the last op spent on each stream (load-balance analysis). */
+int t4_streams_cycles(t4_seqset *const *sets, int n_sets, uint64_t *cycles);
 /* Test hook: number of postings in the k-mer index and an order-independent checksum of them. */
 int64_t t4_seqset_index_checksum(t4_seqset *s, uint64_t *checksum);
 

@@ -16,6 +16,10 @@ def test_emu_batch_vs_reference(emu_lib, ref, seed, shards):
     assert pc.check_batch_vs_ref(emu_lib, ref, seed, shards) > 100
 
 
+def test_emu_batch_dealt_shards(emu_lib, ref):
+    assert pc.check_batch_vs_ref(emu_lib, ref, 6, 5, nclones=30, npairs=600, deal=True) > 100
+
+
 def test_emu_stage_parity(emu_lib, ref):
     pc.check_stage_parity(emu_lib, ref, "synth2k", every=131, max_checks=25)
 

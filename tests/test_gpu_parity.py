@@ -22,6 +22,12 @@ def test_gpu_batch_vs_reference(gpu_lib, ref, seed, shards):
     assert pc.check_batch_vs_ref(gpu_lib, ref, seed, shards, nclones=40, npairs=1500) > 100
 
 
+@pytest.mark.parametrize("seed,shards", [(11, 7), (12, 96)])
+def test_gpu_batch_dealt_shards(gpu_lib, ref, seed, shards):
+    """Runs of identical reads dealt round-robin to the streams (bench.py's default sharding)."""
+    assert pc.check_batch_vs_ref(gpu_lib, ref, seed, shards, nclones=60, npairs=2500, deal=True) > 100
+
+
 def test_gpu_batch_larger_single_stream(gpu_lib, ref):
     """One stream, enough contigs for the periodic UpdateAllConsensus (every 10000 assembled reads)."""
     assert pc.check_batch_vs_ref(gpu_lib, ref, 9, 1, nclones=300, npairs=6000) > 10000

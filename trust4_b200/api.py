@@ -31,7 +31,7 @@ EXPORTS = [
     "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch",
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
     "streams_run_resident", "workload_results", "last_counters", "probe_resident", "streams_error",
-    "seqset_index_checksum", "streams_pack_contigs",
+    "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
 ]
 
 
@@ -92,6 +92,7 @@ class Lib:
         f("probe_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
         f("streams_error", ci, [C.POINTER(vp), ci])
         f("seqset_index_checksum", C.c_int64, [vp, C.POINTER(C.c_uint64)])
+        f("streams_cycles", ci, [C.POINTER(vp), ci, vp])
         f("streams_pack_contigs", ci, [C.POINTER(vp), ci, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64)])
 
     def _f(self, name, restype, argtypes):

@@ -1415,6 +1415,19 @@ int T4_API( streams_pack_contigs )( t4_seqset *const *sets, int n_sets, void *de
 	return 0 ;
 }
 
+// Diagnostics: SM clock cycles the last op took on each stream.
+int T4_API( streams_cycles )( t4_seqset *const *sets, int n_sets, uint64_t *cycles )
+{
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		T4Stream st ;
+		int r = get_stream( sets[j], &st ) ;
+		if ( r ) return r ;
+		cycles[j] = st.nReads ;
+	}
+	return 0 ;
+}
+
 // first device-side error among the given streams (0 if none)
 int T4_API( streams_error )( t4_seqset *const *sets, int n_sets )
 {

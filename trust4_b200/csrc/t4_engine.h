@@ -4222,8 +4222,15 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 #if T4_CUDA
 	T4_PHASE( cx, 0 ) ;
 	if ( cx.tid == 0 )
+	{
+		u64 tot = 0 ;
 		for ( int i = 0 ; i < 8 ; ++i )
+		{
 			t4_atomic_add( &cx.g->counters[8 + i], (u64)sm->ph[i] ) ;
+			tot += (u64)sm->ph[i] ;
+		}
+		st->nReads = tot ; // clock cycles this op took on this stream (diagnostics: t4_streams_cycles)
+	}
 #endif
 	(void)sm ;
 }

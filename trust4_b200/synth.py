@@ -422,11 +422,44 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
     return Workload(descs, pool, names, L, order)
 
 
-def shard_workload(w: Workload, n_shards: int):
-    """Deal the sorted records into contiguous shards: returns desc_off[n_shards+1]
-    and a copy of the records with mate_idx / eq_* made shard-relative (mates in other shards -> -1).
-    Shard boundaries never split a run of identical reads."""
+def shard_workload(w: Workload, n_shards: int, deal: bool = False):
+    """Shard the sorted records into n_shards independent streams.  Returns desc_off[n_shards+1]
+    and the records in stream order with mate_idx / eq_* made stream-relative (mates in other streams -> -1).
+    A run of identical reads is never split (RepeatAddRead semantics survive), and every stream keeps the global
+    sorted order of its reads.
+
+    deal=False: contiguous blocks of the sorted list.
+    deal=True : runs are dealt round-robin (run r -> stream r mod n_shards).  Every stream then sees a uniform sample
+                of the library instead of one abundance class, which equalises the work per stream (contiguous blocks
+                of low-abundance reads are ~50x more expensive than blocks of duplicates)."""
     n = len(w.descs)
+    d = w.descs.copy()
+    if deal:
+        same_prev = (d["flags"] & RD_DUP) != 0
+        # a run = maximal range of identical read strings (eq_lo..eq_hi), which contains its DUP records
+        run_id = np.cumsum(d["eq_lo"] == np.arange(n)) - 1
+        shard_of = (run_id % n_shards).astype(np.int64)
+        order = np.argsort(shard_of, kind="stable")
+        counts = np.bincount(shard_of, minlength=n_shards)
+        off = np.zeros(n_shards + 1, dtype=np.int64)
+        off[1:] = np.cumsum(counts)
+        new_pos = np.empty(n, dtype=np.int64)
+        new_pos[order] = np.arange(n)
+        base_new = off[shard_of]                       # stream start in the new array, per old index
+        mate = d["mate_idx"].astype(np.int64)
+        has = mate >= 0
+        same = np.zeros(n, dtype=bool)
+        same[has] = shard_of[mate[has]] == shard_of[has]
+        rel_mate = np.full(n, -1, dtype=np.int64)
+        rel_mate[same] = new_pos[mate[same]] - base_new[same]
+        d["mate_idx"] = rel_mate
+        # a run stays contiguous inside its stream: its new range starts at new_pos[eq_lo]
+        lo_new = new_pos[d["eq_lo"].astype(np.int64)]
+        length = d["eq_hi"].astype(np.int64) - d["eq_lo"].astype(np.int64)
+        d["eq_lo"] = lo_new - base_new
+        d["eq_hi"] = lo_new - base_new + length
+        del same_prev
+        return off, d[order]
     bounds = [0]
     for s in range(1, n_shards):
         b = (n * s) // n_shards
@@ -434,7 +467,6 @@ def shard_workload(w: Workload, n_shards: int):
         bounds.append(max(b, bounds[-1]))
     bounds.append(n)
     off = np.array(bounds, dtype=np.int64)
-    d = w.descs.copy()
     shard_of = np.searchsorted(off, np.arange(n), side="right") - 1
     base = off[shard_of]
     mate = d["mate_idx"].astype(np.int64)
