@@ -160,7 +160,8 @@ def main():
                           % (args.pairs, 2 * args.pairs, args.streams, "in contiguous blocks" if args.contiguous else "dealt round-robin"),
               "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150,
               "l2": "inputs (>= 400 MB of reads + records, GBs of stream state) exceed the 126 MB L2",
-              "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective"}
+              "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective; "
+                          "N>1: one NCCL all-gather of the packed per-rank contig sets per step (merge step)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -219,16 +220,34 @@ def main():
         raise RuntimeError(lib.err())
     handles = (C.c_void_p * S)()
 
+    merged = {"bytes": 0, "contigs": 0}
+
+    def merge_exchange():
+        """Merge step of a read-sharded multi-GPU run: pack this rank's contigs on the device and all-gather them
+        over NCCL (sizes first, then the padded payload); every rank ends up with all contig sets."""
+        if world == 1:
+            return
+        from trust4_b200 import dist as tdist
+        need, nc = C.c_size_t(), C.c_int64()
+        lib.check(lib.streams_pack_contigs(handles, S, None, 0, C.byref(need), C.byref(nc)))
+        buf = torch.empty(max(16, need.value), dtype=torch.uint8, device=dev)
+        lib.check(lib.streams_pack_contigs(handles, S, buf.data_ptr(), buf.numel(), C.byref(need), C.byref(nc)))
+        parts = tdist.allgather_contigs(buf[: need.value])
+        merged["bytes"] = int(sum(p.numel() for p in parts))
+        merged["contigs"] = int(nc.value)
+
     def step_resident():
         lib.check(lib.reset())
         lib.check(lib.seqsets_create(S, 9, handles))
         lib.check(lib.streams_run_resident(handles, S, cfg.ctypes.data, wl, off64.ctypes.data, None))
+        merge_exchange()
 
     def step_e2e():
         lib.check(lib.reset())
         lib.check(lib.seqsets_create(S, 9, handles))
         lib.check(lib.streams_run(handles, S, cfg.ctypes.data, pin_descs.data_ptr(), off64.ctypes.data, pin_pool.data_ptr(),
                                   pin_pool.numel(), names_arr, len(w.names), ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
+        merge_exchange()
 
     def barrier():
         if world > 1:
@@ -345,7 +364,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": 2 * args.steps, "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
-                "assembled_reads": assembled, "reads_per_gpu": n_reads, "workload_gen_s": t_gen,
+                "assembled_reads": assembled, "reads_per_gpu": n_reads, "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
                 "threads_per_stream": int(os.environ.get("T4_NT", 128))}
         print(json.dumps(line))
     lib.workload_free(wl)

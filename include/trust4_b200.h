@@ -205,11 +205,11 @@ int t4_streams_cycles(t4_seqset *const *sets, int n_sets, uint64_t *cycles);
 /* Test hook: number of postings in the k-mer index and an order-independent checksum of them. */
 int64_t t4_seqset_index_checksum(t4_seqset *s, uint64_t *checksum);
 
-/* Per-launch device counters of the last run (summed over streams):
- * [0] reads processed, [1] AddRead executed, [2] k-mer lookups executed, [3] postings read (sum c_j),
- * [4] hits emitted (sum c_j'), [5] read bytes, [6] overlaps scored, [7] full banded DPs,
- * [8] probe-phase clock cycles (sum over CTAs), [9] total clock cycles (sum over CTAs),
- * [10..15] per-phase cycles: sort, chain, score, decide, commit, other. */
+/* Device counters accumulated since the last t4_reset()/probe (summed over streams):
+ * [0] reads processed, [1] overhang DPs (ExtendOverlap), [2] k-mer lookups executed, [3] postings read (sum c_j),
+ * [4] hits emitted (sum c_j'), [5] packed read bytes ceil(L/4), [6] overlaps scored, [7] gap DPs,
+ * [8..15] clock cycles per phase: other, probe, hit sort, chains, scoring, ExtendOverlap, decide+commit,
+ * InputNovelRead/RepeatAddRead/consensus; [16] overlaps extended; [17..23] reserved. */
 #define T4_N_COUNTERS 24
 int t4_last_counters(uint64_t *counters /* T4_N_COUNTERS */);
 

@@ -54,6 +54,7 @@ struct T4Smem
 	u32 wbits[T4_MAX_NT / 32][2][16] ;       // ... and the match bits against the read
 	u32 wact[T4_MAX_NT / 32][2][13 * T4_WACT_WORDS] ; // ... traceback words of the half-warp DP (n <= 16*T4_WACT_WORDS - 1)
 	signed char wal[T4_MAX_NT / 32][2][2 * 16 * T4_WACT_WORDS + 8] ; // ... and its edit string (filled backwards: no reversal pass)
+	u64 ctr[T4_N_COUNTERS] ; // device counters of this op, flushed to the arena header once at the end
 	long long ph[8] ;      // per-phase clock accumulators (thread 0)
 	long long phLast ;
 	int phCur ;
@@ -72,6 +73,17 @@ struct T4Ctx
 } ;
 
 #define T4_PAR_FOR( i, n ) for ( int i = cx.tid ; i < (int)( n ) ; i += cx.nt )
+
+T4_D inline void t4_count( T4Ctx &cx, int idx, u64 v )
+{
+	if ( v == 0 )
+		return ;
+#if T4_CUDA
+	atomicAdd( (unsigned long long *)&cx.sm->ctr[idx], (unsigned long long)v ) ;
+#else
+	cx.sm->ctr[idx] += v ;
+#endif
+}
 
 // phase accounting (thread 0): 0 other, 1 probe, 2 hit sort, 3 chains, 4 overlap sort + scoring, 5 ExtendOverlap,
 // 6 decision + commit, 7 InputNovelRead / RepeatAddRead / consensus maintenance
@@ -141,6 +153,9 @@ T4_D inline u32 t4_atomic_add32( u32 *p, u32 v )
 	u32 o = *p ; *p += v ; return o ;
 #endif
 }
+
+struct T4Ctx ;
+T4_D inline void t4_count( T4Ctx &cx, int idx, u64 v ) ;
 
 T4_D inline void t4_raise( T4Ctx &cx, int code, int aux )
 {
@@ -1450,10 +1465,10 @@ T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool al
 		{
 			sm->bi[0] = (int)total ;
 			sm->bi[1] = 0 ;
-			t4_atomic_add( &cx.g->counters[2], (u64)ltot ) ;
-			t4_atomic_add( &cx.g->counters[3], (u64)total ) ;
-			t4_atomic_add( &cx.g->counters[4], (u64)total ) ;
-			t4_atomic_add( &cx.g->counters[5], (u64)( ( len + 3 ) / 4 ) ) ;
+			t4_count( cx, 2, (u64)ltot ) ;
+			t4_count( cx, 3, (u64)total ) ;
+			t4_count( cx, 4, (u64)total ) ;
+			t4_count( cx, 5, (u64)( ( len + 3 ) / 4 ) ) ;
 		}
 	}
 	// sequential scan along the read: equal-to-previous rule with the stale prevKmerCode semantics and the
@@ -1503,10 +1518,10 @@ T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool al
 		}
 		sm->bi[0] = (int)total ;
 		sm->bi[1] = big ;
-		t4_atomic_add( &cx.g->counters[2], lookups ) ;
-		t4_atomic_add( &cx.g->counters[3], postings ) ;
-		t4_atomic_add( &cx.g->counters[4], (u64)total ) ;
-		t4_atomic_add( &cx.g->counters[5], (u64)( ( len + 3 ) / 4 ) ) ;
+		t4_count( cx, 2, lookups ) ;
+		t4_count( cx, 3, postings ) ;
+		t4_count( cx, 4, (u64)total ) ;
+		t4_count( cx, 5, (u64)( ( len + 3 ) / 4 ) ) ;
 	}
 	T4_SYNC() ;
 	u32 H = (u32)sm->bi[0] ;
@@ -1974,8 +1989,8 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 	}
 #endif
 	if ( fullDps )
-		t4_atomic_add( &cx.g->counters[7], fullDps ) ;
-	t4_atomic_add( &cx.g->counters[6], cx.tid == 0 ? (u64)overlapCnt : 0 ) ;
+		t4_count( cx, 7, fullDps ) ;
+	t4_count( cx, 6, cx.tid == 0 ? (u64)overlapCnt : 0 ) ;
 	T4_SYNC() ;
 	// sequential replay of the loop's bookkeeping: infoFromHits, bestNovelOverlap pre-filters (only when
 	// overlapCnt > 50), final similarity filter (SeqSet.hpp:1673-1794, 2024-2118)
@@ -2202,13 +2217,13 @@ T4_D inline int t4_extend_overlap( T4Ctx &cx, const char *r, int len, T4Contig *
 		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqStart - leftOverhangSize ), r + overlap.readStart - leftOverhangSize,
 			leftOverhangSize, lbits, ds ) ;
 		if ( av.dp )
-			t4_atomic_add( &cx.g->counters[1], 1 ) ;
+			t4_count( cx, 1, 1 ) ;
 		ls = t4_side_stats( av, true ) ;
 	}
 	{
 		T4AlignView av = t4_overhang_align( pw + 4 * ( overlap.seqEnd + 1 ), r + overlap.readEnd + 1, rightOverhangSize, rbits, ds ) ;
 		if ( av.dp )
-			t4_atomic_add( &cx.g->counters[1], 1 ) ;
+			t4_count( cx, 1, 1 ) ;
 		rs = t4_side_stats( av, false ) ;
 	}
 	return t4_extend_finish( cx, len, seq, mismatchThresholdFactor, overlap, ext, ls, rs ) ;
@@ -2459,7 +2474,7 @@ T4_D inline void c_extend_all_warp( T4Ctx &cx, const char *r, int len, double fa
 				alR = bufR + acap - 1 - lenR ;
 			}
 			if ( lane == 0 )
-				t4_atomic_add( &cx.g->counters[1], (u64)( ( dpL ? 1 : 0 ) + ( dpR ? 1 : 0 ) ) ) ;
+				t4_count( cx, 1, (u64)( ( dpL ? 1 : 0 ) + ( dpR ? 1 : 0 ) ) ) ;
 			(void)ds ;
 		}
 		long long tc2 = clock64() ;
@@ -2475,10 +2490,10 @@ T4_D inline void c_extend_all_warp( T4Ctx &cx, const char *r, int len, double fa
 			e.infoFromHits = ok ;
 			pre[i] = e ;
 			long long tc3 = clock64() ;
-			t4_atomic_add( &cx.g->counters[17], (u64)( tc1 - tc0 ) ) ;
-			t4_atomic_add( &cx.g->counters[18], (u64)( tc2 - tc1 ) ) ;
-			t4_atomic_add( &cx.g->counters[19], (u64)( tc3 - tc2 ) ) ;
-			t4_atomic_add( &cx.g->counters[20], (u64)( ( dpL || dpR ) ? ( ( dpL ? L : 0 ) > ( dpR ? R : 0 ) ? ( dpL ? L : 0 ) : ( dpR ? R : 0 ) ) : 0 ) ) ;
+			t4_count( cx, 17, (u64)( tc1 - tc0 ) ) ;
+			t4_count( cx, 18, (u64)( tc2 - tc1 ) ) ;
+			t4_count( cx, 19, (u64)( tc3 - tc2 ) ) ;
+			t4_count( cx, 20, (u64)( ( dpL || dpR ) ? ( ( dpL ? L : 0 ) > ( dpR ? R : 0 ) ? ( dpL ? L : 0 ) : ( dpR ? R : 0 ) ) : 0 ) ) ;
 		}
 		__syncwarp() ;
 	}
@@ -2597,7 +2612,7 @@ T4_D inline void c_score_all_warp( T4Ctx &cx, T4Ovl *ovl, int overlapCnt, const 
 		__syncwarp() ;
 	}
 	if ( lane == 0 && fullDps )
-		t4_atomic_add( &cx.g->counters[7], fullDps ) ;
+		t4_count( cx, 7, fullDps ) ;
 }
 #endif
 
@@ -3030,7 +3045,7 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 	// ExtendOverlap is a pure function of (overlap, read, contig): evaluate it for every overlap up front
 	T4_PHASE( cx, 5 ) ;
 	if ( cx.tid == 0 )
-		t4_atomic_add( &cx.g->counters[16], (u64)overlapCnt ) ;
+		t4_count( cx, 16, (u64)overlapCnt ) ;
 	T4Ovl *pre = cx.P<T4Ovl>( st->extOff ) ;
 	{
 #if 0
@@ -3089,7 +3104,7 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 				av = t4_overhang_align( pw + 4 * ( o.seqEnd + 1 ), r + o.readEnd + 1, R, bits + 32 * i + 16, ds ) ;
 			}
 			if ( av.dp )
-				t4_atomic_add( &cx.g->counters[1], 1 ) ;
+				t4_count( cx, 1, 1 ) ;
 			sstats[x] = t4_side_stats( av, !right ) ;
 		}
 		T4_SYNC() ;
@@ -3961,7 +3976,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 	{
 		st->assembledReadCnt = assembledReadCnt ;
 		st->prevAddRet = prevAddRet ;
-		t4_atomic_add( &cx.g->counters[0], (u64)n ) ;
+		t4_count( cx, 0, (u64)n ) ;
 	}
 	T4_SYNC() ;
 }
@@ -4055,7 +4070,7 @@ T4_D inline void c_probe_only( T4Ctx &cx, T4Op *op )
 		c_get_hits( cx, d.len, d.strand_in, d.barcode, false, &anyBig ) ;
 	}
 	if ( cx.tid == 0 )
-		t4_atomic_add( &cx.g->counters[0], (u64)op->n ) ;
+		t4_count( cx, 0, (u64)op->n ) ;
 }
 
 // ---------------------------------------------------------------------------
@@ -4071,6 +4086,9 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			op->ret = st->error ;
 		return ;
 	}
+	if ( cx.tid == 0 )
+		for ( int i = 0 ; i < T4_N_COUNTERS ; ++i )
+			sm->ctr[i] = 0 ;
 #if T4_CUDA
 	if ( cx.tid == 0 )
 	{
@@ -4079,8 +4097,8 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		sm->phCur = 0 ;
 		sm->phLast = clock64() ;
 	}
-	T4_SYNC() ;
 #endif
+	T4_SYNC() ;
 	switch ( op->op )
 	{
 		case T4_OP_RUN_LOOP:
@@ -4219,6 +4237,11 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 	T4_SYNC() ;
 	if ( cx.tid == 0 && st->error && op->ret >= T4_E_BASE )
 		op->ret = st->error ;
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+		for ( int i = 0 ; i < T4_N_COUNTERS ; ++i )
+			if ( ( i < 8 || i >= 16 ) && sm->ctr[i] )
+				t4_atomic_add( &cx.g->counters[i], sm->ctr[i] ) ;
 #if T4_CUDA
 	T4_PHASE( cx, 0 ) ;
 	if ( cx.tid == 0 )
