@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="CPU time budget of one reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
-    ap.add_argument("--contiguous", action="store_true", help="contiguous shards instead of dealing runs round-robin")
+    ap.add_argument("--deal", action="store_true", help="deal runs of identical reads round-robin to the streams instead of contiguous shards")
     return ap.parse_args()
 
 
@@ -61,7 +61,7 @@ def make_workload(args, rank, device):
     cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
     rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
     w = synth.build_workload(cl, rd, device=device)
-    off, descs = synth.shard_workload(w, args.streams, deal=not args.contiguous)
+    off, descs = synth.shard_workload(w, args.streams, deal=args.deal)
     return w, off, descs
 
 
@@ -157,7 +157,7 @@ def main():
     cores = os.cpu_count() or 1
     config = {"workload": "configs[1]: %d synthetic 150bp PE pairs (%d reads) per GPU vs human_IMGT+C gene pool, k=9, "
                           "read-sharded into %d streams per GPU (runs of identical reads %s; one SeqSet each, per-shard parity, SURVEY.md 8e)"
-                          % (args.pairs, 2 * args.pairs, args.streams, "in contiguous blocks" if args.contiguous else "dealt round-robin"),
+                          % (args.pairs, 2 * args.pairs, args.streams, "dealt round-robin" if args.deal else "in contiguous blocks of the sorted list"),
               "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150,
               "l2": "inputs (>= 400 MB of reads + records, GBs of stream state) exceed the 126 MB L2",
               "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective; "

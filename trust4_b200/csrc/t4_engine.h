@@ -841,6 +841,32 @@ T4_D inline void c_ensure_ovl( T4Ctx &cx, u32 n )
 // Exclusive scan of one value per thread; returns this thread's offset and the total.
 T4_D inline u32 c_scan_threads( T4Ctx &cx, u32 v, u32 &total )
 {
+#if T4_CUDA
+	// warp shuffle scan + one shared-memory hop across warps (blockDim is a multiple of 32)
+	const int lane = cx.tid & 31, warp = cx.tid >> 5, nwarps = cx.nt >> 5 ;
+	u32 inc = v ;
+#pragma unroll
+	for ( int d = 1 ; d < 32 ; d <<= 1 )
+	{
+		u32 t = __shfl_up_sync( 0xffffffffu, inc, d ) ;
+		if ( lane >= d )
+			inc += t ;
+	}
+	T4_SYNC() ; // previous users of sm->scan are done
+	if ( lane == 31 )
+		cx.sm->scan[warp] = inc ;
+	T4_SYNC() ;
+	u32 base = 0, tot = 0 ;
+	for ( int w = 0 ; w < nwarps ; ++w )
+	{
+		u32 x = cx.sm->scan[w] ;
+		if ( w < warp )
+			base += x ;
+		tot += x ;
+	}
+	total = tot ;
+	return base + inc - v ;
+#else
 	T4_SYNC() ;
 	cx.sm->scan[cx.tid] = v ;
 	T4_SYNC() ;
@@ -858,6 +884,7 @@ T4_D inline u32 c_scan_threads( T4Ctx &cx, u32 v, u32 &total )
 	T4_SYNC() ;
 	total = cx.sm->scan[cx.nt] ;
 	return cx.sm->scan[cx.tid] ;
+#endif
 }
 
 // Sort n keys ascending.  Returns the buffer (a or b) holding the result.
@@ -2989,6 +3016,18 @@ T4_D inline int c_repeat_add_read( T4Ctx &cx, int len )
 	return st->prevSeqIdx ;
 }
 
+// exact ExtendOverlap of overlap i on demand (thread 0 of the decision loop)
+T4_D inline void s_make_exact( T4Ctx &cx, const char *r, int len, double factor, const T4Ovl *overlaps, T4Ovl *pre, int i )
+{
+	T4DpScratch ds = t4_dp_scratch( cx ) ;
+	const u32 *bits = cx.P<u32>( cx.st->bitsOff ) ;
+	T4Ovl e ;
+	int ok = t4_extend_overlap( cx, r, len, t4_seq( cx, overlaps[i].seqIdx ), factor, ds, overlaps[i], e, bits + 32 * i, bits + 32 * i + 16 ) ;
+	e.infoFromHits = ok ;
+	e.hcCnt = 2 ;
+	pre[i] = e ;
+}
+
 // ---------------------------------------------------------------------------
 // SeqSet::AddRead (SeqSet.hpp:3426-4473), novel-contig set.  Collective; reads cx.sm->read / rc.
 // ---------------------------------------------------------------------------
@@ -3083,37 +3122,121 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 			bits[x] = m ;
 		}
 		T4_SYNC() ;
-		// one thread per (overlap, side): the two overhang alignments of an overlap are independent
-		T4DpScratch ds = t4_dp_scratch( cx ) ;
+		// Lazy ExtendOverlap.  One thread per (overlap, side) settles the sides that need no DP (<= 1 column, or <= 2
+		// mismatches on the diagonal, AlignAlgo.hpp:59-103) from the bit masks.  An overlap whose sides are all settled gets
+		// its exact result now (state 2).  Otherwise the DP is deferred: the decision loop below asks for the exact result
+		// only when it really consults it (s_make_exact); and when the return value alone matters (the bridging loop,
+		// SeqSet.hpp:3736-3750) an overlap is skipped without any DP if ExtendOverlap provably returns 0 (state 1): with the
+		// total diagonal mismatch count M over the mismatch budget and density, either every deferred side aligns without
+		// indel (then its counts ARE the diagonal counts and the budget test fails) or some side has an indel (ret = 0).
 		T4SideStats *sstats = (T4SideStats *)cx.P<char>( st->failOff ) ; // scratch: 2 per overlap (failOff is unused until the decision)
 		T4_PAR_FOR( x, 2 * overlapCnt )
 		{
 			int i = x >> 1, right = x & 1 ;
 			const T4Ovl &o = overlaps[i] ;
 			T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
-			int *pw = t4_pw( cx, seq ) ;
-			T4AlignView av ;
-			if ( !right )
+			int n = right ? t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) : t4_min( o.readStart, o.seqStart ) ;
+			const u32 *bb = bits + 32 * i + ( right ? 16 : 0 ) ;
+			int matches = 0 ;
+			for ( int w = 0 ; w * 32 < n ; ++w )
 			{
-				int L = t4_min( o.readStart, o.seqStart ) ;
-				av = t4_overhang_align( pw + 4 * ( o.seqStart - L ), r + o.readStart - L, L, bits + 32 * i, ds ) ;
+				u32 v = bb[w] ;
+				if ( ( w + 1 ) * 32 > n )
+					v &= ( 1u << ( n - w * 32 ) ) - 1u ;
+#if T4_CUDA
+				matches += __popc( v ) ;
+#else
+				matches += __builtin_popcount( v ) ;
+#endif
+			}
+			T4SideStats ss ;
+			bool needDp = n >= 2 && ( SCORE_MATCH * matches + SCORE_MISMATCH * ( n - matches ) < n * SCORE_MATCH + 2 * SCORE_INDEL ) ;
+			if ( !needDp )
+			{
+				T4AlignView av ;
+				av.a = 0 ; av.bits = bb ; av.n = n ; av.dp = 0 ;
+				ss = t4_side_stats( av, !right ) ;
+				ss.ind = 0 ;
 			}
 			else
 			{
-				int R = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
-				av = t4_overhang_align( pw + 4 * ( o.seqEnd + 1 ), r + o.readEnd + 1, R, bits + 32 * i + 16, ds ) ;
+				ss.m = matches ;
+				ss.x = n - matches ;
+				ss.ind = -1 ; // deferred
+				ss.good = 0 ;
 			}
-			if ( av.dp )
-				t4_count( cx, 1, 1 ) ;
-			sstats[x] = t4_side_stats( av, !right ) ;
+			sstats[x] = ss ;
 		}
 		T4_SYNC() ;
 		T4_PAR_FOR( i, overlapCnt )
 		{
-			T4Ovl e ;
-			int ok = t4_extend_finish( cx, len, t4_seq( cx, overlaps[i].seqIdx ), factor, overlaps[i], e, sstats[2 * i], sstats[2 * i + 1] ) ;
-			e.infoFromHits = ok ; // aux: the return value
+			const T4SideStats ls = sstats[2 * i], rs = sstats[2 * i + 1] ;
+			T4Ovl e = overlaps[i] ;
+			T4Contig *seq = t4_seq( cx, overlaps[i].seqIdx ) ;
+			if ( ls.ind == 0 && rs.ind == 0 )
+			{
+				int ok = t4_extend_finish( cx, len, seq, factor, overlaps[i], e, ls, rs ) ;
+				e.infoFromHits = ok ; // aux: the return value
+				e.hcCnt = 2 ;         // aux: exact
+			}
+			else
+			{
+				int L = t4_min( overlaps[i].readStart, overlaps[i].seqStart ) ;
+				int R = t4_min( len - 1 - overlaps[i].readEnd, seq->len - 1 - overlaps[i].seqEnd ) ;
+				int M = ls.x + rs.x ;
+				int thr = 2 + ( L >= 2 ? 1 : 0 ) + ( R >= 2 ? 1 : 0 ) ;
+				thr = (int)( thr * factor ) ;
+				bool surely0 = ( M > thr ) && ( (double)M / ( L + R ) > 1.5 / st->kmerLength ) ;
+				e.infoFromHits = 0 ;
+				e.hcCnt = surely0 ? 1 : 0 ;
+			}
 			pre[i] = e ;
+		}
+		T4_SYNC() ;
+		// Easy read: the best overlap is settled, extends, clears the threshold and covers the whole read.  The
+		// decision loop then consults the other overlaps (almost) only through the bridging loop, where state 1 suffices,
+		// and stragglers are made exact on demand.  Any other read: finish every deferred overlap now, one thread per
+		// (overlap, side) -- the decision loop may need many exact results and they must not serialise on thread 0.
+		bool easy = ( pre[0].hcCnt == 2 && pre[0].infoFromHits == 1 && pre[0].similarity >= similarityThreshold
+			&& pre[0].readStart == 0 && pre[0].readEnd == len - 1 ) ;
+		T4_SYNC() ;
+		if ( !easy )
+		{
+			T4DpScratch ds = t4_dp_scratch( cx ) ;
+			T4_PAR_FOR( x, 2 * overlapCnt )
+			{
+				int i = x >> 1, right = x & 1 ;
+				if ( sstats[x].ind != -1 )
+					continue ;
+				const T4Ovl &o = overlaps[i] ;
+				T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+				int *pw = t4_pw( cx, seq ) ;
+				T4AlignView av ;
+				if ( !right )
+				{
+					int L = t4_min( o.readStart, o.seqStart ) ;
+					av = t4_overhang_align( pw + 4 * ( o.seqStart - L ), r + o.readStart - L, L, bits + 32 * i, ds ) ;
+				}
+				else
+				{
+					int R = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
+					av = t4_overhang_align( pw + 4 * ( o.seqEnd + 1 ), r + o.readEnd + 1, R, bits + 32 * i + 16, ds ) ;
+				}
+				if ( av.dp )
+					t4_count( cx, 1, 1 ) ;
+				sstats[x] = t4_side_stats( av, !right ) ;
+			}
+			T4_SYNC() ;
+			T4_PAR_FOR( i, overlapCnt )
+			{
+				if ( pre[i].hcCnt == 2 )
+					continue ;
+				T4Ovl e ;
+				int ok = t4_extend_finish( cx, len, t4_seq( cx, overlaps[i].seqIdx ), factor, overlaps[i], e, sstats[2 * i], sstats[2 * i + 1] ) ;
+				e.infoFromHits = ok ;
+				e.hcCnt = 2 ;
+				pre[i] = e ;
+			}
 		}
 #endif
 	}
@@ -3167,6 +3290,8 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 			}
 			if ( j < k )
 				continue ;
+			if ( pre[i].hcCnt != 2 )
+				s_make_exact( cx, r, len, factor, overlaps, pre, i ) ;
 			extendedOverlaps[k] = pre[i] ;
 			if ( pre[i].infoFromHits == 1 )
 			{
@@ -3249,6 +3374,10 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 			{
 				if ( tag == i )
 					continue ;
+				if ( pre[i].hcCnt == 1 )
+					continue ; // ExtendOverlap provably returns 0; only the return value is consulted here
+				if ( pre[i].hcCnt != 2 )
+					s_make_exact( cx, r, len, factor, overlaps, pre, i ) ;
 				extendedOverlaps[k] = pre[i] ;
 				if ( pre[i].infoFromHits == 1 )
 				{
