@@ -163,3 +163,65 @@ def check_dp(lib, ref, seed=5):
     for (tw, p), (sc, ed) in zip(cases, got):
         rs, re_ = ref.dp_pos_weight(tw, p)
         assert (sc, ed) == (rs, re_), (tw.tolist(), p, sc, rs, ed, re_)
+
+
+def check_big_repeats(lib, ref, n_copies=10050):
+    """A k-mer with more than 10000 postings: the `repeats > 10000` rules of GetOverlapsFromHits, including the
+    run-local `hits[k]` indexing slip (SeqSet.hpp:931-947), and the >=100-postings skip rule of GetHitsFromRead."""
+    lib.check(lib.reset())
+    rng = np.random.default_rng(77)
+    base = "".join("ACGT"[c] for c in rng.integers(0, 4, size=120))
+    other = "".join("ACGT"[c] for c in rng.integers(0, 4, size=150))
+    g = api.SeqSet(9, lib)
+    r = ref.RefSeqSet(9)
+    # many contigs that all carry the k-mers of `base`; each gets a unique tail so they stay distinct sequences
+    tails = ["".join("ACGT"[c] for c in rng.integers(0, 4, size=30)) for _ in range(64)]
+    reads = [base + tails[i % 64] for i in range(n_copies)]
+    for rd in reads:
+        r.input_novel_read("IGHV1-2*01", rd, 1, -1)
+        g.input_novel_read("IGHV1-2*01", rd, 1, -1)
+    assert g.size() == r.size() == n_copies
+    assert g.index_checksum() == r.index_checksum()
+    for q in (base[10:110] + other[:50], other[:60] + base[:90], base[:100], other):
+        for strand in (0, 1):
+            hr = canon_hits(r.get_hits(q, strand))
+            hg = g.get_hits(q, strand)
+            assert hr.shape == hg.shape and (hr == hg).all()
+            if q is not other:
+                assert hr[:, 4].max() > 10000      # the scenario really has a k-mer with > 10000 postings
+            n1, o1, s1 = r.get_overlaps(q, strand)
+            n2, o2, s2 = g.get_overlaps(q, strand)
+            assert n1 == n2, (n1, n2)
+            if n1 > 0:
+                assert (o1 == o2).all() and (s1 == s2).all()
+        assert g.add_read(q, "IGHV", 0, -1, 1, 0, 0.9) == r.add_read(q, "IGHV", 0, -1, 1, 0, 0.9)
+    assert g.index_checksum() == r.index_checksum()
+
+
+def check_barcode_mode(lib, ref, seed=31, n_barcodes=5):
+    """Barcode mode inside one stream (BASELINE configs[3] flavour): barcode-salted index keys
+    (KmerIndex.hpp:29-33), per-hit barcode filter and repeats = 1 (SeqSet.hpp:1394-1418), hitLenRequired 13,
+    ExtendOverlap mismatch factor 2.0, no periodic consensus update (main.cpp:1549-1560, 1862).
+    ReleaseFinishedBarcodeSeq is not part of this path (both sides skip it)."""
+    lib.check(lib.reset())
+    w = small_workload(seed, 20, 500)
+    d = w.descs.copy()
+    L = w.L
+    reads = w.pool.reshape(-1, L)
+    h = (reads.astype(np.int64) * np.arange(1, L + 1)).sum(axis=1)
+    d["barcode"] = (h % n_barcodes).astype(np.int32)
+    d["sim_threshold"] = 0.9
+    d["mate_idx"] = -1
+    cfg = synth.run_cfg(has_barcode=1)
+    g = api.SeqSet(9, lib)
+    r = ref.RefSeqSet(9)
+    for s in (g, r):
+        s.set_hit_len_required(13)
+    g.set_consider_barcode_in_hash(1)
+    ref.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
+    _, gret, gstr, gres = g.run_descs(cfg, d, w.pool, w.names)
+    _, rret, rstr, rres = r.run_descs(cfg, d, w.pool, w.names)
+    assert (gret == rret).all() and (gstr == rstr).all() and (gres == rres).all()
+    assert g.output() == r.output()
+    assert g.index_checksum() == r.index_checksum()
+    assert len(set(c["barcode"] for c in (g.get_contig(i) for i in range(g.size())) if c)) > 1

@@ -26,6 +26,8 @@ def lib():
         l.t4ref_set_novel_seq_similarity.argtypes = [C.c_void_p, C.c_double]
         l.t4ref_set_novel_seq_similarity.restype = C.c_double
         l.t4ref_size.argtypes = [C.c_void_p]
+        l.t4ref_set_consider_barcode_in_hash.argtypes = [C.c_void_p, C.c_int]
+        l.t4ref_reverse_complement_in_place.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         l.t4ref_kmer_length.argtypes = [C.c_void_p]
         l.t4ref_add_read.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_double]
         l.t4ref_repeat_add_read.argtypes = [C.c_void_p, C.c_char_p]

@@ -26,3 +26,11 @@ def test_emu_stage_parity(emu_lib, ref):
 
 def test_emu_dp(emu_lib, ref):
     pc.check_dp(emu_lib, ref)
+
+
+def test_emu_big_repeats(emu_lib, ref):
+    pc.check_big_repeats(emu_lib, ref)
+
+
+def test_emu_barcode_mode(emu_lib, ref):
+    pc.check_barcode_mode(emu_lib, ref)

@@ -74,3 +74,12 @@ def test_gpu_empty_and_short_inputs(gpu_lib, ref):
     # zero-length batch
     e = synth.READ_DESC
     assert g.run_descs(synth.run_cfg(), np.zeros(0, dtype=e), np.zeros(16, dtype=np.uint8), [])[0] == 0
+
+
+def test_gpu_big_repeats(gpu_lib, ref):
+    """k-mers with > 10000 postings (the `repeats` rules and their indexing slip, SeqSet.hpp:798-808, 871-887, 931-947)."""
+    pc.check_big_repeats(gpu_lib, ref)
+
+
+def test_gpu_barcode_mode(gpu_lib, ref):
+    pc.check_barcode_mode(gpu_lib, ref)

@@ -115,6 +115,8 @@ struct T4Stream            // one SeqSet (SeqSet.hpp:189-230 private members) + 
 	u64 keysAOff, keysBOff ;       // u64[hitCap] each
 	u64 grpOff, runOff ;           // u32[hitCap + 1]
 	u32 hitCap ;
+	u64 keysROff, keysR2Off ;      // u64[hitCapR]: the hits once more in SortHits order, only when a k-mer has > 10000 postings
+	u32 hitCapR ;
 	u64 posOff ;                   // per read position scratch, see T4Pos
 	u64 ovlOff, ovlTmpOff, extOff, failOff, anchorOff ;
 	u64 bitsOff ;                  // u32[ovlCap * 32]: IsBaseEqual bit masks of the overhangs (ExtendOverlap)

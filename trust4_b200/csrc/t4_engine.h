@@ -1910,11 +1910,40 @@ T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, boo
 		const u64 *keysR = 0 ;
 		if ( anyBig )
 		{
-			// rare: reproduce SortHits order (strand, idx, a, b) in a second array.  Not supported yet.
-			if ( cx.tid == 0 )
-				t4_raise( cx, T4_E_UNSUPPORTED, 3 ) ;
+			// Rare: some k-mer of the read has more than 10000 postings.  GetOverlapsFromHits then consults
+			// hits[x].repeats at positions x of the SortHits order (strand, idx, readOffset, offset) -- including the
+			// run-local indexing slip of SeqSet.hpp:931-947 -- so keep a second copy of the hits in that order.
+			if ( H > st->hitCapR )
+			{
+				if ( cx.tid == 0 )
+				{
+					u32 nc = st->hitCapR ? st->hitCapR : 4096 ;
+					while ( nc < H )
+						nc *= 2 ;
+					u64 x = s_alloc( cx, (u64)nc * 8 ) ;
+					u64 y = s_alloc( cx, (u64)nc * 8 ) ;
+					if ( x && y )
+					{
+						st->keysROff = x ;
+						st->keysR2Off = y ;
+						st->hitCapR = nc ;
+					}
+				}
+				T4_SYNC() ;
+				if ( st->error )
+					return 0 ;
+			}
+			u64 *ra = cx.P<u64>( st->keysROff ) ;
+			u64 *rb = cx.P<u64>( st->keysR2Off ) ;
+			for ( u32 i = cx.tid ; i < H ; i += cx.nt )
+			{
+				u64 kx = a[i] ;
+				if ( kx != T4_KEY_INVALID )
+					kx = ( kx & ( ~0ull << T4_KEY_IDX_SHIFT ) ) | ( (u64)t4_key_a( kx ) << 30 ) | ( (u64)t4_key_b( kx ) << 11 ) | ( kx & 1 ) ;
+				ra[i] = kx ;
+			}
 			T4_SYNC() ;
-			return 0 ;
+			keysR = c_sort_keys( cx, ra, rb, H ) ;
 		}
 		u64 *sorted = c_sort_keys( cx, a, b, H ) ;
 		// invalid keys (barcode filter) sorted to the end
