@@ -22,4 +22,5 @@ c = np.zeros(api.N_COUNTERS, dtype=np.uint64); lib.check(lib.last_counters(c.cty
 names = ["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"]
 nr = len(sub)
 print("ms", e0.elapsed_time(e1), "reads", nr, dict(zip(names, (c[8:16] / c[8:16].sum()).round(3))),
-      {"hits": c[4] / nr, "ovl_scored": c[6] / nr, "ovl_ext": c[16] / nr, "ext_dps": c[1] / nr, "gap_dps": c[7] / nr})
+      {"hits": c[4] / nr, "ovl_scored": c[6] / nr, "ovl_ext": c[16] / nr, "ext_dps": c[1] / nr, "gap_dps": c[7] / nr,
+       "ext_bits_cyc": c[17] / max(1, c[6] and nr), "ext_classify_cyc": c[18] / nr, "ext_dp_cyc": c[19] / nr, "easy_frac": c[20] / nr})

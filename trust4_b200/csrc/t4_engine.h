@@ -25,6 +25,7 @@
 #define T4_MAX_NT 128
 #define T4_IDX_CHUNK 256
 #define T4_WACT_WORDS 12
+#define T4_SMEM_SORT 2048
 #define T4_RADIX_BITS 4
 #define T4_RADIX (1 << T4_RADIX_BITS)
 #define T4_DP_BAND 5
@@ -43,6 +44,7 @@ struct T4Smem
 	char read[T4_DEV_MAX_READ + 8] ;
 	char rc[T4_DEV_MAX_READ + 8] ;
 	u32 radix[T4_RADIX * T4_MAX_NT] ;
+	u64 sortbuf[T4_SMEM_SORT] ;  // bitonic sort of up to T4_SMEM_SORT hit keys
 	u32 scan[T4_MAX_NT + 4] ;
 	u64 bu[4] ;
 	int bi[16] ;
@@ -896,11 +898,10 @@ T4_D inline u64 *c_sort_keys( T4Ctx &cx, u64 *a, u64 *b, u32 n )
 #else
 	if ( n <= 1 )
 		return a ;
-	if ( n <= T4_RADIX * T4_MAX_NT / 2 )
+	if ( n <= T4_SMEM_SORT )
 	{
-		// small inputs (the common case for sharded streams): bitonic sort entirely in shared memory,
-		// in the area the radix counters would use (u64[1024])
-		u64 *sk = (u64 *)cx.sm->radix ;
+		// small inputs (the common case for sharded streams): bitonic sort entirely in shared memory
+		u64 *sk = cx.sm->sortbuf ;
 		u32 np = 1 ;
 		while ( np < n )
 			np <<= 1 ;
@@ -948,58 +949,71 @@ T4_D inline u64 *c_sort_keys( T4Ctx &cx, u64 *a, u64 *b, u32 n )
 	atomicAnd( (unsigned long long *)&cx.sm->red[1], (unsigned long long)va ) ;
 	T4_SYNC() ;
 	u64 vary = cx.sm->red[0] ^ cx.sm->red[1] ;
-	u32 chunk = ( n + cx.nt - 1 ) / cx.nt ;
-	u32 lo = cx.tid * chunk ;
-	u32 hi = lo + chunk < n ? lo + chunk : n ;
-	if ( lo > n )
-		lo = n ;
+	// LSD radix sort, 8-bit digits, one contiguous chunk of keys per WARP.  Within a warp keys are taken 32 at a time
+	// in order; lanes with equal digits find each other with __match_any_sync and rank themselves by lane, so the
+	// scatter is stable.  Counters: digit-major, warp-minor (256 x nwarps) in the shared radix area.
+	const int lane = cx.tid & 31, warp = cx.tid >> 5, nwarps = cx.nt >> 5 ;
+	const u32 wchunk = ( ( n + nwarps - 1 ) / nwarps + 31 ) & ~31u ;
+	const u32 wlo = warp * wchunk < n ? warp * wchunk : n ;
+	const u32 whi = wlo + wchunk < n ? wlo + wchunk : n ;
+	const unsigned lt = ( 1u << lane ) - 1u ;
+	u32 *cnt = cx.sm->radix ; // [256][nwarps]
 	u64 *src = a, *dst = b ;
-	for ( int shift = 0 ; shift < 64 ; shift += T4_RADIX_BITS )
+	for ( int shift = 0 ; shift < 64 ; shift += 8 )
 	{
-		if ( ( ( vary >> shift ) & ( T4_RADIX - 1 ) ) == 0 )
+		if ( ( ( vary >> shift ) & 255 ) == 0 )
 			continue ;
-		u32 *cnt = cx.sm->radix ;
-		for ( int d = 0 ; d < T4_RADIX ; ++d )
-			cnt[d * cx.nt + cx.tid] = 0 ;
-		for ( u32 i = lo ; i < hi ; ++i )
-			++cnt[( ( src[i] >> shift ) & ( T4_RADIX - 1 ) ) * cx.nt + cx.tid] ;
+		for ( int x = cx.tid ; x < 256 * nwarps ; x += cx.nt )
+			cnt[x] = 0 ;
 		T4_SYNC() ;
-		// exclusive scan over (digit major, thread minor)
-		if ( cx.tid < T4_RADIX )
+		for ( u32 i0 = wlo ; i0 < whi ; i0 += 32 )
 		{
-			u32 s = 0 ;
-			for ( int t = 0 ; t < cx.nt ; ++t )
-				s += cnt[cx.tid * cx.nt + t] ;
-			cx.sm->scan[cx.tid] = s ;
+			u32 i = i0 + lane ;
+			bool have = i < whi ;
+			u32 d = have ? (u32)( ( src[i] >> shift ) & 255 ) : 256u + lane ; // idle lanes get private pseudo digits
+			unsigned peers = __match_any_sync( 0xffffffffu, d ) ;
+			if ( have && ( peers & lt ) == 0 )
+				cnt[d * nwarps + warp] += __popc( peers ) ;
+			__syncwarp() ;
 		}
 		T4_SYNC() ;
-		if ( cx.tid == 0 )
+		// exclusive scan of the 256 * nwarps counters (digit major): each thread takes a contiguous piece
 		{
-			u32 s = 0 ;
-			for ( int d = 0 ; d < T4_RADIX ; ++d )
+			const int total = 256 * nwarps ;
+			const int per = ( total + cx.nt - 1 ) / cx.nt ;
+			const int lo2 = cx.tid * per < total ? cx.tid * per : total ;
+			const int hi2 = lo2 + per < total ? lo2 + per : total ;
+			u32 sum = 0 ;
+			for ( int x = lo2 ; x < hi2 ; ++x )
+				sum += cnt[x] ;
+			u32 tot ;
+			u32 base = c_scan_threads( cx, sum, tot ) ;
+			for ( int x = lo2 ; x < hi2 ; ++x )
 			{
-				u32 x = cx.sm->scan[d] ;
-				cx.sm->scan[d] = s ;
-				s += x ;
+				u32 v = cnt[x] ;
+				cnt[x] = base ;
+				base += v ;
 			}
 		}
 		T4_SYNC() ;
-		if ( cx.tid < T4_RADIX )
+		for ( u32 i0 = wlo ; i0 < whi ; i0 += 32 )
 		{
-			u32 s = cx.sm->scan[cx.tid] ;
-			for ( int t = 0 ; t < cx.nt ; ++t )
+			u32 i = i0 + lane ;
+			bool have = i < whi ;
+			u64 k = have ? src[i] : 0 ;
+			u32 d = have ? (u32)( ( k >> shift ) & 255 ) : 256u + lane ;
+			unsigned peers = __match_any_sync( 0xffffffffu, d ) ;
+			u32 pos = 0 ;
+			if ( have )
+				pos = cnt[d * nwarps + warp] + __popc( peers & lt ) ;
+			__syncwarp() ;
+			if ( have )
 			{
-				u32 x = cnt[cx.tid * cx.nt + t] ;
-				cnt[cx.tid * cx.nt + t] = s ;
-				s += x ;
+				dst[pos] = k ;
+				if ( ( peers & lt ) == 0 )
+					cnt[d * nwarps + warp] += __popc( peers ) ;
 			}
-		}
-		T4_SYNC() ;
-		for ( u32 i = lo ; i < hi ; ++i )
-		{
-			u64 k = src[i] ;
-			u32 d = ( k >> shift ) & ( T4_RADIX - 1 ) ;
-			dst[cnt[d * cx.nt + cx.tid]++] = k ;
+			__syncwarp() ;
 		}
 		T4_SYNC() ;
 		u64 *t = src ; src = dst ; dst = t ;
@@ -3120,7 +3134,65 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		c_extend_all_warp( cx, r, len, factor, overlaps, overlapCnt, pre ) ;
 #else
 		// IsBaseEqual of every overhang column, 32 positions per work item, spread over the CTA
+#if T4_CUDA
+		long long xt0 = clock64() ;
+#endif
 		u32 *bits = cx.P<u32>( st->bitsOff ) ;
+#if T4_CUDA
+		{
+			// one warp per overlap (metadata fetched once), then per 32-column word lane t loads column t
+			// (one coalesced 512-byte request) and a ballot forms the word
+			const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31 ;
+			for ( int oi = warp ; oi < overlapCnt ; oi += nwarps )
+			{
+				const T4Ovl o = overlaps[oi] ;
+				T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+				const int seqLen = seq->len ;
+				const int4 *pw4 = (const int4 *)t4_pw( cx, seq ) ;
+				for ( int right = 0 ; right < 2 ; ++right )
+				{
+					int n, col0, rp0 ;
+					if ( !right )
+					{
+						n = t4_min( o.readStart, o.seqStart ) ;
+						col0 = o.seqStart - n ;
+						rp0 = o.readStart - n ;
+					}
+					else
+					{
+						n = t4_min( len - 1 - o.readEnd, seqLen - 1 - o.seqEnd ) ;
+						col0 = o.seqEnd + 1 ;
+						rp0 = o.readEnd + 1 ;
+					}
+					u32 *out = bits + 32 * oi + 16 * right ;
+					for ( int w = 0 ; w < 16 ; ++w )
+					{
+						if ( w * 32 >= n )
+						{
+							if ( lane == 0 )
+								out[w] = 0 ;
+							continue ;
+						}
+						int t = w * 32 + lane ;
+						bool eq = false ;
+						if ( t < n )
+						{
+							const int4 wv = pw4[col0 + t] ;
+							char pc = r[rp0 + t] ;
+							int c = t4_nuc( pc ) ;
+							int sum = wv.x + wv.y + wv.z + wv.w ;
+							int wc = c == 0 ? wv.x : ( c == 1 ? wv.y : ( c == 2 ? wv.z : wv.w ) ) ;
+							eq = ( sum == 0 || pc == 'N' || sum < 3 * wc ) ;
+						}
+						unsigned m = __ballot_sync( 0xffffffffu, eq ) ;
+						if ( lane == 0 )
+							out[w] = m ;
+					}
+				}
+			}
+		}
+		T4_SYNC() ;
+#else
 		T4_PAR_FOR( x, overlapCnt * 32 )
 		{
 			int oi = x >> 5, w = x & 15, right = ( x >> 4 ) & 1 ;
@@ -3151,6 +3223,10 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 			bits[x] = m ;
 		}
 		T4_SYNC() ;
+#endif
+#if T4_CUDA
+		long long xt1 = clock64() ;
+#endif
 		// Lazy ExtendOverlap.  One thread per (overlap, side) settles the sides that need no DP (<= 1 column, or <= 2
 		// mismatches on the diagonal, AlignAlgo.hpp:59-103) from the bit masks.  An overlap whose sides are all settled gets
 		// its exact result now (state 2).  Otherwise the DP is deferred: the decision loop below asks for the exact result
@@ -3226,6 +3302,9 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		// decision loop then consults the other overlaps (almost) only through the bridging loop, where state 1 suffices,
 		// and stragglers are made exact on demand.  Any other read: finish every deferred overlap now, one thread per
 		// (overlap, side) -- the decision loop may need many exact results and they must not serialise on thread 0.
+#if T4_CUDA
+		long long xt2 = clock64() ;
+#endif
 		bool easy = ( pre[0].hcCnt == 2 && pre[0].infoFromHits == 1 && pre[0].similarity >= similarityThreshold
 			&& pre[0].readStart == 0 && pre[0].readEnd == len - 1 ) ;
 		T4_SYNC() ;
@@ -3267,6 +3346,17 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 				pre[i] = e ;
 			}
 		}
+#if T4_CUDA
+		T4_SYNC() ;
+		if ( cx.tid == 0 )
+		{
+			long long xt3 = clock64() ;
+			t4_count( cx, 17, (u64)( xt1 - xt0 ) ) ;
+			t4_count( cx, 18, (u64)( xt2 - xt1 ) ) ;
+			t4_count( cx, 19, (u64)( xt3 - xt2 ) ) ;
+			t4_count( cx, 20, easy ? 1 : 0 ) ;
+		}
+#endif
 #endif
 	}
 	T4_SYNC() ;
