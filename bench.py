@@ -317,9 +317,21 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # DRAM traffic of this kernel from the committed ncu --set full capture of the default workload (profiles/)
+    traffic = None
+    try:
+        if args.pairs == 1000000 and args.streams == 4096 and not args.deal:
+            import csv
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_stream_kernel_full_raw.csv"))))
+            hdr, units, vals = rows[0], rows[1], rows[2]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            traffic = sum(float(vals[hdr.index(m)]) * scale[units[hdr.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        traffic = None
     ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "t4_stream_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                "traffic": traffic, "traffic_source": "profiles/r1_stream_kernel_full_raw.csv (ncu --set full, same workload)" if traffic else None,
+                "algorithmic_bytes_total": alg_bytes, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes": {"probe": b_probe, "chain": b_chain, "commit": b_commit},
                 "per_read": {"lookups": dc[2] / n_reads, "hits": dc[4] / n_reads, "overlaps_scored": dc[6] / n_reads, "gap_dps": dc[7] / n_reads,
                              "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads,

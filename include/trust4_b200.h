@@ -209,7 +209,8 @@ int64_t t4_seqset_index_checksum(t4_seqset *s, uint64_t *checksum);
  * [0] reads processed, [1] overhang DPs (ExtendOverlap), [2] k-mer lookups executed, [3] postings read (sum c_j),
  * [4] hits emitted (sum c_j'), [5] packed read bytes ceil(L/4), [6] overlaps scored, [7] gap DPs,
  * [8..15] clock cycles per phase: other, probe, hit sort, chains, scoring, ExtendOverlap, decide+commit,
- * InputNovelRead/RepeatAddRead/consensus; [16] overlaps extended; [17..23] reserved. */
+ * InputNovelRead/RepeatAddRead/consensus; [16] overlaps extended; [17..19] cycles inside ExtendOverlap (bit masks,
+ * classification, DPs), [20] reads taking the lazy ExtendOverlap path; [21..23] reserved. */
 #define T4_N_COUNTERS 24
 int t4_last_counters(uint64_t *counters /* T4_N_COUNTERS */);
 

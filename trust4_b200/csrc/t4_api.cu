@@ -1434,10 +1434,20 @@ int T4_API( streams_cycles )( t4_seqset *const *sets, int n_sets, uint64_t *cycl
 // first device-side error among the given streams (0 if none)
 int T4_API( streams_error )( t4_seqset *const *sets, int n_sets )
 {
+	// fast path: one word in the arena header says whether any stream raised an error since the last reset
+	if ( !E.up )
+		return T4_E_INVAL ;
+	int r = dsync() ;
+	if ( r ) return r ;
+	u64 fe = 0 ;
+	r = d2h( &fe, E.A + offsetof( T4Global, firstError ), sizeof( u64 ) ) ;
+	if ( r ) return r ;
+	if ( fe == 0 )
+		return 0 ;
 	for ( int j = 0 ; j < n_sets ; ++j )
 	{
 		T4Stream st ;
-		int r = get_stream( sets[j], &st ) ;
+		r = get_stream( sets[j], &st ) ;
 		if ( r ) return r ;
 		if ( st.error )
 		{

@@ -49,7 +49,8 @@ struct T4Global            // arena header at offset 0
 	u64 top ;              // bump pointer (bytes), device-side atomicAdd
 	u64 cap ;
 	u64 counters[T4_N_COUNTERS] ;
-	u64 pad[6] ;
+	u64 firstError ;       // first T4_E_* raised by any stream since the last reset: (u32)code | aux << 32; 0 = none
+	u64 pad[5] ;
 } ;
 
 struct T4Dir               // one k-mer directory slot (32 B = one HBM sector); KmerIndex.hpp:20-116

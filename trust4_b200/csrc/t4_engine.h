@@ -25,7 +25,7 @@
 #define T4_MAX_NT 128
 #define T4_IDX_CHUNK 256
 #define T4_WACT_WORDS 12
-#define T4_SMEM_SORT 2048
+#define T4_SMEM_SORT ( T4_RADIX * T4_MAX_NT / 2 )
 #define T4_RADIX_BITS 4
 #define T4_RADIX (1 << T4_RADIX_BITS)
 #define T4_DP_BAND 5
@@ -44,7 +44,6 @@ struct T4Smem
 	char read[T4_DEV_MAX_READ + 8] ;
 	char rc[T4_DEV_MAX_READ + 8] ;
 	u32 radix[T4_RADIX * T4_MAX_NT] ;
-	u64 sortbuf[T4_SMEM_SORT] ;  // bitonic sort of up to T4_SMEM_SORT hit keys
 	u32 scan[T4_MAX_NT + 4] ;
 	u64 bu[4] ;
 	int bi[16] ;
@@ -75,6 +74,19 @@ struct T4Ctx
 } ;
 
 #define T4_PAR_FOR( i, n ) for ( int i = cx.tid ; i < (int)( n ) ; i += cx.nt )
+
+T4_D inline u64 t4_atomic_cas( u64 *p, u64 cmp, u64 val ) ;
+
+T4_D inline void t4_raise( T4Ctx &cx, int code, int aux )
+{
+	if ( cx.st->error == 0 )
+	{
+		cx.st->error = code ;
+		cx.st->errorAux = aux ;
+	}
+	if ( cx.g->firstError == 0 )
+		t4_atomic_cas( &cx.g->firstError, 0ull, (u64)(u32)code | ( (u64)(u32)aux << 32 ) ) ;
+}
 
 T4_D inline void t4_count( T4Ctx &cx, int idx, u64 v )
 {
@@ -159,14 +171,7 @@ T4_D inline u32 t4_atomic_add32( u32 *p, u32 v )
 struct T4Ctx ;
 T4_D inline void t4_count( T4Ctx &cx, int idx, u64 v ) ;
 
-T4_D inline void t4_raise( T4Ctx &cx, int code, int aux )
-{
-	if ( cx.st->error == 0 )
-	{
-		cx.st->error = code ;
-		cx.st->errorAux = aux ;
-	}
-}
+T4_D inline void t4_raise( T4Ctx &cx, int code, int aux ) ;
 
 // Bump allocation from the arena; callable by any thread.  Returns 0 (and raises T4_E_NOMEM) when exhausted.
 // Small requests are served from a stream-local slab (refilled by thread 0 between reads, c_refill_slab) so
@@ -901,7 +906,7 @@ T4_D inline u64 *c_sort_keys( T4Ctx &cx, u64 *a, u64 *b, u32 n )
 	if ( n <= T4_SMEM_SORT )
 	{
 		// small inputs (the common case for sharded streams): bitonic sort entirely in shared memory
-		u64 *sk = cx.sm->sortbuf ;
+		u64 *sk = (u64 *)cx.sm->radix ; // the radix counter area doubles as the sort buffer (u64[1024])
 		u32 np = 1 ;
 		while ( np < n )
 			np <<= 1 ;
