@@ -166,7 +166,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        w, off, descs = make_workload(args, 0, None)
+        gen_dev = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                gen_dev = torch.device("cuda", local)      # workload preparation only (21-mer statistics); the arm itself is CPU
+        except Exception:
+            gen_dev = None
+        w, off, descs = make_workload(args, 0, gen_dev)
         per_step = max(2.0, min(args.ref_seconds, 150.0 / max(1, args.steps + args.warmup)))
         vals = []
         for it in range(args.warmup + args.steps):

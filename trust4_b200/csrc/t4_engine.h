@@ -2482,98 +2482,6 @@ T4_D inline signed char *t4_align_of_thread( T4Ctx &cx, int tid )
 		+ ( T4_DEV_MAX_READ + 1 ) * T4_DP_W + 8 ) ;
 }
 
-// number of matches among the first n bits
-T4_D inline int t4_bits_matches( const u32 *bits, int n )
-{
-	int m = 0 ;
-	for ( int w = 0 ; w * 32 < n ; ++w )
-	{
-		u32 x = bits[w] ;
-		if ( ( w + 1 ) * 32 > n )
-			x &= ( 1u << ( n - w * 32 ) ) - 1u ;
-		m += __popc( x ) ;
-	}
-	return m ;
-}
-
-// ExtendOverlap for every overlap: one warp per overlap (round robin), both overhang DPs at once in the two half warps.
-T4_D inline void c_extend_all_warp( T4Ctx &cx, const char *r, int len, double factor, const T4Ovl *overlaps, int overlapCnt,
-	T4Ovl *pre )
-{
-	T4Smem *sm = cx.sm ;
-	const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31 ;
-	for ( int i = warp ; i < overlapCnt ; i += nwarps )
-	{
-		long long tc0 = clock64() ;
-		const T4Ovl o = overlaps[i] ;
-		T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
-		const int *pw = t4_pw( cx, seq ) ;
-		const int L = t4_min( o.readStart, o.seqStart ) ;
-		const int R = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
-		u32 *lb = sm->wbits[warp][0], *rb = sm->wbits[warp][1] ;
-		const int *twL = pw + 4 * ( o.seqStart - L ), *twR = pw + 4 * ( o.seqEnd + 1 ) ;
-		const char *pL = r + o.readStart - L, *pR = r + o.readEnd + 1 ;
-		const int mL = w_stage_side( twL, pL, L, sm->wnib[warp][0], lb, lane ) ;
-		const int mR = w_stage_side( twR, pR, R, sm->wnib[warp][1], rb, lane ) ;
-		const bool dpL = L >= 2 && ( SCORE_MATCH * mL + SCORE_MISMATCH * ( L - mL ) < L * SCORE_MATCH + 2 * SCORE_INDEL ) ;
-		const bool dpR = R >= 2 && ( SCORE_MATCH * mR + SCORE_MISMATCH * ( R - mR ) < R * SCORE_MATCH + 2 * SCORE_INDEL ) ;
-		long long tc1 = clock64() ;
-		signed char *alL = 0, *alR = 0 ;
-		int lenL = L, lenR = R ;
-		if ( dpL || dpR )
-		{
-			const bool left = lane < 16 ;
-			int n = left ? ( dpL ? L : 0 ) : ( dpR ? R : 0 ) ;
-			int nOther = __shfl_xor_sync( T4_FULL, n, 16 ) ;
-			bool small = ( n < 16 * T4_WACT_WORDS ) && ( nOther < 16 * T4_WACT_WORDS ) ;
-			T4DpScratch ds = t4_dp_scratch( cx ) ;
-			// traceback words: shared memory when both sides fit, else this thread-group's global scratch
-			u32 *actBase = small ? sm->wact[warp][left ? 0 : 1] : (u32 *)t4_dp_scratch_of( cx, ( cx.tid & ~15 ) ).act ;
-			int actStride = small ? T4_WACT_WORDS : (int)( T4_DP_STRIDE / 4 ) ;
-			int al = 0 ;
-			signed char *abuf = small ? sm->wal[warp][left ? 0 : 1] : t4_align_of_thread( cx, cx.tid & ~15 ) ;
-			int acap = small ? (int)sizeof( sm->wal[0][0] ) : 2 * T4_DEV_MAX_READ + 8 ;
-			w_dp_equal_half( cx, sm->wnib[warp][left ? 0 : 1], left ? pL : pR, n, abuf, acap, &al, actBase, actStride ) ;
-			int alOther = __shfl_xor_sync( T4_FULL, al, 16 ) ;
-			// start of each side's edit string (every lane needs both pointers)
-			signed char *bufL = small ? sm->wal[warp][0] : t4_align_of_thread( cx, warp * 32 ) ;
-			signed char *bufR = small ? sm->wal[warp][1] : t4_align_of_thread( cx, warp * 32 + 16 ) ;
-			if ( dpL )
-			{
-				lenL = left ? al : alOther ;
-				alL = bufL + acap - 1 - lenL ;
-			}
-			if ( dpR )
-			{
-				lenR = left ? alOther : al ;
-				alR = bufR + acap - 1 - lenR ;
-			}
-			if ( lane == 0 )
-				t4_count( cx, 1, (u64)( ( dpL ? 1 : 0 ) + ( dpR ? 1 : 0 ) ) ) ;
-			(void)ds ;
-		}
-		long long tc2 = clock64() ;
-		T4AlignView vl, vr ;
-		vl.a = dpL ? alL : 0 ; vl.bits = lb ; vl.n = lenL ; vl.dp = dpL ;
-		vr.a = dpR ? alR : 0 ; vr.bits = rb ; vr.n = lenR ; vr.dp = dpR ;
-		T4SideStats ls = w_side_stats( vl, true, lane ) ;
-		T4SideStats rs = w_side_stats( vr, false, lane ) ;
-		if ( lane == 0 )
-		{
-			T4Ovl e ;
-			int ok = t4_extend_finish( cx, len, seq, factor, o, e, ls, rs ) ;
-			e.infoFromHits = ok ;
-			pre[i] = e ;
-			long long tc3 = clock64() ;
-			t4_count( cx, 17, (u64)( tc1 - tc0 ) ) ;
-			t4_count( cx, 18, (u64)( tc2 - tc1 ) ) ;
-			t4_count( cx, 19, (u64)( tc3 - tc2 ) ) ;
-			t4_count( cx, 20, (u64)( ( dpL || dpR ) ? ( ( dpL ? L : 0 ) > ( dpR ? R : 0 ) ? ( dpL ? L : 0 ) : ( dpR ? R : 0 ) ) : 0 ) ) ;
-		}
-		__syncwarp() ;
-	}
-}
-
 // Overlap scoring (SeqSet.hpp:1832-2020) for every overlap: one warp per overlap, lanes over consecutive hit pairs.
 // A failed overlap (gap over the limit, or an indel in a gap) gets similarity 0; its counts are unobservable.
 T4_D inline void c_score_all_warp( T4Ctx &cx, T4Ovl *ovl, int overlapCnt, const u64 *keys )
@@ -3135,9 +3043,7 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		t4_count( cx, 16, (u64)overlapCnt ) ;
 	T4Ovl *pre = cx.P<T4Ovl>( st->extOff ) ;
 	{
-#if 0
-		c_extend_all_warp( cx, r, len, factor, overlaps, overlapCnt, pre ) ;
-#else
+		{
 		// IsBaseEqual of every overhang column, 32 positions per work item, spread over the CTA
 #if T4_CUDA
 		long long xt0 = clock64() ;
@@ -3362,7 +3268,7 @@ T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 			t4_count( cx, 20, easy ? 1 : 0 ) ;
 		}
 #endif
-#endif
+		}
 	}
 	T4_SYNC() ;
 	T4_PHASE( cx, 6 ) ;
