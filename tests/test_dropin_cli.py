@@ -1,0 +1,75 @@
+"""The drop-in stage-1 binary: the UNMODIFIED reference main.cpp + integration/t4_seqset_adapter.hpp + this
+repository's C-ABI library must write the same _raw.out, _final.out and _assembled_reads.fa as the stock `trust4`
+(oracle/_ref/trust4) -- flags, file formats and `run-trust4 --stage 1` compatibility included.
+
+CPU variant: the binding linked against the test emulation of the engine (needs the reference sources to build).
+GPU variant: integration/_build/trust4_gpu, prebuilt by __graft_entry__.build() where the reference sources exist;
+both binaries run on the box itself on freshly generated synthetic FASTQ, so nothing under /root/reference is read."""
+import os
+import subprocess
+
+import pytest
+
+from trust4_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STOCK = os.path.join(ROOT, "oracle", "_ref", "trust4")
+REF = "/root/reference"
+SUFFIXES = ("_raw.out", "_final.out", "_assembled_reads.fa")
+
+
+def write_inputs(tmp, npairs=1500, nclones=40, seed=21):
+    pool = synth.load_gene_pool()
+    fa = os.path.join(tmp, "genes.fa")
+    with open(fa, "w") as f:
+        for ch in pool.values():
+            for seg in ch.values():
+                for name, seq in seg:
+                    f.write(">%s\n%s\n" % (name, seq))
+    cl = synth.make_clones(nclones, seed)
+    rd = synth.sample_pairs(cl, npairs, 150, seed)
+    synth.write_fastq(rd, os.path.join(tmp, "reads"))
+    return ["-f", fa, "-1", os.path.join(tmp, "reads_1.fq"), "-2", os.path.join(tmp, "reads_2.fq")]
+
+
+def run_and_compare(binary, args, tmp, extra=()):
+    for exe, tag in ((STOCK, "stock"), (binary, "dropin")):
+        subprocess.run([exe, "-t", "1", "-o", os.path.join(tmp, tag)] + list(extra) + args, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    for suf in SUFFIXES:
+        a = open(os.path.join(tmp, "stock" + suf), "rb").read()
+        b = open(os.path.join(tmp, "dropin" + suf), "rb").read()
+        assert len(a) > 0 and a == b, suf
+
+
+@pytest.fixture(scope="module")
+def emu_binary(emu_lib):
+    if not os.path.exists(os.path.join(REF, "main.cpp")):
+        pytest.skip("reference sources not present (needed to compile main.cpp)")
+    if not os.path.exists(STOCK):
+        pytest.skip("oracle/_ref/trust4 not built")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "integration"), "_build/trust4_emu"], check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(ROOT, "integration", "_build", "trust4_emu")
+
+
+def test_dropin_emu_shipped_example(emu_binary, tmp_path):
+    """BASELINE.json configs[0]: example_1.fq + example_2.fq -f hg38_bcrtcr.fa, -t 1."""
+    args = ["-f", REF + "/hg38_bcrtcr.fa", "-1", REF + "/example/example_1.fq", "-2", REF + "/example/example_2.fq"]
+    run_and_compare(emu_binary, args, str(tmp_path))
+
+
+def test_dropin_emu_synthetic(emu_binary, tmp_path):
+    run_and_compare(emu_binary, write_inputs(str(tmp_path)), str(tmp_path))
+
+
+def test_dropin_emu_repseq_flags(emu_binary, tmp_path):
+    """run-trust4 --repseq expands to --trimLevel 2 --skipMateExtension (run-trust4:288-291): repetitiveData = true."""
+    run_and_compare(emu_binary, write_inputs(str(tmp_path), 800, 25, 22), str(tmp_path), extra=("--trimLevel", "2", "--skipMateExtension"))
+
+
+@pytest.mark.gpu
+def test_dropin_gpu_synthetic(tmp_path):
+    binary = os.path.join(ROOT, "integration", "_build", "trust4_gpu")
+    if not (os.path.exists(binary) and os.path.exists(STOCK)):
+        pytest.skip("prebuilt drop-in / stock binaries not present")
+    run_and_compare(binary, write_inputs(str(tmp_path)), str(tmp_path))
