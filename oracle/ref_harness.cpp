@@ -11,7 +11,7 @@
 // Besides the per-call wrappers, t4ref_run_descs() restates the stage-1 driver
 // loop rules (main.cpp:1583-1880, rescue pass 1897-1940) over t4_read_desc
 // records -- the oracle for the batch entry t4_seqset_add_reads_batch().  That
-// restatement is pinned against the stock binary by tests/test_oracle_pin.py
+// restatement is pinned against the stock binary by tests/test_oracle.py
 // (call-trace replay must reproduce trust4's own _raw.out byte for byte).
 #include <stdio.h>
 #include <stdlib.h>
@@ -291,6 +291,57 @@ int64_t t4ref_index_checksum( void *h, uint64_t *checksum )
 }
 
 int t4ref_nomatch_gap_limit( void *h ) { return ((SeqSet *)h)->nomatchGapLimit ; }
+
+// Merge oracle of SURVEY.md section 8e(2): the reference's own in-tree merge idiom (main.cpp:2288-2294) applied to the
+// concatenation of the shard contig sets in the given (rank, stream) order:
+//   merged.InputSeqSet( shard, false ) for every shard ; merged.ChangeKmerLength( 31 ) ; merged.RemoveRedundantSeq()
+// (SeqSet.hpp:3108, 4624, 4965: a contig that is a <= 1-mismatch substring of another one is dropped).
+// Returns a new SeqSet handle (free with t4ref_destroy); *removed receives the number of contigs dropped.
+void *t4ref_merge_sets( void *const *shards, int n, int kmerLength, int *removed )
+{
+	SeqSet *m = new SeqSet( kmerLength ) ;
+	for ( int i = 0 ; i < n ; ++i )
+		m->InputSeqSet( *(SeqSet *)shards[i], false ) ;
+	int before = 0 ;
+	for ( size_t i = 0 ; i < m->seqs.size() ; ++i )
+		if ( m->seqs[i].consensus != NULL )
+			++before ;
+	m->ChangeKmerLength( 31 ) ;
+	int after = m->RemoveRedundantSeq() ;
+	if ( removed )
+		*removed = before - after ;
+	return m ;
+}
+
+// Load one contig (consensus + posWeight + name) into a reference SeqSet: lets a test rebuild shard sets from the
+// packed buffers of t4_streams_pack_contigs and feed them to t4ref_merge_sets.
+int t4ref_input_contig( void *h, const char *name, const char *consensus, const int32_t *posWeight, int barcode, int numRead )
+{
+	SeqSet *s = (SeqSet *)h ;
+	int len = strlen( consensus ) ;
+	struct _seqWrapper ns ;
+	ns.name = strdup( name ) ;
+	ns.consensus = strdup( consensus ) ;
+	ns.consensusLen = len ;
+	ns.isRef = false ;
+	ns.minLeftExtAnchor = ns.minRightExtAnchor = 0 ;
+	ns.barcode = barcode ;
+	ns.numRead = numRead ;
+	ns.index = true ;
+	ns.posWeightCompressed = false ;
+	for ( int j = 0 ; j < 3 ; ++j )
+		ns.info[j].a = ns.info[j].b = ns.info[j].c = 0 ;
+	int idx = s->seqs.size() ;
+	s->seqs.push_back( ns ) ;
+	struct _seqWrapper &sw = s->seqs[idx] ;
+	sw.posWeight.ExpandTo( len ) ;
+	for ( int i = 0 ; i < len ; ++i )
+		for ( int k = 0 ; k < 4 ; ++k )
+			sw.posWeight[i].count[k] = posWeight[4 * i + k] ;
+	KmerCode kmerCode( s->kmerLength ) ;
+	s->seqIndex.BuildIndexFromRead( kmerCode, sw.consensus, len, idx, barcode ) ;
+	return idx ;
+}
 
 // ---- restated driver loop over read descriptors ---------------------------
 // Follows main.cpp:1583-1880 (main pass) and 1897-1940 (rescue pass).  The static

@@ -26,6 +26,9 @@ def lib():
         l.t4ref_set_novel_seq_similarity.argtypes = [C.c_void_p, C.c_double]
         l.t4ref_set_novel_seq_similarity.restype = C.c_double
         l.t4ref_size.argtypes = [C.c_void_p]
+        l.t4ref_merge_sets.restype = C.c_void_p
+        l.t4ref_merge_sets.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_int)]
+        l.t4ref_input_contig.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         l.t4ref_set_consider_barcode_in_hash.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_reverse_complement_in_place.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         l.t4ref_kmer_length.argtypes = [C.c_void_p]
@@ -57,9 +60,9 @@ def lib():
 class RefSeqSet:
     """The reference SeqSet (compiled from /root/reference) behind the same call names as trust4_b200.api.SeqSet."""
 
-    def __init__(self, k=9):
+    def __init__(self, k=9, handle=None):
         self.l = lib()
-        self.h = self.l.t4ref_create(k)
+        self.h = handle if handle is not None else self.l.t4ref_create(k)
 
     def close(self):
         if self.h:
@@ -176,3 +179,20 @@ def dp_pos_weight(tw, p):
             break
         e.append(int(v))
     return sc, e
+
+
+def merge_sets(shards, k=9):
+    """SURVEY.md 8e(2) merge oracle over reference SeqSets in (rank, stream) order -> (merged RefSeqSet, n removed)."""
+    arr = (C.c_void_p * len(shards))(*[s.h for s in shards])
+    removed = C.c_int()
+    h = lib().t4ref_merge_sets(arr, len(shards), k, C.byref(removed))
+    return RefSeqSet(k, handle=h), removed.value
+
+
+def set_from_contigs(contigs, k=9):
+    """Reference SeqSet holding the given contigs (dicts as produced by trust4_b200.dist.unpack_contigs)."""
+    s = RefSeqSet(k)
+    for c in contigs:
+        pw = np.ascontiguousarray(c["pos_weight"], dtype=np.int32)
+        lib().t4ref_input_contig(s.h, c["name"].encode(), c["consensus"].encode(), pw.ctypes.data, c["barcode"], c["num_read"])
+    return s

@@ -61,3 +61,34 @@ def test_two_rank_shard_and_allgather(emu_lib, ref):
         assert p.exitcode == 0
     res = sorted(q.get() for _ in range(2))
     assert res[0][1] == res[1][1] and res[0][1] > 0
+
+
+def test_merge_oracle_on_packed_contigs(emu_lib, ref):
+    """the merged multi-GPU output is DEFINED as the reference's in-tree merge idiom
+    (InputSeqSet + ChangeKmerLength(31) + RemoveRedundantSeq, main.cpp:2288-2294) over the concatenation of the shard
+    contig sets in rank order.  What every rank holds after the all-gather (packed contigs) is enough to run that
+    oracle: rebuilding the shard sets from the packed buffers gives the same merged set as merging the reference's
+    own shard SeqSets.  (The merge itself stays reference CPU code in round 1 -- a 'next' row.)"""
+    from trust4_b200 import api, synth, dist as tdist
+    emu_lib.check(emu_lib.reset())
+    cl = synth.make_clones(15, 8)
+    rd = synth.sample_pairs(cl, 500, 150, 8)
+    w = synth.build_workload(cl, rd)
+    S = 4
+    off, descs = synth.shard_workload(w, S)
+    cfg = synth.run_cfg()
+    sets = api.SeqSet.create_many(S, 9, emu_lib)
+    api.streams_run(sets, cfg, descs, off, w.pool, w.names, emu_lib)
+    buf, n = tdist.pack_contigs(emu_lib, sets)
+    contigs = tdist.unpack_contigs(buf)
+    assert len(contigs) == n
+    rebuilt = [ref.set_from_contigs([c for c in contigs if c["set"] == j]) for j in range(S)]
+    direct = []
+    for j in range(S):
+        r = ref.RefSeqSet(9)
+        r.run_descs(cfg, descs[int(off[j]):int(off[j + 1])].copy(), w.pool, w.names)
+        direct.append(r)
+    m1, removed1 = ref.merge_sets(rebuilt)
+    m2, removed2 = ref.merge_sets(direct)
+    assert m1.output() == m2.output() and removed1 == removed2
+    assert m1.size() == sum(1 for _ in contigs) - removed1 and removed1 >= 0
