@@ -119,7 +119,7 @@ def reference_sample(args, w, off, descs, budget_s, cores):
     cfg = synth.run_cfg()
     n_shards = len(off) - 1
     lock = threading.Lock()
-    state = {"next": 0, "reads": 0, "shards": 0}
+    state = {"next": 0, "reads": 0, "shards": 0, "codes": {}}
     t0 = time.perf_counter()
 
     def worker():
@@ -131,11 +131,13 @@ def reference_sample(args, w, off, descs, budget_s, cores):
                 state["next"] += 1
             lo, hi = int(off[j]), int(off[j + 1])
             r = rh.RefSeqSet(9)
-            r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)     # ctypes releases the GIL
+            out = r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)     # ctypes releases the GIL
             r.close()
             with lock:
                 state["reads"] += hi - lo
                 state["shards"] += 1
+                if len(state["codes"]) < 256:
+                    state["codes"][j] = (out[1], out[3])     # AddRead-loop and rescue return codes of this shard
 
     th = [threading.Thread(target=worker) for _ in range(cores)]
     for t in th:
@@ -143,6 +145,7 @@ def reference_sample(args, w, off, descs, budget_s, cores):
     for t in th:
         t.join()
     el = time.perf_counter() - t0
+    reference_sample.codes = state["codes"]
     return {"value": state["reads"] / el, "unit": "reads/s", "cores": cores, "kind": "reference",
             "sample": "first %d of %d read shards (%d reads) of the same workload, %.1f s wall on %d threads; "
                       "oracle/_ref/libt4ref.so = reference SeqSet::AddRead/RepeatAddRead/InputNovelRead driven by the "
@@ -377,13 +380,25 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = reference_sample(args, w, off, descs, args.ref_seconds, cores)
+        # the CPU baseline leg doubles as a full-scale spot check: the reference's return codes of the shards it
+        # processed must equal what the GPU produced for the same shards in the e2e leg
+        parity = None
+        try:
+            codes = getattr(reference_sample, "codes", {}) if cpu else {}
+            if codes:
+                gret, gres = ret.numpy(), resc.numpy()
+                okc = all((gret[int(off[j]):int(off[j + 1])] == c[0]).all() and (gres[int(off[j]):int(off[j + 1])] == c[1]).all()
+                          for j, c in codes.items())
+                parity = {"shards_checked": len(codes), "return_codes_equal_reference": bool(okc)}
+        except Exception as ex:      # never let the checker break the measurement
+            parity = {"error": str(ex)[:200]}
         line = {"metric": "reads/sec assembled (150bp PE)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": 2 * args.steps, "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
-                "assembled_reads": assembled, "reads_per_gpu": n_reads, "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
+                "assembled_reads": assembled, "reads_per_gpu": n_reads, "parity_spot_check": parity, "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
                 "threads_per_stream": int(os.environ.get("T4_NT", 128))}
         print(json.dumps(line))
     lib.workload_free(wl)
