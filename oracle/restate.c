@@ -227,3 +227,243 @@ int rs_has_motif(const char *read, int strand)
     free(aa);
     return ret;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SeqSet::GetHitsFromRead (SeqSet.hpp:1341-1501) + SortHits (SeqSet.hpp:1306), restated over a freshly built
+ * index of the given contigs (KmerIndex::BuildIndexFromRead per contig, idx = position in the array).
+ * Includes the equal-to-previous rule with its stale prevKmerCode (the `continue`s skip the update), the
+ * >= 100 postings skip rule (skipLimit = k/2, not for the first / last k-mer) and allowTotalSkip.
+ * Output: int32[5] per hit {idx, offset, readOffset, strand, repeats}, ordered by (strand, idx, readOffset, offset).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct { uint64_t code; int32_t idx, off; } rs_posting;
+typedef struct { int32_t idx, off, roff, strand, rep; } rs_hit;
+
+static int cmp_posting(const void *a, const void *b)
+{
+    const rs_posting *x = a, *y = b;
+    if (x->code != y->code) return x->code < y->code ? -1 : 1;
+    if (x->idx != y->idx) return x->idx < y->idx ? -1 : 1;
+    return x->off < y->off ? -1 : (x->off > y->off);
+}
+
+static int cmp_hit(const void *a, const void *b)
+{
+    const rs_hit *x = a, *y = b;
+    if (x->strand != y->strand) return x->strand < y->strand ? -1 : 1;
+    if (x->idx != y->idx) return x->idx < y->idx ? -1 : 1;
+    if (x->roff != y->roff) return x->roff < y->roff ? -1 : 1;
+    return x->off < y->off ? -1 : (x->off > y->off);
+}
+
+static void revcomp(char *rc, const char *s, int len) /* SeqSet.hpp:2616 */
+{
+    for (int i = 0; i < len; ++i) {
+        char c = s[len - 1 - i];
+        rc[i] = c == 'N' ? 'N' : "ACGT"[3 - nuc(c)];
+    }
+    rc[len] = 0;
+}
+
+int rs_get_hits(const char *const *contigs, int n_contigs, const char *read, int strand, int k, int allow_total_skip,
+                int32_t *out, int cap)
+{
+    /* index */
+    size_t total = 0;
+    for (int c = 0; c < n_contigs; ++c)
+        total += strlen(contigs[c]);
+    rs_posting *post = malloc(sizeof(rs_posting) * (total + 1));
+    int32_t *offs = malloc(sizeof(int32_t) * (total + 1));
+    uint64_t *codes = malloc(sizeof(uint64_t) * (total + 1));
+    size_t np = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        int len = (int)strlen(contigs[c]);
+        int m = rs_index_offsets(contigs[c], len, k, 0, offs, codes);
+        for (int i = 0; i < m; ++i) {
+            post[np].code = codes[i];
+            post[np].idx = c;
+            post[np].off = offs[i];
+            ++np;
+        }
+    }
+    qsort(post, np, sizeof(rs_posting), cmp_posting);
+
+    int len = (int)strlen(read);
+    char *rc = malloc(len + 1);
+    revcomp(rc, read, len);
+    uint64_t *rcodes = malloc(sizeof(uint64_t) * (len + 1));
+    unsigned char *rvalid = malloc(len + 1);
+    rs_hit *hits = NULL;
+    size_t nh = 0, hcap = 0;
+    uint64_t prev = 0;              /* KmerCode prevKmerCode(k): code 0; carried over from the forward to the reverse pass */
+    int skip_limit = k / 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        if ((pass == 0 && strand == -1) || (pass == 1 && strand == 1))
+            continue;
+        const char *r = pass ? rc : read;
+        rs_kmer_codes(r, len, k, rcodes, rvalid);
+        int skip_cnt = 0;
+        for (int i = k - 1; i < len; ++i) {
+            if (i == k - 1 || rcodes[i] != prev) {
+                /* KmerIndex::Search: postings of this code (none when the k-mer contains an N) */
+                size_t lo = 0, hi = np;
+                if (rvalid[i]) {
+                    while (lo < hi) { size_t mid = (lo + hi) / 2; if (post[mid].code < rcodes[i]) lo = mid + 1; else hi = mid; }
+                    hi = lo;
+                    while (hi < np && post[hi].code == rcodes[i]) ++hi;
+                } else
+                    lo = hi = 0;
+                int size = (int)(hi - lo);
+                if (size >= 100 && i != k - 1 && i != len - 1 && skip_cnt < skip_limit) {
+                    ++skip_cnt;
+                    continue;           /* NB: prev is NOT updated */
+                }
+                if (size >= 100 && allow_total_skip)
+                    continue;
+                skip_cnt = 0;
+                for (size_t j = lo; j < hi; ++j) {
+                    if (nh == hcap) { hcap = hcap ? 2 * hcap : 1024; hits = realloc(hits, hcap * sizeof(rs_hit)); }
+                    hits[nh].idx = post[j].idx;
+                    hits[nh].off = post[j].off;
+                    hits[nh].roff = i - k + 1;
+                    hits[nh].strand = pass ? -1 : 1;
+                    hits[nh].rep = size;
+                    ++nh;
+                }
+            }
+            prev = rcodes[i];
+        }
+    }
+    qsort(hits, nh, sizeof(rs_hit), cmp_hit);
+    for (size_t i = 0; i < nh && (int)i < cap; ++i) {
+        out[5 * i] = hits[i].idx;
+        out[5 * i + 1] = hits[i].off;
+        out[5 * i + 2] = hits[i].roff;
+        out[5 * i + 3] = hits[i].strand;
+        out[5 * i + 4] = hits[i].rep;
+    }
+    free(hits); free(post); free(offs); free(codes); free(rc); free(rcodes); free(rvalid);
+    return (int)nh;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SeqSet::GetOverlapsFromHits (SeqSet.hpp:763-1063) for a set of novel contigs (isRef false everywhere, so
+ * adjustRadius = 0 and LongestIncreasingSubsequence is the identity on a run of one diagonal), restated over the
+ * hit array produced by rs_get_hits (ordered by strand, idx, readOffset, offset = SortHits order).
+ * filter == 1 runs the candidate-count pre-pass including its `i = j ; ++i` group skipping (SeqSet.hpp:784-810).
+ * contig_lens is not needed: the novel-contig test `2 * hitLen < seqSpan` only uses the chain itself.
+ * Output: int32[8] per chain {seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, nHits}, in emission
+ * order (group order, then diagonal ascending).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct { int a, b, c; } rs_triple;
+
+static int cmp_triple(const void *x, const void *y)
+{
+    const rs_triple *p = x, *q = y;
+    if (p->c != q->c) return p->c < q->c ? -1 : 1;
+    if (p->b != q->b) return p->b < q->b ? -1 : 1;
+    return p->a < q->a ? -1 : (p->a > q->a);
+}
+
+int rs_get_chains(const int32_t *hits, int n_hits, int k, int hit_len_required, int filter, int32_t *out, int cap)
+{
+#define H_IDX(i) hits[5 * (i)]
+#define H_OFF(i) hits[5 * (i) + 1]
+#define H_ROFF(i) hits[5 * (i) + 2]
+#define H_STRAND(i) hits[5 * (i) + 3]
+#define H_REP(i) hits[5 * (i) + 4]
+    int novel_min[2] = {3, 3};
+    int remove_only_repeats[2] = {0, 0};
+    int i, j, x;
+    if (filter == 1) {
+        int possible[2] = {0, 0}, longest[2] = {0, 0};
+        for (i = 0; i < n_hits; ++i) {
+            int plus = (1 + H_STRAND(i)) / 2;
+            for (j = i + 1; j < n_hits; ++j)
+                if (H_STRAND(j) != H_STRAND(i) || H_IDX(j) != H_IDX(i))
+                    break;
+            if (j - i > novel_min[plus])
+                ++possible[plus];
+            if (j - i > longest[plus])
+                longest[plus] = j - i;
+            if (!remove_only_repeats[plus]) {
+                int cnt = 0;
+                for (x = i; x < j; ++x)
+                    if (H_REP(x) <= 10000)
+                        ++cnt;
+                if (cnt >= novel_min[plus])
+                    remove_only_repeats[plus] = 1;
+            }
+            i = j; /* and the for-loop adds one more */
+        }
+        for (i = 0; i <= 1; ++i) {
+            if (possible[i] > 100000) novel_min[i] = (int)(longest[i] * 0.75);
+            else if (possible[i] > 10000) novel_min[i] = longest[i] / 2;
+            else if (possible[i] > 1000) novel_min[i] = longest[i] / 3;
+            else if (possible[i] > 100) novel_min[i] = longest[i] / 4;
+        }
+    }
+    int n_out = 0;
+    rs_triple *t = malloc(sizeof(rs_triple) * (n_hits + 1));
+    for (i = 0; i < n_hits;) {
+        for (j = i + 1; j < n_hits; ++j)
+            if (H_STRAND(j) != H_STRAND(i) || H_IDX(j) != H_IDX(i))
+                break;
+        int plus = (1 + H_STRAND(i)) / 2;
+        int min_hit = novel_min[plus];
+        if (j - i < min_hit) { i = j; continue; }
+        if (remove_only_repeats[plus]) {
+            int has_unique = 0;
+            for (x = i; x < j; ++x)
+                if (H_REP(x) <= 10000) { has_unique = 1; break; }
+            if (!has_unique) { i = j; continue; }
+        }
+        for (x = i; x < j; ++x) {
+            t[x - i].a = H_ROFF(x);
+            t[x - i].b = H_OFF(x);
+            t[x - i].c = H_ROFF(x) - H_OFF(x);
+        }
+        qsort(t, j - i, sizeof(rs_triple), cmp_triple);
+        int s, e;
+        for (s = 0; s < j - i;) {
+            for (e = s + 1; e < j - i; ++e)
+                if (t[e].c != t[e - 1].c) /* adjustRadius 0 */
+                    break;
+            if (e - s < min_hit || (e - s) * k < hit_len_required) { s = e; continue; }
+            if (remove_only_repeats[plus]) {
+                int has_unique = 0;
+                for (x = s; x < e; ++x) /* the reference indexes hits[] with the run-local x here (SeqSet.hpp:934-941) */
+                    if (H_REP(x) <= 10000) { has_unique = 1; break; }
+                if (!has_unique) { s = e; continue; }
+            }
+            /* chain = the run; union length of its k-mers (identical on read and contig) */
+            int hit_len = 0;
+            for (x = s; x < e;) {
+                int y;
+                for (y = x + 1; y < e; ++y)
+                    if (t[y].a > t[y - 1].a + k - 1)
+                        break;
+                hit_len += t[y - 1].a - t[x].a + k;
+                x = y;
+            }
+            if (hit_len < hit_len_required) { s = e; continue; }
+            int seq_start = t[s].b, seq_end = t[e - 1].b + k - 1;
+            if (hit_len * 2 < seq_end - seq_start + 1) { s = e; continue; }
+            if (n_out < cap) {
+                int32_t *o = out + 8 * n_out;
+                o[0] = H_IDX(i);
+                o[1] = t[s].a;
+                o[2] = t[e - 1].a + k - 1;
+                o[3] = seq_start;
+                o[4] = seq_end;
+                o[5] = H_STRAND(i);
+                o[6] = 2 * hit_len;
+                o[7] = e - s;
+            }
+            ++n_out;
+            s = e;
+        }
+        i = j;
+    }
+    free(t);
+    return n_out;
+}
