@@ -369,6 +369,15 @@ int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, 
 	std::vector<char> goodCandidate( n, 0 ) ;
 	std::vector<int> info( n, -1 ) ;
 	std::vector<int> rescue ;
+	// cfg->reserved_ == 1: also purge finished barcodes like main.cpp:1575-1581, 1846-1859 (ReleaseFinishedBarcodeSeq with
+	// release_index = true, contigMinCov = 0, early_stop = true).  The engine has no such op: the call is memory management
+	// plus an early UpdateConsensus and is observationally a no-op on Output when the index is barcode-salted
+	// (tests/test_emu_parity.py::test_emu_barcode_release_is_unobservable).
+	std::map<int, int> barcodeTotalReadCount, barcodeReadCount ;
+	if ( cfg->has_barcode && cfg->reserved_ == 1 )
+		for ( i = 0 ; i < n ; ++i )
+			if ( descs[i].barcode != -1 )
+				++barcodeTotalReadCount[ descs[i].barcode ] ;
 	char *buf = (char *)malloc( T4_MAX_READ_LEN + 2 ) ;
 	for ( i = 0 ; i < n ; ++i )
 	{
@@ -450,6 +459,17 @@ int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, 
 					goodCandidate[ d.mate_idx ] = 1 ;
 					info[ d.mate_idx ] = i ;
 				}
+			}
+		}
+		if ( addRet >= 0 && cfg->has_barcode && cfg->reserved_ == 1 && d.barcode != -1 )
+		{
+			int barcode = d.barcode ;
+			++barcodeReadCount[barcode] ;
+			if ( barcodeReadCount[barcode] >= barcodeTotalReadCount[barcode] )
+			{
+				std::map<int, int> finishedBarcodes ;
+				finishedBarcodes[barcode] = barcodeTotalReadCount[barcode] ;
+				s->ReleaseFinishedBarcodeSeq( finishedBarcodes, true, 0, true ) ;
 			}
 		}
 		retCodes[i] = addRet ;

@@ -225,3 +225,47 @@ def check_barcode_mode(lib, ref, seed=31, n_barcodes=5):
     assert g.output() == r.output()
     assert g.index_checksum() == r.index_checksum()
     assert len(set(c["barcode"] for c in (g.get_contig(i) for i in range(g.size())) if c)) > 1
+
+
+def check_barcode_release_unobservable(lib, ref, seed=33):
+    """SeqSet::ReleaseFinishedBarcodeSeq (SeqSet.hpp:10815; driver main.cpp:1846-1859) frees a finished barcode's
+    contigs from the index and compresses their posWeight.  With a barcode-salted index and contigMinCov = 0 that is
+    memory management plus an early UpdateConsensus: the reference run WITH the call must print the same contigs as
+    the engine (which has no such op) -- and as the reference without it."""
+    lib.check(lib.reset())
+    cl = synth.make_clones(6, seed)
+    rd = synth.sample_pairs(cl, 400, 150, seed)
+    w = synth.build_workload(cl, rd)
+    d = w.descs.copy()
+    # barcode = clone-ish hash; sort by barcode first like main.cpp:1126 (CompReadWithBarcode), keeping the order inside
+    reads = w.pool.reshape(-1, w.L)
+    h = (reads.astype(np.int64) * np.arange(1, w.L + 1)).sum(axis=1) % 3
+    order = np.argsort(h, kind="stable")
+    d = d[order]
+    d["barcode"] = h[order].astype(np.int32)
+    d["mate_idx"] = -1
+    d["sim_threshold"] = 0.9
+    n = len(d)
+    same_prev = np.zeros(n, dtype=bool)
+    rs = reads[order]
+    same_prev[1:] = (rs[1:] == rs[:-1]).all(axis=1) & (d["barcode"][1:] == d["barcode"][:-1])
+    d["flags"] = np.where(same_prev, d["flags"] | synth.RD_DUP, d["flags"] & ~np.uint32(synth.RD_DUP))
+    d["eq_lo"] = np.arange(n)
+    d["eq_hi"] = np.arange(n) + 1
+    outs, sums = [], []
+    for release in (0, 1):
+        cfg = synth.run_cfg(has_barcode=1)
+        cfg["reserved_"] = release
+        r = ref.RefSeqSet(9)
+        r.set_hit_len_required(13)
+        ref.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
+        r.run_descs(cfg, d, w.pool, w.names)
+        outs.append(r.output())
+        sums.append(r.index_checksum()[0])
+    assert sums[1] < sums[0]            # the release really happened: postings of finished barcodes left the index
+    g = api.SeqSet(9, lib)
+    g.set_hit_len_required(13)
+    g.set_consider_barcode_in_hash(1)
+    g.run_descs(synth.run_cfg(has_barcode=1), d, w.pool, w.names)
+    assert outs[0] == outs[1] == g.output()
+    assert len(outs[0]) > 1000

@@ -34,3 +34,7 @@ def test_emu_big_repeats(emu_lib, ref):
 
 def test_emu_barcode_mode(emu_lib, ref):
     pc.check_barcode_mode(emu_lib, ref)
+
+
+def test_emu_barcode_release_is_unobservable(emu_lib, ref):
+    pc.check_barcode_release_unobservable(emu_lib, ref)
