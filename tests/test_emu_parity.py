@@ -38,3 +38,14 @@ def test_emu_barcode_mode(emu_lib, ref):
 
 def test_emu_barcode_release_is_unobservable(emu_lib, ref):
     pc.check_barcode_release_unobservable(emu_lib, ref)
+
+
+def test_emu_single_stream_at_scale(emu_lib, ref):
+    """One stream, 80 000 reads: thousands of contigs, ChangeKmerLength 9 -> 11 in mid-run (slot compaction + full
+    re-index), periodic UpdateAllConsensus, reads with more than 50 candidate overlaps (the order-dependent
+    bestNovelOverlap pre-filters, SeqSet.hpp:1705-1794), postings lists over the 100-entry skip rule.
+    (The same check on 300 000 reads / 10 019 contigs / 58 overlaps per read also passes -- 4.5 min, not part of the suite.)"""
+    from trust4_b200 import synth
+    cfg = synth.run_cfg(change_k_threshold=1500)
+    n = pc.check_batch_vs_ref(emu_lib, ref, 43, 1, nclones=3000, npairs=40000, cfg=cfg)
+    assert n > 70000
