@@ -397,7 +397,9 @@ def main():
                 "dtype": "int32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": (2 + (2 if world > 1 else 0)) * args.steps,   # init + stream kernel (+ pack-size + pack when N > 1) "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
+                # init + stream kernel (+ pack-size + pack when N > 1)
+                "gpu_launches": (2 + (2 if world > 1 else 0)) * args.steps,
+                "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
                 "assembled_reads": assembled, "reads_per_gpu": n_reads, "parity_spot_check": parity, "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
                 "threads_per_stream": int(os.environ.get("T4_NT", 128))}
         print(json.dumps(line))
