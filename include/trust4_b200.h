@@ -36,7 +36,7 @@ extern "C" {
 #define T4_E_NODEVICE (-21)    /* no CUDA device: there is NO CPU fallback */
 #define T4_E_INTERNAL (-22)    /* device-side invariant violated */
 
-#define T4_MAX_READ_LEN 1000
+#define T4_MAX_READ_LEN 512    /* device-side read length limit; longer reads return T4_E_UNSUPPORTED */
 
 typedef struct t4_seqset t4_seqset;
 
@@ -119,6 +119,13 @@ int t4_seqset_get_overlaps(t4_seqset *s, const char *read, int strand, int barco
 int t4_dp_pos_weight_batch(int n, const int32_t *t_weights, const int64_t *t_off, const char *p,
                            const int64_t *p_off, int8_t *align_out, const int64_t *align_off,
                            int32_t *score_out);
+
+/* The same alignment through the two routines the stream kernel actually runs for its equal-length problems
+ * (overhangs of ExtendOverlap, SeqSet.hpp:1165; same-diagonal gaps of GetOverlapsFromRead, SeqSet.hpp:1832-2006):
+ * variant 0 = per-thread register banded DP, variant 1 = half-warp anti-diagonal DP (no <=2-mismatch fast path:
+ * its caller settles those from popcounts).  Problem i spans columns/bases off[i]..off[i+1) of both inputs. */
+int t4_dp_hot_path_batch(int n, int variant, const int32_t *t_weights, const int64_t *off, const char *p,
+                         int8_t *align_out, const int64_t *align_off, int32_t *score_out);
 
 /* ---- batch / multi-stream entry (the throughput path) ------------------ */
 /* One element per iteration of the reference's AddRead loop (main.cpp:1583-1880):

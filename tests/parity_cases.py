@@ -165,6 +165,76 @@ def check_dp(lib, ref, seed=5):
         assert (sc, ed) == (rs, re_), (tw.tolist(), p, sc, rs, ed, re_)
 
 
+def dp_equal_cases(seed=11, n=260):
+    """Equal-length GlobalAlignment_PosWeight problems as the hot path poses them (overhangs, same-diagonal gaps):
+    clean, substitution bursts, frame shifts that an in-band gap pair can repair, N's, mixed-support columns,
+    lengths on both sides of the shared-memory limit of the half-warp DP (192)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.choice([2, 3, 7, 12, 13, 14, 30, 45, 64, 100, 150, 191, 192, 230, 300])) if i % 3 == 0 else int(rng.integers(2, 160))
+        t = rng.integers(0, 4, size=L)
+        p = list(t)
+        kind = int(rng.integers(0, 6))
+        if kind == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                p[int(rng.integers(L))] = int(rng.integers(4))
+        elif kind == 2:                      # > 2 substitutions: forces the banded DP, answer stays on the diagonal
+            for _ in range(int(rng.integers(3, 9))):
+                x = int(rng.integers(L))
+                p[x] = (p[x] + 1 + int(rng.integers(3))) % 4
+        elif kind == 3 and L > 12:           # delete d bases early, insert d later: a frame shift inside the band
+            d = int(rng.integers(1, 5))
+            x = int(rng.integers(1, L - d - 4))
+            del p[x:x + d]
+            y = int(rng.integers(x + 1, len(p)))
+            for _ in range(d):
+                p.insert(y, int(rng.integers(4)))
+        elif kind == 4:                      # unrelated
+            p = list(rng.integers(0, 4, size=L))
+        elif kind == 5:                      # N's + substitutions
+            for _ in range(int(rng.integers(1, 4))):
+                p[int(rng.integers(L))] = 4
+            for _ in range(int(rng.integers(0, 6))):
+                p[int(rng.integers(L))] = int(rng.integers(4))
+        assert len(p) == L
+        tw = np.zeros((L, 4), dtype=np.int32)
+        for j in range(L):
+            tw[j, t[j]] = int(rng.integers(1, 30))
+            if rng.random() < 0.3:
+                tw[j, int(rng.integers(4))] += int(rng.integers(0, 12))
+            if rng.random() < 0.03:
+                tw[j] = 0
+        out.append((tw, "".join("ACGTN"[c] for c in p)))
+    return out
+
+
+def _diag_mismatches(tw, p):
+    """Mismatches of the all-diagonal alignment under AlignAlgo::IsBaseEqual (AlignAlgo.hpp:49-55)."""
+    x = 0
+    for j, c in enumerate(p):
+        s = int(tw[j].sum())
+        if s == 0 or c == "N":
+            continue
+        if not s < 3 * int(tw[j, "ACGT".index(c)]):
+            x += 1
+    return x
+
+
+def check_dp_hot(lib, ref, seed, variant):
+    """The DP routines the stream kernel really runs, against AlignAlgo::GlobalAlignment_PosWeight (AlignAlgo.hpp:57-216):
+    score and edit string.  variant 0 = t4_dp_equal (has the reference's <= 2-mismatch fast path), variant 1 =
+    w_dp_equal_half (always the banded DP; its caller only invokes it beyond 2 mismatches, so only those cases count)."""
+    cases = dp_equal_cases(seed)
+    if variant == 1:
+        cases = [(tw, p) for tw, p in cases if _diag_mismatches(tw, p) > 2]
+        assert len(cases) > 40
+    got = api.dp_hot_path_batch(cases, variant, lib)
+    for (tw, p), (sc, ed) in zip(cases, got):
+        rs, re_ = ref.dp_pos_weight(tw, p)
+        assert (sc, ed) == (rs, re_), (variant, len(p), p, sc, rs, ed, re_)
+
+
 def check_big_repeats(lib, ref, n_copies=10050):
     """A k-mer with more than 10000 postings: the `repeats > 10000` rules of GetOverlapsFromHits, including the
     run-local `hits[k]` indexing slip (SeqSet.hpp:931-947), and the >=100-postings skip rule of GetHitsFromRead."""

@@ -26,6 +26,7 @@ def test_emu_stage_parity(emu_lib, ref):
 
 def test_emu_dp(emu_lib, ref):
     pc.check_dp(emu_lib, ref)
+    pc.check_dp_hot(emu_lib, ref, 11, 0)      # t4_dp_equal, the register DP of the hot path (host-compilable)
 
 
 def test_emu_big_repeats(emu_lib, ref):

@@ -43,6 +43,18 @@ def test_gpu_dp(gpu_lib, ref):
         pc.check_dp(gpu_lib, ref, seed)
 
 
+def test_gpu_dp_hot_path_register(gpu_lib, ref):
+    """t4_dp_equal -- the per-thread register banded DP ExtendOverlap runs -- score + edit string vs the reference."""
+    for seed in (11, 12):
+        pc.check_dp_hot(gpu_lib, ref, seed, 0)
+
+
+def test_gpu_dp_hot_path_half_warp(gpu_lib, ref):
+    """w_dp_equal_half -- the half-warp anti-diagonal DP of gap scoring -- score + edit string vs the reference."""
+    for seed in (11, 12):
+        pc.check_dp_hot(gpu_lib, ref, seed, 1)
+
+
 def test_gpu_change_kmer_length(gpu_lib, ref):
     """ChangeKmerLength (slot compaction + full re-index) in the middle of a stream."""
     gpu_lib.check(gpu_lib.reset())

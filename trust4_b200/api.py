@@ -28,7 +28,7 @@ EXPORTS = [
     "seqset_size", "seqset_kmer_length", "seqset_add_read", "seqset_repeat_add_read",
     "seqset_input_novel_read", "seqset_update_all_consensus", "seqset_change_kmer_length",
     "seqset_output", "seqset_output_mem", "free", "seqset_get_contig", "has_motif",
-    "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch",
+    "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch", "dp_hot_path_batch",
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
     "streams_run_resident", "workload_results", "last_counters", "probe_resident", "streams_error",
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
@@ -82,6 +82,7 @@ class Lib:
         f("seqset_get_hits", ci, [vp, cs, ci, ci, ci, vp, ci])
         f("seqset_get_overlaps", ci, [vp, cs, ci, ci, ci, vp, vp, ci])
         f("dp_pos_weight_batch", ci, [ci, vp, vp, vp, vp, vp, vp, vp])
+        f("dp_hot_path_batch", ci, [ci, ci, vp, vp, vp, vp, vp, vp])
         f("seqset_add_reads_batch", ci, [vp, vp, vp, ci, vp, C.c_size_t, C.POINTER(cs), ci, vp, vp, vp])
         f("streams_run", ci, [C.POINTER(vp), ci, vp, vp, vp, vp, C.c_size_t, C.POINTER(cs), ci, vp, vp, vp])
         f("workload_upload", vp, [vp, C.c_int64, vp, C.c_size_t, C.POINTER(cs), ci])
@@ -275,6 +276,35 @@ def dp_pos_weight_batch(problems, lib: Lib | None = None):
     score = np.zeros(n, dtype=np.int32)
     lib.check(lib.dp_pos_weight_batch(n, tw_all.ctypes.data, t_off.ctypes.data, p_all.ctypes.data, p_off.ctypes.data,
                                       align.ctypes.data, a_off.ctypes.data, score.ctypes.data))
+    out = []
+    for i in range(n):
+        e = []
+        for v in align[a_off[i]:a_off[i + 1]]:
+            if v == -1:
+                break
+            e.append(int(v))
+        out.append((int(score[i]), e))
+    return out
+
+
+def dp_hot_path_batch(problems, variant, lib: Lib | None = None):
+    """Equal-length problems through the hot-path DP routines (t4_dp_hot_path_batch).  Returns [(score, [edit ops])]."""
+    lib = lib or default_lib()
+    n = len(problems)
+    off = np.zeros(n + 1, dtype=np.int64)
+    a_off = np.zeros(n + 1, dtype=np.int64)
+    for i, (tw, p) in enumerate(problems):
+        assert len(tw) == len(p)
+        off[i + 1] = off[i] + len(p)
+        a_off[i + 1] = a_off[i] + 2 * len(p) + 2
+    tw_all = np.zeros((max(1, off[n]), 4), dtype=np.int32)
+    for i, (tw, p) in enumerate(problems):
+        tw_all[off[i]:off[i + 1]] = tw
+    p_all = np.frombuffer(("".join(p for _, p in problems) + "\0").encode(), dtype=np.uint8).copy()
+    align = np.zeros(a_off[n] + 16, dtype=np.int8)
+    score = np.zeros(n, dtype=np.int32)
+    lib.check(lib.dp_hot_path_batch(n, variant, tw_all.ctypes.data, off.ctypes.data, p_all.ctypes.data,
+                                    align.ctypes.data, a_off.ctypes.data, score.ctypes.data))
     out = []
     for i in range(n):
         e = []

@@ -112,6 +112,53 @@ __global__ void t4_dp_kernel( int n, const int *tw, const i64 *tOff, const char 
 		(unsigned char *)( s + 8 * W ), 0 ) ;
 }
 
+// Test entry for the two DP routines the stream kernel really runs (equal lengths: overhangs and same-diagonal gaps):
+// variant 0 = t4_dp_equal (register-resident banded DP, one thread per problem, ExtendOverlap),
+// variant 1 = w_stage_side + w_dp_equal_half (half-warp anti-diagonal DP over staged IsBaseEqual nibbles, gap scoring;
+//             it has no fast path: the caller only runs it when the diagonal has > 2 mismatches).
+// One warp per problem.  scratch: per problem 13 * actStride u32 traceback words + an edit-string buffer (large n).
+__global__ void t4_dp_hot_kernel( int n, int variant, const int *tw, const i64 *off, const char *p, signed char *align, const i64 *alignOff,
+	int *score, u32 *scratch, const i64 *scratchOff )
+{
+	__shared__ u32 nib[64] ;
+	__shared__ u32 bits[16] ;
+	__shared__ u32 act[2][13 * T4_WACT_WORDS] ;
+	__shared__ signed char wal[2][2 * 16 * T4_WACT_WORDS + 8] ;
+	int i = blockIdx.x ;
+	if ( i >= n )
+		return ;
+	const int len = (int)( off[i + 1] - off[i] ) ;
+	const int lane = threadIdx.x ;
+	const int *t = tw + 4 * off[i] ;
+	const char *pp = p + off[i] ;
+	signed char *out = align + alignOff[i] ;
+	if ( variant == 0 )
+	{
+		if ( lane == 0 )
+			score[i] = t4_dp_equal( t, pp, len, out, scratch + scratchOff[i], false, 0 ) ;
+		return ;
+	}
+	T4Ctx cx ;
+	cx.tid = lane ;
+	cx.nt = 32 ;
+	int matches = w_stage_side( t, pp, len, nib, bits, lane ) ;
+	(void)matches ;
+	const bool small = len < 16 * T4_WACT_WORDS ;
+	const int actStride = small ? T4_WACT_WORDS : ( len / 16 + 2 ) ;
+	u32 *actBase = small ? act[lane < 16 ? 0 : 1] : scratch + scratchOff[i] + ( lane < 16 ? 0 : 13 * actStride ) ;
+	const int acap = small ? (int)sizeof( wal[0] ) : 2 * len + 8 ;
+	signed char *abuf = small ? wal[lane < 16 ? 0 : 1] : (signed char *)( scratch + scratchOff[i] + 26 * actStride ) + ( lane < 16 ? 0 : acap ) ;
+	int alen = 0 ;
+	int sc = w_dp_equal_half( cx, nib, pp, lane < 16 ? len : 0, abuf, acap, &alen, actBase, actStride ) ;
+	alen = __shfl_sync( 0xffffffffu, alen, 0 ) ;
+	sc = __shfl_sync( 0xffffffffu, sc, 0 ) ;
+	signed char *buf0 = small ? wal[0] : (signed char *)( scratch + scratchOff[i] + 26 * actStride ) ;
+	for ( int x = lane ; x <= alen ; x += 32 )
+		out[x] = ( x == alen ) ? (signed char)-1 : buf0[acap - 1 - alen + x] ;
+	if ( lane == 0 )
+		score[i] = sc ;
+}
+
 __global__ void t4_pack_size_kernel( char *A, const u64 *streamOff, u64 *sizes, u64 *counts )
 {
 	if ( threadIdx.x != 0 )
@@ -156,6 +203,9 @@ __global__ void t4_pack_kernel( char *A, const u64 *streamOff, const u64 *outOff
 			rec[32 + k.len + x] = pw[x] ;
 		for ( int x = threadIdx.x ; x < k.nameLen ; x += blockDim.x )
 			rec[32 + 17 * k.len + x] = nm[x] ;
+		// tail padding of the 16-byte aligned record: defined bytes (the all-gathered buffers are compared bytewise)
+		for ( u64 x = 32ull + 17ull * k.len + k.nameLen + threadIdx.x ; x < rb ; x += blockDim.x )
+			rec[x] = 0 ;
 		o += rb ;
 	}
 }
@@ -363,11 +413,7 @@ int T4_API( shutdown )( void )
 	dsync() ;
 	dfree( E.A ) ;
 	if ( E.gapTable )
-#if T4_CUDA
 		dfree( E.gapTable ) ;
-#else
-		free( E.gapTable ) ;
-#endif
 	if ( E.stage )
 		dfree( E.stage ) ;
 	if ( E.wl )
@@ -408,12 +454,15 @@ int T4_API( init )( int device, size_t arena_bytes )
 	env = getenv( "T4_NT" ) ;
 	if ( env )
 		E.nt = atoi( env ) ;
-	if ( E.nt < 1 || E.nt > T4_MAX_NT || ( E.nt & ( E.nt - 1 ) ) )
+#if T4_CUDA
+	// the warp-collective sections (ballots with a full mask, per-warp shared arrays) need whole warps
+	if ( E.nt < 32 || E.nt > T4_MAX_NT || ( E.nt & ( E.nt - 1 ) ) )
 	{
-		set_err( "T4_NT must be a power of two <= 128" ) ;
+		set_err( "T4_NT must be 32, 64 or 128" ) ;
+		E.nt = 128 ;
 		return T4_E_INVAL ;
 	}
-#if !T4_CUDA
+#else
 	E.nt = 1 ;
 #endif
 	void *p = 0 ;
@@ -428,17 +477,25 @@ int T4_API( init )( int device, size_t arena_bytes )
 	g.top = ( sizeof( T4Global ) + 255 ) & ~255ull ;
 	g.cap = arena_bytes ;
 	r = h2d( E.A, &g, sizeof( g ) ) ;
-	if ( r )
-		return r ;
 	for ( int k = 0 ; k < 40 ; ++k )
 		E.hostGap[k] = ( k >= 2 && k <= 32 ) ? nomatch_gap_limit( k ) : 0 ;
-	r = dmalloc( &p, sizeof( E.hostGap ) ) ;
-	if ( r )
-		return r ;
+	p = 0 ;
+	if ( !r )
+		r = dmalloc( &p, sizeof( E.hostGap ) ) ;
 	E.gapTable = (int *)p ;
-	r = h2d( E.gapTable, E.hostGap, sizeof( E.hostGap ) ) ;
+	if ( !r )
+		r = h2d( E.gapTable, E.hostGap, sizeof( E.hostGap ) ) ;
 	if ( r )
+	{
+		// a failed init leaves nothing behind: the next t4_init() starts from scratch
+		if ( E.gapTable )
+			dfree( E.gapTable ) ;
+		dfree( E.A ) ;
+		E.gapTable = 0 ;
+		E.A = 0 ;
+		E.cap = 0 ;
 		return r ;
+	}
 	E.up = true ;
 	return 0 ;
 }
@@ -588,6 +645,12 @@ int T4_API( seqset_set_novel_seq_similarity )( t4_seqset *s, double v ) { return
 int T4_API( seqset_set_consider_barcode_in_hash )( t4_seqset *s, int on )
 {
 	int v = on ? 1 : 0 ;
+	// the barcode salt lives above the 2k code bits of the 64-bit directory key (t4_index_key): 32 barcode bits need 2k <= 31
+	if ( v && s && s->k > 15 )
+	{
+		set_err( "barcode-salted index needs k <= 15" ) ;
+		return T4_E_UNSUPPORTED ;
+	}
 	return put_field( s, offsetof( T4Stream, considerBarcode ), &v, sizeof( int ) ) ;
 }
 int T4_API( seqset_set_is_long )( t4_seqset *s, int on )
@@ -747,6 +810,17 @@ int T4_API( seqset_change_kmer_length )( t4_seqset *s, int kl )
 	if ( r ) return r ;
 	if ( kl < 2 || kl > 31 )
 		return T4_E_INVAL ;
+	if ( kl > 15 )
+	{
+		T4Stream st ;
+		r = get_stream( s, &st ) ;
+		if ( r ) return r ;
+		if ( st.considerBarcode )
+		{
+			set_err( "barcode-salted index needs k <= 15" ) ;
+			return T4_E_UNSUPPORTED ;
+		}
+	}
 	T4Op op ;
 	memset( &op, 0, sizeof( op ) ) ;
 	op.streamOff = s->off ;
@@ -1092,16 +1166,20 @@ int T4_API( dp_pos_weight_batch )( int n, const int32_t *t_weights, const int64_
 	}
 	so[n] = tot ;
 	size_t szT = (size_t)t_off[n] * 16, szP = (size_t)p_off[n], szO = ( n + 1 ) * 8 ;
-	void *dT = 0, *dP = 0, *dTo = 0, *dPo = 0, *dA = 0, *dAo = 0, *dS = 0, *dScr = 0, *dSo = 0 ;
-	if ( dmalloc( &dT, szT + 16 ) || dmalloc( &dP, szP + 16 ) || dmalloc( &dTo, szO ) || dmalloc( &dPo, szO ) || dmalloc( &dA, alignTot + 16 )
-		|| dmalloc( &dAo, szO ) || dmalloc( &dS, n * 4 ) || dmalloc( &dScr, tot + 16 ) || dmalloc( &dSo, szO ) )
-		return T4_E_NOMEM ;
-	h2d( dT, t_weights, szT ) ;
-	h2d( dP, p, szP ) ;
-	h2d( dTo, t_off, szO ) ;
-	h2d( dPo, p_off, szO ) ;
-	h2d( dAo, align_off, szO ) ;
-	h2d( dSo, so.data(), szO ) ;
+	// one device allocation carved into the nine buffers: a single cleanup path whatever fails
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	size_t oT = 0, oP = oT + al( szT + 16 ), oTo = oP + al( szP + 16 ), oPo = oTo + al( szO ), oA = oPo + al( szO ),
+		oAo = oA + al( (size_t)alignTot + 16 ), oS = oAo + al( szO ), oScr = oS + al( (size_t)n * 4 ), oSo = oScr + al( (size_t)tot + 16 ),
+		total = oSo + al( szO ) ;
+	void *base = 0 ;
+	r = dmalloc( &base, total ) ;
+	if ( r ) return r ;
+	struct Guard { void *p ; ~Guard() { dfree( p ) ; } } guard = { base } ;
+	char *B = (char *)base ;
+	void *dT = B + oT, *dP = B + oP, *dTo = B + oTo, *dPo = B + oPo, *dA = B + oA, *dAo = B + oAo, *dS = B + oS, *dScr = B + oScr, *dSo = B + oSo ;
+	if ( ( r = h2d( dT, t_weights, szT ) ) || ( r = h2d( dP, p, szP ) ) || ( r = h2d( dTo, t_off, szO ) ) || ( r = h2d( dPo, p_off, szO ) )
+		|| ( r = h2d( dAo, align_off, szO ) ) || ( r = h2d( dSo, so.data(), szO ) ) )
+		return r ;
 #if T4_CUDA
 	t4_dp_kernel<<<( n + 63 ) / 64, 64>>>( n, (const int *)dT, (const i64 *)dTo, (const char *)dP, (const i64 *)dPo, (signed char *)dA,
 		(const i64 *)dAo, (int *)dS, (char *)dScr, (const i64 *)dSo ) ;
@@ -1118,9 +1196,66 @@ int T4_API( dp_pos_weight_batch )( int n, const int32_t *t_weights, const int64_
 			(signed char *)dA + align_off[i], (int *)sc, (unsigned char *)( sc + 8 * W ), 0 ) ;
 	}
 #endif
-	d2h( align_out, dA, alignTot ) ;
-	d2h( score_out, dS, n * 4 ) ;
-	dfree( dT ) ; dfree( dP ) ; dfree( dTo ) ; dfree( dPo ) ; dfree( dA ) ; dfree( dAo ) ; dfree( dS ) ; dfree( dScr ) ; dfree( dSo ) ;
+	if ( ( r = d2h( align_out, dA, alignTot ) ) || ( r = d2h( score_out, dS, (size_t)n * 4 ) ) )
+		return r ;
+	return 0 ;
+}
+
+// The hot-path DP routines on n equal-length problems (problem i: columns / bases off[i]..off[i+1)).
+// variant 0: t4_dp_equal; variant 1: w_dp_equal_half (product build only).
+int T4_API( dp_hot_path_batch )( int n, int variant, const int32_t *t_weights, const int64_t *off, const char *p, int8_t *align_out,
+	const int64_t *align_off, int32_t *score_out )
+{
+	int r = ensure_up() ;
+	if ( r ) return r ;
+	if ( n <= 0 )
+		return 0 ;
+	if ( variant != 0 && variant != 1 )
+		return T4_E_INVAL ;
+#if !T4_CUDA
+	if ( variant == 1 )
+	{
+		set_err( "w_dp_equal_half exists only in the CUDA build" ) ;
+		return T4_E_UNSUPPORTED ;
+	}
+#endif
+	std::vector<i64> so( n + 1 ) ;
+	i64 tot = 0, alignTot = 0 ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		i64 len = off[i + 1] - off[i] ;
+		so[i] = tot ;
+		i64 stride = len / 16 + 2 ;
+		tot += 26 * stride + ( 2 * ( 2 * len + 8 ) + 3 ) / 4 + len + 8 ; // u32 words: traceback of both halves, edit strings, act32 of variant 0
+		i64 e = align_off[i] + 2 * len + 2 ;
+		if ( e > alignTot )
+			alignTot = e ;
+	}
+	so[n] = tot ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	size_t szT = (size_t)off[n] * 16, szP = (size_t)off[n], szO = (size_t)( n + 1 ) * 8 ;
+	size_t oT = 0, oP = oT + al( szT + 16 ), oOff = oP + al( szP + 16 ), oA = oOff + al( szO ), oAo = oA + al( (size_t)alignTot + 16 ),
+		oS = oAo + al( szO ), oScr = oS + al( (size_t)n * 4 ), oSo = oScr + al( (size_t)tot * 4 + 16 ), total = oSo + al( szO ) ;
+	void *base = 0 ;
+	r = dmalloc( &base, total ) ;
+	if ( r ) return r ;
+	struct Guard { void *p ; ~Guard() { dfree( p ) ; } } guard = { base } ;
+	char *B = (char *)base ;
+	if ( ( r = h2d( B + oT, t_weights, szT ) ) || ( r = h2d( B + oP, p, szP ) ) || ( r = h2d( B + oOff, off, szO ) )
+		|| ( r = h2d( B + oAo, align_off, szO ) ) || ( r = h2d( B + oSo, so.data(), szO ) ) )
+		return r ;
+#if T4_CUDA
+	t4_dp_hot_kernel<<<n, 32>>>( n, variant, (const int *)( B + oT ), (const i64 *)( B + oOff ), B + oP, (signed char *)( B + oA ),
+		(const i64 *)( B + oAo ), (int *)( B + oS ), (u32 *)( B + oScr ), (const i64 *)( B + oSo ) ) ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaDeviceSynchronize() ) ;
+#else
+	for ( int i = 0 ; i < n ; ++i )
+		( (int *)( B + oS ) )[i] = t4_dp_equal( (const int *)( B + oT ) + 4 * off[i], B + oP + off[i], (int)( off[i + 1] - off[i] ),
+			(signed char *)( B + oA ) + align_off[i], (u32 *)( B + oScr ) + so[i], false, 0 ) ;
+#endif
+	if ( ( r = d2h( align_out, B + oA, alignTot ) ) || ( r = d2h( score_out, B + oS, (size_t)n * 4 ) ) )
+		return r ;
 	return 0 ;
 }
 

@@ -28,7 +28,7 @@ typedef int64_t i64;
 #define T4_SYNC() ((void)0)
 #endif
 
-#define T4_DEV_MAX_READ 512       /* device-side read length limit (reads > 200 bp make the reference switch to isLongSeqSet) */
+#define T4_DEV_MAX_READ T4_MAX_READ_LEN       /* device-side read length limit (reads > 200 bp make the reference switch to isLongSeqSet) */
 #define T4_ALIGN 16
 #define T4_BIG_REPEAT 10000       /* SeqSet.hpp:799, 875, 937: hits[k].repeats <= 10000 */
 

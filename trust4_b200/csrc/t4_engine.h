@@ -797,11 +797,16 @@ T4_D inline void t4_revcomp( char *rc, const char *s, int len )
 T4_D inline void c_ensure_hits( T4Ctx &cx, u32 n )
 {
 	T4Stream *st = cx.st ;
-	if ( n + 1 > st->hitCap )
+	// the grow decision must be CTA-uniform (a barrier sits inside the branch): every thread reads the cap between
+	// two barriers, before thread 0 can overwrite it
+	T4_SYNC() ;
+	const u32 capNow = st->hitCap ;
+	T4_SYNC() ;
+	if ( n + 1 > capNow )
 	{
 		if ( cx.tid == 0 )
 		{
-			u32 nc = st->hitCap ;
+			u32 nc = capNow ;
 			while ( nc < n + 1 )
 				nc *= 2 ;
 			u64 a = s_alloc( cx, (u64)nc * 8 ) ;
@@ -821,11 +826,14 @@ T4_D inline void c_ensure_hits( T4Ctx &cx, u32 n )
 T4_D inline void c_ensure_ovl( T4Ctx &cx, u32 n )
 {
 	T4Stream *st = cx.st ;
-	if ( n + 1 > st->ovlCap )
+	T4_SYNC() ; // CTA-uniform decision, see c_ensure_hits
+	const u32 capNow = st->ovlCap ;
+	T4_SYNC() ;
+	if ( n + 1 > capNow )
 	{
 		if ( cx.tid == 0 )
 		{
-			u32 nc = st->ovlCap ;
+			u32 nc = capNow ;
 			while ( nc < n + 1 )
 				nc *= 2 ;
 			u64 a = s_alloc( cx, (u64)nc * sizeof( T4Ovl ) ) ;
