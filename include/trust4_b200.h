@@ -83,6 +83,15 @@ int t4_seqset_input_novel_read(t4_seqset *s, const char *id, const char *read, i
 int t4_seqset_update_all_consensus(t4_seqset *s);
 /* void SeqSet::ChangeKmerLength(int kl), SeqSet.hpp:4624 (compacts slots, rebuilds the index) */
 int t4_seqset_change_kmer_length(t4_seqset *s, int kmer_length);
+/* void SeqSet::ReleaseFinishedBarcodeSeq(std::map<int,int> barcodes, bool removeFromIndex, int contigMinCov,
+ *   bool earlyStop), SeqSet.hpp:10815, as the stage-1 driver calls it (main.cpp:1855): one finished barcode,
+ *   removeFromIndex = true, earlyStop = true. */
+int t4_seqset_release_finished_barcode(t4_seqset *s, int barcode, int contig_min_cov);
+/* void SeqSet::ReleaseShallowContigs(int minCov), SeqSet.hpp:10928 (main.cpp:1954) */
+int t4_seqset_release_shallow_contigs(t4_seqset *s, int min_cov);
+/* void SeqSet::InputNovelFa(char *filename), SeqSet.hpp:2986 (--debug-ns, main.cpp:711): every FASTA record becomes a
+ * contig through InputNovelRead(id, seq, 1, -1).  Returns the number of records or a T4_E_* code. */
+int t4_seqset_input_novel_fa(t4_seqset *s, const char *filename);
 /* void SeqSet::Output(FILE*, std::vector<std::string>*), SeqSet.hpp:10939 */
 int t4_seqset_output(t4_seqset *s, FILE *fp, const char *const *barcode_names, int n_barcode_names);
 /* Same text into a malloc'ed buffer (caller frees with t4_free). */
@@ -95,6 +104,11 @@ void t4_free(void *p);
 int t4_seqset_get_contig(t4_seqset *s, int slot, char *consensus, int consensus_cap,
                          int32_t *pos_weight /* 4*len, [pos][ACGT] */, char *name, int name_cap,
                          int *barcode, int *num_read, int *min_left_ext_anchor, int *min_right_ext_anchor);
+
+/* T4_CONTIG_PURGED: the contig was purged by ReleaseFinishedBarcodeSeq (reference: seqs[i].index == false and
+ * posWeight compressed / freed; a host mirror re-applies that storage change, see integration/).  -1 for a released slot. */
+#define T4_CONTIG_PURGED 1
+int t4_seqset_contig_flags(t4_seqset *s, int slot);
 
 /* int SeqSet::HasMotif(char *read, int strand), SeqSet.hpp:5029 (host utility) */
 int t4_has_motif(const char *read, int strand);
@@ -165,6 +179,10 @@ typedef struct t4_run_cfg {
     int32_t do_rescue;             /* run the rescue pass main.cpp:1897-1940 */
     int32_t first_read_len;        /* firstReadLen (rescue is skipped when > 200) */
     int32_t final_update;          /* UpdateAllConsensus after each pass (main.cpp:1881,1939) */
+    int32_t release_barcodes;      /* hasBarcode && !keepMissingBarcode: purge a barcode's contigs once all of its reads
+                                      were assembled (main.cpp:1846-1859 -> ReleaseFinishedBarcodeSeq, SeqSet.hpp:10815);
+                                      the per-barcode totals are counted over this seqset's records (main.cpp:1572-1581) */
+    int32_t contig_min_cov;        /* --contigMinCov (main.cpp:741): argument of the purge above */
     int32_t reserved_;
 } t4_run_cfg;
 

@@ -5,7 +5,8 @@
 //     AssignRead / mate extension, RemoveRedundantSeq) keeps running the reference's own CPU code;
 //   * routes the novel-contig set of the stage-1 driver (`SeqSet seqSet`, main.cpp:642 -- the first SeqSet constructed)
 //     through the C ABI of include/trust4_b200.h: AddRead, RepeatAddRead, InputNovelRead, UpdateAllConsensus,
-//     ChangeKmerLength, Size, SetHitLenRequired, Output (SeqSet.hpp:3426, 4477, 3028, 4525, 4624, 2591, 2601, 10939);
+//     ChangeKmerLength, Size, SetHitLenRequired, Output (SeqSet.hpp:3426, 4477, 3028, 4525, 4624, 2591, 2601, 10939),
+//     ReleaseFinishedBarcodeSeq, ReleaseShallowContigs, InputNovelFa (SeqSet.hpp:10815, 10928, 2986);
 //   * hands the contigs back to the CPU object after the assembly (Output is the driver's first use of them,
 //     main.cpp:1957-1975) so that `extendedSeq.InputSeqSet( seqSet, false )` (main.cpp:2049) sees them.
 // The resulting binary is a drop-in `trust4`: same flags, same _raw.out / _final.out / _assembled_reads.fa
@@ -27,6 +28,10 @@
 #define t4_seqset_set_consider_barcode_in_hash t4emu_seqset_set_consider_barcode_in_hash
 #define t4_seqset_output t4emu_seqset_output
 #define t4_seqset_get_contig t4emu_seqset_get_contig
+#define t4_seqset_contig_flags t4emu_seqset_contig_flags
+#define t4_seqset_release_finished_barcode t4emu_seqset_release_finished_barcode
+#define t4_seqset_release_shallow_contigs t4emu_seqset_release_shallow_contigs
+#define t4_seqset_input_novel_fa t4emu_seqset_input_novel_fa
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
 #endif
@@ -63,6 +68,7 @@ class T4GpuSeqSet : public SeqSet
 		seqs.clear() ;
 		std::vector<char> cons, name( 4096 ) ;
 		std::vector<int32_t> pw ;
+		std::map<int, int> purgedBarcodes ;
 		for ( int i = 0 ; i < n ; ++i )
 		{
 			struct _seqWrapper ns ;
@@ -86,6 +92,8 @@ class T4GpuSeqSet : public SeqSet
 				ns.consensus = strdup( cons.data() ) ;
 				ns.name = strdup( name.data() ) ;
 				ns.consensusLen = len ;
+				if ( Check( t4_seqset_contig_flags( h, i ) ) & T4_CONTIG_PURGED )
+					purgedBarcodes[ns.barcode] = 1 ;
 			}
 			seqs.push_back( ns ) ;
 			if ( len >= 0 )
@@ -97,6 +105,12 @@ class T4GpuSeqSet : public SeqSet
 						sw.posWeight[j].count[k] = pw[4 * j + k] ;
 			}
 		}
+		// Contigs the device purged (ReleaseFinishedBarcodeSeq) keep their full posWeight columns there; the reference
+		// compresses or frees them and marks them un-indexed.  Re-apply exactly that storage change to the mirror with the
+		// reference's own code (the index removal and UpdateConsensus inside it are no-ops here: the host index is empty
+		// and the consensus is already final), so everything downstream of Output sees the reference's object state.
+		if ( !purgedBarcodes.empty() )
+			SeqSet::ReleaseFinishedBarcodeSeq( purgedBarcodes, true, 0, false ) ;
 	}
 public:
 	T4GpuSeqSet( int kl ) : SeqSet( kl ), h( NULL )
@@ -147,6 +161,37 @@ public:
 		if ( gpu )
 			Check( t4_seqset_set_consider_barcode_in_hash( h, s ) ) ;
 		SeqSet::SetConsiderBarcodeInIndexHash( s ) ;
+	}
+	// main.cpp:1855 -- one finished barcode, removeFromIndex = true, earlyStop = true
+	void ReleaseFinishedBarcodeSeq( std::map<int, int> barcodes, bool removeFromIndex, int contigMinCov, bool earlyStop )
+	{
+		if ( !gpu )
+		{
+			SeqSet::ReleaseFinishedBarcodeSeq( barcodes, removeFromIndex, contigMinCov, earlyStop ) ;
+			return ;
+		}
+		if ( barcodes.size() != 1 || !removeFromIndex || !earlyStop )
+		{
+			fprintf( stderr, "trust4_b200: ReleaseFinishedBarcodeSeq is only supported as the stage-1 driver calls it\n" ) ;
+			exit( 1 ) ;
+		}
+		Check( t4_seqset_release_finished_barcode( h, barcodes.begin()->first, contigMinCov ) ) ;
+	}
+	// main.cpp:1954 (--contigMinCov)
+	void ReleaseShallowContigs( int minCov )
+	{
+		if ( gpu )
+			Check( t4_seqset_release_shallow_contigs( h, minCov ) ) ;
+		else
+			SeqSet::ReleaseShallowContigs( minCov ) ;
+	}
+	// main.cpp:711 (--debug-ns)
+	void InputNovelFa( char *filename )
+	{
+		if ( gpu )
+			Check( t4_seqset_input_novel_fa( h, filename ) ) ;
+		else
+			SeqSet::InputNovelFa( filename ) ;
 	}
 	void Output( FILE *fp, std::vector<std::string> *barcodeIntToStr = NULL )
 	{

@@ -78,6 +78,23 @@ int t4ref_input_novel_read( void *h, const char *id, const char *read, int stran
 }
 
 void t4ref_update_all_consensus( void *h ) { ((SeqSet *)h)->UpdateAllConsensus() ; }
+// SeqSet::ReleaseFinishedBarcodeSeq as the driver calls it (main.cpp:1855), ReleaseShallowContigs (main.cpp:1954),
+// InputNovelFa (main.cpp:711)
+void t4ref_release_finished_barcode( void *h, int barcode, int contigMinCov )
+{
+	std::map<int, int> fin ;
+	fin[barcode] = 1 ;
+	((SeqSet *)h)->ReleaseFinishedBarcodeSeq( fin, true, contigMinCov, true ) ;
+}
+void t4ref_release_shallow_contigs( void *h, int minCov ) { ((SeqSet *)h)->ReleaseShallowContigs( minCov ) ; }
+void t4ref_input_novel_fa( void *h, const char *filename ) { ((SeqSet *)h)->InputNovelFa( (char *)filename ) ; }
+int t4ref_num_read( void *h, int slot )
+{
+	SeqSet *s = (SeqSet *)h ;
+	if ( slot < 0 || slot >= (int)s->seqs.size() || s->seqs[slot].consensus == NULL )
+		return -1 ;
+	return s->seqs[slot].numRead ;
+}
 void t4ref_change_kmer_length( void *h, int kl ) { ((SeqSet *)h)->ChangeKmerLength( kl ) ; }
 
 int t4ref_has_motif( void *h, const char *read, int strand )
@@ -369,12 +386,11 @@ int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, 
 	std::vector<char> goodCandidate( n, 0 ) ;
 	std::vector<int> info( n, -1 ) ;
 	std::vector<int> rescue ;
-	// cfg->reserved_ == 1: also purge finished barcodes like main.cpp:1575-1581, 1846-1859 (ReleaseFinishedBarcodeSeq with
-	// release_index = true, contigMinCov = 0, early_stop = true).  The engine has no such op: the call is memory management
-	// plus an early UpdateConsensus and is observationally a no-op on Output when the index is barcode-salted
-	// (tests/test_emu_parity.py::test_emu_barcode_release_is_unobservable).
+	// cfg->release_barcodes: purge finished barcodes like main.cpp:1572-1581, 1846-1859 (ReleaseFinishedBarcodeSeq with
+	// release_index = true, contigMinCov = cfg->contig_min_cov, early_stop = true); note that the driver only counts reads
+	// with addRet >= 0 towards "finished" (the block sits inside `else if ( addRet >= 0 )`).
 	std::map<int, int> barcodeTotalReadCount, barcodeReadCount ;
-	if ( cfg->has_barcode && cfg->reserved_ == 1 )
+	if ( cfg->has_barcode && cfg->release_barcodes )
 		for ( i = 0 ; i < n ; ++i )
 			if ( descs[i].barcode != -1 )
 				++barcodeTotalReadCount[ descs[i].barcode ] ;
@@ -461,7 +477,7 @@ int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, 
 				}
 			}
 		}
-		if ( addRet >= 0 && cfg->has_barcode && cfg->reserved_ == 1 && d.barcode != -1 )
+		if ( addRet >= 0 && cfg->has_barcode && cfg->release_barcodes && d.barcode != -1 )
 		{
 			int barcode = d.barcode ;
 			++barcodeReadCount[barcode] ;
@@ -469,7 +485,7 @@ int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, 
 			{
 				std::map<int, int> finishedBarcodes ;
 				finishedBarcodes[barcode] = barcodeTotalReadCount[barcode] ;
-				s->ReleaseFinishedBarcodeSeq( finishedBarcodes, true, 0, true ) ;
+				s->ReleaseFinishedBarcodeSeq( finishedBarcodes, true, cfg->contig_min_cov, true ) ;
 			}
 		}
 		retCodes[i] = addRet ;

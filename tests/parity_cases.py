@@ -297,19 +297,14 @@ def check_barcode_mode(lib, ref, seed=31, n_barcodes=5):
     assert len(set(c["barcode"] for c in (g.get_contig(i) for i in range(g.size())) if c)) > 1
 
 
-def check_barcode_release_unobservable(lib, ref, seed=33):
-    """SeqSet::ReleaseFinishedBarcodeSeq (SeqSet.hpp:10815; driver main.cpp:1846-1859) frees a finished barcode's
-    contigs from the index and compresses their posWeight.  With a barcode-salted index and contigMinCov = 0 that is
-    memory management plus an early UpdateConsensus: the reference run WITH the call must print the same contigs as
-    the engine (which has no such op) -- and as the reference without it."""
-    lib.check(lib.reset())
-    cl = synth.make_clones(6, seed)
-    rd = synth.sample_pairs(cl, 400, 150, seed)
+def _barcode_descs(seed, n_barcodes=3, nclones=6, npairs=400):
+    """A barcode-sorted record list (main.cpp:1126 CompReadWithBarcode order) over a small synthetic library."""
+    cl = synth.make_clones(nclones, seed)
+    rd = synth.sample_pairs(cl, npairs, 150, seed)
     w = synth.build_workload(cl, rd)
     d = w.descs.copy()
-    # barcode = clone-ish hash; sort by barcode first like main.cpp:1126 (CompReadWithBarcode), keeping the order inside
     reads = w.pool.reshape(-1, w.L)
-    h = (reads.astype(np.int64) * np.arange(1, w.L + 1)).sum(axis=1) % 3
+    h = (reads.astype(np.int64) * np.arange(1, w.L + 1)).sum(axis=1) % n_barcodes
     order = np.argsort(h, kind="stable")
     d = d[order]
     d["barcode"] = h[order].astype(np.int32)
@@ -322,20 +317,101 @@ def check_barcode_release_unobservable(lib, ref, seed=33):
     d["flags"] = np.where(same_prev, d["flags"] | synth.RD_DUP, d["flags"] & ~np.uint32(synth.RD_DUP))
     d["eq_lo"] = np.arange(n)
     d["eq_hi"] = np.arange(n) + 1
-    outs, sums = [], []
-    for release in (0, 1):
-        cfg = synth.run_cfg(has_barcode=1)
-        cfg["reserved_"] = release
-        r = ref.RefSeqSet(9)
-        r.set_hit_len_required(13)
-        ref.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
-        r.run_descs(cfg, d, w.pool, w.names)
-        outs.append(r.output())
-        sums.append(r.index_checksum()[0])
-    assert sums[1] < sums[0]            # the release really happened: postings of finished barcodes left the index
+    return w, d
+
+
+def _same_sets(g, r):
+    assert g.size() == r.size()
+    assert g.output() == r.output()
+    assert g.index_checksum() == r.index_checksum()
+    for i in range(g.size()):
+        gc = g.get_contig(i)
+        assert (gc is None) == (r.num_read(i) < 0), i
+        if gc is not None:
+            assert gc["num_read"] == r.num_read(i), i
+
+
+def check_barcode_release(lib, ref, seed=33):
+    """SeqSet::ReleaseFinishedBarcodeSeq (SeqSet.hpp:10815; driver main.cpp:1846-1859: only reads with addRet >= 0 count
+    towards "finished"), ReleaseShallowContigs (SeqSet.hpp:10928) and IsContigShallow (:2512): inside the batch loop
+    (cfg.release_barcodes, contig_min_cov 0 / 2 / 20) and through the per-call entries, against the reference --
+    Output text, slot count, numRead of every slot and the index multiset (purged contigs leave the index)."""
+    w, d = _barcode_descs(seed)
+    base_sum = None
+    for min_cov in (0, 2, 20):
+        lib.check(lib.reset())
+        outs = []
+        for release in (0, 1):
+            cfg = synth.run_cfg(has_barcode=1, release_barcodes=release, contig_min_cov=min_cov)
+            r = ref.RefSeqSet(9)
+            r.set_hit_len_required(13)
+            ref.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
+            _, rret, rstr, rres = r.run_descs(cfg, d, w.pool, w.names)
+            g = api.SeqSet(9, lib)
+            g.set_hit_len_required(13)
+            g.set_consider_barcode_in_hash(1)
+            _, gret, gstr, gres = g.run_descs(cfg, d, w.pool, w.names)
+            assert (gret == rret).all() and (gstr == rstr).all() and (gres == rres).all()
+            _same_sets(g, r)
+            outs.append((r.output(), r.index_checksum()[0]))
+            if release == 1 and min_cov > 0:
+                # --contigMinCov: the driver's last step before Output (main.cpp:1952-1955)
+                r.release_shallow_contigs(min_cov)
+                g.release_shallow_contigs(min_cov)
+                assert g.output() == r.output()
+                assert g.size() == r.size()
+                outs.append((r.output(), 0))
+        if min_cov == 0:
+            assert outs[1][1] < outs[0][1]       # the purge really happened: postings left the index ...
+            assert outs[0][0] == outs[1][0]      # ... and is invisible in Output when nothing is shallow
+            assert len(outs[0][0]) > 1000
+        if min_cov == 20:
+            assert 0 < len(outs[1][0]) < len(outs[0][0])    # shallow contigs were dropped inside the loop, deep ones stayed
+    # per-call route, like the driver: assemble one barcode, purge it (the purge walks the slots from the end and stops at
+    # the first contig of another barcode or an already purged one), go on with the next
+    lib.check(lib.reset())
+    cfg = synth.run_cfg(has_barcode=1, final_update=0, do_rescue=0)
+    r = ref.RefSeqSet(9)
+    r.set_hit_len_required(13)
+    ref.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
     g = api.SeqSet(9, lib)
     g.set_hit_len_required(13)
     g.set_consider_barcode_in_hash(1)
-    g.run_descs(synth.run_cfg(has_barcode=1), d, w.pool, w.names)
-    assert outs[0] == outs[1] == g.output()
-    assert len(outs[0]) > 1000
+    for bc, cov in ((0, 0), (1, 20), (2, 2)):
+        part = d[d["barcode"] == bc].copy()
+        part["flags"][0] &= ~np.uint32(synth.RD_DUP)
+        _, rret, _, _ = r.run_descs(cfg, part, w.pool, w.names)
+        _, gret, _, _ = g.run_descs(cfg, part, w.pool, w.names)
+        assert (gret == rret).all()
+        if bc == 2:
+            r.release_finished_barcode(1, 0)     # stops at once: the tail belongs to barcode 2
+            g.release_finished_barcode(1, 0)
+            _same_sets(g, r)
+        r.release_finished_barcode(bc, cov)
+        g.release_finished_barcode(bc, cov)
+        _same_sets(g, r)
+    purged = [g.contig_flags(i) for i in range(g.size())]
+    assert 1 in purged and -1 in purged      # purged contigs and (barcode 1, cov 20) dropped ones
+    # a purged set survives UpdateAllConsensus and ChangeKmerLength (Clean skips contigs with index == false)
+    r.update_all_consensus()
+    g.update_all_consensus()
+    _same_sets(g, r)
+
+
+def check_input_novel_fa(lib, ref, tmp_path):
+    """SeqSet::InputNovelFa (SeqSet.hpp:2986, --debug-ns)."""
+    lib.check(lib.reset())
+    rng = np.random.default_rng(3)
+    fa = tmp_path / "ns.fa"
+    with open(fa, "w") as f:
+        for i in range(7):
+            s = "".join("ACGT"[c] for c in rng.integers(0, 4, size=int(rng.integers(40, 400))))
+            f.write(">ns%d some comment\n" % i)
+            for j in range(0, len(s), 60):
+                f.write(s[j:j + 60] + "\n")
+    r = ref.RefSeqSet(9)
+    g = api.SeqSet(9, lib)
+    r.input_novel_fa(str(fa))
+    assert g.input_novel_fa(str(fa)) == 7
+    assert g.output() == r.output() and len(g.output()) > 500
+    assert g.index_checksum() == r.index_checksum()

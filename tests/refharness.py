@@ -53,6 +53,10 @@ def lib():
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         l.t4ref_run_descs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_char_p), C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        l.t4ref_release_finished_barcode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        l.t4ref_release_shallow_contigs.argtypes = [C.c_void_p, C.c_int]
+        l.t4ref_input_novel_fa.argtypes = [C.c_void_p, C.c_char_p]
+        l.t4ref_num_read.argtypes = [C.c_void_p, C.c_int]
         _lib = l
     return _lib
 
@@ -97,6 +101,18 @@ class RefSeqSet:
 
     def change_kmer_length(self, k):
         self.l.t4ref_change_kmer_length(self.h, k)
+
+    def release_finished_barcode(self, barcode, contig_min_cov=0):
+        self.l.t4ref_release_finished_barcode(self.h, barcode, contig_min_cov)
+
+    def release_shallow_contigs(self, min_cov):
+        self.l.t4ref_release_shallow_contigs(self.h, min_cov)
+
+    def input_novel_fa(self, filename):
+        self.l.t4ref_input_novel_fa(self.h, filename.encode())
+
+    def num_read(self, slot):
+        return self.l.t4ref_num_read(self.h, slot)
 
     def has_motif(self, read, strand):
         return self.l.t4ref_has_motif(self.h, read.encode(), strand)

@@ -32,6 +32,31 @@ def write_inputs(tmp, npairs=1500, nclones=40, seed=21):
     return ["-f", fa, "-1", os.path.join(tmp, "reads_1.fq"), "-2", os.path.join(tmp, "reads_2.fq")]
 
 
+def write_barcode_inputs(tmp, nreads=1500, nclones=24, n_barcodes=6, seed=23):
+    """10x-style single-end input (BASELINE configs[3] flavour): every read carries a cell barcode (--barcode file with
+    the same ids); a cell = a few clonotypes, plus a few ambient reads of other cells' clones."""
+    import numpy as np
+    pool = synth.load_gene_pool()
+    fa = os.path.join(tmp, "genes.fa")
+    with open(fa, "w") as f:
+        for ch in pool.values():
+            for seg in ch.values():
+                for name, seq in seg:
+                    f.write(">%s\n%s\n" % (name, seq))
+    cl = synth.make_clones(nclones, seed)
+    rd = synth.sample_pairs(cl, nreads, 150, seed, paired=False)
+    rng = np.random.default_rng(seed)
+    bc = rd.clone % n_barcodes
+    amb = rng.random(nreads) < 0.02
+    bc = np.where(amb, rng.integers(0, n_barcodes, size=nreads), bc)
+    tags = ["".join("ACGT"[c] for c in rng.integers(0, 4, size=16)) for _ in range(n_barcodes)]
+    with open(os.path.join(tmp, "reads.fq"), "w") as fq, open(os.path.join(tmp, "bc.fa"), "w") as fb:
+        for i in range(nreads):
+            fq.write("@r%d\n%s\n+\n%s\n" % (i, synth.decode(rd.codes[i]), "I" * 150))
+            fb.write(">r%d\n%s\n" % (i, tags[int(bc[i])]))
+    return ["-f", fa, "-u", os.path.join(tmp, "reads.fq"), "--barcode", os.path.join(tmp, "bc.fa")]
+
+
 def run_and_compare(binary, args, tmp, extra=()):
     for exe, tag in ((STOCK, "stock"), (binary, "dropin")):
         subprocess.run([exe, "-t", "1", "-o", os.path.join(tmp, tag)] + list(extra) + args, check=True,
@@ -65,6 +90,26 @@ def test_dropin_emu_synthetic(emu_binary, tmp_path):
 def test_dropin_emu_repseq_flags(emu_binary, tmp_path):
     """run-trust4 --repseq expands to --trimLevel 2 --skipMateExtension (run-trust4:288-291): repetitiveData = true."""
     run_and_compare(emu_binary, write_inputs(str(tmp_path), 800, 25, 22), str(tmp_path), extra=("--trimLevel", "2", "--skipMateExtension"))
+
+
+def test_dropin_emu_contig_min_cov(emu_binary, tmp_path):
+    """--contigMinCov: ReleaseShallowContigs before Output (main.cpp:1952-1955) runs on the device set."""
+    run_and_compare(emu_binary, write_inputs(str(tmp_path), 800, 25, 24), str(tmp_path), extra=("--contigMinCov", "3"))
+
+
+@pytest.mark.parametrize("extra", [(), ("--contigMinCov", "4")])
+def test_dropin_emu_barcodes(emu_binary, tmp_path, extra):
+    """--barcode: hitLenRequired 13, barcode-salted index, ReleaseFinishedBarcodeSeq after a cell's last read
+    (main.cpp:1549-1560, 1846-1859), barcode names in Output."""
+    run_and_compare(emu_binary, write_barcode_inputs(str(tmp_path)), str(tmp_path), extra=extra)
+
+
+@pytest.mark.gpu
+def test_dropin_gpu_barcodes(tmp_path):
+    binary = os.path.join(ROOT, "integration", "_build", "trust4_gpu")
+    if not (os.path.exists(binary) and os.path.exists(STOCK)):
+        pytest.skip("prebuilt drop-in / stock binaries not present")
+    run_and_compare(binary, write_barcode_inputs(str(tmp_path)), str(tmp_path), extra=("--contigMinCov", "4"))
 
 
 @pytest.mark.gpu

@@ -37,8 +37,12 @@ def test_emu_barcode_mode(emu_lib, ref):
     pc.check_barcode_mode(emu_lib, ref)
 
 
-def test_emu_barcode_release_is_unobservable(emu_lib, ref):
-    pc.check_barcode_release_unobservable(emu_lib, ref)
+def test_emu_barcode_release(emu_lib, ref):
+    pc.check_barcode_release(emu_lib, ref)
+
+
+def test_emu_input_novel_fa(emu_lib, ref, tmp_path):
+    pc.check_input_novel_fa(emu_lib, ref, tmp_path)
 
 
 def test_emu_single_stream_at_scale(emu_lib, ref):

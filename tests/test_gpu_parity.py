@@ -95,3 +95,12 @@ def test_gpu_big_repeats(gpu_lib, ref):
 
 def test_gpu_barcode_mode(gpu_lib, ref):
     pc.check_barcode_mode(gpu_lib, ref)
+
+
+def test_gpu_barcode_release(gpu_lib, ref):
+    """ReleaseFinishedBarcodeSeq / ReleaseShallowContigs on the device (batch loop and per-call), contigMinCov 0/2/20."""
+    pc.check_barcode_release(gpu_lib, ref)
+
+
+def test_gpu_input_novel_fa(gpu_lib, ref, tmp_path):
+    pc.check_input_novel_fa(gpu_lib, ref, tmp_path)

@@ -32,6 +32,7 @@ EXPORTS = [
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
     "streams_run_resident", "workload_results", "last_counters", "probe_resident", "streams_error",
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
+    "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
 ]
 
 
@@ -83,6 +84,10 @@ class Lib:
         f("seqset_get_overlaps", ci, [vp, cs, ci, ci, ci, vp, vp, ci])
         f("dp_pos_weight_batch", ci, [ci, vp, vp, vp, vp, vp, vp, vp])
         f("dp_hot_path_batch", ci, [ci, ci, vp, vp, vp, vp, vp, vp])
+        f("seqset_release_finished_barcode", ci, [vp, ci, ci])
+        f("seqset_release_shallow_contigs", ci, [vp, ci])
+        f("seqset_input_novel_fa", ci, [vp, cs])
+        f("seqset_contig_flags", ci, [vp, ci])
         f("seqset_add_reads_batch", ci, [vp, vp, vp, ci, vp, C.c_size_t, C.POINTER(cs), ci, vp, vp, vp])
         f("streams_run", ci, [C.POINTER(vp), ci, vp, vp, vp, vp, C.c_size_t, C.POINTER(cs), ci, vp, vp, vp])
         f("workload_upload", vp, [vp, C.c_int64, vp, C.c_size_t, C.POINTER(cs), ci])
@@ -184,6 +189,21 @@ class SeqSet:
 
     def change_kmer_length(self, k):
         self.lib.check(self.lib.seqset_change_kmer_length(self.h, k))
+
+    def release_finished_barcode(self, barcode, contig_min_cov=0):
+        """SeqSet::ReleaseFinishedBarcodeSeq({barcode}, true, contig_min_cov, true), SeqSet.hpp:10815."""
+        self.lib.check(self.lib.seqset_release_finished_barcode(self.h, barcode, contig_min_cov))
+
+    def release_shallow_contigs(self, min_cov):
+        """SeqSet::ReleaseShallowContigs, SeqSet.hpp:10928."""
+        self.lib.check(self.lib.seqset_release_shallow_contigs(self.h, min_cov))
+
+    def input_novel_fa(self, filename):
+        """SeqSet::InputNovelFa, SeqSet.hpp:2986."""
+        return self.lib.check(self.lib.seqset_input_novel_fa(self.h, filename.encode()))
+
+    def contig_flags(self, slot):
+        return self.lib.seqset_contig_flags(self.h, slot)
 
     def output(self) -> bytes:
         buf = C.c_void_p()

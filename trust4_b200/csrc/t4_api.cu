@@ -832,6 +832,100 @@ int T4_API( seqset_change_kmer_length )( t4_seqset *s, int kl )
 	return op.ret < T4_E_BASE ? op.ret : 0 ;
 }
 
+int T4_API( seqset_release_finished_barcode )( t4_seqset *s, int barcode, int contig_min_cov )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_RELEASE_BARCODE ;
+	op.barcode = barcode ;
+	op.minKmerCount = contig_min_cov ;
+	r = run_single( op, 0, 0, 0, 0, 0, sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	return op.ret < T4_E_BASE ? op.ret : 0 ;
+}
+
+int T4_API( seqset_release_shallow_contigs )( t4_seqset *s, int min_cov )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = s->off ;
+	op.op = T4_OP_RELEASE_SHALLOW ;
+	op.minKmerCount = min_cov ;
+	r = run_single( op, 0, 0, 0, 0, 0, sizeof( T4Op ) ) ;
+	if ( r ) return r ;
+	return op.ret < T4_E_BASE ? op.ret : 0 ;
+}
+
+// SeqSet::InputNovelFa (SeqSet.hpp:2986): ReadFiles (kseq) semantics -- id = header up to the first white space,
+// sequence lines concatenated.
+int T4_API( seqset_input_novel_fa )( t4_seqset *s, const char *filename )
+{
+	int r = check( s ) ;
+	if ( r ) return r ;
+	FILE *fp = fopen( filename, "r" ) ;
+	if ( !fp )
+	{
+		set_err( std::string( "cannot open " ) + filename ) ;
+		return T4_E_INVAL ;
+	}
+	std::string id, seq, line ;
+	int n = 0 ;
+	bool have = false ;
+	char buf[4096] ;
+	auto flush = [&]() -> int
+	{
+		if ( !have )
+			return 0 ;
+		have = false ;
+		int rr = T4_API( seqset_input_novel_read )( s, id.c_str(), seq.c_str(), 1, -1 ) ;
+		if ( rr < T4_E_BASE )
+			return rr ;
+		++n ;
+		return 0 ;
+	} ;
+	while ( fgets( buf, sizeof( buf ), fp ) )
+	{
+		line = buf ;
+		while ( !line.empty() && ( line.back() == '\n' || line.back() == '\r' ) )
+			line.pop_back() ;
+		if ( !line.empty() && line[0] == '>' )
+		{
+			if ( ( r = flush() ) )
+				break ;
+			size_t e = line.find_first_of( " \t" ) ;
+			id = line.substr( 1, e == std::string::npos ? std::string::npos : e - 1 ) ;
+			seq.clear() ;
+			have = true ;
+		}
+		else if ( have )
+			seq += line ;
+	}
+	if ( !r )
+		r = flush() ;
+	fclose( fp ) ;
+	return r ? r : n ;
+}
+
+int T4_API( seqset_contig_flags )( t4_seqset *s, int slot )
+{
+	T4Stream st ;
+	int r = get_stream( s, &st ) ;
+	if ( r ) return r ;
+	if ( slot < 0 || slot >= st.nSeqs )
+		return -1 ;
+	T4Contig k ;
+	r = d2h( &k, E.A + st.seqsOff + (size_t)slot * sizeof( T4Contig ), sizeof( k ) ) ;
+	if ( r ) return r ;
+	if ( !k.consOff )
+		return -1 ;
+	return ( k.flags & T4_CF_NOINDEX ) ? T4_CONTIG_PURGED : 0 ;
+}
+
 int T4_API( seqset_get_hits )( t4_seqset *s, const char *read, int strand, int barcode, int allow_total_skip, int32_t *hits, int cap )
 {
 	int r = check( s ) ;

@@ -75,7 +75,10 @@ struct T4Contig            // SeqSet.hpp:19 `_seqWrapper`, novel contigs only (i
 	int minLeftExtAnchor, minRightExtAnchor ;
 	int barcode ;
 	int numRead ;
+	int flags ;            // T4_CF_*
+	int pad_ ;
 } ;
+#define T4_CF_NOINDEX 1    /* seqs[i].index == false: purged by ReleaseFinishedBarcodeSeq (SeqSet.hpp:10849) */
 
 // bytes of one packed contig record (t4_streams_pack_contigs)
 T4_HD inline u64 t4_pack_record_bytes( const T4Contig &k ) { return ( 32ull + 17ull * k.len + k.nameLen + 15 ) & ~15ull ; }
@@ -170,6 +173,8 @@ enum
 	T4_OP_RUN_LOOP,
 	T4_OP_PROBE_ONLY,
 	T4_OP_INIT,
+	T4_OP_RELEASE_BARCODE,
+	T4_OP_RELEASE_SHALLOW,
 } ;
 
 struct T4Op                // per-CTA launch record

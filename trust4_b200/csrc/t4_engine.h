@@ -714,6 +714,8 @@ T4_D inline int s_new_contig( T4Ctx &cx, int len )
 	c->minLeftExtAnchor = c->minRightExtAnchor = 0 ;
 	c->barcode = -1 ;
 	c->numRead = 0 ;
+	c->flags = 0 ;
+	c->pad_ = 0 ;
 	++st->nSeqs ;
 	return idx ;
 }
@@ -2802,7 +2804,7 @@ T4_D inline void c_update_all_consensus( T4Ctx &cx )
 		{
 			T4Contig *seq = t4_seq( cx, s ) ;
 			u32 f = 0 ;
-			if ( seq->consOff != 0 )
+			if ( seq->consOff != 0 && !( seq->flags & T4_CF_NOINDEX ) ) // purged: `if (seq.posWeightCompressed) return` (SeqSet.hpp:4542)
 			{
 				const char *cons = t4_cons( cx, seq ) ;
 				const int *pw = t4_pw( cx, seq ) ;
@@ -2830,7 +2832,7 @@ T4_D inline void c_update_all_consensus( T4Ctx &cx )
 	{
 		if ( cx.tid == 0 )
 			for ( int s = 0 ; s < st->nSeqs ; ++s )
-				if ( t4_seq( cx, s )->consOff != 0 )
+				if ( t4_seq( cx, s )->consOff != 0 && !( t4_seq( cx, s )->flags & T4_CF_NOINDEX ) )
 					s_update_consensus( cx, s, true ) ;
 		T4_SYNC() ;
 		return ;
@@ -2865,6 +2867,144 @@ T4_D inline void c_update_all_consensus( T4Ctx &cx )
 	T4_SYNC() ;
 }
 
+// SeqSet::IsContigShallow (SeqSet.hpp:2512-2556) on the uncompressed posWeight columns (the engine never compresses
+// them; for a purged contig with flat coverage every column sums to numRead, which is the reference's
+// `posWeight.Size() == 0` branch).  Serial.
+T4_D inline int s_contig_shallow( T4Ctx &cx, int idx, int minCov )
+{
+	T4Contig *c = t4_seq( cx, idx ) ;
+	if ( c->consOff == 0 )
+		return 0 ;
+	const int *pw = t4_pw( cx, c ) ;
+	const int len = c->len ;
+	int j ;
+	for ( j = 0 ; j < len ; ++j )
+		if ( pw[4 * j] + pw[4 * j + 1] + pw[4 * j + 2] + pw[4 * j + 3] >= minCov )
+			break ;
+	int start = j ;
+	for ( j = len - 1 ; j >= start ; --j )
+		if ( pw[4 * j] + pw[4 * j + 1] + pw[4 * j + 2] + pw[4 * j + 3] >= minCov )
+			break ;
+	int end = j ;
+	for ( j = start ; j <= end ; ++j )
+		if ( pw[4 * j] + pw[4 * j + 1] + pw[4 * j + 2] + pw[4 * j + 3] < minCov )
+			break ;
+	return ( j <= end || end < start ) ? 1 : 0 ;
+}
+
+// SeqSet::ReleaseFinishedBarcodeSeq( {barcode}, removeFromIndex = true, contigMinCov, earlyStop = true )
+// (SeqSet.hpp:10815-10924), the only way the stage-1 driver calls it (main.cpp:1855).  Walks the slots from the end
+// while they belong to `barcode` and are not purged yet: shallow contigs are dropped (index entries removed,
+// ReleaseSeq), the others leave the index, get a final UpdateConsensus( i, false ) and, when their coverage is flat,
+// numRead = that coverage.  The reference then compresses / frees posWeight -- storage only: Output prints the same
+// numbers either way (SeqSet.hpp:10956-10992), so the columns stay as they are here.
+T4_D inline void c_release_barcode( T4Ctx &cx, int barcode, int contigMinCov )
+{
+	T4Stream *st = cx.st ;
+	T4Smem *sm = cx.sm ;
+	T4_SYNC() ;
+	for ( int i = st->nSeqs - 1 ; i >= 0 ; --i )
+	{
+		T4Contig *c = t4_seq( cx, i ) ;
+		T4_SYNC() ;
+		const bool dead = c->consOff == 0 ;
+		const bool stop = !dead && ( ( c->flags & T4_CF_NOINDEX ) || c->barcode != barcode ) ;
+		T4_SYNC() ;
+		if ( dead )
+			continue ;
+		if ( stop )
+			break ;
+		int shallow = 0 ;
+		if ( contigMinCov > 0 )
+		{
+			if ( cx.tid == 0 )
+				sm->bi[0] = s_contig_shallow( cx, i, contigMinCov ) ;
+			T4_SYNC() ;
+			shallow = sm->bi[0] ;
+			T4_SYNC() ;
+		}
+		c_index_op( cx, t4_cons( cx, c ), c->len, T4_IDX_REMOVE, i, c->barcode, 0, 0 ) ;
+		if ( cx.tid == 0 )
+		{
+			if ( shallow )
+				c->consOff = 0 ; // ReleaseSeq: the slot stays, Size() still counts it
+			else
+			{
+				c->flags |= T4_CF_NOINDEX ;
+				s_update_consensus( cx, i, false ) ;
+				const char *cons = t4_cons( cx, c ) ;
+				const int *pw = t4_pw( cx, c ) ;
+				int cov = 0, j, k ;
+				for ( j = 0 ; j < c->len ; ++j )
+				{
+					for ( k = 0 ; k < 4 ; ++k )
+					{
+						if ( k == t4_nuc( cons[j] ) )
+						{
+							if ( pw[4 * j + k] == 0 )
+								break ;
+							if ( j == 0 )
+								cov = pw[4 * j + k] ;
+							else if ( pw[4 * j + k] != cov )
+								break ;
+						}
+						else if ( pw[4 * j + k] != 0 )
+							break ;
+					}
+					if ( k < 4 )
+						break ;
+				}
+				if ( j >= c->len )
+					c->numRead = cov ;
+			}
+		}
+		T4_SYNC() ;
+	}
+	T4_SYNC() ;
+}
+
+// SeqSet::ReleaseShallowContigs (SeqSet.hpp:10928): ReleaseSeq on every shallow contig; like the reference it leaves
+// their index entries behind (the driver calls it after the last AddRead, main.cpp:1952-1955).
+T4_D inline void c_release_shallow( T4Ctx &cx, int minCov )
+{
+	T4Stream *st = cx.st ;
+	T4_SYNC() ;
+	T4_PAR_FOR( i, st->nSeqs )
+		if ( s_contig_shallow( cx, i, minCov ) )
+			t4_seq( cx, i )->consOff = 0 ;
+	T4_SYNC() ;
+}
+
+// Per-barcode read counters of the driver loop (main.cpp:1572-1581 barcodeTotalReadCount / barcodeReadCount): an
+// open-addressing table over the barcodes of this stream's records.
+struct T4BcTable
+{
+	u64 *key ;   // barcode + 1, 0 = empty
+	u32 *total, *done ;
+	u32 cap ;
+} ;
+
+T4_D inline u32 t4_bc_slot( const T4BcTable &t, int barcode, bool claim )
+{
+	u64 key = (u64)(u32)barcode + 1 ;
+	u32 s = (u32)( ( key * 0x9E3779B97F4A7C15ull ) >> 33 ) & ( t.cap - 1 ) ;
+	while ( 1 )
+	{
+		u64 kk = t.key[s] ;
+		if ( kk == key )
+			return s ;
+		if ( kk == 0 )
+		{
+			if ( !claim )
+				return 0xffffffffu ;
+			u64 old = t4_atomic_cas( &t.key[s], 0ull, key ) ;
+			if ( old == 0 || old == key )
+				return s ;
+		}
+		s = ( s + 1 ) & ( t.cap - 1 ) ;
+	}
+}
+
 // SeqSet::Clean(false) + ChangeKmerLength (SeqSet.hpp:4591-4629): compact the slots, rebuild the index.
 // nomatchGapLimit is computed on the host (pow/log) and passed in.
 T4_D inline void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
@@ -2896,6 +3036,8 @@ T4_D inline void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
 	for ( int i = 0 ; i < st->nSeqs ; ++i )
 	{
 		T4Contig *d = t4_seq( cx, i ) ;
+		if ( d->flags & T4_CF_NOINDEX ) // Clean(): `if (seqs[k].index)` (SeqSet.hpp:4616)
+			continue ;
 		c_index_op( cx, t4_cons( cx, d ), d->len, T4_IDX_BUILD, i, d->barcode, 0, 0 ) ;
 	}
 	T4_SYNC() ;
@@ -3981,6 +4123,38 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		rescueRet[i] = INT32_MIN ;
 	}
 	T4_SYNC() ;
+	// barcodeTotalReadCount (main.cpp:1572-1581), only when finished barcodes are purged
+	T4BcTable bc ;
+	bc.cap = 0 ;
+	const bool releaseBarcodes = cfg.has_barcode && cfg.release_barcodes && n > 0 ;
+	if ( releaseBarcodes )
+	{
+		u32 cap = 16 ;
+		while ( cap < 2u * (u32)n )
+			cap *= 2 ;
+		if ( cx.tid == 0 )
+			sm->bu[0] = s_alloc( cx, (u64)cap * 16 ) ;
+		T4_SYNC() ;
+		u64 off = sm->bu[0] ;
+		T4_SYNC() ;
+		if ( !off )
+			return ;
+		bc.cap = cap ;
+		bc.key = cx.P<u64>( off ) ;
+		bc.total = (u32 *)( bc.key + cap ) ;
+		bc.done = bc.total + cap ;
+		T4_PAR_FOR( i, cap )
+		{
+			bc.key[i] = 0 ;
+			bc.total[i] = 0 ;
+			bc.done[i] = 0 ;
+		}
+		T4_SYNC() ;
+		T4_PAR_FOR( i, n )
+			if ( descs[i].barcode != -1 )
+				t4_atomic_add32( &bc.total[t4_bc_slot( bc, descs[i].barcode, true )], 1 ) ;
+		T4_SYNC() ;
+	}
 	int assembledReadCnt = 0 ;
 	int prevAddRet = -1 ;
 	int indexKmerLength = st->kmerLength ;
@@ -4100,6 +4274,25 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		else if ( addRet >= 0 )
 			++assembledReadCnt ;
 		T4_SYNC() ;
+		// main.cpp:1846-1859 (inside `else if ( addRet >= 0 )`): a barcode is finished when as many of its reads were
+		// assembled as it has reads
+		if ( releaseBarcodes && addRet >= 0 && d.barcode != -1 )
+		{
+			if ( cx.tid == 0 )
+			{
+				u32 sl = t4_bc_slot( bc, d.barcode, false ) ;
+				sm->bi[0] = ( sl != 0xffffffffu && ++bc.done[sl] >= bc.total[sl] ) ? 1 : 0 ;
+			}
+			T4_SYNC() ;
+			const bool fin = sm->bi[0] != 0 ;
+			T4_SYNC() ;
+			if ( fin )
+			{
+				T4_PHASE( cx, 7 ) ;
+				c_release_barcode( cx, d.barcode, cfg.contig_min_cov ) ;
+				T4_PHASE( cx, 0 ) ;
+			}
+		}
 		if ( assembledReadCnt > 0 && cfg.update_consensus_every > 0 && assembledReadCnt % cfg.update_consensus_every == 0
 			&& !cfg.has_barcode )
 		{
@@ -4308,6 +4501,16 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			break ;
 		case T4_OP_CHANGE_K:
 			c_change_kmer_length( cx, op->kl, gapLimitTable[op->kl] ) ;
+			if ( cx.tid == 0 )
+				op->ret = 0 ;
+			break ;
+		case T4_OP_RELEASE_BARCODE:
+			c_release_barcode( cx, op->barcode, op->minKmerCount ) ;
+			if ( cx.tid == 0 )
+				op->ret = 0 ;
+			break ;
+		case T4_OP_RELEASE_SHALLOW:
+			c_release_shallow( cx, op->minKmerCount ) ;
 			if ( cx.tid == 0 )
 				op->ret = 0 ;
 			break ;

@@ -65,13 +65,15 @@ RUN_CFG = np.dtype(
         ("do_rescue", "<i4"),
         ("first_read_len", "<i4"),
         ("final_update", "<i4"),
+        ("release_barcodes", "<i4"),
+        ("contig_min_cov", "<i4"),
         ("reserved_", "<i4"),
     ]
 )
 
 
 def run_cfg(has_barcode=0, repetitive=0, change_k_threshold=4096, update_consensus_every=10000, do_rescue=1,
-            first_read_len=150, final_update=1):
+            first_read_len=150, final_update=1, release_barcodes=0, contig_min_cov=0):
     c = np.zeros(1, dtype=RUN_CFG)
     c["has_barcode"] = has_barcode
     c["repetitive"] = repetitive
@@ -80,6 +82,8 @@ def run_cfg(has_barcode=0, repetitive=0, change_k_threshold=4096, update_consens
     c["do_rescue"] = do_rescue
     c["first_read_len"] = first_read_len
     c["final_update"] = final_update
+    c["release_barcodes"] = release_barcodes
+    c["contig_min_cov"] = contig_min_cov
     return c
 
 
