@@ -4,16 +4,16 @@
 Workload (BASELINE.json configs[1]): 1 M synthetic 150 bp pairs (2 M reads) per GPU against the IMGT gene
 set, k = 9, read-sharded into S independent streams (contiguous shards of the sorted read
 list, one SeqSet each; parity is per shard).  A step = one pass of the whole loop over the whole workload:
-fresh streams -> stream kernel -> results.
+fresh streams -> stream kernel -> packed contigs (-> all-gather when N > 1).
 
   value      inputs resident in HBM, CUDA-event time over K steps (max over ranks)
-  e2e        the same through t4_streams_run with pinned HOST buffers: H2D of records + reads and D2H of
-             the per-read results inside the timed region
-  roofline   the stream kernel (the only hot kernel of a step): algorithmic bytes from the
-             device counters / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs;
-             roofline_probe: the standalone probe kernel (GetHitsFromRead only) over the final contig sets
+  e2e        the same through t4_streams_run with pinned HOST buffers: H2D of records + reads, D2H of the per-read
+             results AND of the packed contigs (the product of stage 1) inside the timed region
+  roofline   the stream kernel (the hot kernel of a step): algorithmic bytes from the device counters /
+             its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  roofline_probe   the dedicated k-mer probe kernel (t4_probe_kernel: GetHitsFromRead of all reads over the final sets)
   cpu_baseline / --impl reference: the reference's own SeqSet (oracle/_ref/libt4ref.so, compiled from the
-             reference sources) driven over the same shards on the host cores, bounded sample.
+             reference sources) driven over a uniform sample of the same shards on the host cores.
 """
 import argparse
 import ctypes as C
@@ -30,8 +30,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+REQUIRED_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                 "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "roofline_probe", "cpu_baseline")
 
-def parse():
+
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -45,7 +48,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
     ap.add_argument("--deal", action="store_true", help="deal runs of identical reads round-robin to the streams instead of contiguous shards")
-    return ap.parse_args()
+    ap.add_argument("--balance", default=os.environ.get("T4_BENCH_BALANCE", "cost"), choices=["reads", "cost"],
+                    help="contiguous shards of equal read count, or of equal predicted cost (abundance model, synth.read_cost)")
+    ap.add_argument("--dump-streams", default="", help="write per-stream cycles + features (npz) for cost-model calibration")
+    return ap.parse_args(argv)
 
 
 def dist_env():
@@ -61,7 +67,7 @@ def make_workload(args, rank, device):
     cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
     rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
     w = synth.build_workload(cl, rd, device=device)
-    off, descs = synth.shard_workload(w, args.streams, deal=args.deal)
+    off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance)
     return w, off, descs
 
 
@@ -109,8 +115,17 @@ class ClockSampler:
         return out
 
 
-def reference_sample(args, w, off, descs, budget_s, cores):
-    """The reference's SeqSet over the first shards of the workload on `cores` host threads for ~budget_s."""
+def sample_order(n_shards):
+    """Visit order of the reference sample: a fixed pseudo-random permutation, so that whatever prefix the time budget
+    allows is a uniform sample over the shard index range (the sorted read list runs from cheap high-abundance shards
+    to expensive singleton shards; a prefix of the index order would be biased)."""
+    return np.random.default_rng(12345).permutation(n_shards)
+
+
+def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
+    """The reference's SeqSet over a uniform sample of the shards on `cores` host threads for ~budget_s.
+    reads/s = sum(reads of the sampled shards) / wall: with a uniform shard sample this estimates
+    total_reads / total_cpu_time_on_cores for the whole workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refharness as rh
     from trust4_b200 import synth
@@ -118,26 +133,31 @@ def reference_sample(args, w, off, descs, budget_s, cores):
         return None
     cfg = synth.run_cfg()
     n_shards = len(off) - 1
+    order = sample_order(n_shards)
     lock = threading.Lock()
-    state = {"next": 0, "reads": 0, "shards": 0, "codes": {}}
+    state = {"next": 0, "reads": 0, "shards": 0, "kept": {}}
     t0 = time.perf_counter()
 
     def worker():
         while True:
             with lock:
-                j = state["next"]
-                if j >= n_shards or time.perf_counter() - t0 > budget_s:
+                x = state["next"]
+                if x >= n_shards or time.perf_counter() - t0 > budget_s:
                     return
                 state["next"] += 1
+            j = int(order[x])
             lo, hi = int(off[j]), int(off[j + 1])
             r = rh.RefSeqSet(9)
             out = r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)     # ctypes releases the GIL
+            rec = None
+            if x < keep:                                                     # the first `keep` of the order: full parity record
+                rec = (out[1], out[3], r.output(), r.index_checksum())
             r.close()
             with lock:
                 state["reads"] += hi - lo
                 state["shards"] += 1
-                if len(state["codes"]) < 256:
-                    state["codes"][j] = (out[1], out[3])     # AddRead-loop and rescue return codes of this shard
+                if rec is not None:
+                    state["kept"][j] = rec
 
     th = [threading.Thread(target=worker) for _ in range(cores)]
     for t in th:
@@ -145,11 +165,23 @@ def reference_sample(args, w, off, descs, budget_s, cores):
     for t in th:
         t.join()
     el = time.perf_counter() - t0
-    reference_sample.codes = state["codes"]
+    reference_sample.kept = state["kept"]
     return {"value": state["reads"] / el, "unit": "reads/s", "cores": cores, "kind": "reference",
-            "sample": "first %d of %d read shards (%d reads) of the same workload, %.1f s wall on %d threads; "
-                      "oracle/_ref/libt4ref.so = reference SeqSet::AddRead/RepeatAddRead/InputNovelRead driven by the "
+            "sample": "%d of %d read shards (%d reads), uniformly sampled over the shard index range (fixed permutation), %.1f s wall "
+                      "on %d threads; oracle/_ref/libt4ref.so = reference SeqSet::AddRead/RepeatAddRead/InputNovelRead driven by the "
                       "restated main.cpp loop" % (state["shards"], n_shards, state["reads"], el, cores)}
+
+
+def build_line(args, config, value, ms_per_step, clocks, e2e, launches, roofline, roofline_probe, cpu, extra):
+    """The ONE JSON line of the contract.  Kept as a pure function so that a unit test can assert its keys."""
+    line = {"metric": "reads/sec assembled (150bp PE)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu}
+    line.update(extra)
+    for k in REQUIRED_KEYS:
+        assert k in line, k
+    return line
 
 
 def main():
@@ -158,10 +190,12 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     cores = os.cpu_count() or 1
+    mode = "dealt round-robin" if args.deal else ("in contiguous blocks of the sorted list, block sizes equalising the predicted cost (abundance model)"
+                                                   if args.balance == "cost" else "in contiguous blocks of the sorted list, equal read counts")
     config = {"workload": "configs[1]: %d synthetic 150bp PE pairs (%d reads) per GPU vs human_IMGT+C gene pool, k=9, "
                           "read-sharded into %d streams per GPU (runs of identical reads %s; one SeqSet each, per-shard parity, SURVEY.md 8e)"
-                          % (args.pairs, 2 * args.pairs, args.streams, "dealt round-robin" if args.deal else "in contiguous blocks of the sorted list"),
-              "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150,
+                          % (args.pairs, 2 * args.pairs, args.streams, mode),
+              "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150, "shard_balance": "deal" if args.deal else args.balance,
               "l2": "inputs (>= 400 MB of reads + records, GBs of stream state) exceed the 126 MB L2",
               "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective; "
                           "N>1: one NCCL all-gather of the packed per-rank contig sets per step (merge step)"}
@@ -180,7 +214,7 @@ def main():
         per_step = max(2.0, min(args.ref_seconds, 150.0 / max(1, args.steps + args.warmup)))
         vals = []
         for it in range(args.warmup + args.steps):
-            s = reference_sample(args, w, off, descs, per_step, cores)
+            s = reference_sample(args, w, off, descs, per_step, cores, keep=0)
             if s is None:
                 print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libt4ref.so not built"}))
                 return
@@ -223,41 +257,50 @@ def main():
     strands = torch.zeros(n_reads, dtype=torch.int8).pin_memory()
     resc = torch.zeros(n_reads, dtype=torch.int32).pin_memory()
     h2d_bytes = pin_descs.numel() + pin_pool.numel() + S * 256
-    d2h_bytes = n_reads * 9
 
     wl = lib.workload_upload(pin_descs.data_ptr(), n_reads, pin_pool.data_ptr(), pin_pool.numel(), names_arr, len(w.names))
     if not wl:
         raise RuntimeError(lib.err())
     handles = (C.c_void_p * S)()
 
-    merged = {"bytes": 0, "contigs": 0}
+    merged = {"bytes": 0, "contigs": 0, "pack_bytes": 0}
+    pack = {"buf": None, "host": None}
 
-    def merge_exchange():
-        """Merge step of a read-sharded multi-GPU run: pack this rank's contigs on the device and all-gather them
-        over NCCL (sizes first, then the padded payload); every rank ends up with all contig sets."""
+    def pack_contigs():
+        """Stage-1 product: every live contig of this rank, packed on the device into one buffer."""
+        need, nc = C.c_size_t(), C.c_int64()
+        lib.check(lib.streams_pack_contigs(handles, S, None, 0, C.byref(need), C.byref(nc)))
+        if pack["buf"] is None or pack["buf"].numel() < need.value:
+            pack["buf"] = torch.empty(int(need.value * 1.1) + 1024, dtype=torch.uint8, device=dev)
+        lib.check(lib.streams_pack_contigs(handles, S, pack["buf"].data_ptr(), pack["buf"].numel(), C.byref(need), C.byref(nc)))
+        merged["contigs"] = int(nc.value)
+        merged["pack_bytes"] = int(need.value)
+        return pack["buf"][: need.value]
+
+    def merge_exchange(buf):
+        """Merge step of a read-sharded multi-GPU run: all-gather the packed contig sets over NCCL."""
         if world == 1:
             return
         from trust4_b200 import dist as tdist
-        need, nc = C.c_size_t(), C.c_int64()
-        lib.check(lib.streams_pack_contigs(handles, S, None, 0, C.byref(need), C.byref(nc)))
-        buf = torch.empty(max(16, need.value), dtype=torch.uint8, device=dev)
-        lib.check(lib.streams_pack_contigs(handles, S, buf.data_ptr(), buf.numel(), C.byref(need), C.byref(nc)))
-        parts = tdist.allgather_contigs(buf[: need.value])
+        parts = tdist.allgather_contigs(buf)
         merged["bytes"] = int(sum(p.numel() for p in parts))
-        merged["contigs"] = int(nc.value)
 
     def step_resident():
         lib.check(lib.reset())
         lib.check(lib.seqsets_create(S, 9, handles))
         lib.check(lib.streams_run_resident(handles, S, cfg.ctypes.data, wl, off64.ctypes.data, None))
-        merge_exchange()
+        merge_exchange(pack_contigs())
 
     def step_e2e():
         lib.check(lib.reset())
         lib.check(lib.seqsets_create(S, 9, handles))
         lib.check(lib.streams_run(handles, S, cfg.ctypes.data, pin_descs.data_ptr(), off64.ctypes.data, pin_pool.data_ptr(),
                                   pin_pool.numel(), names_arr, len(w.names), ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
-        merge_exchange()
+        buf = pack_contigs()
+        if pack["host"] is None or pack["host"].numel() < buf.numel():
+            pack["host"] = torch.empty(int(buf.numel() * 1.1) + 1024, dtype=torch.uint8).pin_memory()
+        pack["host"][: buf.numel()].copy_(buf, non_blocking=True)          # the contigs cross PCIe inside the timed region
+        merge_exchange(buf)
 
     def barrier():
         if world > 1:
@@ -288,9 +331,6 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
-    counters = np.zeros(api.N_COUNTERS, dtype=np.uint64)
-    lib.check(lib.last_counters(counters.ctypes.data))
-    assembled = None
     lib.check(lib.workload_results(wl, ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
     assembled = int((ret >= 0).sum().item() + (resc >= 0).sum().item())
 
@@ -312,8 +352,12 @@ def main():
     cyc = np.zeros(S, dtype=np.uint64)
     lib.check(lib.streams_cycles(handles, S, cyc.ctypes.data))
     cycf = cyc.astype(np.float64)
+    if args.dump_streams and rank == 0:
+        lib.check(lib.workload_results(wl, ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
+        np.savez_compressed(args.dump_streams, cycles=cyc, off=off64, flags=descs["flags"], min_cnt=descs["min_cnt"], eq_lo=descs["eq_lo"],
+                            eq_hi=descs["eq_hi"], ret=ret.numpy().copy())
     balance = {"mean_ms": float(cycf.mean() / 1.965e6), "max_ms": float(cycf.max() / 1.965e6), "p50_ms": float(np.median(cycf) / 1.965e6),
-               "p99_ms": float(np.percentile(cycf, 99) / 1.965e6),
+               "p99_ms": float(np.percentile(cycf, 99) / 1.965e6), "reads_per_stream_min_max": [int(np.diff(off64).min()), int(np.diff(off64).max())],
                "by_decile_of_stream_index_ms": [float(x.mean() / 1.965e6) for x in np.array_split(cycf, 10)]}
     # probe ceil(L/4) + sum(8 + 8 c_j) + 16 sum c_j'; chain 2 x 16 sum c_j'; commit 8 L per assembled read
     b_probe = dc[5] + 8 * dc[2] + 8 * dc[3] + 16 * dc[4]
@@ -327,81 +371,128 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # DRAM traffic of this kernel from the committed ncu --set full capture of the default workload (profiles/)
-    traffic = None
-    try:
-        if args.pairs == 1000000 and args.streams == 4096 and not args.deal:
+
+    def ncu_traffic(fname):
+        """DRAM bytes (read + write) of a kernel from a committed ncu --set full raw page of the default workload."""
+        try:
+            if args.pairs != 1000000 or args.streams != 4096 or args.deal:
+                return None
             import csv
-            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_stream_kernel_full_raw.csv"))))
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", fname))))
             hdr, units, vals = rows[0], rows[1], rows[2]
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-            traffic = sum(float(vals[hdr.index(m)]) * scale[units[hdr.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    except Exception:
-        traffic = None
+            return sum(float(vals[hdr.index(m)]) * scale[units[hdr.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except Exception:
+            return None
+
+    traffic_file = "r2_stream_kernel_full_raw.csv" if os.path.exists(os.path.join(ROOT, "profiles", "r2_stream_kernel_full_raw.csv")) else "r1_stream_kernel_full_raw.csv"
+    traffic = ncu_traffic(traffic_file)
     ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "t4_stream_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1_stream_kernel_full_raw.csv (ncu --set full, same workload)" if traffic else None,
+                "traffic": traffic, "traffic_source": ("profiles/%s (ncu --set full, same workload)" % traffic_file) if traffic else None,
                 "algorithmic_bytes_total": alg_bytes, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "algorithmic_bytes": {"probe": b_probe, "chain": b_chain, "commit": b_commit},
                 "per_read": {"lookups": dc[2] / n_reads, "hits": dc[4] / n_reads, "overlaps_scored": dc[6] / n_reads, "gap_dps": dc[7] / n_reads,
-                             "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads,
-                             "ext_cycles_stage_dp_tail_per_overlap": [dc[17] / max(1, dc[16]), dc[18] / max(1, dc[16]), dc[19] / max(1, dc[16])],
-                             "ext_dp_rows_per_overlap": dc[20] / max(1, dc[16])},
+                             "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads},
                 "stream_balance": balance, "phase_share": dict(zip(["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"],
                                         [round(float(x), 4) for x in (dc[8:16] / max(1.0, dc[8:16].sum()))]))}
 
+    # ---- the dedicated probe kernel over the final sets of this very run
     roofline_probe = None
     if not args.no_probe:
-        pb, ph = C.c_uint64(), C.c_uint64()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        lib.check(lib.probe_resident(handles, S, wl, off64.ctypes.data, None, None, None))     # warm
-        torch.cuda.synchronize()
-        p0.record()
-        lib.check(lib.probe_resident(handles, S, wl, off64.ctypes.data, None, None, None))
-        p1.record()
-        torch.cuda.synchronize()
-        pms = p0.elapsed_time(p1)
-        lib.check(lib.probe_resident(handles, S, wl, off64.ctypes.data, None, C.byref(pb), C.byref(ph)))
-        a = pb.value / (pms * 1e-3) / 1e9
-        roofline_probe = {"bound": "hbm", "kernel": "t4_stream_kernel<PROBE_ONLY> (GetHitsFromRead over the final contig sets)",
-                          "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "kernel_ms": pms,
-                          "algorithmic_bytes": pb.value, "hits": ph.value, "reads_per_s": n_reads / (pms * 1e-3)}
+        cap = int(2.2e9 if n_reads >= 1000000 else max(1 << 22, 2000 * n_reads))
+        st = np.zeros(8, dtype=np.uint64)
+        hits = None
+        for attempt in range(2):
+            hits = lib.hits_create(n_reads, cap)
+            if not hits:
+                raise RuntimeError(lib.err())
+            lib.check(lib.streams_get_hits(handles, S, wl, off64.ctypes.data, 0, None, hits))      # warm-up + sizing
+            r = lib.hits_stats(hits, st.ctypes.data)
+            if r == api.T4_E_NOMEM and attempt == 0:
+                need = int(lib.err().split(":")[1].split()[0])
+                lib.hits_free(hits)
+                cap = int(need * 1.02) + 1024
+                continue
+            lib.check(r)
+            break
+        pms = []
+        for _ in range(3):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            p0.record()
+            lib.check(lib.streams_get_hits(handles, S, wl, off64.ctypes.data, 0, None, hits))
+            p1.record()
+            torch.cuda.synchronize()
+            pms.append(p0.elapsed_time(p1))
+        lib.check(lib.hits_stats(hits, st.ctypes.data))
+        lib.hits_free(hits)
+        pm = float(np.median(pms))
+        a = float(st[4]) / (pm * 1e-3) / 1e9
+        a16 = float(st[5]) / (pm * 1e-3) / 1e9
+        roofline_probe = {"bound": "hbm", "kernel": "t4_probe_kernel (+ t4_bucket_kernel): GetHitsFromRead of every read over the final contig sets, warp per read",
+                          "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "kernel_ms": pm, "kernel_ms_all": pms,
+                          "algorithmic_bytes": int(st[4]),
+                          "algorithmic_bytes_note": "SURVEY.md 8d with the 8-byte hit key this kernel writes: ceil(L/4) + 8 lookups + 8 postings + 8 hits",
+                          "achieved_with_16B_hits": a16, "frac_with_16B_hits": a16 / peak,
+                          "hits": int(st[0]), "lookups": int(st[1]), "postings": int(st[2]), "reads_per_s": n_reads / (pm * 1e-3),
+                          "traffic": ncu_traffic("r2_probe_kernel_full_raw.csv"),
+                          "l2_note": "reads are visited set by set, so directory and postings sectors of a set are re-used from L2"}
 
-    # e2e leg
-    for _ in range(1):
-        step_e2e()
+    # ---- e2e leg, with separately timed copies
+    step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     e2e_assembled = int((ret >= 0).sum().item() + (resc >= 0).sum().item())
     assert e2e_assembled == assembled, (e2e_assembled, assembled)
+    d2h_bytes = n_reads * 9 + merged["pack_bytes"]
+    dpool = torch.empty(pin_pool.numel() + pin_descs.numel(), dtype=torch.uint8, device=dev)
+    x0, x1, x2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    x0.record()
+    dpool[: pin_pool.numel()].copy_(pin_pool, non_blocking=True)
+    dpool[pin_pool.numel():].copy_(pin_descs, non_blocking=True)
+    x1.record()
+    pack["host"][: merged["pack_bytes"]].copy_(pack["buf"][: merged["pack_bytes"]], non_blocking=True)
+    x2.record()
+    torch.cuda.synchronize()
+    copies = {"h2d_ms": x0.elapsed_time(x1), "h2d_gbs": (pin_pool.numel() + pin_descs.numel()) / x0.elapsed_time(x1) / 1e6,
+              "d2h_contigs_ms": x1.elapsed_time(x2), "d2h_contigs_gbs": merged["pack_bytes"] / max(1e-6, x1.elapsed_time(x2)) / 1e6}
+    del dpool
 
     value = world * n_reads * args.steps / (ms * 1e-3)
     e2e = world * n_reads * args.steps / (ms_e2e * 1e-3)
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             cpu = reference_sample(args, w, off, descs, args.ref_seconds, cores)
-        # the CPU baseline leg doubles as a full-scale spot check: the reference's return codes of the shards it
-        # processed must equal what the GPU produced for the same shards in the e2e leg
+        # the CPU baseline leg doubles as a full-scale parity check: for the first shards of the sample the reference's return
+        # codes, rescue codes, Output text and index checksum must equal what the GPU produced in the e2e leg
         parity = None
         try:
-            codes = getattr(reference_sample, "codes", {}) if cpu else {}
-            if codes:
+            kept = getattr(reference_sample, "kept", {}) if cpu else {}
+            if kept:
                 gret, gres = ret.numpy(), resc.numpy()
-                okc = all((gret[int(off[j]):int(off[j + 1])] == c[0]).all() and (gres[int(off[j]):int(off[j + 1])] == c[1]).all()
-                          for j, c in codes.items())
-                parity = {"shards_checked": len(codes), "return_codes_equal_reference": bool(okc)}
+                bad = []
+                for j, (rret, rres, rout, rsum) in kept.items():
+                    lo, hi = int(off[j]), int(off[j + 1])
+                    g = api.SeqSet(9, lib, handles[j])
+                    ok = (gret[lo:hi] == rret).all() and (gres[lo:hi] == rres).all() and g.output() == rout and g.index_checksum() == rsum
+                    if not ok:
+                        bad.append(int(j))
+                parity = {"shards_checked": len(kept), "checked": "return codes, rescue codes, Output text, index checksum",
+                          "equal_reference": len(bad) == 0, "bad_shards": bad[:8]}
         except Exception as ex:      # never let the checker break the measurement
             parity = {"error": str(ex)[:200]}
-        line = {"metric": "reads/sec assembled (150bp PE)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int32", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                        "ms_per_step": ms_e2e / args.steps},
-                # init + stream kernel (+ pack-size + pack when N > 1)
-                "gpu_launches": (2 + (2 if world > 1 else 0)) * args.steps,
-                "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu,
-                "assembled_reads": assembled, "reads_per_gpu": n_reads, "parity_spot_check": parity, "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
-                "threads_per_stream": int(os.environ.get("T4_NT", 128))}
+        line = build_line(
+            args, config, value, ms / args.steps, clocks,
+            {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+             "ms_per_step": ms_e2e / args.steps, "copies": copies,
+             "d2h_note": "per-read return codes (9 B/read) + the packed contigs of every stream (consensus, posWeight, names)"},
+            # init + stream kernel + pack-size + pack per step
+            4 * args.steps, roofline, roofline_probe, cpu,
+            {"assembled_reads": assembled, "reads_per_gpu": n_reads, "contigs_per_gpu": merged["contigs"], "parity_spot_check": parity,
+             "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
+             "threads_per_stream": int(os.environ.get("T4_NT", 128))})
         print(json.dumps(line))
     lib.workload_free(wl)
     if world > 1:

@@ -239,11 +239,29 @@ int64_t t4_seqset_index_checksum(t4_seqset *s, uint64_t *checksum);
 #define T4_N_COUNTERS 24
 int t4_last_counters(uint64_t *counters /* T4_N_COUNTERS */);
 
-/* Standalone probe kernel over frozen sets (roofline measurement):
- * reads of the workload are probed against the set of their stream, hits written to HBM.
- * Returns 0; kernel time is measured by the caller with CUDA events on cuda_stream. */
-int t4_probe_resident(t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off,
-                      void *cuda_stream, uint64_t *algorithmic_bytes, uint64_t *hits_emitted);
+/* ---- batch k-mer probe over frozen sets (the north-star "k-mer probe kernel") ----------------------------
+ * SeqSet::GetHitsFromRead (SeqSet.hpp:1341-1501) + KmerIndex::Search (KmerIndex.hpp:104) for every record of an uploaded
+ * workload against the set of its stream (record i belongs to set j iff desc_off[j] <= i < desc_off[j+1]; desc_off[0]
+ * must be 0), with the record's strand_in and barcode.  The sets are only read: reads are independent, so this runs
+ * one warp per read over the whole GPU (2-bit packed reads, 256-bit directory probes, TMA-staged postings) instead of
+ * one CTA per set.  Results stay on the device in `out` (hit keys + per-record offset/count); the launch is
+ * asynchronous on cuda_stream.  Consumers: read-only passes over finished contigs (AssignRead, SeqSet.hpp:4632, is the
+ * next one) and the roofline measurement of SURVEY.md 8d. */
+typedef struct t4_hits t4_hits;
+t4_hits *t4_hits_create(int64_t max_records, size_t max_hits);
+void t4_hits_free(t4_hits *h);
+int t4_streams_get_hits(t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off,
+                        int allow_total_skip, void *cuda_stream, t4_hits *out);
+/* Totals of the last probe (synchronises): stats[0] hits written (sum c_j'), [1] lookups executed, [2] postings read
+ * (sum c_j), [3] packed read bytes, [4] algorithmic bytes of SURVEY.md 8d with the 8-byte hit key really written,
+ * [5] the same with the survey's nominal 16-byte hit, [6] records longer than T4_MAX_READ_LEN (skipped), [7] records.
+ * Returns T4_E_NOMEM (and the needed key count in t4_last_error) when `max_hits` was too small. */
+int t4_hits_stats(t4_hits *h, uint64_t stats[8]);
+/* Hits of one record as int32[4] = {seqIdx, seqOffset, readOffset, strand}, in read-position order (forward pass
+ * first); returns their number (may exceed cap).  *flags bit 0: some k-mer has more than 10000 postings. */
+int t4_hits_fetch(t4_hits *h, int64_t record, int32_t *hits, int cap, int *flags);
+/* Device pointers of the result for device-side consumers: u64 keys[], u64 hit_off[records], u32 hit_cnt[records]. */
+int t4_hits_device_buffers(t4_hits *h, void **keys, void **hit_off, void **hit_cnt);
 
 #ifdef __cplusplus
 }

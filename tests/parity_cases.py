@@ -55,6 +55,107 @@ def check_batch_vs_ref(lib, ref, seed, n_shards, nclones=25, npairs=400, cfg=Non
     return int((ret >= 0).sum())
 
 
+def _canon4(h):
+    if len(h) == 0:
+        return h[:, :4]
+    h = h[:, :4]
+    return h[np.lexsort((h[:, 1], h[:, 2], h[:, 0], h[:, 3]))]
+
+
+def _ragged_records(rng, sources, n, kmer=9):
+    """Probe records of mixed lengths (shorter than k .. 400 bp: the probe tiles 288 positions), N's, all strand modes."""
+    reads, descs = [], np.zeros(n, dtype=synth.READ_DESC)
+    off = 0
+    for i in range(n):
+        src = sources[int(rng.integers(len(sources)))]
+        L = int(rng.choice([5, kmer - 1, kmer, kmer + 1, 31, 64, 100, 144, 145, 150, 152, 153, 200, 290, 400]))
+        while len(src) < L:
+            src = src + sources[int(rng.integers(len(sources)))]
+        a = int(rng.integers(0, len(src) - L + 1))
+        s = list(src[a:a + L])
+        for _ in range(int(rng.integers(0, 4))):
+            s[int(rng.integers(L))] = "ACGTN"[int(rng.integers(5))]
+        if rng.random() < 0.15:
+            p0 = int(rng.integers(L))
+            s[p0:p0 + 14] = list("A" * len(s[p0:p0 + 14]))                             # homopolymer: equal consecutive k-mers
+        s = "".join(s)
+        assert len(s) == L
+        if rng.random() < 0.4:
+            s = "".join({"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}[c] for c in reversed(s))
+        reads.append(s)
+        descs[i]["seq_off"] = off
+        descs[i]["len"] = L
+        descs[i]["barcode"] = -1
+        descs[i]["strand_in"] = int(rng.choice([0, 0, 1, -1]))
+        off += L
+    pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    return reads, descs, pool
+
+
+def check_probe_batch(lib, ref, seed=41, n_shards=5, sample=160):
+    """t4_streams_get_hits (the grid-wide warp-per-read probe: 2-bit packed reads, directory + postings over frozen sets)
+    against SeqSet::GetHitsFromRead of the reference on the same sets: hit multisets per record, for the assembled reads
+    of every shard and for ragged records (lengths 5..400, N's, homopolymers, both strands, strand -1/0/+1 modes)."""
+    lib.check(lib.reset())
+    w = small_workload(seed, 25, 500)
+    cfg = synth.run_cfg()
+    off, descs = synth.shard_workload(w, n_shards)
+    sets = api.SeqSet.create_many(n_shards, 9, lib)
+    api.streams_run(sets, cfg, descs, off, w.pool, w.names, lib)
+    refs = []
+    for j in range(n_shards):
+        r = ref.RefSeqSet(9)
+        r.run_descs(cfg, descs[int(off[j]):int(off[j + 1])].copy(), w.pool, w.names)
+        assert r.index_checksum() == sets[j].index_checksum()
+        refs.append(r)
+    rng = np.random.default_rng(seed)
+    # (1) the workload's own records
+    wl = api.Workload(descs, w.pool, w.names, lib)
+    hits = api.Hits(len(descs), 4 << 20, lib)
+    api.streams_get_hits(sets, wl, off, hits)
+    st = hits.stats()
+    assert st["records"] == len(descs) and st["hits"] > 1000 and st["unsupported"] == 0
+    reads = w.pool[: len(w.descs) * w.L].reshape(-1, w.L)
+    total = 0
+    for i in rng.choice(len(descs), size=min(sample, len(descs)), replace=False):
+        j = int(np.searchsorted(off, i, side="right") - 1)
+        d = descs[i]
+        rd = bytes(w.pool[int(d["seq_off"]):int(d["seq_off"]) + int(d["len"])]).decode()
+        hr = _canon4(refs[j].get_hits(rd, int(d["strand_in"]), int(d["barcode"])))
+        hg, _ = hits.fetch(int(i))
+        hg = _canon4(hg)
+        assert hr.shape == hg.shape and (hr == hg).all(), ("probe", int(i), j, hr.shape, hg.shape)
+        total += len(hr)
+    assert total > 100
+    wl.close()
+    # (2) ragged records against the same frozen sets
+    srcs = []
+    for j in range(n_shards):
+        for line in sets[j].output().split(b"\n"):
+            if line and line[:1] in b"ACGT" and len(line) > 60 and b" " not in line:
+                srcs.append(line.decode())
+    assert len(srcs) >= n_shards
+    n = 300
+    rreads, rdescs, rpool = _ragged_records(rng, srcs, n)
+    roff = np.linspace(0, n, n_shards + 1).astype(np.int64)
+    wl = api.Workload(rdescs, rpool, [], lib)
+    for skip in (0, 1):
+        api.streams_get_hits(sets, wl, roff, hits, allow_total_skip=skip)
+        st = hits.stats()
+        assert st["records"] == n
+        nz = 0
+        for i in range(n):
+            j = int(np.searchsorted(roff, i, side="right") - 1)
+            hr = _canon4(refs[j].get_hits(rreads[i], int(rdescs[i]["strand_in"]), -1, bool(skip)))
+            hg, _ = hits.fetch(i)
+            hg = _canon4(hg)
+            assert hr.shape == hg.shape and (hr == hg).all(), ("ragged", i, len(rreads[i]), int(rdescs[i]["strand_in"]), hr.shape, hg.shape)
+            nz += len(hr) > 0
+        assert nz > n // 3
+    wl.close()
+    hits.close()
+
+
 def check_stage_parity(lib, ref, name="synth2k", every=97, max_checks=60):
     """k-mer hits (after SortHits) and scored overlaps of individual reads against a frozen snapshot:
     replay the golden trace on both sides and compare the stage outputs at sampled AddRead calls."""
@@ -266,6 +367,28 @@ def check_big_repeats(lib, ref, n_copies=10050):
                 assert (o1 == o2).all() and (s1 == s2).all()
         assert g.add_read(q, "IGHV", 0, -1, 1, 0, 0.9) == r.add_read(q, "IGHV", 0, -1, 1, 0, 0.9)
     assert g.index_checksum() == r.index_checksum()
+    # the batch probe on the same set: lists of > 10000 postings (streamed, `repeats > 10000` flag), the >= 100 rules
+    qs = [base[10:110] + other[:50], other[:60] + base[:90], base[:100], other, base + other + base[:60]]
+    d = np.zeros(2 * len(qs), dtype=synth.READ_DESC)
+    o = 0
+    for i, q in enumerate(qs + qs):
+        d[i]["seq_off"], d[i]["len"], d[i]["barcode"], d[i]["strand_in"] = o, len(q), -1, 0 if i < len(qs) else 1
+        o += len(q)
+    pool = np.frombuffer(("".join(qs + qs) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    wl = api.Workload(d, pool, [], lib)
+    hits = api.Hits(len(d), 24 << 20, lib)
+    for skip in (0, 1):
+        api.streams_get_hits([g], wl, [0, len(d)], hits, allow_total_skip=skip)
+        assert hits.stats()["records"] == len(d)       # also raises when the key buffer was too small
+        for i, q in enumerate(qs + qs):
+            hr = _canon4(r.get_hits(q, int(d[i]["strand_in"]), -1, bool(skip)))
+            hg, fl = hits.fetch(i)
+            hg = _canon4(hg)
+            assert hr.shape == hg.shape and (hr == hg).all(), ("big probe", i, skip)
+            if skip == 0 and q is not other:
+                assert fl & 1
+    wl.close()
+    hits.close()
 
 
 def check_barcode_mode(lib, ref, seed=31, n_barcodes=5):

@@ -29,6 +29,11 @@ def test_emu_dp(emu_lib, ref):
     pc.check_dp_hot(emu_lib, ref, 11, 0)      # t4_dp_equal, the register DP of the hot path (host-compilable)
 
 
+def test_emu_probe_batch(emu_lib, ref):
+    """API plumbing of t4_streams_get_hits (the emulation answers through the engine's own GetHitsFromRead)."""
+    pc.check_probe_batch(emu_lib, ref, sample=60)
+
+
 def test_emu_big_repeats(emu_lib, ref):
     pc.check_big_repeats(emu_lib, ref)
 

@@ -104,3 +104,9 @@ def test_gpu_barcode_release(gpu_lib, ref):
 
 def test_gpu_input_novel_fa(gpu_lib, ref, tmp_path):
     pc.check_input_novel_fa(gpu_lib, ref, tmp_path)
+
+
+def test_gpu_probe_batch(gpu_lib, ref):
+    """The dedicated warp-per-read probe kernel (t4_probe_kernel) vs the reference's GetHitsFromRead."""
+    pc.check_probe_batch(gpu_lib, ref, seed=41, n_shards=5)
+    pc.check_probe_batch(gpu_lib, ref, seed=42, n_shards=1, sample=120)

@@ -30,7 +30,8 @@ EXPORTS = [
     "seqset_output", "seqset_output_mem", "free", "seqset_get_contig", "has_motif",
     "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch", "dp_hot_path_batch",
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
-    "streams_run_resident", "workload_results", "last_counters", "probe_resident", "streams_error",
+    "streams_run_resident", "workload_results", "last_counters", "streams_error",
+    "hits_create", "hits_free", "streams_get_hits", "hits_stats", "hits_fetch", "hits_device_buffers",
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
     "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
 ]
@@ -95,7 +96,12 @@ class Lib:
         f("streams_run_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, vp])
         f("workload_results", ci, [vp, vp, vp, vp])
         f("last_counters", ci, [vp])
-        f("probe_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+        f("hits_create", vp, [C.c_int64, C.c_size_t])
+        f("hits_free", None, [vp])
+        f("streams_get_hits", ci, [C.POINTER(vp), ci, vp, vp, ci, vp, vp])
+        f("hits_stats", ci, [vp, vp])
+        f("hits_fetch", ci, [vp, C.c_int64, vp, ci, C.POINTER(ci)])
+        f("hits_device_buffers", ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)])
         f("streams_error", ci, [C.POINTER(vp), ci])
         f("seqset_index_checksum", C.c_int64, [vp, C.POINTER(C.c_uint64)])
         f("streams_cycles", ci, [C.POINTER(vp), ci, vp])
@@ -334,3 +340,59 @@ def dp_hot_path_batch(problems, variant, lib: Lib | None = None):
             e.append(int(v))
         out.append((int(score[i]), e))
     return out
+
+
+class Workload:
+    """Device-resident copy of a record list + read pool (t4_workload_upload); reads are 2-bit packed on upload."""
+
+    def __init__(self, descs, pool, names, lib: Lib | None = None):
+        self.lib = lib or default_lib()
+        self.descs = np.ascontiguousarray(descs)
+        self.pool = np.ascontiguousarray(pool)
+        self.n = len(self.descs)
+        self.h = self.lib.workload_upload(self.descs.ctypes.data, self.n, self.pool.ctypes.data, self.pool.nbytes,
+                                          _names_array(names), len(names))
+        if not self.h:
+            raise T4Error(T4_E_NOMEM, self.lib.err())
+
+    def close(self):
+        if self.h:
+            self.lib.workload_free(self.h)
+            self.h = None
+
+
+class Hits:
+    """Result buffers of t4_streams_get_hits (device resident)."""
+
+    def __init__(self, max_records, max_hits, lib: Lib | None = None):
+        self.lib = lib or default_lib()
+        self.h = self.lib.hits_create(max_records, max_hits)
+        if not self.h:
+            raise T4Error(T4_E_NOMEM, self.lib.err())
+
+    def close(self):
+        if self.h:
+            self.lib.hits_free(self.h)
+            self.h = None
+
+    def stats(self):
+        s = np.zeros(8, dtype=np.uint64)
+        self.lib.check(self.lib.hits_stats(self.h, s.ctypes.data))
+        return dict(hits=int(s[0]), lookups=int(s[1]), postings=int(s[2]), read_bytes=int(s[3]), algorithmic_bytes=int(s[4]),
+                    algorithmic_bytes_16B_hits=int(s[5]), unsupported=int(s[6]), records=int(s[7]))
+
+    def fetch(self, record, cap=1 << 16):
+        out = np.zeros((cap, 4), dtype=np.int32)
+        fl = C.c_int()
+        n = self.lib.check(self.lib.hits_fetch(self.h, record, out.ctypes.data, cap, C.byref(fl)))
+        if n > cap:
+            return self.fetch(record, n)
+        return out[:n], fl.value
+
+
+def streams_get_hits(sets, wl: Workload, desc_off, hits: Hits, allow_total_skip=0, cuda_stream=None):
+    """t4_streams_get_hits: SeqSet::GetHitsFromRead of every record against the (frozen) set of its stream."""
+    lib = wl.lib
+    off = np.ascontiguousarray(desc_off, dtype=np.int64)
+    hs = (C.c_void_p * len(sets))(*[s.h if isinstance(s, SeqSet) else s for s in sets])
+    lib.check(lib.streams_get_hits(hs, len(sets), wl.h, off.ctypes.data, int(allow_total_skip), cuda_stream, hits.h))

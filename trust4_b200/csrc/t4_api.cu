@@ -17,6 +17,7 @@
 
 #if T4_CUDA
 #include <cuda_runtime.h>
+#include "t4_probe.cuh"
 #endif
 
 #ifdef T4_EMU
@@ -391,6 +392,9 @@ struct t4_workload
 	T4Op *ops ;
 	int opCap ;
 	bool persistent ;
+	u64 *packed ;          // 2-bit packed reads, record i at packed + i * packStride (t4_common.h)
+	u64 packStride ;
+	bool usePacked ;       // every read is pure ACGTN: the stream kernel assembles from the packed pool
 } ;
 
 extern "C" {
@@ -1380,7 +1384,15 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 	size_t oGood = oRl + al( (size_t)n * 4 ) ;
 	size_t oInfo = oGood + al( (size_t)n ) ;
 	size_t oOps = oInfo + al( (size_t)n * 4 ) ;
-	size_t total = oOps ;
+	// 2-bit packed copy of the reads, fixed stride (the longest supported read of the workload)
+	int maxLen = 0 ;
+	for ( int64_t i = 0 ; i < n ; ++i )
+		if ( descs[i].len > maxLen && descs[i].len <= T4_DEV_MAX_READ )
+			maxLen = descs[i].len ;
+	const u64 packStride = t4_pack_words( maxLen ) ;
+	size_t oPacked = oOps ;
+	size_t oOdd = oPacked + al( (size_t)n * packStride * 8 + 16 ) ;
+	size_t total = oOdd + 256 ;
 	void *p = 0 ;
 	if ( persistent )
 	{
@@ -1417,6 +1429,9 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 	w->rescueList = (int32_t *)( w->buf + oRl ) ;
 	w->good = (int8_t *)( w->buf + oGood ) ;
 	w->info = (int32_t *)( w->buf + oInfo ) ;
+	w->packed = (u64 *)( w->buf + oPacked ) ;
+	w->packStride = packStride ;
+	w->usePacked = false ;
 	T4Names hn ;
 	hn.pool = (u64)(uintptr_t)( w->buf + oNpool ) ;
 	hn.off = (u64)(uintptr_t)( w->buf + oNoff ) ;
@@ -1430,6 +1445,45 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 		delete w ;
 		return 0 ;
 	}
+	// pack on the device (the host API takes ASCII reads like the reference; they cross PCIe once, as ASCII)
+	u32 odd = 0 ;
+	u32 *dOdd = (u32 *)( w->buf + oOdd ) ;
+	bool ok = true ;
+	if ( n > 0 && packStride > 0 )
+	{
+#if T4_CUDA
+		ok = cudaMemsetAsync( dOdd, 0, 4 ) == cudaSuccess ;
+		if ( ok )
+		{
+			t4_pack_reads_kernel<<<(unsigned)n, 32>>>( w->descs, n, w->pool, packStride, w->packed, dOdd ) ;
+			ok = cudaGetLastError() == cudaSuccess && cudaMemcpy( &odd, dOdd, 4, cudaMemcpyDeviceToHost ) == cudaSuccess ;
+		}
+#else
+		for ( int64_t r = 0 ; r < n ; ++r )
+		{
+			const int len = descs[r].len ;
+			if ( len <= 0 || len > T4_DEV_MAX_READ )
+				continue ;
+			const int W = (int)t4_pack_w( len ) ;
+			u64 *fw = w->packed + (u64)r * packStride, *rc = fw + W ;
+			u32 *nm = (u32 *)( fw + 2 * W ) ;
+			for ( int x = 0 ; x < W ; ++x )
+				t4_pack_word( w->pool + descs[r].seq_off, len, x, fw + x, rc + x, nm + x, &odd ) ;
+			if ( W & 1 )
+				nm[W] = 0 ;
+		}
+		(void)dOdd ;
+#endif
+	}
+	if ( !ok )
+	{
+		set_err( "packing the reads failed" ) ;
+		if ( !persistent )
+			dfree( p ) ;
+		delete w ;
+		return 0 ;
+	}
+	w->usePacked = ( odd == 0 && n > 0 && packStride > 0 && getenv( "T4_ASCII_READS" ) == NULL ) ;
 	return w ;
 }
 
@@ -1481,6 +1535,11 @@ static int build_ops( t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg,
 		op.rescueList = (u64)(uintptr_t)( w->rescueList + lo ) ;
 		op.good = (u64)(uintptr_t)( w->good + lo ) ;
 		op.info = (u64)(uintptr_t)( w->info + lo ) ;
+		if ( w->usePacked )
+		{
+			op.packed = (u64)(uintptr_t)( w->packed + (u64)lo * w->packStride ) ;
+			op.packStride = w->packStride ;
+		}
 		if ( cfg )
 			op.cfg = *cfg ;
 	}
@@ -1519,35 +1578,241 @@ int T4_API( streams_run_resident )( t4_seqset *const *sets, int n_sets, const t4
 	return launch_ops( w->ops, n_sets, cuda_stream ) ;
 }
 
-int T4_API( probe_resident )( t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off, void *cuda_stream,
-	uint64_t *algorithmic_bytes, uint64_t *hits_emitted )
+// ---- batch probe over frozen sets (t4_probe.cuh) ---------------------------------------------------
+struct t4_hits
 {
-	if ( !w || n_sets <= 0 )
-		return T4_E_INVAL ;
-	std::vector<T4Op> ops ;
-	int r = build_ops( sets, n_sets, NULL, w, desc_off, T4_OP_PROBE_ONLY, ops ) ;
-	if ( r ) return r ;
-	r = ensure_ops( w, n_sets ) ;
-	if ( r ) return r ;
-	r = dsync() ;
-	if ( r ) return r ;
-	r = reset_counters() ;
-	if ( r ) return r ;
-	r = h2d( w->ops, ops.data(), (size_t)n_sets * sizeof( T4Op ) ) ;
-	if ( r ) return r ;
-	r = launch_ops( w->ops, n_sets, cuda_stream ) ;
-	if ( r ) return r ;
-	if ( algorithmic_bytes || hits_emitted )
+	i64 maxReads ;
+	size_t keyCap ;
+	char *buf ;            // one device allocation
+	u64 *keys, *hitOff, *ord, *ctrl ;
+	u32 *hitCnt, *hitFlags ;
+	u64 *dStreamOff ;      // grow-only side buffers: stream offsets and desc_off of the last call
+	i64 *dDescOff ;
+	int setCap ;
+	i64 nReads ;           // of the last probe
+	int kLast ;
+} ;
+
+t4_hits *T4_API( hits_create )( int64_t max_reads, size_t max_hits )
+{
+	if ( ensure_up() || max_reads <= 0 )
+		return 0 ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	size_t oKeys = 0, oOff = oKeys + al( max_hits * 8 + 16 ), oOrd = oOff + al( (size_t)max_reads * 8 ), oCnt = oOrd + al( (size_t)max_reads * 8 ),
+		oFl = oCnt + al( (size_t)max_reads * 4 ), oCtrl = oFl + al( (size_t)max_reads * 4 ), total = oCtrl + 256 ;
+	void *p = 0 ;
+	if ( dmalloc( &p, total ) )
+		return 0 ;
+	t4_hits *h = new t4_hits ;
+	memset( h, 0, sizeof( *h ) ) ;
+	h->maxReads = max_reads ;
+	h->keyCap = max_hits ;
+	h->buf = (char *)p ;
+	h->keys = (u64 *)( h->buf + oKeys ) ;
+	h->hitOff = (u64 *)( h->buf + oOff ) ;
+	h->ord = (u64 *)( h->buf + oOrd ) ;
+	h->hitCnt = (u32 *)( h->buf + oCnt ) ;
+	h->hitFlags = (u32 *)( h->buf + oFl ) ;
+	h->ctrl = (u64 *)( h->buf + oCtrl ) ;
+	if ( dzero( h->ctrl, 64 ) )
 	{
-		r = dsync() ;
-		if ( r ) return r ;
-		u64 c[T4_N_COUNTERS] ;
-		r = T4_API( last_counters )( c ) ;
-		if ( r ) return r ;
-		// B_probe = ceil(L/4) + sum_j (8 + 8 c_j) + 16 sum_j c_j'
-		if ( algorithmic_bytes ) *algorithmic_bytes = c[5] + 8 * c[2] + 8 * c[3] + 16 * c[4] ;
-		if ( hits_emitted ) *hits_emitted = c[4] ;
+		dfree( p ) ;
+		delete h ;
+		return 0 ;
 	}
+	return h ;
+}
+
+void T4_API( hits_free )( t4_hits *h )
+{
+	if ( !h )
+		return ;
+	dfree( h->buf ) ;
+	if ( h->dStreamOff ) dfree( h->dStreamOff ) ;
+	if ( h->dDescOff ) dfree( h->dDescOff ) ;
+	delete h ;
+}
+
+int T4_API( streams_get_hits )( t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off, int allow_total_skip,
+	void *cuda_stream, t4_hits *h )
+{
+	if ( !w || !h || n_sets <= 0 )
+		return T4_E_INVAL ;
+	const i64 n = desc_off[n_sets] - desc_off[0] ;
+	if ( desc_off[0] != 0 || n > w->nDescs || n > h->maxReads )
+	{
+		set_err( "t4_streams_get_hits: desc_off must start at 0 and fit the workload and the hit buffer" ) ;
+		return T4_E_INVAL ;
+	}
+	std::vector<u64> so( n_sets ) ;
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		int r = check( sets[j] ) ;
+		if ( r ) return r ;
+		so[j] = sets[j]->off ;
+	}
+	if ( n_sets > h->setCap )
+	{
+		if ( h->dStreamOff ) dfree( h->dStreamOff ) ;
+		if ( h->dDescOff ) dfree( h->dDescOff ) ;
+		h->dStreamOff = 0 ; h->dDescOff = 0 ; h->setCap = 0 ;
+		void *a = 0, *b = 0 ;
+		int r = dmalloc( &a, (size_t)n_sets * 8 ) ;
+		if ( !r ) r = dmalloc( &b, (size_t)( n_sets + 1 ) * 8 ) ;
+		if ( r )
+		{
+			if ( a ) dfree( a ) ;
+			return r ;
+		}
+		h->dStreamOff = (u64 *)a ; h->dDescOff = (i64 *)b ; h->setCap = n_sets ;
+	}
+	h->nReads = n ;
+#if T4_CUDA
+	cudaStream_t cs = (cudaStream_t)cuda_stream ;
+	CK( cudaMemcpyAsync( h->dStreamOff, so.data(), (size_t)n_sets * 8, cudaMemcpyHostToDevice, cs ) ) ;
+	CK( cudaMemcpyAsync( h->dDescOff, desc_off, (size_t)( n_sets + 1 ) * 8, cudaMemcpyHostToDevice, cs ) ) ;
+	CK( cudaMemsetAsync( h->ctrl, 0, 64, cs ) ) ;
+	if ( n == 0 )
+		return 0 ;
+	t4_bucket_kernel<<<n_sets, 128, 0, cs>>>( w->descs, h->dDescOff, h->ord ) ;
+	CK( cudaGetLastError() ) ;
+	T4ProbeParams P ;
+	P.A = E.A ;
+	P.streamOff = h->dStreamOff ;
+	P.descs = w->descs ;
+	P.packed = w->packed ;
+	P.packStride = w->packStride ;
+	P.ord = h->ord ;
+	P.nReads = n ;
+	P.keys = h->keys ;
+	P.keyCap = h->keyCap ;
+	P.hitOff = h->hitOff ;
+	P.hitCnt = h->hitCnt ;
+	P.hitFlags = h->hitFlags ;
+	P.ctrl = h->ctrl ;
+	P.allowTotalSkip = allow_total_skip ? 1 : 0 ;
+	static int probeBlocks = 0 ;
+	if ( probeBlocks == 0 )
+	{
+		int perSm = 0, sms = 0 ;
+		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, t4_probe_kernel, 32 * T4P_WARPS, 0 ) ) ;
+		CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ) ;
+		probeBlocks = ( perSm > 0 ? perSm : 1 ) * ( sms > 0 ? sms : 148 ) ; // persistent: one wave, a multiple of the SM count
+	}
+	i64 need = ( n + T4P_WARPS - 1 ) / T4P_WARPS ;
+	int blocks = need < probeBlocks ? (int)need : probeBlocks ;
+	t4_probe_kernel<<<blocks, 32 * T4P_WARPS, 0, cs>>>( P ) ;
+	CK( cudaGetLastError() ) ;
+#else
+	// TEST EMULATION: the same result through the stream engine's own GetHitsFromRead, one read at a time
+	(void)cuda_stream ;
+	memcpy( h->dStreamOff, so.data(), (size_t)n_sets * 8 ) ;
+	memset( h->ctrl, 0, 64 ) ;
+	T4Smem *sm = new T4Smem ;
+	u64 top = 0 ;
+	for ( int j = 0 ; j < n_sets ; ++j )
+		for ( i64 i = desc_off[j] ; i < desc_off[j + 1] ; ++i )
+		{
+			T4Ctx cx ;
+			cx.A = E.A ; cx.g = (T4Global *)E.A ; cx.st = (T4Stream *)( E.A + so[j] ) ; cx.sm = sm ; cx.cap = cx.g->cap ; cx.tid = 0 ; cx.nt = 1 ;
+			const t4_read_desc &d = w->descs[i] ;
+			h->hitOff[i] = top ;
+			h->hitCnt[i] = 0 ;
+			h->hitFlags[i] = 0 ;
+			if ( d.len > T4_DEV_MAX_READ )
+				++h->ctrl[7] ;
+			if ( d.len > T4_DEV_MAX_READ || d.len < cx.st->kmerLength )
+				continue ;
+			for ( int x = 0 ; x < T4_N_COUNTERS ; ++x )
+				sm->ctr[x] = 0 ;
+			c_load_read_packed( cx, w->packed + (u64)i * w->packStride, d.len ) ;
+			int anyBig = 0 ;
+			u32 H = c_get_hits( cx, d.len, d.strand_in, d.barcode, allow_total_skip != 0, &anyBig ) ;
+			if ( top + H > h->keyCap )
+			{
+				h->ctrl[2] = 1 ;
+				top += H ;
+				continue ;
+			}
+			memcpy( h->keys + top, E.A + cx.st->keysAOff, (size_t)H * 8 ) ;
+			h->hitCnt[i] = H ;
+			h->hitFlags[i] = anyBig ? 1u : 0u ;
+			top += H ;
+			h->ctrl[3] += sm->ctr[2] ; h->ctrl[4] += sm->ctr[3] ; h->ctrl[5] += sm->ctr[4] ; h->ctrl[6] += sm->ctr[5] ;
+		}
+	h->ctrl[1] = top ;
+	delete sm ;
+#endif
+	return 0 ;
+}
+
+// stats[0] hits emitted (sum c_j', keys written), [1] lookups executed, [2] postings read (sum c_j), [3] packed read bytes ceil(L/4),
+// [4] algorithmic bytes by SURVEY.md 8d with the 8-byte key this kernel really writes: [3] + 8 [1] + 8 [2] + 8 [0],
+// [5] the same with the survey's nominal 16-byte hit, [6] reads longer than T4_MAX_READ_LEN (skipped), [7] reads probed.
+int T4_API( hits_stats )( t4_hits *h, uint64_t *stats )
+{
+	if ( !h )
+		return T4_E_INVAL ;
+	int r = dsync() ;
+	if ( r ) return r ;
+	u64 c[8] ;
+	r = d2h( c, h->ctrl, 64 ) ;
+	if ( r ) return r ;
+	stats[0] = c[5] ; stats[1] = c[3] ; stats[2] = c[4] ; stats[3] = c[6] ;
+	stats[4] = c[6] + 8 * c[3] + 8 * c[4] + 8 * c[5] ;
+	stats[5] = c[6] + 8 * c[3] + 8 * c[4] + 16 * c[5] ;
+	stats[6] = c[7] ;
+	stats[7] = (u64)h->nReads ;
+	if ( c[2] )
+	{
+		set_err( "hit buffer too small: " + std::to_string( c[1] ) + " keys needed" ) ;
+		return T4_E_NOMEM ;
+	}
+	return 0 ;
+}
+
+// Hits of record i as int32[4] = { seqIdx, seqOffset, readOffset, strand }; hits removed by the barcode filter
+// (SeqSet.hpp:1418) are dropped.  Order: by read position (forward pass first), postings order inside a k-mer.
+int T4_API( hits_fetch )( t4_hits *h, int64_t record, int32_t *hits, int cap, int *flags )
+{
+	if ( !h || record < 0 || record >= h->nReads )
+		return T4_E_INVAL ;
+	int r = dsync() ;
+	if ( r ) return r ;
+	u64 off ;
+	u32 cnt, fl ;
+	if ( ( r = d2h( &off, h->hitOff + record, 8 ) ) || ( r = d2h( &cnt, h->hitCnt + record, 4 ) ) || ( r = d2h( &fl, h->hitFlags + record, 4 ) ) )
+		return r ;
+	if ( flags )
+		*flags = (int)fl ;
+	std::vector<u64> k( cnt ) ;
+	if ( cnt && ( r = d2h( k.data(), h->keys + off, (size_t)cnt * 8 ) ) )
+		return r ;
+	int n = 0 ;
+	for ( u32 i = 0 ; i < cnt ; ++i )
+	{
+		if ( k[i] == T4_KEY_INVALID )
+			continue ;
+		if ( n < cap )
+		{
+			hits[4 * n] = t4_key_idx( k[i] ) ;
+			hits[4 * n + 1] = t4_key_b( k[i] ) ;
+			hits[4 * n + 2] = t4_key_a( k[i] ) ;
+			hits[4 * n + 3] = t4_key_strand( k[i] ) ;
+		}
+		++n ;
+	}
+	return n ;
+}
+
+// raw access for device-side consumers and tests: device pointers of the last probe
+int T4_API( hits_device_buffers )( t4_hits *h, void **keys, void **hit_off, void **hit_cnt )
+{
+	if ( !h )
+		return T4_E_INVAL ;
+	if ( keys ) *keys = h->keys ;
+	if ( hit_off ) *hit_off = h->hitOff ;
+	if ( hit_cnt ) *hit_cnt = h->hitCnt ;
 	return 0 ;
 }
 

@@ -29,7 +29,7 @@ typedef int64_t i64;
 #endif
 
 #define T4_DEV_MAX_READ T4_MAX_READ_LEN       /* device-side read length limit (reads > 200 bp make the reference switch to isLongSeqSet) */
-#define T4_ALIGN 16
+#define T4_ALIGN 32               /* arena allocations are sector aligned: a postings list of <= 4 entries is ONE 32-byte sector */
 #define T4_BIG_REPEAT 10000       /* SeqSet.hpp:799, 875, 937: hits[k].repeats <= 10000 */
 
 // ---- key layout of a seed hit (one u64 per hit; SeqSet.hpp:53 `_hit` carries the same information) ----
@@ -148,6 +148,46 @@ struct T4Pos               // per (strand pass, read position) lookup record
 	u32 base ;                     // first hit slot, 0xffffffff = lookup not taken
 } ;
 
+// ---- 2-bit packed reads (KmerCode.hpp:94-109 semantics on words) ----
+// A read of `len` bases occupies t4_pack_words(len) u64 words, W = ceil(len / 32):
+//   fw[W]  forward strand, base j in bits [63 - 2 (j & 31) - 1, 63 - 2 (j & 31)] of word j >> 5 (first base most
+//          significant, like KmerCode::Append shifting left), A 0 C 1 G 2 T 3, N stored as 00;
+//   rc[W]  the reverse complement in the same layout (N stays N: 00);
+//   nm[ceil(W/2)] u64 = u32[W]: bit (j & 31) of word j >> 5 set iff forward base j is 'N'.
+// A k-mer is then one funnel shift of two words; its validity window (KmerCode::IsValid) is k bits of the N mask.
+T4_HD inline u32 t4_pack_w( int len ) { return (u32)( len + 31 ) >> 5 ; }
+T4_HD inline u32 t4_pack_words( int len ) { u32 W = t4_pack_w( len ) ; return 2 * W + ( ( W + 1 ) >> 1 ) ; }
+
+// Word w of a packed read: 32 forward bases, 32 reverse-complement bases, 32 mask bits.  *odd is set when a base is
+// none of ACGTN (the packed form cannot carry it: such workloads keep assembling from the ASCII pool).
+T4_HD inline int t4_nuc2( char c ) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 0 : 3 ; }
+T4_HD inline void t4_pack_word( const char *s, int len, int w, u64 *fw, u64 *rc, u32 *nm, u32 *odd )
+{
+	u64 f = 0, b = 0 ;
+	u32 mk = 0 ;
+	for ( int i = 0 ; i < 32 ; ++i )
+	{
+		const int j = 32 * w + i ;
+		if ( j >= len )
+			break ;
+		const char c = s[j] ;
+		if ( c == 'N' )
+			mk |= 1u << i ;
+		else
+		{
+			if ( c != 'A' && c != 'C' && c != 'G' && c != 'T' )
+				*odd = 1 ;
+			f |= (u64)t4_nuc2( c ) << ( 62 - 2 * i ) ;
+		}
+		const char cr = s[len - 1 - j] ; // reverse-complement base j (SeqSet::ReverseComplement, SeqSet.hpp:2616)
+		if ( cr != 'N' )
+			b |= (u64)( 3 - t4_nuc2( cr ) ) << ( 62 - 2 * i ) ;
+	}
+	*fw = f ;
+	*rc = b ;
+	*nm = mk ;
+}
+
 // Pointers to buffers outside the arena (workloads, staging, outputs) are absolute addresses stored in u64.
 template <class T> T4_HD inline T *t4_x( u64 p ) { return (T *)(uintptr_t)p ; }
 
@@ -171,7 +211,7 @@ enum
 	T4_OP_GET_HITS,
 	T4_OP_GET_OVERLAPS,
 	T4_OP_RUN_LOOP,
-	T4_OP_PROBE_ONLY,
+	T4_OP_UNUSED_,
 	T4_OP_INIT,
 	T4_OP_RELEASE_BARCODE,
 	T4_OP_RELEASE_SHALLOW,
@@ -181,7 +221,7 @@ struct T4Op                // per-CTA launch record
 {
 	u64 streamOff ;                // arena offset of the T4Stream
 	int op ;
-	int n ;                        // RUN_LOOP / PROBE_ONLY: number of descs
+	int n ;                        // RUN_LOOP: number of descs
 	u64 desc ;                     // t4_read_desc[n]            (absolute)
 	u64 pool ;                     // read pool                  (absolute)
 	u64 names ;                    // T4Names                    (absolute)
@@ -189,6 +229,8 @@ struct T4Op                // per-CTA launch record
 	u64 rescueList ;               // int32[n] scratch
 	u64 good ;                     // int8[n] goodCandidate
 	u64 info ;                     // int32[n]
+	u64 packed ;                   // 2-bit packed reads of this op's records (absolute; record i at packed + i * packStride words), 0 = ASCII pool
+	u64 packStride ;               // u64 words per record
 	t4_run_cfg cfg ;
 	// single-call ops
 	u64 read ;                     // char[len] (absolute)
@@ -207,7 +249,7 @@ struct T4Op                // per-CTA launch record
 	int strandOut ;
 	int pad1 ;
 	u64 out2 ;
-	u64 stat0, stat1 ;             // PROBE_ONLY: algorithmic bytes, hits
+	u64 stat0, stat1 ;
 } ;
 
 struct T4InitParams        // T4_OP_INIT: lay out and initialise a fresh stream at streamOff

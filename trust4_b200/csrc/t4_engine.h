@@ -4086,6 +4086,32 @@ T4_D inline void c_load_read( T4Ctx &cx, const char *src, int len )
 	T4_SYNC() ;
 }
 
+// The same from the 2-bit packed pool (t4_common.h): 2.7x fewer HBM bytes per read than ASCII and no revcomp pass.
+T4_D inline void c_load_read_packed( T4Ctx &cx, const u64 *pk, int len )
+{
+	T4Smem *sm = cx.sm ;
+	const int W = (int)t4_pack_w( len ) ;
+	const u64 *fw = pk, *rc = pk + W ;
+	const u32 *nm = (const u32 *)( pk + 2 * W ) ;
+	T4_SYNC() ;
+	T4_PAR_FOR( i, len )
+	{
+		const int sh = 62 - 2 * ( i & 31 ) ;
+		const bool n = ( nm[i >> 5] >> ( i & 31 ) ) & 1u ;
+		const int j = len - 1 - i ; // forward position of reverse-complement base i
+		const bool nr = ( nm[j >> 5] >> ( j & 31 ) ) & 1u ;
+		sm->read[i] = n ? 'N' : t4_numToNuc( (int)( ( fw[i >> 5] >> sh ) & 3 ) ) ;
+		sm->rc[i] = nr ? 'N' : t4_numToNuc( (int)( ( rc[i >> 5] >> sh ) & 3 ) ) ;
+	}
+	if ( cx.tid == 0 )
+	{
+		sm->read[len] = '\0' ;
+		sm->rc[len] = '\0' ;
+		s_refill_slab( cx ) ;
+	}
+	T4_SYNC() ;
+}
+
 // ---------------------------------------------------------------------------
 // the stage-1 driver loop (main.cpp:1583-1881) and rescue pass (main.cpp:1897-1940) over read descriptors
 // ---------------------------------------------------------------------------
@@ -4116,6 +4142,8 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 	int32_t *info = t4_x<int32_t>( op->info ) ;
 	const t4_run_cfg cfg = op->cfg ;
 	const int n = op->n ;
+	const u64 *packed = t4_x<u64>( op->packed ) ;
+	const u64 packStride = op->packStride ;
 	T4_PAR_FOR( i, n )
 	{
 		goodCandidate[i] = 0 ;
@@ -4171,7 +4199,10 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			T4_SYNC() ;
 			break ;
 		}
-		c_load_read( cx, pool + d.seq_off, d.len ) ;
+		if ( packed )
+			c_load_read_packed( cx, packed + (u64)i * packStride, d.len ) ;
+		else
+			c_load_read( cx, pool + d.seq_off, d.len ) ;
 		int finalStrand = 0 ;
 		if ( !( d.flags & T4_RD_DUP ) )
 		{
@@ -4318,7 +4349,10 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		{
 			int i = rescueList[x] ;
 			const t4_read_desc d = descs[i] ;
-			c_load_read( cx, pool + d.seq_off, d.len ) ;
+			if ( packed )
+				c_load_read_packed( cx, packed + (u64)i * packStride, d.len ) ;
+			else
+				c_load_read( cx, pool + d.seq_off, d.len ) ;
 			char name[2] = "" ;
 			int strand = 0 ;
 			int addRet = c_add_read( cx, d.len, name, strand, d.barcode, 1, cfg.repetitive != 0, t4_rescue_threshold( d.min_cnt ) ) ;
@@ -4412,25 +4446,6 @@ T4_D inline void c_init_stream( T4Ctx &cx, u64 base, const T4InitParams &ip )
 		dir[i].cnt = dir[i].cap = dir[i].lock = dir[i].pad = 0 ;
 	}
 	T4_SYNC() ;
-}
-
-// Probe only: GetHitsFromRead of every read of the op against the (frozen) stream; the hits are written
-// to the stream's key buffer exactly as AddRead would.  Used for the probe-kernel roofline measurement.
-T4_D inline void c_probe_only( T4Ctx &cx, T4Op *op )
-{
-	const t4_read_desc *descs = t4_x<t4_read_desc>( op->desc ) ;
-	const char *pool = t4_x<char>( op->pool ) ;
-	for ( int i = 0 ; i < op->n && !cx.st->error ; ++i )
-	{
-		const t4_read_desc d = descs[i] ;
-		if ( d.len > T4_DEV_MAX_READ || d.len < cx.st->kmerLength )
-			continue ;
-		c_load_read( cx, pool + d.seq_off, d.len ) ;
-		int anyBig ;
-		c_get_hits( cx, d.len, d.strand_in, d.barcode, false, &anyBig ) ;
-	}
-	if ( cx.tid == 0 )
-		t4_count( cx, 0, (u64)op->n ) ;
 }
 
 // ---------------------------------------------------------------------------
@@ -4596,11 +4611,6 @@ T4_D inline void c_run_op( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 				op->ret = n ;
 			break ;
 		}
-		case T4_OP_PROBE_ONLY:
-			c_probe_only( cx, op ) ;
-			if ( cx.tid == 0 )
-				op->ret = 0 ;
-			break ;
 		default:
 			break ;
 	}

@@ -426,13 +426,32 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
     return Workload(descs, pool, names, L, order)
 
 
-def shard_workload(w: Workload, n_shards: int, deal: bool = False):
+# Cost model of one record in the stream kernel, used to size contiguous shards (relative units).  A duplicate is a
+# RepeatAddRead (posWeight increments only); a distinct read runs the whole AddRead path, and the rarer its k-mers
+# (minCnt of the 21-mer statistics, known before the launch) the less it assembles: singletons become contigs of their
+# own, which every later read of the shard then has to be scored against.  Constants fitted to per-stream cycle counts
+# of the default bench workload (bench.py --dump-streams, bench/fit_cost_model.py).
+COST_DUP = 1.0
+COST_BY_MINCNT = ((1, 60.0), (2, 40.0), (4, 25.0), (8, 15.0), (16, 10.0), (1 << 30, 6.0))
+
+
+def read_cost(descs) -> np.ndarray:
+    mc = descs["min_cnt"].astype(np.int64)
+    c = np.full(len(descs), COST_BY_MINCNT[-1][1], dtype=np.float64)
+    for hi, v in reversed(COST_BY_MINCNT):
+        c[mc <= hi] = v
+    c[(descs["flags"] & RD_DUP) != 0] = COST_DUP
+    return c
+
+
+def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str = "reads"):
     """Shard the sorted records into n_shards independent streams.  Returns desc_off[n_shards+1]
     and the records in stream order with mate_idx / eq_* made stream-relative (mates in other streams -> -1).
     A run of identical reads is never split (RepeatAddRead semantics survive), and every stream keeps the global
     sorted order of its reads.
 
-    deal=False: contiguous blocks of the sorted list.
+    deal=False: contiguous blocks of the sorted list; balance = "reads" (equal read counts) or "cost" (equal predicted
+                cost, read_cost()).
     deal=True : runs are dealt round-robin (run r -> stream r mod n_shards).  Every stream then sees a uniform sample
                 of the library instead of one abundance class, which equalises the work per stream (contiguous blocks
                 of low-abundance reads are ~50x more expensive than blocks of duplicates)."""
@@ -465,8 +484,15 @@ def shard_workload(w: Workload, n_shards: int, deal: bool = False):
         del same_prev
         return off, d[order]
     bounds = [0]
-    for s in range(1, n_shards):
-        b = (n * s) // n_shards
+    if balance == "cost" and n > 0:
+        # balance="cost": the same contiguous blocks of the sorted list, cut where the cumulative predicted cost crosses
+        # s / n_shards of the total instead of where the read count does (a stream is a serial chain: the launch lasts as
+        # long as its most expensive shard)
+        cum = np.cumsum(read_cost(w.descs))
+        cuts = np.searchsorted(cum, cum[-1] * np.arange(1, n_shards) / n_shards, side="left")
+    else:
+        cuts = (n * np.arange(1, n_shards)) // n_shards
+    for b in cuts:
         b = int(w.descs["eq_lo"][b]) if b < n else n
         bounds.append(max(b, bounds[-1]))
     bounds.append(n)
