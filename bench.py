@@ -51,7 +51,25 @@ def parse(argv=None):
     ap.add_argument("--balance", default=os.environ.get("T4_BENCH_BALANCE", "cost"), choices=["reads", "cost"],
                     help="contiguous shards of equal read count, or of equal predicted cost (abundance model, synth.read_cost)")
     ap.add_argument("--dump-streams", default="", help="write per-stream cycles + features (npz) for cost-model calibration")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
+                    help="BASELINE.json configs[] index: 1 = bulk 150 bp PE (the metric's config), 3 = 10x-style barcoded single-end "
+                         "reads (whole barcodes per stream), 4 = --repseq bulk TCR-seq 100 bp SE amplicons")
+    ap.add_argument("--barcodes", type=int, default=int(os.environ.get("T4_BENCH_BARCODES", 1000)), help="config 3: cells per GPU (configs[3] full size: 6250)")
+    ap.add_argument("--reads-per-barcode", type=int, default=2000)
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("T4_BENCH_READS", 2000000)), help="config 4: reads per GPU (configs[4] full size: 6250000)")
     return ap.parse_args(argv)
+
+
+def setup_of(args):
+    """Per-config constants: read length, driver-loop configuration (main.cpp:1541-1568) and SeqSet setters."""
+    from trust4_b200 import synth
+    if args.config == 3:      # --barcode: hitLenRequired 13, barcode-salted index, per-barcode purge (main.cpp:1549-1560, 1846-1859)
+        return {"L": 150, "cfg": synth.run_cfg(has_barcode=1, release_barcodes=1), "hit_len": 13, "consider_barcode": 1,
+                "metric": "reads/sec assembled (150bp SE, 10x barcodes)"}
+    if args.config == 4:      # --repseq = --trimLevel 2 --skipMateExtension: repetitiveData, k-change threshold halved (main.cpp:1567)
+        return {"L": 100, "cfg": synth.run_cfg(repetitive=1, change_k_threshold=2048, first_read_len=100), "hit_len": 31, "consider_barcode": 0,
+                "metric": "reads/sec assembled (100bp SE, --repseq)"}
+    return {"L": 150, "cfg": synth.run_cfg(), "hit_len": 31, "consider_barcode": 0, "metric": "reads/sec assembled (150bp PE)"}
 
 
 def dist_env():
@@ -63,6 +81,20 @@ def dist_env():
 
 def make_workload(args, rank, device):
     from trust4_b200 import synth
+    if args.config == 3:
+        nclones = args.clones or max(20, 2 * args.barcodes)
+        cl = synth.make_clones(nclones, args.seed)
+        rd, bc = synth.sample_single_cell(cl, args.barcodes, args.reads_per_barcode, 150, args.seed * 1000 + rank)
+        w = synth.build_workload(cl, rd, device=device, barcode=bc)
+        off, descs = synth.shard_workload(w, args.streams, balance=args.balance, align="barcode")
+        return w, off, descs
+    if args.config == 4:
+        nclones = args.clones or max(20, args.reads // 50)
+        cl = synth.make_clones(nclones, args.seed, chains=("TRB",))
+        rd = synth.sample_amplicon(cl, args.reads, 100, args.seed * 1000 + rank, alpha=1.0)
+        w = synth.build_workload(cl, rd, device=device, repseq=True)
+        off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance)
+        return w, off, descs
     nclones = args.clones or max(20, args.pairs // 50)
     cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
     rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
@@ -131,7 +163,8 @@ def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
     from trust4_b200 import synth
     if not rh.available():
         return None
-    cfg = synth.run_cfg()
+    su = setup_of(args)
+    cfg = su["cfg"]
     n_shards = len(off) - 1
     order = sample_order(n_shards)
     lock = threading.Lock()
@@ -148,6 +181,10 @@ def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
             j = int(order[x])
             lo, hi = int(off[j]), int(off[j + 1])
             r = rh.RefSeqSet(9)
+            if su["hit_len"] != 31:
+                r.set_hit_len_required(su["hit_len"])
+            if su["consider_barcode"]:
+                rh.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
             out = r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)     # ctypes releases the GIL
             rec = None
             if x < keep:                                                     # the first `keep` of the order: full parity record
@@ -172,9 +209,9 @@ def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
                       "restated main.cpp loop" % (state["shards"], n_shards, state["reads"], el, cores)}
 
 
-def build_line(args, config, value, ms_per_step, clocks, e2e, launches, roofline, roofline_probe, cpu, extra):
+def build_line(args, config, value, ms_per_step, clocks, e2e, launches, roofline, roofline_probe, cpu, extra, metric="reads/sec assembled (150bp PE)"):
     """The ONE JSON line of the contract.  Kept as a pure function so that a unit test can assert its keys."""
-    line = {"metric": "reads/sec assembled (150bp PE)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "roofline_probe": roofline_probe, "cpu_baseline": cpu}
@@ -192,10 +229,22 @@ def main():
     cores = os.cpu_count() or 1
     mode = "dealt round-robin" if args.deal else ("in contiguous blocks of the sorted list, block sizes equalising the predicted cost (abundance model)"
                                                    if args.balance == "cost" else "in contiguous blocks of the sorted list, equal read counts")
-    config = {"workload": "configs[1]: %d synthetic 150bp PE pairs (%d reads) per GPU vs human_IMGT+C gene pool, k=9, "
-                          "read-sharded into %d streams per GPU (runs of identical reads %s; one SeqSet each, per-shard parity, SURVEY.md 8e)"
-                          % (args.pairs, 2 * args.pairs, args.streams, mode),
-              "pairs_per_gpu": args.pairs, "streams_per_gpu": args.streams, "kmer": 9, "read_len": 150, "shard_balance": "deal" if args.deal else args.balance,
+    if args.config == 3:
+        args.streams = min(args.streams, args.barcodes)
+        wtxt = ("configs[3] shape: %d cell barcodes x %d synthetic 150bp SE reads per GPU (configs[3] full size is 6250 barcodes per GPU), "
+                "hitLenRequired 13, barcode-salted index, whole barcodes per stream (%d streams per GPU, SURVEY.md 8e), finished barcodes purged"
+                % (args.barcodes, args.reads_per_barcode, args.streams))
+    elif args.config == 4:
+        wtxt = ("configs[4] shape: %d synthetic 100bp SE TRB amplicon reads per GPU (--repseq: repetitiveData, V-gene pseudo barcodes; configs[4] "
+                "full size is 6.25 M per GPU), read-sharded into %d streams per GPU (%s)" % (args.reads, args.streams, mode))
+    else:
+        wtxt = ("configs[1]: %d synthetic 150bp PE pairs (%d reads) per GPU vs human_IMGT+C gene pool, k=9, "
+                "read-sharded into %d streams per GPU (runs of identical reads %s; one SeqSet each, per-shard parity, SURVEY.md 8e)"
+                % (args.pairs, 2 * args.pairs, args.streams, mode))
+    su = setup_of(args)
+    L = su["L"]
+    config = {"workload": wtxt, "baseline_config": args.config,
+              "pairs_per_gpu": args.pairs if args.config == 1 else None, "streams_per_gpu": args.streams, "kmer": 9, "read_len": L, "shard_balance": "deal" if args.deal else args.balance,
               "l2": "inputs (>= 400 MB of reads + records, GBs of stream state) exceed the 126 MB L2",
               "sharding": "rank r sequences its own reads of the shared repertoire; no data-path collective; "
                           "N>1: one NCCL all-gather of the packed per-rank contig sets per step (merge step)"}
@@ -222,7 +271,7 @@ def main():
                 vals.append(s)
         v = float(np.mean([x["value"] for x in vals]))
         n_reads = len(descs)
-        line = {"impl": "reference", "metric": "reads/sec assembled (150bp PE)", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": su["metric"], "value": v, "unit": "reads/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_reads / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
                 "cpu_baseline": dict(vals[-1], value=v),
@@ -246,7 +295,7 @@ def main():
     torch.cuda.empty_cache()
     n_reads = len(descs)
     S = args.streams
-    cfg = synth.run_cfg()
+    cfg = su["cfg"]
     names_arr = api._names_array(w.names)
     off64 = np.ascontiguousarray(off, dtype=np.int64)
 
@@ -287,13 +336,13 @@ def main():
 
     def step_resident():
         lib.check(lib.reset())
-        lib.check(lib.seqsets_create(S, 9, handles))
+        lib.check(lib.seqsets_create_ex(S, 9, su["hit_len"], su["consider_barcode"], handles))
         lib.check(lib.streams_run_resident(handles, S, cfg.ctypes.data, wl, off64.ctypes.data, None))
         merge_exchange(pack_contigs())
 
     def step_e2e():
         lib.check(lib.reset())
-        lib.check(lib.seqsets_create(S, 9, handles))
+        lib.check(lib.seqsets_create_ex(S, 9, su["hit_len"], su["consider_barcode"], handles))
         lib.check(lib.streams_run(handles, S, cfg.ctypes.data, pin_descs.data_ptr(), off64.ctypes.data, pin_pool.data_ptr(),
                                   pin_pool.numel(), names_arr, len(w.names), ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
         buf = pack_contigs()
@@ -336,7 +385,7 @@ def main():
 
     # kernel-only duration of the stream kernel (one launch per step) for the roofline
     lib.check(lib.reset())
-    lib.check(lib.seqsets_create(S, 9, handles))
+    lib.check(lib.seqsets_create_ex(S, 9, su["hit_len"], su["consider_barcode"], handles))
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0 = np.zeros(api.N_COUNTERS, dtype=np.uint64)
@@ -362,7 +411,7 @@ def main():
     # probe ceil(L/4) + sum(8 + 8 c_j) + 16 sum c_j'; chain 2 x 16 sum c_j'; commit 8 L per assembled read
     b_probe = dc[5] + 8 * dc[2] + 8 * dc[3] + 16 * dc[4]
     b_chain = 32 * dc[4]
-    b_commit = 8.0 * 150 * assembled
+    b_commit = 8.0 * L * assembled
     alg_bytes = b_probe + b_chain + b_commit
     peaks = {}
     try:
@@ -375,7 +424,7 @@ def main():
     def ncu_traffic(fname):
         """DRAM bytes (read + write) of a kernel from a committed ncu --set full raw page of the default workload."""
         try:
-            if args.pairs != 1000000 or args.streams != 4096 or args.deal:
+            if args.config != 1 or args.pairs != 1000000 or args.streams != 4096 or args.deal:
                 return None
             import csv
             rows = list(csv.reader(open(os.path.join(ROOT, "profiles", fname))))
@@ -492,7 +541,7 @@ def main():
             4 * args.steps, roofline, roofline_probe, cpu,
             {"assembled_reads": assembled, "reads_per_gpu": n_reads, "contigs_per_gpu": merged["contigs"], "parity_spot_check": parity,
              "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
-             "threads_per_stream": int(os.environ.get("T4_NT", 128))})
+             "threads_per_stream": int(os.environ.get("T4_NT", 128))}, metric=su["metric"])
         print(json.dumps(line))
     lib.workload_free(wl)
     if world > 1:

@@ -58,6 +58,9 @@ int t4_reset(void);
 t4_seqset *t4_seqset_create(int kmer_length);
 /* n sets with one device launch (read-sharded runs create thousands of streams). */
 int t4_seqsets_create(int n, int kmer_length, t4_seqset **handles);
+/* ... with SetHitLenRequired(l) and SetConsiderBarcodeInIndexHash(on) (SeqSet.hpp:2601, 2611; the driver sets them
+ * once before the loop, main.cpp:1549-1565) applied to every new set by the same launch. */
+int t4_seqsets_create_ex(int n, int kmer_length, int hit_len_required, int consider_barcode, t4_seqset **handles);
 void t4_seqset_destroy(t4_seqset *s);
 /* SeqSet::SetHitLenRequired, SeqSet.hpp:2601 */
 int t4_seqset_set_hit_len_required(t4_seqset *s, int l);
@@ -215,6 +218,17 @@ int t4_streams_run_resident(t4_seqset *const *sets, int n_sets, const t4_run_cfg
                             t4_workload *w, const int64_t *desc_off, void *cuda_stream);
 /* Copy results of the last resident run back. */
 int t4_workload_results(t4_workload *w, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
+/* Which SeqSet calls each iteration of the loop made (what a call trace of the reference driver would show), one byte
+ * per record: lets a host driver that keeps the reference's own loop replay the device's decisions call by call
+ * (integration/t4_seqset_adapter.hpp, batch mode) and lets tests compare call sequences. */
+#define T4_EV_ADD_READ (1u << 0)        /* AddRead was called (main.cpp:1700) */
+#define T4_EV_REPEAT (1u << 1)          /* RepeatAddRead (main.cpp:1766) */
+#define T4_EV_NOVEL_ANCHORED (1u << 2)  /* InputNovelRead with the gene name (main.cpp:1742) */
+#define T4_EV_NOVEL_MOTIF (1u << 3)     /* InputNovelRead("Novel") after a good mate + motif (main.cpp:1752) */
+#define T4_EV_CHANGE_K (1u << 4)        /* ChangeKmerLength after this iteration (main.cpp:1874-1879) */
+#define T4_EV_RESCUED (1u << 5)         /* AddRead of the rescue pass (main.cpp:1926) */
+#define T4_EV_PURGED (1u << 6)          /* ReleaseFinishedBarcodeSeq after this iteration (main.cpp:1855) */
+int t4_workload_events(t4_workload *w, uint8_t *events);
 
 /* Merge step: pack every live contig of the given sets, in (set, slot) order, into ONE caller-provided
  * DEVICE buffer (e.g. a torch tensor) ready for an NCCL all-gather.  Record = 32-byte header {u32 set, slot, len,

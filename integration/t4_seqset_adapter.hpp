@@ -23,6 +23,7 @@
 #define t4_seqset_update_all_consensus t4emu_seqset_update_all_consensus
 #define t4_seqset_change_kmer_length t4emu_seqset_change_kmer_length
 #define t4_seqset_size t4emu_seqset_size
+#define t4_seqset_kmer_length t4emu_seqset_kmer_length
 #define t4_seqset_set_hit_len_required t4emu_seqset_set_hit_len_required
 #define t4_seqset_set_is_long t4emu_seqset_set_is_long
 #define t4_seqset_set_consider_barcode_in_hash t4emu_seqset_set_consider_barcode_in_hash
@@ -32,6 +33,13 @@
 #define t4_seqset_release_finished_barcode t4emu_seqset_release_finished_barcode
 #define t4_seqset_release_shallow_contigs t4emu_seqset_release_shallow_contigs
 #define t4_seqset_input_novel_fa t4emu_seqset_input_novel_fa
+#define t4_seqsets_create_ex t4emu_seqsets_create_ex
+#define t4_workload_upload t4emu_workload_upload
+#define t4_workload_free t4emu_workload_free
+#define t4_streams_run_resident t4emu_streams_run_resident
+#define t4_workload_results t4emu_workload_results
+#define t4_workload_events t4emu_workload_events
+#define t4_streams_error t4emu_streams_error
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
 #endif
@@ -39,6 +47,7 @@
 #include <stdarg.h>
 #include <time.h>
 #include <assert.h>
+#include <limits.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,13 +62,22 @@ class T4GpuSeqSet : public SeqSet
 {
 	t4_seqset *h ;
 	bool gpu ;
+	// ---- batch route (T4_BATCH_PREPARE, below): the device runs the whole loop, the driver's own loop replays it ----
+	std::vector<t4_seqset *> sets ;      // sets[0] == h
+	bool replay ;
+	int curK, curHitLen, curConsiderBarcode ;
+	std::vector<int32_t> bRet, bResc ;
+	std::vector<int8_t> bStrand ;
+	std::vector<uint8_t> bEv ;
+	std::vector<int> rescueOrder ;
+	size_t cur, rescuePos ;
+	int maxFinalK ;
 	void Die() { fprintf( stderr, "trust4_b200: %s\n", t4_last_error() ) ; exit( 1 ) ; }
 	int Check( int r ) { if ( r < T4_E_BASE ) Die() ; return r ; }
 
 	// Copy the device contigs into the CPU object (slot numbers preserved; released slots stay NULL).
 	void SyncToHost()
 	{
-		int n = Check( t4_seqset_size( h ) ) ;
 		for ( size_t i = 0 ; i < seqs.size() ; ++i )
 		{
 			if ( seqs[i].consensus ) free( seqs[i].consensus ) ;
@@ -69,6 +87,12 @@ class T4GpuSeqSet : public SeqSet
 		std::vector<char> cons, name( 4096 ) ;
 		std::vector<int32_t> pw ;
 		std::map<int, int> purgedBarcodes ;
+		// read-sharded batch runs hold one device set per stream: the mirror is their concatenation in stream order
+		// (global slot = local slot + slots of the earlier streams)
+		for ( size_t si = 0 ; si < sets.size() ; ++si )
+		{
+		t4_seqset *h = sets[si] ;
+		int n = Check( t4_seqset_size( h ) ) ;
 		for ( int i = 0 ; i < n ; ++i )
 		{
 			struct _seqWrapper ns ;
@@ -98,12 +122,13 @@ class T4GpuSeqSet : public SeqSet
 			seqs.push_back( ns ) ;
 			if ( len >= 0 )
 			{
-				struct _seqWrapper &sw = seqs[i] ;
+				struct _seqWrapper &sw = seqs.back() ;
 				sw.posWeight.ExpandTo( len ) ;
 				for ( int j = 0 ; j < len ; ++j )
 					for ( int k = 0 ; k < 4 ; ++k )
 						sw.posWeight[j].count[k] = pw[4 * j + k] ;
 			}
+		}
 		}
 		// Contigs the device purged (ReleaseFinishedBarcodeSeq) keep their full posWeight columns there; the reference
 		// compresses or frees them and marks them un-indexed.  Re-apply exactly that storage change to the mirror with the
@@ -113,7 +138,8 @@ class T4GpuSeqSet : public SeqSet
 			SeqSet::ReleaseFinishedBarcodeSeq( purgedBarcodes, true, 0, false ) ;
 	}
 public:
-	T4GpuSeqSet( int kl ) : SeqSet( kl ), h( NULL )
+	T4GpuSeqSet( int kl ) : SeqSet( kl ), h( NULL ), replay( false ), curK( kl ), curHitLen( 31 ), curConsiderBarcode( 0 ), cur( 0 ), rescuePos( 0 ),
+		maxFinalK( kl )
 	{
 		gpu = ( t4_adapter_instances++ == 0 ) ;
 		if ( gpu )
@@ -121,33 +147,341 @@ public:
 			h = t4_seqset_create( kl ) ;
 			if ( !h )
 				Die() ;
+			sets.push_back( h ) ;
 		}
 	}
-	~T4GpuSeqSet() { if ( h ) t4_seqset_destroy( h ) ; }
+	~T4GpuSeqSet()
+	{
+		for ( size_t i = 0 ; i < sets.size() ; ++i )
+			t4_seqset_destroy( sets[i] ) ;
+	}
+
+	// ---- the batch route ---------------------------------------------------------------------------------------------
+	// T4_BATCH_PREPARE() is the ONE line added to main.cpp, directly in front of the AddRead loop (main.cpp:1583).  When the
+	// environment variable T4_STREAMS = S >= 1 is set, it restates the loop's per-read preparation (main.cpp:1596-1745: the
+	// duplicate test, the V/D/J/C order and constant-gene filters, gene prefix / strand / similarity threshold /
+	// minKmerCount of the AddRead call, the may-seed-a-contig rule, the mate hints) into t4_read_desc records, runs the
+	// whole loop and the rescue pass on the device (S = 1: one stream = the reference's serial semantics; S > 1: S
+	// contiguous shards of the sorted list, one SeqSet each) and arms `replay`: the driver's own unmodified loop then
+	// asks AddRead / RepeatAddRead / InputNovelRead / Size again and gets the device's answers, so all of its
+	// bookkeeping (assembledReadIdx, strands, rescue list, k) ends up exactly as if it had done the work.
+	template <class Reads, class RefSet>
+	void BatchPrepare( Reads &sortedReads, RefSet &refSet, int readCnt, bool hasBarcode, bool keepMissingBarcode, int trimLevel,
+		int firstReadLen, int constantGeneEnd, int contigMinCov, int changeKmerLengthThreshold )
+	{
+		const char *env = getenv( "T4_STREAMS" ) ;
+		if ( !gpu || env == NULL || atoi( env ) < 1 || readCnt <= 0 )
+			return ;
+		int S = atoi( env ) ;
+		const int n = readCnt ;
+		std::vector<t4_read_desc> d( n ) ;
+		std::string pool ;
+		std::vector<std::string> names ;
+		std::map<std::string, int> nameId ;
+		struct _overlap go[4] ;
+		memset( go, 0, sizeof( go ) ) ;
+		for ( int j = 0 ; j < 4 ; ++j )
+			go[j].seqIdx = -1 ;
+		int runLo = 0 ;
+		uint32_t runGood = 0 ;
+		for ( int i = 0 ; i < n ; ++i )
+		{
+			t4_read_desc &r = d[i] ;
+			memset( &r, 0, sizeof( r ) ) ;
+			const char *read = sortedReads[i].read ;
+			const int len = (int)strlen( read ) ;
+			if ( len > T4_MAX_READ_LEN )
+			{
+				fprintf( stderr, "trust4_b200: read longer than %d bases\n", T4_MAX_READ_LEN ) ;
+				exit( 1 ) ;
+			}
+			const bool sameString = i > 0 && !strcmp( read, sortedReads[i - 1].read ) ;
+			const bool dup = sameString && sortedReads[i].barcode == sortedReads[i - 1].barcode ; // main.cpp:1596
+			if ( !sameString )
+				runLo = i ;
+			r.seq_off = pool.size() ;
+			pool.append( read, len ) ;
+			r.len = len ;
+			r.barcode = sortedReads[i].barcode ;
+			r.min_cnt = sortedReads[i].minCnt ;
+			r.min_kmer_count = hasBarcode ? ( sortedReads[i].minCnt + sortedReads[i].barcodeMinCnt + 1 ) / 2 : sortedReads[i].minCnt ;
+			r.sim_threshold = 0.9 ;
+			r.name_id = -1 ;
+			r.mate_idx = sortedReads[i].mateIdx ;
+			r.eq_lo = runLo ;
+			if ( dup )
+			{
+				r.flags = T4_RD_DUP | runGood ; // the static geneOverlap of main.cpp:1588 still holds the run's first read
+				continue ;
+			}
+			for ( int j = 0 ; j < 4 ; ++j )
+				go[j] = sortedReads[i].geneOverlap[j] ;
+			bool filter = false ;
+			for ( int j = 0 ; j < 4 && !filter ; ++j ) // main.cpp:1620-1638
+			{
+				if ( go[j].seqIdx == -1 )
+					continue ;
+				for ( int l = j + 1 ; l < 4 ; ++l )
+					if ( go[l].seqIdx != -1 && go[j].readEnd - 10 > go[l].readStart )
+					{
+						filter = true ;
+						break ;
+					}
+			}
+			if ( go[3].seqIdx != -1 && go[0].seqIdx == -1 && go[2].seqIdx == -1 ) // main.cpp:1640-1651
+			{
+				if ( go[3].seqStart >= constantGeneEnd )
+					filter = true ;
+				else if ( constantGeneEnd <= 200 && go[3].seqStart >= 100
+					&& ( go[3].strand == 1 || go[3].readEnd - go[3].readStart + 1 < sortedReads[i].len ) )
+					filter = true ;
+			}
+			uint32_t fl = 0 ;
+			if ( filter )
+				fl |= T4_RD_FILTERED ;
+			else
+			{
+				char name[5] = "" ;
+				int strand = 0, ambiguous = 0 ;
+				for ( int j = 0 ; j < 4 ; ++j ) // main.cpp:1660-1673
+					if ( go[j].seqIdx != -1 )
+					{
+						char *sn = refSet.GetSeqName( go[j].seqIdx ) ;
+						name[0] = sn[0] ; name[1] = sn[1] ; name[2] = sn[2] ; name[3] = sn[3] ; name[4] = '\0' ;
+						if ( strand != 0 && strand != go[j].strand )
+							ambiguous = 1 ;
+						strand = go[j].strand ;
+					}
+				if ( ambiguous )
+					strand = 0 ;
+				double thr = 0.9 ; // main.cpp:1675-1694
+				if ( sortedReads[i].minCnt >= 20 )
+					thr = 0.97 ;
+				else if ( sortedReads[i].minCnt >= 2 || ( sortedReads[i].minCnt >= 5 && firstReadLen > 200 ) )
+					thr = 0.95 ;
+				if ( name[0] == 'T' && thr < 0.95 )
+					thr = 0.95 ;
+				if ( hasBarcode || trimLevel > 1 )
+					thr = 0.9 ;
+				r.sim_threshold = thr ;
+				r.strand_in = (int8_t)strand ;
+				for ( int j = 0 ; j < 4 ; ++j )
+					r.gene4[j] = name[j] ;
+				// main.cpp:1704-1745: may InputNovelRead seed a contig when AddRead fails?
+				int matchCnt = 0, first = 4 ;
+				for ( int j = 3 ; j >= 0 ; --j )
+					if ( go[j].seqIdx != -1 )
+					{
+						matchCnt += go[j].matchCnt / 2 ;
+						first = j ;
+					}
+				bool f2 = true ;
+				if ( matchCnt >= 31 )
+					f2 = false ;
+				else if ( go[0].seqIdx != -1 && go[2].seqIdx != -1 && go[0].readEnd < go[2].readStart )
+					f2 = false ;
+				else if ( go[0].seqIdx != -1 )
+				{
+					if ( go[0].seqEnd >= refSet.GetSeqConsensusLen( go[0].seqIdx ) - 17 )
+						f2 = false ;
+				}
+				else if ( go[2].seqIdx != -1 )
+				{
+					if ( go[2].seqStart <= 17 )
+						f2 = false ;
+				}
+				if ( !f2 && first < 4 )
+				{
+					fl |= T4_RD_NOVEL_ON_FAIL ;
+					std::string gn( refSet.GetSeqName( go[first].seqIdx ) ) ;
+					std::map<std::string, int>::iterator it = nameId.find( gn ) ;
+					if ( it == nameId.end() )
+					{
+						nameId[gn] = (int)names.size() ;
+						r.name_id = (int)names.size() ;
+						names.push_back( gn ) ;
+					}
+					else
+						r.name_id = it->second ;
+					r.novel_strand = (int8_t)go[first].strand ;
+				}
+				if ( SeqSet::HasMotif( sortedReads[i].read, 1 ) ) // main.cpp:1752 (the result does not depend on the sign)
+					fl |= T4_RD_MOTIF ;
+			}
+			// main.cpp:1782-1808 for either outcome of sortedReads[i].strand; consulted only when the read was added
+			runGood = 0 ;
+			for ( int sgn = 1 ; sgn >= -1 ; sgn -= 2 )
+			{
+				bool good = false, maySpan = false ;
+				if ( go[0].seqIdx != -1 && go[0].similarity >= 0.9 && sgn == 1 )
+				{
+					good = true ;
+					if ( go[2].seqIdx != -1 && go[2].readStart > go[0].readEnd ) maySpan = true ;
+					if ( go[3].seqIdx != -1 && go[3].readStart > go[0].readEnd ) maySpan = true ;
+				}
+				for ( int j = 2 ; j <= 3 ; ++j )
+					if ( go[j].seqIdx != -1 && go[j].similarity >= 0.9 && sgn == -1 )
+					{
+						good = true ;
+						if ( go[0].seqIdx != -1 && go[j].readStart > go[0].readEnd ) maySpan = true ;
+					}
+				if ( maySpan )
+					good = false ;
+				if ( good )
+					runGood |= ( sgn == 1 ) ? T4_RD_GOOD_PLUS : T4_RD_GOOD_MINUS ;
+			}
+			r.flags = fl | runGood ;
+		}
+		for ( int i = n - 1, hi = n ; i >= 0 ; --i ) // eq_hi: end of the run of identical read strings (main.cpp:1826-1835)
+		{
+			d[i].eq_hi = hi ;
+			if ( d[i].eq_lo == i )
+				hi = i ;
+		}
+		// shards: contiguous, never splitting a run of identical reads nor (with barcodes) a barcode
+		if ( S > n )
+			S = n ;
+		std::vector<int64_t> off( S + 1, 0 ) ;
+		for ( int s = 1 ; s < S ; ++s )
+		{
+			int64_t b = (int64_t)n * s / S ;
+			b = d[b].eq_lo ;
+			if ( hasBarcode )
+				while ( b > 0 && d[b].barcode == d[b - 1].barcode && d[b].barcode != -1 )
+					--b ;
+			off[s] = b > off[s - 1] ? b : off[s - 1] ;
+		}
+		off[S] = n ;
+		for ( int s = 0 ; s < S ; ++s )
+			for ( int64_t i = off[s] ; i < off[s + 1] ; ++i )
+			{
+				int m = d[i].mate_idx ;
+				d[i].mate_idx = ( m >= off[s] && m < off[s + 1] ) ? (int)( m - off[s] ) : -1 ; // mates in other shards give no hint
+				d[i].eq_lo = (int)( ( d[i].eq_lo > off[s] ? d[i].eq_lo : off[s] ) - off[s] ) ;
+				d[i].eq_hi = (int)( ( d[i].eq_hi < off[s + 1] ? d[i].eq_hi : off[s + 1] ) - off[s] ) ;
+			}
+		if ( S > 1 )
+		{
+			sets.resize( S ) ;
+			Check( t4_seqsets_create_ex( S - 1, curK, curHitLen, curConsiderBarcode, sets.data() + 1 ) ) ;
+		}
+		t4_run_cfg cfg ;
+		memset( &cfg, 0, sizeof( cfg ) ) ;
+		cfg.has_barcode = hasBarcode ;
+		cfg.repetitive = trimLevel > 1 ;
+		cfg.change_k_threshold = changeKmerLengthThreshold ;
+		cfg.update_consensus_every = 10000 ;
+		cfg.do_rescue = 1 ;
+		cfg.first_read_len = firstReadLen ;
+		cfg.final_update = 1 ;
+		cfg.release_barcodes = hasBarcode && !keepMissingBarcode ;
+		cfg.contig_min_cov = contigMinCov ;
+		std::vector<const char *> np ;
+		for ( size_t i = 0 ; i < names.size() ; ++i )
+			np.push_back( names[i].c_str() ) ;
+		pool.append( 16, '\0' ) ;
+		t4_workload *w = t4_workload_upload( d.data(), n, pool.data(), pool.size(), np.data(), (int)np.size() ) ;
+		if ( !w )
+			Die() ;
+		Check( t4_streams_run_resident( sets.data(), S, &cfg, w, off.data(), NULL ) ) ;
+		bRet.resize( n ) ; bResc.resize( n ) ; bStrand.resize( n ) ; bEv.resize( n ) ;
+		Check( t4_workload_results( w, bRet.data(), bStrand.data(), bResc.data() ) ) ;
+		Check( t4_workload_events( w, bEv.data() ) ) ;
+		Check( t4_streams_error( sets.data(), S ) ) ;
+		t4_workload_free( w ) ;
+		rescueOrder.clear() ;
+		for ( int i = 0 ; i < n ; ++i )
+			if ( bRet[i] == -2 )
+				rescueOrder.push_back( i ) ;
+		int nk = 0 ;
+		for ( int i = 0 ; i < n ; ++i )
+			if ( bEv[i] & T4_EV_CHANGE_K )
+				++nk ;
+		maxFinalK = curK + 2 * ( S == 1 ? nk : ( nk > 0 ? 1 : 0 ) ) ;
+		for ( int s = 0 ; S > 1 && s < S ; ++s )
+		{
+			int ks = Check( t4_seqset_kmer_length( sets[s] ) ) ;
+			if ( ks > maxFinalK )
+				maxFinalK = ks ;
+		}
+		replay = true ;
+		cur = 0 ;
+		rescuePos = 0 ;
+		fprintf( stderr, "[trust4_b200] batch route: %d reads on %d device stream(s)\n", n, S ) ;
+	}
 
 	int AddRead( char *read, char *geneName, int &strand, int barcode, int minKmerCount, bool repetitiveData, double similarityThreshold )
 	{
 		if ( !gpu )
 			return SeqSet::AddRead( read, geneName, strand, barcode, minKmerCount, repetitiveData, similarityThreshold ) ;
+		if ( replay )
+		{
+			if ( cur < bRet.size() ) // main loop, iteration `cur` (Size() closes an iteration)
+			{
+				if ( bEv[cur] & ( T4_EV_NOVEL_ANCHORED | T4_EV_NOVEL_MOTIF ) )
+					return -1 ; // AddRead failed; the InputNovelRead that follows returns the recorded slot
+				if ( bRet[cur] >= 0 )
+					strand = bStrand[cur] ; // SeqSet.hpp:4469: only set on success
+				return bRet[cur] ;
+			}
+			// rescue pass (main.cpp:1897-1940): reads with addRet == -2, in order
+			if ( rescuePos >= rescueOrder.size() )
+			{
+				fprintf( stderr, "trust4_b200: replay out of step (rescue)\n" ) ;
+				exit( 1 ) ;
+			}
+			int i = rescueOrder[rescuePos++] ;
+			strand = bStrand[i] ;
+			return bResc[i] ;
+		}
 		return Check( t4_seqset_add_read( h, read, geneName, &strand, barcode, minKmerCount, repetitiveData, similarityThreshold ) ) ;
 	}
-	int RepeatAddRead( char *read ) { return gpu ? Check( t4_seqset_repeat_add_read( h, read ) ) : SeqSet::RepeatAddRead( read ) ; }
+	int RepeatAddRead( char *read )
+	{
+		if ( gpu && replay && cur < bRet.size() )
+			return bRet[cur] ;
+		return gpu ? Check( t4_seqset_repeat_add_read( h, read ) ) : SeqSet::RepeatAddRead( read ) ;
+	}
 	int InputNovelRead( const char *id, char *read, int strand, int barcode )
 	{
+		if ( gpu && replay && cur < bRet.size() )
+			return bRet[cur] ; // negative when the device loop made no such call (hint from a mate in another shard)
 		return gpu ? Check( t4_seqset_input_novel_read( h, id, read, strand, barcode ) ) : SeqSet::InputNovelRead( id, read, strand, barcode ) ;
 	}
-	void UpdateAllConsensus() { if ( gpu ) Check( t4_seqset_update_all_consensus( h ) ) ; else SeqSet::UpdateAllConsensus() ; }
+	void UpdateAllConsensus()
+	{
+		if ( gpu && replay )
+			return ; // done on the device (periodic, after the loop, after the rescue pass)
+		if ( gpu ) Check( t4_seqset_update_all_consensus( h ) ) ; else SeqSet::UpdateAllConsensus() ;
+	}
 	void ChangeKmerLength( int kl )
 	{
-		if ( gpu )
+		if ( gpu && !replay )
 			Check( t4_seqset_change_kmer_length( h, kl ) ) ;
+		if ( gpu )
+			curK = kl ;
 		SeqSet::ChangeKmerLength( kl ) ; // keeps kmerLength of the CPU object in step (its seqs are empty until SyncToHost)
 	}
-	int Size() { return gpu ? Check( t4_seqset_size( h ) ) : SeqSet::Size() ; }
+	int Size()
+	{
+		if ( gpu && replay )
+		{
+			// main.cpp:1874 asks once per iteration: answer so that the driver's indexKmerLength follows the device's k
+			int r = 0 ;
+			if ( cur < bEv.size() && ( bEv[cur] & T4_EV_CHANGE_K ) && curK < maxFinalK )
+				r = INT_MAX ;
+			++cur ;
+			return r ;
+		}
+		return gpu ? Check( t4_seqset_size( h ) ) : SeqSet::Size() ;
+	}
 	int SetHitLenRequired( int l )
 	{
 		if ( gpu )
+		{
 			Check( t4_seqset_set_hit_len_required( h, l ) ) ;
+			curHitLen = l ;
+		}
 		return SeqSet::SetHitLenRequired( l ) ;
 	}
 	void SetIsLongSeqSet( bool in )
@@ -159,7 +493,10 @@ public:
 	void SetConsiderBarcodeInIndexHash( bool s )
 	{
 		if ( gpu )
+		{
 			Check( t4_seqset_set_consider_barcode_in_hash( h, s ) ) ;
+			curConsiderBarcode = s ? 1 : 0 ;
+		}
 		SeqSet::SetConsiderBarcodeInIndexHash( s ) ;
 	}
 	// main.cpp:1855 -- one finished barcode, removeFromIndex = true, earlyStop = true
@@ -170,6 +507,8 @@ public:
 			SeqSet::ReleaseFinishedBarcodeSeq( barcodes, removeFromIndex, contigMinCov, earlyStop ) ;
 			return ;
 		}
+		if ( replay )
+			return ; // purged inside the device loop (cfg.release_barcodes)
 		if ( barcodes.size() != 1 || !removeFromIndex || !earlyStop )
 		{
 			fprintf( stderr, "trust4_b200: ReleaseFinishedBarcodeSeq is only supported as the stage-1 driver calls it\n" ) ;
@@ -181,7 +520,8 @@ public:
 	void ReleaseShallowContigs( int minCov )
 	{
 		if ( gpu )
-			Check( t4_seqset_release_shallow_contigs( h, minCov ) ) ;
+			for ( size_t i = 0 ; i < sets.size() ; ++i )
+				Check( t4_seqset_release_shallow_contigs( sets[i], minCov ) ) ;
 		else
 			SeqSet::ReleaseShallowContigs( minCov ) ;
 	}
@@ -200,6 +540,13 @@ public:
 			SeqSet::Output( fp, barcodeIntToStr ) ;
 			return ;
 		}
+		if ( sets.size() > 1 )
+		{
+			// read-sharded run: the output is the concatenation of the streams' contig sets with global slot numbers
+			SyncToHost() ;
+			SeqSet::Output( fp, barcodeIntToStr ) ;
+			return ;
+		}
 		std::vector<const char *> names ;
 		if ( barcodeIntToStr )
 			for ( size_t i = 0 ; i < barcodeIntToStr->size() ; ++i )
@@ -208,6 +555,10 @@ public:
 		SyncToHost() ; // from here on the driver only reads the contigs (main.cpp:2049 InputSeqSet)
 	}
 } ;
+
+// The one line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
+#define T4_BATCH_PREPARE() seqSet.BatchPrepare( sortedReads, refSet, readCnt, hasBarcode, keepMissingBarcode, trimLevel, firstReadLen, \
+	constantGeneEnd, contigMinCov, changeKmerLengthThreshold )
 
 #define SeqSet T4GpuSeqSet
 #endif

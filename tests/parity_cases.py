@@ -521,6 +521,62 @@ def check_barcode_release(lib, ref, seed=33):
     _same_sets(g, r)
 
 
+def check_single_cell(lib, ref, seed=51, n_barcodes=24, reads_per_barcode=150, n_shards=5, contig_min_cov=0):
+    """BASELINE configs[3] in small: 10x-style barcoded single-end reads, whole barcodes per stream,
+    hitLenRequired 13, barcode-salted index, finished barcodes purged -- per stream against the reference SeqSet driven
+    by the restated loop (return codes, strands, rescue codes, Output with barcode slots, index multiset, numRead)."""
+    lib.check(lib.reset())
+    cl = synth.make_clones(60, seed)
+    rd, bc = synth.sample_single_cell(cl, n_barcodes, reads_per_barcode, 150, seed)
+    w = synth.build_workload(cl, rd, barcode=bc)
+    cfg = synth.run_cfg(has_barcode=1, release_barcodes=1, contig_min_cov=contig_min_cov)
+    off, descs = synth.shard_workload(w, n_shards, align="barcode")
+    for j in range(1, n_shards):     # no barcode straddles two streams
+        assert descs["barcode"][off[j] - 1] != descs["barcode"][off[j]]
+    sets = api.SeqSet.create_many(n_shards, 9, lib, hit_len_required=13, consider_barcode=1)
+    ret, strands, resc = api.streams_run(sets, cfg, descs, off, w.pool, w.names, lib)
+    total = 0
+    for j in range(n_shards):
+        lo, hi = int(off[j]), int(off[j + 1])
+        r = ref.RefSeqSet(9)
+        r.set_hit_len_required(13)
+        ref.lib().t4ref_set_consider_barcode_in_hash(r.h, 1)
+        _, rret, rstr, rresc = r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)
+        assert (rret == ret[lo:hi]).all(), ("ret", j, np.flatnonzero(rret != ret[lo:hi])[:5])
+        assert (rstr == strands[lo:hi]).all() and (rresc == resc[lo:hi]).all(), ("strand/rescue", j)
+        _same_sets(sets[j], r)
+        total += int((rret >= 0).sum())
+    assert total > n_barcodes * reads_per_barcode // 2
+    return total
+
+
+def check_repseq(lib, ref, seed=61, n_reads=4000, n_shards=3):
+    """BASELINE configs[4] in small: --repseq (trimLevel 2) amplicon TCR-seq reads, 100 bp single end: repetitiveData = true
+    (skip-repeats first pass SeqSet.hpp:1520-1531, ExtendOverlap mismatch factor 2.0 :1226-1237), V-gene pseudo barcodes
+    on an unsalted index (main.cpp:1224-1235), halved k-change threshold (main.cpp:1567)."""
+    lib.check(lib.reset())
+    cl = synth.make_clones(120, seed, chains=("TRB",))
+    rd = synth.sample_amplicon(cl, n_reads, 100, seed)
+    w = synth.build_workload(cl, rd, repseq=True)
+    assert (w.descs["barcode"] >= 0).mean() > 0.5
+    cfg = synth.run_cfg(repetitive=1, change_k_threshold=40, first_read_len=100)      # small threshold: k changes mid-run
+    off, descs = synth.shard_workload(w, n_shards)
+    sets = api.SeqSet.create_many(n_shards, 9, lib, hit_len_required=50)           # main.cpp:1541-1547: max(21, L/2) when L/2 < 31 -> here L/2 = 50 > 31 keeps 31; exercise the setter anyway
+    for s_ in sets:
+        s_.set_hit_len_required(31)
+    ret, strands, resc = api.streams_run(sets, cfg, descs, off, w.pool, w.names, lib)
+    for j in range(n_shards):
+        lo, hi = int(off[j]), int(off[j + 1])
+        r = ref.RefSeqSet(9)
+        _, rret, rstr, rresc = r.run_descs(cfg, descs[lo:hi].copy(), w.pool, w.names)
+        assert (rret == ret[lo:hi]).all(), ("ret", j, np.flatnonzero(rret != ret[lo:hi])[:5])
+        assert (rstr == strands[lo:hi]).all() and (rresc == resc[lo:hi]).all(), ("strand/rescue", j)
+        assert r.output() == sets[j].output(), ("contigs", j)
+        assert r.index_checksum() == sets[j].index_checksum(), ("index", j)
+        assert r.kmer_length() == sets[j].kmer_length()
+    assert int((ret >= 0).sum()) > n_reads // 2
+
+
 def check_input_novel_fa(lib, ref, tmp_path):
     """SeqSet::InputNovelFa (SeqSet.hpp:2986, --debug-ns)."""
     lib.check(lib.reset())

@@ -46,6 +46,15 @@ def test_emu_barcode_release(emu_lib, ref):
     pc.check_barcode_release(emu_lib, ref)
 
 
+def test_emu_single_cell_streams(emu_lib, ref):
+    pc.check_single_cell(emu_lib, ref)
+    pc.check_single_cell(emu_lib, ref, seed=52, n_barcodes=9, reads_per_barcode=260, n_shards=2, contig_min_cov=3)
+
+
+def test_emu_repseq_streams(emu_lib, ref):
+    pc.check_repseq(emu_lib, ref)
+
+
 def test_emu_input_novel_fa(emu_lib, ref, tmp_path):
     pc.check_input_novel_fa(emu_lib, ref, tmp_path)
 

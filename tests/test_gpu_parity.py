@@ -110,3 +110,14 @@ def test_gpu_probe_batch(gpu_lib, ref):
     """The dedicated warp-per-read probe kernel (t4_probe_kernel) vs the reference's GetHitsFromRead."""
     pc.check_probe_batch(gpu_lib, ref, seed=41, n_shards=5)
     pc.check_probe_batch(gpu_lib, ref, seed=42, n_shards=1, sample=120)
+
+
+def test_gpu_single_cell_streams(gpu_lib, ref):
+    """configs[3] in small: barcode-partitioned streams with per-barcode purge, on the device."""
+    pc.check_single_cell(gpu_lib, ref, n_barcodes=60, reads_per_barcode=400, n_shards=7)
+    pc.check_single_cell(gpu_lib, ref, seed=52, n_barcodes=9, reads_per_barcode=260, n_shards=2, contig_min_cov=3)
+
+
+def test_gpu_repseq_streams(gpu_lib, ref):
+    """configs[4] in small: repetitiveData = true (allowTotalSkip pass, mismatch factor 2.0), pseudo barcodes."""
+    pc.check_repseq(gpu_lib, ref, n_reads=12000, n_shards=4)

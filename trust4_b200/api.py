@@ -23,14 +23,14 @@ N_COUNTERS = 24
 
 EXPORTS = [
     "init", "shutdown", "last_error", "version", "arena_stats", "reset",
-    "seqset_create", "seqsets_create", "seqset_destroy", "seqset_set_hit_len_required",
+    "seqset_create", "seqsets_create", "seqsets_create_ex", "seqset_destroy", "seqset_set_hit_len_required",
     "seqset_set_novel_seq_similarity", "seqset_set_consider_barcode_in_hash", "seqset_set_is_long",
     "seqset_size", "seqset_kmer_length", "seqset_add_read", "seqset_repeat_add_read",
     "seqset_input_novel_read", "seqset_update_all_consensus", "seqset_change_kmer_length",
     "seqset_output", "seqset_output_mem", "free", "seqset_get_contig", "has_motif",
     "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch", "dp_hot_path_batch",
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
-    "streams_run_resident", "workload_results", "last_counters", "streams_error",
+    "streams_run_resident", "workload_results", "workload_events", "last_counters", "streams_error",
     "hits_create", "hits_free", "streams_get_hits", "hits_stats", "hits_fetch", "hits_device_buffers",
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
     "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
@@ -64,6 +64,7 @@ class Lib:
         f("arena_stats", ci, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)])
         f("seqset_create", vp, [ci])
         f("seqsets_create", ci, [ci, ci, C.POINTER(vp)])
+        f("seqsets_create_ex", ci, [ci, ci, ci, ci, C.POINTER(vp)])
         f("seqset_destroy", None, [vp])
         f("seqset_set_hit_len_required", ci, [vp, ci])
         f("seqset_set_novel_seq_similarity", ci, [vp, cd])
@@ -95,6 +96,7 @@ class Lib:
         f("workload_free", None, [vp])
         f("streams_run_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, vp])
         f("workload_results", ci, [vp, vp, vp, vp])
+        f("workload_events", ci, [vp, vp])
         f("last_counters", ci, [vp])
         f("hits_create", vp, [C.c_int64, C.c_size_t])
         f("hits_free", None, [vp])
@@ -149,10 +151,10 @@ class SeqSet:
         self.h = C.c_void_p(handle)
 
     @classmethod
-    def create_many(cls, n, k=9, lib: Lib | None = None):
+    def create_many(cls, n, k=9, lib: Lib | None = None, hit_len_required=31, consider_barcode=0):
         lib = lib or default_lib()
         arr = (C.c_void_p * n)()
-        lib.check(lib.seqsets_create(n, k, arr))
+        lib.check(lib.seqsets_create_ex(n, k, hit_len_required, consider_barcode, arr))
         return [cls(k, lib, arr[i]) for i in range(n)]
 
     def close(self):

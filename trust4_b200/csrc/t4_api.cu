@@ -389,6 +389,7 @@ struct t4_workload
 	int32_t *rescueList ;
 	int8_t *good ;
 	int32_t *info ;
+	uint8_t *events ;
 	T4Op *ops ;
 	int opCap ;
 	bool persistent ;
@@ -557,7 +558,26 @@ static int reset_counters()
 }
 
 // Create n seqsets in one go (one init launch).  handles[i] receives the new set.
+static int seqsets_create_impl( int n, int kmer_length, int hit_len_required, int consider_barcode, t4_seqset **handles ) ;
+
 int T4_API( seqsets_create )( int n, int kmer_length, t4_seqset **handles )
+{
+	return seqsets_create_impl( n, kmer_length, 31, 0, handles ) ;
+}
+
+// The same with SetHitLenRequired / SetConsiderBarcodeInIndexHash applied to every set by the init launch
+// (main.cpp:1549-1565 configures the set once before the loop; thousands of streams should not cost thousands of copies).
+int T4_API( seqsets_create_ex )( int n, int kmer_length, int hit_len_required, int consider_barcode, t4_seqset **handles )
+{
+	if ( consider_barcode && kmer_length > 15 )
+	{
+		set_err( "barcode-salted index needs k <= 15" ) ;
+		return T4_E_UNSUPPORTED ;
+	}
+	return seqsets_create_impl( n, kmer_length, hit_len_required, consider_barcode ? 1 : 0, handles ) ;
+}
+
+static int seqsets_create_impl( int n, int kmer_length, int hit_len_required, int consider_barcode, t4_seqset **handles )
 {
 	int r = ensure_up() ;
 	if ( r ) return r ;
@@ -567,6 +587,8 @@ int T4_API( seqsets_create )( int n, int kmer_length, t4_seqset **handles )
 		return T4_E_INVAL ;
 	}
 	T4InitParams ip ;
+	ip.hitLenRequired = hit_len_required ;
+	ip.considerBarcode = consider_barcode ;
 	ip.kmerLength = kmer_length ;
 	ip.nomatchGapLimit = E.hostGap[kmer_length] ;
 	ip.nThreads = E.nt ;
@@ -1383,7 +1405,8 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 	size_t oRl = oResc + al( (size_t)n * 4 ) ;
 	size_t oGood = oRl + al( (size_t)n * 4 ) ;
 	size_t oInfo = oGood + al( (size_t)n ) ;
-	size_t oOps = oInfo + al( (size_t)n * 4 ) ;
+	size_t oEv = oInfo + al( (size_t)n * 4 ) ;
+	size_t oOps = oEv + al( (size_t)n ) ;
 	// 2-bit packed copy of the reads, fixed stride (the longest supported read of the workload)
 	int maxLen = 0 ;
 	for ( int64_t i = 0 ; i < n ; ++i )
@@ -1429,6 +1452,7 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 	w->rescueList = (int32_t *)( w->buf + oRl ) ;
 	w->good = (int8_t *)( w->buf + oGood ) ;
 	w->info = (int32_t *)( w->buf + oInfo ) ;
+	w->events = (uint8_t *)( w->buf + oEv ) ;
 	w->packed = (u64 *)( w->buf + oPacked ) ;
 	w->packStride = packStride ;
 	w->usePacked = false ;
@@ -1535,6 +1559,7 @@ static int build_ops( t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg,
 		op.rescueList = (u64)(uintptr_t)( w->rescueList + lo ) ;
 		op.good = (u64)(uintptr_t)( w->good + lo ) ;
 		op.info = (u64)(uintptr_t)( w->info + lo ) ;
+		op.events = (u64)(uintptr_t)( w->events + lo ) ;
 		if ( w->usePacked )
 		{
 			op.packed = (u64)(uintptr_t)( w->packed + (u64)lo * w->packStride ) ;
@@ -1824,6 +1849,15 @@ int T4_API( workload_results )( t4_workload *w, int32_t *ret_codes, int8_t *stra
 	if ( strands && ( r = d2h( strands, w->strands, (size_t)w->nDescs ) ) ) return r ;
 	if ( rescue_ret && ( r = d2h( rescue_ret, w->rescue, (size_t)w->nDescs * 4 ) ) ) return r ;
 	return 0 ;
+}
+
+int T4_API( workload_events )( t4_workload *w, uint8_t *events )
+{
+	if ( !w || !events )
+		return T4_E_INVAL ;
+	int r = dsync() ;
+	if ( r ) return r ;
+	return d2h( events, w->events, (size_t)w->nDescs ) ;
 }
 
 int T4_API( streams_pack_contigs )( t4_seqset *const *sets, int n_sets, void *dev_buf, size_t cap, size_t *bytes_needed, int64_t *n_contigs )

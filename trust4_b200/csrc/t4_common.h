@@ -229,6 +229,7 @@ struct T4Op                // per-CTA launch record
 	u64 rescueList ;               // int32[n] scratch
 	u64 good ;                     // int8[n] goodCandidate
 	u64 info ;                     // int32[n]
+	u64 events ;                   // uint8[n] T4_EV_* of every loop iteration (absolute), 0 = not recorded
 	u64 packed ;                   // 2-bit packed reads of this op's records (absolute; record i at packed + i * packStride words), 0 = ASCII pool
 	u64 packStride ;               // u64 words per record
 	t4_run_cfg cfg ;
@@ -259,6 +260,8 @@ struct T4InitParams        // T4_OP_INIT: lay out and initialise a fresh stream 
 	int nThreads ;
 	u32 seqCap, dirCap, hitCap, ovlCap ;
 	u32 footprint ;
+	int hitLenRequired ;       // SetHitLenRequired (SeqSet.hpp:2601), 31 by default
+	int considerBarcode ;      // SetConsiderBarcodeInIndexHash (SeqSet.hpp:2611)
 } ;
 
 #endif

@@ -4144,6 +4144,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 	const int n = op->n ;
 	const u64 *packed = t4_x<u64>( op->packed ) ;
 	const u64 packStride = op->packStride ;
+	uint8_t *events = t4_x<uint8_t>( op->events ) ;
 	T4_PAR_FOR( i, n )
 	{
 		goodCandidate[i] = 0 ;
@@ -4204,11 +4205,13 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		else
 			c_load_read( cx, pool + d.seq_off, d.len ) ;
 		int finalStrand = 0 ;
+		u32 ev = 0 ;
 		if ( !( d.flags & T4_RD_DUP ) )
 		{
 			int strand = 0 ;
 			if ( !( d.flags & T4_RD_FILTERED ) )
 			{
+				ev |= T4_EV_ADD_READ ;
 				char name[5] ;
 				name[0] = d.gene4[0] ; name[1] = d.gene4[1] ; name[2] = d.gene4[2] ; name[3] = d.gene4[3] ; name[4] = '\0' ;
 				strand = d.strand_in ;
@@ -4222,6 +4225,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 					int nmLen = 0 ;
 					if ( d.flags & T4_RD_NOVEL_ON_FAIL )
 					{
+						ev |= T4_EV_NOVEL_ANCHORED ;
 						novelStrand = d.novel_strand ;
 						nm = namePool + nameOff[d.name_id] ;
 						nmLen = (int)( nameOff[d.name_id + 1] - nameOff[d.name_id] ) ;
@@ -4230,6 +4234,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 					{
 						if ( d.novel_strand != 0 && ( d.flags & T4_RD_MOTIF ) )
 						{
+							ev |= T4_EV_NOVEL_MOTIF ;
 							novelStrand = d.novel_strand ;
 							nm = "Novel" ;
 							nmLen = 5 ;
@@ -4240,6 +4245,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 						int ms = -strands[info[i]] ;
 						if ( ms != 0 && ( d.flags & T4_RD_MOTIF ) )
 						{
+							ev |= T4_EV_NOVEL_MOTIF ;
 							novelStrand = ms ;
 							nm = "Novel" ;
 							nmLen = 5 ;
@@ -4259,7 +4265,10 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		{
 			T4_PHASE( cx, 7 ) ;
 			if ( prevAddRet != -1 && prevAddRet != -3 )
+			{
+				ev |= T4_EV_REPEAT ;
 				addRet = c_repeat_add_read( cx, d.len ) ;
+			}
 			else if ( prevAddRet == -3 )
 				addRet = -3 ;
 			T4_PHASE( cx, 0 ) ;
@@ -4319,6 +4328,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			T4_SYNC() ;
 			if ( fin )
 			{
+				ev |= T4_EV_PURGED ;
 				T4_PHASE( cx, 7 ) ;
 				c_release_barcode( cx, d.barcode, cfg.contig_min_cov ) ;
 				T4_PHASE( cx, 0 ) ;
@@ -4336,8 +4346,11 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		{
 			changeKmerLengthThreshold *= 4 ;
 			indexKmerLength += 2 ;
+			ev |= T4_EV_CHANGE_K ;
 			c_change_kmer_length( cx, indexKmerLength, gapLimitTable[indexKmerLength] ) ;
 		}
+		if ( events && cx.tid == 0 )
+			events[i] = (uint8_t)ev ;
 	}
 	T4_PHASE( cx, 7 ) ;
 	if ( cfg.final_update && !st->error )
@@ -4360,6 +4373,8 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			{
 				strands[i] = (int8_t)strand ;
 				rescueRet[i] = addRet ;
+				if ( events )
+					events[i] |= T4_EV_RESCUED ;
 			}
 			T4_SYNC() ;
 		}
@@ -4404,10 +4419,10 @@ T4_D inline void c_init_stream( T4Ctx &cx, u64 base, const T4InitParams &ip )
 		memset( st, 0, sizeof( T4Stream ) ) ;
 		st->kmerLength = ip.kmerLength ;
 		st->radius = 10 ;
-		st->hitLenRequired = 31 ;
+		st->hitLenRequired = ip.hitLenRequired ;
 		st->nomatchGapLimit = ip.nomatchGapLimit ;
 		st->isLongSeqSet = 0 ;
-		st->considerBarcode = 0 ;
+		st->considerBarcode = ip.considerBarcode ;
 		st->novelSeqSimilarity = 0.9 ;
 		st->repeatSimilarity = 0.95 ;
 		st->nSeqs = 0 ;

@@ -49,7 +49,7 @@ struct T4ProbeParams
 	int allowTotalSkip ;
 } ;
 
-struct T4ProbeWarp
+struct __align__( 16 ) T4ProbeWarp // sizeof is a multiple of 16: every warp's staging tile is a legal TMA destination
 {
 	u64 stg[T4P_STG] ;         // 16-byte aligned TMA destination
 	u64 fw[18], rc[18] ;       // packed words (+ zero padding for the two-word funnel shift)

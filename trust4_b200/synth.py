@@ -198,6 +198,56 @@ def sample_pairs(clones: Clones, npairs: int, L: int, seed: int, alpha: float = 
     return Reads(codes, clone.astype(np.int64), tstart, strand, pair, L)
 
 
+def sample_single_cell(clones: Clones, n_barcodes: int, reads_per_barcode: int, L: int, seed: int, ambient: float = 0.02,
+                       sub_rate: float = 0.005):
+    """10x-style single-cell reads (SURVEY.md 8d config 4 / BASELINE configs[3]): every cell (barcode) expresses one or
+    two clonotypes (e.g. a heavy/beta and a light/alpha chain), `reads_per_barcode` single-end reads each, plus a
+    fraction of ambient reads drawn from the clones of other cells.  Returns (Reads, barcode[n])."""
+    rng = np.random.default_rng([seed, 0x10C])
+    nclones = len(clones.off) - 1
+    n = n_barcodes * reads_per_barcode
+    bc = np.repeat(np.arange(n_barcodes, dtype=np.int64), reads_per_barcode)
+    c1 = rng.integers(0, nclones, size=n_barcodes)
+    c2 = rng.integers(0, nclones, size=n_barcodes)
+    two = rng.random(n_barcodes) < 0.7
+    pick2 = two[bc] & (rng.random(n) < 0.4)
+    cl = np.where(pick2, c2[bc], c1[bc])
+    amb = rng.random(n) < ambient
+    cl = np.where(amb, rng.integers(0, nclones, size=n), cl)
+    tlen = (clones.off[1:] - clones.off[:-1])[cl]
+    start = (rng.random(n) * (tlen - L + 1)).astype(np.int64)
+    base = clones.off[cl] + start
+    ar = np.arange(L, dtype=np.int64)
+    fwd = clones.seq[base[:, None] + ar[None, :]]
+    rev = 3 - clones.seq[(base + L - 1)[:, None] - ar[None, :]]
+    minus = rng.random(n) < 0.5
+    codes = np.where(minus[:, None], rev, fwd)
+    err = rng.random(codes.shape) < sub_rate
+    sub = rng.integers(0, 4, size=codes.shape, dtype=np.uint8)
+    codes = np.where(err, sub, codes).astype(np.uint8)
+    strand = np.where(minus, -1, 1).astype(np.int8)
+    return Reads(codes, cl.astype(np.int64), start, strand, np.arange(n, dtype=np.int64), L), bc
+
+
+def sample_amplicon(clones: Clones, n: int, L: int, seed: int, alpha: float = 1.0, primer_in_c: int = 20, sub_rate: float = 0.005) -> Reads:
+    """Bulk TCR-seq amplicon reads (SURVEY.md 8d config 5 / BASELINE configs[4]): every read starts at the C-gene primer
+    (`primer_in_c` bases into the constant region) and runs antisense across J and the CDR3 into V; clonotype
+    abundance follows rank^-alpha."""
+    rng = np.random.default_rng([seed, 0xA3B])
+    nclones = len(clones.off) - 1
+    w = 1.0 / np.power(np.arange(1, nclones + 1, dtype=np.float64), alpha)
+    w /= w.sum()
+    cl = rng.choice(nclones, size=n, p=w)
+    end = clones.seg_end[cl, 2].astype(np.int64) + primer_in_c          # exclusive transcript coordinate of the primer end
+    start = np.maximum(0, end - L)
+    ar = np.arange(L, dtype=np.int64)
+    codes = 3 - clones.seq[(clones.off[cl] + start + L - 1)[:, None] - ar[None, :]]
+    err = rng.random(codes.shape) < sub_rate
+    sub = rng.integers(0, 4, size=codes.shape, dtype=np.uint8)
+    codes = np.where(err, sub, codes).astype(np.uint8)
+    return Reads(codes, cl.astype(np.int64), start, -np.ones(n, dtype=np.int8), np.arange(n, dtype=np.int64), L)
+
+
 def write_fastq(reads: Reads, prefix: str):
     """Write <prefix>_1.fq / _2.fq (mates interleaved in `reads`) for the reference binary."""
     L = reads.L
@@ -211,7 +261,7 @@ def write_fastq(reads: Reads, prefix: str):
 # ---------------------------------------------------------------------------
 # pre-processing stand-in: k-mer statistics, sort, annotation from truth
 # ---------------------------------------------------------------------------
-def kmer_stats(codes: np.ndarray, k: int = 21, device=None):
+def kmer_stats(codes: np.ndarray, k: int = 21, device=None, salt=None):
     """Canonical k-mer counts over all reads -> per-read (min, median, mean) like
     KmerCount::GetCountStatsAndTrim (KmerCount.hpp:177) without trimming.  `device`: a torch device
     to do the counting on (workload preparation only -- 260 M k-mers for 1 M pairs)."""
@@ -225,7 +275,10 @@ def kmer_stats(codes: np.ndarray, k: int = 21, device=None):
         for j in range(k):
             fw = (fw << 2) | c[:, j:j + m]
             rc = rc | ((3 - c[:, j:j + m]) << (2 * j))
-        canon = torch.minimum(fw, rc).reshape(-1)
+        canon = torch.minimum(fw, rc)
+        if salt is not None:      # per-read salt above the 2k code bits: counts per (k-mer, cell) -- the barcode-wise KmerCount of main.cpp:1128-1150
+            canon = canon | (torch.from_numpy(np.ascontiguousarray(salt, dtype=np.int64)).to(device)[:, None] << (2 * k))
+        canon = canon.reshape(-1)
         del fw, rc, c
         uniq, inv, cnt = torch.unique(canon, return_inverse=True, return_counts=True)
         del canon, uniq
@@ -242,7 +295,10 @@ def kmer_stats(codes: np.ndarray, k: int = 21, device=None):
     for j in range(k):
         fw = (fw << np.uint64(2)) | c64[:, j:j + m]
         rc = rc | ((np.uint64(3) - c64[:, j:j + m]) << np.uint64(2 * j))
-    canon = np.minimum(fw, rc).ravel()
+    canon = np.minimum(fw, rc)
+    if salt is not None:
+        canon = canon | (np.asarray(salt, dtype=np.uint64)[:, None] << np.uint64(2 * k))
+    canon = canon.ravel()
     uniq, inv, cnt = np.unique(canon, return_inverse=True, return_counts=True)
     per = cnt[inv].reshape(n, m)
     per_sorted = np.sort(per, axis=1)
@@ -283,16 +339,26 @@ class Workload:
     names: list            # gene names (bytes)
     L: int
     order: np.ndarray      # index into the unsorted reads for each desc
+    med_cnt: np.ndarray = None   # medianCnt of the 21-mer statistics per record (cost model of the sharding only)
 
     def read(self, i: int) -> str:
         d = self.descs[i]
         return self.pool[int(d["seq_off"]): int(d["seq_off"]) + int(d["len"])].tobytes().decode()
 
 
-def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=None) -> Workload:
-    """Truth-annotated stand-in for main.cpp:981-1526 -> AddRead-loop records."""
+def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=None, barcode=None, repseq: bool = False) -> Workload:
+    """Truth-annotated stand-in for main.cpp:981-1526 -> AddRead-loop records.
+
+    barcode: per-read cell barcode (10x mode, BASELINE configs[3]): 21-mer statistics are taken per cell (the stand-in
+             uses them for both minCnt and barcodeMinCnt), records are ordered by CompReadWithBarcode (main.cpp:128:
+             barcode, then barcodeMinCnt desc, then the default order), duplicates need equal barcodes (main.cpp:1596),
+             minKmerCount = (minCnt + barcodeMinCnt + 1) / 2 and similarityThreshold = 0.9 (main.cpp:1694, 1701).
+    repseq:  --repseq = --trimLevel 2 (BASELINE configs[4]): the V gene assignment becomes a pseudo barcode
+             (main.cpp:1224-1235, no re-sort, index not salted) and similarityThreshold = 0.9 (main.cpp:1693)."""
     n, L = reads.codes.shape
-    mn, med, avg = kmer_stats(reads.codes, device=device)
+    if barcode is not None:
+        barcode = np.asarray(barcode, dtype=np.int64)
+    mn, med, avg = kmer_stats(reads.codes, device=device, salt=barcode)
     # sort: minCnt desc, medianCnt desc, avgCnt desc, len desc, read asc, id asc  (main.cpp:103-125)
     words = []
     nw = (L + 31) // 32
@@ -304,7 +370,10 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
             wv = (wv << np.uint64(2)) | padded[:, wi * 32 + j]
         words.append(wv)
     keys = [np.arange(n)] + words[::-1] + [-avg.astype(np.float64), -med.astype(np.int64), -mn.astype(np.int64)]
+    if barcode is not None:
+        keys.append(barcode)
     order = np.lexsort(keys)
+    bc_sorted = barcode[order] if barcode is not None else None
     codes = reads.codes[order]
     cl = reads.clone[order]
     ts = reads.tstart[order]
@@ -322,6 +391,9 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
 
     same_prev = np.zeros(n, dtype=bool)
     same_prev[1:] = (codes[1:] == codes[:-1]).all(axis=1)
+    if bc_sorted is not None:
+        same_prev[1:] &= bc_sorted[1:] == bc_sorted[:-1]
+        descs["barcode"] = bc_sorted.astype(np.int32)
     flags = np.zeros(n, dtype=np.uint32)
     flags[same_prev] |= RD_DUP
     run_id = np.cumsum(~same_prev) - 1
@@ -400,7 +472,16 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
     thr[mn >= 20] = 0.97
     tcr = np.array([g[:1] == b"T" for g in gene4])
     thr[tcr & (thr < 0.95)] = 0.95
+    if barcode is not None or repseq:
+        thr[:] = 0.9                                           # main.cpp:1692-1694
     descs["sim_threshold"] = thr
+    if repseq:
+        # pseudo barcode = index of the V gene in the reference set (any injective numbering of the V names does)
+        vid = {}
+        pb = np.full(n, -1, dtype=np.int32)
+        idx = np.flatnonzero(pv)
+        pb[idx] = [vid.setdefault(gname[c][0], len(vid)) for c in cl[idx]]
+        descs["barcode"] = pb
 
     # main.cpp:1706-1736: may the read seed a new contig when AddRead fails?
     match_half = (np.where(present, ov, 0)).sum(axis=1)
@@ -423,7 +504,7 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
     keep = RD_GOOD_PLUS | RD_GOOD_MINUS
     flags = np.where(same_prev, (flags & ~np.uint32(keep)) | (flags[first_of_run] & np.uint32(keep)), flags)
     descs["flags"] = flags
-    return Workload(descs, pool, names, L, order)
+    return Workload(descs, pool, names, L, order, med.astype(np.int32))
 
 
 # Cost model of one record in the stream kernel, used to size contiguous shards (relative units).  A duplicate is a
@@ -444,14 +525,15 @@ def read_cost(descs) -> np.ndarray:
     return c
 
 
-def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str = "reads"):
+def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str = "reads", align: str = "run"):
     """Shard the sorted records into n_shards independent streams.  Returns desc_off[n_shards+1]
     and the records in stream order with mate_idx / eq_* made stream-relative (mates in other streams -> -1).
     A run of identical reads is never split (RepeatAddRead semantics survive), and every stream keeps the global
     sorted order of its reads.
 
     deal=False: contiguous blocks of the sorted list; balance = "reads" (equal read counts) or "cost" (equal predicted
-                cost, read_cost()).
+                cost, read_cost()); align = "run" (never split a run of identical reads) or "barcode" (never split a
+                barcode: 10x mode, barcodes are independent assemblies).
     deal=True : runs are dealt round-robin (run r -> stream r mod n_shards).  Every stream then sees a uniform sample
                 of the library instead of one abundance class, which equalises the work per stream (contiguous blocks
                 of low-abundance reads are ~50x more expensive than blocks of duplicates)."""
@@ -492,8 +574,17 @@ def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str 
         cuts = np.searchsorted(cum, cum[-1] * np.arange(1, n_shards) / n_shards, side="left")
     else:
         cuts = (n * np.arange(1, n_shards)) // n_shards
+    if align == "barcode":
+        # whole barcodes per stream: a cut moves back to the first record of its barcode
+        bcs = w.descs["barcode"]
+        first_of_bc = np.flatnonzero(np.r_[True, bcs[1:] != bcs[:-1]])
     for b in cuts:
-        b = int(w.descs["eq_lo"][b]) if b < n else n
+        if b >= n:
+            b = n
+        elif align == "barcode":
+            b = int(first_of_bc[np.searchsorted(first_of_bc, b, side="right") - 1])
+        else:
+            b = int(w.descs["eq_lo"][b])
         bounds.append(max(b, bounds[-1]))
     bounds.append(n)
     off = np.array(bounds, dtype=np.int64)
