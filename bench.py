@@ -403,8 +403,8 @@ def main():
     cycf = cyc.astype(np.float64)
     if args.dump_streams and rank == 0:
         lib.check(lib.workload_results(wl, ret.data_ptr(), strands.data_ptr(), resc.data_ptr()))
-        np.savez_compressed(args.dump_streams, cycles=cyc, off=off64, flags=descs["flags"], min_cnt=descs["min_cnt"], eq_lo=descs["eq_lo"],
-                            eq_hi=descs["eq_hi"], ret=ret.numpy().copy())
+        np.savez_compressed(args.dump_streams, cycles=cyc, off=off64, flags=descs["flags"], min_cnt=descs["min_cnt"], med=w.med_cnt,
+                            ret=ret.numpy().copy())
     balance = {"mean_ms": float(cycf.mean() / 1.965e6), "max_ms": float(cycf.max() / 1.965e6), "p50_ms": float(np.median(cycf) / 1.965e6),
                "p99_ms": float(np.percentile(cycf, 99) / 1.965e6), "reads_per_stream_min_max": [int(np.diff(off64).min()), int(np.diff(off64).max())],
                "by_decile_of_stream_index_ms": [float(x.mean() / 1.965e6) for x in np.array_split(cycf, 10)]}

@@ -65,7 +65,7 @@ def test_sharding_invariants():
     for deal, balance in ((False, "reads"), (True, "reads"), (False, "cost")):
         off, d = synth.shard_workload(w, 7, deal=deal, balance=balance)
         if balance == "cost":
-            cost = np.add.reduceat(synth.read_cost(d), off[:-1][np.diff(off) > 0])
+            cost = np.add.reduceat(synth.read_cost(w.descs, w.med_cnt), off[:-1][np.diff(off) > 0])
             assert cost.max() < 2.0 * cost.mean()          # cut by predicted cost, not by read count
         assert off[0] == 0 and off[-1] == n and (np.diff(off) >= 0).all()
         seen = np.zeros(n, dtype=int)

@@ -1717,16 +1717,21 @@ int T4_API( streams_get_hits )( t4_seqset *const *sets, int n_sets, t4_workload 
 	P.ctrl = h->ctrl ;
 	P.allowTotalSkip = allow_total_skip ? 1 : 0 ;
 	static int probeBlocks = 0 ;
+	static void ( *probeKernel )( T4ProbeParams ) = 0 ;
+	const size_t probeSmem = sizeof( T4ProbeWarp ) * T4P_WARPS ;
 	if ( probeBlocks == 0 )
 	{
 		int perSm = 0, sms = 0 ;
-		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, t4_probe_kernel, 32 * T4P_WARPS, 0 ) ) ;
+		const char *pv = getenv( "T4_PROBE_MINB" ) ;
+		probeKernel = ( pv && atoi( pv ) == 2 ) ? t4_probe_kernel<2> : t4_probe_kernel<3> ;
+		CK( cudaFuncSetAttribute( probeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probeSmem ) ) ;
+		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, probeKernel, 32 * T4P_WARPS, probeSmem ) ) ;
 		CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ) ;
 		probeBlocks = ( perSm > 0 ? perSm : 1 ) * ( sms > 0 ? sms : 148 ) ; // persistent: one wave, a multiple of the SM count
 	}
 	i64 need = ( n + T4P_WARPS - 1 ) / T4P_WARPS ;
 	int blocks = need < probeBlocks ? (int)need : probeBlocks ;
-	t4_probe_kernel<<<blocks, 32 * T4P_WARPS, 0, cs>>>( P ) ;
+	probeKernel<<<blocks, 32 * T4P_WARPS, probeSmem, cs>>>( P ) ;
 	CK( cudaGetLastError() ) ;
 #else
 	// TEST EMULATION: the same result through the stream engine's own GetHitsFromRead, one read at a time

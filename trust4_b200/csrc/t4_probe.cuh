@@ -52,6 +52,10 @@ struct T4ProbeParams
 struct __align__( 16 ) T4ProbeWarp // sizeof is a multiple of 16: every warp's staging tile is a legal TMA destination
 {
 	u64 stg[T4P_STG] ;         // 16-byte aligned TMA destination
+	u32 lo[T4P_TILE] ;         // per position of the tile: postings list offset >> 5 (lists are 32-byte aligned) ...
+	u32 cnt[T4P_TILE] ;        // ... its length (0: k-mer with an N, pass not probed, code absent) ...
+	u32 base[T4P_TILE] ;       // ... first hit slot of the read, T4P_NONE = lookup not taken
+	u32 sb[T4P_TILE] ;         // ... staging offset of the current TMA round
 	u64 fw[18], rc[18] ;       // packed words (+ zero padding for the two-word funnel shift)
 	u32 nm[20] ;
 	u64 bar ;                  // mbarrier
@@ -135,9 +139,8 @@ struct T4ProbeRead
 {
 	const T4Dir *dir ;
 	u32 dirMask ;
-	const T4Contig *seqs ;
 	u64 salt ;                 // barcode salt of the directory key (t4_index_key)
-	int k, len, m, strand, barcode ;
+	int k, len, m, strand, barcode, nPos ; // nPos = 2 m positions: forward pass [0, m), reverse-complement pass [m, 2 m)
 } ;
 
 // Serial rule state (SeqSet.hpp:1376-1392, 1441-1455), carried across tiles and from the forward into the reverse pass.
@@ -149,231 +152,239 @@ struct T4ProbeScan
 	int big ;
 } ;
 
-// Directory probes of one tile: position x = tile0 + c * 32 + lane -> cnt[c], lo[c] (0 postings when the k-mer holds an N,
-// the pass is not probed for this strand, or the code is absent).  Returns true iff some list has >= 100 postings.
-__device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, const T4ProbeWarp *sw, const char *A, int tile0, int lane,
-	u32 ( &cnt )[T4P_PMAX], u32 ( &lo )[T4P_PMAX] )
+__device__ __forceinline__ bool t4p_active( const T4ProbeRead &R, int x, int &pass, int &q )
+{
+	pass = x >= R.m ;
+	q = pass ? x - R.m : x ;
+	return x < R.nPos && !( ( pass == 0 && R.strand == -1 ) || ( pass == 1 && R.strand == 1 ) ) ;
+}
+
+// Directory probes of one tile: position x = tile0 + i -> sw->cnt[i], sw->lo[i].  Three positions per lane are in flight
+// together (one LDG.E.256 each = the 32-byte T4Dir sector).  Returns true iff some list has >= 100 postings.
+// The loops over the chunks of a tile are deliberately NOT unrolled: the kernel has to stay inside the instruction cache
+// (the first version, fully unrolled over register arrays, spent 8.7 of 16 stall cycles per issue on instruction fetch).
+__device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int nChunks, int lane )
 {
 	bool large = false ;
-	// groups of T4P_G positions: the first-slot loads of a group are in flight together
-#pragma unroll
-	for ( int h = 0 ; h < T4P_PMAX / T4P_G ; ++h )
+#pragma unroll 1
+	for ( int c0 = 0 ; c0 < nChunks ; c0 += T4P_G )
 	{
 		u64 key[T4P_G], v[T4P_G][4] ;
 		u32 slot[T4P_G] ;
 #pragma unroll
 		for ( int cc = 0 ; cc < T4P_G ; ++cc )
 		{
-			const int c = h * T4P_G + cc ;
-			const int x = tile0 + c * 32 + lane ;
-			cnt[c] = 0 ;
-			lo[c] = 0 ;
+			const int i = ( c0 + cc ) * 32 + lane ;
+			int pass, q ;
 			key[cc] = 0 ;
-			if ( x >= 2 * R.m )
-				continue ;
-			const int pass = x >= R.m ;
-			const int q = pass ? x - R.m : x ;
-			if ( ( pass == 0 && R.strand == -1 ) || ( pass == 1 && R.strand == 1 ) )
-				continue ;
-			// validity window: forward positions [q, q + k) or, for the reverse pass, [len - q - k, len - q)
-			if ( t4p_has_n( sw->nm, pass ? R.len - q - R.k : q, R.k ) )
-				continue ;
-			const u64 code = t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) ;
-			key[cc] = code + R.salt + 1 ;
-			slot[cc] = (u32)( ( key[cc] * 0x9E3779B97F4A7C15ull ) >> 32 ) & R.dirMask ;
-			t4p_ld256( R.dir + slot[cc], v[cc][0], v[cc][1], v[cc][2], v[cc][3] ) ;
+			slot[cc] = 0 ;
+			if ( c0 + cc < nChunks && t4p_active( R, tile0 + i, pass, q )
+				// validity window: forward positions [q, q + k) or, for the reverse pass, [len - q - k, len - q)
+				&& !t4p_has_n( sw->nm, pass ? R.len - q - R.k : q, R.k ) )
+			{
+				const u64 code = t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) ;
+				key[cc] = code + R.salt + 1 ;
+				slot[cc] = (u32)( ( key[cc] * 0x9E3779B97F4A7C15ull ) >> 32 ) & R.dirMask ;
+				t4p_ld256( R.dir + slot[cc], v[cc][0], v[cc][1], v[cc][2], v[cc][3] ) ;
+			}
 		}
 #pragma unroll
 		for ( int cc = 0 ; cc < T4P_G ; ++cc )
 		{
-			const int c = h * T4P_G + cc ;
-			if ( key[cc] == 0 )
-				continue ;
-			u64 kk = v[cc][0], lOff = v[cc][1], cw = v[cc][2], pad ;
-			u32 s = slot[cc] ;
-			while ( kk != key[cc] && kk != 0 ) // linear probing past a colliding slot (rare at load factor <= 1/2)
+			if ( c0 + cc >= nChunks )
+				break ;
+			const int i = ( c0 + cc ) * 32 + lane ;
+			u32 n = 0, l = 0 ;
+			if ( key[cc] != 0 )
 			{
-				s = ( s + 1 ) & R.dirMask ;
-				t4p_ld256( R.dir + s, kk, lOff, cw, pad ) ;
+				u64 kk = v[cc][0], lOff = v[cc][1], cw = v[cc][2], pad ;
+				u32 s = slot[cc] ;
+				while ( kk != key[cc] && kk != 0 ) // linear probing past a colliding slot (rare at load factor <= 1/2)
+				{
+					s = ( s + 1 ) & R.dirMask ;
+					t4p_ld256( R.dir + s, kk, lOff, cw, pad ) ;
+				}
+				if ( kk == key[cc] )
+				{
+					n = (u32)cw ;
+					l = (u32)( lOff >> 5 ) ;
+					if ( n >= 100 )
+						large = true ;
+				}
 			}
-			if ( kk == key[cc] )
-			{
-				cnt[c] = (u32)cw ;
-				lo[c] = (u32)( lOff >> 5 ) ; // lists are 32-byte aligned (T4_ALIGN)
-				if ( cnt[c] >= 100 )
-					large = true ;
-			}
+			sw->cnt[i] = n ;
+			sw->lo[i] = l ;
 		}
 	}
+	__syncwarp() ;
 	return __any_sync( 0xffffffffu, large ) ;
 }
 
 // No list reaches 100 postings: "taken" is a per-position predicate (first k-mer of the pass, or code differs from the
 // previous k-mer's -- N counted as A, KmerCode.hpp:94), hit slots are an exclusive prefix sum in position order.
-__device__ __forceinline__ void t4p_scan_fast( const T4ProbeRead &R, const T4ProbeWarp *sw, int tile0, int lane, const u32 ( &cnt )[T4P_PMAX],
-	u32 ( &base )[T4P_PMAX], T4ProbeScan &S )
+__device__ __forceinline__ void t4p_scan_fast( const T4ProbeRead &R, T4ProbeWarp *sw, int nChunks, int lane, T4ProbeScan &S )
 {
-#pragma unroll
-	for ( int c = 0 ; c < T4P_PMAX ; ++c )
+#pragma unroll 1
+	for ( int c = 0 ; c < nChunks ; ++c )
 	{
-		const int x = tile0 + c * 32 + lane ;
+		const int i = c * 32 + lane ;
+		int pass, q ;
 		bool taken = false ;
-		if ( x < 2 * R.m )
+		if ( t4p_active( R, i, pass, q ) )
 		{
-			const int pass = x >= R.m ;
-			const int q = pass ? x - R.m : x ;
-			if ( !( ( pass == 0 && R.strand == -1 ) || ( pass == 1 && R.strand == 1 ) ) )
-			{
-				const u64 *W = pass ? sw->rc : sw->fw ;
-				taken = ( q == 0 ) || ( t4p_extract( W, q, R.k ) != t4p_extract( W, q - 1, R.k ) ) ;
-			}
+			const u64 *W = pass ? sw->rc : sw->fw ;
+			taken = ( q == 0 ) || ( t4p_extract( W, q, R.k ) != t4p_extract( W, q - 1, R.k ) ) ;
 		}
-		const u32 v = taken ? cnt[c] : 0 ;
+		const u32 v = taken ? sw->cnt[i] : 0 ;
 		u32 tot ;
 		const u32 o = t4p_warp_excl_scan( v, tot, lane ) ;
-		base[c] = ( taken && v > 0 ) ? S.total + o : T4P_NONE ;
+		sw->base[i] = ( taken && v > 0 ) ? S.total + o : T4P_NONE ;
 		S.total += tot ;
 		S.lookups += __popc( __ballot_sync( 0xffffffffu, taken ) ) ;
 	}
+	__syncwarp() ;
 }
 
-// Some list has >= 100 postings: the reference's loop, position by position, warp-uniform over shuffled sizes.
-__device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, const T4ProbeWarp *sw, int tile0, int lane, int allowTotalSkip,
-	const u32 ( &cnt )[T4P_PMAX], u32 ( &base )[T4P_PMAX], T4ProbeScan &S )
+// Some list has >= 100 postings: the reference's loop, position by position; every lane runs the same scalar state machine
+// over the sizes in shared memory (broadcast reads), lane 0 records the slots.
+__device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int nChunks, int lane, int allowTotalSkip,
+	T4ProbeScan &S )
 {
 	const int skipLimit = R.k / 2 ;
-#pragma unroll
-	for ( int c = 0 ; c < T4P_PMAX ; ++c )
+	const int nTile = min( nChunks * 32, R.nPos - tile0 ) ;
+#pragma unroll 1
+	for ( int i = 0 ; i < nTile ; ++i )
 	{
-		base[c] = T4P_NONE ;
-		const int x0 = tile0 + c * 32 ;
-		if ( x0 >= 2 * R.m )
-			continue ;
-		for ( int src = 0 ; src < 32 ; ++src )
+		int pass, q ;
+		u32 b = T4P_NONE ;
+		if ( t4p_active( R, tile0 + i, pass, q ) )
 		{
-			const int x = x0 + src ;
-			const u32 size = __shfl_sync( 0xffffffffu, cnt[c], src ) ;
-			if ( x >= 2 * R.m )
-				break ;
-			const int pass = x >= R.m ;
-			const int q = pass ? x - R.m : x ;
-			if ( ( pass == 0 && R.strand == -1 ) || ( pass == 1 && R.strand == 1 ) )
-				continue ;
 			if ( pass != S.curPass )
 			{
 				S.curPass = pass ;
 				S.skipCnt = 0 ;
 			}
+			const u32 size = sw->cnt[i] ;
 			const u64 code = t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) ;
-			const int i = q + R.k - 1 ;
-			if ( i == R.k - 1 || code != S.prev )
+			const int e = q + R.k - 1 ;
+			bool setPrev = true ;
+			if ( q == 0 || code != S.prev )
 			{
 				++S.lookups ;
-				if ( size >= 100 && i != R.k - 1 && i != R.len - 1 && S.skipCnt < skipLimit )
+				if ( size >= 100 && q != 0 && e != R.len - 1 && S.skipCnt < skipLimit )
 				{
 					++S.skipCnt ;
-					continue ; // prevKmerCode keeps its stale value (SeqSet.hpp:1381-1388)
+					setPrev = false ; // prevKmerCode keeps its stale value (SeqSet.hpp:1381-1388)
 				}
-				if ( size >= 100 && allowTotalSkip )
-					continue ;
-				S.skipCnt = 0 ;
-				if ( size > 0 )
+				else if ( size >= 100 && allowTotalSkip )
+					setPrev = false ;
+				else
 				{
-					if ( lane == src )
-						base[c] = S.total ;
-					S.total += size ;
-					if ( R.barcode == -1 && size > T4_BIG_REPEAT )
-						S.big = 1 ;
+					S.skipCnt = 0 ;
+					if ( size > 0 )
+					{
+						b = S.total ;
+						S.total += size ;
+						if ( R.barcode == -1 && size > T4_BIG_REPEAT )
+							S.big = 1 ;
+					}
 				}
 			}
-			S.prev = code ;
+			if ( setPrev )
+				S.prev = code ;
 		}
+		if ( lane == 0 )
+			sw->base[i] = b ;
 	}
+	for ( int i = nTile + lane ; i < nChunks * 32 ; i += 32 )
+		sw->base[i] = T4P_NONE ;
+	__syncwarp() ;
 }
 
-__device__ __forceinline__ u64 t4p_key( const T4ProbeRead &R, int pass, int q, u64 posting, int big )
+__device__ __forceinline__ u64 t4p_key( int pass, int q, u64 posting, int big )
 {
-	const int idx = (int)( posting >> 32 ) ;
-	const int off = (int)(u32)posting ;
-	u64 key = t4_key_of( pass ? -1 : 1, idx, q, off, big ) ;
-	if ( R.barcode != -1 && __ldg( &R.seqs[idx].barcode ) != R.barcode ) // SeqSet.hpp:1418
-		key = T4_KEY_INVALID ;
-	return key ;
+	return t4_key_of( pass ? -1 : 1, (int)( posting >> 32 ), q, (int)(u32)posting, big ) ;
 }
 
 // Postings -> hit keys for one tile.  out: first key of this read.
-__device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp *sw, const char *A, int tile0, int lane, const u32 ( &cnt )[T4P_PMAX],
-	const u32 ( &lo )[T4P_PMAX], const u32 ( &base )[T4P_PMAX], u64 *out, u32 &barPhase )
+__device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp *sw, const char *A, int tile0, int nChunks, int lane, u64 *out,
+	u32 &barPhase )
 {
-	// ---- lists of <= 4 postings: one sector, fetched by the owner lane (the loads of a group are issued before the first use)
-#pragma unroll
-	for ( int h = 0 ; h < T4P_PMAX / T4P_G ; ++h )
+	// ---- lists of <= 4 postings: one sector, fetched by the owner lane; three lists per lane in flight
+#pragma unroll 1
+	for ( int c0 = 0 ; c0 < nChunks ; c0 += T4P_G )
 	{
 		u64 p[T4P_G][4] ;
+		u32 n[T4P_G], b[T4P_G] ;
 #pragma unroll
 		for ( int cc = 0 ; cc < T4P_G ; ++cc )
 		{
-			const int c = h * T4P_G + cc ;
-			if ( base[c] != T4P_NONE && cnt[c] <= T4P_SHORT )
-				t4p_ld256( A + ( (u64)lo[c] << 5 ), p[cc][0], p[cc][1], p[cc][2], p[cc][3] ) ;
-		}
-#pragma unroll
-		for ( int cc = 0 ; cc < T4P_G ; ++cc )
-		{
-			const int c = h * T4P_G + cc ;
-			if ( base[c] != T4P_NONE && cnt[c] <= T4P_SHORT )
+			const int i = ( c0 + cc ) * 32 + lane ;
+			n[cc] = 0 ;
+			if ( c0 + cc < nChunks )
 			{
-				const int x = tile0 + c * 32 + lane ;
-				const int pass = x >= R.m ;
-				const int q = pass ? x - R.m : x ;
-				u64 *o = out + base[c] ;
-#pragma unroll
-				for ( int j = 0 ; j < T4P_SHORT ; ++j )
-					if ( j < (int)cnt[c] )
-						o[j] = t4p_key( R, pass, q, p[cc][j], 0 ) ;
+				b[cc] = sw->base[i] ;
+				const u32 cn = sw->cnt[i] ;
+				if ( b[cc] != T4P_NONE && cn <= T4P_SHORT )
+				{
+					n[cc] = cn ;
+					t4p_ld256( A + ( (u64)sw->lo[i] << 5 ), p[cc][0], p[cc][1], p[cc][2], p[cc][3] ) ;
+				}
 			}
 		}
+#pragma unroll
+		for ( int cc = 0 ; cc < T4P_G ; ++cc )
+			if ( n[cc] )
+			{
+				const int x = tile0 + ( c0 + cc ) * 32 + lane ;
+				const int pass = x >= R.m ;
+				const int q = pass ? x - R.m : x ;
+				u64 *o = out + b[cc] ;
+#pragma unroll
+				for ( int j = 0 ; j < T4P_SHORT ; ++j )
+					if ( j < (int)n[cc] )
+						o[j] = t4p_key( pass, q, p[cc][j], 0 ) ;
+			}
 	}
 	// ---- lists of 5 .. T4P_TMA_MAX postings: TMA into the staging tile, rounds of at most T4P_STG postings
-	u32 pending = 0 ; // bit c: list of position c still to be staged
-#pragma unroll
-	for ( int c = 0 ; c < T4P_PMAX ; ++c )
-		if ( base[c] != T4P_NONE && cnt[c] > T4P_SHORT && cnt[c] <= T4P_TMA_MAX )
-			pending |= 1u << c ;
-	while ( __any_sync( 0xffffffffu, pending != 0 ) )
+	u32 pendingAny = 0 ;
+#pragma unroll 1
+	for ( int c = 0 ; c < nChunks ; ++c )
 	{
-		// staging offsets of this round: exclusive prefix (in position order) over the even-rounded counts of the pending lists;
-		// a list is taken iff it fits entirely, which selects a prefix of the pending lists
-		u32 sb[T4P_PMAX] ;
-		u32 run = 0 ;
-		bool full = false ;
-#pragma unroll
-		for ( int c = 0 ; c < T4P_PMAX ; ++c )
+		const int i = c * 32 + lane ;
+		const u32 cn = sw->cnt[i] ;
+		const bool pend = sw->base[i] != T4P_NONE && cn > T4P_SHORT && cn <= T4P_TMA_MAX ;
+		sw->sb[i] = pend ? T4P_NONE - 1 : T4P_NONE ; // NONE - 1: waiting for a round, NONE: nothing to stage
+		pendingAny |= pend ;
+	}
+	pendingAny = __any_sync( 0xffffffffu, pendingAny != 0 ) ;
+	while ( pendingAny )
+	{
+		// staging offsets of this round: exclusive prefix (in position order) over the even-rounded counts of the waiting
+		// lists; a list is taken iff it still fits, and since the offsets include the lists that do not fit, the taken
+		// ones are a prefix of the waiting ones
+		u32 run = 0, roundBytes = 0 ;
+		bool more = false ;
+#pragma unroll 1
+		for ( int c = 0 ; c < nChunks ; ++c )
 		{
-			const bool pend = ( pending >> c ) & 1u ;
-			const u32 v = pend ? ( ( cnt[c] + 1 ) & ~1u ) : 0 ;
+			const int i = c * 32 + lane ;
+			const bool wait = sw->sb[i] == T4P_NONE - 1 ;
+			const u32 v = wait ? ( ( sw->cnt[i] + 1 ) & ~1u ) : 0 ;
 			u32 tot ;
 			const u32 o = t4p_warp_excl_scan( v, tot, lane ) ;
-			sb[c] = T4P_NONE ;
-			if ( pend && !full && run + o + v <= T4P_STG )
-				sb[c] = run + o ;
-			// once one pending list does not fit, no later list may be taken (keeps the selection a prefix)
-			const u32 miss = __ballot_sync( 0xffffffffu, pend && sb[c] == T4P_NONE ) ;
-			if ( miss )
+			if ( wait )
 			{
-				const int first = __ffs( miss ) - 1 ;
-				if ( lane > first && sb[c] != T4P_NONE )
-					sb[c] = T4P_NONE ;
-				full = true ;
+				if ( run + o + v <= T4P_STG )
+				{
+					sw->sb[i] = run + o ;
+					roundBytes += v * 8 ;
+				}
+				else
+					more = true ;
 			}
 			run += tot ;
 		}
-		u32 myBytes = 0 ;
-#pragma unroll
-		for ( int c = 0 ; c < T4P_PMAX ; ++c )
-			if ( sb[c] != T4P_NONE )
-				myBytes += ( ( cnt[c] + 1 ) & ~1u ) * 8 ;
-		u32 roundBytes = myBytes ;
 #pragma unroll
 		for ( int d = 16 ; d > 0 ; d >>= 1 )
 			roundBytes += __shfl_xor_sync( 0xffffffffu, roundBytes, d ) ;
@@ -383,75 +394,80 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 		if ( lane == 0 )
 			t4p_bar_expect( &sw->bar, roundBytes ) ;
 		__syncwarp() ;
-#pragma unroll
-		for ( int c = 0 ; c < T4P_PMAX ; ++c )
-			if ( sb[c] != T4P_NONE )
-				t4p_bulk_g2s( sw->stg + sb[c], A + ( (u64)lo[c] << 5 ), ( ( cnt[c] + 1 ) & ~1u ) * 8, &sw->bar ) ;
+#pragma unroll 1
+		for ( int c = 0 ; c < nChunks ; ++c )
+		{
+			const int i = c * 32 + lane ;
+			const u32 so = sw->sb[i] ;
+			if ( so < T4P_NONE - 1 )
+				t4p_bulk_g2s( sw->stg + so, A + ( (u64)sw->lo[i] << 5 ), ( ( sw->cnt[i] + 1 ) & ~1u ) * 8, &sw->bar ) ;
+		}
 		t4p_bar_wait( &sw->bar, barPhase ) ;
 		barPhase ^= 1 ;
-		// convert: one staged list at a time, the whole warp on it
-#pragma unroll
-		for ( int c = 0 ; c < T4P_PMAX ; ++c )
+		// convert: one staged list at a time, the whole warp on it (coalesced 8-byte stores)
+#pragma unroll 1
+		for ( int c = 0 ; c < nChunks ; ++c )
 		{
-			u32 mask = __ballot_sync( 0xffffffffu, sb[c] != T4P_NONE ) ;
+			const int i = c * 32 + lane ;
+			const u32 mySo = sw->sb[i] ;
+			u32 mask = __ballot_sync( 0xffffffffu, mySo < T4P_NONE - 1 ) ;
 			while ( mask )
 			{
 				const int src = __ffs( mask ) - 1 ;
 				mask &= mask - 1 ;
-				const u32 n = __shfl_sync( 0xffffffffu, cnt[c], src ) ;
-				const u32 so = __shfl_sync( 0xffffffffu, sb[c], src ) ;
-				const u32 bo = __shfl_sync( 0xffffffffu, base[c], src ) ;
-				const int x = tile0 + c * 32 + src ;
+				const int is = c * 32 + src ;
+				const u32 n = sw->cnt[is], so = sw->sb[is], bo = sw->base[is] ;
+				const int x = tile0 + is ;
 				const int pass = x >= R.m ;
 				const int q = pass ? x - R.m : x ;
 				for ( u32 j = lane ; j < n ; j += 32 )
-					out[bo + j] = t4p_key( R, pass, q, sw->stg[so + j], 0 ) ;
+					out[bo + j] = t4p_key( pass, q, sw->stg[so + j], 0 ) ;
 			}
-			if ( sb[c] != T4P_NONE )
-				pending &= ~( 1u << c ) ;
+			__syncwarp() ;
+			if ( mySo < T4P_NONE - 1 )
+				sw->sb[i] = T4P_NONE ;
 		}
+		pendingAny = __any_sync( 0xffffffffu, more ) ;
 		__syncwarp() ;
 	}
 	// ---- longer lists: streamed by the whole warp, two postings (128 bits) per lane and load
-#pragma unroll
-	for ( int c = 0 ; c < T4P_PMAX ; ++c )
+#pragma unroll 1
+	for ( int c = 0 ; c < nChunks ; ++c )
 	{
-		u32 mask = __ballot_sync( 0xffffffffu, base[c] != T4P_NONE && cnt[c] > T4P_TMA_MAX ) ;
+		const int i = c * 32 + lane ;
+		u32 mask = __ballot_sync( 0xffffffffu, sw->base[i] != T4P_NONE && sw->cnt[i] > T4P_TMA_MAX ) ;
 		while ( mask )
 		{
 			const int src = __ffs( mask ) - 1 ;
 			mask &= mask - 1 ;
-			const u32 n = __shfl_sync( 0xffffffffu, cnt[c], src ) ;
-			const u64 l = (u64)__shfl_sync( 0xffffffffu, lo[c], src ) << 5 ;
-			const u32 bo = __shfl_sync( 0xffffffffu, base[c], src ) ;
-			const int x = tile0 + c * 32 + src ;
+			const int is = c * 32 + src ;
+			const u32 n = sw->cnt[is], bo = sw->base[is] ;
+			const char *l = A + ( (u64)sw->lo[is] << 5 ) ;
+			const int x = tile0 + is ;
 			const int pass = x >= R.m ;
 			const int q = pass ? x - R.m : x ;
 			const int big = ( R.barcode == -1 && n > T4_BIG_REPEAT ) ? 1 : 0 ;
 			for ( u32 j = 2 * lane ; j < n ; j += 64 )
 			{
-				u64 a, b ;
-				t4p_ld128( A + l + 8ull * j, a, b ) ;
-				out[bo + j] = t4p_key( R, pass, q, a, big ) ;
+				u64 a, b2 ;
+				t4p_ld128( l + 8ull * j, a, b2 ) ;
+				out[bo + j] = t4p_key( pass, q, a, big ) ;
 				if ( j + 1 < n )
-					out[bo + j + 1] = t4p_key( R, pass, q, b, big ) ;
+					out[bo + j + 1] = t4p_key( pass, q, b2, big ) ;
 			}
 		}
 	}
 }
 
-__global__ void __launch_bounds__( 32 * T4P_WARPS, 2 ) t4_probe_kernel( T4ProbeParams P )
+// MINB: resident CTAs per SM the register allocation is bounded for (3: 80 registers, 24 warps per SM; 2: 128 registers)
+template <int MINB>
+__global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4ProbeParams P )
 {
-	__shared__ __align__( 16 ) T4ProbeWarp smem[T4P_WARPS] ;
+	extern __shared__ __align__( 16 ) unsigned char t4p_dyn[] ; // T4P_WARPS x T4ProbeWarp (> 48 KB: dynamic, opted in by the host)
 	const int lane = threadIdx.x & 31 ;
-	T4ProbeWarp *sw = &smem[threadIdx.x >> 5] ;
+	T4ProbeWarp *sw = (T4ProbeWarp *)t4p_dyn + ( threadIdx.x >> 5 ) ;
 	if ( lane == 0 )
 		t4p_bar_init( &sw->bar ) ;
-	if ( lane < 2 )
-	{
-		sw->fw[16 + lane] = 0 ;
-		sw->rc[16 + lane] = 0 ;
-	}
 	__syncwarp() ;
 	u32 barPhase = 0 ;
 	u64 accLook = 0, accPost = 0, accBytes = 0, accUnsup = 0 ;
@@ -473,9 +489,9 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, 2 ) t4_probe_kernel( T4ProbeP
 		R.strand = d->strand_in ;
 		R.k = st->kmerLength ;
 		R.m = R.len - R.k + 1 ;
+		R.nPos = 2 * R.m ;
 		R.dir = (const T4Dir *)( P.A + st->dirOff ) ;
 		R.dirMask = st->dirCap - 1 ;
-		R.seqs = (const T4Contig *)( P.A + st->seqsOff ) ;
 		R.salt = st->considerBarcode ? ( (u64)(u32)( R.barcode + 1 ) << ( 2 * R.k ) ) : 0ull ;
 		if ( R.len > T4_DEV_MAX_READ || R.len < R.k )
 		{
@@ -489,61 +505,58 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, 2 ) t4_probe_kernel( T4ProbeP
 			}
 			continue ;
 		}
-		// packed read -> shared memory (<= 16 + 16 words + 16 mask words)
+		// packed read -> shared memory (<= 16 + 16 words + 16 mask words, zero padded)
 		{
 			const int W = (int)t4_pack_w( R.len ) ;
 			const u64 *pk = P.packed + (u64)ri * P.packStride ;
 			__syncwarp() ;
-			if ( lane < W )
+			if ( lane < 18 )
 			{
-				sw->fw[lane] = __ldg( pk + lane ) ;
-				sw->rc[lane] = __ldg( pk + W + lane ) ;
-				sw->nm[lane] = __ldg( (const u32 *)( pk + 2 * W ) + lane ) ;
+				sw->fw[lane] = lane < W ? __ldg( pk + lane ) : 0 ;
+				sw->rc[lane] = lane < W ? __ldg( pk + W + lane ) : 0 ;
 			}
-			else if ( lane < 18 )
-			{
-				sw->fw[lane] = 0 ;
-				sw->rc[lane] = 0 ;
-				sw->nm[lane] = 0 ;
-			}
-			if ( lane >= 18 && lane < 20 )
-				sw->nm[lane] = 0 ;
+			if ( lane < 20 )
+				sw->nm[lane] = lane < W ? __ldg( (const u32 *)( pk + 2 * W ) + lane ) : 0 ;
 			__syncwarp() ;
 		}
 		T4ProbeScan S ;
-		u32 cnt[T4P_PMAX], base[T4P_PMAX], lo[T4P_PMAX] ;
-		const int nTiles = ( 2 * R.m + T4P_TILE - 1 ) / T4P_TILE ;
+		const int nTiles = ( R.nPos + T4P_TILE - 1 ) / T4P_TILE ;
 		u32 flags = 0 ;
 		u64 *out = 0 ;
+		u32 T = 0 ;
 		// sweep 0 counts (directory probes + slot assignment), then the output range is reserved, sweep 1 emits.  A read
-		// that fits one tile (<= 288 positions: 150 bp at k >= 7) keeps its probe results in registers between the two;
-		// a longer one probes its tiles again (L1/L2 hits) and always uses the serial rules, which reduce to the plain
-		// predicate when no list is large.
+		// that fits one tile (<= 288 positions: 150 bp at k >= 7) keeps its probe results in shared memory between the
+		// two; a longer one probes its tiles again (L1/L2 hits) and always uses the serial rules, which reduce to the
+		// plain predicate when no list is large.
+#pragma unroll 1
 		for ( int sweep = 0 ; sweep < 2 ; ++sweep )
 		{
 			if ( sweep == 0 || nTiles > 1 )
 			{
 				S.prev = 0 ; S.skipCnt = 0 ; S.curPass = -1 ; S.total = 0 ; S.lookups = 0 ; S.big = 0 ;
 			}
+#pragma unroll 1
 			for ( int t = 0 ; t < nTiles ; ++t )
 			{
+				const int tile0 = t * T4P_TILE ;
+				const int nChunks = ( min( T4P_TILE, R.nPos - tile0 ) + 31 ) >> 5 ;
 				if ( sweep == 0 || nTiles > 1 )
 				{
-					const bool large = t4p_probe_tile( R, sw, P.A, t * T4P_TILE, lane, cnt, lo ) ;
+					const bool large = t4p_probe_tile( R, sw, tile0, nChunks, lane ) ;
 					if ( nTiles == 1 && !large )
-						t4p_scan_fast( R, sw, 0, lane, cnt, base, S ) ;
+						t4p_scan_fast( R, sw, nChunks, lane, S ) ;
 					else
 					{
-						t4p_scan_serial( R, sw, t * T4P_TILE, lane, P.allowTotalSkip, cnt, base, S ) ;
+						t4p_scan_serial( R, sw, tile0, nChunks, lane, P.allowTotalSkip, S ) ;
 						flags |= 2 ;
 					}
 				}
 				if ( sweep == 1 )
-					t4p_emit_tile( R, sw, P.A, t * T4P_TILE, lane, cnt, lo, base, out, barPhase ) ;
+					t4p_emit_tile( R, sw, P.A, tile0, nChunks, lane, out, barPhase ) ;
 			}
 			if ( sweep == 0 )
 			{
-				const u32 T = S.total ;
+				T = S.total ;
 				unsigned long long o0 = 0 ;
 				if ( lane == 0 )
 					o0 = atomicAdd( (unsigned long long *)&P.ctrl[1], (unsigned long long)T ) ;
@@ -563,6 +576,19 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, 2 ) t4_probe_kernel( T4ProbeP
 				if ( !fits || T == 0 )
 					break ;
 				out = P.keys + o0 ;
+			}
+		}
+		// barcode filter (SeqSet.hpp:1418): hits on contigs of another barcode become invalid keys.  Off the hot path: only
+		// reads that carry a barcode pay for it, in one pass over their own keys.
+		if ( R.barcode != -1 && out != 0 )
+		{
+			const T4Contig *seqs = (const T4Contig *)( P.A + st->seqsOff ) ;
+			__syncwarp() ;
+			for ( u32 t = lane ; t < T ; t += 32 )
+			{
+				const u64 key = __ldcg( out + t ) ;
+				if ( __ldg( &seqs[t4_key_idx( key )].barcode ) != R.barcode )
+					out[t] = T4_KEY_INVALID ;
 			}
 		}
 	}

@@ -507,20 +507,27 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
     return Workload(descs, pool, names, L, order, med.astype(np.int32))
 
 
-# Cost model of one record in the stream kernel, used to size contiguous shards (relative units).  A duplicate is a
-# RepeatAddRead (posWeight increments only); a distinct read runs the whole AddRead path, and the rarer its k-mers
-# (minCnt of the 21-mer statistics, known before the launch) the less it assembles: singletons become contigs of their
-# own, which every later read of the shard then has to be scored against.  Constants fitted to per-stream cycle counts
-# of the default bench workload (bench.py --dump-streams, bench/fit_cost_model.py).
-COST_DUP = 1.0
-COST_BY_MINCNT = ((1, 60.0), (2, 40.0), (4, 25.0), (8, 15.0), (16, 10.0), (1 << 30, 6.0))
+# Cost model of one record in the stream kernel, used to size contiguous shards (microseconds at 1965 MHz, only the
+# ratios matter).  A duplicate is a RepeatAddRead (posWeight increments only); a distinct read runs the whole AddRead
+# path, and what it costs depends on where it sits in the abundance spectrum, which the 21-mer statistics give before
+# the launch: minCnt (the rarest k-mer) says whether the read is error free, medianCnt how abundant its clonotype is.
+# An erroneous copy of an abundant clonotype (minCnt 1, medianCnt > 65536) is the most expensive kind: it overlaps
+# many contigs of its shard and most of its overhangs need the banded DP.  Table fitted by non-negative least squares
+# to the per-stream cycle counts of the default bench workload (bench.py --dump-streams, bench/fit_cost_model.py;
+# correlation 0.93 with the measured stream times), smoothed where a cell has too few reads.
+COST_DUP = 3.0
+COST_MIN_EDGES = (1, 2, 4, 8, 16, 64, 256, 1 << 40)
+COST_MED_EDGES = (4, 16, 64, 256, 1024, 4096, 16384, 65536, 1 << 40)
+COST_TABLE = np.array([[348, 225, 374, 322, 207, 298, 538, 575, 918], [330, 330, 198, 356, 161, 214, 351, 330, 651],
+                       [324, 324, 324, 465, 190, 208, 284, 363, 635], [298, 298, 298, 115, 296, 241, 300, 447, 687],
+                       [369, 369, 369, 387, 278, 313, 352, 429, 952], [242, 242, 242, 242, 125, 235, 366, 242, 347],
+                       [173, 173, 173, 60, 60, 162, 289, 185, 281], [125, 125, 125, 125, 152, 124, 125, 120, 137]], dtype=np.float64)
 
 
-def read_cost(descs) -> np.ndarray:
+def read_cost(descs, med_cnt=None) -> np.ndarray:
     mc = descs["min_cnt"].astype(np.int64)
-    c = np.full(len(descs), COST_BY_MINCNT[-1][1], dtype=np.float64)
-    for hi, v in reversed(COST_BY_MINCNT):
-        c[mc <= hi] = v
+    med = np.asarray(med_cnt, dtype=np.int64) if med_cnt is not None else mc
+    c = COST_TABLE[np.searchsorted(np.array(COST_MIN_EDGES), mc, side="left"), np.searchsorted(np.array(COST_MED_EDGES), med, side="left")].copy()
     c[(descs["flags"] & RD_DUP) != 0] = COST_DUP
     return c
 
@@ -570,7 +577,7 @@ def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str 
         # balance="cost": the same contiguous blocks of the sorted list, cut where the cumulative predicted cost crosses
         # s / n_shards of the total instead of where the read count does (a stream is a serial chain: the launch lasts as
         # long as its most expensive shard)
-        cum = np.cumsum(read_cost(w.descs))
+        cum = np.cumsum(read_cost(w.descs, w.med_cnt))
         cuts = np.searchsorted(cum, cum[-1] * np.arange(1, n_shards) / n_shards, side="left")
     else:
         cuts = (n * np.arange(1, n_shards)) // n_shards
