@@ -57,6 +57,7 @@ def parse(argv=None):
     ap.add_argument("--barcodes", type=int, default=int(os.environ.get("T4_BENCH_BARCODES", 1000)), help="config 3: cells per GPU (configs[3] full size: 6250)")
     ap.add_argument("--reads-per-barcode", type=int, default=2000)
     ap.add_argument("--reads", type=int, default=int(os.environ.get("T4_BENCH_READS", 2000000)), help="config 4: reads per GPU (configs[4] full size: 6250000)")
+    ap.add_argument("--no-quality", action="store_true", help="skip the assembly-quality figure (clonotypes spanned by one contig)")
     return ap.parse_args(argv)
 
 
@@ -100,6 +101,7 @@ def make_workload(args, rank, device):
     rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
     w = synth.build_workload(cl, rd, device=device)
     off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance)
+    make_workload.truth = (cl, rd)          # kept for the assembly-quality figure (bench/quality.py)
     return w, off, descs
 
 
@@ -510,6 +512,20 @@ def main():
 
     value = world * n_reads * args.steps / (ms * 1e-3)
     e2e = world * n_reads * args.steps / (ms_e2e * 1e-3)
+    quality_fig = None
+    if rank == 0 and not args.no_quality and args.config == 1 and getattr(make_workload, "truth", None) is not None:
+        # what the sharding costs in contiguity: clonotypes whose V(D)J core lies inside ONE contig of this rank's output
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "bench"))
+            import quality
+            torch.cuda.synchronize()
+            tq = time.perf_counter()
+            codes, coff, ncont = quality.contigs_from_packed(pack["host"][: merged["pack_bytes"]].numpy())
+            cl_, rd_ = make_workload.truth
+            quality_fig = quality.spanning_fraction(cl_, rd_, codes, coff)
+            quality_fig.update(contigs=ncont, contig_bases=int(len(codes)), streams=S, seconds=time.perf_counter() - tq)
+        except Exception as ex:
+            quality_fig = {"error": str(ex)[:200]}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -540,6 +556,7 @@ def main():
             # init + stream kernel + pack-size + pack per step
             4 * args.steps, roofline, roofline_probe, cpu,
             {"assembled_reads": assembled, "reads_per_gpu": n_reads, "contigs_per_gpu": merged["contigs"], "parity_spot_check": parity,
+             "assembly_quality": quality_fig,
              "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
              "threads_per_stream": int(os.environ.get("T4_NT", 128))}, metric=su["metric"])
         print(json.dumps(line))
