@@ -22,11 +22,11 @@
 
 #if T4_CUDA
 
-#define T4P_WARPS 8                 // warps per CTA
+#define T4P_WARPS 1                 // warps per CTA: one, so that the warp's shared-memory tile sits at a constant address
+                                    // (with 8 warps per CTA 18 % of all issued instructions recomputed `smem + warp * sizeof`)
 #define T4P_PMAX 9                  // positions per lane and tile
-#define T4P_G 3                     // positions whose loads are issued together (groups of the unrolled loops)
 #define T4P_TILE ( 32 * T4P_PMAX )  // positions (both strand passes) per tile: a 150 bp read at k = 9 has 284
-#define T4P_STG 512                 // TMA staging tile per warp, postings (4 KB)
+#define T4P_STG 384                 // TMA staging tile per warp, postings (3 KB; 24 one-warp CTAs x (8 KB + 1 KB reserved) fit an SM)
 #define T4P_SHORT 4                 // a list of <= 4 postings is one 32-byte sector
 #define T4P_TMA_MAX 256             // longer lists stream through 128-bit loads instead of the staging tile
 #define T4P_NONE 0xffffffffu
@@ -140,7 +140,9 @@ struct T4ProbeRead
 	const T4Dir *dir ;
 	u32 dirMask ;
 	u64 salt ;                 // barcode salt of the directory key (t4_index_key)
+	u64 mask ;                 // 2k low bits
 	int k, len, m, strand, barcode, nPos ; // nPos = 2 m positions: forward pass [0, m), reverse-complement pass [m, 2 m)
+	bool anyN ;                // the read holds an 'N' (otherwise every k-mer is valid and the mask test is skipped)
 } ;
 
 // Serial rule state (SeqSet.hpp:1376-1392, 1441-1455), carried across tiles and from the forward into the reverse pass.
@@ -159,47 +161,77 @@ __device__ __forceinline__ bool t4p_active( const T4ProbeRead &R, int x, int &pa
 	return x < R.nPos && !( ( pass == 0 && R.strand == -1 ) || ( pass == 1 && R.strand == 1 ) ) ;
 }
 
-// Directory probes of one tile: position x = tile0 + i -> sw->cnt[i], sw->lo[i].  Three positions per lane are in flight
-// together (one LDG.E.256 each = the 32-byte T4Dir sector).  Returns true iff some list has >= 100 postings.
-// The loops over the chunks of a tile are deliberately NOT unrolled: the kernel has to stay inside the instruction cache
-// (the first version, fully unrolled over register arrays, spent 8.7 of 16 stall cycles per issue on instruction fetch).
-__device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int nChunks, int lane )
+__device__ __forceinline__ u64 t4p_base_at( const u64 *W, int p ) { return ( W[p >> 5] >> ( 62 - 2 * ( p & 31 ) ) ) & 3ull ; }
+
+// Directory probes of one tile.  Lane l owns the CONTIGUOUS positions [l * ppl, (l + 1) * ppl) of the tile, so its k-mer
+// codes roll (KmerCode::Append, KmerCode.hpp:94: one 2-bit base per step) and "equal to the previous k-mer"
+// (SeqSet.hpp:1376) is a register compare; G positions per lane are in flight together, one LDG.E.256 each = the
+// 32-byte T4Dir sector.  Results: sw->cnt[i], sw->lo[i] per position i of the tile; takenBits (bit c: the lane's c-th
+// position passes the plain "taken" predicate) and localSum (its postings) feed the fast slot assignment.
+// Returns true iff some list has >= 100 postings.  Loops over a lane's positions are deliberately not fully unrolled:
+// the kernel has to stay inside the instruction cache (a first, fully unrolled version over register arrays spent 8.7
+// of 16 stall cycles per issue on instruction fetch).
+template <int G>
+__device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int tileLen, int ppl, int lane,
+	u32 &takenBits, u32 &localSum )
 {
 	bool large = false ;
+	takenBits = 0 ;
+	localSum = 0 ;
+	u64 code = 0 ;
+	int lastX = -2 ;
 #pragma unroll 1
-	for ( int c0 = 0 ; c0 < nChunks ; c0 += T4P_G )
+	for ( int c0 = 0 ; c0 < ppl ; c0 += G )
 	{
-		u64 key[T4P_G], v[T4P_G][4] ;
-		u32 slot[T4P_G] ;
+		u64 key[G], v[G][4] ;
+		u32 slot[G] ;
 #pragma unroll
-		for ( int cc = 0 ; cc < T4P_G ; ++cc )
+		for ( int cc = 0 ; cc < G ; ++cc )
 		{
-			const int i = ( c0 + cc ) * 32 + lane ;
+			const int c = c0 + cc ;
+			const int i = lane * ppl + c ;
 			int pass, q ;
 			key[cc] = 0 ;
 			slot[cc] = 0 ;
-			if ( c0 + cc < nChunks && t4p_active( R, tile0 + i, pass, q )
-				// validity window: forward positions [q, q + k) or, for the reverse pass, [len - q - k, len - q)
-				&& !t4p_has_n( sw->nm, pass ? R.len - q - R.k : q, R.k ) )
+			if ( c < ppl && i < tileLen && t4p_active( R, tile0 + i, pass, q ) )
 			{
-				const u64 code = t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) ;
-				key[cc] = code + R.salt + 1 ;
-				slot[cc] = (u32)( ( key[cc] * 0x9E3779B97F4A7C15ull ) >> 32 ) & R.dirMask ;
-				t4p_ld256( R.dir + slot[cc], v[cc][0], v[cc][1], v[cc][2], v[cc][3] ) ;
+				const u64 *W = pass ? sw->rc : sw->fw ;
+				u64 prev ;
+				if ( q == 0 || lastX != tile0 + i - 1 )
+				{
+					code = t4p_extract( W, q, R.k ) ;
+					prev = q > 0 ? t4p_extract( W, q - 1, R.k ) : 0 ;
+				}
+				else
+				{
+					prev = code ;
+					code = ( ( code << 2 ) & R.mask ) | t4p_base_at( W, q + R.k - 1 ) ;
+				}
+				lastX = tile0 + i ;
+				if ( q == 0 || code != prev )
+					takenBits |= 1u << c ;
+				// validity window: forward positions [q, q + k) or, for the reverse pass, [len - q - k, len - q)
+				if ( !R.anyN || !t4p_has_n( sw->nm, pass ? R.len - q - R.k : q, R.k ) )
+				{
+					key[cc] = code + R.salt + 1 ;
+					slot[cc] = (u32)( ( key[cc] * 0x9E3779B97F4A7C15ull ) >> 32 ) & R.dirMask ;
+					t4p_ld256( R.dir + slot[cc], v[cc][0], v[cc][1], v[cc][2], v[cc][3] ) ;
+				}
 			}
 		}
 #pragma unroll
-		for ( int cc = 0 ; cc < T4P_G ; ++cc )
+		for ( int cc = 0 ; cc < G ; ++cc )
 		{
-			if ( c0 + cc >= nChunks )
+			const int c = c0 + cc ;
+			const int i = lane * ppl + c ;
+			if ( c >= ppl || i >= tileLen )
 				break ;
-			const int i = ( c0 + cc ) * 32 + lane ;
 			u32 n = 0, l = 0 ;
 			if ( key[cc] != 0 )
 			{
 				u64 kk = v[cc][0], lOff = v[cc][1], cw = v[cc][2], pad ;
 				u32 s = slot[cc] ;
-				while ( kk != key[cc] && kk != 0 ) // linear probing past a colliding slot (rare at load factor <= 1/2)
+				while ( kk != key[cc] && kk != 0 ) // linear probing past a colliding slot
 				{
 					s = ( s + 1 ) & R.dirMask ;
 					t4p_ld256( R.dir + s, kk, lOff, cw, pad ) ;
@@ -210,6 +242,8 @@ __device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWar
 					l = (u32)( lOff >> 5 ) ;
 					if ( n >= 100 )
 						large = true ;
+					if ( ( takenBits >> c ) & 1u )
+						localSum += n ;
 				}
 			}
 			sw->cnt[i] = n ;
@@ -220,40 +254,44 @@ __device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWar
 	return __any_sync( 0xffffffffu, large ) ;
 }
 
-// No list reaches 100 postings: "taken" is a per-position predicate (first k-mer of the pass, or code differs from the
-// previous k-mer's -- N counted as A, KmerCode.hpp:94), hit slots are an exclusive prefix sum in position order.
-__device__ __forceinline__ void t4p_scan_fast( const T4ProbeRead &R, T4ProbeWarp *sw, int nChunks, int lane, T4ProbeScan &S )
+// No list reaches 100 postings: "taken" is the per-position predicate computed above (first k-mer of the pass, or code
+// differs from the previous k-mer's -- N counted as A), and the hit slots are an exclusive prefix sum in position order:
+// one warp scan over the lanes' sums, then every lane walks its own contiguous positions.
+__device__ __forceinline__ void t4p_scan_fast( T4ProbeWarp *sw, int tileLen, int ppl, int lane, u32 takenBits, u32 localSum, T4ProbeScan &S )
 {
+	u32 tot ;
+	u32 o = S.total + t4p_warp_excl_scan( localSum, tot, lane ) ;
 #pragma unroll 1
-	for ( int c = 0 ; c < nChunks ; ++c )
+	for ( int c = 0 ; c < ppl ; ++c )
 	{
-		const int i = c * 32 + lane ;
-		int pass, q ;
-		bool taken = false ;
-		if ( t4p_active( R, i, pass, q ) )
-		{
-			const u64 *W = pass ? sw->rc : sw->fw ;
-			taken = ( q == 0 ) || ( t4p_extract( W, q, R.k ) != t4p_extract( W, q - 1, R.k ) ) ;
-		}
-		const u32 v = taken ? sw->cnt[i] : 0 ;
-		u32 tot ;
-		const u32 o = t4p_warp_excl_scan( v, tot, lane ) ;
-		sw->base[i] = ( taken && v > 0 ) ? S.total + o : T4P_NONE ;
-		S.total += tot ;
-		S.lookups += __popc( __ballot_sync( 0xffffffffu, taken ) ) ;
+		const int i = lane * ppl + c ;
+		if ( i >= tileLen )
+			break ;
+		const u32 n = sw->cnt[i] ;
+		const bool emit = ( ( takenBits >> c ) & 1u ) && n > 0 ;
+		sw->base[i] = emit ? o : T4P_NONE ;
+		if ( emit )
+			o += n ;
 	}
+	S.total += tot ;
+	u32 looks = __popc( takenBits ) ;
+#pragma unroll
+	for ( int d = 16 ; d > 0 ; d >>= 1 )
+		looks += __shfl_xor_sync( 0xffffffffu, looks, d ) ;
+	S.lookups += looks ;
 	__syncwarp() ;
 }
 
 // Some list has >= 100 postings: the reference's loop, position by position; every lane runs the same scalar state machine
 // over the sizes in shared memory (broadcast reads), lane 0 records the slots.
-__device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int nChunks, int lane, int allowTotalSkip,
+__device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int tileLen, int lane, int allowTotalSkip,
 	T4ProbeScan &S )
 {
 	const int skipLimit = R.k / 2 ;
-	const int nTile = min( nChunks * 32, R.nPos - tile0 ) ;
+	u64 code = 0 ;
+	int lastX = -2 ;
 #pragma unroll 1
-	for ( int i = 0 ; i < nTile ; ++i )
+	for ( int i = 0 ; i < tileLen ; ++i )
 	{
 		int pass, q ;
 		u32 b = T4P_NONE ;
@@ -264,8 +302,13 @@ __device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, T4ProbeWa
 				S.curPass = pass ;
 				S.skipCnt = 0 ;
 			}
+			const u64 *W = pass ? sw->rc : sw->fw ;
+			if ( q == 0 || lastX != tile0 + i - 1 )
+				code = t4p_extract( W, q, R.k ) ;
+			else
+				code = ( ( code << 2 ) & R.mask ) | t4p_base_at( W, q + R.k - 1 ) ;
+			lastX = tile0 + i ;
 			const u32 size = sw->cnt[i] ;
-			const u64 code = t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) ;
 			const int e = q + R.k - 1 ;
 			bool setPrev = true ;
 			if ( q == 0 || code != S.prev )
@@ -296,8 +339,6 @@ __device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, T4ProbeWa
 		if ( lane == 0 )
 			sw->base[i] = b ;
 	}
-	for ( int i = nTile + lane ; i < nChunks * 32 ; i += 32 )
-		sw->base[i] = T4P_NONE ;
 	__syncwarp() ;
 }
 
@@ -307,21 +348,23 @@ __device__ __forceinline__ u64 t4p_key( int pass, int q, u64 posting, int big )
 }
 
 // Postings -> hit keys for one tile.  out: first key of this read.
-__device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp *sw, const char *A, int tile0, int nChunks, int lane, u64 *out,
-	u32 &barPhase )
+template <int G>
+__device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp *sw, const char *A, int tile0, int tileLen, int ppl, int lane,
+	u64 *out, u32 &barPhase )
 {
-	// ---- lists of <= 4 postings: one sector, fetched by the owner lane; three lists per lane in flight
+	const int nChunks = ( tileLen + 31 ) >> 5 ;
+	// ---- lists of <= 4 postings: one sector, fetched by the owner lane (its contiguous positions); G lists in flight
 #pragma unroll 1
-	for ( int c0 = 0 ; c0 < nChunks ; c0 += T4P_G )
+	for ( int c0 = 0 ; c0 < ppl ; c0 += G )
 	{
-		u64 p[T4P_G][4] ;
-		u32 n[T4P_G], b[T4P_G] ;
+		u64 p[G][4] ;
+		u32 n[G], b[G] ;
 #pragma unroll
-		for ( int cc = 0 ; cc < T4P_G ; ++cc )
+		for ( int cc = 0 ; cc < G ; ++cc )
 		{
-			const int i = ( c0 + cc ) * 32 + lane ;
+			const int i = lane * ppl + c0 + cc ;
 			n[cc] = 0 ;
-			if ( c0 + cc < nChunks )
+			if ( c0 + cc < ppl && i < tileLen )
 			{
 				b[cc] = sw->base[i] ;
 				const u32 cn = sw->cnt[i] ;
@@ -333,10 +376,10 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 			}
 		}
 #pragma unroll
-		for ( int cc = 0 ; cc < T4P_G ; ++cc )
+		for ( int cc = 0 ; cc < G ; ++cc )
 			if ( n[cc] )
 			{
-				const int x = tile0 + ( c0 + cc ) * 32 + lane ;
+				const int x = tile0 + lane * ppl + c0 + cc ;
 				const int pass = x >= R.m ;
 				const int q = pass ? x - R.m : x ;
 				u64 *o = out + b[cc] ;
@@ -352,8 +395,8 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 	for ( int c = 0 ; c < nChunks ; ++c )
 	{
 		const int i = c * 32 + lane ;
-		const u32 cn = sw->cnt[i] ;
-		const bool pend = sw->base[i] != T4P_NONE && cn > T4P_SHORT && cn <= T4P_TMA_MAX ;
+		const u32 cn = i < tileLen ? sw->cnt[i] : 0 ;
+		const bool pend = i < tileLen && sw->base[i] != T4P_NONE && cn > T4P_SHORT && cn <= T4P_TMA_MAX ;
 		sw->sb[i] = pend ? T4P_NONE - 1 : T4P_NONE ; // NONE - 1: waiting for a round, NONE: nothing to stage
 		pendingAny |= pend ;
 	}
@@ -435,7 +478,7 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 	for ( int c = 0 ; c < nChunks ; ++c )
 	{
 		const int i = c * 32 + lane ;
-		u32 mask = __ballot_sync( 0xffffffffu, sw->base[i] != T4P_NONE && sw->cnt[i] > T4P_TMA_MAX ) ;
+		u32 mask = __ballot_sync( 0xffffffffu, i < tileLen && sw->base[i] != T4P_NONE && sw->cnt[i] > T4P_TMA_MAX ) ;
 		while ( mask )
 		{
 			const int src = __ffs( mask ) - 1 ;
@@ -459,8 +502,8 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 	}
 }
 
-// MINB: resident CTAs per SM the register allocation is bounded for (3: 80 registers, 24 warps per SM; 2: 128 registers)
-template <int MINB>
+// MINB: resident CTAs (= warps) per SM the register allocation is bounded for (24: 80 registers; 16: 128 registers)
+template <int MINB, int G>
 __global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4ProbeParams P )
 {
 	extern __shared__ __align__( 16 ) unsigned char t4p_dyn[] ; // T4P_WARPS x T4ProbeWarp (> 48 KB: dynamic, opted in by the host)
@@ -493,6 +536,7 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4Pro
 		R.dir = (const T4Dir *)( P.A + st->dirOff ) ;
 		R.dirMask = st->dirCap - 1 ;
 		R.salt = st->considerBarcode ? ( (u64)(u32)( R.barcode + 1 ) << ( 2 * R.k ) ) : 0ull ;
+		R.mask = ( 1ull << ( 2 * R.k ) ) - 1ull ; // k <= 31
 		if ( R.len > T4_DEV_MAX_READ || R.len < R.k )
 		{
 			if ( lane == 0 )
@@ -515,8 +559,13 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4Pro
 				sw->fw[lane] = lane < W ? __ldg( pk + lane ) : 0 ;
 				sw->rc[lane] = lane < W ? __ldg( pk + W + lane ) : 0 ;
 			}
+			u32 nmw = 0 ;
 			if ( lane < 20 )
-				sw->nm[lane] = lane < W ? __ldg( (const u32 *)( pk + 2 * W ) + lane ) : 0 ;
+			{
+				nmw = lane < W ? __ldg( (const u32 *)( pk + 2 * W ) + lane ) : 0 ;
+				sw->nm[lane] = nmw ;
+			}
+			R.anyN = __any_sync( 0xffffffffu, nmw != 0 ) ;
 			__syncwarp() ;
 		}
 		T4ProbeScan S ;
@@ -539,20 +588,22 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4Pro
 			for ( int t = 0 ; t < nTiles ; ++t )
 			{
 				const int tile0 = t * T4P_TILE ;
-				const int nChunks = ( min( T4P_TILE, R.nPos - tile0 ) + 31 ) >> 5 ;
+				const int tileLen = min( T4P_TILE, R.nPos - tile0 ) ;
+				const int ppl = ( tileLen + 31 ) >> 5 ;
 				if ( sweep == 0 || nTiles > 1 )
 				{
-					const bool large = t4p_probe_tile( R, sw, tile0, nChunks, lane ) ;
+					u32 takenBits, localSum ;
+					const bool large = t4p_probe_tile<G>( R, sw, tile0, tileLen, ppl, lane, takenBits, localSum ) ;
 					if ( nTiles == 1 && !large )
-						t4p_scan_fast( R, sw, nChunks, lane, S ) ;
+						t4p_scan_fast( sw, tileLen, ppl, lane, takenBits, localSum, S ) ;
 					else
 					{
-						t4p_scan_serial( R, sw, tile0, nChunks, lane, P.allowTotalSkip, S ) ;
+						t4p_scan_serial( R, sw, tile0, tileLen, lane, P.allowTotalSkip, S ) ;
 						flags |= 2 ;
 					}
 				}
 				if ( sweep == 1 )
-					t4p_emit_tile( R, sw, P.A, tile0, nChunks, lane, out, barPhase ) ;
+					t4p_emit_tile<G>( R, sw, P.A, tile0, tileLen, ppl, lane, out, barPhase ) ;
 			}
 			if ( sweep == 0 )
 			{

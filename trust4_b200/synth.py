@@ -514,14 +514,15 @@ def build_workload(clones: Clones, reads: Reads, min_anchor: int = 17, device=No
 # An erroneous copy of an abundant clonotype (minCnt 1, medianCnt > 65536) is the most expensive kind: it overlaps
 # many contigs of its shard and most of its overhangs need the banded DP.  Table fitted by non-negative least squares
 # to the per-stream cycle counts of the default bench workload (bench.py --dump-streams, bench/fit_cost_model.py;
-# correlation 0.93 with the measured stream times), smoothed where a cell has too few reads.
-COST_DUP = 3.0
+# correlation 0.93 with the measured stream times; geometric mean of the fits on equal-count and on cost-balanced shards,
+# because the cost of a record also grows with the size of its shard), smoothed where a cell has too few reads.
+COST_DUP = 2.5
 COST_MIN_EDGES = (1, 2, 4, 8, 16, 64, 256, 1 << 40)
 COST_MED_EDGES = (4, 16, 64, 256, 1024, 4096, 16384, 65536, 1 << 40)
-COST_TABLE = np.array([[348, 225, 374, 322, 207, 298, 538, 575, 918], [330, 330, 198, 356, 161, 214, 351, 330, 651],
-                       [324, 324, 324, 465, 190, 208, 284, 363, 635], [298, 298, 298, 115, 296, 241, 300, 447, 687],
-                       [369, 369, 369, 387, 278, 313, 352, 429, 952], [242, 242, 242, 242, 125, 235, 366, 242, 347],
-                       [173, 173, 173, 60, 60, 162, 289, 185, 281], [125, 125, 125, 125, 152, 124, 125, 120, 137]], dtype=np.float64)
+COST_TABLE = np.array([[306, 228, 305, 301, 205, 276, 454, 464, 630], [314, 182, 285, 316, 174, 209, 334, 361, 581],
+                       [295, 180, 302, 406, 192, 206, 271, 339, 565], [284, 284, 280, 270, 273, 236, 285, 399, 586],
+                       [332, 332, 200, 377, 279, 293, 324, 380, 686], [256, 256, 256, 412, 132, 234, 335, 238, 336],
+                       [215, 215, 215, 205, 127, 164, 279, 185, 274], [117, 117, 117, 117, 173, 117, 112, 114, 124]], dtype=np.float64)
 
 
 def read_cost(descs, med_cnt=None) -> np.ndarray:
