@@ -26,7 +26,7 @@
                                     // (with 8 warps per CTA 18 % of all issued instructions recomputed `smem + warp * sizeof`)
 #define T4P_PMAX 9                  // positions per lane and tile
 #define T4P_TILE ( 32 * T4P_PMAX )  // positions (both strand passes) per tile: a 150 bp read at k = 9 has 284
-#define T4P_STG 384                 // TMA staging tile per warp, postings (3 KB; 24 one-warp CTAs x (8 KB + 1 KB reserved) fit an SM)
+#define T4P_STG 512                 // TMA staging tile per warp, postings (4 KB)
 #define T4P_SHORT 4                 // a list of <= 4 postings is one 32-byte sector
 #define T4P_TMA_MAX 256             // longer lists stream through 128-bit loads instead of the staging tile
 #define T4P_NONE 0xffffffffu
@@ -55,7 +55,7 @@ struct __align__( 16 ) T4ProbeWarp // sizeof is a multiple of 16: every warp's s
 	u32 lo[T4P_TILE] ;         // per position of the tile: postings list offset >> 5 (lists are 32-byte aligned) ...
 	u32 cnt[T4P_TILE] ;        // ... its length (0: k-mer with an N, pass not probed, code absent) ...
 	u32 base[T4P_TILE] ;       // ... first hit slot of the read, T4P_NONE = lookup not taken
-	u32 sb[T4P_TILE] ;         // ... staging offset of the current TMA round
+	u32 sb[T4P_TILE] ;         // table of the tile's TMA-staged lists: position index per entry, in position order
 	u64 fw[18], rc[18] ;       // packed words (+ zero padding for the two-word funnel shift)
 	u32 nm[20] ;
 	u64 bar ;                  // mbarrier
@@ -389,88 +389,66 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 						o[j] = t4p_key( pass, q, p[cc][j], 0 ) ;
 			}
 	}
-	// ---- lists of 5 .. T4P_TMA_MAX postings: TMA into the staging tile, rounds of at most T4P_STG postings
-	u32 pendingAny = 0 ;
+	// ---- lists of 5 .. T4P_TMA_MAX postings: through the TMA staging tile.
+	// (1) compact them, in position order, into a table in shared memory (sw->sb: position index per entry);
+	// (2) rounds of up to 32 entries whose even-rounded lengths fit the tile: lane e owns entry w0 + e, issues its bulk
+	//     copy, all wait on the mbarrier; (3) one staged list at a time is turned into keys by the whole warp.
+	u32 nLong = 0 ;
 #pragma unroll 1
 	for ( int c = 0 ; c < nChunks ; ++c )
 	{
 		const int i = c * 32 + lane ;
 		const u32 cn = i < tileLen ? sw->cnt[i] : 0 ;
-		const bool pend = i < tileLen && sw->base[i] != T4P_NONE && cn > T4P_SHORT && cn <= T4P_TMA_MAX ;
-		sw->sb[i] = pend ? T4P_NONE - 1 : T4P_NONE ; // NONE - 1: waiting for a round, NONE: nothing to stage
-		pendingAny |= pend ;
+		const bool isLong = i < tileLen && cn > T4P_SHORT && cn <= T4P_TMA_MAX && sw->base[i] != T4P_NONE ;
+		const u32 m = __ballot_sync( 0xffffffffu, isLong ) ;
+		if ( isLong )
+			sw->sb[nLong + __popc( m & ( ( 1u << lane ) - 1u ) )] = (u32)i ;
+		nLong += __popc( m ) ;
 	}
-	pendingAny = __any_sync( 0xffffffffu, pendingAny != 0 ) ;
-	while ( pendingAny )
-	{
-		// staging offsets of this round: exclusive prefix (in position order) over the even-rounded counts of the waiting
-		// lists; a list is taken iff it still fits, and since the offsets include the lists that do not fit, the taken
-		// ones are a prefix of the waiting ones
-		u32 run = 0, roundBytes = 0 ;
-		bool more = false ;
+	__syncwarp() ;
 #pragma unroll 1
-		for ( int c = 0 ; c < nChunks ; ++c )
+	for ( u32 w0 = 0 ; w0 < nLong ; )
+	{
+		// my entry of this round
+		const u32 e = w0 + lane ;
+		int pi = -1 ;
+		u32 n = 0, v = 0 ;
+		if ( e < nLong )
 		{
-			const int i = c * 32 + lane ;
-			const bool wait = sw->sb[i] == T4P_NONE - 1 ;
-			const u32 v = wait ? ( ( sw->cnt[i] + 1 ) & ~1u ) : 0 ;
-			u32 tot ;
-			const u32 o = t4p_warp_excl_scan( v, tot, lane ) ;
-			if ( wait )
-			{
-				if ( run + o + v <= T4P_STG )
-				{
-					sw->sb[i] = run + o ;
-					roundBytes += v * 8 ;
-				}
-				else
-					more = true ;
-			}
-			run += tot ;
+			pi = (int)sw->sb[e] ;
+			n = sw->cnt[pi] ;
+			v = ( n + 1 ) & ~1u ;
 		}
-#pragma unroll
-		for ( int d = 16 ; d > 0 ; d >>= 1 )
-			roundBytes += __shfl_xor_sync( 0xffffffffu, roundBytes, d ) ;
+		u32 tot ;
+		const u32 so = t4p_warp_excl_scan( v, tot, lane ) ;
+		const bool in = pi >= 0 && so + v <= T4P_STG ;                  // a prefix of the 32 candidates (offsets are monotone)
+		const u32 inMask = __ballot_sync( 0xffffffffu, in ) ;
+		const int nIn = __popc( inMask ) ;                              // >= 1: a single list always fits (n <= T4P_TMA_MAX <= T4P_STG)
+		const u32 roundBytes = __shfl_sync( 0xffffffffu, so + v, nIn - 1 ) * 8 ;
 		// the previous round's generic-proxy reads of the tile are ordered before the async-proxy writes of this one
 		asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ) ;
 		__syncwarp() ;
 		if ( lane == 0 )
 			t4p_bar_expect( &sw->bar, roundBytes ) ;
 		__syncwarp() ;
-#pragma unroll 1
-		for ( int c = 0 ; c < nChunks ; ++c )
-		{
-			const int i = c * 32 + lane ;
-			const u32 so = sw->sb[i] ;
-			if ( so < T4P_NONE - 1 )
-				t4p_bulk_g2s( sw->stg + so, A + ( (u64)sw->lo[i] << 5 ), ( ( sw->cnt[i] + 1 ) & ~1u ) * 8, &sw->bar ) ;
-		}
+		if ( in )
+			t4p_bulk_g2s( sw->stg + so, A + ( (u64)sw->lo[pi] << 5 ), v * 8, &sw->bar ) ;
+		const u32 bo = in ? sw->base[pi] : 0 ;
 		t4p_bar_wait( &sw->bar, barPhase ) ;
 		barPhase ^= 1 ;
-		// convert: one staged list at a time, the whole warp on it (coalesced 8-byte stores)
 #pragma unroll 1
-		for ( int c = 0 ; c < nChunks ; ++c )
+		for ( int src = 0 ; src < nIn ; ++src )
 		{
-			const int i = c * 32 + lane ;
-			const u32 mySo = sw->sb[i] ;
-			u32 mask = __ballot_sync( 0xffffffffu, mySo < T4P_NONE - 1 ) ;
-			while ( mask )
-			{
-				const int src = __ffs( mask ) - 1 ;
-				mask &= mask - 1 ;
-				const int is = c * 32 + src ;
-				const u32 n = sw->cnt[is], so = sw->sb[is], bo = sw->base[is] ;
-				const int x = tile0 + is ;
-				const int pass = x >= R.m ;
-				const int q = pass ? x - R.m : x ;
-				for ( u32 j = lane ; j < n ; j += 32 )
-					out[bo + j] = t4p_key( pass, q, sw->stg[so + j], 0 ) ;
-			}
-			__syncwarp() ;
-			if ( mySo < T4P_NONE - 1 )
-				sw->sb[i] = T4P_NONE ;
+			const u32 ln = __shfl_sync( 0xffffffffu, n, src ) ;
+			const u32 lso = __shfl_sync( 0xffffffffu, so, src ) ;
+			const u32 lbo = __shfl_sync( 0xffffffffu, bo, src ) ;
+			const int x = tile0 + __shfl_sync( 0xffffffffu, pi, src ) ;
+			const int pass = x >= R.m ;
+			const int q = pass ? x - R.m : x ;
+			for ( u32 j = lane ; j < ln ; j += 32 )
+				out[lbo + j] = t4p_key( pass, q, sw->stg[lso + j], 0 ) ;
 		}
-		pendingAny = __any_sync( 0xffffffffu, more ) ;
+		w0 += nIn ;
 		__syncwarp() ;
 	}
 	// ---- longer lists: streamed by the whole warp, two postings (128 bits) per lane and load
