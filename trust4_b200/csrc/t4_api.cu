@@ -12,6 +12,7 @@
 #include <vector>
 #include <string>
 #include <mutex>
+#include <thread>
 
 #include "t4_engine.h"
 
@@ -1409,9 +1410,25 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 	size_t oOps = oEv + al( (size_t)n ) ;
 	// 2-bit packed copy of the reads, fixed stride (the longest supported read of the workload)
 	int maxLen = 0 ;
-	for ( int64_t i = 0 ; i < n ; ++i )
-		if ( descs[i].len > maxLen && descs[i].len <= T4_DEV_MAX_READ )
-			maxLen = descs[i].len ;
+	{
+		// one pass over the record array (64 B stride); a few host threads, this sits inside the e2e path
+		const int nth = n > ( 1 << 18 ) ? 8 : 1 ;
+		std::vector<int> part( nth, 0 ) ;
+		std::vector<std::thread> th ;
+		for ( int t = 0 ; t < nth ; ++t )
+			th.emplace_back( [&, t]() {
+				int m = 0 ;
+				for ( int64_t i = n * t / nth ; i < n * ( t + 1 ) / nth ; ++i )
+					if ( descs[i].len > m && descs[i].len <= T4_DEV_MAX_READ )
+						m = descs[i].len ;
+				part[t] = m ;
+			} ) ;
+		for ( auto &x : th )
+			x.join() ;
+		for ( int t = 0 ; t < nth ; ++t )
+			if ( part[t] > maxLen )
+				maxLen = part[t] ;
+	}
 	const u64 packStride = t4_pack_words( maxLen ) ;
 	size_t oPacked = oOps ;
 	size_t oOdd = oPacked + al( (size_t)n * packStride * 8 + 16 ) ;

@@ -163,53 +163,53 @@ __device__ __forceinline__ bool t4p_active( const T4ProbeRead &R, int x, int &pa
 
 __device__ __forceinline__ u64 t4p_base_at( const u64 *W, int p ) { return ( W[p >> 5] >> ( 62 - 2 * ( p & 31 ) ) ) & 3ull ; }
 
-// Directory probes of one tile.  Lane l owns the CONTIGUOUS positions [l * ppl, (l + 1) * ppl) of the tile, so its k-mer
-// codes roll (KmerCode::Append, KmerCode.hpp:94: one 2-bit base per step) and "equal to the previous k-mer"
-// (SeqSet.hpp:1376) is a register compare; G positions per lane are in flight together, one LDG.E.256 each = the
-// 32-byte T4Dir sector.  Results: sw->cnt[i], sw->lo[i] per position i of the tile; takenBits (bit c: the lane's c-th
-// position passes the plain "taken" predicate) and localSum (its postings) feed the fast slot assignment.
-// Returns true iff some list has >= 100 postings.  Loops over a lane's positions are deliberately not fully unrolled:
-// the kernel has to stay inside the instruction cache (a first, fully unrolled version over register arrays spent 8.7
-// of 16 stall cycles per issue on instruction fetch).
+#define T4P_TAKEN 0x80000000u       // bit 31 of sw->cnt[i]: the position passes the plain "taken" predicate
+#define T4P_CNT( v ) ( ( v ) & 0x7fffffffu )
+
+// Directory probes of one tile.  Position i of the tile belongs to lane i & 31 (chunk i >> 5): the G positions a lane
+// has in flight are 32 apart, each probe is one LDG.E.256 = the 32-byte T4Dir sector.  One funnel shift gives a k-mer
+// code; the code of the previous position (for "equal to the previous k-mer", SeqSet.hpp:1376) comes from the
+// neighbouring lane by shuffle.  Results per position: sw->cnt[i] (postings, bit 31 = taken), sw->lo[i].
+// Returns true iff some list has >= 100 postings.  Loops over chunks are deliberately not fully unrolled: the kernel has
+// to stay inside the instruction cache (a first, fully unrolled version over register arrays spent 8.7 of 16 stall
+// cycles per issue on instruction fetch).
 template <int G>
-__device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int tileLen, int ppl, int lane,
-	u32 &takenBits, u32 &localSum )
+__device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWarp *sw, int tile0, int tileLen, int lane )
 {
 	bool large = false ;
-	takenBits = 0 ;
-	localSum = 0 ;
-	u64 code = 0 ;
-	int lastX = -2 ;
+	const int nChunks = ( tileLen + 31 ) >> 5 ;
+	u64 carry = 0 ; // code of the last position of the previous chunk
+	if ( tile0 > 0 )
+	{
+		int pass, q ;
+		if ( t4p_active( R, tile0 - 1, pass, q ) )
+			carry = t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) ;
+	}
 #pragma unroll 1
-	for ( int c0 = 0 ; c0 < ppl ; c0 += G )
+	for ( int c0 = 0 ; c0 < nChunks ; c0 += G )
 	{
 		u64 key[G], v[G][4] ;
-		u32 slot[G] ;
+		u32 slot[G], tk[G] ;
 #pragma unroll
 		for ( int cc = 0 ; cc < G ; ++cc )
 		{
-			const int c = c0 + cc ;
-			const int i = lane * ppl + c ;
+			const int i = ( c0 + cc ) * 32 + lane ;
 			int pass, q ;
 			key[cc] = 0 ;
 			slot[cc] = 0 ;
-			if ( c < ppl && i < tileLen && t4p_active( R, tile0 + i, pass, q ) )
+			tk[cc] = 0 ;
+			if ( c0 + cc >= nChunks )
+				continue ;                                       // warp-uniform
+			const bool act = i < tileLen && t4p_active( R, tile0 + i, pass, q ) ;
+			const u64 code = act ? t4p_extract( pass ? sw->rc : sw->fw, q, R.k ) : 0 ;
+			u64 prev = __shfl_up_sync( 0xffffffffu, code, 1 ) ;
+			if ( lane == 0 )
+				prev = carry ;
+			carry = __shfl_sync( 0xffffffffu, code, 31 ) ;
+			if ( act )
 			{
-				const u64 *W = pass ? sw->rc : sw->fw ;
-				u64 prev ;
-				if ( q == 0 || lastX != tile0 + i - 1 )
-				{
-					code = t4p_extract( W, q, R.k ) ;
-					prev = q > 0 ? t4p_extract( W, q - 1, R.k ) : 0 ;
-				}
-				else
-				{
-					prev = code ;
-					code = ( ( code << 2 ) & R.mask ) | t4p_base_at( W, q + R.k - 1 ) ;
-				}
-				lastX = tile0 + i ;
 				if ( q == 0 || code != prev )
-					takenBits |= 1u << c ;
+					tk[cc] = T4P_TAKEN ;
 				// validity window: forward positions [q, q + k) or, for the reverse pass, [len - q - k, len - q)
 				if ( !R.anyN || !t4p_has_n( sw->nm, pass ? R.len - q - R.k : q, R.k ) )
 				{
@@ -222,9 +222,8 @@ __device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWar
 #pragma unroll
 		for ( int cc = 0 ; cc < G ; ++cc )
 		{
-			const int c = c0 + cc ;
-			const int i = lane * ppl + c ;
-			if ( c >= ppl || i >= tileLen )
+			const int i = ( c0 + cc ) * 32 + lane ;
+			if ( c0 + cc >= nChunks )
 				break ;
 			u32 n = 0, l = 0 ;
 			if ( key[cc] != 0 )
@@ -242,12 +241,13 @@ __device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWar
 					l = (u32)( lOff >> 5 ) ;
 					if ( n >= 100 )
 						large = true ;
-					if ( ( takenBits >> c ) & 1u )
-						localSum += n ;
 				}
 			}
-			sw->cnt[i] = n ;
-			sw->lo[i] = l ;
+			if ( i < tileLen )
+			{
+				sw->cnt[i] = n | tk[cc] ;
+				sw->lo[i] = l ;
+			}
 		}
 	}
 	__syncwarp() ;
@@ -255,26 +255,35 @@ __device__ __forceinline__ bool t4p_probe_tile( const T4ProbeRead &R, T4ProbeWar
 }
 
 // No list reaches 100 postings: "taken" is the per-position predicate computed above (first k-mer of the pass, or code
-// differs from the previous k-mer's -- N counted as A), and the hit slots are an exclusive prefix sum in position order:
-// one warp scan over the lanes' sums, then every lane walks its own contiguous positions.
-__device__ __forceinline__ void t4p_scan_fast( T4ProbeWarp *sw, int tileLen, int ppl, int lane, u32 takenBits, u32 localSum, T4ProbeScan &S )
+// differs from the previous k-mer's -- N counted as A), and the hit slots are an exclusive prefix sum in position order.
+// Here lane l owns the CONTIGUOUS positions [l * ppl, (l + 1) * ppl): a local sum, ONE warp scan, a local walk.
+__device__ __forceinline__ void t4p_scan_fast( T4ProbeWarp *sw, int tileLen, int lane, T4ProbeScan &S )
 {
-	u32 tot ;
-	u32 o = S.total + t4p_warp_excl_scan( localSum, tot, lane ) ;
+	const int ppl = ( tileLen + 31 ) >> 5 ;
+	const int i0 = lane * ppl, i1 = min( tileLen, i0 + ppl ) ;
+	u32 local = 0, looks = 0 ;
 #pragma unroll 1
-	for ( int c = 0 ; c < ppl ; ++c )
+	for ( int i = i0 ; i < i1 ; ++i )
 	{
-		const int i = lane * ppl + c ;
-		if ( i >= tileLen )
-			break ;
-		const u32 n = sw->cnt[i] ;
-		const bool emit = ( ( takenBits >> c ) & 1u ) && n > 0 ;
+		const u32 cv = sw->cnt[i] ;
+		if ( cv & T4P_TAKEN )
+		{
+			local += T4P_CNT( cv ) ;
+			++looks ;
+		}
+	}
+	u32 tot ;
+	u32 o = S.total + t4p_warp_excl_scan( local, tot, lane ) ;
+#pragma unroll 1
+	for ( int i = i0 ; i < i1 ; ++i )
+	{
+		const u32 cv = sw->cnt[i] ;
+		const bool emit = ( cv & T4P_TAKEN ) && T4P_CNT( cv ) > 0 ;
 		sw->base[i] = emit ? o : T4P_NONE ;
 		if ( emit )
-			o += n ;
+			o += T4P_CNT( cv ) ;
 	}
 	S.total += tot ;
-	u32 looks = __popc( takenBits ) ;
 #pragma unroll
 	for ( int d = 16 ; d > 0 ; d >>= 1 )
 		looks += __shfl_xor_sync( 0xffffffffu, looks, d ) ;
@@ -308,7 +317,7 @@ __device__ __forceinline__ void t4p_scan_serial( const T4ProbeRead &R, T4ProbeWa
 			else
 				code = ( ( code << 2 ) & R.mask ) | t4p_base_at( W, q + R.k - 1 ) ;
 			lastX = tile0 + i ;
-			const u32 size = sw->cnt[i] ;
+			const u32 size = T4P_CNT( sw->cnt[i] ) ;
 			const int e = q + R.k - 1 ;
 			bool setPrev = true ;
 			if ( q == 0 || code != S.prev )
@@ -349,25 +358,26 @@ __device__ __forceinline__ u64 t4p_key( int pass, int q, u64 posting, int big )
 
 // Postings -> hit keys for one tile.  out: first key of this read.
 template <int G>
-__device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp *sw, const char *A, int tile0, int tileLen, int ppl, int lane,
+__device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp *sw, const char *A, int tile0, int tileLen, int lane,
 	u64 *out, u32 &barPhase )
 {
 	const int nChunks = ( tileLen + 31 ) >> 5 ;
-	// ---- lists of <= 4 postings: one sector, fetched by the owner lane (its contiguous positions); G lists in flight
+	// ---- lists of <= 4 postings: one sector, fetched by the owner lane (position i & 31 == lane); G lists in flight.
+	// Hit slots grow with the position, so neighbouring lanes write neighbouring output ranges.
 #pragma unroll 1
-	for ( int c0 = 0 ; c0 < ppl ; c0 += G )
+	for ( int c0 = 0 ; c0 < nChunks ; c0 += G )
 	{
 		u64 p[G][4] ;
 		u32 n[G], b[G] ;
 #pragma unroll
 		for ( int cc = 0 ; cc < G ; ++cc )
 		{
-			const int i = lane * ppl + c0 + cc ;
+			const int i = ( c0 + cc ) * 32 + lane ;
 			n[cc] = 0 ;
-			if ( c0 + cc < ppl && i < tileLen )
+			if ( c0 + cc < nChunks && i < tileLen )
 			{
 				b[cc] = sw->base[i] ;
-				const u32 cn = sw->cnt[i] ;
+				const u32 cn = T4P_CNT( sw->cnt[i] ) ;
 				if ( b[cc] != T4P_NONE && cn <= T4P_SHORT )
 				{
 					n[cc] = cn ;
@@ -379,7 +389,7 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 		for ( int cc = 0 ; cc < G ; ++cc )
 			if ( n[cc] )
 			{
-				const int x = tile0 + lane * ppl + c0 + cc ;
+				const int x = tile0 + ( c0 + cc ) * 32 + lane ;
 				const int pass = x >= R.m ;
 				const int q = pass ? x - R.m : x ;
 				u64 *o = out + b[cc] ;
@@ -391,14 +401,15 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 	}
 	// ---- lists of 5 .. T4P_TMA_MAX postings: through the TMA staging tile.
 	// (1) compact them, in position order, into a table in shared memory (sw->sb: position index per entry);
-	// (2) rounds of up to 32 entries whose even-rounded lengths fit the tile: lane e owns entry w0 + e, issues its bulk
-	//     copy, all wait on the mbarrier; (3) one staged list at a time is turned into keys by the whole warp.
+	// (2) rounds of up to 32 entries whose even-rounded lengths fit the tile: lane e owns entry w0 + e and issues its bulk
+	//     copy, all wait on the mbarrier; (3) the staged slots are converted FLAT, 32 per step: every lane finds the list
+	//     of its slot by a binary search over the lanes' staging offsets (5 shuffles), so short lists do not idle lanes.
 	u32 nLong = 0 ;
 #pragma unroll 1
 	for ( int c = 0 ; c < nChunks ; ++c )
 	{
 		const int i = c * 32 + lane ;
-		const u32 cn = i < tileLen ? sw->cnt[i] : 0 ;
+		const u32 cn = i < tileLen ? T4P_CNT( sw->cnt[i] ) : 0 ;
 		const bool isLong = i < tileLen && cn > T4P_SHORT && cn <= T4P_TMA_MAX && sw->base[i] != T4P_NONE ;
 		const u32 m = __ballot_sync( 0xffffffffu, isLong ) ;
 		if ( isLong )
@@ -409,44 +420,59 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 #pragma unroll 1
 	for ( u32 w0 = 0 ; w0 < nLong ; )
 	{
-		// my entry of this round
 		const u32 e = w0 + lane ;
-		int pi = -1 ;
+		int pi = 0 ;
 		u32 n = 0, v = 0 ;
 		if ( e < nLong )
 		{
 			pi = (int)sw->sb[e] ;
-			n = sw->cnt[pi] ;
+			n = T4P_CNT( sw->cnt[pi] ) ;
 			v = ( n + 1 ) & ~1u ;
 		}
 		u32 tot ;
-		const u32 so = t4p_warp_excl_scan( v, tot, lane ) ;
-		const bool in = pi >= 0 && so + v <= T4P_STG ;                  // a prefix of the 32 candidates (offsets are monotone)
-		const u32 inMask = __ballot_sync( 0xffffffffu, in ) ;
-		const int nIn = __popc( inMask ) ;                              // >= 1: a single list always fits (n <= T4P_TMA_MAX <= T4P_STG)
-		const u32 roundBytes = __shfl_sync( 0xffffffffu, so + v, nIn - 1 ) * 8 ;
+		u32 so = t4p_warp_excl_scan( v, tot, lane ) ;
+		const bool in = e < nLong && so + v <= T4P_STG ;                // a prefix of the 32 candidates (offsets are monotone)
+		const int nIn = __popc( __ballot_sync( 0xffffffffu, in ) ) ;    // >= 1: a single list always fits (n <= T4P_TMA_MAX <= T4P_STG)
+		const u32 slots = __shfl_sync( 0xffffffffu, so + v, nIn - 1 ) ;
 		// the previous round's generic-proxy reads of the tile are ordered before the async-proxy writes of this one
 		asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ) ;
 		__syncwarp() ;
 		if ( lane == 0 )
-			t4p_bar_expect( &sw->bar, roundBytes ) ;
+			t4p_bar_expect( &sw->bar, slots * 8 ) ;
 		__syncwarp() ;
 		if ( in )
 			t4p_bulk_g2s( sw->stg + so, A + ( (u64)sw->lo[pi] << 5 ), v * 8, &sw->bar ) ;
 		const u32 bo = in ? sw->base[pi] : 0 ;
+		if ( !in )
+			so = 0xffffffffu ;                                            // never "<= slot" in the search below
 		t4p_bar_wait( &sw->bar, barPhase ) ;
 		barPhase ^= 1 ;
 #pragma unroll 1
-		for ( int src = 0 ; src < nIn ; ++src )
+		for ( u32 s0 = 0 ; s0 < slots ; s0 += 32 )
 		{
-			const u32 ln = __shfl_sync( 0xffffffffu, n, src ) ;
-			const u32 lso = __shfl_sync( 0xffffffffu, so, src ) ;
-			const u32 lbo = __shfl_sync( 0xffffffffu, bo, src ) ;
-			const int x = tile0 + __shfl_sync( 0xffffffffu, pi, src ) ;
-			const int pass = x >= R.m ;
-			const int q = pass ? x - R.m : x ;
-			for ( u32 j = lane ; j < ln ; j += 32 )
-				out[lbo + j] = t4p_key( pass, q, sw->stg[lso + j], 0 ) ;
+			const u32 sl = s0 + lane ;
+			int lo_ = 0, hi_ = nIn - 1 ;                                  // largest entry with so <= sl
+#pragma unroll
+			for ( int it = 0 ; it < 5 ; ++it )
+			{
+				const int mid = ( lo_ + hi_ + 1 ) >> 1 ;
+				const u32 som = __shfl_sync( 0xffffffffu, so, mid ) ;
+				if ( som <= sl )
+					lo_ = mid ;
+				else
+					hi_ = mid - 1 ;
+			}
+			const u32 fn = __shfl_sync( 0xffffffffu, n, lo_ ) ;
+			const u32 fso = __shfl_sync( 0xffffffffu, so, lo_ ) ;
+			const u32 fbo = __shfl_sync( 0xffffffffu, bo, lo_ ) ;
+			const int x = tile0 + __shfl_sync( 0xffffffffu, pi, lo_ ) ;
+			const u32 j = sl - fso ;
+			if ( sl < slots && j < fn )
+			{
+				const int pass = x >= R.m ;
+				const int q = pass ? x - R.m : x ;
+				out[fbo + j] = t4p_key( pass, q, sw->stg[sl], 0 ) ;
+			}
 		}
 		w0 += nIn ;
 		__syncwarp() ;
@@ -456,13 +482,13 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 	for ( int c = 0 ; c < nChunks ; ++c )
 	{
 		const int i = c * 32 + lane ;
-		u32 mask = __ballot_sync( 0xffffffffu, i < tileLen && sw->base[i] != T4P_NONE && sw->cnt[i] > T4P_TMA_MAX ) ;
+		u32 mask = __ballot_sync( 0xffffffffu, i < tileLen && sw->base[i] != T4P_NONE && T4P_CNT( sw->cnt[i] ) > T4P_TMA_MAX ) ;
 		while ( mask )
 		{
 			const int src = __ffs( mask ) - 1 ;
 			mask &= mask - 1 ;
 			const int is = c * 32 + src ;
-			const u32 n = sw->cnt[is], bo = sw->base[is] ;
+			const u32 n = T4P_CNT( sw->cnt[is] ), bo = sw->base[is] ;
 			const char *l = A + ( (u64)sw->lo[is] << 5 ) ;
 			const int x = tile0 + is ;
 			const int pass = x >= R.m ;
@@ -567,13 +593,11 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4Pro
 			{
 				const int tile0 = t * T4P_TILE ;
 				const int tileLen = min( T4P_TILE, R.nPos - tile0 ) ;
-				const int ppl = ( tileLen + 31 ) >> 5 ;
 				if ( sweep == 0 || nTiles > 1 )
 				{
-					u32 takenBits, localSum ;
-					const bool large = t4p_probe_tile<G>( R, sw, tile0, tileLen, ppl, lane, takenBits, localSum ) ;
+					const bool large = t4p_probe_tile<G>( R, sw, tile0, tileLen, lane ) ;
 					if ( nTiles == 1 && !large )
-						t4p_scan_fast( sw, tileLen, ppl, lane, takenBits, localSum, S ) ;
+						t4p_scan_fast( sw, tileLen, lane, S ) ;
 					else
 					{
 						t4p_scan_serial( R, sw, tile0, tileLen, lane, P.allowTotalSkip, S ) ;
@@ -581,7 +605,7 @@ __global__ void __launch_bounds__( 32 * T4P_WARPS, MINB ) t4_probe_kernel( T4Pro
 					}
 				}
 				if ( sweep == 1 )
-					t4p_emit_tile<G>( R, sw, P.A, tile0, tileLen, ppl, lane, out, barPhase ) ;
+					t4p_emit_tile<G>( R, sw, P.A, tile0, tileLen, lane, out, barPhase ) ;
 			}
 			if ( sweep == 0 )
 			{
