@@ -230,9 +230,10 @@ int t4_workload_results(t4_workload *w, int32_t *ret_codes, int8_t *strands, int
 #define T4_EV_PURGED (1u << 6)          /* ReleaseFinishedBarcodeSeq after this iteration (main.cpp:1855) */
 int t4_workload_events(t4_workload *w, uint8_t *events);
 
-/* Merge step: pack every live contig of the given sets, in (set, slot) order, into ONE caller-provided
- * DEVICE buffer (e.g. a torch tensor) ready for an NCCL all-gather.  Record = 32-byte header {u32 set, slot, len,
- * nameLen; i32 barcode, numRead; u32 recordBytes, 0} + consensus[len] + posWeight int32[len][4] + name, padded to 16 B.
+/* Merge step and stage-1 product: pack every live contig of the given sets, in (set, slot) order, into ONE
+ * caller-provided DEVICE buffer (e.g. a torch tensor) ready for an NCCL all-gather or one D2H copy.  Record = 32-byte
+ * header {u32 set, slot, len, nameLen; i32 barcode, numRead; u32 recordBytes, flags} + consensus[len] + posWeight
+ * columns [len][4] as u16 (flags bit 0, when every count of the contig fits 16 bits) or int32 + name, padded to 16 B.
  * With dev_buf == NULL only *bytes_needed / *n_contigs are computed. */
 int t4_streams_pack_contigs(t4_seqset *const *sets, int n_sets, void *dev_buf, size_t cap, size_t *bytes_needed,
                             int64_t *n_contigs);

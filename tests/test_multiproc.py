@@ -92,3 +92,29 @@ def test_merge_oracle_on_packed_contigs(emu_lib, ref):
     m2, removed2 = ref.merge_sets(direct)
     assert m1.output() == m2.output() and removed1 == removed2
     assert m1.size() == sum(1 for _ in contigs) - removed1 and removed1 >= 0
+
+
+def test_pack_narrow_and_wide_counts(emu_lib):
+    """Packed contig records: posWeight as u16 when every count fits, int32 otherwise (a contig with 70 000 copies of one read)."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from trust4_b200 import api, dist as tdist
+    emu_lib.check(emu_lib.reset())
+    rng = np.random.default_rng(9)
+    a = "".join("ACGT"[c] for c in rng.integers(0, 4, size=120))
+    b = "".join("ACGT"[c] for c in rng.integers(0, 4, size=140))
+    s = api.SeqSet(9, emu_lib)
+    s.input_novel_read("IGHV1-2*01", a, 1, -1)
+    s.input_novel_read("TRBV7-9*01", b, 1, -1)
+    assert s.add_read(a, "IGHV", 0, -1, 5, 0, 0.9)[0] == 0
+    for _ in range(70000):
+        assert s.repeat_add_read(a) == 0
+    buf, n = tdist.pack_contigs(emu_lib, [s])
+    assert n == 2
+    recs = tdist.unpack_contigs(buf)
+    raw = buf.numpy()
+    assert int(raw[28:32].view(np.uint32)[0]) == 0                       # contig 0: wide (int32) columns
+    rb0 = int(raw[24:28].view(np.uint32)[0])
+    assert int(raw[rb0 + 28:rb0 + 32].view(np.uint32)[0]) == 1           # contig 1: u16 columns
+    assert recs[0]["pos_weight"].max() == 70002 and recs[1]["pos_weight"].max() == 1
+    assert tdist.format_output(recs)[0] == s.output()

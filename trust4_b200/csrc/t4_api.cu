@@ -161,21 +161,34 @@ __global__ void t4_dp_hot_kernel( int n, int variant, const int *tw, const i64 *
 		score[i] = sc ;
 }
 
+// One CTA per stream: decide for every live contig whether its posWeight counts fit 16 bits (scratch flag in the contig
+// record), and sum the record sizes.
 __global__ void t4_pack_size_kernel( char *A, const u64 *streamOff, u64 *sizes, u64 *counts )
 {
-	if ( threadIdx.x != 0 )
-		return ;
 	const T4Stream *st = (const T4Stream *)( A + streamOff[blockIdx.x] ) ;
-	const T4Contig *ct = (const T4Contig *)( A + st->seqsOff ) ;
+	T4Contig *ct = (T4Contig *)( A + st->seqsOff ) ;
 	u64 tot = 0, n = 0 ;
 	for ( int i = 0 ; i < st->nSeqs ; ++i )
-		if ( ct[i].consOff )
-		{
-			tot += t4_pack_record_bytes( ct[i] ) ;
-			++n ;
-		}
-	sizes[blockIdx.x] = tot ;
-	counts[blockIdx.x] = n ;
+	{
+		T4Contig &k = ct[i] ;
+		if ( !k.consOff )
+			continue ;
+		const int *pw = (const int *)( A + k.pwOff + 16ull * k.lead ) ;
+		int wide = 0 ;
+		for ( int x = threadIdx.x ; x < 4 * k.len ; x += blockDim.x )
+			wide |= ( (unsigned)pw[x] > 65535u ) ;
+		wide = __syncthreads_or( wide ) ;
+		if ( threadIdx.x == 0 )
+			k.packNarrow = wide ? 0 : 1 ;
+		__syncthreads() ;
+		tot += t4_pack_record_bytes( k ) ;
+		++n ;
+	}
+	if ( threadIdx.x == 0 )
+	{
+		sizes[blockIdx.x] = tot ;
+		counts[blockIdx.x] = n ;
+	}
 }
 
 __global__ void t4_pack_kernel( char *A, const u64 *streamOff, const u64 *outOff, char *out )
@@ -194,19 +207,37 @@ __global__ void t4_pack_kernel( char *A, const u64 *streamOff, const u64 *outOff
 		{
 			u32 *h = (u32 *)rec ;
 			h[0] = blockIdx.x ; h[1] = (u32)i ; h[2] = (u32)k.len ; h[3] = (u32)k.nameLen ;
-			h[4] = (u32)k.barcode ; h[5] = (u32)k.numRead ; h[6] = (u32)rb ; h[7] = 0 ;
+			h[4] = (u32)k.barcode ; h[5] = (u32)k.numRead ; h[6] = (u32)rb ; h[7] = k.packNarrow ? 1u : 0u ;
 		}
 		const char *cons = A + k.consOff + k.lead ;
-		const char *pw = A + k.pwOff + 16ull * k.lead ;
+		const int *pw = (const int *)( A + k.pwOff + 16ull * k.lead ) ;
 		const char *nm = A + k.nameOff ;
 		for ( int x = threadIdx.x ; x < k.len ; x += blockDim.x )
 			rec[32 + x] = cons[x] ;
-		for ( int x = threadIdx.x ; x < 16 * k.len ; x += blockDim.x )
-			rec[32 + k.len + x] = pw[x] ;
+		u64 nameAt ;
+		if ( k.packNarrow )
+		{
+			// the columns start at byte 32 + len (any alignment): byte stores
+			unsigned char *d = (unsigned char *)rec + 32 + k.len ;
+			for ( int x = threadIdx.x ; x < 4 * k.len ; x += blockDim.x )
+			{
+				const unsigned v = (unsigned)pw[x] ;
+				d[2 * x] = (unsigned char)( v & 255u ) ;
+				d[2 * x + 1] = (unsigned char)( v >> 8 ) ;
+			}
+			nameAt = 32ull + 9ull * k.len ;
+		}
+		else
+		{
+			const char *pb = (const char *)pw ;
+			for ( int x = threadIdx.x ; x < 16 * k.len ; x += blockDim.x )
+				rec[32 + k.len + x] = pb[x] ;
+			nameAt = 32ull + 17ull * k.len ;
+		}
 		for ( int x = threadIdx.x ; x < k.nameLen ; x += blockDim.x )
-			rec[32 + 17 * k.len + x] = nm[x] ;
+			rec[nameAt + x] = nm[x] ;
 		// tail padding of the 16-byte aligned record: defined bytes (the all-gathered buffers are compared bytewise)
-		for ( u64 x = 32ull + 17ull * k.len + k.nameLen + threadIdx.x ; x < rb ; x += blockDim.x )
+		for ( u64 x = nameAt + k.nameLen + threadIdx.x ; x < rb ; x += blockDim.x )
 			rec[x] = 0 ;
 		o += rb ;
 	}
@@ -1904,7 +1935,7 @@ int T4_API( streams_pack_contigs )( t4_seqset *const *sets, int n_sets, void *de
 	u64 *dSo = (u64 *)E.stage, *dSz = dSo + n_sets, *dCnt = dSz + n_sets, *dOff = dCnt + n_sets ;
 	r = h2d( dSo, so.data(), (size_t)n_sets * 8 ) ;
 	if ( r ) return r ;
-	t4_pack_size_kernel<<<n_sets, 32>>>( E.A, dSo, dSz, dCnt ) ;
+	t4_pack_size_kernel<<<n_sets, 128>>>( E.A, dSo, dSz, dCnt ) ;
 	CK( cudaGetLastError() ) ;
 	r = d2h( sizes.data(), dSz, (size_t)n_sets * 8 ) ;
 	if ( r ) return r ;
@@ -1914,11 +1945,16 @@ int T4_API( streams_pack_contigs )( t4_seqset *const *sets, int n_sets, void *de
 	for ( int j = 0 ; j < n_sets ; ++j )
 	{
 		const T4Stream *st = (const T4Stream *)( E.A + so[j] ) ;
-		const T4Contig *ct = (const T4Contig *)( E.A + st->seqsOff ) ;
+		T4Contig *ct = (T4Contig *)( E.A + st->seqsOff ) ;
 		sizes[j] = counts[j] = 0 ;
 		for ( int i = 0 ; i < st->nSeqs ; ++i )
 			if ( ct[i].consOff )
 			{
+				const int *pw = (const int *)( E.A + ct[i].pwOff + 16ull * ct[i].lead ) ;
+				int wide = 0 ;
+				for ( int x = 0 ; x < 4 * ct[i].len ; ++x )
+					wide |= ( (unsigned)pw[x] > 65535u ) ;
+				ct[i].packNarrow = wide ? 0 : 1 ;
 				sizes[j] += t4_pack_record_bytes( ct[i] ) ;
 				++counts[j] ;
 			}
@@ -1961,9 +1997,24 @@ int T4_API( streams_pack_contigs )( t4_seqset *const *sets, int n_sets, void *de
 			memset( rec, 0, rb ) ;
 			u32 *h = (u32 *)rec ;
 			h[0] = j ; h[1] = (u32)i ; h[2] = (u32)k.len ; h[3] = (u32)k.nameLen ; h[4] = (u32)k.barcode ; h[5] = (u32)k.numRead ; h[6] = (u32)rb ;
+			h[7] = k.packNarrow ? 1u : 0u ;
 			memcpy( rec + 32, E.A + k.consOff + k.lead, k.len ) ;
-			memcpy( rec + 32 + k.len, E.A + k.pwOff + 16ull * k.lead, 16ull * k.len ) ;
-			memcpy( rec + 32 + 17ull * k.len, E.A + k.nameOff, k.nameLen ) ;
+			if ( k.packNarrow )
+			{
+				const int *pw = (const int *)( E.A + k.pwOff + 16ull * k.lead ) ;
+				unsigned char *d = (unsigned char *)rec + 32 + k.len ;
+				for ( int x = 0 ; x < 4 * k.len ; ++x )
+				{
+					d[2 * x] = (unsigned char)( (unsigned)pw[x] & 255u ) ;
+					d[2 * x + 1] = (unsigned char)( (unsigned)pw[x] >> 8 ) ;
+				}
+				memcpy( rec + 32 + 9ull * k.len, E.A + k.nameOff, k.nameLen ) ;
+			}
+			else
+			{
+				memcpy( rec + 32 + k.len, E.A + k.pwOff + 16ull * k.lead, 16ull * k.len ) ;
+				memcpy( rec + 32 + 17ull * k.len, E.A + k.nameOff, k.nameLen ) ;
+			}
 			o += rb ;
 		}
 	}

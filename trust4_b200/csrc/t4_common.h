@@ -76,12 +76,17 @@ struct T4Contig            // SeqSet.hpp:19 `_seqWrapper`, novel contigs only (i
 	int barcode ;
 	int numRead ;
 	int flags ;            // T4_CF_*
-	int pad_ ;
+	int packNarrow ;       // scratch of t4_streams_pack_contigs: 1 = every posWeight count of this contig fits 16 bits
 } ;
 #define T4_CF_NOINDEX 1    /* seqs[i].index == false: purged by ReleaseFinishedBarcodeSeq (SeqSet.hpp:10849) */
 
-// bytes of one packed contig record (t4_streams_pack_contigs)
-T4_HD inline u64 t4_pack_record_bytes( const T4Contig &k ) { return ( 32ull + 17ull * k.len + k.nameLen + 15 ) & ~15ull ; }
+// bytes of one packed contig record (t4_streams_pack_contigs): 32-byte header + consensus + posWeight columns as 4 x u16
+// (when all counts of the contig fit; the usual case, halves the merge exchange and the contig D2H) or 4 x i32 + name,
+// padded to 16 bytes
+T4_HD inline u64 t4_pack_record_bytes( const T4Contig &k )
+{
+	return ( 32ull + ( k.packNarrow ? 9ull : 17ull ) * k.len + k.nameLen + 15 ) & ~15ull ;
+}
 
 struct T4Ovl               // SeqSet.hpp:76 `_overlap`
 {

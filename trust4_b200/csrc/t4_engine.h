@@ -715,7 +715,7 @@ T4_D inline int s_new_contig( T4Ctx &cx, int len )
 	c->barcode = -1 ;
 	c->numRead = 0 ;
 	c->flags = 0 ;
-	c->pad_ = 0 ;
+	c->packNarrow = 0 ;
 	++st->nSeqs ;
 	return idx ;
 }

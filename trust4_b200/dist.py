@@ -19,21 +19,26 @@ def pack_contigs(lib, sets, device=None):
 
 
 def allgather_contigs(buf):
-    """All ranks receive the list of per-rank packed buffers, in rank order (variable sizes: sizes first, then a
-    padded all_gather -- the 'allgather of sizes + offset gather' of SURVEY.md section 5)."""
+    """All ranks receive the per-rank packed buffers, in rank order: the sizes first (one small all-gather), then ONE
+    all_gather_into_tensor on a flat buffer padded to the largest size (NCCL: a single collective, no per-rank copies)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
     n = torch.tensor([buf.numel()], dtype=torch.int64, device=buf.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
+    sizes_t = torch.zeros(world, dtype=torch.int64, device=buf.device)
+    dist.all_gather_into_tensor(sizes_t, n)
+    sizes = [int(x) for x in sizes_t.tolist()]
     mx = max(max(sizes), 16)
-    padded = torch.zeros(mx, dtype=torch.uint8, device=buf.device)
-    padded[: buf.numel()] = buf
-    out = [torch.empty(mx, dtype=torch.uint8, device=buf.device) for _ in range(world)]
-    dist.all_gather(out, padded)
-    return [o[:s] for o, s in zip(out, sizes)]
+    mx = (mx + 15) & ~15
+    base = buf._base if getattr(buf, "_base", None) is not None else buf
+    if base.numel() >= mx and buf.storage_offset() == 0 and base.dim() == 1:
+        padded = base[:mx]                 # the pack buffer has slack: bytes past this rank's size are never read back
+    else:
+        padded = torch.zeros(mx, dtype=torch.uint8, device=buf.device)
+        padded[: buf.numel()] = buf
+    out = torch.empty(world * mx, dtype=torch.uint8, device=buf.device)
+    dist.all_gather_into_tensor(out, padded)
+    return [out[r * mx: r * mx + sizes[r]] for r in range(world)]
 
 
 def unpack_contigs(buf):
@@ -46,8 +51,13 @@ def unpack_contigs(buf):
         st, slot, ln, nl, rb = int(h[0]), int(h[1]), int(h[2]), int(h[3]), int(h[6])
         bc, nr = int(h[4:6].view(np.int32)[0]), int(h[4:6].view(np.int32)[1])
         cons = a[o + 32:o + 32 + ln].tobytes().decode()
-        pw = a[o + 32 + ln:o + 32 + 17 * ln].copy().view(np.int32).reshape(ln, 4)
-        name = a[o + 32 + 17 * ln:o + 32 + 17 * ln + nl].tobytes().decode()
+        if int(h[7]) & 1:       # posWeight counts stored as u16
+            pw = a[o + 32 + ln:o + 32 + 9 * ln].copy().view(np.uint16).reshape(ln, 4).astype(np.int32)
+            na = o + 32 + 9 * ln
+        else:
+            pw = a[o + 32 + ln:o + 32 + 17 * ln].copy().view(np.int32).reshape(ln, 4)
+            na = o + 32 + 17 * ln
+        name = a[na:na + nl].tobytes().decode()
         out.append(dict(set=st, slot=slot, consensus=cons, pos_weight=pw, name=name, barcode=bc, num_read=nr))
         o += rb
     return out
