@@ -1772,9 +1772,9 @@ int T4_API( streams_get_hits )( t4_seqset *const *sets, int n_sets, t4_workload 
 		int perSm = 0, sms = 0 ;
 		const char *pv = getenv( "T4_PROBE_VARIANT" ) ;
 		// variants: resident warps per SM the registers are bounded for x directory probes in flight per lane (T4_PROBE_VARIANT=<warps><g>)
-		const int var = pv ? atoi( pv ) : 202 ;
+		const int var = pv ? atoi( pv ) : 242 ;
 		probeKernel = var == 163 ? t4_probe_kernel<16, 3> : var == 203 ? t4_probe_kernel<20, 3> : var == 242 ? t4_probe_kernel<24, 2>
-			: var == 243 ? t4_probe_kernel<24, 3> : var == 162 ? t4_probe_kernel<16, 2> : t4_probe_kernel<20, 2> ;
+			: var == 243 ? t4_probe_kernel<24, 3> : var == 162 ? t4_probe_kernel<16, 2> : var == 202 ? t4_probe_kernel<20, 2> : t4_probe_kernel<24, 2> ;
 		CK( cudaFuncSetAttribute( probeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probeSmem ) ) ;
 		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, probeKernel, 32 * T4P_WARPS, probeSmem ) ) ;
 		CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ) ;
