@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrust4_b200.so")
+LIB_PATH = os.environ.get("T4_LIB_PATH") or os.path.join(_HERE, "libtrust4_b200.so")     # T4_LIB_PATH: build variants for experiments
 
 T4_E_BASE = -16
 T4_E_CUDA, T4_E_NOMEM, T4_E_INVAL, T4_E_UNSUPPORTED, T4_E_NODEVICE, T4_E_INTERNAL = -17, -18, -19, -20, -21, -22
