@@ -21,7 +21,15 @@ typedef int64_t i64;
 #define T4_HD __host__ __device__
 #define T4_D __device__
 #define T4_SYNC() __syncthreads()
+// Large collective routines with several call sites are real functions in the product build: inlined everywhere the
+// stream kernel was 70 k SASS instructions (1.1 MB) and 18 % of its stall cycles were instruction fetch.
+#ifdef T4_INLINE_ALL
+#define T4_BIG inline
 #else
+#define T4_BIG __noinline__
+#endif
+#else
+#define T4_BIG inline
 #define T4_CUDA 0
 #define T4_HD
 #define T4_D

@@ -572,7 +572,7 @@ T4_D inline void t4_list_append( T4Ctx &cx, T4Dir *d, u64 v )
 // mode BUILD:  BuildIndexFromRead( s, len, id, barcode, shift = arg )
 // mode REMOVE: RemoveIndexFromRead( s, len, id, barcode, offset = arg )
 // mode UPDATE: UpdateIndexFromRead( s, len, barcode, shift = arg, oldId, id )
-T4_D inline void c_index_op( T4Ctx &cx, const char *s, int len, int mode, int id, int barcode, int arg, int oldId )
+T4_D T4_BIG void c_index_op( T4Ctx &cx, const char *s, int len, int mode, int id, int barcode, int arg, int oldId )
 {
 	T4Stream *st = cx.st ;
 	T4Smem *sm = cx.sm ;
@@ -1920,7 +1920,7 @@ T4_D inline void c_score_all_warp( T4Ctx &cx, T4Ovl *ovl, int overlapCnt, const 
 // SeqSet::GetOverlapsFromRead (SeqSet.hpp:1508-2124), readType 0, novel contigs
 // ---------------------------------------------------------------------------
 // Returns the number of overlaps left in ovl[] (-1 when the read is shorter than k).
-T4_D inline int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, bool skipRepeats )
+T4_D T4_BIG int c_get_overlaps( T4Ctx &cx, int len, int strand, int barcode, bool skipRepeats )
 {
 	T4Stream *st = cx.st ;
 	T4Smem *sm = cx.sm ;
@@ -2793,7 +2793,7 @@ T4_D inline void s_update_consensus( T4Ctx &cx, int seqIdx, bool updateIndex )
 
 // SeqSet::UpdateAllConsensus (SeqSet.hpp:4525).  Collective: contigs are scanned in parallel, the rare
 // contigs that change are fixed up serially in slot order.
-T4_D inline void c_update_all_consensus( T4Ctx &cx )
+T4_D T4_BIG void c_update_all_consensus( T4Ctx &cx )
 {
 	T4Stream *st = cx.st ;
 	T4_SYNC() ;
@@ -2901,7 +2901,7 @@ T4_D inline int s_contig_shallow( T4Ctx &cx, int idx, int minCov )
 // ReleaseSeq), the others leave the index, get a final UpdateConsensus( i, false ) and, when their coverage is flat,
 // numRead = that coverage.  The reference then compresses / frees posWeight -- storage only: Output prints the same
 // numbers either way (SeqSet.hpp:10956-10992), so the columns stay as they are here.
-T4_D inline void c_release_barcode( T4Ctx &cx, int barcode, int contigMinCov )
+T4_D T4_BIG void c_release_barcode( T4Ctx &cx, int barcode, int contigMinCov )
 {
 	T4Stream *st = cx.st ;
 	T4Smem *sm = cx.sm ;
@@ -3010,7 +3010,7 @@ T4_D inline u32 t4_bc_slot( const T4BcTable &t, int barcode, bool claim )
 
 // SeqSet::Clean(false) + ChangeKmerLength (SeqSet.hpp:4591-4629): compact the slots, rebuild the index.
 // nomatchGapLimit is computed on the host (pow/log) and passed in.
-T4_D inline void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
+T4_D T4_BIG void c_change_kmer_length( T4Ctx &cx, int kl, int nomatchGapLimit )
 {
 	T4Stream *st = cx.st ;
 	T4_SYNC() ;
@@ -3140,7 +3140,7 @@ T4_D inline void s_make_exact( T4Ctx &cx, const char *r, int len, double factor,
 // ---------------------------------------------------------------------------
 // SeqSet::AddRead (SeqSet.hpp:3426-4473), novel-contig set.  Collective; reads cx.sm->read / rc.
 // ---------------------------------------------------------------------------
-T4_D inline int c_add_read( T4Ctx &cx, int len, const char *geneName, int &strand, int barcode, int minKmerCount,
+T4_D T4_BIG int c_add_read( T4Ctx &cx, int len, const char *geneName, int &strand, int barcode, int minKmerCount,
 	bool repetitiveData, double similarityThreshold )
 {
 	T4Stream *st = cx.st ;
