@@ -577,6 +577,30 @@ def check_repseq(lib, ref, seed=61, n_reads=4000, n_shards=3):
     assert int((ret >= 0).sum()) > n_reads // 2
 
 
+def check_dup_runs(lib, ref, seed=71):
+    """Long runs of duplicate records (amplicon data: every read of a clonotype is the same string): the device applies a
+    run of RepeatAddRead calls in one pass; the periodic UpdateAllConsensus (here every 37 assembled reads) and a pending
+    k change must still see exactly the reference's state."""
+    lib.check(lib.reset())
+    cl = synth.make_clones(7, seed, chains=("TRB",))
+    rd = synth.sample_amplicon(cl, 6000, 100, seed, alpha=0.7, sub_rate=0.001)
+    w = synth.build_workload(cl, rd, repseq=True)
+    assert (w.descs["flags"] & synth.RD_DUP).mean() > 0.8
+    for every, chk in ((37, 4096), (10000, 3), (5000, 4096)):
+        lib.check(lib.reset())
+        cfg = synth.run_cfg(repetitive=1, change_k_threshold=chk, update_consensus_every=every, first_read_len=100)
+        g = api.SeqSet(9, lib)
+        r = ref.RefSeqSet(9)
+        _, gret, gstr, gres = g.run_descs(cfg, w.descs, w.pool, w.names)
+        _, rret, rstr, rres = r.run_descs(cfg, w.descs, w.pool, w.names)
+        assert (gret == rret).all() and (gstr == rstr).all() and (gres == rres).all(), (every, chk)
+        assert g.output() == r.output(), (every, chk)
+        assert g.index_checksum() == r.index_checksum() and g.kmer_length() == r.kmer_length()
+        for i in range(g.size()):
+            c = g.get_contig(i)
+            assert (c is None) == (r.num_read(i) < 0) and (c is None or c["num_read"] == r.num_read(i))
+
+
 def check_input_novel_fa(lib, ref, tmp_path):
     """SeqSet::InputNovelFa (SeqSet.hpp:2986, --debug-ns)."""
     lib.check(lib.reset())

@@ -55,6 +55,10 @@ def test_emu_repseq_streams(emu_lib, ref):
     pc.check_repseq(emu_lib, ref)
 
 
+def test_emu_dup_runs(emu_lib, ref):
+    pc.check_dup_runs(emu_lib, ref)
+
+
 def test_emu_input_novel_fa(emu_lib, ref, tmp_path):
     pc.check_input_novel_fa(emu_lib, ref, tmp_path)
 

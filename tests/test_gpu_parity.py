@@ -121,3 +121,8 @@ def test_gpu_single_cell_streams(gpu_lib, ref):
 def test_gpu_repseq_streams(gpu_lib, ref):
     """configs[4] in small: repetitiveData = true (allowTotalSkip pass, mismatch factor 2.0), pseudo barcodes."""
     pc.check_repseq(gpu_lib, ref, n_reads=12000, n_shards=4)
+
+
+def test_gpu_dup_runs(gpu_lib, ref):
+    """Run-length RepeatAddRead in the device loop vs the reference, with consensus updates and k changes inside dup runs."""
+    pc.check_dup_runs(gpu_lib, ref)

@@ -3125,6 +3125,61 @@ T4_D inline int c_repeat_add_read( T4Ctx &cx, int len )
 	return st->prevSeqIdx ;
 }
 
+// L consecutive RepeatAddRead calls of the same read in one pass: the call only increments counters (SeqSet.hpp:4495-4501),
+// so L calls add L.  The driver loop uses it for runs of duplicate records (c_run_loop).
+T4_D inline int c_repeat_add_read_n( T4Ctx &cx, int len, int L )
+{
+	T4Stream *st = cx.st ;
+	if ( st->prevSeqIdx < 0 )
+		return st->prevSeqIdx ;
+	const char *r = ( st->prevStrand == -1 ) ? cx.sm->rc : cx.sm->read ;
+	T4Contig *seq = t4_seq( cx, st->prevSeqIdx ) ;
+	int *pw = t4_pw( cx, seq ) ;
+	for ( int i = st->prevReadStart + cx.tid ; i <= st->prevReadEnd ; i += cx.nt )
+	{
+		if ( r[i] == 'N' )
+			continue ;
+		pw[4 * ( i + st->prevSeqStart ) + t4_nuc( r[i] )] += L ;
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+		seq->numRead += L ;
+	T4_SYNC() ;
+	return st->prevSeqIdx ;
+}
+
+// Number of consecutive records from i on that carry T4_RD_DUP (record i included), at most cap.  Collective.
+T4_D inline int c_dup_run_len( T4Ctx &cx, const t4_read_desc *descs, int i, int n, int cap )
+{
+	T4Smem *sm = cx.sm ;
+	const int lim = ( n - i < cap ) ? n - i : cap ;
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+		sm->bi[0] = lim ;
+	T4_SYNC() ;
+	for ( int base = 0 ; base < lim ; base += cx.nt )
+	{
+		const int t = base + cx.tid ;
+		if ( t < lim && !( descs[i + t].flags & T4_RD_DUP ) )
+		{
+#if T4_CUDA
+			atomicMin( &sm->bi[0], t ) ;
+#else
+			if ( t < sm->bi[0] )
+				sm->bi[0] = t ;
+#endif
+		}
+		T4_SYNC() ;
+		const int v = sm->bi[0] ;
+		T4_SYNC() ;
+		if ( v < base + cx.nt )
+			break ;
+	}
+	const int r = sm->bi[0] ;
+	T4_SYNC() ;
+	return r ;
+}
+
 // exact ExtendOverlap of overlap i on demand (thread 0 of the decision loop)
 T4_D inline void s_make_exact( T4Ctx &cx, const char *r, int len, double factor, const T4Ovl *overlaps, T4Ovl *pre, int i )
 {
@@ -4192,10 +4247,12 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 	int indexKmerLength = st->kmerLength ;
 	int changeKmerLengthThreshold = cfg.change_k_threshold ;
 	int rescueCnt = 0 ;
+	int dupCredit = 0 ; // upcoming duplicate records whose RepeatAddRead increments are already applied
 	for ( int i = 0 ; i < n && !st->error ; ++i )
 	{
 		const t4_read_desc d = descs[i] ;
 		int addRet = -1 ;
+		const bool credited = ( d.flags & T4_RD_DUP ) && dupCredit > 0 ;
 		if ( d.len > T4_DEV_MAX_READ || d.len < 0 )
 		{
 			if ( cx.tid == 0 )
@@ -4203,7 +4260,9 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			T4_SYNC() ;
 			break ;
 		}
-		if ( packed )
+		if ( credited )
+			; // same read string as the record before: nothing to load, nothing to add
+		else if ( packed )
 			c_load_read_packed( cx, packed + (u64)i * packStride, d.len ) ;
 		else
 			c_load_read( cx, pool + d.seq_off, d.len ) ;
@@ -4270,7 +4329,35 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			if ( prevAddRet != -1 && prevAddRet != -3 )
 			{
 				ev |= T4_EV_REPEAT ;
-				addRet = c_repeat_add_read( cx, d.len ) ;
+				if ( credited )
+				{
+					addRet = st->prevSeqIdx ;
+					--dupCredit ;
+				}
+				else
+				{
+					// A run of L duplicate records is L RepeatAddRead calls on unchanged prevAddInfo: apply them in one pass.
+					// L stops where the loop could act between two of them: at the record that makes assembledReadCnt a
+					// multiple of update_consensus_every (UpdateAllConsensus must see exactly the counts of the records so
+					// far, main.cpp:1862), and it is 1 when a k change is pending (ChangeKmerLength resets prevAddInfo).
+					int L = 1 ;
+					const bool kPending = changeKmerLengthThreshold > 0 && st->nSeqs > changeKmerLengthThreshold && indexKmerLength < 16
+						&& !cfg.has_barcode ;
+					if ( st->prevSeqIdx >= 0 && !kPending )
+					{
+						L = c_dup_run_len( cx, descs, i, n, 4096 ) ;
+						if ( cfg.update_consensus_every > 0 && !cfg.has_barcode )
+						{
+							const int room = cfg.update_consensus_every - ( assembledReadCnt % cfg.update_consensus_every ) ;
+							if ( L > room )
+								L = room ;
+						}
+						if ( L < 1 )
+							L = 1 ;
+					}
+					addRet = c_repeat_add_read_n( cx, d.len, L ) ;
+					dupCredit = L - 1 ;
+				}
 			}
 			else if ( prevAddRet == -3 )
 				addRet = -3 ;
