@@ -4183,6 +4183,38 @@ T4_D inline double t4_rescue_threshold( int minCnt )
 	return t ;
 }
 
+// main.cpp:1782-1843: a read that was added and annotates well marks its mate (and the mate's identical copies) as a
+// good candidate for a motif-anchored new contig.  Thread 0.
+T4_D inline void s_mate_hint( const t4_read_desc *descs, int n, int i, int mateIdx, u32 flags, int finalStrand, int8_t *goodCandidate,
+	int32_t *info )
+{
+	bool good = false ;
+	if ( finalStrand == 1 && ( flags & T4_RD_GOOD_PLUS ) )
+		good = true ;
+	if ( finalStrand == -1 && ( flags & T4_RD_GOOD_MINUS ) )
+		good = true ;
+	if ( good && !goodCandidate[mateIdx] )
+	{
+		int tagm = mateIdx ;
+		const t4_read_desc &md = descs[tagm] ;
+		for ( int j = tagm - 1 ; j > 0 && j >= md.eq_lo ; --j )
+		{
+			goodCandidate[j] = 1 ;
+			info[j] = i ;
+		}
+		for ( int j = tagm + 1 ; j < n && j < md.eq_hi ; ++j )
+		{
+			goodCandidate[j] = 1 ;
+			info[j] = i ;
+		}
+	}
+	if ( good )
+	{
+		goodCandidate[mateIdx] = 1 ;
+		info[mateIdx] = i ;
+	}
+}
+
 T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 {
 	T4Stream *st = cx.st ;
@@ -4253,6 +4285,7 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 		const t4_read_desc d = descs[i] ;
 		int addRet = -1 ;
 		const bool credited = ( d.flags & T4_RD_DUP ) && dupCredit > 0 ;
+		int batchExtra = 0 ;
 		if ( d.len > T4_DEV_MAX_READ || d.len < 0 )
 		{
 			if ( cx.tid == 0 )
@@ -4356,7 +4389,10 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 							L = 1 ;
 					}
 					addRet = c_repeat_add_read_n( cx, d.len, L ) ;
-					dupCredit = L - 1 ;
+					if ( releaseBarcodes )
+						dupCredit = L - 1 ; // the purge bookkeeping stays per record
+					else
+						batchExtra = L - 1 ; // the other L - 1 records are closed right below, without a loop iteration each
 				}
 			}
 			else if ( prevAddRet == -3 )
@@ -4371,39 +4407,38 @@ T4_D inline void c_run_loop( T4Ctx &cx, T4Op *op, const int *gapLimitTable )
 			if ( addRet == -2 )
 				rescueList[rescueCnt] = i ;
 			else if ( addRet >= 0 && d.mate_idx > i )
-			{
-				bool good = false ;
-				if ( finalStrand == 1 && ( d.flags & T4_RD_GOOD_PLUS ) )
-					good = true ;
-				if ( finalStrand == -1 && ( d.flags & T4_RD_GOOD_MINUS ) )
-					good = true ;
-				if ( good && !goodCandidate[d.mate_idx] )
-				{
-					int tagm = d.mate_idx ;
-					const t4_read_desc &md = descs[tagm] ;
-					for ( int j = tagm - 1 ; j > 0 && j >= md.eq_lo ; --j )
-					{
-						goodCandidate[j] = 1 ;
-						info[j] = i ;
-					}
-					for ( int j = tagm + 1 ; j < n && j < md.eq_hi ; ++j )
-					{
-						goodCandidate[j] = 1 ;
-						info[j] = i ;
-					}
-				}
-				if ( good )
-				{
-					goodCandidate[d.mate_idx] = 1 ;
-					info[d.mate_idx] = i ;
-				}
-			}
+				s_mate_hint( descs, n, i, d.mate_idx, d.flags, finalStrand, goodCandidate, info ) ;
 		}
 		if ( addRet == -2 )
 			++rescueCnt ;
 		else if ( addRet >= 0 )
 			++assembledReadCnt ;
 		T4_SYNC() ;
+		if ( batchExtra > 0 )
+		{
+			// records i + 1 .. i + batchExtra: duplicates whose RepeatAddRead is already applied (addRet >= 0, same strand)
+			for ( int t = cx.tid ; t < batchExtra ; t += cx.nt )
+			{
+				retCodes[i + 1 + t] = addRet ;
+				strands[i + 1 + t] = (int8_t)finalStrand ;
+				if ( events )
+					events[i + 1 + t] = (uint8_t)T4_EV_REPEAT ;
+			}
+			if ( cx.tid == 0 )
+				for ( int t = 0 ; t < batchExtra ; ++t )
+				{
+					const int idx = i + 1 + t ;
+					const int mi = descs[idx].mate_idx ;
+					if ( mi > idx )
+						s_mate_hint( descs, n, idx, mi, descs[idx].flags, finalStrand, goodCandidate, info ) ;
+				}
+			assembledReadCnt += batchExtra ;
+			if ( events && cx.tid == 0 )
+				events[i] = (uint8_t)ev ; // the head record's own byte (the loop end writes index i + batchExtra)
+			i += batchExtra ;
+			ev = T4_EV_REPEAT ;
+			T4_SYNC() ;
+		}
 		// main.cpp:1846-1859 (inside `else if ( addRet >= 0 )`): a barcode is finished when as many of its reads were
 		// assembled as it has reads
 		if ( releaseBarcodes && addRet >= 0 && d.barcode != -1 )
