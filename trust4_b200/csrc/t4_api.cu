@@ -1527,7 +1527,9 @@ static t4_workload *workload_upload_impl( const t4_read_desc *descs, int64_t n, 
 		ok = cudaMemsetAsync( dOdd, 0, 4 ) == cudaSuccess ;
 		if ( ok )
 		{
-			t4_pack_reads_kernel<<<(unsigned)n, 32>>>( w->descs, n, w->pool, packStride, w->packed, dOdd ) ;
+			const int wMax = (int)t4_pack_w( maxLen ) ;
+			const i64 threads = (i64)n * wMax ;
+			t4_pack_reads_kernel<<<(unsigned)( ( threads + 255 ) / 256 ), 256>>>( w->descs, n, w->pool, packStride, wMax, w->packed, dOdd ) ;
 			ok = cudaGetLastError() == cudaSuccess && cudaMemcpy( &odd, dOdd, 4, cudaMemcpyDeviceToHost ) == cudaSuccess ;
 		}
 #else
