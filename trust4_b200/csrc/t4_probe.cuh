@@ -26,7 +26,7 @@
                                     // (with 8 warps per CTA 18 % of all issued instructions recomputed `smem + warp * sizeof`)
 #define T4P_PMAX 9                  // positions per lane and tile
 #define T4P_TILE ( 32 * T4P_PMAX )  // positions (both strand passes) per tile: a 150 bp read at k = 9 has 284
-#define T4P_STG 512                 // TMA staging tile per warp, postings (4 KB)
+#define T4P_STG 448                 // TMA staging tile per warp, postings (3.5 KB: 24 one-warp CTAs of 8.4 KB + 1 KB reserved fit an SM)
 #define T4P_SHORT 4                 // a list of <= 4 postings is one 32-byte sector
 #define T4P_TMA_MAX 256             // longer lists stream through 128-bit loads instead of the staging tile
 #define T4P_NONE 0xffffffffu
