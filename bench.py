@@ -57,6 +57,9 @@ def parse(argv=None):
     ap.add_argument("--barcodes", type=int, default=int(os.environ.get("T4_BENCH_BARCODES", 1000)), help="config 3: cells per GPU (configs[3] full size: 6250)")
     ap.add_argument("--reads-per-barcode", type=int, default=2000)
     ap.add_argument("--reads", type=int, default=int(os.environ.get("T4_BENCH_READS", 2000000)), help="config 4: reads per GPU (configs[4] full size: 6250000)")
+    ap.add_argument("--shard-by", default="rank", choices=["rank", "gene"],
+                    help="rank: contiguous blocks of the sorted read list (SURVEY.md 8e); gene: reads grouped by the gene of their rough "
+                         "annotation first (clonotypes stay together: higher contiguity, dearer reads), groups packed by predicted cost")
     ap.add_argument("--no-quality", action="store_true", help="skip the assembly-quality figure (clonotypes spanned by one contig)")
     return ap.parse_args(argv)
 
@@ -100,7 +103,8 @@ def make_workload(args, rank, device):
     cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
     rd = synth.sample_pairs(cl, args.pairs, 150, args.seed * 1000 + rank)   # each rank sequences its own reads
     w = synth.build_workload(cl, rd, device=device)
-    off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance)
+    off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance, group="gene" if args.shard_by == "gene" else "")
+    args.streams = len(off) - 1
     make_workload.truth = (cl, rd)          # kept for the assembly-quality figure (bench/quality.py)
     return w, off, descs
 
@@ -229,7 +233,7 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     cores = os.cpu_count() or 1
-    mode = "dealt round-robin" if args.deal else ("in contiguous blocks of the sorted list, block sizes equalising the predicted cost (abundance model)"
+    mode = "grouped by annotated gene, groups packed by predicted cost" if args.shard_by == "gene" else "dealt round-robin" if args.deal else ("in contiguous blocks of the sorted list, block sizes equalising the predicted cost (abundance model)"
                                                    if args.balance == "cost" else "in contiguous blocks of the sorted list, equal read counts")
     if args.config == 3:
         args.streams = min(args.streams, args.barcodes)

@@ -20,6 +20,10 @@ def test_emu_batch_dealt_shards(emu_lib, ref):
     assert pc.check_batch_vs_ref(emu_lib, ref, 6, 5, nclones=30, npairs=600, deal=True) > 100
 
 
+def test_emu_batch_gene_grouped_shards(emu_lib, ref):
+    assert pc.check_batch_vs_ref(emu_lib, ref, 8, 9, nclones=40, npairs=700, group="gene") > 100
+
+
 def test_emu_stage_parity(emu_lib, ref):
     pc.check_stage_parity(emu_lib, ref, "synth2k", every=131, max_checks=25)
 

@@ -126,3 +126,8 @@ def test_gpu_repseq_streams(gpu_lib, ref):
 def test_gpu_dup_runs(gpu_lib, ref):
     """Run-length RepeatAddRead in the device loop vs the reference, with consensus updates and k changes inside dup runs."""
     pc.check_dup_runs(gpu_lib, ref)
+
+
+def test_gpu_batch_gene_grouped_shards(gpu_lib, ref):
+    """Streams built by grouping reads by annotated gene (bench.py --shard-by gene): per-shard parity as for any other sharding."""
+    assert pc.check_batch_vs_ref(gpu_lib, ref, 8, 9, nclones=40, npairs=700, group="gene") > 100

@@ -62,14 +62,14 @@ def test_kmer_stats_torch_equals_numpy():
 def test_sharding_invariants():
     cl, rd, w = _wl(5)
     n = len(w.descs)
-    for deal, balance in ((False, "reads"), (True, "reads"), (False, "cost")):
-        off, d = synth.shard_workload(w, 7, deal=deal, balance=balance)
-        if balance == "cost":
+    for deal, balance, group in ((False, "reads", ""), (True, "reads", ""), (False, "cost", ""), (False, "cost", "gene")):
+        off, d = synth.shard_workload(w, 7, deal=deal, balance=balance, group=group)
+        if balance == "cost" and not group:
             cost = np.add.reduceat(synth.read_cost(w.descs, w.med_cnt), off[:-1][np.diff(off) > 0])
             assert cost.max() < 2.0 * cost.mean()          # cut by predicted cost, not by read count
         assert off[0] == 0 and off[-1] == n and (np.diff(off) >= 0).all()
         seen = np.zeros(n, dtype=int)
-        for j in range(7):
+        for j in range(len(off) - 1):
             lo, hi = int(off[j]), int(off[j + 1])
             dd = d[lo:hi]
             if hi > lo:

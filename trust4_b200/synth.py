@@ -533,7 +533,50 @@ def read_cost(descs, med_cnt=None) -> np.ndarray:
     return c
 
 
-def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str = "reads", align: str = "run"):
+def _gene_shards(w: Workload, n_shards: int) -> np.ndarray:
+    """group="gene": stream of every record when reads are first grouped by the gene of their rough annotation (the name
+    InputNovelRead would give them, i.e. mostly the V gene) and the groups are then packed into n_shards streams of equal
+    predicted cost: a group dearer than one stream's share is cut into contiguous sub-blocks (at run boundaries), the
+    small ones are bin-packed (largest first into the least loaded stream).  Reads of one clonotype that reach into its V
+    gene then meet in the same SeqSet whatever their abundance rank -- the reference itself shards --repseq data by V gene
+    (pseudo barcodes, main.cpp:1224-1235)."""
+    d = w.descs
+    n = len(d)
+    head = d["eq_lo"].astype(np.int64)
+    key = d["name_id"][head].astype(np.int64)                    # the whole run shares the annotation of its first record
+    cost = read_cost(d, w.med_cnt)
+    keys, inv = np.unique(key, return_inverse=True)
+    gcost = np.bincount(inv, weights=cost, minlength=len(keys))
+    target = cost.sum() / max(1, n_shards)
+    shard_of = np.full(n, -1, dtype=np.int64)
+    nxt = 0
+    small = []
+    for g in np.argsort(-gcost):
+        if gcost[g] > 1.25 * target and nxt < n_shards - 1:
+            idx = np.flatnonzero(inv == g)                        # ascending = sorted order
+            k = int(min(np.ceil(gcost[g] / target), n_shards - 1 - nxt)) or 1
+            cum = np.cumsum(cost[idx])
+            cuts = np.searchsorted(cum, cum[-1] * np.arange(1, k) / k)
+            part = np.zeros(len(idx), dtype=np.int64)
+            for c in cuts:
+                c = int(np.searchsorted(idx, head[idx[min(c, len(idx) - 1)]]))   # move back to the start of the run
+                part[c:] += 1
+            _, part = np.unique(part, return_inverse=True)
+            shard_of[idx] = nxt + part
+            nxt += int(part.max()) + 1
+        else:
+            small.append(g)
+    bins = max(1, n_shards - nxt)
+    load = np.zeros(bins)
+    for g in small:                                               # already in descending cost order
+        b = int(np.argmin(load))
+        load[b] += gcost[g]
+        shard_of[inv == g] = nxt + b
+    _, shard_of = np.unique(shard_of, return_inverse=True)        # drop empty streams, keep ids dense
+    return shard_of.astype(np.int64)
+
+
+def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str = "reads", align: str = "run", group: str = ""):
     """Shard the sorted records into n_shards independent streams.  Returns desc_off[n_shards+1]
     and the records in stream order with mate_idx / eq_* made stream-relative (mates in other streams -> -1).
     A run of identical reads is never split (RepeatAddRead semantics survive), and every stream keeps the global
@@ -542,16 +585,22 @@ def shard_workload(w: Workload, n_shards: int, deal: bool = False, balance: str 
     deal=False: contiguous blocks of the sorted list; balance = "reads" (equal read counts) or "cost" (equal predicted
                 cost, read_cost()); align = "run" (never split a run of identical reads) or "barcode" (never split a
                 barcode: 10x mode, barcodes are independent assemblies).
+    group="gene": runs are grouped by the gene of their rough annotation and the groups packed into streams of equal
+                predicted cost (_gene_shards); the number of streams returned may be smaller than n_shards.
     deal=True : runs are dealt round-robin (run r -> stream r mod n_shards).  Every stream then sees a uniform sample
                 of the library instead of one abundance class, which equalises the work per stream (contiguous blocks
                 of low-abundance reads are ~50x more expensive than blocks of duplicates)."""
     n = len(w.descs)
     d = w.descs.copy()
-    if deal:
+    if deal or group == "gene":
         same_prev = (d["flags"] & RD_DUP) != 0
         # a run = maximal range of identical read strings (eq_lo..eq_hi), which contains its DUP records
         run_id = np.cumsum(d["eq_lo"] == np.arange(n)) - 1
-        shard_of = (run_id % n_shards).astype(np.int64)
+        if group == "gene":
+            shard_of = _gene_shards(w, n_shards)
+            n_shards = int(shard_of.max()) + 1 if n else n_shards
+        else:
+            shard_of = (run_id % n_shards).astype(np.int64)
         order = np.argsort(shard_of, kind="stable")
         counts = np.bincount(shard_of, minlength=n_shards)
         off = np.zeros(n_shards + 1, dtype=np.int64)
