@@ -207,6 +207,23 @@ int t4_streams_run(t4_seqset *const *sets, int n_sets, const t4_run_cfg *cfg,
                    const char *const *names, int n_names,
                    int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret);
 
+/* Host-side read sharding (no device work): which of at most n_streams independent SeqSets assembles
+ * which records of the driver's sorted read list (main.cpp:1583 walks sortedReads in this order).  `descs` is
+ * reordered in place into stream order (a stream keeps the sorted order of its records), eq_lo / eq_hi / mate_idx are
+ * rewritten relative to the record's stream (a mate in another stream becomes -1: no hint), desc_off[0..S] receives
+ * the stream boundaries and order[j] the original index of new record j (to map t4_workload_results back).  A run of
+ * identical read strings is never split.  Returns S (1 <= S <= n_streams; empty streams are dropped) or < 0.
+ *   T4_SHARD_RANK    contiguous blocks of the sorted list with equal predicted cost (abundance ranks stay together)
+ *   T4_SHARD_BARCODE the same, and a cut never falls inside a barcode (10x data: barcodes are independent assemblies,
+ *                    main.cpp:1846-1859)
+ *   T4_SHARD_GENE    runs grouped by the gene of their rough annotation (names[name_id] of the run's first record),
+ *                    groups cut / packed into streams of equal predicted cost: a clonotype's reads meet in one SeqSet
+ *                    whatever their abundance (the reference shards --repseq input by V gene too, main.cpp:1224-1235) */
+#define T4_SHARD_RANK 0
+#define T4_SHARD_BARCODE 1
+#define T4_SHARD_GENE 2
+int t4_shard_reads(t4_read_desc *descs, int64_t n_descs, int n_streams, int mode, int64_t *desc_off, int64_t *order);
+
 /* Device-resident variant used by bench.py's `value` leg: the workload is
  * uploaded once (t4_workload_upload), then t4_streams_run_resident() only
  * launches kernels on `cuda_stream` (a cudaStream_t cast to void*, NULL = default). */

@@ -39,6 +39,7 @@
 #define t4_streams_run_resident t4emu_streams_run_resident
 #define t4_workload_results t4emu_workload_results
 #define t4_workload_events t4emu_workload_events
+#define t4_shard_reads t4emu_shard_reads
 #define t4_streams_error t4emu_streams_error
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
@@ -338,28 +339,16 @@ public:
 			if ( d[i].eq_lo == i )
 				hi = i ;
 		}
-		// shards: contiguous, never splitting a run of identical reads nor (with barcodes) a barcode
-		if ( S > n )
-			S = n ;
-		std::vector<int64_t> off( S + 1, 0 ) ;
-		for ( int s = 1 ; s < S ; ++s )
-		{
-			int64_t b = (int64_t)n * s / S ;
-			b = d[b].eq_lo ;
-			if ( hasBarcode )
-				while ( b > 0 && d[b].barcode == d[b - 1].barcode && d[b].barcode != -1 )
-					--b ;
-			off[s] = b > off[s - 1] ? b : off[s - 1] ;
-		}
-		off[S] = n ;
-		for ( int s = 0 ; s < S ; ++s )
-			for ( int64_t i = off[s] ; i < off[s + 1] ; ++i )
-			{
-				int m = d[i].mate_idx ;
-				d[i].mate_idx = ( m >= off[s] && m < off[s + 1] ) ? (int)( m - off[s] ) : -1 ; // mates in other shards give no hint
-				d[i].eq_lo = (int)( ( d[i].eq_lo > off[s] ? d[i].eq_lo : off[s] ) - off[s] ) ;
-				d[i].eq_hi = (int)( ( d[i].eq_hi < off[s + 1] ? d[i].eq_hi : off[s + 1] ) - off[s] ) ;
-			}
+		// streams: T4_SHARD_BY = gene (default without barcodes: reads grouped by annotated gene, so a
+		// clonotype's reads meet in one SeqSet) | rank (contiguous blocks of the sorted list); whole barcodes with --barcode.
+		// Neither splits a run of identical reads; S = 1 is the identity.
+		const char *by = getenv( "T4_SHARD_BY" ) ;
+		int mode = hasBarcode ? T4_SHARD_BARCODE : ( by && !strcmp( by, "rank" ) ) ? T4_SHARD_RANK : T4_SHARD_GENE ;
+		std::vector<int64_t> off( ( S > n ? n : S ) + 1, 0 ), order( n ) ;
+		S = t4_shard_reads( d.data(), n, S, mode, off.data(), order.data() ) ;
+		if ( S < 1 )
+			Die() ;
+		off.resize( S + 1 ) ;
 		if ( S > 1 )
 		{
 			sets.resize( S ) ;
@@ -385,8 +374,18 @@ public:
 			Die() ;
 		Check( t4_streams_run_resident( sets.data(), S, &cfg, w, off.data(), NULL ) ) ;
 		bRet.resize( n ) ; bResc.resize( n ) ; bStrand.resize( n ) ; bEv.resize( n ) ;
-		Check( t4_workload_results( w, bRet.data(), bStrand.data(), bResc.data() ) ) ;
-		Check( t4_workload_events( w, bEv.data() ) ) ;
+		{
+			std::vector<int> ret( n ), resc( n ) ;
+			std::vector<int8_t> str( n ) ;
+			std::vector<uint8_t> ev( n ) ;
+			Check( t4_workload_results( w, ret.data(), str.data(), resc.data() ) ) ;
+			Check( t4_workload_events( w, ev.data() ) ) ;
+			for ( int j = 0 ; j < n ; ++j ) // back to the driver's order: the replay walks sortedReads
+			{
+				const int64_t i = order[j] ;
+				bRet[i] = ret[j] ; bResc[i] = resc[j] ; bStrand[i] = str[j] ; bEv[i] = ev[j] ;
+			}
+		}
 		Check( t4_streams_error( sets.data(), S ) ) ;
 		t4_workload_free( w ) ;
 		rescueOrder.clear() ;

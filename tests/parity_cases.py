@@ -33,12 +33,16 @@ def small_workload(seed, nclones=25, npairs=400, L=150):
     return synth.build_workload(cl, rd)
 
 
-def check_batch_vs_ref(lib, ref, seed, n_shards, nclones=25, npairs=400, cfg=None, deal=False, group=""):
-    """t4_streams_run over read shards == the reference SeqSet driven by the restated loop, per shard."""
+def check_batch_vs_ref(lib, ref, seed, n_shards, nclones=25, npairs=400, cfg=None, deal=False, group="", c_mode=None):
+    """t4_streams_run over read shards == the reference SeqSet driven by the restated loop, per shard.
+    c_mode: shard with the library's t4_shard_reads (what the batch drop-in calls) instead of synth.shard_workload."""
     lib.check(lib.reset())
     w = small_workload(seed, nclones, npairs)
     cfg = cfg if cfg is not None else synth.run_cfg()
-    off, descs = synth.shard_workload(w, n_shards, deal=deal, balance="cost" if group else "reads", group=group)
+    if c_mode is not None:
+        off, descs, _ = api.shard_reads(w.descs, n_shards, c_mode, lib)
+    else:
+        off, descs = synth.shard_workload(w, n_shards, deal=deal, balance="cost" if group else "reads", group=group)
     n_shards = len(off) - 1
     k = 9
     sets = api.SeqSet.create_many(n_shards, k, lib)

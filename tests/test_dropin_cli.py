@@ -111,17 +111,24 @@ def test_batch_emu_barcodes(emu_batch_binary, tmp_path):
 
 def test_batch_emu_sharded_runs(emu_batch_binary, tmp_path):
     """S > 1: read-sharded assembly through the same driver; the output differs from the unsharded run by
-    definition, so only the invariants are checked: it completes, every assembled read is reported once, contigs exist."""
+    definition, so only the invariants are checked: it completes, every assembled read is reported once, contigs exist --
+    for both stream assignments of t4_shard_reads (T4_SHARD_BY=gene, the default, and rank); grouping by gene must not
+    fragment the assembly more than rank blocks do."""
     tmp = str(tmp_path)
     args = write_inputs(tmp, 600, 20, 25)
-    e = dict(os.environ, T4_STREAMS="3")
-    subprocess.run([emu_batch_binary, "-t", "1", "-o", os.path.join(tmp, "s3")] + args, check=True, stdout=subprocess.DEVNULL,
-                   stderr=subprocess.DEVNULL, timeout=900, env=e)
-    raw = open(os.path.join(tmp, "s3_raw.out")).read()
-    names = [l.split()[0] for l in raw.split("\n") if l.startswith(">")]
-    assert len(names) > 5 and len(set(names)) == len(names)          # global slot numbers are unique
-    reads = [l for l in open(os.path.join(tmp, "s3_assembled_reads.fa")) if l.startswith(">")]
-    assert len(reads) > 600 and len(set(reads)) == len(reads)
+    n_contigs = {}
+    for by in ("gene", "rank"):
+        e = dict(os.environ, T4_STREAMS="3", T4_SHARD_BY=by)
+        pre = os.path.join(tmp, "s3" + by)
+        subprocess.run([emu_batch_binary, "-t", "1", "-o", pre] + args, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, timeout=900, env=e)
+        raw = open(pre + "_raw.out").read()
+        names = [l.split()[0] for l in raw.split("\n") if l.startswith(">")]
+        assert len(names) > 5 and len(set(names)) == len(names)          # global slot numbers are unique
+        reads = [l for l in open(pre + "_assembled_reads.fa") if l.startswith(">")]
+        assert len(reads) > 600 and len(set(reads)) == len(reads)
+        n_contigs[by] = len(names)
+    assert n_contigs["gene"] <= n_contigs["rank"], n_contigs
 
 
 def test_dropin_emu_shipped_example(emu_binary, tmp_path):

@@ -30,7 +30,7 @@ EXPORTS = [
     "seqset_output", "seqset_output_mem", "free", "seqset_get_contig", "has_motif",
     "reverse_complement_in_place", "seqset_get_hits", "seqset_get_overlaps", "dp_pos_weight_batch", "dp_hot_path_batch",
     "seqset_add_reads_batch", "streams_run", "workload_upload", "workload_free",
-    "streams_run_resident", "workload_results", "workload_events", "last_counters", "streams_error",
+    "streams_run_resident", "workload_results", "workload_events", "shard_reads", "last_counters", "streams_error",
     "hits_create", "hits_free", "streams_get_hits", "hits_stats", "hits_fetch", "hits_device_buffers",
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
     "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
@@ -97,6 +97,7 @@ class Lib:
         f("streams_run_resident", ci, [C.POINTER(vp), ci, vp, vp, vp, vp])
         f("workload_results", ci, [vp, vp, vp, vp])
         f("workload_events", ci, [vp, vp])
+        f("shard_reads", ci, [vp, C.c_int64, ci, ci, vp, vp])
         f("last_counters", ci, [vp])
         f("hits_create", vp, [C.c_int64, C.c_size_t])
         f("hits_free", None, [vp])
@@ -398,3 +399,19 @@ def streams_get_hits(sets, wl: Workload, desc_off, hits: Hits, allow_total_skip=
     off = np.ascontiguousarray(desc_off, dtype=np.int64)
     hs = (C.c_void_p * len(sets))(*[s.h if isinstance(s, SeqSet) else s for s in sets])
     lib.check(lib.streams_get_hits(hs, len(sets), wl.h, off.ctypes.data, int(allow_total_skip), cuda_stream, hits.h))
+
+
+SHARD_RANK, SHARD_BARCODE, SHARD_GENE = 0, 1, 2
+
+
+def shard_reads(descs, n_streams, mode=SHARD_GENE, lib=None):
+    """t4_shard_reads: (desc_off[S+1], records in stream order, order[new] = old index).  Host-only, no device needed."""
+    lib = lib or default_lib()
+    d = np.ascontiguousarray(descs).copy()
+    n = len(d)
+    off = np.zeros(max(1, min(n_streams, max(n, 1))) + 1, dtype=np.int64)
+    order = np.zeros(max(n, 1), dtype=np.int64)
+    S = lib.shard_reads(d.ctypes.data, n, int(n_streams), int(mode), off.ctypes.data, order.ctypes.data)
+    if S < 0:
+        lib.check(S)
+    return off[:S + 1].copy(), d, order[:n]

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include "t4_probe.cuh"
 #endif
+#include "t4_shard.h"
 
 #ifdef T4_EMU
 #define T4_CAT2( a, b ) a##b
@@ -1907,6 +1908,22 @@ int T4_API( workload_results )( t4_workload *w, int32_t *ret_codes, int8_t *stra
 	if ( strands && ( r = d2h( strands, w->strands, (size_t)w->nDescs ) ) ) return r ;
 	if ( rescue_ret && ( r = d2h( rescue_ret, w->rescue, (size_t)w->nDescs * 4 ) ) ) return r ;
 	return 0 ;
+}
+
+int T4_API( shard_reads )( t4_read_desc *descs, int64_t n_descs, int n_streams, int mode, int64_t *desc_off, int64_t *order )
+{
+	if ( mode != T4_SHARD_RANK && mode != T4_SHARD_BARCODE && mode != T4_SHARD_GENE )
+	{
+		set_err( "t4_shard_reads: unknown mode" ) ;
+		return T4_E_INVAL ;
+	}
+	int S = t4shard::Shard( descs, n_descs, n_streams, mode, desc_off, order ) ;
+	if ( S < 0 )
+	{
+		set_err( "t4_shard_reads: bad arguments or inconsistent eq_lo / eq_hi / mate_idx" ) ;
+		return T4_E_INVAL ;
+	}
+	return S ;
 }
 
 int T4_API( workload_events )( t4_workload *w, uint8_t *events )

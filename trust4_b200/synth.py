@@ -536,8 +536,8 @@ def read_cost(descs, med_cnt=None) -> np.ndarray:
 def _gene_shards(w: Workload, n_shards: int) -> np.ndarray:
     """group="gene": stream of every record when reads are first grouped by the gene of their rough annotation (the name
     InputNovelRead would give them, i.e. mostly the V gene) and the groups are then packed into n_shards streams of equal
-    predicted cost: a group dearer than one stream's share is cut into contiguous sub-blocks (at run boundaries), the
-    small ones are bin-packed (largest first into the least loaded stream).  Reads of one clonotype that reach into its V
+    predicted cost: with t the smallest cap for which everything fits, a group dearer than t is cut into ceil(cost / t)
+    contiguous sub-blocks (at run boundaries), the others are bin-packed (largest first into the least loaded stream).  Reads of one clonotype that reach into its V
     gene then meet in the same SeqSet whatever their abundance rank -- the reference itself shards --repseq data by V gene
     (pseudo barcodes, main.cpp:1224-1235)."""
     d = w.descs
@@ -547,28 +547,48 @@ def _gene_shards(w: Workload, n_shards: int) -> np.ndarray:
     cost = read_cost(d, w.med_cnt)
     keys, inv = np.unique(key, return_inverse=True)
     gcost = np.bincount(inv, weights=cost, minlength=len(keys))
-    target = cost.sum() / max(1, n_shards)
     shard_of = np.full(n, -1, dtype=np.int64)
-    nxt = 0
-    small = []
-    for g in np.argsort(-gcost):
-        if gcost[g] > 1.25 * target and nxt < n_shards - 1:
-            idx = np.flatnonzero(inv == g)                        # ascending = sorted order
-            k = int(min(np.ceil(gcost[g] / target), n_shards - 1 - nxt)) or 1
-            cum = np.cumsum(cost[idx])
-            cuts = np.searchsorted(cum, cum[-1] * np.arange(1, k) / k)
-            part = np.zeros(len(idx), dtype=np.int64)
-            for c in cuts:
-                c = int(np.searchsorted(idx, head[idx[min(c, len(idx) - 1)]]))   # move back to the start of the run
-                part[c:] += 1
-            _, part = np.unique(part, return_inverse=True)
-            shard_of[idx] = nxt + part
-            nxt += int(part.max()) + 1
+
+    def budget(t):
+        """streams needed when no stream may be dearer than t: ceil(cost / t) per big group + the bin-packed rest"""
+        bg = np.flatnonzero(gcost > t)
+        kb = np.ceil(gcost[bg] / t).astype(np.int64)
+        rest = gcost.sum() - gcost[bg].sum()
+        return bg, kb, (max(1, int(np.ceil(1.03 * rest / t))) if len(bg) < len(keys) else 0)
+
+    lo = cost.sum() / max(1, n_shards)                            # the smallest cap t whose budget fits n_shards streams
+    hi = 2.0 * lo + gcost.max() / max(1, n_shards)
+    while True:
+        bg, kb, bins = budget(hi)
+        if kb.sum() + bins <= n_shards:
+            break
+        hi *= 2.0
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        bg, kb, bins = budget(mid)
+        if kb.sum() + bins <= n_shards:
+            hi = mid
         else:
-            small.append(g)
-    bins = max(1, n_shards - nxt)
-    load = np.zeros(bins)
-    for g in small:                                               # already in descending cost order
+            lo = mid
+    big, k_big, bins = budget(hi)
+    order = np.argsort(-gcost[big])
+    big, k_big = big[order], k_big[order]
+    small = np.setdiff1d(np.arange(len(keys)), big)
+    small = small[np.argsort(-gcost[small])]
+    nxt = 0
+    for g, k in zip(big, k_big):
+        idx = np.flatnonzero(inv == g)                            # ascending = sorted order
+        cum = np.cumsum(cost[idx])
+        cuts = np.searchsorted(cum, cum[-1] * np.arange(1, k) / k)
+        part = np.zeros(len(idx), dtype=np.int64)
+        for c in cuts:
+            c = int(np.searchsorted(idx, head[idx[min(c, len(idx) - 1)]]))   # move back to the start of the run
+            part[c:] += 1
+        _, part = np.unique(part, return_inverse=True)
+        shard_of[idx] = nxt + part
+        nxt += int(part.max()) + 1
+    load = np.zeros(max(1, bins))
+    for g in small:                                               # descending cost: largest first into the least loaded stream
         b = int(np.argmin(load))
         load[b] += gcost[g]
         shard_of[inv == g] = nxt + b
