@@ -403,7 +403,7 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 	// (1) compact them, in position order, into a table in shared memory (sw->sb: position index per entry);
 	// (2) rounds of up to 32 entries whose even-rounded lengths fit the tile: lane e owns entry w0 + e and issues its bulk
 	//     copy, all wait on the mbarrier; (3) the staged slots are converted FLAT, 32 per step: every lane finds the list
-	//     of its slot by a binary search over the lanes' staging offsets (5 shuffles), so short lists do not idle lanes.
+	//     of its slot from the list heads inside the step's window (one REDUX.OR + popcount), so short lists do not idle lanes.
 	u32 nLong = 0 ;
 #pragma unroll 1
 	for ( int c = 0 ; c < nChunks ; ++c )
@@ -447,21 +447,17 @@ __device__ __forceinline__ void t4p_emit_tile( const T4ProbeRead &R, T4ProbeWarp
 			so = 0xffffffffu ;                                            // never "<= slot" in the search below
 		t4p_bar_wait( &sw->bar, barPhase ) ;
 		barPhase ^= 1 ;
+		u32 passed = 0 ;                                                // lists that start before the current window
 #pragma unroll 1
 		for ( u32 s0 = 0 ; s0 < slots ; s0 += 32 )
 		{
 			const u32 sl = s0 + lane ;
-			int lo_ = 0, hi_ = nIn - 1 ;                                  // largest entry with so <= sl
-#pragma unroll
-			for ( int it = 0 ; it < 5 ; ++it )
-			{
-				const int mid = ( lo_ + hi_ + 1 ) >> 1 ;
-				const u32 som = __shfl_sync( 0xffffffffu, so, mid ) ;
-				if ( som <= sl )
-					lo_ = mid ;
-				else
-					hi_ = mid - 1 ;
-			}
+			// list of slot sl = the last one starting at or before it: the round's lists are lanes 0 .. nIn-1 in staging
+			// order, so one OR-reduction of "my list starts at window bit b" + a popcount replaces a search
+			const u32 rel = so - s0 ;                                     // so = 0xffffffff (not staged) never lands in the window
+			const u32 heads = __reduce_or_sync( 0xffffffffu, rel < 32u ? 1u << rel : 0u ) ;
+			const int lo_ = (int)( passed + __popc( heads & ( 0xffffffffu >> ( 31 - lane ) ) ) ) - 1 ;
+			passed += __popc( heads ) ;
 			const u32 fn = __shfl_sync( 0xffffffffu, n, lo_ ) ;
 			const u32 fso = __shfl_sync( 0xffffffffu, so, lo_ ) ;
 			const u32 fbo = __shfl_sync( 0xffffffffu, bo, lo_ ) ;
