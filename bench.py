@@ -454,6 +454,7 @@ def main():
                 "algorithmic_bytes": {"probe": b_probe, "chain": b_chain, "commit": b_commit},
                 "per_read": {"lookups": dc[2] / n_reads, "hits": dc[4] / n_reads, "overlaps_scored": dc[6] / n_reads, "gap_dps": dc[7] / n_reads,
                              "extend_dps": dc[1] / n_reads, "overlaps_extended": dc[16] / n_reads},
+                "extend_split": dict(zip(["overhang_bits", "settle", "deferred_dps"], [round(float(x), 4) for x in (dc[17:20] / max(1.0, dc[17:20].sum()))])),
                 "stream_balance": balance, "phase_share": dict(zip(["other", "probe", "hit_sort", "chains", "score", "extend", "decide_commit", "novel_repeat_consensus"],
                                         [round(float(x), 4) for x in (dc[8:16] / max(1.0, dc[8:16].sum()))]))}
 

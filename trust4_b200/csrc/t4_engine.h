@@ -3429,6 +3429,57 @@ T4_D T4_BIG int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		T4_SYNC() ;
 		if ( !easy )
 		{
+#if T4_CUDA && defined( T4_EXT_WARP_DP )
+			// Variant (off): one warp per overlap, the left overhang's DP on lanes 0..15, the right one's on lanes 16..31, both
+			// on the anti-diagonal schedule of w_dp_equal_half (2 n + 12 shuffle steps instead of 13 n cells walked by one
+			// thread).  Parity green, but measured equal to the thread-per-side form below (606.5 vs 609.5 ms per launch on the
+			// bench workload): a step costs two dependent shuffles, a row of the register-resident DP about as much, and the
+			// thread form runs all sides of a read at once instead of four overlaps at a time.
+			{
+				T4Smem *sm = cx.sm ;
+				const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31, half = lane >> 4 ;
+				for ( int i = warp ; i < overlapCnt ; i += nwarps )
+				{
+					const bool dl = sstats[2 * i].ind == -1, dr = sstats[2 * i + 1].ind == -1 ;
+					if ( !dl && !dr )
+						continue ;
+					const T4Ovl o = overlaps[i] ;
+					T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+					const int *pw = t4_pw( cx, seq ) ;
+					const int L = t4_min( o.readStart, o.seqStart ), R = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
+					const char *pl = r + o.readStart - L, *pr = r + o.readEnd + 1 ;
+					if ( dl )
+						w_stage_side( pw + 4 * ( o.seqStart - L ), pl, L, sm->wnib[warp][0], sm->wbits[warp][0], lane ) ;
+					if ( dr )
+						w_stage_side( pw + 4 * ( o.seqEnd + 1 ), pr, R, sm->wnib[warp][1], sm->wbits[warp][1], lane ) ;
+					const int n = half ? ( dr ? R : 0 ) : ( dl ? L : 0 ) ;
+					const bool small = n < 16 * T4_WACT_WORDS ;
+					u32 *actBase = small ? sm->wact[warp][half] : (u32 *)t4_dp_scratch_of( cx, cx.tid & ~15 ).act ;
+					const int actStride = small ? T4_WACT_WORDS : (int)( T4_DP_STRIDE / 4 ) ;
+					signed char *abuf = small ? sm->wal[warp][half] : t4_align_of_thread( cx, cx.tid & ~15 ) ;
+					const int acap = small ? (int)sizeof( sm->wal[0][0] ) : 2 * T4_DEV_MAX_READ + 8 ;
+					int alen = 0 ;
+					w_dp_equal_half( cx, sm->wnib[warp][half], half ? pr : pl, n, abuf, acap, &alen, actBase, actStride ) ;
+					for ( int side = 0 ; side < 2 ; ++side )
+					{
+						if ( !( side ? dr : dl ) )
+							continue ;
+						T4AlignView v ;
+						v.n = __shfl_sync( T4_FULL, alen, 16 * side ) ;
+						v.a = (const signed char *)__shfl_sync( T4_FULL, (unsigned long long)( abuf + acap - 1 ), 16 * side ) - v.n ;
+						v.bits = 0 ;
+						v.dp = 1 ;
+						const T4SideStats ss = w_side_stats( v, side == 0, lane ) ;
+						if ( lane == 0 )
+						{
+							sstats[2 * i + side] = ss ;
+							t4_count( cx, 1, 1 ) ;
+						}
+					}
+					__syncwarp() ;
+				}
+			}
+#else
 			T4DpScratch ds = t4_dp_scratch( cx ) ;
 			T4_PAR_FOR( x, 2 * overlapCnt )
 			{
@@ -3453,6 +3504,7 @@ T4_D T4_BIG int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 					t4_count( cx, 1, 1 ) ;
 				sstats[x] = t4_side_stats( av, !right ) ;
 			}
+#endif
 			T4_SYNC() ;
 			T4_PAR_FOR( i, overlapCnt )
 			{
