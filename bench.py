@@ -101,7 +101,10 @@ def make_workload(args, rank, device):
         cl = synth.make_clones(nclones, args.seed, chains=("TRB",))
         rd = synth.sample_amplicon(cl, args.reads, 100, args.seed * 1000 + rank, alpha=1.0)
         w = synth.build_workload(cl, rd, device=device, repseq=True)
-        off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance)
+        by_gene = (os.environ.get("T4_BENCH_CFG4_SHARD_BY", "rank") == "gene")
+        off, descs = synth.shard_workload(w, args.streams, deal=args.deal, balance=args.balance, group="gene" if by_gene else "")
+        args.streams = len(off) - 1
+        make_workload.truth = (cl, rd)
         return w, off, descs
     nclones = args.clones or max(20, args.pairs // 50)
     cl = synth.make_clones(nclones, args.seed)                    # one repertoire for all ranks
@@ -523,7 +526,7 @@ def main():
     value = world * n_reads * args.steps / (ms * 1e-3)
     e2e = world * n_reads * args.steps / (ms_e2e * 1e-3)
     quality_fig = None
-    if rank == 0 and not args.no_quality and args.config == 1 and getattr(make_workload, "truth", None) is not None:
+    if rank == 0 and not args.no_quality and args.config in (1, 4) and getattr(make_workload, "truth", None) is not None:
         # what the sharding costs in contiguity: clonotypes whose V(D)J core lies inside ONE contig of this rank's output
         try:
             sys.path.insert(0, os.path.join(ROOT, "bench"))
@@ -532,7 +535,10 @@ def main():
             tq = time.perf_counter()
             codes, coff, ncont = quality.contigs_from_packed(pack["host"][: merged["pack_bytes"]].numpy())
             cl_, rd_ = make_workload.truth
-            quality_fig = quality.spanning_fraction(cl_, rd_, codes, coff)
+            if args.config == 4:    # amplicon reads all start at the C primer: the 200 bp window is never covered, so count
+                quality_fig = quality.recovered_fraction(cl_, rd_, codes, coff)     # clonotypes whose junction 24-mer is in a contig
+            else:
+                quality_fig = quality.spanning_fraction(cl_, rd_, codes, coff)
             quality_fig.update(contigs=ncont, contig_bases=int(len(codes)), streams=S, seconds=time.perf_counter() - tq)
         except Exception as ex:
             quality_fig = {"error": str(ex)[:200]}
