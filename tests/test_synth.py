@@ -93,22 +93,14 @@ def test_has_motif_matches_c_abi_host_utility():
         assert bool(flags[i] & synth.RD_MOTIF) == (lib.has_motif(w.read(i).encode(), 1) != 0)
 
 
-def test_gene_streams_budget_and_launch_order(monkeypatch):
-    """_gene_shards: every stream budget is used sensibly (no giant leftover stream), the dearest-first launch order is a
-    pure renumbering of the index-order partition, and gene types follow SeqSet::GetGeneType's reading of name[3]."""
-    assert [synth._gene_type(x) for x in (b"IGHV3-30*01", b"TRBJ2-7*01", b"IGHD3-10*01", b"IGHD", b"IGHG1", b"TRBC2", b"IGKC")] == \
-        ["V", "J", "D", "C", "C", "C", "C"]
+def test_gene_streams_budget():
+    """_gene_shards: the cap search leaves no giant leftover stream, never more than n_shards streams, runs stay whole."""
     cl, rd, w = _wl(9, 150, 5000)
     cost = synth.read_cost(w.descs, w.med_cnt)
     for S in (8, 64, 300):
-        monkeypatch.setenv("T4_STREAM_ORDER", "index")
         a = synth._gene_shards(w, S)
-        monkeypatch.setenv("T4_STREAM_ORDER", "lpt")
-        b = synth._gene_shards(w, S)
-        assert a.max() + 1 <= S and b.max() + 1 == a.max() + 1
-        pairs = np.unique(np.stack([a, b], 1), axis=0)
-        assert len(pairs) == a.max() + 1                       # same partition, streams renumbered
+        assert a.max() + 1 <= S
         c = np.bincount(a, weights=cost)
-        assert c.max() < 2.0 * c.mean() + cost.max() * 40      # the cap search leaves no stream far above the others
+        assert c.max() < 2.0 * c.mean() + cost.max() * 40
         head = w.descs["eq_lo"].astype(np.int64)
-        assert (a == a[head]).all()                            # runs of identical reads stay whole
+        assert (a == a[head]).all()

@@ -533,20 +533,6 @@ def read_cost(descs, med_cnt=None) -> np.ndarray:
     return c
 
 
-GENE_TYPE_COST = {"V": 0.79, "J": 1.33, "C": 0.29}
-
-
-def _gene_type(name) -> str:
-    """V / D / J / C of an IMGT-style gene name (SeqSet::GetGeneType reads name[3], SeqSet.hpp:5076)."""
-    nm = name.decode() if isinstance(name, bytes) else name
-    c = nm[3:4]
-    if c in ("V", "J"):
-        return c
-    if c == "D" and nm[4:5].isdigit():
-        return "D"
-    return "C"
-
-
 def _gene_shards(w: Workload, n_shards: int) -> np.ndarray:
     """group="gene": stream of every record when reads are first grouped by the gene of their rough annotation (the name
     InputNovelRead would give them, i.e. mostly the V gene) and the groups are then packed into n_shards streams of equal
@@ -607,16 +593,6 @@ def _gene_shards(w: Workload, n_shards: int) -> np.ndarray:
         load[b] += gcost[g]
         shard_of[inv == g] = nxt + b
     _, shard_of = np.unique(shard_of, return_inverse=True)        # drop empty streams, keep ids dense
-    if os.environ.get("T4_STREAM_ORDER", "lpt") == "lpt" and len(w.names):
-        # Launch order: CTAs start in stream order and 4096 streams run on 592 resident CTAs, so the dear streams go
-        # first (longest-processing-time-first list scheduling).  The per-record table is blind to what a stream's reads
-        # have in common; measured per-stream cycles say a stream of C-gene anchored reads costs 0.29 of its prediction
-        # (constant regions collapse into few contigs), V-anchored 0.79, J-anchored 1.33 -- used for the order only.
-        fac = np.array([GENE_TYPE_COST.get(_gene_type(nm), 1.0) for nm in w.names] + [1.0])
-        pred = np.bincount(shard_of, weights=cost * fac[key])    # key -1 (no annotation) -> the trailing 1.0
-        rank = np.empty(len(pred), dtype=np.int64)
-        rank[np.argsort(-pred, kind="stable")] = np.arange(len(pred))
-        shard_of = rank[shard_of]
     return shard_of.astype(np.int64)
 
 
