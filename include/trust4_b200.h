@@ -295,6 +295,37 @@ int t4_hits_fetch(t4_hits *h, int64_t record, int32_t *hits, int cap, int *flags
 /* Device pointers of the result for device-side consumers: u64 keys[], u64 hit_off[records], u32 hit_cnt[records]. */
 int t4_hits_device_buffers(t4_hits *h, void **keys, void **hit_off, void **hit_cnt);
 
+/* ---- AssignRead pass over the finished sets (the reference's second largest stage-1 cost) ----------
+ * What the stage-1 driver does after the assembly for paired-end bulk data (main.cpp:2047-2118):
+ *   SeqSet extendedSeq(k); extendedSeq.InputSeqSet(seqSet, false);      SeqSet.hpp:3108  (k = max(17, indexKmerLength))
+ *   extendedSeq.SetNovelSeqSimilarity(0.95);
+ *   for every assembled read, in the driver's order (main pass, then the rescued reads; main.cpp:1779, 1933):
+ *       extendedSeq.AssignRead(read, strand, barcode, assign)           SeqSet.hpp:4632  (threads: AssignReads_Thread, main.cpp:607)
+ *       -- a read whose string equals its predecessor's in that list keeps the predecessor's result (main.cpp:2078-2081)
+ *   extendedSeq.SetNovelSeqSimilarity(0.9); extendedSeq.RecomputePosWeight(assembledReads)   SeqSet.hpp:4705
+ * for every stage-1 set j = 0..n_sets-1 and the records desc_off[j]..desc_off[j+1] of the workload it assembled (the
+ * results of the last t4_streams_run_resident on `w` say which reads were assembled and with which strand).
+ * AssignRead only reads the set, so the reads are spread over `n_workers` CTAs of the whole GPU (0 = one resident wave),
+ * whatever set they belong to.  Asynchronous on cuda_stream; the accessors below synchronise.  NULL on failure. */
+typedef struct t4_assign t4_assign;
+t4_assign *t4_streams_assign_reads(t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off,
+                                   int kmer_length, int n_workers, void *cuda_stream);
+void t4_assign_free(t4_assign *a);
+/* Per RECORD of the workload: assign[8*i] = {seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, 0} and
+ * similarity[i] -- the fields of `struct _overlap` AssignRead returns (SeqSet.hpp:1248-1256).  seqIdx >= 0: slot in the
+ * extended set; -1: AssignRead found no contig (the reference leaves the other fields stale then; here they are 0);
+ * T4_ASSIGN_NOT_LISTED: the read was not assembled and is not part of the pass.  Either pointer may be NULL. */
+#define T4_ASSIGN_NOT_LISTED (-2)
+int t4_assign_results(t4_assign *a, int32_t *assign, double *similarity);
+/* stats[0] reads in the pass, [1] AssignRead calls made (identical neighbours share one), [2] reads assigned to a
+ * contig, [3] worker CTAs used. */
+int t4_assign_stats(t4_assign *a, uint64_t stats[4]);
+/* extendedSeq of set j after RecomputePosWeight (owned by `a`; valid until t4_reset / t4_assign_free): feed it to
+ * t4_seqset_output / t4_seqset_get_contig, or on to the CPU mate-extension code (SeqSet::ExtendSeqFromReads). */
+t4_seqset *t4_assign_extended_set(t4_assign *a, int j);
+/* Device pointers of the two result arrays above, for device-side consumers. */
+int t4_assign_device_buffers(t4_assign *a, void **assign, void **similarity);
+
 #ifdef __cplusplus
 }
 #endif

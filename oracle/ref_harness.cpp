@@ -529,4 +529,82 @@ int t4ref_run_descs( void *h, const t4_run_cfg *cfg, const t4_read_desc *descs, 
 	return assembledReadCnt ;
 }
 
+// ---- AssignRead pass --------------------------------------
+// `SeqSet extendedSeq( k ) ; extendedSeq.InputSeqSet( seqSet, false )` (main.cpp:2047-2048, SeqSet.hpp:3108).
+void *t4ref_input_seqset( void *src, int kmerLength )
+{
+	SeqSet *m = new SeqSet( kmerLength ) ;
+	m->InputSeqSet( *(SeqSet *)src, false ) ;
+	return m ;
+}
+
+// int SeqSet::AssignRead( read, strand, barcode, assign ), SeqSet.hpp:4632.  out[8] = {seqIdx, readStart, readEnd,
+// seqStart, seqEnd, strand, matchCnt, 0} (the fields ExtendOverlap assigns, SeqSet.hpp:1248-1256) and *sim, written
+// only when a contig was found; returns AssignRead's value.
+int t4ref_assign_read( void *h, const char *read, int strand, int barcode, int32_t *out, double *sim )
+{
+	SeqSet *s = (SeqSet *)h ;
+	struct _overlap assign ;
+	memset( &assign, 0, sizeof( assign ) ) ;
+	char *r = strdup( read ) ;
+	int ret = s->AssignRead( r, strand, barcode, assign ) ;
+	free( r ) ;
+	if ( ret >= 0 )
+	{
+		out[0] = assign.seqIdx ; out[1] = assign.readStart ; out[2] = assign.readEnd ; out[3] = assign.seqStart ;
+		out[4] = assign.seqEnd ; out[5] = assign.strand ; out[6] = assign.matchCnt ; out[7] = 0 ;
+		*sim = assign.similarity ;
+	}
+	return ret ;
+}
+
+// The driver's AssignRead pass (main.cpp:2047-2118) over the stage-1 set `h`, restated on read descriptors:
+//   extendedSeq( k ).InputSeqSet( seqSet, false ) ; SetNovelSeqSimilarity( 0.95 ) ;
+//   for the assembled reads in the driver's order (list[], main.cpp:1779, 1933: main pass ascending, then the rescued
+//   ones) AssignRead( read, sortedReads[].strand, barcode ) unless the read string equals its predecessor's in the list
+//   (then the previous result is kept, main.cpp:2078-2081) ; SetNovelSeqSimilarity( 0.9 ) ; RecomputePosWeight.
+// assign[8 * i], sim[i] describe list element i (seqIdx -1: not assigned; the reference leaves the other fields stale
+// then and nothing reads them).  Returns the extended set (t4ref_destroy).
+void *t4ref_assign_pass( void *h, int kmerLength, const t4_read_desc *descs, const char *pool, const int32_t *list, int nList,
+	const int8_t *strands, int recompute, int32_t *assignOut, double *simOut )
+{
+	SeqSet *ext = new SeqSet( kmerLength ) ;
+	ext->InputSeqSet( *(SeqSet *)h, false ) ;
+	ext->SetNovelSeqSimilarity( 0.95 ) ;
+	std::vector<struct _assignRead> reads( nList ) ;
+	struct _overlap assign ;
+	memset( &assign, 0, sizeof( assign ) ) ;
+	assign.seqIdx = -1 ;
+	for ( int i = 0 ; i < nList ; ++i )
+	{
+		const t4_read_desc &d = descs[ list[i] ] ;
+		struct _assignRead &nr = reads[i] ;
+		nr.id = NULL ;
+		nr.read = (char *)malloc( d.len + 1 ) ;
+		memcpy( nr.read, pool + d.seq_off, d.len ) ;
+		nr.read[d.len] = '\0' ;
+		nr.barcode = d.barcode ;
+		nr.umi = -1 ;
+		nr.info = list[i] ;
+		nr.overlap.seqIdx = -1 ;
+		nr.overlap.strand = strands[ list[i] ] ;
+	}
+	for ( int i = 0 ; i < nList ; ++i )
+	{
+		if ( i == 0 || strcmp( reads[i].read, reads[i - 1].read ) )
+			ext->AssignRead( reads[i].read, reads[i].overlap.strand, reads[i].barcode, assign ) ;
+		reads[i].overlap = assign ;
+		int32_t *o = assignOut + 8 * i ;
+		o[0] = assign.seqIdx ; o[1] = assign.readStart ; o[2] = assign.readEnd ; o[3] = assign.seqStart ;
+		o[4] = assign.seqEnd ; o[5] = assign.strand ; o[6] = assign.matchCnt ; o[7] = 0 ;
+		simOut[i] = assign.similarity ;
+	}
+	ext->SetNovelSeqSimilarity( 0.9 ) ;
+	if ( recompute )
+		ext->RecomputePosWeight( reads ) ;
+	for ( int i = 0 ; i < nList ; ++i )
+		free( reads[i].read ) ;
+	return ext ;
+}
+
 } // extern "C"

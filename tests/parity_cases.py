@@ -623,3 +623,68 @@ def check_input_novel_fa(lib, ref, tmp_path):
     assert g.input_novel_fa(str(fa)) == 7
     assert g.output() == r.output() and len(g.output()) > 500
     assert g.index_checksum() == r.index_checksum()
+
+
+def _run_resident(lib, sets, cfg, wl, off):
+    hs = (api.C.c_void_p * len(sets))(*[s.h for s in sets])
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    lib.check(lib.streams_run_resident(hs, len(sets), cfg.ctypes.data, wl.h, off.ctypes.data, None))
+    n = wl.n
+    ret = np.zeros(n, dtype=np.int32)
+    strands = np.zeros(n, dtype=np.int8)
+    resc = np.zeros(n, dtype=np.int32)
+    lib.check(lib.workload_results(wl.h, ret.ctypes.data, strands.ctypes.data, resc.ctypes.data))
+    return ret, strands, resc
+
+
+def check_assign_pass(lib, ref, seed, n_shards, nclones=25, npairs=400, kmer=17, group="", workload=None, cfg=None, n_workers=0,
+                      drop=0.0):
+    """t4_streams_assign_reads against the reference's own pass (main.cpp:2047-2118): for every shard the
+    extended set built by InputSeqSet at k, AssignRead of every assembled read in the driver's order (identical
+    neighbours share a call) with novelSeqSimilarity 0.95, and RecomputePosWeight -- per read the assigned contig,
+    coordinates, strand, matchCnt and the similarity double; per extended set the Output text (consensus + recomputed
+    posWeight) and the index checksum."""
+    lib.check(lib.reset())
+    w = workload if workload is not None else small_workload(seed, nclones, npairs)
+    cfg = cfg if cfg is not None else synth.run_cfg()
+    off, descs = synth.shard_workload(w, n_shards, balance="cost" if group else "reads", group=group)
+    n_shards = len(off) - 1
+    if drop > 0:   # reads the driver's gene-order / constant-gene filters reject (main.cpp:1609-1654): never assembled, never listed
+        descs = descs.copy()
+        rng = np.random.default_rng(seed)
+        descs["flags"] |= np.where(rng.random(len(descs)) < drop, synth.RD_FILTERED, 0).astype(descs["flags"].dtype)
+    sets = api.SeqSet.create_many(n_shards, 9, lib)
+    wl = api.Workload(descs, w.pool, w.names, lib)
+    ret, strands, resc = _run_resident(lib, sets, cfg, wl, off)
+    a = api.Assign(sets, wl, off, kmer, n_workers=n_workers)
+    ga, gs = a.results()
+    st = a.stats()
+    n_listed = n_assigned = n_calls = 0
+    for j in range(n_shards):
+        lo, hi = int(off[j]), int(off[j + 1])
+        r = ref.RefSeqSet(9)
+        d = descs[lo:hi].copy()
+        _, rret, rstr, rresc = r.run_descs(cfg, d, w.pool, w.names)
+        assert (rret == ret[lo:hi]).all() and (rstr == strands[lo:hi]).all() and (rresc == resc[lo:hi]).all(), ("assembly", j)
+        lst = ref.assembled_list(rret, rresc)
+        ext, ra, rs = ref.assign_pass(r, kmer, d, w.pool, lst, rstr)
+        listed = np.zeros(hi - lo, dtype=bool)
+        listed[lst] = True
+        assert (ga[lo:hi][~listed, 0] == api.ASSIGN_NOT_LISTED).all(), ("not listed", j)
+        g = ga[lo:hi][lst]
+        assert (g[:, 0] == ra[:, 0]).all(), ("seqIdx", j, np.flatnonzero(g[:, 0] != ra[:, 0])[:5])
+        ok = ra[:, 0] >= 0
+        assert (g[ok] == ra[ok]).all(), ("overlap", j, np.flatnonzero((g[ok] != ra[ok]).any(axis=1))[:5])
+        assert (gs[lo:hi][lst][ok] == rs[ok]).all(), ("similarity", j)
+        ge = a.extended_set(j)
+        assert ge.kmer_length() == kmer and ge.size() == ext.size()
+        assert ge.output() == ext.output(), ("extended set", j)
+        assert ge.index_checksum() == ext.index_checksum(), ("extended index", j)
+        n_listed += len(lst)
+        n_assigned += int(ok.sum())
+        rd = [bytes(w.pool[int(x["seq_off"]):int(x["seq_off"]) + int(x["len"])]) for x in d[lst]]
+        n_calls += sum(1 for i in range(len(rd)) if i == 0 or rd[i] != rd[i - 1])
+    assert st["reads"] == n_listed and st["assigned"] == n_assigned and st["assign_calls"] == n_calls, (st, n_listed, n_assigned, n_calls)
+    a.close()
+    wl.close()
+    return n_listed, n_assigned

@@ -57,6 +57,12 @@ def lib():
         l.t4ref_release_shallow_contigs.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_input_novel_fa.argtypes = [C.c_void_p, C.c_char_p]
         l.t4ref_num_read.argtypes = [C.c_void_p, C.c_int]
+        l.t4ref_input_seqset.restype = C.c_void_p
+        l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]
+        l.t4ref_assign_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        l.t4ref_assign_pass.restype = C.c_void_p
+        l.t4ref_assign_pass.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -195,6 +201,31 @@ def dp_pos_weight(tw, p):
             break
         e.append(int(v))
     return sc, e
+
+
+def assembled_list(ret, resc):
+    """The driver's assembledReadIdx (main.cpp:1779, 1933): reads added in the main pass, in order, then the rescued ones."""
+    ret = np.asarray(ret)
+    main = np.nonzero(ret >= 0)[0]
+    if resc is None:
+        return main.astype(np.int32)
+    resc = np.asarray(resc)
+    rescued = np.nonzero((resc != np.iinfo(np.int32).min) & (resc >= 0))[0]
+    return np.concatenate([main, rescued]).astype(np.int32)
+
+
+def assign_pass(src, k, descs, pool, lst, strands, recompute=True):
+    """main.cpp:2047-2118 on the reference SeqSet `src`: (extended RefSeqSet, assign int32[n, 8], similarity[n]) per list element."""
+    descs = np.ascontiguousarray(descs)
+    pool = np.ascontiguousarray(pool)
+    lst = np.ascontiguousarray(lst, dtype=np.int32)
+    strands = np.ascontiguousarray(strands, dtype=np.int8)
+    n = len(lst)
+    a = np.zeros((max(1, n), 8), dtype=np.int32)
+    s = np.zeros(max(1, n), dtype=np.float64)
+    h = lib().t4ref_assign_pass(src.h, k, descs.ctypes.data, pool.ctypes.data, lst.ctypes.data, n, strands.ctypes.data,
+                                int(recompute), a.ctypes.data, s.ctypes.data)
+    return RefSeqSet(k, handle=h), a[:n], s[:n]
 
 
 def merge_sets(shards, k=9):

@@ -76,3 +76,23 @@ def test_emu_single_stream_at_scale(emu_lib, ref):
     cfg = synth.run_cfg(change_k_threshold=1500)
     n = pc.check_batch_vs_ref(emu_lib, ref, 43, 1, nclones=3000, npairs=40000, cfg=cfg)
     assert n > 70000
+
+
+@pytest.mark.parametrize("seed,shards,kmer,drop", [(81, 1, 17, 0.0), (82, 4, 17, 0.15), (83, 3, 19, 0.0)])
+def test_emu_assign_pass(emu_lib, ref, seed, shards, kmer, drop):
+    """InputSeqSet + AssignRead of every assembled read + RecomputePosWeight (main.cpp:2047-2118)."""
+    listed, assigned = pc.check_assign_pass(emu_lib, ref, seed, shards, nclones=30, npairs=500, kmer=kmer, drop=drop)
+    assert listed > 500 and assigned > 300
+
+
+def test_emu_assign_pass_noisy_and_duplicates(emu_lib, ref):
+    """Reads AssignRead cannot place (4 % substitutions: several ExtendOverlap attempts per read, some -1 results) and
+    amplicon data where most list neighbours are identical strings and share one AssignRead call."""
+    from trust4_b200 import synth
+    cl = synth.make_clones(60, 92)
+    w = synth.build_workload(cl, synth.sample_pairs(cl, 1200, 150, 92, sub_rate=0.04))
+    listed, assigned = pc.check_assign_pass(emu_lib, ref, 92, 2, workload=w)
+    assert listed - assigned > 50
+    cl = synth.make_clones(9, 95, chains=("TRB",))
+    w = synth.build_workload(cl, synth.sample_amplicon(cl, 5000, 100, 95, alpha=0.7, sub_rate=0.002), repseq=True)
+    pc.check_assign_pass(emu_lib, ref, 95, 2, workload=w, cfg=synth.run_cfg(repetitive=1, first_read_len=100))

@@ -131,3 +131,25 @@ def test_gpu_dup_runs(gpu_lib, ref):
 def test_gpu_batch_gene_grouped_shards(gpu_lib, ref):
     """Streams built by grouping reads by annotated gene (bench.py --shard-by gene): per-shard parity as for any other sharding."""
     assert pc.check_batch_vs_ref(gpu_lib, ref, 8, 9, nclones=40, npairs=700, group="gene") > 100
+
+
+@pytest.mark.parametrize("seed,shards,kmer,drop", [(81, 1, 17, 0.0), (82, 4, 17, 0.15), (83, 40, 19, 0.0)])
+def test_gpu_assign_pass(gpu_lib, ref, seed, shards, kmer, drop):
+    """SURVEY.md 8f-2 on the device (t4_aux_kernel): extended sets by InputSeqSet at k, AssignRead of every assembled read
+    by worker CTAs over the whole GPU, RecomputePosWeight -- assignments (contig, coordinates, strand, matchCnt, similarity
+    double) and the extended sets' Output / index equal to the reference's pass (main.cpp:2047-2118)."""
+    listed, assigned = pc.check_assign_pass(gpu_lib, ref, seed, shards, nclones=60, npairs=2500, kmer=kmer, drop=drop)
+    assert listed > 2000 and assigned > 1500
+
+
+def test_gpu_assign_pass_noisy_and_duplicates(gpu_lib, ref):
+    cl = synth.make_clones(60, 92)
+    w = synth.build_workload(cl, synth.sample_pairs(cl, 1200, 150, 92, sub_rate=0.04))
+    listed, assigned = pc.check_assign_pass(gpu_lib, ref, 92, 2, workload=w)
+    assert listed - assigned > 50
+    cl = synth.make_clones(9, 95, chains=("TRB",))
+    w = synth.build_workload(cl, synth.sample_amplicon(cl, 5000, 100, 95, alpha=0.7, sub_rate=0.002), repseq=True)
+    pc.check_assign_pass(gpu_lib, ref, 95, 2, workload=w, cfg=synth.run_cfg(repetitive=1, first_read_len=100))
+    # fewer workers than sets, and a single worker
+    pc.check_assign_pass(gpu_lib, ref, 84, 6, nclones=30, npairs=500, n_workers=3)
+    pc.check_assign_pass(gpu_lib, ref, 85, 2, nclones=30, npairs=500, n_workers=1)

@@ -34,6 +34,7 @@ EXPORTS = [
     "hits_create", "hits_free", "streams_get_hits", "hits_stats", "hits_fetch", "hits_device_buffers",
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
     "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
+    "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
 ]
 
 
@@ -109,6 +110,12 @@ class Lib:
         f("seqset_index_checksum", C.c_int64, [vp, C.POINTER(C.c_uint64)])
         f("streams_cycles", ci, [C.POINTER(vp), ci, vp])
         f("streams_pack_contigs", ci, [C.POINTER(vp), ci, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64)])
+        f("streams_assign_reads", vp, [C.POINTER(vp), ci, vp, vp, ci, ci, vp])
+        f("assign_free", None, [vp])
+        f("assign_results", ci, [vp, vp, vp])
+        f("assign_stats", ci, [vp, vp])
+        f("assign_extended_set", vp, [vp, ci])
+        f("assign_device_buffers", ci, [vp, C.POINTER(vp), C.POINTER(vp)])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)
@@ -399,6 +406,55 @@ def streams_get_hits(sets, wl: Workload, desc_off, hits: Hits, allow_total_skip=
     off = np.ascontiguousarray(desc_off, dtype=np.int64)
     hs = (C.c_void_p * len(sets))(*[s.h if isinstance(s, SeqSet) else s for s in sets])
     lib.check(lib.streams_get_hits(hs, len(sets), wl.h, off.ctypes.data, int(allow_total_skip), cuda_stream, hits.h))
+
+
+ASSIGN_NOT_LISTED = -2
+
+
+class Assign:
+    """The AssignRead pass of the stage-1 driver over finished sets (t4_streams_assign_reads; main.cpp:2047-2118):
+    extended sets built from the stage-1 sets, AssignRead of every assembled read of the workload, RecomputePosWeight."""
+
+    def __init__(self, sets, wl: Workload, desc_off, kmer_length=17, n_workers=0, cuda_stream=None):
+        self.lib = wl.lib
+        self.n = int(desc_off[len(sets)])
+        off = np.ascontiguousarray(desc_off, dtype=np.int64)
+        hs = (C.c_void_p * len(sets))(*[s.h if isinstance(s, SeqSet) else s for s in sets])
+        self.h = self.lib.streams_assign_reads(hs, len(sets), wl.h, off.ctypes.data, int(kmer_length), int(n_workers), cuda_stream)
+        if not self.h:
+            raise T4Error(T4_E_CUDA, self.lib.err())
+        self.n_sets = len(sets)
+        self.kmer_length = kmer_length
+
+    def close(self):
+        if self.h:
+            self.lib.assign_free(self.h)
+            self.h = None
+
+    def results(self):
+        """(assign int32[n, 8], similarity float64[n]) per record of the workload."""
+        a = np.zeros((max(1, self.n), 8), dtype=np.int32)
+        s = np.zeros(max(1, self.n), dtype=np.float64)
+        self.lib.check(self.lib.assign_results(self.h, a.ctypes.data, s.ctypes.data))
+        return a[:self.n], s[:self.n]
+
+    def stats(self):
+        s = np.zeros(4, dtype=np.uint64)
+        self.lib.check(self.lib.assign_stats(self.h, s.ctypes.data))
+        return dict(reads=int(s[0]), assign_calls=int(s[1]), assigned=int(s[2]), workers=int(s[3]))
+
+    def extended_set(self, j) -> "SeqSet":
+        h = self.lib.assign_extended_set(self.h, j)
+        if not h:
+            raise T4Error(T4_E_INVAL, self.lib.err())
+        return _BorrowedSeqSet(self.kmer_length, self.lib, h)
+
+
+class _BorrowedSeqSet(SeqSet):
+    """A set owned by another object (t4_assign): same calls, never destroyed from here."""
+
+    def close(self):
+        self.h = None
 
 
 SHARD_RANK, SHARD_BARCODE, SHARD_GENE = 0, 1, 2

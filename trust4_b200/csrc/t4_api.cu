@@ -15,6 +15,7 @@
 #include <thread>
 
 #include "t4_engine.h"
+#include "t4_assign.h"
 
 #if T4_CUDA
 #include <cuda_runtime.h>
@@ -64,6 +65,23 @@ __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_stream_kernel( 
 	cx.tid = threadIdx.x ;
 	cx.nt = blockDim.x ;
 	c_run_op( cx, op, gapTable ) ;
+}
+
+// The read-only passes over finished sets (t4_assign.h) are a kernel of their own: they share the engine's collectives
+// but must not weigh on the register allocation of the assembly loop above.
+__global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_aux_kernel( char *A, T4Op *ops )
+{
+	__shared__ T4Smem sm ;
+	T4Op *op = ops + blockIdx.x ;
+	T4Ctx cx ;
+	cx.A = A ;
+	cx.g = (T4Global *)A ;
+	cx.st = (T4Stream *)( A + op->streamOff ) ;
+	cx.sm = &sm ;
+	cx.cap = cx.g->cap ;
+	cx.tid = threadIdx.x ;
+	cx.nt = blockDim.x ;
+	c_run_aux_op( cx, op ) ;
 }
 
 __global__ void t4_init_kernel( char *A, u64 base, T4InitParams ip )
@@ -342,6 +360,30 @@ static int launch_ops( T4Op *dOps, int n, void *stream )
 		cx.tid = 0 ;
 		cx.nt = 1 ;
 		c_run_op( cx, dOps + b, E.gapTable ) ;
+	}
+	delete sm ;
+#endif
+	return 0 ;
+}
+
+static int launch_aux_ops( T4Op *dOps, int n, void *stream )
+{
+#if T4_CUDA
+	t4_aux_kernel<<<n, E.nt, 0, (cudaStream_t)stream>>>( E.A, dOps ) ;
+	CK( cudaGetLastError() ) ;
+#else
+	T4Smem *sm = new T4Smem ;
+	for ( int b = 0 ; b < n ; ++b )
+	{
+		T4Ctx cx ;
+		cx.A = E.A ;
+		cx.g = (T4Global *)E.A ;
+		cx.st = (T4Stream *)( E.A + dOps[b].streamOff ) ;
+		cx.sm = sm ;
+		cx.cap = cx.g->cap ;
+		cx.tid = 0 ;
+		cx.nt = 1 ;
+		c_run_aux_op( cx, dOps + b ) ;
 	}
 	delete sm ;
 #endif
@@ -1897,6 +1939,213 @@ int T4_API( hits_device_buffers )( t4_hits *h, void **keys, void **hit_off, void
 	if ( keys ) *keys = h->keys ;
 	if ( hit_off ) *hit_off = h->hitOff ;
 	if ( hit_cnt ) *hit_cnt = h->hitCnt ;
+	return 0 ;
+}
+
+int T4_API( streams_error )( t4_seqset *const *sets, int n_sets ) ;
+
+// ---- AssignRead pass over frozen sets (t4_assign.h) ------------------------------------------------
+struct t4_assign
+{
+	char *buf ;            // one device allocation: parameter block, op records, result arrays
+	i64 nDescs ;
+	int nSets ;
+	T4AssignParams *dP ;
+	int32_t *dAssign ;
+	double *dSim ;
+	u64 *dCursor ;
+	std::vector<t4_seqset *> ext ;     // the extended sets (extendedSeq of main.cpp:2047), one per stage-1 set
+	std::vector<t4_seqset *> workers ; // scratch-only streams of the ASSIGN launch
+	uint32_t gen ;
+} ;
+
+void T4_API( assign_free )( t4_assign *a )
+{
+	if ( !a )
+		return ;
+	if ( a->buf ) dfree( a->buf ) ;
+	for ( size_t i = 0 ; i < a->ext.size() ; ++i ) delete a->ext[i] ;
+	for ( size_t i = 0 ; i < a->workers.size() ; ++i ) delete a->workers[i] ;
+	delete a ;
+}
+
+t4_assign *T4_API( streams_assign_reads )( t4_seqset *const *sets, int n_sets, t4_workload *w, const int64_t *desc_off, int kmer_length,
+	int n_workers, void *cuda_stream )
+{
+	if ( !w || !sets || !desc_off || n_sets <= 0 )
+	{
+		set_err( "t4_streams_assign_reads: bad argument" ) ;
+		return 0 ;
+	}
+	const i64 n = desc_off[n_sets] ;
+	if ( desc_off[0] != 0 || n > w->nDescs || n >= ( 1ll << 31 ) )
+	{
+		set_err( "t4_streams_assign_reads: desc_off must start at 0 and fit the workload" ) ;
+		return 0 ;
+	}
+	for ( int j = 0 ; j < n_sets ; ++j )
+		if ( check( sets[j] ) || desc_off[j + 1] < desc_off[j] )
+		{
+			set_err( "t4_streams_assign_reads: stale handle or unordered desc_off" ) ;
+			return 0 ;
+		}
+	if ( n_workers <= 0 )
+	{
+#if T4_CUDA
+		int sms = 148 ;
+		cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ;
+		n_workers = sms * T4_MIN_BLOCKS ; // one resident wave of the auxiliary kernel
+#else
+		n_workers = 2 ;
+#endif
+	}
+	t4_assign *a = new t4_assign ;
+	a->buf = 0 ; a->nDescs = n ; a->nSets = n_sets ; a->gen = g_gen ;
+	a->ext.assign( n_sets, (t4_seqset *)0 ) ;
+	a->workers.assign( n_workers, (t4_seqset *)0 ) ;
+	// fresh sets with the constructor's defaults (SeqSet.hpp:2558-2576): the extended sets at the pass's k, the workers' shells
+	if ( seqsets_create_impl( n_sets, kmer_length, 31, 0, a->ext.data() ) || seqsets_create_impl( n_workers, kmer_length, 31, 0, a->workers.data() ) )
+	{
+		T4_API( assign_free )( a ) ;
+		return 0 ;
+	}
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t nn = (size_t)( n > 0 ? n : 1 ) ;
+	size_t o = 0 ;
+	const size_t oP = o ; o += al( sizeof( T4AssignParams ) ) ;
+	const size_t oCur = o ; o += 256 ;
+	const size_t oOpsA = o ; o += al( (size_t)n_sets * sizeof( T4Op ) ) ;
+	const size_t oOpsB = o ; o += al( (size_t)n_workers * sizeof( T4Op ) ) ;
+	const size_t oOpsC = o ; o += al( (size_t)n_sets * sizeof( T4Op ) ) ;
+	const size_t oExt = o ; o += al( (size_t)n_sets * 8 ) ;
+	const size_t oSrc = o ; o += al( (size_t)n_sets * 8 ) ;
+	const size_t oDoff = o ; o += al( (size_t)( n_sets + 1 ) * 8 ) ;
+	const size_t oCnt = o ; o += al( (size_t)n_sets * 4 ) ;
+	const size_t oList = o ; o += al( nn * 4 ) ;
+	const size_t oLead = o ; o += al( nn * 4 ) ;
+	const size_t oSet = o ; o += al( nn * 4 ) ;
+	const size_t oAsg = o ; o += al( nn * 32 ) ;
+	const size_t oSim = o ; o += al( nn * 8 ) ;
+	void *p = 0 ;
+	if ( dmalloc( &p, o ) )
+	{
+		T4_API( assign_free )( a ) ;
+		return 0 ;
+	}
+	a->buf = (char *)p ;
+	a->dP = (T4AssignParams *)( a->buf + oP ) ;
+	a->dAssign = (int32_t *)( a->buf + oAsg ) ;
+	a->dSim = (double *)( a->buf + oSim ) ;
+	a->dCursor = (u64 *)( a->buf + oCur ) ;
+	T4AssignParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	auto dp = [&]( size_t off ) { return (u64)(uintptr_t)( a->buf + off ) ; } ;
+	P.descs = (u64)(uintptr_t)w->descs ;
+	P.pool = (u64)(uintptr_t)w->pool ;
+	P.ret = (u64)(uintptr_t)w->ret ;
+	P.strands = (u64)(uintptr_t)w->strands ;
+	P.rescue = (u64)(uintptr_t)w->rescue ;
+	P.list = dp( oList ) ; P.leader = dp( oLead ) ; P.slotSet = dp( oSet ) ; P.assign = dp( oAsg ) ; P.sim = dp( oSim ) ;
+	P.extOff = dp( oExt ) ; P.srcOff = dp( oSrc ) ; P.descOff = dp( oDoff ) ; P.listCnt = dp( oCnt ) ; P.cursor = dp( oCur ) ;
+	P.nDescs = n ; P.nSets = n_sets ; P.kmerLength = kmer_length ;
+	std::vector<u64> eo( n_sets ), so( n_sets ) ;
+	std::vector<T4Op> opsA( n_sets ), opsB( n_workers ), opsC( n_sets ) ;
+	for ( int j = 0 ; j < n_sets ; ++j )
+	{
+		eo[j] = a->ext[j]->off ;
+		so[j] = sets[j]->off ;
+		T4Op &x = opsA[j] ;
+		memset( &x, 0, sizeof( x ) ) ;
+		x.streamOff = eo[j] ;
+		x.op = T4_OP_ASSIGN_PREP ;
+		x.n = j ;
+		x.out = dp( oP ) ;
+		opsC[j] = x ;
+		opsC[j].op = T4_OP_ASSIGN_RECOMPUTE ;
+	}
+	for ( int b = 0 ; b < n_workers ; ++b )
+	{
+		T4Op &x = opsB[b] ;
+		memset( &x, 0, sizeof( x ) ) ;
+		x.streamOff = a->workers[b]->off ;
+		x.op = T4_OP_ASSIGN ;
+		x.n = b ;
+		x.out = dp( oP ) ;
+	}
+	int r = h2d( a->buf + oP, &P, sizeof( P ) ) ;
+	if ( !r ) r = dzero( a->buf + oCur, 256 ) ;
+	if ( !r ) r = h2d( a->buf + oOpsA, opsA.data(), (size_t)n_sets * sizeof( T4Op ) ) ;
+	if ( !r ) r = h2d( a->buf + oOpsB, opsB.data(), (size_t)n_workers * sizeof( T4Op ) ) ;
+	if ( !r ) r = h2d( a->buf + oOpsC, opsC.data(), (size_t)n_sets * sizeof( T4Op ) ) ;
+	if ( !r ) r = h2d( a->buf + oExt, eo.data(), (size_t)n_sets * 8 ) ;
+	if ( !r ) r = h2d( a->buf + oSrc, so.data(), (size_t)n_sets * 8 ) ;
+	if ( !r ) r = h2d( a->buf + oDoff, desc_off, (size_t)( n_sets + 1 ) * 8 ) ;
+	if ( !r ) r = launch_aux_ops( (T4Op *)( a->buf + oOpsA ), n_sets, cuda_stream ) ;
+	if ( !r ) r = launch_aux_ops( (T4Op *)( a->buf + oOpsB ), n_workers, cuda_stream ) ;
+	if ( !r ) r = launch_aux_ops( (T4Op *)( a->buf + oOpsC ), n_sets, cuda_stream ) ;
+	if ( r )
+	{
+		T4_API( assign_free )( a ) ;
+		return 0 ;
+	}
+	return a ;
+}
+
+static int assign_check( t4_assign *a )
+{
+	if ( !a || !E.up || a->gen != g_gen )
+	{
+		set_err( "stale or null t4_assign handle" ) ;
+		return T4_E_INVAL ;
+	}
+	return 0 ;
+}
+
+int T4_API( assign_results )( t4_assign *a, int32_t *assign, double *similarity )
+{
+	int r = assign_check( a ) ;
+	if ( r ) return r ;
+	r = dsync() ;
+	if ( r ) return r ;
+	r = T4_API( streams_error )( a->ext.data(), a->nSets ) ;
+	if ( r ) return r ;
+	r = T4_API( streams_error )( a->workers.data(), (int)a->workers.size() ) ;
+	if ( r ) return r ;
+	if ( assign && ( r = d2h( assign, a->dAssign, (size_t)a->nDescs * 32 ) ) ) return r ;
+	if ( similarity && ( r = d2h( similarity, a->dSim, (size_t)a->nDescs * 8 ) ) ) return r ;
+	return 0 ;
+}
+
+int T4_API( assign_stats )( t4_assign *a, uint64_t *stats )
+{
+	int r = assign_check( a ) ;
+	if ( r ) return r ;
+	r = dsync() ;
+	if ( r ) return r ;
+	u64 c[4] ;
+	r = d2h( c, a->dCursor, sizeof( c ) ) ;
+	if ( r ) return r ;
+	stats[0] = c[3] ; // reads in the pass (assembled reads)
+	stats[1] = c[1] ; // AssignRead calls (identical neighbours share one)
+	stats[2] = c[2] ; // reads assigned to a contig
+	stats[3] = (u64)a->workers.size() ;
+	return 0 ;
+}
+
+t4_seqset *T4_API( assign_extended_set )( t4_assign *a, int j )
+{
+	if ( assign_check( a ) || j < 0 || j >= a->nSets )
+		return 0 ;
+	return a->ext[j] ;
+}
+
+// device pointers of the per-record results for device-side consumers (bench: no host copy inside the timed region)
+int T4_API( assign_device_buffers )( t4_assign *a, void **assign, void **similarity )
+{
+	int r = assign_check( a ) ;
+	if ( r ) return r ;
+	if ( assign ) *assign = a->dAssign ;
+	if ( similarity ) *similarity = a->dSim ;
 	return 0 ;
 }
 

@@ -228,6 +228,10 @@ enum
 	T4_OP_INIT,
 	T4_OP_RELEASE_BARCODE,
 	T4_OP_RELEASE_SHALLOW,
+	// auxiliary kernel (t4_assign.h): the AssignRead pass over frozen sets
+	T4_OP_ASSIGN_PREP,
+	T4_OP_ASSIGN,
+	T4_OP_ASSIGN_RECOMPUTE,
 } ;
 
 struct T4Op                // per-CTA launch record

@@ -3192,6 +3192,99 @@ T4_D inline void s_make_exact( T4Ctx &cx, const char *r, int len, double factor,
 	pre[i] = e ;
 }
 
+// IsBaseEqual( posWeight column, read base ) of every overhang column of every overlap (ExtendOverlap, SeqSet.hpp:1165-1175) as bit
+// masks: bits[32 * i + 16 * side + w] holds overhang positions 32 w .. 32 w + 31 of side (0 left, 1 right) of overlap i.
+// Collective; r is the read in the strand of the overlaps.
+T4_D inline void c_overhang_bits( T4Ctx &cx, const T4Ovl *overlaps, int overlapCnt, const char *r, int len, u32 *bits )
+{
+#if T4_CUDA
+	{
+		// one warp per overlap (metadata fetched once), then per 32-column word lane t loads column t
+		// (one coalesced 512-byte request) and a ballot forms the word
+		const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31 ;
+		for ( int oi = warp ; oi < overlapCnt ; oi += nwarps )
+		{
+			const T4Ovl o = overlaps[oi] ;
+			T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+			const int seqLen = seq->len ;
+			const int4 *pw4 = (const int4 *)t4_pw( cx, seq ) ;
+			for ( int right = 0 ; right < 2 ; ++right )
+			{
+				int n, col0, rp0 ;
+				if ( !right )
+				{
+					n = t4_min( o.readStart, o.seqStart ) ;
+					col0 = o.seqStart - n ;
+					rp0 = o.readStart - n ;
+				}
+				else
+				{
+					n = t4_min( len - 1 - o.readEnd, seqLen - 1 - o.seqEnd ) ;
+					col0 = o.seqEnd + 1 ;
+					rp0 = o.readEnd + 1 ;
+				}
+				u32 *out = bits + 32 * oi + 16 * right ;
+				for ( int w = 0 ; w < 16 ; ++w )
+				{
+					if ( w * 32 >= n )
+					{
+						if ( lane == 0 )
+							out[w] = 0 ;
+						continue ;
+					}
+					int t = w * 32 + lane ;
+					bool eq = false ;
+					if ( t < n )
+					{
+						const int4 wv = pw4[col0 + t] ;
+						char pc = r[rp0 + t] ;
+						int c = t4_nuc( pc ) ;
+						int sum = wv.x + wv.y + wv.z + wv.w ;
+						int wc = c == 0 ? wv.x : ( c == 1 ? wv.y : ( c == 2 ? wv.z : wv.w ) ) ;
+						eq = ( sum == 0 || pc == 'N' || sum < 3 * wc ) ;
+					}
+					unsigned m = __ballot_sync( 0xffffffffu, eq ) ;
+					if ( lane == 0 )
+						out[w] = m ;
+				}
+			}
+		}
+	}
+	T4_SYNC() ;
+#else
+	T4_PAR_FOR( x, overlapCnt * 32 )
+	{
+		int oi = x >> 5, w = x & 15, right = ( x >> 4 ) & 1 ;
+		const T4Ovl &o = overlaps[oi] ;
+		T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
+		int n, col0, rp0 ;
+		if ( !right )
+		{
+			n = t4_min( o.readStart, o.seqStart ) ;
+			col0 = o.seqStart - n ;
+			rp0 = o.readStart - n ;
+		}
+		else
+		{
+			n = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
+			col0 = o.seqEnd + 1 ;
+			rp0 = o.readEnd + 1 ;
+		}
+		u32 m = 0 ;
+		if ( w * 32 < n )
+		{
+			const int *pw = t4_pw( cx, seq ) ;
+			int hi = n - w * 32 < 32 ? n - w * 32 : 32 ;
+			for ( int t = 0 ; t < hi ; ++t )
+				if ( t4_base_equal( pw + 4 * ( col0 + w * 32 + t ), r[rp0 + w * 32 + t] ) )
+					m |= 1u << t ;
+		}
+		bits[x] = m ;
+	}
+	T4_SYNC() ;
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // SeqSet::AddRead (SeqSet.hpp:3426-4473), novel-contig set.  Collective; reads cx.sm->read / rc.
 // ---------------------------------------------------------------------------
@@ -3257,92 +3350,7 @@ T4_D T4_BIG int c_add_read( T4Ctx &cx, int len, const char *geneName, int &stran
 		long long xt0 = clock64() ;
 #endif
 		u32 *bits = cx.P<u32>( st->bitsOff ) ;
-#if T4_CUDA
-		{
-			// one warp per overlap (metadata fetched once), then per 32-column word lane t loads column t
-			// (one coalesced 512-byte request) and a ballot forms the word
-			const int warp = cx.tid >> 5, nwarps = cx.nt >> 5, lane = cx.tid & 31 ;
-			for ( int oi = warp ; oi < overlapCnt ; oi += nwarps )
-			{
-				const T4Ovl o = overlaps[oi] ;
-				T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
-				const int seqLen = seq->len ;
-				const int4 *pw4 = (const int4 *)t4_pw( cx, seq ) ;
-				for ( int right = 0 ; right < 2 ; ++right )
-				{
-					int n, col0, rp0 ;
-					if ( !right )
-					{
-						n = t4_min( o.readStart, o.seqStart ) ;
-						col0 = o.seqStart - n ;
-						rp0 = o.readStart - n ;
-					}
-					else
-					{
-						n = t4_min( len - 1 - o.readEnd, seqLen - 1 - o.seqEnd ) ;
-						col0 = o.seqEnd + 1 ;
-						rp0 = o.readEnd + 1 ;
-					}
-					u32 *out = bits + 32 * oi + 16 * right ;
-					for ( int w = 0 ; w < 16 ; ++w )
-					{
-						if ( w * 32 >= n )
-						{
-							if ( lane == 0 )
-								out[w] = 0 ;
-							continue ;
-						}
-						int t = w * 32 + lane ;
-						bool eq = false ;
-						if ( t < n )
-						{
-							const int4 wv = pw4[col0 + t] ;
-							char pc = r[rp0 + t] ;
-							int c = t4_nuc( pc ) ;
-							int sum = wv.x + wv.y + wv.z + wv.w ;
-							int wc = c == 0 ? wv.x : ( c == 1 ? wv.y : ( c == 2 ? wv.z : wv.w ) ) ;
-							eq = ( sum == 0 || pc == 'N' || sum < 3 * wc ) ;
-						}
-						unsigned m = __ballot_sync( 0xffffffffu, eq ) ;
-						if ( lane == 0 )
-							out[w] = m ;
-					}
-				}
-			}
-		}
-		T4_SYNC() ;
-#else
-		T4_PAR_FOR( x, overlapCnt * 32 )
-		{
-			int oi = x >> 5, w = x & 15, right = ( x >> 4 ) & 1 ;
-			const T4Ovl &o = overlaps[oi] ;
-			T4Contig *seq = t4_seq( cx, o.seqIdx ) ;
-			int n, col0, rp0 ;
-			if ( !right )
-			{
-				n = t4_min( o.readStart, o.seqStart ) ;
-				col0 = o.seqStart - n ;
-				rp0 = o.readStart - n ;
-			}
-			else
-			{
-				n = t4_min( len - 1 - o.readEnd, seq->len - 1 - o.seqEnd ) ;
-				col0 = o.seqEnd + 1 ;
-				rp0 = o.readEnd + 1 ;
-			}
-			u32 m = 0 ;
-			if ( w * 32 < n )
-			{
-				const int *pw = t4_pw( cx, seq ) ;
-				int hi = n - w * 32 < 32 ? n - w * 32 : 32 ;
-				for ( int t = 0 ; t < hi ; ++t )
-					if ( t4_base_equal( pw + 4 * ( col0 + w * 32 + t ), r[rp0 + w * 32 + t] ) )
-						m |= 1u << t ;
-			}
-			bits[x] = m ;
-		}
-		T4_SYNC() ;
-#endif
+		c_overhang_bits( cx, overlaps, overlapCnt, r, len, bits ) ;
 #if T4_CUDA
 		long long xt1 = clock64() ;
 #endif
