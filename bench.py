@@ -65,6 +65,9 @@ def parse(argv=None):
                          "of the V(D)J cores in one contig at S = 4096, same reads/s); rank: contiguous blocks of the sorted read list "
                          "(SURVEY.md 8e; 56 %%)")
     ap.add_argument("--no-quality", action="store_true", help="skip the assembly-quality figure (clonotypes spanned by one contig)")
+    ap.add_argument("--assign-pass", type=int, default=int(os.environ.get("T4_BENCH_ASSIGN", 1)),
+                    help="config 1: also time the AssignRead pass over the finished sets (SURVEY.md 8f-2, main.cpp:2047-2118) -- a "
+                         "separate figure (`assign_pass`), outside `value` and `e2e`; 0 = skip")
     return ap.parse_args(argv)
 
 
@@ -182,7 +185,7 @@ def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
     order = sample_order(n_shards)
     n_sample = min(n_shards, max(1, args.ref_shards))       # a fixed subset, not "whatever fits the budget"
     lock = threading.Lock()
-    state = {"next": 0, "reads": 0, "shards": 0, "kept": {}}
+    state = {"next": 0, "reads": 0, "shards": 0, "kept": {}, "assign_s": 0.0, "assign_reads": 0}
     t0 = time.perf_counter()
 
     def worker():
@@ -203,6 +206,15 @@ def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
             rec = None
             if x < keep:                                                     # the first `keep` of the order: full parity record
                 rec = (out[1], out[3], r.output(), r.index_checksum())
+                if args.config == 1 and args.assign_pass:                    # ... and the reference's AssignRead pass over the shard
+                    ta = time.perf_counter()
+                    lst = rh.assembled_list(out[1], out[3])
+                    ext, ra, rs = rh.assign_pass(r, 17, descs[lo:hi], w.pool, lst, out[2])
+                    rec = rec + ((lst, ra, rs, ext.output()),)
+                    ext.close()
+                    with lock:
+                        state["assign_s"] += time.perf_counter() - ta
+                        state["assign_reads"] += len(lst)
             r.close()
             with lock:
                 state["reads"] += hi - lo
@@ -215,8 +227,9 @@ def reference_sample(args, w, off, descs, budget_s, cores, keep=64):
         t.start()
     for t in th:
         t.join()
-    el = time.perf_counter() - t0
+    el = time.perf_counter() - t0 - state["assign_s"] / max(1, cores)     # the AssignRead checks of the kept shards are not part of the loop's time
     reference_sample.kept = state["kept"]
+    reference_sample.assign = {"reads": state["assign_reads"], "thread_seconds": state["assign_s"]}
     return {"value": state["reads"] / el, "unit": "reads/s", "cores": cores, "kind": "reference",
             "sample": "%d of %d read shards (%d reads), uniformly sampled over the shard index range (fixed permutation), %.1f s wall "
                       "on %d threads; oracle/_ref/libt4ref.so = reference SeqSet::AddRead/RepeatAddRead/InputNovelRead driven by the "
@@ -523,6 +536,33 @@ def main():
               "d2h_contigs_ms": x1.elapsed_time(x2), "d2h_contigs_gbs": merged["pack_bytes"] / max(1e-6, x1.elapsed_time(x2)) / 1e6}
     del dpool
 
+
+    # ---- the AssignRead pass over the finished sets (main.cpp:2047-2118): its own figure, outside value / e2e
+    assign_fig, assign_obj = None, None
+    if args.config == 1 and args.assign_pass:
+        try:
+            ams = []
+            st4 = np.zeros(4, dtype=np.uint64)
+            for _ in range(2):                   # the second run is the timed one (the first also warms the allocator)
+                if assign_obj:
+                    lib.assign_free(assign_obj)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                assign_obj = lib.streams_assign_reads(handles, S, wl, off64.ctypes.data, 17, 0, None)
+                if not assign_obj:
+                    raise RuntimeError(lib.err())
+                a1.record()
+                torch.cuda.synchronize()
+                ams.append(a0.elapsed_time(a1))
+            lib.check(lib.assign_stats(assign_obj, st4.ctypes.data))
+            assign_fig = {"what": "extendedSeq(17).InputSeqSet per stream + AssignRead of every assembled read (worker CTAs over the whole "
+                                  "GPU) + RecomputePosWeight; three launches of t4_aux_kernel",
+                          "ms": ams[-1], "ms_all": ams, "reads": int(st4[0]), "assign_calls": int(st4[1]), "assigned": int(st4[2]),
+                          "worker_ctas": int(st4[3]), "reads_per_s": float(st4[0]) / (ams[-1] * 1e-3), "kmer": 17}
+        except Exception as ex:      # a separate figure: never let it break the headline measurement
+            assign_fig = {"error": str(ex)[:300]}
+
     value = world * n_reads * args.steps / (ms * 1e-3)
     e2e = world * n_reads * args.steps / (ms_e2e * 1e-3)
     quality_fig = None
@@ -554,14 +594,39 @@ def main():
             if kept:
                 gret, gres = ret.numpy(), resc.numpy()
                 bad = []
-                for j, (rret, rres, rout, rsum) in kept.items():
+                ga = gs = None
+                abad, achecked = [], 0
+                if assign_obj:
+                    ga = np.zeros((n_reads, 8), dtype=np.int32)
+                    gs = np.zeros(n_reads, dtype=np.float64)
+                    lib.check(lib.assign_results(assign_obj, ga.ctypes.data, gs.ctypes.data))
+                for j, rec in kept.items():
+                    rret, rres, rout, rsum = rec[:4]
                     lo, hi = int(off[j]), int(off[j + 1])
                     g = api.SeqSet(9, lib, handles[j])
                     ok = (gret[lo:hi] == rret).all() and (gres[lo:hi] == rres).all() and g.output() == rout and g.index_checksum() == rsum
                     if not ok:
                         bad.append(int(j))
+                    if ga is not None and len(rec) > 4:
+                        lst, ra, rs, eout = rec[4]
+                        gj = ga[lo:hi][lst]
+                        okr = ra[:, 0] >= 0
+                        ge = api.SeqSet(17, lib, lib.assign_extended_set(assign_obj, int(j)))
+                        oka = ((gj[:, 0] == ra[:, 0]).all() and (gj[okr] == ra[okr]).all() and (gs[lo:hi][lst][okr] == rs[okr]).all()
+                               and ge.output() == eout)
+                        ge.h = None
+                        achecked += 1
+                        if not oka:
+                            abad.append(int(j))
                 parity = {"shards_checked": len(kept), "checked": "return codes, rescue codes, Output text, index checksum",
                           "equal_reference": len(bad) == 0, "bad_shards": bad[:8]}
+                if assign_fig is not None and "error" not in assign_fig:
+                    ra_ = getattr(reference_sample, "assign", None) or {}
+                    assign_fig["parity_spot_check"] = {"shards_checked": achecked, "equal_reference": achecked > 0 and len(abad) == 0, "bad_shards": abad[:8],
+                                                       "checked": "per read: contig, coordinates, strand, matchCnt, similarity; per stream: Output text of the extended set after RecomputePosWeight"}
+                    if ra_.get("thread_seconds"):
+                        assign_fig["cpu_reference"] = {"reads_per_s_per_thread": ra_["reads"] / ra_["thread_seconds"], "reads": ra_["reads"],
+                                                       "note": "reference InputSeqSet + AssignRead + RecomputePosWeight over the same sampled shards, per host thread (the reference runs this pass on -t threads, main.cpp:2086-2116)"}
         except Exception as ex:      # never let the checker break the measurement
             parity = {"error": str(ex)[:200]}
         line = build_line(
@@ -572,10 +637,12 @@ def main():
             # init + stream kernel + pack-size + pack per step
             4 * args.steps, roofline, roofline_probe, cpu,
             {"assembled_reads": assembled, "reads_per_gpu": n_reads, "contigs_per_gpu": merged["contigs"], "parity_spot_check": parity,
-             "assembly_quality": quality_fig,
+             "assembly_quality": quality_fig, "assign_pass": assign_fig,
              "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
              "threads_per_stream": int(os.environ.get("T4_NT", 128))}, metric=su["metric"])
         print(json.dumps(line))
+    if assign_obj:
+        lib.assign_free(assign_obj)
     lib.workload_free(wl)
     if world > 1:
         dist.destroy_process_group()

@@ -41,6 +41,10 @@
 #define t4_workload_events t4emu_workload_events
 #define t4_shard_reads t4emu_shard_reads
 #define t4_streams_error t4emu_streams_error
+#define t4_streams_assign_reads t4emu_streams_assign_reads
+#define t4_assign_results t4emu_assign_results
+#define t4_assign_extended_set t4emu_assign_extended_set
+#define t4_assign_free t4emu_assign_free
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
 #endif
@@ -73,6 +77,8 @@ class T4GpuSeqSet : public SeqSet
 	std::vector<int> rescueOrder ;
 	size_t cur, rescuePos ;
 	int maxFinalK ;
+	t4_workload *wl ;                    // the uploaded read list, kept for the AssignRead pass (BatchAssign)
+	std::vector<int64_t> wlOff, wlOrder ;
 	void Die() { fprintf( stderr, "trust4_b200: %s\n", t4_last_error() ) ; exit( 1 ) ; }
 	int Check( int r ) { if ( r < T4_E_BASE ) Die() ; return r ; }
 
@@ -140,7 +146,7 @@ class T4GpuSeqSet : public SeqSet
 	}
 public:
 	T4GpuSeqSet( int kl ) : SeqSet( kl ), h( NULL ), replay( false ), curK( kl ), curHitLen( 31 ), curConsiderBarcode( 0 ), cur( 0 ), rescuePos( 0 ),
-		maxFinalK( kl )
+		maxFinalK( kl ), wl( NULL )
 	{
 		gpu = ( t4_adapter_instances++ == 0 ) ;
 		if ( gpu )
@@ -153,6 +159,8 @@ public:
 	}
 	~T4GpuSeqSet()
 	{
+		if ( wl )
+			t4_workload_free( wl ) ;
 		for ( size_t i = 0 ; i < sets.size() ; ++i )
 			t4_seqset_destroy( sets[i] ) ;
 	}
@@ -387,7 +395,9 @@ public:
 			}
 		}
 		Check( t4_streams_error( sets.data(), S ) ) ;
-		t4_workload_free( w ) ;
+		wl = w ; // the AssignRead pass (BatchAssign) reads the same records and the per-read results on the device
+		wlOff = off ;
+		wlOrder = order ;
 		rescueOrder.clear() ;
 		for ( int i = 0 ; i < n ; ++i )
 			if ( bRet[i] == -2 )
@@ -407,6 +417,79 @@ public:
 		cur = 0 ;
 		rescuePos = 0 ;
 		fprintf( stderr, "[trust4_b200] batch route: %d reads on %d device stream(s)\n", n, S ) ;
+	}
+
+	// T4_BATCH_ASSIGN() is the second inserted line of the batch route: `if ( !seqSet.BatchAssign( ... ) )` in front of the
+	// driver's AssignRead loop (main.cpp:2075: `if ( threadCnt <= 1 ) { ... } else { ... pthreads ... }`), which thereby
+	// becomes the fall-back branch.  The device runs the pass (t4_streams_assign_reads: extended sets by InputSeqSet at
+	// extendedSeq's k, AssignRead of every assembled read with novelSeqSimilarity 0.95, worker CTAs over the whole GPU) on the
+	// sets and the read list of BatchPrepare, and assembledReads[].overlap receives what the driver's own loop would have
+	// stored -- including the reference's reuse of one `assign` variable: a read AssignRead cannot place only gets
+	// seqIdx = -1, the other fields keep the previous assignment (main.cpp:2051, 2078-2081).  extendedSeq itself is the CPU
+	// object the driver built (InputSeqSet of the synced contigs): its slots are the concatenation of the streams' extended
+	// sets, so a device slot becomes a global one by adding the sizes of the earlier streams' sets.  RecomputePosWeight
+	// (main.cpp:2118) then runs on the CPU object from these assignments.  T4_ASSIGN=0 keeps the pass on the CPU.
+	template <class ExtSet, class AReads>
+	bool BatchAssign( ExtSet &extendedSeq, AReads &assembledReads, int assembledReadCnt )
+	{
+		const char *env = getenv( "T4_ASSIGN" ) ;
+		if ( !gpu || !replay || wl == NULL || ( env && atoi( env ) == 0 ) )
+			return false ;
+		const int S = (int)sets.size() ;
+		const int64_t n = (int64_t)wlOrder.size() ;
+		t4_assign *a = t4_streams_assign_reads( sets.data(), S, wl, wlOff.data(), extendedSeq.kmerLength, 0, NULL ) ;
+		if ( !a )
+			Die() ;
+		std::vector<int32_t> as( 8 * (size_t)n + 8 ) ;
+		std::vector<double> sim( (size_t)n + 1 ) ;
+		Check( t4_assign_results( a, as.data(), sim.data() ) ) ;
+		std::vector<int> base( S + 1, 0 ), streamOf( (size_t)n ) ;
+		for ( int s = 0 ; s < S ; ++s )
+		{
+			base[s + 1] = base[s] + Check( t4_seqset_size( t4_assign_extended_set( a, s ) ) ) ;
+			for ( int64_t j = wlOff[s] ; j < wlOff[s + 1] ; ++j )
+				streamOf[j] = s ;
+		}
+		if ( base[S] != (int)extendedSeq.seqs.size() )
+		{
+			fprintf( stderr, "trust4_b200: extended sets out of step (%d device slots, %d host slots)\n", base[S], (int)extendedSeq.seqs.size() ) ;
+			exit( 1 ) ;
+		}
+		std::vector<int64_t> recOf( (size_t)n ) ;
+		for ( int64_t j = 0 ; j < n ; ++j )
+			recOf[ wlOrder[j] ] = j ;
+		struct _overlap assign ;
+		memset( &assign, 0, sizeof( assign ) ) ;
+		assign.seqIdx = -1 ;
+		int placed = 0 ;
+		for ( int x = 0 ; x < assembledReadCnt ; ++x )
+		{
+			const int64_t j = recOf[ assembledReads[x].info ] ;
+			const int32_t *o = &as[8 * j] ;
+			if ( o[0] == T4_ASSIGN_NOT_LISTED )
+			{
+				fprintf( stderr, "trust4_b200: assembled read %d is not part of the device's AssignRead pass\n", x ) ;
+				exit( 1 ) ;
+			}
+			if ( o[0] >= 0 )
+			{
+				assign.seqIdx = o[0] + base[ streamOf[j] ] ;
+				assign.readStart = o[1] ; assign.readEnd = o[2] ;
+				assign.seqStart = o[3] ; assign.seqEnd = o[4] ;
+				assign.strand = o[5] ;
+				assign.matchCnt = o[6] ;
+				assign.similarity = sim[j] ;
+				++placed ;
+			}
+			else
+				assign.seqIdx = -1 ;
+			assembledReads[x].overlap = assign ;
+		}
+		t4_assign_free( a ) ;
+		t4_workload_free( wl ) ;
+		wl = NULL ;
+		fprintf( stderr, "[trust4_b200] batch route: AssignRead pass on the device, %d of %d reads placed\n", placed, assembledReadCnt ) ;
+		return true ;
 	}
 
 	int AddRead( char *read, char *geneName, int &strand, int barcode, int minKmerCount, bool repetitiveData, double similarityThreshold )
@@ -558,6 +641,9 @@ public:
 // The one line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
 #define T4_BATCH_PREPARE() seqSet.BatchPrepare( sortedReads, refSet, readCnt, hasBarcode, keepMissingBarcode, trimLevel, firstReadLen, \
 	constantGeneEnd, contigMinCov, changeKmerLengthThreshold )
+
+// The second line of the batch route, in front of the AssignRead loop (main.cpp:2075); see BatchAssign.
+#define T4_BATCH_ASSIGN() if ( !seqSet.BatchAssign( extendedSeq, assembledReads, assembledReadCnt ) )
 
 #define SeqSet T4GpuSeqSet
 #endif

@@ -100,6 +100,24 @@ def test_batch_emu_synthetic(emu_batch_binary, tmp_path):
     run_and_compare(emu_batch_binary, write_inputs(str(tmp_path)), str(tmp_path), env={"T4_STREAMS": "1"})
 
 
+def test_batch_emu_assign_pass_on_device(emu_batch_binary, tmp_path):
+    """The second offloaded pass of the batch route: with paired-end bulk input the driver's AssignRead
+    loop (main.cpp:2075-2116) is replaced by t4_streams_assign_reads; _final.out -- which the reference derives from those
+    assignments through RecomputePosWeight and the mate extension -- must stay byte-identical, with the pass on the device
+    (default) and with T4_ASSIGN=0 (the driver's own CPU loop)."""
+    tmp = str(tmp_path)
+    args = write_inputs(tmp, 2500, 80, 31)
+    subprocess.run([STOCK, "-t", "1", "-o", os.path.join(tmp, "stock")] + args, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=900)
+    for tag, env in (("dev", {"T4_STREAMS": "1"}), ("cpu", {"T4_STREAMS": "1", "T4_ASSIGN": "0"})):
+        r = subprocess.run([emu_batch_binary, "-t", "1", "-o", os.path.join(tmp, tag)] + args, check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, **env), text=True)
+        assert ("AssignRead pass on the device" in r.stderr) == (tag == "dev")
+        for suf in SUFFIXES:
+            a = open(os.path.join(tmp, "stock" + suf), "rb").read()
+            assert len(a) > 0 and a == open(os.path.join(tmp, tag + suf), "rb").read(), (tag, suf)
+
+
 def test_batch_emu_repseq_and_min_cov(emu_batch_binary, tmp_path):
     run_and_compare(emu_batch_binary, write_inputs(str(tmp_path), 800, 25, 22), str(tmp_path),
                     extra=("--trimLevel", "2", "--skipMateExtension", "--contigMinCov", "2"), env={"T4_STREAMS": "1"})
