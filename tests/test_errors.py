@@ -59,3 +59,35 @@ def test_stale_handle_after_reset(emu_lib):
     with pytest.raises(api.T4Error) as e:
         s.size()
     assert e.value.code == api.T4_E_INVAL
+
+
+def test_assign_pass_errors(emu_lib):
+    """t4_streams_assign_reads: bad arguments give NULL + a message; a t4_assign does not survive t4_reset."""
+    import ctypes as C
+    import numpy as np
+    from trust4_b200 import synth
+    emu_lib.check(emu_lib.reset())
+    cl = synth.make_clones(10, 4)
+    w = synth.build_workload(cl, synth.sample_pairs(cl, 100, 150, 4))
+    sets = api.SeqSet.create_many(1, 9, emu_lib)
+    wl = api.Workload(w.descs, w.pool, w.names, emu_lib)
+    hs = (C.c_void_p * 1)(sets[0].h)
+    bad = np.array([1, len(w.descs)], dtype=np.int64)
+    assert not emu_lib.streams_assign_reads(hs, 1, wl.h, bad.ctypes.data, 17, 0, None)
+    assert b"desc_off" in emu_lib.last_error()
+    assert not emu_lib.streams_assign_reads(hs, 1, None, bad.ctypes.data, 17, 0, None)
+    with pytest.raises(api.T4Error):
+        api.Assign(sets, wl, np.array([0, len(w.descs)]), kmer_length=40)      # k out of range
+    with pytest.raises(api.T4Error):
+        api.Assign(sets, wl, np.array([0, len(w.descs)]), 17)                  # no assembly run on this workload yet
+    assert b"no assembly results" in emu_lib.last_error()
+    off = np.array([0, len(w.descs)], dtype=np.int64)
+    emu_lib.check(emu_lib.streams_run_resident(hs, 1, synth.run_cfg().ctypes.data, wl.h, off.ctypes.data, None))
+    a = api.Assign(sets, wl, off, 17)
+    assert a.stats()["reads"] > 100
+    emu_lib.check(emu_lib.reset())
+    with pytest.raises(api.T4Error) as e:
+        a.results()
+    assert e.value.code == api.T4_E_INVAL
+    a.close()
+    wl.close()

@@ -471,6 +471,7 @@ struct t4_workload
 	u64 *packed ;          // 2-bit packed reads, record i at packed + i * packStride (t4_common.h)
 	u64 packStride ;
 	bool usePacked ;       // every read is pure ACGTN: the stream kernel assembles from the packed pool
+	bool ran ;             // the result arrays hold the outcome of an assembly run (t4_streams_run_resident)
 } ;
 
 extern "C" {
@@ -1688,6 +1689,7 @@ int T4_API( streams_run_resident )( t4_seqset *const *sets, int n_sets, const t4
 	if ( r ) return r ;
 	r = ensure_ops( w, n_sets ) ;
 	if ( r ) return r ;
+	w->ran = true ;
 #if T4_CUDA
 	CK( cudaMemcpyAsync( w->ops, ops.data(), (size_t)n_sets * sizeof( T4Op ), cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream ) ) ;
 #else
@@ -1981,6 +1983,11 @@ t4_assign *T4_API( streams_assign_reads )( t4_seqset *const *sets, int n_sets, t
 	if ( desc_off[0] != 0 || n > w->nDescs || n >= ( 1ll << 31 ) )
 	{
 		set_err( "t4_streams_assign_reads: desc_off must start at 0 and fit the workload" ) ;
+		return 0 ;
+	}
+	if ( !w->ran )
+	{
+		set_err( "t4_streams_assign_reads: the workload holds no assembly results yet (t4_streams_run_resident comes first)" ) ;
 		return 0 ;
 	}
 	for ( int j = 0 ; j < n_sets ; ++j )

@@ -40,6 +40,19 @@ struct T4AssignParams      // device resident; every CTA of the three launches r
 
 #define T4_ASSIGN_CHUNK 8          /* list slots per cursor step */
 
+// st->error as ONE value for the whole CTA: a thread may raise an error after the last barrier of a collective, so
+// control flow that leads to barriers must not branch on each thread's own load of it.
+T4_D inline int c_uniform_error( T4Ctx &cx )
+{
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+		cx.sm->bi[1] = cx.st->error ;
+	T4_SYNC() ;
+	const int e = cx.sm->bi[1] ;
+	T4_SYNC() ;
+	return e ;
+}
+
 // ---- PREP --------------------------------------------------------------------------------------------------------
 // SeqSet::InputSeqSet( in, false ), SeqSet.hpp:3108-3139: every live contig of `src`, in slot order, becomes the next
 // slot of this (fresh) set -- consensus, posWeight, anchors, numRead, barcode, name -- and is indexed at this set's k
@@ -73,7 +86,7 @@ T4_D inline void c_input_seqset( T4Ctx &cx, const T4Stream *src )
 		T4_SYNC() ;
 		const int idx = sm->bi[0] ;
 		T4_SYNC() ;
-		if ( idx < 0 || cx.st->error )
+		if ( idx < 0 || c_uniform_error( cx ) )
 			return ;
 		T4Contig *c = t4_seq( cx, idx ) ;
 		char *cons = t4_cons( cx, c ) ;
@@ -215,7 +228,7 @@ T4_D inline int c_assign_read( T4Ctx &cx, int len, int strand, int barcode )
 	T4Smem *sm = cx.sm ;
 	int overlapCnt = c_get_overlaps( cx, len, strand, barcode, false ) ;
 	T4_PHASE( cx, 0 ) ;
-	if ( st->error || overlapCnt <= 0 || st->nSeqs == 0 )
+	if ( c_uniform_error( cx ) || overlapCnt <= 0 || st->nSeqs == 0 )
 		return -1 ;
 	c_sort_overlaps( cx, overlapCnt ) ; // std::sort( overlaps ), SeqSet.hpp:4649
 	T4Ovl *overlaps = cx.P<T4Ovl>( st->ovlOff ) ;
@@ -320,6 +333,7 @@ T4_D inline void c_assign_loop( T4Ctx &cx, T4Op *op )
 	u64 *cursor = t4_x<u64>( P->cursor ) ;
 	int cur = -1 ;
 	u64 nAssigned = 0 ;
+	bool failed = false ;
 	while ( 1 )
 	{
 		T4_SYNC() ;
@@ -344,7 +358,8 @@ T4_D inline void c_assign_loop( T4Ctx &cx, T4Op *op )
 			const t4_read_desc d = descs[rec] ;
 			c_load_read( cx, pool + d.seq_off, d.len ) ;
 			const int ret = c_assign_read( cx, d.len, strands[rec], d.barcode ) ;
-			if ( cx.st->error )
+			failed = c_uniform_error( cx ) != 0 ;
+			if ( failed )
 				break ;
 			// the result goes to this record and to the neighbours that share it (a contiguous range of slots)
 			const T4Ovl e = sm->e0 ;
@@ -364,7 +379,7 @@ T4_D inline void c_assign_loop( T4Ctx &cx, T4Op *op )
 					o[0] = -1 ;
 			}
 		}
-		if ( cx.st->error )
+		if ( failed )
 			break ;
 	}
 	T4_SYNC() ;
