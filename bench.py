@@ -65,6 +65,9 @@ def parse(argv=None):
                          "of the V(D)J cores in one contig at S = 4096, same reads/s); rank: contiguous blocks of the sorted read list "
                          "(SURVEY.md 8e; 56 %%)")
     ap.add_argument("--no-quality", action="store_true", help="skip the assembly-quality figure (clonotypes spanned by one contig)")
+    ap.add_argument("--kmer-stats", type=int, default=int(os.environ.get("T4_BENCH_KCOUNT", 1)),
+                    help="configs 1/4: also time the 21-mer counting + per-read count statistics of the pre-processing on the device "
+                         "(SURVEY.md 8f-3; `preprocess_kmer_stats`, outside value / e2e) and compare with the generator's figures; 0 = skip")
     ap.add_argument("--assign-pass", type=int, default=int(os.environ.get("T4_BENCH_ASSIGN", 1)),
                     help="config 1: also time the AssignRead pass over the finished sets (SURVEY.md 8f-2, main.cpp:2047-2118) -- a "
                          "separate figure (`assign_pass`), outside `value` and `e2e`; 0 = skip")
@@ -563,6 +566,46 @@ def main():
         except Exception as ex:      # a separate figure: never let it break the headline measurement
             assign_fig = {"error": str(ex)[:300]}
 
+
+    # ---- 21-mer counting + per-read count statistics of the pre-processing, its own figure
+    kc_fig = None
+    if args.config in (1, 4) and args.kmer_stats and rank == 0:
+        try:
+            dpool2 = torch.from_numpy(w.pool).to(dev)
+            doff = torch.from_numpy(w.descs["seq_off"].astype(np.int64)).to(dev)
+            dlen = torch.from_numpy(w.descs["len"].astype(np.int32)).to(dev)
+            inst = int(np.maximum(w.descs["len"].astype(np.int64) - 20, 0).sum())
+            tb = int(lib.kmer_count_table_bytes(max(1 << 20, inst // 2)))       # capacity hint: half the instances (distinct k-mers are far fewer)
+            table = torch.empty(tb, dtype=torch.uint8, device=dev)
+            omn = torch.empty(n_reads, dtype=torch.int32, device=dev)
+            omed = torch.empty(n_reads, dtype=torch.int32, device=dev)
+            oavg = torch.empty(n_reads, dtype=torch.float32, device=dev)
+            kms = []
+            for _ in range(3):
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                q0.record()
+                lib.check(lib.kmer_count_stats_device(dpool2.data_ptr(), doff.data_ptr(), dlen.data_ptr(), n_reads, 21, table.data_ptr(), tb,
+                                                      omn.data_ptr(), omed.data_ptr(), oavg.data_ptr(), None))
+                q1.record()
+                torch.cuda.synchronize()
+                kms.append(q0.elapsed_time(q1))
+            ks = np.zeros(4, dtype=np.uint64)
+            lib.check(lib.kmer_count_table_stats(table.data_ptr(), tb, ks.ctypes.data))
+            km = float(np.median(kms))
+            eq_min = bool((omn.cpu().numpy() == w.descs["min_cnt"]).all())
+            eq_med = bool((omed.cpu().numpy() == w.med_cnt).all()) if w.med_cnt is not None else None
+            kc_fig = {"what": "KmerCount(21): AddCount of every read + GetCountStatsAndTrim (no trimming) -> minCnt / medianCnt / avgCnt per read; "
+                              "two launches of t4_kcount_kernel over one HBM hash table",
+                      "ms": km, "ms_all": kms, "reads_per_s": n_reads / (km * 1e-3), "kmers": int(ks[0]), "distinct_kmers": int(ks[1]),
+                      "table_slots": int(ks[2]), "table_overflow": bool(ks[3]), "kmers_per_s": float(ks[0]) / (km * 1e-3),
+                      "equals_generator_min_cnt": eq_min, "equals_generator_median_cnt": eq_med,
+                      "note": "the workload generator's own statistics come from torch.unique/sort (library calls); parity against the "
+                              "reference's KmerCount is tests/test_gpu_parity.py::test_gpu_kmer_count_stats"}
+            del dpool2, table
+        except Exception as ex:
+            kc_fig = {"error": str(ex)[:300]}
+
     value = world * n_reads * args.steps / (ms * 1e-3)
     e2e = world * n_reads * args.steps / (ms_e2e * 1e-3)
     quality_fig = None
@@ -637,7 +680,7 @@ def main():
             # init + stream kernel + pack-size + pack per step
             4 * args.steps, roofline, roofline_probe, cpu,
             {"assembled_reads": assembled, "reads_per_gpu": n_reads, "contigs_per_gpu": merged["contigs"], "parity_spot_check": parity,
-             "assembly_quality": quality_fig, "assign_pass": assign_fig,
+             "assembly_quality": quality_fig, "assign_pass": assign_fig, "preprocess_kmer_stats": kc_fig,
              "merge_allgather": merged if world > 1 else None, "workload_gen_s": t_gen,
              "threads_per_stream": int(os.environ.get("T4_NT", 128))}, metric=su["metric"])
         print(json.dumps(line))

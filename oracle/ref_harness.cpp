@@ -28,6 +28,8 @@
 #include "SeqSet.hpp"
 #undef private
 
+#include "KmerCount.hpp"
+
 #include "../include/trust4_b200.h"
 
 // Each reference executable defines these (main.cpp:39-44); values restated from defs.h's contract.
@@ -605,6 +607,35 @@ void *t4ref_assign_pass( void *h, int kmerLength, const t4_read_desc *descs, con
 	for ( int i = 0 ; i < nList ; ++i )
 		free( reads[i].read ) ;
 	return ext ;
+}
+
+// ---- k-mer counting ------------------------------------------
+// KmerCount( k ): AddCount of every read, then GetCountStatsAndTrim( read, NULL, ... ) of every read (main.cpp:404-440, 981-1010).
+int t4ref_kmer_count_stats( const char *pool, const uint64_t *seqOff, const int32_t *len, int64_t n, int k, int32_t *minCnt,
+	int32_t *medianCnt, float *avgCnt )
+{
+	KmerCount kc( k ) ;
+	int maxLen = 0 ;
+	std::vector<char> buf ;
+	for ( int64_t i = 0 ; i < n ; ++i )
+	{
+		buf.assign( pool + seqOff[i], pool + seqOff[i] + len[i] ) ;
+		buf.push_back( '\0' ) ;
+		kc.AddCount( buf.data() ) ;
+		if ( len[i] > maxLen )
+			maxLen = len[i] ;
+	}
+	kc.SetBuffer( maxLen + 1 ) ;
+	for ( int64_t i = 0 ; i < n ; ++i )
+	{
+		buf.assign( pool + seqOff[i], pool + seqOff[i] + len[i] ) ;
+		buf.push_back( '\0' ) ;
+		int a = 0, b = 0 ;
+		float c = 0 ;
+		kc.GetCountStatsAndTrim( buf.data(), NULL, a, b, c ) ;
+		minCnt[i] = a ; medianCnt[i] = b ; avgCnt[i] = c ;
+	}
+	return 0 ;
 }
 
 } // extern "C"

@@ -688,3 +688,42 @@ def check_assign_pass(lib, ref, seed, n_shards, nclones=25, npairs=400, kmer=17,
     a.close()
     wl.close()
     return n_listed, n_assigned
+
+
+def check_kmer_count_stats(lib, ref, seed=101, n=1500, k=21):
+    """t4_kmer_count_stats against the reference's KmerCount: AddCount of every read, then
+    GetCountStatsAndTrim without trimming -- min / median exact, avg the same float.  Reads: sampled pairs of a clone set
+    (shared k-mers with high counts) plus ragged ones: lengths 5..400, N's, reads of N's only, homopolymers, duplicates."""
+    rng = np.random.default_rng(seed)
+    cl = synth.make_clones(30, seed)
+    rd = synth.sample_pairs(cl, n // 3, 150, seed, sub_rate=0.01)
+    reads = [synth.decode(c) for c in rd.codes]
+    src = reads[: 50]
+    while len(reads) < n:
+        s = src[int(rng.integers(len(src)))]
+        L = int(rng.integers(5, 401))
+        t = (s * 4)[int(rng.integers(0, 100)):][:L]
+        kind = int(rng.integers(0, 8))
+        if kind == 0:
+            t = "N" * L
+        elif kind == 1:
+            t = "ACGT"[int(rng.integers(4))] * L
+        elif kind in (2, 3):
+            t = list(t)
+            for p in rng.integers(0, L, size=int(rng.integers(1, 6))):
+                t[int(p)] = "N"
+            t = "".join(t)
+        elif kind == 4 and len(reads) > 3:
+            t = reads[int(rng.integers(len(reads)))]
+        reads.append(t)
+    lens = np.array([len(r) for r in reads], dtype=np.int32)
+    off = np.zeros(len(reads), dtype=np.uint64)
+    off[1:] = np.cumsum(lens[:-1])
+    pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    rmn, rmed, ravg = ref.kmer_count_stats(pool, off, lens, k)
+    gmn, gmed, gavg = api.kmer_count_stats(pool, off, lens, k, lib)
+    assert (gmn == rmn).all(), ("min", np.flatnonzero(gmn != rmn)[:5])
+    assert (gmed == rmed).all(), ("median", np.flatnonzero(gmed != rmed)[:5])
+    assert (gavg.view(np.uint32) == ravg.view(np.uint32)).all(), ("avg", np.flatnonzero(gavg != ravg)[:5])
+    assert (rmn < 0).sum() > 10 and (rmn == 0).sum() > 10 and (rmn > 1).sum() > 100 and rmed.max() > 20
+    return int(len(reads))

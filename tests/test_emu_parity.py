@@ -96,3 +96,9 @@ def test_emu_assign_pass_noisy_and_duplicates(emu_lib, ref):
     cl = synth.make_clones(9, 95, chains=("TRB",))
     w = synth.build_workload(cl, synth.sample_amplicon(cl, 5000, 100, 95, alpha=0.7, sub_rate=0.002), repseq=True)
     pc.check_assign_pass(emu_lib, ref, 95, 2, workload=w, cfg=synth.run_cfg(repetitive=1, first_read_len=100))
+
+
+@pytest.mark.parametrize("k", [21, 9, 31])
+def test_emu_kmer_count_stats(emu_lib, ref, k):
+    """canonical k-mer counts + per-read min / median / avg (KmerCount.hpp) -- the numbers that order the reads."""
+    assert pc.check_kmer_count_stats(emu_lib, ref, seed=100 + k, k=k) >= 1500

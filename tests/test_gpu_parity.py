@@ -153,3 +153,10 @@ def test_gpu_assign_pass_noisy_and_duplicates(gpu_lib, ref):
     # fewer workers than sets, and a single worker
     pc.check_assign_pass(gpu_lib, ref, 84, 6, nclones=30, npairs=500, n_workers=3)
     pc.check_assign_pass(gpu_lib, ref, 85, 2, nclones=30, npairs=500, n_workers=1)
+
+
+@pytest.mark.parametrize("k", [21, 9, 31])
+def test_gpu_kmer_count_stats(gpu_lib, ref, k):
+    """SURVEY.md 8f-3 on the device (t4_kcount_kernel): canonical k-mer counts in one HBM hash table, per-read min / median /
+    avg equal to the reference's KmerCount::AddCount + GetCountStatsAndTrim (ragged reads, N's, duplicates)."""
+    assert pc.check_kmer_count_stats(gpu_lib, ref, seed=100 + k, n=6000, k=k) >= 6000

@@ -35,6 +35,7 @@ EXPORTS = [
     "seqset_index_checksum", "streams_pack_contigs", "streams_cycles",
     "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
     "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
+    "kmer_count_stats", "kmer_count_table_bytes", "kmer_count_stats_device", "kmer_count_table_stats",
 ]
 
 
@@ -116,6 +117,10 @@ class Lib:
         f("assign_stats", ci, [vp, vp])
         f("assign_extended_set", vp, [vp, ci])
         f("assign_device_buffers", ci, [vp, C.POINTER(vp), C.POINTER(vp)])
+        f("kmer_count_stats", ci, [vp, C.c_size_t, vp, vp, C.c_int64, ci, vp, vp, vp])
+        f("kmer_count_table_bytes", C.c_size_t, [C.c_int64])
+        f("kmer_count_stats_device", ci, [vp, vp, vp, C.c_int64, ci, vp, C.c_size_t, vp, vp, vp, vp])
+        f("kmer_count_table_stats", ci, [vp, C.c_size_t, vp])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)
@@ -406,6 +411,22 @@ def streams_get_hits(sets, wl: Workload, desc_off, hits: Hits, allow_total_skip=
     off = np.ascontiguousarray(desc_off, dtype=np.int64)
     hs = (C.c_void_p * len(sets))(*[s.h if isinstance(s, SeqSet) else s for s in sets])
     lib.check(lib.streams_get_hits(hs, len(sets), wl.h, off.ctypes.data, int(allow_total_skip), cuda_stream, hits.h))
+
+
+def kmer_count_stats(pool, seq_off, lens, k=21, lib: Lib | None = None):
+    """t4_kmer_count_stats: (min, median, avg) of the canonical k-mer counts of every read, counts taken over all the reads
+    (KmerCount::AddCount + GetCountStatsAndTrim without trimming)."""
+    lib = lib or default_lib()
+    pool = np.ascontiguousarray(pool)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    n = len(lens)
+    mn = np.zeros(max(1, n), dtype=np.int32)
+    med = np.zeros(max(1, n), dtype=np.int32)
+    avg = np.zeros(max(1, n), dtype=np.float32)
+    lib.check(lib.kmer_count_stats(pool.ctypes.data, pool.nbytes, seq_off.ctypes.data, lens.ctypes.data, n, int(k),
+                                   mn.ctypes.data, med.ctypes.data, avg.ctypes.data))
+    return mn[:n], med[:n], avg[:n]
 
 
 ASSIGN_NOT_LISTED = -2

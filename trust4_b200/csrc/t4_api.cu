@@ -16,6 +16,7 @@
 
 #include "t4_engine.h"
 #include "t4_assign.h"
+#include "t4_kcount.h"
 
 #if T4_CUDA
 #include <cuda_runtime.h>
@@ -82,6 +83,20 @@ __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_aux_kernel( cha
 	cx.tid = threadIdx.x ;
 	cx.nt = blockDim.x ;
 	c_run_aux_op( cx, op ) ;
+}
+
+// k-mer counting / per-read count statistics (t4_kcount.h): persistent CTAs, reads handed out by an atomic cursor
+__global__ void __launch_bounds__( T4_MAX_NT ) t4_kcount_kernel( T4KcParams P, int stats )
+{
+	__shared__ T4KcSmem sm ;
+	T4KcCtx cx ;
+	cx.sm = &sm ;
+	cx.tid = threadIdx.x ;
+	cx.nt = blockDim.x ;
+	if ( stats )
+		kc_stats_body( cx, P ) ;
+	else
+		kc_count_body( cx, P ) ;
 }
 
 __global__ void t4_init_kernel( char *A, u64 base, T4InitParams ip )
@@ -2154,6 +2169,149 @@ int T4_API( assign_device_buffers )( t4_assign *a, void **assign, void **similar
 	if ( assign ) *assign = a->dAssign ;
 	if ( similarity ) *similarity = a->dSim ;
 	return 0 ;
+}
+
+// ---- canonical k-mer counts + per-read statistics (t4_kcount.h) ------------------------------------
+static int kc_launch( const T4KcParams &P, int stats, void *stream )
+{
+#if T4_CUDA
+	int sms = 148 ;
+	cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ;
+	CK( cudaMemsetAsync( (void *)(uintptr_t)P.ctrl, 0, 8, (cudaStream_t)stream ) ) ; // the read cursor
+	t4_kcount_kernel<<<sms * 8, T4_MAX_NT, 0, (cudaStream_t)stream>>>( P, stats ) ;
+	CK( cudaGetLastError() ) ;
+#else
+	*(u64 *)(uintptr_t)P.ctrl = 0 ;
+	T4KcSmem *sm = new T4KcSmem ;
+	T4KcCtx cx ;
+	cx.sm = sm ; cx.tid = 0 ; cx.nt = 1 ;
+	if ( stats )
+		kc_stats_body( cx, P ) ;
+	else
+		kc_count_body( cx, P ) ;
+	delete sm ;
+#endif
+	return 0 ;
+}
+
+// Device-pointer form: `pool`, `seq_off` (u64[n]), `len` (i32[n]) and the three outputs are DEVICE buffers (e.g. torch
+// tensors), `table` is a caller-provided device buffer of t4_kmer_count_table_bytes() bytes.  Asynchronous on cuda_stream.
+size_t T4_API( kmer_count_table_bytes )( int64_t n_kmer_instances )
+{
+	u64 cap = 1024 ;
+	while ( cap < 2 * (u64)( n_kmer_instances > 0 ? n_kmer_instances : 0 ) )
+		cap <<= 1 ;
+	return (size_t)( cap * 12 + 256 ) ;
+}
+
+int T4_API( kmer_count_stats_device )( const void *pool, const void *seq_off, const void *len, int64_t n, int kmer_length,
+	void *table, size_t table_bytes, void *min_cnt, void *median_cnt, void *avg_cnt, void *cuda_stream )
+{
+	int r = ensure_up() ;
+	if ( r ) return r ;
+	if ( n < 0 || kmer_length < 2 || kmer_length > 31 || table_bytes < 1024 * 12 + 256 )
+	{
+		set_err( "t4_kmer_count_stats: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	u64 cap = 1024 ;
+	while ( cap * 2 * 12 + 256 <= table_bytes )
+		cap <<= 1 ;
+	T4KcParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	char *t = (char *)table ;
+	P.keys = (u64)(uintptr_t)t ;
+	P.counts = (u64)(uintptr_t)( t + cap * 8 ) ;
+	P.ctrl = (u64)(uintptr_t)( t + cap * 12 ) ;
+	P.cap = cap ;
+	P.pool = (u64)(uintptr_t)pool ;
+	P.seqOff = (u64)(uintptr_t)seq_off ;
+	P.len = (u64)(uintptr_t)len ;
+	P.minCnt = (u64)(uintptr_t)min_cnt ;
+	P.medianCnt = (u64)(uintptr_t)median_cnt ;
+	P.avgCnt = (u64)(uintptr_t)avg_cnt ;
+	P.n = n ;
+	P.k = kmer_length ;
+#if T4_CUDA
+	CK( cudaMemsetAsync( table, 0, cap * 12 + 64, (cudaStream_t)cuda_stream ) ) ;
+#else
+	memset( table, 0, cap * 12 + 64 ) ;
+#endif
+	r = kc_launch( P, 0, cuda_stream ) ;
+	if ( !r ) r = kc_launch( P, 1, cuda_stream ) ;
+	return r ;
+}
+
+// Totals of the last call on this table (synchronises): stats[0] k-mers counted, [1] distinct k-mers, [2] table slots,
+// [3] 1 if the table overflowed (results invalid).
+int T4_API( kmer_count_table_stats )( const void *table, size_t table_bytes, uint64_t *stats )
+{
+	u64 cap = 1024 ;
+	while ( cap * 2 * 12 + 256 <= table_bytes )
+		cap <<= 1 ;
+	int r = dsync() ;
+	if ( r ) return r ;
+	u64 c[4] ;
+	r = d2h( c, (const char *)table + cap * 12, sizeof( c ) ) ;
+	if ( r ) return r ;
+	stats[0] = c[1] ; stats[1] = c[2] ; stats[2] = cap ; stats[3] = c[3] ;
+	return 0 ;
+}
+
+// Host form: KmerCount( kmer_length ).AddCount( read ) for every read, then GetCountStatsAndTrim( read, NULL, ... ) for
+// every read (main.cpp:404-440, 981-1010).  Reads longer than T4_MAX_READ_LEN are not supported (T4_E_UNSUPPORTED).
+int T4_API( kmer_count_stats )( const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, int64_t n,
+	int kmer_length, int32_t *min_cnt, int32_t *median_cnt, float *avg_cnt )
+{
+	int r = ensure_up() ;
+	if ( r ) return r ;
+	if ( n < 0 || !read_pool || !seq_off || !len || kmer_length < 2 || kmer_length > 31 )
+	{
+		set_err( "t4_kmer_count_stats: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	u64 inst = 0 ;
+	for ( i64 i = 0 ; i < n ; ++i )
+	{
+		if ( len[i] > T4_DEV_MAX_READ )
+		{
+			set_err( "t4_kmer_count_stats: read longer than the device limit" ) ;
+			return T4_E_UNSUPPORTED ;
+		}
+		if ( len[i] < 0 || seq_off[i] + (u64)len[i] > pool_bytes )
+		{
+			set_err( "t4_kmer_count_stats: record outside the pool" ) ;
+			return T4_E_INVAL ;
+		}
+		if ( len[i] >= kmer_length )
+			inst += (u64)( len[i] - kmer_length + 1 ) ;
+	}
+	if ( n == 0 )
+		return 0 ;
+	const size_t tb = T4_API( kmer_count_table_bytes )( (int64_t)inst ) ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t oPool = 0, oOff = al( pool_bytes + 16 ), oLen = oOff + al( (size_t)n * 8 ), oMin = oLen + al( (size_t)n * 4 ),
+		oMed = oMin + al( (size_t)n * 4 ), oAvg = oMed + al( (size_t)n * 4 ), oTab = oAvg + al( (size_t)n * 4 ), total = oTab + tb ;
+	void *p = 0 ;
+	r = dmalloc( &p, total ) ;
+	if ( r ) return r ;
+	char *b = (char *)p ;
+	r = h2d( b + oPool, read_pool, pool_bytes ) ;
+	if ( !r ) r = h2d( b + oOff, seq_off, (size_t)n * 8 ) ;
+	if ( !r ) r = h2d( b + oLen, len, (size_t)n * 4 ) ;
+	if ( !r ) r = T4_API( kmer_count_stats_device )( b + oPool, b + oOff, b + oLen, n, kmer_length, b + oTab, tb, b + oMin, b + oMed, b + oAvg, 0 ) ;
+	u64 st[4] = { 0, 0, 0, 0 } ;
+	if ( !r ) r = T4_API( kmer_count_table_stats )( b + oTab, tb, st ) ;
+	if ( !r && st[3] )
+	{
+		set_err( "t4_kmer_count_stats: count table overflow" ) ;
+		r = T4_E_INTERNAL ;
+	}
+	if ( !r && min_cnt ) r = d2h( min_cnt, b + oMin, (size_t)n * 4 ) ;
+	if ( !r && median_cnt ) r = d2h( median_cnt, b + oMed, (size_t)n * 4 ) ;
+	if ( !r && avg_cnt ) r = d2h( avg_cnt, b + oAvg, (size_t)n * 4 ) ;
+	dfree( p ) ;
+	return r ;
 }
 
 int T4_API( workload_results )( t4_workload *w, int32_t *ret_codes, int8_t *strands, int32_t *rescue_ret )
