@@ -585,8 +585,8 @@ def main():
                 q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 q0.record()
-                lib.check(lib.kmer_count_stats_device(dpool2.data_ptr(), doff.data_ptr(), dlen.data_ptr(), n_reads, 21, table.data_ptr(), tb,
-                                                      omn.data_ptr(), omed.data_ptr(), oavg.data_ptr(), None))
+                lib.check(lib.kmer_count_stats_device(dpool2.data_ptr(), None, doff.data_ptr(), dlen.data_ptr(), n_reads, 21, table.data_ptr(), tb,
+                                                      omn.data_ptr(), omed.data_ptr(), oavg.data_ptr(), None, None))
                 q1.record()
                 torch.cuda.synchronize()
                 kms.append(q0.elapsed_time(q1))

@@ -328,19 +328,23 @@ int t4_assign_device_buffers(t4_assign *a, void **assign, void **similarity);
 
 /* ---- canonical k-mer counts and per-read count statistics (the counting part of the pre-processing) --
  * KmerCount kmerCount(k); kmerCount.AddCount(read) for every read (KmerCount.hpp:64-97; main.cpp:404-440), then
- * kmerCount.GetCountStatsAndTrim(read, NULL, minCnt, medianCnt, avgCnt) for every read (KmerCount.hpp:177-288 with
- * qual == NULL, i.e. without the quality trimming; main.cpp:981-1010): min / median / average of the counts of the read's
- * canonical k-mers (a k-mer with an N does not count; no valid k-mer: -len; shorter than k: -1; any N: min 0).  These
- * three numbers order the reads (main.cpp:103-125) and pick the AddRead thresholds (main.cpp:1675-1694).
- * Host buffers; record i is read_pool[seq_off[i] .. seq_off[i] + len[i]).  Any output may be NULL. */
-int t4_kmer_count_stats(const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, int64_t n,
-                        int kmer_length, int32_t *min_cnt, int32_t *median_cnt, float *avg_cnt);
-/* The same on DEVICE buffers (all pointers; `table` = scratch of t4_kmer_count_table_bytes(total k-mer instances) bytes),
- * asynchronous on cuda_stream: two launches of t4_kcount_kernel (count, statistics). */
+ * kmerCount.GetCountStatsAndTrim(read, qual, minCnt, medianCnt, avgCnt) for every read (KmerCount.hpp:177-288;
+ * main.cpp:981-1010): with qualities (--trimLevel >= 1, the default) the low-quality tail behind the last k-mer seen more
+ * than once is cut first (new_len[i]: what is left, 0 = the driver drops the read), then min / median / average of the
+ * counts of the read's canonical k-mers (a k-mer with an N does not count; no valid k-mer: -len; shorter than k: -1; any
+ * N: min 0).  These numbers order the reads (main.cpp:103-125) and pick the AddRead thresholds (main.cpp:1675-1694).
+ * Host buffers; record i is read_pool[seq_off[i] .. seq_off[i] + len[i]) and qual_pool at the same offsets (NULL = the
+ * qual == NULL call of --trimLevel 0).  Any output may be NULL. */
+int t4_kmer_count_stats(const char *read_pool, const char *qual_pool, size_t pool_bytes, const uint64_t *seq_off,
+                        const int32_t *len, int64_t n, int kmer_length, int32_t *min_cnt, int32_t *median_cnt,
+                        float *avg_cnt, int32_t *new_len);
+/* The same on DEVICE buffers (all pointers; qual / new_len may be NULL; `table` = scratch of
+ * t4_kmer_count_table_bytes(capacity hint, at most the total number of k-mer instances) bytes), asynchronous on
+ * cuda_stream: two launches of t4_kcount_kernel (count, statistics). */
 size_t t4_kmer_count_table_bytes(int64_t n_kmer_instances);
-int t4_kmer_count_stats_device(const void *read_pool, const void *seq_off, const void *len, int64_t n, int kmer_length,
-                               void *table, size_t table_bytes, void *min_cnt, void *median_cnt, void *avg_cnt,
-                               void *cuda_stream);
+int t4_kmer_count_stats_device(const void *read_pool, const void *qual_pool, const void *seq_off, const void *len, int64_t n,
+                               int kmer_length, void *table, size_t table_bytes, void *min_cnt, void *median_cnt,
+                               void *avg_cnt, void *new_len, void *cuda_stream);
 /* stats[0] k-mers counted, [1] distinct k-mers, [2] table slots, [3] 1 = table overflow (results invalid).  Synchronises. */
 int t4_kmer_count_table_stats(const void *table, size_t table_bytes, uint64_t stats[4]);
 

@@ -610,13 +610,14 @@ void *t4ref_assign_pass( void *h, int kmerLength, const t4_read_desc *descs, con
 }
 
 // ---- k-mer counting ------------------------------------------
-// KmerCount( k ): AddCount of every read, then GetCountStatsAndTrim( read, NULL, ... ) of every read (main.cpp:404-440, 981-1010).
-int t4ref_kmer_count_stats( const char *pool, const uint64_t *seqOff, const int32_t *len, int64_t n, int k, int32_t *minCnt,
-	int32_t *medianCnt, float *avgCnt )
+// KmerCount( k ): AddCount of every read, then GetCountStatsAndTrim( read, qual, ... ) of every read (main.cpp:404-440,
+// 981-1010; qualPool == NULL: the qual == NULL call).  newLen[i] = strlen( read ) afterwards.
+int t4ref_kmer_count_stats( const char *pool, const char *qualPool, const uint64_t *seqOff, const int32_t *len, int64_t n, int k,
+	int32_t *minCnt, int32_t *medianCnt, float *avgCnt, int32_t *newLen )
 {
 	KmerCount kc( k ) ;
 	int maxLen = 0 ;
-	std::vector<char> buf ;
+	std::vector<char> buf, qbuf ;
 	for ( int64_t i = 0 ; i < n ; ++i )
 	{
 		buf.assign( pool + seqOff[i], pool + seqOff[i] + len[i] ) ;
@@ -630,10 +631,17 @@ int t4ref_kmer_count_stats( const char *pool, const uint64_t *seqOff, const int3
 	{
 		buf.assign( pool + seqOff[i], pool + seqOff[i] + len[i] ) ;
 		buf.push_back( '\0' ) ;
+		if ( qualPool )
+		{
+			qbuf.assign( qualPool + seqOff[i], qualPool + seqOff[i] + len[i] ) ;
+			qbuf.push_back( '\0' ) ;
+		}
 		int a = 0, b = 0 ;
 		float c = 0 ;
-		kc.GetCountStatsAndTrim( buf.data(), NULL, a, b, c ) ;
+		kc.GetCountStatsAndTrim( buf.data(), qualPool ? qbuf.data() : NULL, a, b, c ) ;
 		minCnt[i] = a ; medianCnt[i] = b ; avgCnt[i] = c ;
+		if ( newLen )
+			newLen[i] = (int)strlen( buf.data() ) ;
 	}
 	return 0 ;
 }

@@ -720,10 +720,34 @@ def check_kmer_count_stats(lib, ref, seed=101, n=1500, k=21):
     off = np.zeros(len(reads), dtype=np.uint64)
     off[1:] = np.cumsum(lens[:-1])
     pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
-    rmn, rmed, ravg = ref.kmer_count_stats(pool, off, lens, k)
-    gmn, gmed, gavg = api.kmer_count_stats(pool, off, lens, k, lib)
-    assert (gmn == rmn).all(), ("min", np.flatnonzero(gmn != rmn)[:5])
-    assert (gmed == rmed).all(), ("median", np.flatnonzero(gmed != rmed)[:5])
-    assert (gavg.view(np.uint32) == ravg.view(np.uint32)).all(), ("avg", np.flatnonzero(gavg != ravg)[:5])
-    assert (rmn < 0).sum() > 10 and (rmn == 0).sum() > 10 and (rmn > 1).sum() > 100 and rmed.max() > 20
+    # qualities: mostly good; a third of the N-free reads get a bad tail (Phred <= 15 from some position on, some sparse,
+    # some whole reads) so that the trimming rules fire: cut positions, reads cut below k (dropped), untouched reads
+    quals = []
+    for t in reads:
+        q = ["I"] * len(t)
+        if "N" not in t and len(t) > 30 and rng.random() < 0.35:
+            mode = int(rng.integers(0, 4))
+            st = int(rng.integers(0, len(t))) if mode != 3 else 0
+            for p in range(st, len(t)):
+                if mode == 1 and rng.random() < 0.5:
+                    continue
+                q[p] = "#$%&'()*+,-./0"[int(rng.integers(0, 14))]     # Phred 2..15
+            if mode == 2:
+                q[-1] = "I"
+        quals.append("".join(q))
+    qpool = np.frombuffer(("".join(quals) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    n_trim = 0
+    for qp in (None, qpool):
+        rmn, rmed, ravg, rnl = ref.kmer_count_stats(pool, off, lens, k, qual=qp)
+        gmn, gmed, gavg, gnl = api.kmer_count_stats(pool, off, lens, k, lib, qual=qp)
+        assert (gnl == rnl).all(), ("new length", qp is not None, np.flatnonzero(gnl != rnl)[:5])
+        assert (gmn == rmn).all(), ("min", qp is not None, np.flatnonzero(gmn != rmn)[:5])
+        assert (gmed == rmed).all(), ("median", qp is not None, np.flatnonzero(gmed != rmed)[:5])
+        assert (gavg.view(np.uint32) == ravg.view(np.uint32)).all(), ("avg", qp is not None, np.flatnonzero(gavg.view(np.uint32) != ravg.view(np.uint32))[:5])
+        if qp is None:
+            assert (rnl == lens).all()
+            assert (rmn < 0).sum() > 10 and (rmn == 0).sum() > 10 and (rmn > 1).sum() > 100 and rmed.max() > 20
+        else:
+            n_trim = int((rnl < lens).sum())
+            assert n_trim > 50 and ((rnl == 0) & (lens >= k)).sum() > 3
     return int(len(reads))

@@ -57,7 +57,8 @@ def lib():
         l.t4ref_release_shallow_contigs.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_input_novel_fa.argtypes = [C.c_void_p, C.c_char_p]
         l.t4ref_num_read.argtypes = [C.c_void_p, C.c_int]
-        l.t4ref_kmer_count_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.t4ref_kmer_count_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
         l.t4ref_input_seqset.restype = C.c_void_p
         l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_assign_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
@@ -204,8 +205,8 @@ def dp_pos_weight(tw, p):
     return sc, e
 
 
-def kmer_count_stats(pool, seq_off, lens, k=21):
-    """The reference's KmerCount over the reads: (min, median, avg) per read (KmerCount.hpp:64-97, 177-288, qual == NULL)."""
+def kmer_count_stats(pool, seq_off, lens, k=21, qual=None):
+    """The reference's KmerCount over the reads: (min, median, avg, new length) per read (KmerCount.hpp:64-97, 177-288)."""
     pool = np.ascontiguousarray(pool)
     seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
     lens = np.ascontiguousarray(lens, dtype=np.int32)
@@ -213,8 +214,12 @@ def kmer_count_stats(pool, seq_off, lens, k=21):
     mn = np.zeros(max(1, n), dtype=np.int32)
     med = np.zeros(max(1, n), dtype=np.int32)
     avg = np.zeros(max(1, n), dtype=np.float32)
-    lib().t4ref_kmer_count_stats(pool.ctypes.data, seq_off.ctypes.data, lens.ctypes.data, n, k, mn.ctypes.data, med.ctypes.data, avg.ctypes.data)
-    return mn[:n], med[:n], avg[:n]
+    nl = np.zeros(max(1, n), dtype=np.int32)
+    if qual is not None:
+        qual = np.ascontiguousarray(qual)
+    lib().t4ref_kmer_count_stats(pool.ctypes.data, qual.ctypes.data if qual is not None else None, seq_off.ctypes.data, lens.ctypes.data, n, k,
+                                 mn.ctypes.data, med.ctypes.data, avg.ctypes.data, nl.ctypes.data)
+    return mn[:n], med[:n], avg[:n], nl[:n]
 
 
 def assembled_list(ret, resc):

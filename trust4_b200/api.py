@@ -117,9 +117,9 @@ class Lib:
         f("assign_stats", ci, [vp, vp])
         f("assign_extended_set", vp, [vp, ci])
         f("assign_device_buffers", ci, [vp, C.POINTER(vp), C.POINTER(vp)])
-        f("kmer_count_stats", ci, [vp, C.c_size_t, vp, vp, C.c_int64, ci, vp, vp, vp])
+        f("kmer_count_stats", ci, [vp, vp, C.c_size_t, vp, vp, C.c_int64, ci, vp, vp, vp, vp])
         f("kmer_count_table_bytes", C.c_size_t, [C.c_int64])
-        f("kmer_count_stats_device", ci, [vp, vp, vp, C.c_int64, ci, vp, C.c_size_t, vp, vp, vp, vp])
+        f("kmer_count_stats_device", ci, [vp, vp, vp, vp, C.c_int64, ci, vp, C.c_size_t, vp, vp, vp, vp, vp])
         f("kmer_count_table_stats", ci, [vp, C.c_size_t, vp])
 
     def _f(self, name, restype, argtypes):
@@ -413,9 +413,9 @@ def streams_get_hits(sets, wl: Workload, desc_off, hits: Hits, allow_total_skip=
     lib.check(lib.streams_get_hits(hs, len(sets), wl.h, off.ctypes.data, int(allow_total_skip), cuda_stream, hits.h))
 
 
-def kmer_count_stats(pool, seq_off, lens, k=21, lib: Lib | None = None):
-    """t4_kmer_count_stats: (min, median, avg) of the canonical k-mer counts of every read, counts taken over all the reads
-    (KmerCount::AddCount + GetCountStatsAndTrim without trimming)."""
+def kmer_count_stats(pool, seq_off, lens, k=21, lib: Lib | None = None, qual=None):
+    """t4_kmer_count_stats: (min, median, avg, new_len) of the canonical k-mer counts of every read, counts taken over all
+    the reads (KmerCount::AddCount + GetCountStatsAndTrim; qual = None: without the quality trimming)."""
     lib = lib or default_lib()
     pool = np.ascontiguousarray(pool)
     seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
@@ -424,9 +424,13 @@ def kmer_count_stats(pool, seq_off, lens, k=21, lib: Lib | None = None):
     mn = np.zeros(max(1, n), dtype=np.int32)
     med = np.zeros(max(1, n), dtype=np.int32)
     avg = np.zeros(max(1, n), dtype=np.float32)
-    lib.check(lib.kmer_count_stats(pool.ctypes.data, pool.nbytes, seq_off.ctypes.data, lens.ctypes.data, n, int(k),
-                                   mn.ctypes.data, med.ctypes.data, avg.ctypes.data))
-    return mn[:n], med[:n], avg[:n]
+    nl = np.zeros(max(1, n), dtype=np.int32)
+    if qual is not None:
+        qual = np.ascontiguousarray(qual)
+        assert qual.nbytes == pool.nbytes
+    lib.check(lib.kmer_count_stats(pool.ctypes.data, qual.ctypes.data if qual is not None else None, pool.nbytes, seq_off.ctypes.data,
+                                   lens.ctypes.data, n, int(k), mn.ctypes.data, med.ctypes.data, avg.ctypes.data, nl.ctypes.data))
+    return mn[:n], med[:n], avg[:n], nl[:n]
 
 
 ASSIGN_NOT_LISTED = -2

@@ -2204,8 +2204,8 @@ size_t T4_API( kmer_count_table_bytes )( int64_t n_kmer_instances )
 	return (size_t)( cap * 12 + 256 ) ;
 }
 
-int T4_API( kmer_count_stats_device )( const void *pool, const void *seq_off, const void *len, int64_t n, int kmer_length,
-	void *table, size_t table_bytes, void *min_cnt, void *median_cnt, void *avg_cnt, void *cuda_stream )
+int T4_API( kmer_count_stats_device )( const void *pool, const void *qual, const void *seq_off, const void *len, int64_t n, int kmer_length,
+	void *table, size_t table_bytes, void *min_cnt, void *median_cnt, void *avg_cnt, void *new_len, void *cuda_stream )
 {
 	int r = ensure_up() ;
 	if ( r ) return r ;
@@ -2230,6 +2230,8 @@ int T4_API( kmer_count_stats_device )( const void *pool, const void *seq_off, co
 	P.minCnt = (u64)(uintptr_t)min_cnt ;
 	P.medianCnt = (u64)(uintptr_t)median_cnt ;
 	P.avgCnt = (u64)(uintptr_t)avg_cnt ;
+	P.qual = (u64)(uintptr_t)qual ;
+	P.newLen = (u64)(uintptr_t)new_len ;
 	P.n = n ;
 	P.k = kmer_length ;
 #if T4_CUDA
@@ -2258,10 +2260,10 @@ int T4_API( kmer_count_table_stats )( const void *table, size_t table_bytes, uin
 	return 0 ;
 }
 
-// Host form: KmerCount( kmer_length ).AddCount( read ) for every read, then GetCountStatsAndTrim( read, NULL, ... ) for
-// every read (main.cpp:404-440, 981-1010).  Reads longer than T4_MAX_READ_LEN are not supported (T4_E_UNSUPPORTED).
-int T4_API( kmer_count_stats )( const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, int64_t n,
-	int kmer_length, int32_t *min_cnt, int32_t *median_cnt, float *avg_cnt )
+// Host form: KmerCount( kmer_length ).AddCount( read ) for every read, then GetCountStatsAndTrim( read, qual, ... ) for
+// every read (main.cpp:404-440, 981-1010; qual_pool == NULL: no trimming).  Reads longer than T4_MAX_READ_LEN are not supported (T4_E_UNSUPPORTED).
+int T4_API( kmer_count_stats )( const char *read_pool, const char *qual_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len,
+	int64_t n, int kmer_length, int32_t *min_cnt, int32_t *median_cnt, float *avg_cnt, int32_t *new_len )
 {
 	int r = ensure_up() ;
 	if ( r ) return r ;
@@ -2290,16 +2292,19 @@ int T4_API( kmer_count_stats )( const char *read_pool, size_t pool_bytes, const 
 		return 0 ;
 	const size_t tb = T4_API( kmer_count_table_bytes )( (int64_t)inst ) ;
 	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
-	const size_t oPool = 0, oOff = al( pool_bytes + 16 ), oLen = oOff + al( (size_t)n * 8 ), oMin = oLen + al( (size_t)n * 4 ),
-		oMed = oMin + al( (size_t)n * 4 ), oAvg = oMed + al( (size_t)n * 4 ), oTab = oAvg + al( (size_t)n * 4 ), total = oTab + tb ;
+	const size_t oPool = 0, oQual = al( pool_bytes + 16 ), oOff = oQual + ( qual_pool ? al( pool_bytes + 16 ) : 0 ), oLen = oOff + al( (size_t)n * 8 ),
+		oMin = oLen + al( (size_t)n * 4 ), oMed = oMin + al( (size_t)n * 4 ), oAvg = oMed + al( (size_t)n * 4 ), oNew = oAvg + al( (size_t)n * 4 ),
+		oTab = oNew + al( (size_t)n * 4 ), total = oTab + tb ;
 	void *p = 0 ;
 	r = dmalloc( &p, total ) ;
 	if ( r ) return r ;
 	char *b = (char *)p ;
 	r = h2d( b + oPool, read_pool, pool_bytes ) ;
+	if ( !r && qual_pool ) r = h2d( b + oQual, qual_pool, pool_bytes ) ;
 	if ( !r ) r = h2d( b + oOff, seq_off, (size_t)n * 8 ) ;
 	if ( !r ) r = h2d( b + oLen, len, (size_t)n * 4 ) ;
-	if ( !r ) r = T4_API( kmer_count_stats_device )( b + oPool, b + oOff, b + oLen, n, kmer_length, b + oTab, tb, b + oMin, b + oMed, b + oAvg, 0 ) ;
+	if ( !r ) r = T4_API( kmer_count_stats_device )( b + oPool, qual_pool ? b + oQual : 0, b + oOff, b + oLen, n, kmer_length, b + oTab, tb, b + oMin,
+		b + oMed, b + oAvg, b + oNew, 0 ) ;
 	u64 st[4] = { 0, 0, 0, 0 } ;
 	if ( !r ) r = T4_API( kmer_count_table_stats )( b + oTab, tb, st ) ;
 	if ( !r && st[3] )
@@ -2310,6 +2315,7 @@ int T4_API( kmer_count_stats )( const char *read_pool, size_t pool_bytes, const 
 	if ( !r && min_cnt ) r = d2h( min_cnt, b + oMin, (size_t)n * 4 ) ;
 	if ( !r && median_cnt ) r = d2h( median_cnt, b + oMed, (size_t)n * 4 ) ;
 	if ( !r && avg_cnt ) r = d2h( avg_cnt, b + oAvg, (size_t)n * 4 ) ;
+	if ( !r && new_len ) r = d2h( new_len, b + oNew, (size_t)n * 4 ) ;
 	dfree( p ) ;
 	return r ;
 }

@@ -2,9 +2,10 @@
 // stage-1 pre-processing):
 //
 //   KmerCount kmerCount( 21 ) ; kmerCount.AddCount( read ) for every read           KmerCount.hpp:64-97, main.cpp:404-440
-//   kmerCount.GetCountStatsAndTrim( read, NULL, minCnt, medianCnt, avgCnt )          KmerCount.hpp:177-288, main.cpp:981-1010
+//   kmerCount.GetCountStatsAndTrim( read, qual, minCnt, medianCnt, avgCnt )          KmerCount.hpp:177-288, main.cpp:981-1010
 //
-// (qual == NULL: the statistics without the quality trimming).  minCnt / medianCnt / avgCnt order the reads
+// (qual == NULL with --trimLevel 0; otherwise the low-quality tail of the read is cut first, KmerCount.hpp:241-271, and
+// the statistics cover what is left).  minCnt / medianCnt / avgCnt order the reads
 // (main.cpp:103-125) and set the similarity thresholds of the AddRead loop (main.cpp:1675-1694).
 //
 // The reference keeps 1 000 003 std::maps; here the counts live in one open-addressing table in HBM
@@ -31,6 +32,8 @@ struct T4KcParams
 	u64 len ;              // i32[n]
 	u64 minCnt, medianCnt ; // i32[n] out
 	u64 avgCnt ;           // f32[n] out
+	u64 qual ;             // ASCII qualities, same offsets as the reads; 0 = GetCountStatsAndTrim( read, NULL, ... ): no trimming
+	u64 newLen ;           // i32[n] out (may be 0): length of the read after the quality trimming
 	u64 ctrl ;             // u64[4]: [0] read cursor, [1] k-mers inserted, [2] distinct k-mers, [3] table full flag
 	i64 n ;
 	int k ;
@@ -206,6 +209,8 @@ T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 			{
 				minCnt[r] = medianCnt[r] = -1 ; // KmerCount.hpp:196-200 (longer than the device limit: not supported, flagged by the host)
 				avgCnt[r] = -1.0f ;
+				if ( P.newLen )
+					t4_x<int32_t>( P.newLen )[r] = len ;
 			}
 			continue ;
 		}
@@ -239,33 +244,75 @@ T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 				sm->c[o++] = (int)sm->valid[q] ;
 		T4_KC_SYNC() ;
 		const int kk = (int)total ;
+		int32_t *newLen = t4_x<int32_t>( P.newLen ) ;
 		if ( kk == 0 )
 		{
 			if ( cx.tid == 0 )
 			{
 				minCnt[r] = medianCnt[r] = -len ; // KmerCount.hpp:229-239
 				avgCnt[r] = (float)( -len ) ;
+				if ( newLen )
+					newLen[r] = P.qual ? 0 : len ; // `if ( qual != NULL ) read[0] = '\0'`
 			}
 			continue ;
 		}
-		// min, sum, and the element of sorted rank kk / 2
+		// quality trimming (KmerCount.hpp:241-271), serial: the tail behind the last k-mer seen more than once is scanned from
+		// the end; the read is cut at the leftmost position where the bad bases (Phred <= 15) reach 10 % of the tail
+		int kUse = kk, trimStart = -1 ;
+		if ( P.qual )
+		{
+			if ( cx.tid == 0 )
+			{
+				const char *q = t4_x<char>( P.qual ) + t4_x<u64>( P.seqOff )[r] ;
+				int i ;
+				for ( i = kk - 1 ; i >= 0 ; --i )
+					if ( sm->c[i] > 1 )
+						break ;
+				++i ;
+				int badCnt = 0, ts = -1 ;
+				for ( int j = len - 1 ; j >= i + P.k - 1 ; --j )
+					if ( q[j] - 32 <= 15 )
+					{
+						++badCnt ;
+						if ( badCnt >= 0.1 * ( len - j ) )
+							ts = j ;
+					}
+				int ku = kk ;
+				if ( ts > 0 )
+					ku = ts - P.k + 1 ;
+				if ( ts > 0 && ts < P.k )
+					ku = 0 ;
+				if ( ku > kk )
+					ku = kk ; // only with N's in a trimmed read: the reference then sorts stale entries of its shared buffer (undefined)
+				sm->bi[2] = ku ;
+				sm->bi[3] = ts ;
+			}
+			T4_KC_SYNC() ;
+			kUse = sm->bi[2] ;
+			trimStart = sm->bi[3] ;
+			T4_KC_SYNC() ;
+		}
+		// min and the element of sorted rank kUse / 2 over the first kUse counts; the sum runs over ALL counts (the reference
+		// sums before it trims, KmerCount.hpp:224, 274)
 		int mn = 0x7fffffff ;
 		u32 sum = 0 ;
 		int med = -1 ;
 		for ( int i = cx.tid ; i < kk ; i += cx.nt )
 		{
 			const int v = sm->c[i] ;
+			sum += (u32)v ;
+			if ( i >= kUse )
+				continue ;
 			if ( v < mn )
 				mn = v ;
-			sum += (u32)v ;
 			int rank = 0 ;
-			for ( int j = 0 ; j < kk ; ++j )
+			for ( int j = 0 ; j < kUse ; ++j )
 			{
 				const int w = sm->c[j] ;
 				if ( w < v || ( w == v && j < i ) )
 					++rank ;
 			}
-			if ( rank == kk / 2 )
+			if ( rank == kUse / 2 )
 				med = v ;
 		}
 		// CTA reductions through shared memory (one slot per thread)
@@ -284,12 +331,17 @@ T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 		u32 sumTotal ;
 		kc_scan( cx, sum, sumTotal ) ;
 		if ( med >= 0 )
-			sm->bi[1] = med ; // exactly one thread holds the rank kk / 2 element
+			sm->bi[1] = med ; // exactly one thread holds the rank kUse / 2 element
 		T4_KC_SYNC() ;
 		if ( cx.tid == 0 )
 		{
-			int minCount = sm->bi[0] ;
-			for ( int i = 0 ; i < len ; ++i ) // KmerCount.hpp:275-283
+			const bool dropped = trimStart > 0 && trimStart < P.k ; // read[0] = '\0': the driver discards the read
+			int minCount = kUse > 0 ? sm->bi[0] : sm->c[0] ;          // std::sort over nothing: c[0] is the first count as it stands
+			const int medianCount = kUse > 0 ? sm->bi[1] : sm->c[0] ;
+			for ( int i = 0 ; i < len ; ++i ) // KmerCount.hpp:275-283: over the ORIGINAL length; the cut only overwrote read[trimStart] (and read[0])
+			{
+				if ( ( trimStart > 0 && i == trimStart ) || ( dropped && i == 0 ) )
+					continue ;
 				if ( sm->read[i] == 'N' )
 				{
 					if ( minCount >= 0 )
@@ -297,9 +349,12 @@ T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 					else if ( minCount <= 0 )
 						--minCount ;
 				}
+			}
 			minCnt[r] = minCount ;
-			medianCnt[r] = sm->bi[1] ;
-			avgCnt[r] = (float)( (int)sumTotal / (double)kk ) ; // `avgCount = sum / (double)k` into a float, KmerCount.hpp:274
+			medianCnt[r] = medianCount ;
+			avgCnt[r] = (float)( (int)sumTotal / (double)kUse ) ; // `avgCount = sum / (double)k` into a float, KmerCount.hpp:274 (k = 0: inf)
+			if ( newLen )
+				newLen[r] = trimStart > 0 ? ( dropped ? 0 : trimStart ) : len ;
 		}
 	}
 }
