@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """Condense an ncu report for profiles/: the raw page as CSV (one launch) plus a short key-metric text.
 
-    python bench/ncu_extract.py gpurun_out/x.ncu-rep profiles/r2_<name>      -> <name>_full_raw.csv, <name>_key_metrics.txt,
-                                                                               <name>_top_source_lines.txt"""
+    python bench/ncu_extract.py gpurun_out/x.ncu-rep profiles/r2_<name> [launch]   -> <name>_full_raw.csv, <name>_key_metrics.txt,
+                                                                                     <name>_top_source_lines.txt
+`launch`: index of the launch inside the report (default 0)."""
 import csv
 import subprocess
 import sys
@@ -18,10 +19,13 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    open(out + "_full_raw.csv", "w").write(raw)
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + which]
+    with open(out + "_full_raw.csv", "w") as f:      # header, units and the selected launch only
+        w = csv.writer(f)
+        w.writerows([hdr, units, vals])
     with open(out + "_key_metrics.txt", "w") as f:
         f.write("kernel: %s\n" % vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "")
         for k in KEYS:
@@ -37,7 +41,9 @@ def main():
                     continue
                 if v > 0.2:
                     f.write("  %-28s %.2f\n" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    launch_id = vals[hdr.index("ID")] if "ID" in hdr else str(which)
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + (["--launch-skip", str(which), "--launch-count", "1"] if which else []),
+                         capture_output=True, text=True).stdout
     tmp = out + "_src.tmp.csv"
     open(tmp, "w").write(src)
     top = subprocess.run([sys.executable, __file__.replace("ncu_extract.py", "ncu_top_lines.py"), tmp, "40"], capture_output=True, text=True).stdout
