@@ -44,7 +44,8 @@ def run(exe, args, out, env=None):
     p = subprocess.run([exe] + args + ["-o", out], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env, timeout=3600)
     wall = time.perf_counter() - t0
     log = p.stderr.decode(errors="replace")
-    return {"rc": p.returncode, "wall_s": wall, "addread_loop_s_from_log": loop_seconds(log)}
+    return {"rc": p.returncode, "wall_s": wall, "addread_loop_s_from_log": loop_seconds(log),
+            "assign_pass_on_device": "AssignRead pass on the device" in log}
 
 
 def contiguity(cl, rd, prefix):

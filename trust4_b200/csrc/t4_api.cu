@@ -85,14 +85,14 @@ __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_aux_kernel( cha
 	c_run_aux_op( cx, op ) ;
 }
 
-// k-mer counting / per-read count statistics (t4_kcount.h): persistent CTAs, reads handed out by an atomic cursor
+// k-mer counting / per-read count statistics (t4_kcount.h): persistent warps, batches of reads handed out by an atomic cursor
 __global__ void __launch_bounds__( T4_MAX_NT ) t4_kcount_kernel( T4KcParams P, int stats )
 {
-	__shared__ T4KcSmem sm ;
+	__shared__ T4KcSmem sm[T4_MAX_NT / T4_KC_GROUP] ;
 	T4KcCtx cx ;
-	cx.sm = &sm ;
-	cx.tid = threadIdx.x ;
-	cx.nt = blockDim.x ;
+	cx.sm = &sm[threadIdx.x / T4_KC_GROUP] ;
+	cx.tid = threadIdx.x % T4_KC_GROUP ;
+	cx.nt = T4_KC_GROUP ;
 	if ( stats )
 		kc_stats_body( cx, P ) ;
 	else
@@ -2178,7 +2178,7 @@ static int kc_launch( const T4KcParams &P, int stats, void *stream )
 	int sms = 148 ;
 	cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ;
 	CK( cudaMemsetAsync( (void *)(uintptr_t)P.ctrl, 0, 8, (cudaStream_t)stream ) ) ; // the read cursor
-	t4_kcount_kernel<<<sms * 8, T4_MAX_NT, 0, (cudaStream_t)stream>>>( P, stats ) ;
+	t4_kcount_kernel<<<sms * 10, T4_MAX_NT, 0, (cudaStream_t)stream>>>( P, stats ) ; // 40 warps per SM (21 KB of shared memory per CTA)
 	CK( cudaGetLastError() ) ;
 #else
 	*(u64 *)(uintptr_t)P.ctrl = 0 ;

@@ -10,13 +10,16 @@
 //
 // The reference keeps 1 000 003 std::maps; here the counts live in one open-addressing table in HBM
 // (u64 key = canonical code + 1, u32 count; load factor <= 1/2) filled with one atomicCAS + one atomicAdd per k-mer.
-// Both kernels are written against the engine's (tid, nt, barrier) abstraction, so the same source runs as CTAs of
-// 128 threads on the GPU and as one emulated thread in the test-only emulation build:
-//   count  a CTA takes reads in turn; thread q encodes the k-mer at position q (2 bits per base, N-free window
-//          = KmerCode::IsValid), takes min(code, reverse complement) = GetCanonicalKmerCode and inserts it;
-//   stats  a CTA takes reads in turn; thread q looks the k-mer at position q up into shared memory, then the
-//          median is found by rank counting (the element with exactly m/2 smaller-or-earlier elements is
-//          c[m/2] of the sorted array), min and sum by a CTA reduction; the N rules of KmerCount.hpp:275-283 follow.
+// Both kernels are written against a (lane, group size, group barrier) abstraction: on the GPU a group is a WARP that
+// owns a read (persistent warps draw batches of reads from an atomic cursor; no CTA barrier anywhere), in the test-only
+// emulation build it is one thread:
+//   count  the read becomes one code byte per base in shared memory; a lane owns a contiguous block of positions and
+//          rolls the k-mer code and its reverse complement along it (KmerCode::Append; N-free window = IsValid;
+//          min of the two = GetCanonicalKmerCode) and inserts every valid k-mer;
+//   stats  the same walk with a lookup per k-mer; the counts of the valid k-mers are compacted in position order
+//          (scan over the lanes), the median is found by rank counting (the element with exactly m/2 smaller-or-earlier
+//          elements is c[m/2] of the sorted array), min and sum by a group reduction; the trimming and the N rules of
+//          KmerCount.hpp:241-283 follow.
 #ifndef T4_KCOUNT_H
 #define T4_KCOUNT_H
 
@@ -42,85 +45,127 @@ struct T4KcParams
 
 #define T4_KC_MAX_POS T4_DEV_MAX_READ
 #define T4_KC_MAX_PROBES 4096      /* linear-probe bound: at load <= 1/2 clusters are a few slots long; beyond this the table is treated as full */
+#define T4_KC_GROUP 32             /* threads that share a read: one warp (first version: a CTA of 128 -- 36 % of its stall samples were
+                                      CTA barriers and the cursor round trip, ncu profiles/r2_kcount_kernel_*) */
+#define T4_KC_BATCH 4              /* reads per cursor step */
 
-struct T4KcSmem
+struct T4KcSmem                    // per group (warp)
 {
-	char read[T4_DEV_MAX_READ + 8] ;
-	int c[T4_KC_MAX_POS] ;         // counts of the valid k-mers of the current read, in position order
-	u32 valid[T4_KC_MAX_POS] ;     // exclusive prefix: slot of position q among the valid ones
-	u32 scan[T4_MAX_NT + 4] ;
+	unsigned char code[T4_DEV_MAX_READ + 8] ; // the current read, one byte per base: A 0 C 1 G 2 T 3 (anything else 3, like nucToNum & 3), N 4
+	int c[T4_KC_MAX_POS] ;         // counts of the valid k-mers of the current read, compacted in position order
+	u32 valid[T4_KC_MAX_POS] ;     // count at position q, 0 = the k-mer at q holds an N
+	u32 scan[T4_KC_GROUP + 4] ;
 	u64 bu[2] ;
 	int bi[8] ;
 } ;
 
 T4_HD inline u64 t4_kc_hash( u64 key, u64 cap ) { return ( ( key * 0x9E3779B97F4A7C15ull ) >> 20 ) & ( cap - 1 ) ; }
 
-// KmerCode::Append over s[q .. q + k) + GetCanonicalKmerCode (KmerCode.hpp:94-109, 52-67).  false: the window holds an N.
-T4_HD inline bool t4_kc_canonical( const char *s, int q, int k, u64 *out )
+// nucToNum[ c - 'A' ] & 3 (main.cpp:39-42) with N kept apart; selects, no branches
+T4_HD inline unsigned char t4_kc_code( char c )
 {
-	u64 fw = 0, rc = 0 ;
-	for ( int j = 0 ; j < k ; ++j )
+	return (unsigned char)( c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 3 ) ;
+}
+
+// Rolling KmerCode over the base codes of a read (KmerCode::Append, KmerCode.hpp:94-109) with the canonical code
+// (GetCanonicalKmerCode, KmerCode.hpp:52-67: min of the code and its reverse complement) available at every position.
+// A thread owns a contiguous block of positions: k - 1 bases of run-in, then one step per position.  The first version
+// rebuilt every k-mer from scratch with a branch per character: 60 % of the kernel's instructions (ncu source view).
+struct T4KcRoll
+{
+	u64 fw, rc, mask ;
+	int lastN ;                    // position of the last N seen, -1 = none
+	int top ;                      // 2 * (k - 1)
+} ;
+
+T4_HD inline void t4_kc_roll_start( T4KcRoll &R, const unsigned char *code, int q0, int k )
+{
+	R.fw = R.rc = 0 ;
+	R.mask = k < 32 ? ( ( 1ull << ( 2 * k ) ) - 1ull ) : ~0ull ;
+	R.lastN = -1 ;
+	R.top = 2 * ( k - 1 ) ;
+	for ( int j = 0 ; j < k - 1 ; ++j )
 	{
-		const char ch = s[q + j] ;
-		if ( ch == 'N' )
-			return false ;
-		const u64 x = (u64)t4_nuc( ch ) ;
-		fw = ( fw << 2 ) | x ;
-		rc |= ( 3ull - x ) << ( 2 * j ) ;
+		const unsigned x = code[q0 + j] ;
+		if ( x == 4 )
+			R.lastN = q0 + j ;
+		R.fw = ( R.fw << 2 ) | ( x & 3 ) ;
+		R.rc |= (u64)( 3 - ( x & 3 ) ) << ( 2 * ( j + 1 ) ) ; // one slot high: the first step shifts it into place
 	}
-	*out = rc < fw ? rc : fw ;
-	return true ;
+}
+
+// advance to the k-mer starting at q; false: it holds an N (KmerCode::IsValid)
+T4_HD inline bool t4_kc_roll_step( T4KcRoll &R, const unsigned char *code, int q, int k, u64 *canonical )
+{
+	const unsigned x = code[q + k - 1] ;
+	if ( x == 4 )
+		R.lastN = q + k - 1 ;
+	R.fw = ( ( R.fw << 2 ) | ( x & 3 ) ) & R.mask ;
+	R.rc = ( R.rc >> 2 ) | ( (u64)( 3 - ( x & 3 ) ) << R.top ) ;
+	*canonical = R.rc < R.fw ? R.rc : R.fw ;
+	return R.lastN < q ;
 }
 
 struct T4KcCtx
 {
 	T4KcSmem *sm ;
-	int tid, nt ;
+	int tid, nt ;                  // lane and size of the group that shares a read (a warp; one thread in the emulation)
 } ;
 
 #if T4_CUDA
-#define T4_KC_SYNC() __syncthreads()
+#define T4_KC_SYNC() __syncwarp()
 #else
 #define T4_KC_SYNC() ((void)0)
 #endif
 
-// next read of this CTA (atomic cursor); -1 = none left.  Collective.
-T4_D inline i64 kc_next_read( T4KcCtx &cx, const T4KcParams &P )
+// next batch of reads of this group (atomic cursor): first record, -1 = none left.  Collective.
+T4_D inline i64 kc_next_batch( T4KcCtx &cx, const T4KcParams &P )
 {
 	T4_KC_SYNC() ;
 	if ( cx.tid == 0 )
-		cx.sm->bu[0] = t4_atomic_add( t4_x<u64>( P.ctrl ), 1ull ) ;
+		cx.sm->bu[0] = t4_atomic_add( t4_x<u64>( P.ctrl ), (u64)T4_KC_BATCH ) ;
 	T4_KC_SYNC() ;
 	const u64 r = cx.sm->bu[0] ;
+	T4_KC_SYNC() ;
 	return r < (u64)P.n ? (i64)r : -1 ;
 }
 
 T4_D inline void kc_load_read( T4KcCtx &cx, const T4KcParams &P, i64 r, int len )
 {
 	const char *src = t4_x<char>( P.pool ) + t4_x<u64>( P.seqOff )[r] ;
+	T4_KC_SYNC() ; // the previous read is done with
 	for ( int i = cx.tid ; i < len ; i += cx.nt )
-		cx.sm->read[i] = src[i] ;
+		cx.sm->code[i] = t4_kc_code( src[i] ) ;
 	T4_KC_SYNC() ;
 }
 
-// KmerCount::AddCount for the reads this CTA draws
+// KmerCount::AddCount for the reads this group draws
 T4_D inline void kc_count_body( T4KcCtx &cx, const T4KcParams &P )
 {
 	u64 *keys = t4_x<u64>( P.keys ) ;
 	u32 *counts = t4_x<u32>( P.counts ) ;
 	u64 *ctrl = t4_x<u64>( P.ctrl ) ;
 	u64 inserted = 0, fresh = 0 ;
-	for ( i64 r = kc_next_read( cx, P ) ; r >= 0 ; r = kc_next_read( cx, P ) )
+	for ( i64 r0 = kc_next_batch( cx, P ) ; r0 >= 0 ; r0 = kc_next_batch( cx, P ) )
+	for ( i64 r = r0 ; r < r0 + T4_KC_BATCH && r < P.n ; ++r )
 	{
 		const int len = t4_x<int32_t>( P.len )[r] ;
 		if ( len < P.k || len > T4_DEV_MAX_READ )
 			continue ;
 		kc_load_read( cx, P, r, len ) ;
 		const int m = len - P.k + 1 ;
-		for ( int q = cx.tid ; q < m ; q += cx.nt )
+		const int chunk = ( m + cx.nt - 1 ) / cx.nt ;
+		int a = chunk * cx.tid, b = a + chunk ;
+		if ( a > m ) a = m ;
+		if ( b > m ) b = m ;
+		if ( a >= b )
+			continue ;
+		T4KcRoll R ;
+		t4_kc_roll_start( R, cx.sm->code, a, P.k ) ;
+		for ( int q = a ; q < b ; ++q )
 		{
 			u64 code ;
-			if ( !t4_kc_canonical( cx.sm->read, q, P.k, &code ) )
+			if ( !t4_kc_roll_step( R, cx.sm->code, q, P.k, &code ) )
 				continue ;
 			const u64 key = code + 1 ;
 			u64 s = t4_kc_hash( key, P.cap ) ;
@@ -194,13 +239,14 @@ T4_D inline u32 kc_scan( T4KcCtx &cx, u32 v, u32 &total )
 	return base ;
 }
 
-// KmerCount::GetCountStatsAndTrim( read, NULL, ... ) for the reads this CTA draws
+// KmerCount::GetCountStatsAndTrim( read, qual, ... ) for the reads this group draws
 T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 {
 	T4KcSmem *sm = cx.sm ;
 	int32_t *minCnt = t4_x<int32_t>( P.minCnt ), *medianCnt = t4_x<int32_t>( P.medianCnt ) ;
 	float *avgCnt = t4_x<float>( P.avgCnt ) ;
-	for ( i64 r = kc_next_read( cx, P ) ; r >= 0 ; r = kc_next_read( cx, P ) )
+	for ( i64 r0 = kc_next_batch( cx, P ) ; r0 >= 0 ; r0 = kc_next_batch( cx, P ) )
+	for ( i64 r = r0 ; r < r0 + T4_KC_BATCH && r < P.n ; ++r )
 	{
 		const int len = t4_x<int32_t>( P.len )[r] ;
 		if ( len < P.k || len > T4_DEV_MAX_READ )
@@ -223,10 +269,13 @@ T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 		if ( a > m ) a = m ;
 		if ( b > m ) b = m ;
 		u32 nv = 0 ;
+		T4KcRoll R ;
+		if ( a < b )
+			t4_kc_roll_start( R, sm->code, a, P.k ) ;
 		for ( int q = a ; q < b ; ++q )
 		{
 			u64 code ;
-			if ( t4_kc_canonical( sm->read, q, P.k, &code ) )
+			if ( t4_kc_roll_step( R, sm->code, q, P.k, &code ) )
 			{
 				int c = (int)kc_lookup( P, code ) ;
 				if ( c <= 0 )
@@ -342,7 +391,7 @@ T4_D inline void kc_stats_body( T4KcCtx &cx, const T4KcParams &P )
 			{
 				if ( ( trimStart > 0 && i == trimStart ) || ( dropped && i == 0 ) )
 					continue ;
-				if ( sm->read[i] == 'N' )
+				if ( sm->code[i] == 4 )
 				{
 					if ( minCount >= 0 )
 						minCount = 0 ;
