@@ -348,6 +348,31 @@ int t4_kmer_count_stats_device(const void *read_pool, const void *qual_pool, con
 /* stats[0] k-mers counted, [1] distinct k-mers, [2] table slots, [3] 1 = table overflow (results invalid).  Synchronises. */
 int t4_kmer_count_table_stats(const void *table, size_t table_bytes, uint64_t stats[4]);
 
+/* ---- stage-0 candidate extraction against a reference gene set (fastq-extractor's predicate) --------
+ * `SeqSet refSet(k); refSet.InputRefFa(fasta)` (FastqExtractor.cpp:313-318; SeqSet.hpp:2673-2864 with isIMGT == false:
+ * ids with "/OR" skipped except D genes, '.' removed, every character that is not an upper-case A/C/G/T becomes N,
+ * identical sequences kept once with their names joined by '|') as one indexed set on the device.  Plain-text FASTA. */
+typedef struct t4_refset t4_refset;
+t4_refset *t4_refset_create_from_fa(const char *fasta_path, int kmer_length);
+void t4_refset_free(t4_refset *r);
+int t4_refset_size(t4_refset *r);                      /* sequences kept */
+const char *t4_refset_name(t4_refset *r, int i);       /* SeqSet::GetSeqName */
+t4_seqset *t4_refset_seqset(t4_refset *r);             /* the set itself (owned by r), e.g. for t4_seqset_get_hits */
+int t4_refset_set_hit_len_required(t4_refset *r, int l); /* SeqSet::SetHitLenRequired, FastqExtractor.cpp:455 (27, or 23, or readLen / 5) */
+int t4_refset_set_radius(t4_refset *r, int radius);      /* SeqSet::SetRadius, SeqSet.hpp:2596 (default 10) */
+/* For every read: low_complexity_out[i] = IsLowComplexity(read) (FastqExtractor.cpp:106-127) and strand_out[i] =
+ * refSet->HasHitInSet(read, 0) (SeqSet.hpp:3144-3327: 0 no hit, +1 / -1 the strand of the best chain of seed hits on one
+ * gene -- buckets per (strand, gene), GetOverlapsFromHits with the reference-sequence rules: diagonal windows of `radius`,
+ * longest increasing subsequence, hit length on read and gene >= hitLenRequired).  fastq-extractor keeps a read (pair)
+ * iff `!low && strand != 0` for the read or its mate (IsGoodCandidate, FastqExtractor.cpp:129-134, 211-219).
+ * Host buffers; stats (may be NULL): [0] reads with a hit, [1] low-complexity reads. */
+int t4_refset_scan(t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len,
+                   int64_t n, int8_t *strand_out, uint8_t *low_complexity_out, uint64_t stats[2]);
+/* The same on DEVICE buffers (ctrl: 64 bytes of device scratch; afterwards u64 ctrl[1] = reads with a hit, ctrl[2] =
+ * low-complexity reads); n_workers CTAs (0 = one resident wave); asynchronous on cuda_stream. */
+int t4_refset_scan_device(t4_refset *r, const void *read_pool, const void *seq_off, const void *len, int64_t n,
+                          void *strand_out, void *low_complexity_out, void *ctrl, int n_workers, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -646,4 +646,47 @@ int t4ref_kmer_count_stats( const char *pool, const char *qualPool, const uint64
 	return 0 ;
 }
 
+// ---- stage-0 candidate extraction ----------------------------
+// `SeqSet refSet( k ) ; refSet.InputRefFa( file )` (FastqExtractor.cpp:313-318)
+void *t4ref_refset_create( const char *fasta, int k )
+{
+	SeqSet *s = new SeqSet( k ) ;
+	s->InputRefFa( (char *)fasta ) ;
+	return s ;
+}
+const char *t4ref_seq_name( void *h, int i ) { return ((SeqSet *)h)->seqs[i].name ; }
+int t4ref_seq_count( void *h ) { return (int)((SeqSet *)h)->seqs.size() ; }
+void t4ref_set_radius( void *h, int r ) { ((SeqSet *)h)->SetRadius( r ) ; }
+// int SeqSet::HasHitInSet( char *read, int mode ), SeqSet.hpp:3144
+int t4ref_has_hit_in_set( void *h, const char *read, int mode )
+{
+	char *r = strdup( read ) ;
+	int ret = ((SeqSet *)h)->HasHitInSet( r, mode ) ;
+	free( r ) ;
+	return ret ;
+}
+// bool IsLowComplexity( char *seq ), FastqExtractor.cpp:106-127 -- a function of the extractor's main file, which cannot
+// be included (it defines main); restated line by line.
+int t4ref_is_low_complexity( const char *seq )
+{
+	int cnt[5] = {0, 0, 0, 0, 0} ;
+	int i ;
+	for ( i = 0 ; seq[i] ; ++i )
+	{
+		if ( seq[i] == 'N' )
+			++cnt[4] ;
+		else
+			++cnt[ nucToNum[ seq[i] - 'A' ] ] ;
+	}
+	if ( cnt[0] >= i / 2 || cnt[1] >= i / 2 || cnt[2] >= i / 2 || cnt[3] >= i / 2 || cnt[4] >= i / 10 )
+		return 1 ;
+	int lowCnt = 0 ;
+	for ( i = 0 ; i < 4 ; ++i )
+		if ( cnt[i] <= 2 )
+			++lowCnt ;
+	if ( lowCnt >= 2 )
+		return 1 ;
+	return 0 ;
+}
+
 } // extern "C"

@@ -751,3 +751,112 @@ def check_kmer_count_stats(lib, ref, seed=101, n=1500, k=21):
             n_trim = int((rnl < lens).sum())
             assert n_trim > 50 and ((rnl == 0) & (lens >= k)).sum() > 3
     return int(len(reads))
+
+
+def write_gene_fasta(path, messy=True):
+    """The bundled gene pool as FASTA; `messy` adds what InputRefFa has to clean up: IMGT '.' gaps, lower case, ambiguity
+    codes, a duplicated sequence under another name, the same record twice, a '/OR' pseudo-gene, multi-line records."""
+    pool = synth.load_gene_pool()
+    recs = []
+    for ch in pool.values():
+        for seg in ch.values():
+            for name, seq in seg:
+                recs.append((name, seq))
+    out = []
+    for i, (name, seq) in enumerate(recs):
+        s = seq
+        if messy and i % 7 == 0:
+            s = s[:30] + "..." + s[30:60] + "......" + s[60:]
+        if messy and i % 11 == 0 and len(s) > 80:
+            s = s[:70] + s[70:75].lower() + s[75:]
+        if messy and i % 13 == 0 and len(s) > 90:
+            s = s[:85] + "RY" + s[87:]
+        out.append((name, s))
+    if messy:
+        out.insert(5, ("IGHV9-99*01 extra words", recs[2][1]))                 # same sequence as another gene: names joined
+        out.insert(9, (recs[3][0], recs[3][1]))                                 # the same record again: dropped
+        out.insert(12, ("IGHV3/OR16-9*01", recs[20][1][:200] + "ACGTACGTTTGACCA"))  # /OR pseudo-gene: skipped
+        out.insert(14, ("TRBD1*01", "GGGACAGGGGGC"))                            # D genes are kept (short: below k + a few)
+    with open(path, "w") as f:
+        for name, s in out:
+            f.write(">%s\n" % name)
+            for p in range(0, len(s), 60):
+                f.write(s[p:p + 60] + "\n")
+    return recs
+
+
+def check_refset_scan(lib, ref, tmp_path, seed=121, n=1200, radius=None, hit_len=27, k=9):
+    """t4_refset_create_from_fa + t4_refset_scan against the reference: InputRefFa (kept sequences, joined
+    names, the k-mer index) and, per read, IsLowComplexity and HasHitInSet(read, 0) -- candidate reads from clonotypes on both
+    strands, random reads, chimeras of a gene piece and random sequence, reads with N's, low-complexity reads, short reads,
+    reads with indels against the gene (several diagonals inside the radius)."""
+    rng = np.random.default_rng(seed)
+    fa = os.path.join(str(tmp_path), "genes_%d.fa" % seed)
+    recs = write_gene_fasta(fa)
+    lib.check(lib.reset())
+    g = api.RefSet(fa, k, lib, hit_len_required=hit_len)
+    r = ref.RefGeneSet(fa, k, hit_len_required=hit_len)
+    if radius is not None:
+        g.set_radius(radius)
+        r.set_radius(radius)
+    assert g.names() == r.names() and g.size() > 100
+    assert g.seqset().index_checksum() == r.index_checksum()
+    cl = synth.make_clones(40, seed)
+    rd = synth.sample_pairs(cl, 200, 150, seed, sub_rate=0.02)
+    reads = [synth.decode(c) for c in rd.codes]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    genes = [s for _, s in recs if len(s) > 200]
+
+    def rnd(L):
+        return "".join("ACGT"[c] for c in rng.integers(0, 4, size=L))
+
+    while len(reads) < n:
+        kind = int(rng.integers(0, 10))
+        L = int(rng.integers(20, 260))
+        gs = genes[int(rng.integers(len(genes)))]
+        p = int(rng.integers(0, max(1, len(gs) - 60)))
+        piece = gs[p:p + L]
+        if kind == 0:
+            t = rnd(L)
+        elif kind == 1:
+            t = piece[: max(10, len(piece) // 3)] + rnd(L)
+        elif kind == 2:
+            t = rnd(L // 2) + piece[: 20 + int(rng.integers(0, 40))] + rnd(L // 3)
+        elif kind == 3:
+            t = "".join(comp[c] for c in reversed(piece))
+        elif kind == 4:
+            t = list(piece)
+            for q in rng.integers(0, max(1, len(t)), size=int(rng.integers(1, 8))):
+                t[int(q)] = "N"
+            t = "".join(t)
+        elif kind == 5:
+            t = "ACGT"[int(rng.integers(4))] * (L // 2) + piece[: L // 3]
+        elif kind == 6:     # indels: deletions / insertions of 1-6 bases move the chain across neighbouring diagonals
+            t = piece
+            for _ in range(int(rng.integers(1, 4))):
+                q = int(rng.integers(5, max(6, len(t) - 5)))
+                d = int(rng.integers(1, 7))
+                t = t[:q] + (rnd(d) if rng.random() < 0.5 else "") + t[q + (d if rng.random() < 0.5 else 0):]
+        elif kind == 7:
+            t = piece[: int(rng.integers(5, 30))]
+        elif kind == 8:     # two genes in one read
+            g2 = genes[int(rng.integers(len(genes)))]
+            t = piece[: L // 2] + g2[-(L // 2):]
+        else:
+            t = piece
+        if len(t) < 1:
+            t = "A"
+        reads.append(t[:400])
+    lens = np.array([len(x) for x in reads], dtype=np.int32)
+    off = np.zeros(len(reads), dtype=np.uint64)
+    off[1:] = np.cumsum(lens[:-1])
+    pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    gs_, gl_, st = g.scan(pool, off, lens)
+    rs_ = np.array([r.has_hit_in_set(x, 0) for x in reads], dtype=np.int8)
+    rl_ = np.array([ref.is_low_complexity(x) for x in reads], dtype=np.uint8)
+    assert (gl_ == rl_).all(), ("low complexity", np.flatnonzero(gl_ != rl_)[:5])
+    assert (gs_ == rs_).all(), ("HasHitInSet", np.flatnonzero(gs_ != rs_)[:8], gs_[gs_ != rs_][:8], rs_[gs_ != rs_][:8])
+    assert st["with_hit"] == int((rs_ != 0).sum()) and st["low_complexity"] == int(rl_.sum())
+    assert (rs_ == 1).sum() > 50 and (rs_ == -1).sum() > 50 and (rs_ == 0).sum() > 50 and rl_.sum() > 10
+    g.close()
+    return int((rs_ != 0).sum())

@@ -59,6 +59,14 @@ def lib():
         l.t4ref_num_read.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_kmer_count_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]
+        l.t4ref_refset_create.restype = C.c_void_p
+        l.t4ref_refset_create.argtypes = [C.c_char_p, C.c_int]
+        l.t4ref_seq_name.restype = C.c_char_p
+        l.t4ref_seq_name.argtypes = [C.c_void_p, C.c_int]
+        l.t4ref_seq_count.argtypes = [C.c_void_p]
+        l.t4ref_set_radius.argtypes = [C.c_void_p, C.c_int]
+        l.t4ref_has_hit_in_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        l.t4ref_is_low_complexity.argtypes = [C.c_char_p]
         l.t4ref_input_seqset.restype = C.c_void_p
         l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_assign_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
@@ -203,6 +211,28 @@ def dp_pos_weight(tw, p):
             break
         e.append(int(v))
     return sc, e
+
+
+class RefGeneSet(RefSeqSet):
+    """The reference's `SeqSet refSet(k); refSet.InputRefFa(fasta)` (fastq-extractor / trust4 reference gene set)."""
+
+    def __init__(self, fasta, k=9, hit_len_required=27):
+        l = lib()
+        super().__init__(k, handle=l.t4ref_refset_create(fasta.encode(), k))
+        self.set_hit_len_required(hit_len_required)
+
+    def names(self):
+        return [self.l.t4ref_seq_name(self.h, i).decode() for i in range(self.l.t4ref_seq_count(self.h))]
+
+    def set_radius(self, r):
+        self.l.t4ref_set_radius(self.h, r)
+
+    def has_hit_in_set(self, read, mode=0):
+        return self.l.t4ref_has_hit_in_set(self.h, read.encode(), mode)
+
+
+def is_low_complexity(read):
+    return lib().t4ref_is_low_complexity(read.encode())
 
 
 def kmer_count_stats(pool, seq_off, lens, k=21, qual=None):

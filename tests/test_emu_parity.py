@@ -102,3 +102,9 @@ def test_emu_assign_pass_noisy_and_duplicates(emu_lib, ref):
 def test_emu_kmer_count_stats(emu_lib, ref, k):
     """canonical k-mer counts + per-read min / median / avg (KmerCount.hpp) -- the numbers that order the reads."""
     assert pc.check_kmer_count_stats(emu_lib, ref, seed=100 + k, k=k) >= 1500
+
+
+@pytest.mark.parametrize("seed,radius,hit_len", [(121, None, 27), (122, 0, 23), (123, 10, 31)])
+def test_emu_refset_scan(emu_lib, ref, tmp_path, seed, radius, hit_len):
+    """fastq-extractor's candidate predicate (InputRefFa + IsLowComplexity + HasHitInSet(read, 0))."""
+    assert pc.check_refset_scan(emu_lib, ref, tmp_path, seed=seed, radius=radius, hit_len=hit_len) > 100

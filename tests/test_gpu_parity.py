@@ -160,3 +160,11 @@ def test_gpu_kmer_count_stats(gpu_lib, ref, k):
     """SURVEY.md 8f-3 on the device (t4_kcount_kernel): canonical k-mer counts in one HBM hash table, per-read min / median /
     avg equal to the reference's KmerCount::AddCount + GetCountStatsAndTrim (ragged reads, N's, duplicates)."""
     assert pc.check_kmer_count_stats(gpu_lib, ref, seed=100 + k, n=6000, k=k) >= 6000
+
+
+@pytest.mark.parametrize("seed,radius,hit_len,k", [(121, None, 27, 9), (122, 0, 23, 9), (124, 5, 30, 11)])
+def test_gpu_refset_scan(gpu_lib, ref, tmp_path, seed, radius, hit_len, k):
+    """SURVEY.md 8f-4 on the device: the reference gene set by InputRefFa (names, index) and fastq-extractor's per-read
+    predicate -- IsLowComplexity and HasHitInSet(read, 0) with the reference-sequence chain rules (radius windows, LIS) --
+    equal to the reference for 3000 reads (candidates of both strands, random reads, chimeras, indels, N's, short reads)."""
+    assert pc.check_refset_scan(gpu_lib, ref, tmp_path, seed=seed, n=3000, radius=radius, hit_len=hit_len, k=k) > 500

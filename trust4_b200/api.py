@@ -36,6 +36,8 @@ EXPORTS = [
     "seqset_release_finished_barcode", "seqset_release_shallow_contigs", "seqset_input_novel_fa", "seqset_contig_flags",
     "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
     "kmer_count_stats", "kmer_count_table_bytes", "kmer_count_stats_device", "kmer_count_table_stats",
+    "refset_create_from_fa", "refset_free", "refset_size", "refset_name", "refset_seqset", "refset_set_hit_len_required",
+    "refset_set_radius", "refset_scan", "refset_scan_device",
 ]
 
 
@@ -121,6 +123,15 @@ class Lib:
         f("kmer_count_table_bytes", C.c_size_t, [C.c_int64])
         f("kmer_count_stats_device", ci, [vp, vp, vp, vp, C.c_int64, ci, vp, C.c_size_t, vp, vp, vp, vp, vp])
         f("kmer_count_table_stats", ci, [vp, C.c_size_t, vp])
+        f("refset_create_from_fa", vp, [cs, ci])
+        f("refset_free", None, [vp])
+        f("refset_size", ci, [vp])
+        f("refset_name", cs, [vp, ci])
+        f("refset_seqset", vp, [vp])
+        f("refset_set_hit_len_required", ci, [vp, ci])
+        f("refset_set_radius", ci, [vp, ci])
+        f("refset_scan", ci, [vp, vp, C.c_size_t, vp, vp, C.c_int64, vp, vp, vp])
+        f("refset_scan_device", ci, [vp, vp, vp, vp, C.c_int64, vp, vp, vp, ci, vp])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)
@@ -431,6 +442,52 @@ def kmer_count_stats(pool, seq_off, lens, k=21, lib: Lib | None = None, qual=Non
     lib.check(lib.kmer_count_stats(pool.ctypes.data, qual.ctypes.data if qual is not None else None, pool.nbytes, seq_off.ctypes.data,
                                    lens.ctypes.data, n, int(k), mn.ctypes.data, med.ctypes.data, avg.ctypes.data, nl.ctypes.data))
     return mn[:n], med[:n], avg[:n], nl[:n]
+
+
+class RefSet:
+    """Reference gene set on the device (t4_refset_create_from_fa: SeqSet::InputRefFa) and fastq-extractor's per-read
+    predicate over it (t4_refset_scan: IsLowComplexity + SeqSet::HasHitInSet(read, 0))."""
+
+    def __init__(self, fasta_path, k=9, lib: Lib | None = None, hit_len_required=27):
+        self.lib = lib or default_lib()
+        self.h = self.lib.refset_create_from_fa(fasta_path.encode(), int(k))
+        if not self.h:
+            raise T4Error(T4_E_INVAL, self.lib.err())
+        self.k = k
+        self.lib.check(self.lib.refset_set_hit_len_required(self.h, int(hit_len_required)))
+
+    def close(self):
+        if self.h:
+            self.lib.refset_free(self.h)
+            self.h = None
+
+    def size(self):
+        return self.lib.check(self.lib.refset_size(self.h))
+
+    def names(self):
+        return [self.lib.refset_name(self.h, i).decode() for i in range(self.size())]
+
+    def seqset(self) -> "SeqSet":
+        return _BorrowedSeqSet(self.k, self.lib, self.lib.refset_seqset(self.h))
+
+    def set_radius(self, r):
+        self.lib.check(self.lib.refset_set_radius(self.h, int(r)))
+
+    def set_hit_len_required(self, v):
+        self.lib.check(self.lib.refset_set_hit_len_required(self.h, int(v)))
+
+    def scan(self, pool, seq_off, lens):
+        """(strand int8[n] = HasHitInSet(read, 0), low uint8[n] = IsLowComplexity(read), stats)."""
+        pool = np.ascontiguousarray(pool)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        n = len(lens)
+        strand = np.zeros(max(1, n), dtype=np.int8)
+        low = np.zeros(max(1, n), dtype=np.uint8)
+        st = np.zeros(2, dtype=np.uint64)
+        self.lib.check(self.lib.refset_scan(self.h, pool.ctypes.data, pool.nbytes, seq_off.ctypes.data, lens.ctypes.data, n,
+                                            strand.ctypes.data, low.ctypes.data, st.ctypes.data))
+        return strand[:n], low[:n], dict(with_hit=int(st[0]), low_complexity=int(st[1]))
 
 
 ASSIGN_NOT_LISTED = -2

@@ -10,12 +10,14 @@
 #include <math.h>
 #include <limits.h>
 #include <vector>
+#include <map>
 #include <string>
 #include <mutex>
 #include <thread>
 
 #include "t4_engine.h"
 #include "t4_assign.h"
+#include "t4_refscan.h"
 #include "t4_kcount.h"
 
 #if T4_CUDA
@@ -2169,6 +2171,364 @@ int T4_API( assign_device_buffers )( t4_assign *a, void **assign, void **similar
 	if ( assign ) *assign = a->dAssign ;
 	if ( similarity ) *similarity = a->dSim ;
 	return 0 ;
+}
+
+// ---- stage-0 candidate extraction against a reference gene set (t4_refscan.h) ------------------------
+struct t4_refset
+{
+	t4_seqset *set ;                   // the sequences as contigs of one stream, indexed at k
+	std::vector<std::string> names ;   // after the de-duplication ("a|b" for identical sequences, SeqSet.hpp:2751-2760)
+	std::vector<t4_seqset *> workers ; // scratch-only streams of the scan launch (created on first use)
+	char *dbuf ;                       // device: parameter block + op records of the scan launch
+	size_t dbufCap ;
+	int k ;
+	uint32_t gen ;
+} ;
+
+static int refset_check( t4_refset *r )
+{
+	if ( !r || !E.up || r->gen != g_gen )
+	{
+		set_err( "stale or null t4_refset handle" ) ;
+		return T4_E_INVAL ;
+	}
+	return 0 ;
+}
+
+// SeqSet::GetGeneType( name ) == 1 (a D gene), SeqSet.hpp:5076-5100
+static bool ref_is_d_gene( const char *name )
+{
+	if ( name[0] == 'N' && name[1] == 'o' )
+		return false ;
+	size_t n = strlen( name ) ;
+	return n > 4 && name[3] == 'D' && name[4] >= '0' && name[4] <= '9' ;
+}
+
+// SeqSet::InputRefFa( file ) with isIMGT == false (SeqSet.hpp:2673-2760, 2864): FASTA records -> cleaned sequences.
+// Kept out: non-D genes whose id holds "/OR"; '.' removed; lower case and every character outside A-Z, and every letter
+// that is neither ACGT nor N, become 'N' (the reference's lower-case conversion `-= 'a' + 'A'` leaves the range, :2720-2732);
+// a sequence seen before is dropped and its name appended to the first one's ("a|b") unless that already contains it.
+static int ref_parse_fa( const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs )
+{
+	FILE *fp = fopen( path, "r" ) ;
+	if ( !fp )
+	{
+		set_err( std::string( "cannot open " ) + path ) ;
+		return T4_E_INVAL ;
+	}
+	std::vector<std::string> ids, raw ;
+	{
+		std::string line ;
+		int ch ;
+		bool have = false ;
+		auto flush = [&]()
+		{
+			while ( !line.empty() && ( line.back() == '\r' || line.back() == ' ' || line.back() == '\t' ) )
+				line.pop_back() ;
+			if ( line.empty() )
+				return ;
+			if ( line[0] == '>' )
+			{
+				size_t e = 1 ;
+				while ( e < line.size() && line[e] != ' ' && line[e] != '\t' )
+					++e ;
+				ids.push_back( line.substr( 1, e - 1 ) ) ; // kseq: the id ends at the first white space
+				raw.push_back( std::string() ) ;
+				have = true ;
+			}
+			else if ( have )
+				raw.back() += line ;
+		} ;
+		while ( ( ch = fgetc( fp ) ) != EOF )
+		{
+			if ( ch == '\n' )
+			{
+				flush() ;
+				line.clear() ;
+			}
+			else
+				line.push_back( (char)ch ) ;
+		}
+		flush() ;
+	}
+	fclose( fp ) ;
+	std::map<std::string, int> existing ;
+	for ( size_t r = 0 ; r < ids.size() ; ++r )
+	{
+		const std::string &id = ids[r] ;
+		if ( !ref_is_d_gene( id.c_str() ) )
+		{
+			size_t i ;
+			for ( i = 0 ; i < id.size() ; ++i )
+				if ( id[i] == '/' && id.compare( i + 1, 2, "OR" ) == 0 )
+					break ;
+			if ( i < id.size() )
+				continue ;
+		}
+		std::string cons ;
+		for ( size_t i = 0 ; i < raw[r].size() ; ++i )
+		{
+			char c = raw[r][i] ;
+			if ( c == '.' )
+				continue ;
+			if ( !( c >= 'A' && c <= 'Z' ) )
+				c = 'N' ;
+			else if ( c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N' )
+				c = 'N' ;
+			cons.push_back( c ) ;
+		}
+		std::map<std::string, int>::iterator it = existing.find( cons ) ;
+		if ( it != existing.end() )
+		{
+			std::string &first = names[ it->second ] ;
+			if ( first.find( id ) == std::string::npos )
+				first += "|" + id ;
+			continue ;
+		}
+		existing[cons] = (int)names.size() ;
+		names.push_back( id ) ;
+		seqs.push_back( cons ) ;
+	}
+	return 0 ;
+}
+
+void T4_API( refset_free )( t4_refset *r )
+{
+	if ( !r )
+		return ;
+	delete r->set ;
+	for ( size_t i = 0 ; i < r->workers.size() ; ++i )
+		delete r->workers[i] ;
+	if ( r->dbuf )
+		dfree( r->dbuf ) ;
+	delete r ;
+}
+
+// `SeqSet refSet( kmer_length ) ; refSet.InputRefFa( fasta_path )` (FastqExtractor.cpp:313-318) on the device
+t4_refset *T4_API( refset_create_from_fa )( const char *fasta_path, int kmer_length )
+{
+	if ( ensure_up() || !fasta_path )
+		return 0 ;
+	std::vector<std::string> names, seqs ;
+	if ( ref_parse_fa( fasta_path, names, seqs ) )
+		return 0 ;
+	if ( seqs.empty() )
+	{
+		set_err( "t4_refset_create_from_fa: no sequence in the file" ) ;
+		return 0 ;
+	}
+	t4_refset *r = new t4_refset ;
+	r->set = 0 ; r->k = kmer_length ; r->gen = g_gen ; r->dbuf = 0 ; r->dbufCap = 0 ;
+	if ( seqsets_create_impl( 1, kmer_length, 31, 0, &r->set ) )
+	{
+		delete r ;
+		return 0 ;
+	}
+	const int n = (int)seqs.size() ;
+	std::vector<u64> so( n + 1, 0 ), no( n + 1, 0 ) ;
+	std::string sp, np ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		if ( seqs[i].size() > T4_KEY_B_MASK )
+		{
+			set_err( "t4_refset_create_from_fa: sequence too long" ) ;
+			T4_API( refset_free )( r ) ;
+			return 0 ;
+		}
+		sp += seqs[i] ; np += names[i] ;
+		so[i + 1] = sp.size() ; no[i + 1] = np.size() ;
+	}
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t oIn = 0, oOp = al( sizeof( T4RefInput ) ), oSp = oOp + al( sizeof( T4Op ) ), oSo = oSp + al( sp.size() + 16 ),
+		oNp = oSo + al( ( n + 1 ) * 8 ), oNo = oNp + al( np.size() + 16 ), total = oNo + al( ( n + 1 ) * 8 ) ;
+	void *p = 0 ;
+	if ( dmalloc( &p, total ) )
+	{
+		T4_API( refset_free )( r ) ;
+		return 0 ;
+	}
+	char *b = (char *)p ;
+	T4RefInput in ;
+	memset( &in, 0, sizeof( in ) ) ;
+	in.seqPool = (u64)(uintptr_t)( b + oSp ) ; in.seqOff = (u64)(uintptr_t)( b + oSo ) ;
+	in.namePool = (u64)(uintptr_t)( b + oNp ) ; in.nameOff = (u64)(uintptr_t)( b + oNo ) ;
+	in.n = n ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = r->set->off ;
+	op.op = T4_OP_REF_INPUT ;
+	op.out = (u64)(uintptr_t)( b + oIn ) ;
+	int rc = h2d( b + oIn, &in, sizeof( in ) ) ;
+	if ( !rc ) rc = h2d( b + oOp, &op, sizeof( op ) ) ;
+	if ( !rc ) rc = h2d( b + oSp, sp.data(), sp.size() ) ;
+	if ( !rc ) rc = h2d( b + oSo, so.data(), ( n + 1 ) * 8 ) ;
+	if ( !rc ) rc = h2d( b + oNp, np.data(), np.size() ) ;
+	if ( !rc ) rc = h2d( b + oNo, no.data(), ( n + 1 ) * 8 ) ;
+	if ( !rc ) rc = launch_aux_ops( (T4Op *)( b + oOp ), 1, 0 ) ;
+	if ( !rc ) rc = dsync() ;
+	if ( !rc ) rc = d2h( &op, b + oOp, sizeof( op ) ) ;
+	dfree( p ) ;
+	if ( rc || op.ret != n )
+	{
+		if ( !rc )
+			set_err( "t4_refset_create_from_fa: device error " + std::to_string( op.ret ) ) ;
+		T4_API( refset_free )( r ) ;
+		return 0 ;
+	}
+	r->names = names ;
+	return r ;
+}
+
+int T4_API( refset_size )( t4_refset *r ) { return refset_check( r ) ? T4_E_INVAL : (int)r->names.size() ; }
+const char *T4_API( refset_name )( t4_refset *r, int i )
+{
+	if ( refset_check( r ) || i < 0 || i >= (int)r->names.size() )
+		return 0 ;
+	return r->names[i].c_str() ;
+}
+// the set behind it (owned by the refset): t4_seqset_get_hits / t4_seqset_get_contig / t4_seqset_index_checksum work on it
+t4_seqset *T4_API( refset_seqset )( t4_refset *r ) { return refset_check( r ) ? 0 : r->set ; }
+// SeqSet::SetHitLenRequired (FastqExtractor.cpp:455) and SetRadius (SeqSet.hpp:2596)
+int T4_API( refset_set_hit_len_required )( t4_refset *r, int l )
+{
+	int rc = refset_check( r ) ;
+	return rc ? rc : put_field( r->set, offsetof( T4Stream, hitLenRequired ), &l, sizeof( int ) ) ;
+}
+int T4_API( refset_set_radius )( t4_refset *r, int radius )
+{
+	int rc = refset_check( r ) ;
+	return rc ? rc : put_field( r->set, offsetof( T4Stream, radius ), &radius, sizeof( int ) ) ;
+}
+
+// Device-pointer form of the scan: `pool`, `seq_off` (u64[n]), `len` (i32[n]), `strand_out` (i8[n]) and `low_out` (u8[n])
+// are DEVICE buffers, `ctrl` a device scratch of 64 bytes.  Asynchronous on cuda_stream.
+int T4_API( refset_scan_device )( t4_refset *r, const void *pool, const void *seq_off, const void *len, int64_t n, void *strand_out,
+	void *low_out, void *ctrl, int n_workers, void *cuda_stream )
+{
+	int rc = refset_check( r ) ;
+	if ( rc ) return rc ;
+	if ( n < 0 || !pool || !seq_off || !len || !strand_out || !low_out || !ctrl )
+	{
+		set_err( "t4_refset_scan: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	if ( n_workers <= 0 )
+	{
+#if T4_CUDA
+		int sms = 148 ;
+		cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ;
+		n_workers = sms * T4_MIN_BLOCKS ;
+#else
+		n_workers = 2 ;
+#endif
+	}
+	if ( (int)r->workers.size() != n_workers )
+	{
+		// (the arena is a bump allocator: shells of an earlier size stay allocated until t4_reset)
+		for ( size_t i = 0 ; i < r->workers.size() ; ++i )
+			delete r->workers[i] ;
+		r->workers.assign( n_workers, (t4_seqset *)0 ) ;
+		rc = seqsets_create_impl( n_workers, r->k, 31, 0, r->workers.data() ) ;
+		if ( rc )
+		{
+			r->workers.clear() ;
+			return rc ;
+		}
+	}
+	T4ScanParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	P.pool = (u64)(uintptr_t)pool ; P.seqOff = (u64)(uintptr_t)seq_off ; P.len = (u64)(uintptr_t)len ;
+	P.strandOut = (u64)(uintptr_t)strand_out ; P.lowOut = (u64)(uintptr_t)low_out ; P.cursor = (u64)(uintptr_t)ctrl ;
+	P.setOff = r->set->off ;
+	P.n = n ;
+	// parameter block + op records: a device buffer of the refset (the launch reads them until it ends)
+	const size_t need = 256 + (size_t)n_workers * sizeof( T4Op ) ;
+	if ( need > r->dbufCap )
+	{
+		if ( r->dbuf )
+			dfree( r->dbuf ) ;
+		r->dbuf = 0 ; r->dbufCap = 0 ;
+		void *q = 0 ;
+		rc = dmalloc( &q, need ) ;
+		if ( rc ) return rc ;
+		r->dbuf = (char *)q ;
+		r->dbufCap = need ;
+	}
+	std::vector<T4Op> ops( n_workers ) ;
+	for ( int b = 0 ; b < n_workers ; ++b )
+	{
+		T4Op &x = ops[b] ;
+		memset( &x, 0, sizeof( x ) ) ;
+		x.streamOff = r->workers[b]->off ;
+		x.op = T4_OP_REF_SCAN ;
+		x.n = b ;
+		x.out = (u64)(uintptr_t)r->dbuf ;
+	}
+#if T4_CUDA
+	cudaStream_t cs = (cudaStream_t)cuda_stream ;
+	CK( cudaMemcpyAsync( r->dbuf, &P, sizeof( P ), cudaMemcpyHostToDevice, cs ) ) ;
+	CK( cudaMemcpyAsync( r->dbuf + 256, ops.data(), (size_t)n_workers * sizeof( T4Op ), cudaMemcpyHostToDevice, cs ) ) ;
+	CK( cudaMemsetAsync( ctrl, 0, 32, cs ) ) ;
+	CK( cudaStreamSynchronize( cs ) ) ; // P and ops are host temporaries
+#else
+	memcpy( r->dbuf, &P, sizeof( P ) ) ;
+	memcpy( r->dbuf + 256, ops.data(), (size_t)n_workers * sizeof( T4Op ) ) ;
+	memset( ctrl, 0, 32 ) ;
+#endif
+	return launch_aux_ops( (T4Op *)( r->dbuf + 256 ), n_workers, cuda_stream ) ;
+}
+
+// Host form: for every read IsLowComplexity( read ) and refSet->HasHitInSet( read, 0 ) -- fastq-extractor keeps a read
+// (pair) when `!low && strand != 0` holds for it (or its mate), FastqExtractor.cpp:129-134, 211-219.
+// stats (may be NULL): [0] reads with a hit, [1] low-complexity reads.
+int T4_API( refset_scan )( t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, int64_t n,
+	int8_t *strand_out, uint8_t *low_complexity_out, uint64_t *stats )
+{
+	int rc = refset_check( r ) ;
+	if ( rc ) return rc ;
+	if ( n < 0 || !read_pool || !seq_off || !len )
+	{
+		set_err( "t4_refset_scan: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	for ( i64 i = 0 ; i < n ; ++i )
+	{
+		if ( len[i] > T4_DEV_MAX_READ )
+		{
+			set_err( "t4_refset_scan: read longer than the device limit" ) ;
+			return T4_E_UNSUPPORTED ;
+		}
+		if ( len[i] < 0 || seq_off[i] + (u64)len[i] > pool_bytes )
+		{
+			set_err( "t4_refset_scan: record outside the pool" ) ;
+			return T4_E_INVAL ;
+		}
+	}
+	if ( n == 0 )
+		return 0 ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t oPool = 0, oOff = al( pool_bytes + 16 ), oLen = oOff + al( (size_t)n * 8 ), oStr = oLen + al( (size_t)n * 4 ),
+		oLow = oStr + al( (size_t)n ), oCtrl = oLow + al( (size_t)n ), total = oCtrl + 256 ;
+	void *p = 0 ;
+	rc = dmalloc( &p, total ) ;
+	if ( rc ) return rc ;
+	char *b = (char *)p ;
+	rc = h2d( b + oPool, read_pool, pool_bytes ) ;
+	if ( !rc ) rc = h2d( b + oOff, seq_off, (size_t)n * 8 ) ;
+	if ( !rc ) rc = h2d( b + oLen, len, (size_t)n * 4 ) ;
+	if ( !rc ) rc = T4_API( refset_scan_device )( r, b + oPool, b + oOff, b + oLen, n, b + oStr, b + oLow, b + oCtrl, 0, 0 ) ;
+	if ( !rc ) rc = dsync() ;
+	if ( !rc ) rc = T4_API( streams_error )( r->workers.data(), (int)r->workers.size() ) ;
+	if ( !rc && strand_out ) rc = d2h( strand_out, b + oStr, (size_t)n ) ;
+	if ( !rc && low_complexity_out ) rc = d2h( low_complexity_out, b + oLow, (size_t)n ) ;
+	if ( !rc && stats )
+	{
+		u64 c[4] ;
+		rc = d2h( c, b + oCtrl, sizeof( c ) ) ;
+		stats[0] = c[1] ; stats[1] = c[2] ;
+	}
+	dfree( p ) ;
+	return rc ;
 }
 
 // ---- canonical k-mer counts + per-read statistics (t4_kcount.h) ------------------------------------

@@ -460,6 +460,8 @@ T4_D inline void c_assign_recompute( T4Ctx &cx, T4Op *op )
 }
 
 // ---- dispatch: body of the auxiliary kernel (one CTA = one T4Op) ----------------------------------------------------
+T4_D inline void c_run_aux_op_more( T4Ctx &cx, T4Op *op ) ; // t4_refscan.h: the reference-set ops
+
 T4_D inline void c_run_aux_op( T4Ctx &cx, T4Op *op )
 {
 	T4Smem *sm = cx.sm ;
@@ -494,6 +496,7 @@ T4_D inline void c_run_aux_op( T4Ctx &cx, T4Op *op )
 			c_assign_recompute( cx, op ) ;
 			break ;
 		default:
+			c_run_aux_op_more( cx, op ) ;
 			break ;
 	}
 	T4_SYNC() ;

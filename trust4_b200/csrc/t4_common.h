@@ -232,6 +232,9 @@ enum
 	T4_OP_ASSIGN_PREP,
 	T4_OP_ASSIGN,
 	T4_OP_ASSIGN_RECOMPUTE,
+	// ... and the stage-0 scan against a reference gene set (t4_refscan.h)
+	T4_OP_REF_INPUT,
+	T4_OP_REF_SCAN,
 } ;
 
 struct T4Op                // per-CTA launch record

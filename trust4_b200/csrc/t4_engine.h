@@ -1432,7 +1432,9 @@ T4_D inline T4DpScratch t4_dp_scratch_of( T4Ctx &cx, int tid )
 // ---------------------------------------------------------------------------
 // Reads cx.sm->read / rc.  Returns the number of keys written to keysA (invalid keys included,
 // they sort last); *nValid receives the number of hits that survive the barcode filter.
-T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool allowTotalSkip, int *anyBig )
+// refSet: the set holds reference sequences (seqs[0].isRef): skipLimit = 0 (SeqSet.hpp:1351-1353), i.e. the >= 100 postings
+// rule never skips; a compile-time `false` at the assembly path's call sites.
+T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool allowTotalSkip, int *anyBig, bool refSet = false )
 {
 	T4Stream *st = cx.st ;
 	T4Smem *sm = cx.sm ;
@@ -1534,7 +1536,7 @@ T4_D inline u32 c_get_hits( T4Ctx &cx, int len, int strand, int barcode, bool al
 	// >=100-postings skip rule (SeqSet.hpp:1376-1392, 1441-1455)
 	else if ( cx.tid == 0 )
 	{
-		int skipLimit = k / 2 ;
+		int skipLimit = refSet ? 0 : k / 2 ;
 		u32 total = 0 ;
 		int big = 0 ;
 		u64 lookups = 0, postings = 0 ;
