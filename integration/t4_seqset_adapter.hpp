@@ -638,7 +638,7 @@ public:
 	}
 } ;
 
-// The one line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
+// The first line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
 #define T4_BATCH_PREPARE() seqSet.BatchPrepare( sortedReads, refSet, readCnt, hasBarcode, keepMissingBarcode, trimLevel, firstReadLen, \
 	constantGeneEnd, contigMinCov, changeKmerLengthThreshold )
 

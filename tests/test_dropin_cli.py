@@ -80,7 +80,7 @@ def emu_binary(emu_lib):
 
 @pytest.fixture(scope="module")
 def emu_batch_binary(emu_lib):
-    """The batch route: main.cpp + ONE inserted line (integration/make_batch_main.py), T4_STREAMS selects the device streams."""
+    """The batch route: main.cpp + one inserted line per offloaded pass (integration/make_batch_main.py), T4_STREAMS selects the device streams."""
     if not os.path.exists(os.path.join(REF, "main.cpp")):
         pytest.skip("reference sources not present (needed to compile main.cpp)")
     if not os.path.exists(STOCK):
