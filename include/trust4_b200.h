@@ -368,6 +368,9 @@ int t4_refset_set_radius(t4_refset *r, int radius);      /* SeqSet::SetRadius, S
  * Host buffers; stats (may be NULL): [0] reads with a hit, [1] low-complexity reads. */
 int t4_refset_scan(t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len,
                    int64_t n, int8_t *strand_out, uint8_t *low_complexity_out, uint64_t stats[2]);
+/* Test hook, host only: SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) exactly as the scan applies it to the
+ * hits (a[i], b[i]) of a diagonal window sorted by b; returns the chain length, the chain in out_a / out_b (room for n). */
+int t4_test_lis(const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b);
 /* The same on DEVICE buffers (ctrl: 64 bytes of device scratch; afterwards u64 ctrl[1] = reads with a hit, ctrl[2] =
  * low-complexity reads); n_workers CTAs (0 = one resident wave); asynchronous on cuda_stream. */
 int t4_refset_scan_device(t4_refset *r, const void *read_pool, const void *seq_off, const void *len, int64_t n,

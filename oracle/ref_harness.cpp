@@ -689,4 +689,23 @@ int t4ref_is_low_complexity( const char *seq )
 	return 0 ;
 }
 
+// SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342) on explicit (a, b) pairs sorted by b
+int t4ref_lis( void *h, const int32_t *a, const int32_t *b, int n, int32_t *outA, int32_t *outB )
+{
+	SimpleVector<struct _pair> hits, lis ;
+	for ( int i = 0 ; i < n ; ++i )
+	{
+		struct _pair p ;
+		p.a = a[i] ; p.b = b[i] ;
+		hits.PushBack( p ) ;
+	}
+	int ret = ((SeqSet *)h)->LongestIncreasingSubsequence( hits, lis ) ;
+	for ( int i = 0 ; i < ret ; ++i )
+	{
+		outA[i] = lis[i].a ;
+		outB[i] = lis[i].b ;
+	}
+	return ret ;
+}
+
 } // extern "C"

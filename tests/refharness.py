@@ -67,6 +67,7 @@ def lib():
         l.t4ref_set_radius.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_has_hit_in_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         l.t4ref_is_low_complexity.argtypes = [C.c_char_p]
+        l.t4ref_lis.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.t4ref_input_seqset.restype = C.c_void_p
         l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_assign_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]

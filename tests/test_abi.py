@@ -60,3 +60,41 @@ def test_host_utilities_match_reference(ref):
         b2 = ctypes.create_string_buffer(s.encode())
         ref.lib().t4ref_reverse_complement_in_place(r.h, b2, len(s))
         assert b.value == b2.value
+
+
+def test_lis_matches_reference(ref):
+    """t4_test_lis (host utility): the chain rule of the stage-0 scan -- SeqSet::LongestIncreasingSubsequence with its
+    tie rules (closest to the average diagonal among equal read offsets, one element per gene offset, the replacement
+    sweep) -- on random windows with many ties, against the reference's own member function."""
+    import numpy as np
+    from trust4_b200 import api
+    lib = api.Lib()
+    r = ref.RefSeqSet(9)
+    rng = np.random.default_rng(17)
+    n_cases = 0
+    for it in range(3000):
+        n = int(rng.integers(1, 60))
+        mode = it % 4
+        if mode == 0:      # one diagonal with noise
+            b = np.sort(rng.integers(0, 80, size=n))
+            a = b + 20 + rng.integers(-10, 11, size=n)
+        elif mode == 1:    # heavy ties in both coordinates
+            b = np.sort(rng.integers(0, 12, size=n))
+            a = rng.integers(0, 12, size=n)
+        elif mode == 2:    # two diagonals
+            b = np.sort(rng.integers(0, 100, size=n))
+            a = b + np.where(rng.random(n) < 0.5, 5, 12)
+        else:              # random
+            b = np.sort(rng.integers(0, 300, size=n))
+            a = rng.integers(0, 300, size=n)
+        order = np.lexsort((a, b))             # CompSortPairBInc: b, then a
+        a = np.ascontiguousarray(a[order], dtype=np.int32)
+        b = np.ascontiguousarray(b[order], dtype=np.int32)
+        ga, gb = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        ra, rb = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        gl = lib.test_lis(a.ctypes.data, b.ctypes.data, n, ga.ctypes.data, gb.ctypes.data)
+        rl = ref.lib().t4ref_lis(r.h, a.ctypes.data, b.ctypes.data, n, ra.ctypes.data, rb.ctypes.data)
+        assert gl == rl, (it, n, gl, rl)
+        assert (ga[:gl] == ra[:rl]).all() and (gb[:gl] == rb[:rl]).all(), (it, a.tolist(), b.tolist(), ga[:gl].tolist(), ra[:rl].tolist())
+        n_cases += 1
+    assert n_cases == 3000

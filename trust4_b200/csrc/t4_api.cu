@@ -2531,6 +2531,16 @@ int T4_API( refset_scan )( t4_refset *r, const char *read_pool, size_t pool_byte
 	return rc ;
 }
 
+// Test hook (host only, no device): SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) as the stage-0 scan runs it --
+// hits (a[i], b[i]) sorted by b; the chain goes to out_a / out_b (room for n); returns its length.
+int T4_API( test_lis )( const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b )
+{
+	if ( n <= 0 || !a || !b || !out_a || !out_b )
+		return 0 ;
+	std::vector<int> top( n ), link( n ) ;
+	return t4_lis( a, b, n, top.data(), link.data(), out_a, out_b ) ;
+}
+
 // ---- canonical k-mer counts + per-read statistics (t4_kcount.h) ------------------------------------
 static int kc_launch( const T4KcParams &P, int stats, void *stream )
 {
