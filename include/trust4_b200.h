@@ -368,6 +368,12 @@ int t4_refset_set_radius(t4_refset *r, int radius);      /* SeqSet::SetRadius, S
  * Host buffers; stats (may be NULL): [0] reads with a hit, [1] low-complexity reads. */
 int t4_refset_scan(t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len,
                    int64_t n, int8_t *strand_out, uint8_t *low_complexity_out, uint64_t stats[2]);
+/* SeqSet::GetOverlapsFromRead(read, 0, -1, 0, false, overlaps) on the gene set -- the call SeqSet::AnnotateRead makes per
+ * read (SeqSet.hpp:6050), first half of the rough annotation: chains with the reference-sequence rules
+ * (or the V-end / J-start rescue, GetVJOverlapsFromHits), gaps scored by the affine AlignAlgo::GlobalAlignment, indels
+ * allowed, similarity >= 0.75.  Same output layout as t4_seqset_get_overlaps.  Verified through the test emulation only
+ * so far (no GPU run yet). */
+int t4_refset_get_overlaps(t4_refset *r, const char *read, int32_t *overlaps, double *similarity, int cap);
 /* Test hook, host only: SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) exactly as the scan applies it to the
  * hits (a[i], b[i]) of a diagonal window sorted by b; returns the chain length, the chain in out_a / out_b (room for n). */
 int t4_test_lis(const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b);

@@ -860,3 +860,86 @@ def check_refset_scan(lib, ref, tmp_path, seed=121, n=1200, radius=None, hit_len
     assert (rs_ == 1).sum() > 50 and (rs_ == -1).sum() > 50 and (rs_ == 0).sum() > 50 and rl_.sum() > 10
     g.close()
     return int((rs_ != 0).sum())
+
+
+def check_refset_overlaps(lib, ref, tmp_path, seed=131, n=500, radius=None, hit_len=31, k=9):
+    """t4_refset_get_overlaps against SeqSet::GetOverlapsFromRead(read, 0, -1, 0, false) on the reference's gene set (the call
+    AnnotateRead makes per read): every overlap's gene, coordinates, strand, matchCnt, indelCnt and the similarity double,
+    in order.  Reads: clonotype reads (V + junction + J + C: several genes per read), gene pieces with substitutions and
+    indels (gaps scored by the affine GlobalAlignment), chimeras, reverse strands, short V-end / J-start reads (the
+    GetVJOverlapsFromHits rescue), random reads."""
+    rng = np.random.default_rng(seed)
+    fa = os.path.join(str(tmp_path), "genes_o%d.fa" % seed)
+    recs = write_gene_fasta(fa)
+    lib.check(lib.reset())
+    g = api.RefSet(fa, k, lib, hit_len_required=hit_len)
+    r = ref.RefGeneSet(fa, k, hit_len_required=hit_len)
+    if radius is not None:
+        g.set_radius(radius)
+        r.set_radius(radius)
+    cl = synth.make_clones(30, seed)
+    rd = synth.sample_pairs(cl, n // 4, 150, seed, sub_rate=0.02)
+    reads = [synth.decode(c) for c in rd.codes]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    byname = dict(recs)
+    vjs_v = [(nm, s) for nm, s in recs if len(nm) > 3 and nm[3] == "V" and len(s) > 250]
+    vjs_j = [(nm, s) for nm, s in recs if len(nm) > 3 and nm[3] == "J" and len(s) > 35]
+    genes = [s for _, s in recs if len(s) > 200]
+
+    def rnd(L):
+        return "".join("ACGT"[c] for c in rng.integers(0, 4, size=L))
+
+    def mutate(t, subs, indels):
+        t = list(t)
+        for _ in range(subs):
+            q = int(rng.integers(0, len(t)))
+            t[q] = "ACGT"[int(rng.integers(4))]
+        t = "".join(t)
+        for _ in range(indels):
+            q = int(rng.integers(12, max(13, len(t) - 12)))
+            d = int(rng.integers(1, 5))
+            t = t[:q] + (rnd(d) if rng.random() < 0.5 else "") + t[q + (d if rng.random() < 0.5 else 0):]
+        return t
+
+    while len(reads) < n:
+        kind = int(rng.integers(0, 8))
+        gs = genes[int(rng.integers(len(genes)))]
+        L = int(rng.integers(60, 220))
+        p = int(rng.integers(0, max(1, len(gs) - 80)))
+        piece = gs[p:p + L]
+        if kind == 0:
+            t = mutate(piece, int(rng.integers(0, 6)), 0)
+        elif kind == 1:
+            t = mutate(piece, int(rng.integers(0, 4)), int(rng.integers(1, 4)))
+        elif kind == 2:     # V end + random junction + J start of one chain type: the short-anchor rescue (GetVJOverlapsFromHits)
+            vn, v = vjs_v[int(rng.integers(len(vjs_v)))]
+            cand = [x for x in vjs_j if x[0][:3] == vn[:3]] or vjs_j
+            j = cand[int(rng.integers(len(cand)))][1]
+            t = v[-int(rng.integers(18, 30)):] + rnd(int(rng.integers(3, 15))) + j[: int(rng.integers(18, 30))]
+        elif kind == 3:
+            t = "".join(comp[c] for c in reversed(mutate(piece, 2, int(rng.integers(0, 2)))))
+        elif kind == 4:
+            t = rnd(L)
+        elif kind == 5:
+            g2 = genes[int(rng.integers(len(genes)))]
+            t = piece[: L // 2] + g2[-(L // 2):]
+        elif kind == 6:     # a long unmatched stretch between two anchors of the same gene: gap alignment
+            q = min(len(piece) - 30, 40)
+            t = piece[:q] + mutate(piece[q:q + 40], 12, 0) + piece[q + 40:]
+        else:
+            t = piece
+        reads.append(t[:400] if len(t) >= 1 else "A")
+    n_ovl = n_reads = n_vj = n_indel = 0
+    for i, t in enumerate(reads):
+        gn, go, gsim = g.get_overlaps(t)
+        rn, ro, rsim = r.get_overlaps(t, 0, -1, False)
+        assert gn == rn, ("count", i, gn, rn, t)
+        if rn > 0:
+            assert (go == ro).all(), ("overlap", i, go[(go != ro).any(axis=1)][:2], ro[(go != ro).any(axis=1)][:2], t)
+            assert (gsim == rsim).all(), ("similarity", i)
+            n_ovl += rn
+            n_reads += 1
+            n_indel += int((ro[:, 7] > 0).any())
+    assert n_reads > n // 3 and n_ovl > n and (n_indel > 5 or radius == 0), (n_reads, n_ovl, n_indel)
+    g.close()
+    return n_ovl

@@ -108,3 +108,9 @@ def test_emu_kmer_count_stats(emu_lib, ref, k):
 def test_emu_refset_scan(emu_lib, ref, tmp_path, seed, radius, hit_len):
     """fastq-extractor's candidate predicate (InputRefFa + IsLowComplexity + HasHitInSet(read, 0))."""
     assert pc.check_refset_scan(emu_lib, ref, tmp_path, seed=seed, radius=radius, hit_len=hit_len) > 100
+
+
+@pytest.mark.parametrize("seed,radius,hit_len", [(131, None, 31), (132, 0, 27), (133, 10, 21)])
+def test_emu_refset_overlaps(emu_lib, ref, tmp_path, seed, radius, hit_len):
+    """SURVEY.md 8f-1, first half: SeqSet::GetOverlapsFromRead on the reference gene set (emulation only, see t4_annot.h)."""
+    assert pc.check_refset_overlaps(emu_lib, ref, tmp_path, seed=seed, radius=radius, hit_len=hit_len) > 500

@@ -37,7 +37,7 @@ EXPORTS = [
     "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
     "kmer_count_stats", "kmer_count_table_bytes", "kmer_count_stats_device", "kmer_count_table_stats",
     "refset_create_from_fa", "refset_free", "refset_size", "refset_name", "refset_seqset", "refset_set_hit_len_required",
-    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis",
+    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps",
 ]
 
 
@@ -133,6 +133,7 @@ class Lib:
         f("refset_scan", ci, [vp, vp, C.c_size_t, vp, vp, C.c_int64, vp, vp, vp])
         f("refset_scan_device", ci, [vp, vp, vp, vp, C.c_int64, vp, vp, vp, ci, vp])
         f("test_lis", ci, [vp, vp, ci, vp, vp])
+        f("refset_get_overlaps", ci, [vp, cs, vp, vp, ci])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)
@@ -476,6 +477,15 @@ class RefSet:
 
     def set_hit_len_required(self, v):
         self.lib.check(self.lib.refset_set_hit_len_required(self.h, int(v)))
+
+    def get_overlaps(self, read, cap=4096):
+        """SeqSet::GetOverlapsFromRead(read, 0, -1, 0, false) on the gene set: (n, int32[n, 8], similarity[n])."""
+        out = np.zeros((cap, 8), dtype=np.int32)
+        sim = np.zeros(cap, dtype=np.float64)
+        n = self.lib.check(self.lib.refset_get_overlaps(self.h, read.encode(), out.ctypes.data, sim.ctypes.data, cap))
+        if n < 0:
+            return n, None, None
+        return n, out[:n], sim[:n]
 
     def scan(self, pool, seq_off, lens):
         """(strand int8[n] = HasHitInSet(read, 0), low uint8[n] = IsLowComplexity(read), stats)."""

@@ -18,6 +18,7 @@
 #include "t4_engine.h"
 #include "t4_assign.h"
 #include "t4_refscan.h"
+#include "t4_annot.h"
 #include "t4_kcount.h"
 
 #if T4_CUDA
@@ -85,6 +86,23 @@ __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_aux_kernel( cha
 	cx.tid = threadIdx.x ;
 	cx.nt = blockDim.x ;
 	c_run_aux_op( cx, op ) ;
+}
+
+// GetOverlapsFromRead on a reference gene set (t4_annot.h): a kernel of its own, so that the kernels validated on the GPU
+// keep their exact SASS while this one is verified through the emulation only
+__global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_annot_kernel( char *A, T4Op *ops )
+{
+	__shared__ T4Smem sm ;
+	T4Op *op = ops + blockIdx.x ;
+	T4Ctx cx ;
+	cx.A = A ;
+	cx.g = (T4Global *)A ;
+	cx.st = (T4Stream *)( A + op->streamOff ) ;
+	cx.sm = &sm ;
+	cx.cap = cx.g->cap ;
+	cx.tid = threadIdx.x ;
+	cx.nt = blockDim.x ;
+	c_run_annot_op( cx, op ) ;
 }
 
 // k-mer counting / per-read count statistics (t4_kcount.h): persistent warps, batches of reads handed out by an atomic cursor
@@ -2529,6 +2547,78 @@ int T4_API( refset_scan )( t4_refset *r, const char *read_pool, size_t pool_byte
 	}
 	dfree( p ) ;
 	return rc ;
+}
+
+// SeqSet::GetOverlapsFromRead( read, 0, -1, 0, false, overlaps ) on the reference gene set (the call AnnotateRead makes per
+// read, SeqSet.hpp:6050): overlaps as int32[8] = {seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, indelCnt}
+// plus similarity[i], in the reference's order.  Returns the overlap count, -1 for a read shorter than k.
+// NOTE: verified through the test emulation only (see t4_annot.h).
+int T4_API( refset_get_overlaps )( t4_refset *r, const char *read, int32_t *overlaps, double *similarity, int cap )
+{
+	int rc = refset_check( r ) ;
+	if ( rc ) return rc ;
+	int len ;
+	rc = read_ok( read, &len ) ;
+	if ( rc ) return rc ;
+	if ( cap < 0 || ( cap > 0 && ( !overlaps || !similarity ) ) )
+		return T4_E_INVAL ;
+	T4Stream st ;
+	rc = get_stream( r->set, &st ) ;
+	if ( rc ) return rc ;
+	const int hMax = 1 << 16 ;
+	const size_t sb = t4_annot_scratch_bytes( hMax, st.nomatchGapLimit, T4_DEV_MAX_READ ) ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t oOp = 0, oPar = al( sizeof( T4Op ) ), oRead = oPar + al( sizeof( T4RefOvlParams ) ), oOut = oRead + al( (size_t)len + 16 ),
+		oScr = oOut + al( (size_t)cap * 40 + 64 ), total = oScr + sb ;
+	void *p = 0 ;
+	rc = dmalloc( &p, total ) ;
+	if ( rc ) return rc ;
+	char *b = (char *)p ;
+	T4RefOvlParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	P.scratch = (u64)(uintptr_t)( b + oScr ) ;
+	P.scratchBytes = sb ;
+	P.hMax = hMax ;
+	T4Op op ;
+	memset( &op, 0, sizeof( op ) ) ;
+	op.streamOff = r->set->off ;
+	op.op = T4_OP_REF_OVERLAPS ;
+	op.read = (u64)(uintptr_t)( b + oRead ) ;
+	op.len = len ;
+	op.out = (u64)(uintptr_t)( b + oOut ) ;
+	op.out2 = (u64)(uintptr_t)( b + oPar ) ;
+	op.outCap = cap ;
+	rc = h2d( b + oOp, &op, sizeof( op ) ) ;
+	if ( !rc ) rc = h2d( b + oPar, &P, sizeof( P ) ) ;
+	if ( !rc ) rc = h2d( b + oRead, read, (size_t)len + 1 ) ;
+	if ( !rc )
+	{
+#if T4_CUDA
+		t4_annot_kernel<<<1, E.nt>>>( E.A, (T4Op *)( b + oOp ) ) ;
+		if ( cudaGetLastError() != cudaSuccess )
+			rc = T4_E_CUDA ;
+#else
+		T4Smem *sm = new T4Smem ;
+		T4Ctx cx ;
+		cx.A = E.A ; cx.g = (T4Global *)E.A ; cx.st = (T4Stream *)( E.A + op.streamOff ) ; cx.sm = sm ; cx.cap = cx.g->cap ; cx.tid = 0 ; cx.nt = 1 ;
+		c_run_annot_op( cx, (T4Op *)( b + oOp ) ) ;
+		delete sm ;
+#endif
+	}
+	if ( !rc ) rc = dsync() ;
+	if ( !rc ) rc = d2h( &op, b + oOp, sizeof( op ) ) ;
+	int n = op.ret ;
+	if ( !rc && n > 0 )
+	{
+		const int m = n < cap ? n : cap ;
+		rc = d2h( overlaps, b + oOut, (size_t)m * 32 ) ;
+		if ( !rc ) rc = d2h( similarity, b + oOut + (size_t)cap * 32, (size_t)m * 8 ) ;
+	}
+	dfree( p ) ;
+	if ( rc ) return rc ;
+	if ( n < T4_E_BASE )
+		set_err( "t4_refset_get_overlaps: device error " + std::to_string( n ) ) ;
+	return n ;
 }
 
 // Test hook (host only, no device): SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) as the stage-0 scan runs it --

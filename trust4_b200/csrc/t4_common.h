@@ -235,6 +235,8 @@ enum
 	// ... and the stage-0 scan against a reference gene set (t4_refscan.h)
 	T4_OP_REF_INPUT,
 	T4_OP_REF_SCAN,
+	// t4_annot_kernel (t4_annot.h): GetOverlapsFromRead on a reference gene set
+	T4_OP_REF_OVERLAPS,
 } ;
 
 struct T4Op                // per-CTA launch record
