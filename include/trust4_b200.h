@@ -374,6 +374,14 @@ int t4_refset_scan(t4_refset *r, const char *read_pool, size_t pool_bytes, const
  * allowed, similarity >= 0.75.  Same output layout as t4_seqset_get_overlaps.  Verified through the test emulation only
  * so far (no GPU run yet). */
 int t4_refset_get_overlaps(t4_refset *r, const char *read, int32_t *overlaps, double *similarity, int cap);
+/* SeqSet::AnnotateRead(read, 0, geneOverlap, NULL, NULL) for n reads -- the rough annotation of the stage-1 driver
+ * (main.cpp:1084-1120; SeqSet.hpp:6016-6340, detailLevel 0): contig intervals of the read (runs of N's), the overlaps of
+ * every interval (above), the best gene per type with similarity >= 0.8, one cell type and chain per read, the check for a
+ * random short constant-gene match.  gene_overlaps[i][t][8] for t = V, D, J, C = {seqIdx (-1: none), readStart, readEnd,
+ * seqStart, seqEnd, strand, matchCnt, indelCnt}; similarity[i][t].  Host buffers.  Verified through the test emulation
+ * only so far (no GPU run yet). */
+int t4_refset_annotate(t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len,
+                       int64_t n, int32_t *gene_overlaps, double *similarity);
 /* Test hook, host only: SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) exactly as the scan applies it to the
  * hits (a[i], b[i]) of a diagonal window sorted by b; returns the chain length, the chain in out_a / out_b (room for n). */
 int t4_test_lis(const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b);

@@ -708,4 +708,23 @@ int t4ref_lis( void *h, const int32_t *a, const int32_t *b, int n, int32_t *outA
 	return ret ;
 }
 
+// int SeqSet::AnnotateRead( read, detailLevel 0, geneOverlap, NULL, NULL ), SeqSet.hpp:6016: out[t][8] for t = V, D, J, C,
+// sim[t]; fresh `struct _overlap geneOverlap[4]` per call (the driver reuses one array, main.cpp:1086; an unset entry only
+// has seqIdx = -1 and strand = 1 defined).
+int t4ref_annotate_read( void *h, const char *read, int32_t *out, double *sim )
+{
+	struct _overlap geneOverlap[4] ;
+	char *r = strdup( read ) ;
+	int ret = ((SeqSet *)h)->AnnotateRead( r, 0, geneOverlap, NULL, NULL ) ;
+	free( r ) ;
+	for ( int t = 0 ; t < 4 ; ++t )
+	{
+		int32_t *o = out + 8 * t ;
+		o[0] = geneOverlap[t].seqIdx ; o[1] = geneOverlap[t].readStart ; o[2] = geneOverlap[t].readEnd ; o[3] = geneOverlap[t].seqStart ;
+		o[4] = geneOverlap[t].seqEnd ; o[5] = geneOverlap[t].strand ; o[6] = geneOverlap[t].matchCnt ; o[7] = geneOverlap[t].indelCnt ;
+		sim[t] = geneOverlap[t].similarity ;
+	}
+	return ret ;
+}
+
 } // extern "C"

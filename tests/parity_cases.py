@@ -943,3 +943,79 @@ def check_refset_overlaps(lib, ref, tmp_path, seed=131, n=500, radius=None, hit_
     assert n_reads > n // 3 and n_ovl > n and (n_indel > 5 or radius == 0), (n_reads, n_ovl, n_indel)
     g.close()
     return n_ovl
+
+
+def check_refset_annotate(lib, ref, tmp_path, seed=141, n=600, radius=None, hit_len=31, k=9):
+    """t4_refset_annotate against SeqSet::AnnotateRead(read, 0, geneOverlap, NULL, NULL) -- the rough annotation the stage-1
+    driver runs on every read (main.cpp:1084-1120): per gene type V / D / J / C the chosen gene, coordinates, strand, matchCnt,
+    indelCnt, similarity.  Reads: clonotype reads (V + junction + J + C in one read), mutated gene pieces, V/J-only ends,
+    reverse strands, chimeras of two chains (one chain per read rule), random reads, reads cut into several contigs by runs
+    of N's, short constant-gene matches."""
+    rng = np.random.default_rng(seed)
+    fa = os.path.join(str(tmp_path), "genes_a%d.fa" % seed)
+    recs = write_gene_fasta(fa)
+    lib.check(lib.reset())
+    g = api.RefSet(fa, k, lib, hit_len_required=hit_len)
+    r = ref.RefGeneSet(fa, k, hit_len_required=hit_len)
+    if radius is not None:
+        g.set_radius(radius)
+        r.set_radius(radius)
+    cl = synth.make_clones(60, seed)
+    rd = synth.sample_pairs(cl, n // 3, 150, seed, sub_rate=0.02)
+    reads = [synth.decode(c) for c in rd.codes]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    genes = [s for _, s in recs if len(s) > 200]
+    cgenes = [s for nm, s in recs if len(nm) > 3 and nm[3] not in "VDJ" and len(s) > 150]
+    src = list(reads)
+
+    def rnd(L):
+        return "".join("ACGT"[c] for c in rng.integers(0, 4, size=L))
+
+    while len(reads) < n:
+        kind = int(rng.integers(0, 8))
+        base = src[int(rng.integers(len(src)))]
+        gs = genes[int(rng.integers(len(genes)))]
+        p = int(rng.integers(0, max(1, len(gs) - 80)))
+        piece = gs[p:p + int(rng.integers(60, 200))]
+        if kind == 0:       # a run of N's splits the read into contigs
+            q = int(rng.integers(20, len(base) - 30))
+            t = base[:q] + "N" * int(rng.integers(7, 15)) + base[q + 10:]
+        elif kind == 1:     # sparse N's: still one contig
+            t = list(base)
+            for q in rng.integers(0, len(t), size=int(rng.integers(1, 6))):
+                t[int(q)] = "N"
+            t = "".join(t)
+        elif kind == 2:
+            t = "".join(comp[c] for c in reversed(base))
+        elif kind == 3:     # two chains in one read
+            o = src[int(rng.integers(len(src)))]
+            t = base[:75] + o[75:]
+        elif kind == 4:
+            t = rnd(int(rng.integers(40, 200)))
+        elif kind == 5:     # V or J piece followed by a short constant-gene piece deep inside the gene
+            c = cgenes[int(rng.integers(len(cgenes)))]
+            q = int(rng.integers(100, max(101, len(c) - 45)))
+            t = piece[:90] + c[q:q + int(rng.integers(30, 45))]
+        elif kind == 6:
+            t = piece
+        else:
+            t = base[: int(rng.integers(30, 100))]
+        reads.append(t[:400])
+    lens = np.array([len(x) for x in reads], dtype=np.int32)
+    off = np.zeros(len(reads), dtype=np.uint64)
+    off[1:] = np.cumsum(lens[:-1])
+    pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    go, gsim = g.annotate(pool, off, lens)
+    n_set = np.zeros(4, dtype=np.int64)
+    for i, t in enumerate(reads):
+        ro, rsim = r.annotate_read(t)
+        assert (go[i][:, 0] == ro[:, 0]).all(), ("gene", i, go[i][:, 0], ro[:, 0], t)
+        for tt in range(4):
+            if ro[tt, 0] >= 0:
+                assert (go[i][tt] == ro[tt]).all() and gsim[i][tt] == rsim[tt], ("overlap", i, tt, go[i][tt], ro[tt], gsim[i][tt], rsim[tt], t)
+                n_set[tt] += 1
+            else:
+                assert go[i][tt][5] == 1       # strand of an unset entry
+    assert n_set[0] > n // 5 and n_set[2] > n // 20 and n_set[3] > n // 10, n_set
+    g.close()
+    return int(n_set.sum())

@@ -67,6 +67,7 @@ def lib():
         l.t4ref_set_radius.argtypes = [C.c_void_p, C.c_int]
         l.t4ref_has_hit_in_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         l.t4ref_is_low_complexity.argtypes = [C.c_char_p]
+        l.t4ref_annotate_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         l.t4ref_lis.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.t4ref_input_seqset.restype = C.c_void_p
         l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]
@@ -227,6 +228,13 @@ class RefGeneSet(RefSeqSet):
 
     def set_radius(self, r):
         self.l.t4ref_set_radius(self.h, r)
+
+    def annotate_read(self, read):
+        """AnnotateRead(read, 0, ...): (int32[4, 8] for V, D, J, C; similarity[4])."""
+        out = np.zeros((4, 8), dtype=np.int32)
+        sim = np.zeros(4, dtype=np.float64)
+        self.l.t4ref_annotate_read(self.h, read.encode(), out.ctypes.data, sim.ctypes.data)
+        return out, sim
 
     def has_hit_in_set(self, read, mode=0):
         return self.l.t4ref_has_hit_in_set(self.h, read.encode(), mode)

@@ -114,3 +114,9 @@ def test_emu_refset_scan(emu_lib, ref, tmp_path, seed, radius, hit_len):
 def test_emu_refset_overlaps(emu_lib, ref, tmp_path, seed, radius, hit_len):
     """SURVEY.md 8f-1, first half: SeqSet::GetOverlapsFromRead on the reference gene set (emulation only, see t4_annot.h)."""
     assert pc.check_refset_overlaps(emu_lib, ref, tmp_path, seed=seed, radius=radius, hit_len=hit_len) > 500
+
+
+@pytest.mark.parametrize("seed,radius,hit_len", [(141, None, 31), (142, 0, 27), (143, 10, 21)])
+def test_emu_refset_annotate(emu_lib, ref, tmp_path, seed, radius, hit_len):
+    """SURVEY.md 8f-1: SeqSet::AnnotateRead(read, 0, ...) on the reference gene set (emulation only, see t4_annot.h)."""
+    assert pc.check_refset_annotate(emu_lib, ref, tmp_path, seed=seed, radius=radius, hit_len=hit_len) > 300

@@ -37,7 +37,7 @@ EXPORTS = [
     "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
     "kmer_count_stats", "kmer_count_table_bytes", "kmer_count_stats_device", "kmer_count_table_stats",
     "refset_create_from_fa", "refset_free", "refset_size", "refset_name", "refset_seqset", "refset_set_hit_len_required",
-    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps",
+    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps", "refset_annotate",
 ]
 
 
@@ -134,6 +134,7 @@ class Lib:
         f("refset_scan_device", ci, [vp, vp, vp, vp, C.c_int64, vp, vp, vp, ci, vp])
         f("test_lis", ci, [vp, vp, ci, vp, vp])
         f("refset_get_overlaps", ci, [vp, cs, vp, vp, ci])
+        f("refset_annotate", ci, [vp, vp, C.c_size_t, vp, vp, C.c_int64, vp, vp])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)
@@ -486,6 +487,18 @@ class RefSet:
         if n < 0:
             return n, None, None
         return n, out[:n], sim[:n]
+
+    def annotate(self, pool, seq_off, lens):
+        """SeqSet::AnnotateRead(read, 0, ...) per read: (int32[n, 4, 8] for V, D, J, C; similarity float64[n, 4])."""
+        pool = np.ascontiguousarray(pool)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        n = len(lens)
+        out = np.zeros((max(1, n), 4, 8), dtype=np.int32)
+        sim = np.zeros((max(1, n), 4), dtype=np.float64)
+        self.lib.check(self.lib.refset_annotate(self.h, pool.ctypes.data, pool.nbytes, seq_off.ctypes.data, lens.ctypes.data, n,
+                                                out.ctypes.data, sim.ctypes.data))
+        return out[:n], sim[:n]
 
     def scan(self, pool, seq_off, lens):
         """(strand int8[n] = HasHitInSet(read, 0), low uint8[n] = IsLowComplexity(read), stats)."""

@@ -40,8 +40,10 @@ struct T4AnnotScratch      // serial work space of one read (global memory), car
 	T4ScanScratch S ;      // bucket / window / LIS arrays (t4_refscan.h)
 	int *hcA, *hcB ;       // chain pool: hitCoords of all overlaps
 	int hcCap, hcUsed ;
-	T4ROvl *ovl, *ovlTmp ;
+	T4ROvl *ovl, *ovlTmp, *acc ; // acc: the overlaps of all contigs of a read (AnnotateRead)
 	int ovlCap ;
+	int *seqUsed ;         // int[nSeqs]
+	int *ca, *cb ;         // contig intervals of the read (64 each)
 	u64 *vj ;              // keys of the V-end / J-start hits (GetVJOverlapsFromHits)
 	int *dpM, *dpE, *dpF ; // AlignAlgo::GlobalAlignment matrices
 	signed char *align ;
@@ -49,14 +51,15 @@ struct T4AnnotScratch      // serial work space of one read (global memory), car
 	int overflow ;
 } ;
 
-T4_HD inline size_t t4_annot_scratch_bytes( int H, int gapLimit, int readLen )
+T4_HD inline size_t t4_annot_scratch_bytes( int H, int gapLimit, int readLen, int nSeqs = 0 )
 {
 	const size_t h = (size_t)( H > 16 ? H : 16 ) ;
 	const size_t g = (size_t)( gapLimit + 2 ) ;
-	return 256 + 8 * ( 2 * h ) + 4 * ( 6 * h ) + 4 * ( 2 * h ) + 2 * sizeof( T4ROvl ) * h + 8 * h + 3 * 4 * g * g + ( 2 * g + 2 * (size_t)readLen + 64 ) ;
+	return 1024 + 8 * ( 2 * h ) + 4 * ( 6 * h ) + 4 * ( 2 * h ) + 3 * sizeof( T4ROvl ) * h + 8 * h + 3 * 4 * g * g + ( 2 * g + 2 * (size_t)readLen + 64 )
+		+ 4 * (size_t)( nSeqs + 4 ) + 4 * 128 ;
 }
 
-T4_HD inline void t4_annot_carve( T4AnnotScratch &X, char *base, int H, int gapLimit, int readLen )
+T4_HD inline void t4_annot_carve( T4AnnotScratch &X, char *base, int H, int gapLimit, int readLen, int nSeqs = 0 )
 {
 	const size_t h = (size_t)( H > 16 ? H : 16 ) ;
 	const size_t g = (size_t)( gapLimit + 2 ) ;
@@ -70,7 +73,12 @@ T4_HD inline void t4_annot_carve( T4AnnotScratch &X, char *base, int H, int gapL
 	p = (char *)( ( (uintptr_t)p + 15 ) & ~(uintptr_t)15 ) ;
 	X.ovl = (T4ROvl *)p ; p += sizeof( T4ROvl ) * h ;
 	X.ovlTmp = (T4ROvl *)p ; p += sizeof( T4ROvl ) * h ;
+	X.acc = (T4ROvl *)p ; p += sizeof( T4ROvl ) * h ;
 	X.ovlCap = (int)h ;
+	X.seqUsed = (int *)p ; p += 4 * (size_t)( nSeqs + 4 ) ;
+	X.ca = (int *)p ; p += 4 * 64 ;
+	X.cb = (int *)p ; p += 4 * 64 ;
+	p = (char *)( ( (uintptr_t)p + 15 ) & ~(uintptr_t)15 ) ;
 	X.vj = (u64 *)p ; p += 8 * h ;
 	X.dpM = (int *)p ; p += 4 * g * g ;
 	X.dpE = (int *)p ; p += 4 * g * g ;
@@ -549,6 +557,155 @@ T4_HD inline int t4_ref_overlaps_from_read( const u64 *keys, int H, const char *
 	return kk ;
 }
 
+// ---- SeqSet::AnnotateRead( read, 0, geneOverlap, NULL, NULL ) (SeqSet.hpp:6016-6340, the detailLevel 0 statements) ----------
+// SeqSet::GetGeneType / GetChainType, SeqSet.hpp:5076-5100, 5132-5155
+T4_HD inline int t4_ref_chain_type( const char *name )
+{
+	if ( name[0] == 'I' )
+	{
+		if ( name[2] == 'H' ) return 0 ;
+		else if ( name[2] == 'K' ) return 1 ;
+		else if ( name[2] == 'L' ) return 2 ;
+	}
+	else if ( name[0] == 'T' )
+	{
+		if ( name[2] == 'A' ) return 3 ;
+		else if ( name[2] == 'B' ) return 4 ;
+		else if ( name[2] == 'G' ) return 5 ;
+		else if ( name[2] == 'D' ) return 6 ;
+	}
+	return 8 ;
+}
+
+T4_HD inline int t4_ref_gene_type( const char *name )
+{
+	if ( name[0] == 'N' && name[1] == 'o' )
+		return -1 ;
+	switch ( name[3] )
+	{
+		case 'V': return 0 ;
+		case 'D': return ( name[4] >= '0' && name[4] <= '9' ) ? 1 : 3 ;
+		case 'J': return 2 ;
+		case 'L':
+			if ( t4_ref_chain_type( name ) == 2 )
+				return -1 ; // IGLL genes
+			return 3 ;
+		default: return 3 ;
+	}
+}
+
+// SeqSet::GetContigIntervals (SeqSet.hpp:5289-5321): the read is cut where gapN = 7 N's fall into a window of 7
+T4_HD inline int t4_contig_intervals( const char *read, int len, int *ca, int *cb, int cap )
+{
+	const int gapN = 7 ;
+	int n = 0 ;
+	for ( int i = 0 ; i < len ; )
+	{
+		int NCnt = 0, j ;
+		for ( j = i + 1 ; j < len ; ++j )
+		{
+			if ( j >= i + gapN && read[j - gapN] == 'N' )
+				--NCnt ;
+			if ( read[j] == 'N' )
+				++NCnt ;
+			if ( NCnt >= gapN )
+				break ;
+		}
+		if ( n >= cap )
+			return -1 ;
+		ca[n] = i ;
+		cb[n] = j < len ? j - gapN : j - 1 ;
+		++n ;
+		if ( j >= len )
+			break ;
+		i = j + 1 ;
+	}
+	return n ;
+}
+
+// From the overlaps of all contigs (read coordinates already shifted, each contig's list sorted) to geneOverlap[4]
+// (V, D, J, C): SeqSet.hpp:6230-6340 without the detailLevel >= 1 statements.  ovl is reordered in place.
+T4_HD inline int t4_annotate_select( T4ROvl *ovl, T4ROvl *tmp, int overlapCnt, int *seqUsed, int len, const T4RefView &V, T4ROvl geneOverlap[4] )
+{
+	for ( int t = 0 ; t < 4 ; ++t )
+	{
+		geneOverlap[t].seqIdx = -1 ;
+		geneOverlap[t].readStart = geneOverlap[t].readEnd = geneOverlap[t].seqStart = geneOverlap[t].seqEnd = -1 ; // _overlap()
+		geneOverlap[t].strand = 1 ;
+		geneOverlap[t].matchCnt = 0 ;
+		geneOverlap[t].indelCnt = 0 ;
+		geneOverlap[t].similarity = 0 ;
+		geneOverlap[t].infoFromHits = 0 ;
+		geneOverlap[t].hcStart = geneOverlap[t].hcCnt = 0 ;
+		geneOverlap[t].pad = 0 ;
+	}
+	t4_rovl_sort( ovl, tmp, overlapCnt ) ;
+	for ( int i = 0 ; i < V.nSeqs ; ++i )
+		seqUsed[i] = -1 ;
+	const double geneSimilarity = 0.8 ;
+	int k = 0 ;
+	for ( int i = 0 ; i < overlapCnt ; ++i )
+	{
+		const int geneType = t4_ref_gene_type( V.name( ovl[i].seqIdx ) ) ;
+		if ( geneType < 0 || geneType == 1 )
+			continue ;
+		if ( seqUsed[ ovl[i].seqIdx ] == -1 && ovl[i].similarity >= geneSimilarity )
+		{
+			seqUsed[ ovl[i].seqIdx ] = k ;
+			ovl[k] = ovl[i] ;
+			++k ;
+		}
+		else if ( seqUsed[ ovl[i].seqIdx ] != -1 && geneType == 2 )
+		{
+			T4ROvl &baseline = ovl[ seqUsed[ ovl[i].seqIdx ] ] ;
+			if ( ovl[i].matchCnt == baseline.matchCnt && ovl[i].similarity == baseline.similarity )
+			{
+				int j ;
+				for ( j = 0 ; j < k ; ++j )
+					if ( t4_ref_gene_type( V.name( ovl[j].seqIdx ) ) == 3 )
+						break ;
+				if ( j < k && ovl[i].readEnd <= ovl[j].readStart + 3 )
+				{
+					const int d1 = ovl[i].readEnd - ovl[j].readStart, d2 = baseline.readEnd - ovl[j].readStart ;
+					if ( baseline.readEnd > ovl[j].readStart + 3 || ( d1 < 0 ? -d1 : d1 ) < ( d2 < 0 ? -d2 : d2 ) )
+						baseline = ovl[i] ;
+				}
+			}
+		}
+	}
+	overlapCnt = k ;
+	if ( overlapCnt == 0 )
+		return 0 ;
+	char BT = '\0', chain = '\0' ;
+	for ( int i = 0 ; i < overlapCnt ; ++i )
+	{
+		const char *name = V.name( ovl[i].seqIdx ) ;
+		if ( BT && name[0] != BT )
+			continue ;
+		BT = name[0] ;
+		if ( chain && !( name[2] == chain || ( name[2] == 'D' && chain == 'A' ) || ( name[2] == 'A' && chain == 'D' ) ) )
+			continue ;
+		chain = name[2] ;
+		const int geneType = t4_ref_gene_type( name ) ;
+		if ( geneType >= 0 && geneOverlap[geneType].seqIdx == -1 )
+			geneOverlap[geneType] = ovl[i] ;
+	}
+	// a short constant-gene match next to a V / J match that overlaps it is taken for random (SeqSet.hpp:6308-6323)
+	if ( geneOverlap[3].seqIdx != -1 && geneOverlap[3].readEnd - geneOverlap[3].readStart + 1 <= len / 2
+		&& geneOverlap[3].readEnd - geneOverlap[3].readStart + 1 <= 50 )
+	{
+		for ( int i = 0 ; i < 3 ; ++i )
+			if ( geneOverlap[i].seqIdx >= 0
+				&& ( geneOverlap[i].readEnd - 17 > geneOverlap[3].readStart || geneOverlap[3].readEnd < geneOverlap[i].readEnd )
+				&& geneOverlap[3].seqStart >= 100 )
+			{
+				geneOverlap[3].seqIdx = -1 ;
+				break ;
+			}
+	}
+	return 1 ;
+}
+
 // ---- T4_OP_REF_OVERLAPS: one read against the gene set (the per-call entry; body of t4_annot_kernel) ------------------
 struct T4RefOvlParams
 {
@@ -619,6 +776,153 @@ T4_D inline void c_ref_get_overlaps( T4Ctx &cx, T4Op *op )
 		op->ret = cx.st->error ? cx.st->error : ret ;
 }
 
+// ---- T4_OP_REF_ANNOTATE: worker loop, AnnotateRead( read, 0, ... ) for a batch of reads --------------------------------------
+struct T4AnnotParams
+{
+	u64 pool, seqOff, len ;   // reads (device): ASCII pool, u64[n], i32[n]
+	u64 out ;                 // int32[n][4][8]: per gene type V, D, J, C: seqIdx (-1: none), readStart, readEnd, seqStart, seqEnd, strand, matchCnt, indelCnt
+	u64 sim ;                 // double[n][4]
+	u64 cursor ;              // u64[4]
+	u64 setOff ;              // the gene set's stream
+	u64 scratch ;             // per worker blocks of scratchStride bytes
+	u64 scratchStride ;
+	i64 n ;
+	int hMax ;
+	int pad ;
+} ;
+
+// hits of the read in sm->read / rc (length len) against the attached gene set, sorted in SortHits order.  Collective;
+// returns the hit count (keys in *sorted), sets failed on a device error.
+T4_D inline u32 c_ref_sorted_hits( T4Ctx &cx, int len, int hMax, const u64 **sorted, bool &failed )
+{
+	T4Stream *st = cx.st ;
+	int anyBig = 0 ;
+	u32 H = c_get_hits( cx, len, 0, -1, false, &anyBig, true ) ;
+	if ( ( anyBig || (int)H > hMax ) && cx.tid == 0 )
+		t4_raise( cx, anyBig ? T4_E_UNSUPPORTED : T4_E_NOMEM, 7 ) ;
+	failed = c_uniform_error( cx ) != 0 ;
+	if ( failed || H == 0 )
+		return 0 ;
+	u64 *a = cx.P<u64>( st->keysAOff ) ;
+	u64 *b = cx.P<u64>( st->keysBOff ) ;
+	T4_PAR_FOR( i, H )
+	{
+		const u64 kx = a[i] ;
+		a[i] = ( kx & ( ~0ull << T4_KEY_IDX_SHIFT ) ) | ( (u64)t4_key_a( kx ) << 30 ) | ( (u64)t4_key_b( kx ) << 1 ) | ( kx & 1 ) ;
+	}
+	T4_SYNC() ;
+	*sorted = c_sort_keys( cx, a, b, H ) ;
+	return H ;
+}
+
+T4_D inline void c_ref_annotate( T4Ctx &cx, T4Op *op )
+{
+	const T4AnnotParams *P = t4_x<T4AnnotParams>( op->out ) ;
+	T4Smem *sm = cx.sm ;
+	T4Stream *st = cx.st ;
+	const u64 *seqOff = t4_x<u64>( P->seqOff ) ;
+	const int32_t *lens = t4_x<int32_t>( P->len ) ;
+	const char *pool = t4_x<char>( P->pool ) ;
+	int32_t *out = t4_x<int32_t>( P->out ) ;
+	double *sim = t4_x<double>( P->sim ) ;
+	u64 *cursor = t4_x<u64>( P->cursor ) ;
+	char *scratch = t4_x<char>( P->scratch ) + (u64)op->n * P->scratchStride ;
+	c_assign_attach( cx, cx.P<T4Stream>( P->setOff ) ) ;
+	T4RefView V ;
+	V.seqs = cx.P<T4Contig>( st->seqsOff ) ;
+	V.A = cx.A ;
+	V.nSeqs = st->nSeqs ;
+	V.k = st->kmerLength ;
+	V.radius = st->radius ;
+	V.hitLenRequired = st->hitLenRequired ;
+	V.nomatchGapLimit = st->nomatchGapLimit ;
+	V.refSeqSimilarity = 0.75 ;
+	bool failed = false ;
+	while ( !failed )
+	{
+		T4_SYNC() ;
+		if ( cx.tid == 0 )
+			sm->bu[0] = t4_atomic_add( cursor, 1ull ) ;
+		T4_SYNC() ;
+		const i64 r = (i64)sm->bu[0] ;
+		if ( r >= P->n )
+			break ;
+		const int len = lens[r] ;
+		const char *src = pool + seqOff[r] ;
+		if ( len > T4_DEV_MAX_READ )
+		{
+			if ( cx.tid == 0 )
+				t4_raise( cx, T4_E_UNSUPPORTED, 5 ) ;
+			failed = c_uniform_error( cx ) != 0 ;
+			break ;
+		}
+		// contig intervals of the read (thread 0 reads it from global memory), broadcast through the scratch block
+		T4AnnotScratch X ;
+		t4_annot_carve( X, scratch, P->hMax, st->nomatchGapLimit, T4_DEV_MAX_READ, V.nSeqs ) ;
+		if ( cx.tid == 0 )
+			sm->bi[2] = t4_contig_intervals( src, len, X.ca, X.cb, 64 ) ;
+		T4_SYNC() ;
+		const int contigCnt = sm->bi[2] ;
+		T4_SYNC() ;
+		if ( contigCnt < 0 )
+		{
+			if ( cx.tid == 0 )
+				t4_raise( cx, T4_E_UNSUPPORTED, 9 ) ;
+			failed = c_uniform_error( cx ) != 0 ;
+			break ;
+		}
+		int nAcc = 0 ; // thread 0
+		for ( int c = 0 ; c < contigCnt && !failed ; ++c )
+		{
+			const int ca = X.ca[c], clen = X.cb[c] - X.ca[c] + 1 ;
+			if ( clen < st->kmerLength )
+				continue ; // GetOverlapsFromRead returns -1: no overlaps
+			c_load_read( cx, src + ca, clen ) ;
+			const u64 *sorted = 0 ;
+			const u32 H = c_ref_sorted_hits( cx, clen, P->hMax, &sorted, failed ) ;
+			if ( failed )
+				break ;
+			if ( H > 0 && cx.tid == 0 )
+			{
+				const int n = t4_ref_overlaps_from_read( sorted, (int)H, sm->read, sm->rc, clen, V, X ) ;
+				if ( X.overflow || nAcc + n > X.ovlCap )
+					t4_raise( cx, T4_E_NOMEM, 8 ) ;
+				else
+				{
+					// shift to read coordinates and sort this contig's list (SeqSet.hpp:6050-6057), then append
+					for ( int i = 0 ; i < n ; ++i )
+					{
+						X.ovl[i].readStart += ca ;
+						X.ovl[i].readEnd += ca ;
+					}
+					t4_rovl_sort( X.ovl, X.ovlTmp, n ) ;
+					for ( int i = 0 ; i < n ; ++i )
+						X.acc[nAcc + i] = X.ovl[i] ;
+					nAcc += n ;
+				}
+			}
+			failed = c_uniform_error( cx ) != 0 ;
+		}
+		if ( failed )
+			break ;
+		if ( cx.tid == 0 )
+		{
+			T4ROvl go[4] ;
+			t4_annotate_select( X.acc, X.ovlTmp, nAcc, X.seqUsed, len, V, go ) ;
+			for ( int t = 0 ; t < 4 ; ++t )
+			{
+				int32_t *o = out + ( r * 4 + t ) * 8 ;
+				o[0] = go[t].seqIdx ; o[1] = go[t].readStart ; o[2] = go[t].readEnd ; o[3] = go[t].seqStart ; o[4] = go[t].seqEnd ;
+				o[5] = go[t].strand ; o[6] = go[t].matchCnt ; o[7] = go[t].indelCnt ;
+				sim[r * 4 + t] = go[t].similarity ;
+			}
+		}
+	}
+	T4_SYNC() ;
+	if ( cx.tid == 0 )
+		op->ret = cx.st->error ? cx.st->error : 0 ;
+}
+
 T4_D inline void c_run_annot_op( T4Ctx &cx, T4Op *op )
 {
 	T4Smem *sm = cx.sm ;
@@ -637,6 +941,8 @@ T4_D inline void c_run_annot_op( T4Ctx &cx, T4Op *op )
 	T4_SYNC() ;
 	if ( op->op == T4_OP_REF_OVERLAPS )
 		c_ref_get_overlaps( cx, op ) ;
+	else if ( op->op == T4_OP_REF_ANNOTATE )
+		c_ref_annotate( cx, op ) ;
 	T4_SYNC() ;
 }
 

@@ -2621,6 +2621,117 @@ int T4_API( refset_get_overlaps )( t4_refset *r, const char *read, int32_t *over
 	return n ;
 }
 
+// SeqSet::AnnotateRead( read, 0, geneOverlap, NULL, NULL ) for every read (the rough annotation of the stage-1 driver,
+// main.cpp:1084-1120; SeqSet.hpp:6016-6340): gene_overlaps[i][t][8] for t = V, D, J, C = {seqIdx (-1: none), readStart,
+// readEnd, seqStart, seqEnd, strand, matchCnt, indelCnt}, similarity[i][t].  Host buffers.
+// NOTE: verified through the test emulation only (see t4_annot.h).
+int T4_API( refset_annotate )( t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, int64_t n,
+	int32_t *gene_overlaps, double *similarity )
+{
+	int rc = refset_check( r ) ;
+	if ( rc ) return rc ;
+	if ( n < 0 || !read_pool || !seq_off || !len || !gene_overlaps || !similarity )
+	{
+		set_err( "t4_refset_annotate: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	for ( i64 i = 0 ; i < n ; ++i )
+	{
+		if ( len[i] > T4_DEV_MAX_READ )
+		{
+			set_err( "t4_refset_annotate: read longer than the device limit" ) ;
+			return T4_E_UNSUPPORTED ;
+		}
+		if ( len[i] < 0 || seq_off[i] + (u64)len[i] > pool_bytes )
+		{
+			set_err( "t4_refset_annotate: record outside the pool" ) ;
+			return T4_E_INVAL ;
+		}
+	}
+	if ( n == 0 )
+		return 0 ;
+	T4Stream st ;
+	rc = get_stream( r->set, &st ) ;
+	if ( rc ) return rc ;
+#if T4_CUDA
+	int sms = 148 ;
+	cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, E.device ) ;
+	int nw = sms * T4_MIN_BLOCKS ;
+#else
+	int nw = 2 ;
+#endif
+	if ( (i64)nw > n )
+		nw = (int)n ;
+	if ( (int)r->workers.size() < nw )
+	{
+		for ( size_t i = 0 ; i < r->workers.size() ; ++i )
+			delete r->workers[i] ;
+		r->workers.assign( nw, (t4_seqset *)0 ) ;
+		rc = seqsets_create_impl( nw, r->k, 31, 0, r->workers.data() ) ;
+		if ( rc )
+		{
+			r->workers.clear() ;
+			return rc ;
+		}
+	}
+	const int hMax = 1 << 16 ; // hits of one read (contig) a worker has serial work space for: 16 MB per worker
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t stride = al( t4_annot_scratch_bytes( hMax, st.nomatchGapLimit, T4_DEV_MAX_READ, st.nSeqs ) ) ;
+	const size_t oPar = 0, oOps = al( sizeof( T4AnnotParams ) ), oPool = oOps + al( (size_t)nw * sizeof( T4Op ) ), oOff = oPool + al( pool_bytes + 16 ),
+		oLen = oOff + al( (size_t)n * 8 ), oOut = oLen + al( (size_t)n * 4 ), oSim = oOut + al( (size_t)n * 4 * 8 * 4 ), oCtrl = oSim + al( (size_t)n * 4 * 8 ),
+		oScr = oCtrl + 256, total = oScr + stride * (size_t)nw ;
+	void *p = 0 ;
+	rc = dmalloc( &p, total ) ;
+	if ( rc ) return rc ;
+	char *b = (char *)p ;
+	T4AnnotParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	P.pool = (u64)(uintptr_t)( b + oPool ) ; P.seqOff = (u64)(uintptr_t)( b + oOff ) ; P.len = (u64)(uintptr_t)( b + oLen ) ;
+	P.out = (u64)(uintptr_t)( b + oOut ) ; P.sim = (u64)(uintptr_t)( b + oSim ) ; P.cursor = (u64)(uintptr_t)( b + oCtrl ) ;
+	P.setOff = r->set->off ;
+	P.scratch = (u64)(uintptr_t)( b + oScr ) ; P.scratchStride = stride ;
+	P.n = n ; P.hMax = hMax ;
+	std::vector<T4Op> ops( nw ) ;
+	for ( int w = 0 ; w < nw ; ++w )
+	{
+		memset( &ops[w], 0, sizeof( T4Op ) ) ;
+		ops[w].streamOff = r->workers[w]->off ;
+		ops[w].op = T4_OP_REF_ANNOTATE ;
+		ops[w].n = w ;
+		ops[w].out = (u64)(uintptr_t)( b + oPar ) ;
+	}
+	rc = h2d( b + oPar, &P, sizeof( P ) ) ;
+	if ( !rc ) rc = h2d( b + oOps, ops.data(), (size_t)nw * sizeof( T4Op ) ) ;
+	if ( !rc ) rc = h2d( b + oPool, read_pool, pool_bytes ) ;
+	if ( !rc ) rc = h2d( b + oOff, seq_off, (size_t)n * 8 ) ;
+	if ( !rc ) rc = h2d( b + oLen, len, (size_t)n * 4 ) ;
+	if ( !rc ) rc = dzero( b + oCtrl, 64 ) ;
+	if ( !rc )
+	{
+#if T4_CUDA
+		t4_annot_kernel<<<nw, E.nt>>>( E.A, (T4Op *)( b + oOps ) ) ;
+		if ( cudaGetLastError() != cudaSuccess )
+			rc = T4_E_CUDA ;
+#else
+		T4Smem *sm = new T4Smem ;
+		for ( int w = 0 ; w < nw ; ++w )
+		{
+			T4Ctx cx ;
+			T4Op *o = (T4Op *)( b + oOps ) + w ;
+			cx.A = E.A ; cx.g = (T4Global *)E.A ; cx.st = (T4Stream *)( E.A + o->streamOff ) ; cx.sm = sm ; cx.cap = cx.g->cap ; cx.tid = 0 ; cx.nt = 1 ;
+			c_run_annot_op( cx, o ) ;
+		}
+		delete sm ;
+#endif
+	}
+	if ( !rc ) rc = dsync() ;
+	if ( !rc ) rc = T4_API( streams_error )( r->workers.data(), nw ) ;
+	if ( !rc ) rc = d2h( gene_overlaps, b + oOut, (size_t)n * 4 * 8 * 4 ) ;
+	if ( !rc ) rc = d2h( similarity, b + oSim, (size_t)n * 4 * 8 ) ;
+	dfree( p ) ;
+	return rc ;
+}
+
 // Test hook (host only, no device): SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) as the stage-0 scan runs it --
 // hits (a[i], b[i]) sorted by b; the chain goes to out_a / out_b (room for n); returns its length.
 int T4_API( test_lis )( const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b )

@@ -237,6 +237,7 @@ enum
 	T4_OP_REF_SCAN,
 	// t4_annot_kernel (t4_annot.h): GetOverlapsFromRead on a reference gene set
 	T4_OP_REF_OVERLAPS,
+	T4_OP_REF_ANNOTATE,
 } ;
 
 struct T4Op                // per-CTA launch record
