@@ -45,6 +45,13 @@
 #define t4_assign_results t4emu_assign_results
 #define t4_assign_extended_set t4emu_assign_extended_set
 #define t4_assign_free t4emu_assign_free
+#define t4_refset_create_from_fa t4emu_refset_create_from_fa
+#define t4_refset_free t4emu_refset_free
+#define t4_refset_size t4emu_refset_size
+#define t4_refset_name t4emu_refset_name
+#define t4_refset_set_hit_len_required t4emu_refset_set_hit_len_required
+#define t4_refset_set_radius t4emu_refset_set_radius
+#define t4_refset_annotate t4emu_refset_annotate
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
 #endif
@@ -62,6 +69,7 @@
 #include "trust4_b200.h"
 
 static int t4_adapter_instances = 0 ;
+static std::string t4_adapter_ref_fa ; // the -f file, noted when the driver loads its reference gene set (main.cpp:674)
 
 class T4GpuSeqSet : public SeqSet
 {
@@ -492,6 +500,84 @@ public:
 		return true ;
 	}
 
+	// main.cpp:674 `refSet.InputRefFa( optarg )`: the CPU object loads the genes as always; the file name is kept so that the
+	// batch route can build the same gene set on the device (BatchAnnotate).
+	void InputRefFa( char *filename, bool isIMGT = false, const char *imgtAdditionalGap = NULL )
+	{
+		if ( !gpu )
+			t4_adapter_ref_fa = filename ;
+		SeqSet::InputRefFa( filename, isIMGT, imgtAdditionalGap ) ;
+	}
+
+	// T4_BATCH_ANNOTATE() is the third inserted line of the batch route: `if ( !seqSet.BatchAnnotate( ... ) )` in front of the
+	// rough annotation loop (main.cpp:1084: `if ( threadCnt <= 1 ) { ... AnnotateRead( read, 0, ... ) ... } else { pthreads }`),
+	// which becomes the fall-back branch.  OPT-IN (T4_ANNOTATE=1): the device pass behind it (t4_refset_annotate) has been
+	// verified through the CPU emulation only so far.  The gene set is rebuilt on the device from the driver's -f file with
+	// refSet's k, hitLenRequired and radius (main.cpp:766-771, 1082-1083); sortedReads[i].geneOverlap[0..3] receive what
+	// AnnotateRead would have stored (an entry without a gene: seqIdx -1, strand 1).
+	template <class Reads, class RefSet>
+	bool BatchAnnotate( Reads &sortedReads, RefSet &refSet, int readCnt )
+	{
+		const char *env = getenv( "T4_ANNOTATE" ) ;
+		if ( !gpu || env == NULL || atoi( env ) != 1 || getenv( "T4_STREAMS" ) == NULL || readCnt <= 0 || t4_adapter_ref_fa.empty() )
+			return false ;
+		t4_refset *ref = t4_refset_create_from_fa( t4_adapter_ref_fa.c_str(), refSet.kmerLength ) ;
+		if ( !ref )
+			Die() ;
+		Check( t4_refset_set_hit_len_required( ref, refSet.hitLenRequired ) ) ;
+		Check( t4_refset_set_radius( ref, refSet.radius ) ) ;
+		const int ng = Check( t4_refset_size( ref ) ) ;
+		bool same = ng == (int)refSet.seqs.size() ;
+		for ( int i = 0 ; same && i < ng ; ++i )
+			same = !strcmp( t4_refset_name( ref, i ), refSet.seqs[i].name ) ;
+		if ( !same )
+		{
+			fprintf( stderr, "trust4_b200: the device gene set differs from the driver's (%d vs %d sequences)\n", ng, (int)refSet.seqs.size() ) ;
+			exit( 1 ) ;
+		}
+		std::string pool ;
+		std::vector<uint64_t> off( readCnt ) ;
+		std::vector<int32_t> len( readCnt ) ;
+		for ( int i = 0 ; i < readCnt ; ++i )
+		{
+			off[i] = pool.size() ;
+			len[i] = (int)strlen( sortedReads[i].read ) ;
+			if ( len[i] > T4_MAX_READ_LEN )
+			{
+				fprintf( stderr, "trust4_b200: read longer than %d bases\n", T4_MAX_READ_LEN ) ;
+				exit( 1 ) ;
+			}
+			pool.append( sortedReads[i].read, len[i] ) ;
+		}
+		pool.append( 16, '\0' ) ;
+		std::vector<int32_t> go( (size_t)readCnt * 32 ) ;
+		std::vector<double> sim( (size_t)readCnt * 4 ) ;
+		Check( t4_refset_annotate( ref, pool.data(), pool.size(), off.data(), len.data(), readCnt, go.data(), sim.data() ) ) ;
+		int annotated = 0 ;
+		for ( int i = 0 ; i < readCnt ; ++i )
+		{
+			bool any = false ;
+			for ( int j = 0 ; j < 4 ; ++j )
+			{
+				const int32_t *o = &go[( (size_t)i * 4 + j ) * 8] ;
+				struct _overlap g ; // _overlap(): seqIdx -1, strand 1 (what AnnotateRead leaves defined for a missing gene)
+				if ( o[0] >= 0 )
+				{
+					g.seqIdx = o[0] ; g.readStart = o[1] ; g.readEnd = o[2] ; g.seqStart = o[3] ; g.seqEnd = o[4] ;
+					g.strand = o[5] ; g.matchCnt = o[6] ; g.indelCnt = o[7] ;
+					g.similarity = sim[(size_t)i * 4 + j] ;
+					any = true ;
+				}
+				sortedReads[i].geneOverlap[j] = g ;
+			}
+			if ( any )
+				++annotated ;
+		}
+		t4_refset_free( ref ) ;
+		fprintf( stderr, "[trust4_b200] batch route: rough annotation on the device, %d of %d reads hit a gene\n", annotated, readCnt ) ;
+		return true ;
+	}
+
 	int AddRead( char *read, char *geneName, int &strand, int barcode, int minKmerCount, bool repetitiveData, double similarityThreshold )
 	{
 		if ( !gpu )
@@ -641,6 +727,9 @@ public:
 // The first line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
 #define T4_BATCH_PREPARE() seqSet.BatchPrepare( sortedReads, refSet, readCnt, hasBarcode, keepMissingBarcode, trimLevel, firstReadLen, \
 	constantGeneEnd, contigMinCov, changeKmerLengthThreshold )
+
+// The third line (opt-in, T4_ANNOTATE=1), in front of the rough annotation loop (main.cpp:1084); see BatchAnnotate.
+#define T4_BATCH_ANNOTATE() if ( !seqSet.BatchAnnotate( sortedReads, refSet, readCnt ) )
 
 // The second line of the batch route, in front of the AssignRead loop (main.cpp:2075); see BatchAssign.
 #define T4_BATCH_ASSIGN() if ( !seqSet.BatchAssign( extendedSeq, assembledReads, assembledReadCnt ) )

@@ -118,6 +118,33 @@ def test_batch_emu_assign_pass_on_device(emu_batch_binary, tmp_path):
             assert len(a) > 0 and a == open(os.path.join(tmp, tag + suf), "rb").read(), (tag, suf)
 
 
+@pytest.mark.parametrize("case", ["synthetic", "example", "repseq"])
+def test_batch_emu_annotate_on_device(emu_batch_binary, tmp_path, case):
+    """The third pass of the batch route, opt-in with T4_ANNOTATE=1: the driver's rough annotation loop
+    (main.cpp:1084-1120) is replaced by t4_refset_annotate on a gene set rebuilt on the device from the -f file.  With all
+    three passes on the (emulated) device -- rough annotation, AddRead loop + rescue, AssignRead -- the three output files
+    stay byte-identical to the stock binary's: synthetic pairs; the shipped example (BASELINE configs[0], hg38_bcrtcr.fa);
+    --trimLevel 2 (gene set re-indexed at k = 7, radius 0, main.cpp:766-771, 1082-1083).  Emulation only: the device pass
+    has not run on a GPU yet."""
+    tmp = str(tmp_path)
+    extra = []
+    if case == "synthetic":
+        args = write_inputs(tmp, 1500, 50, 33)
+    elif case == "example":
+        args = ["-f", REF + "/hg38_bcrtcr.fa", "-1", REF + "/example/example_1.fq", "-2", REF + "/example/example_2.fq"]
+    else:
+        args = write_inputs(tmp, 800, 25, 34)
+        extra = ["--trimLevel", "2", "--skipMateExtension"]
+    subprocess.run([STOCK, "-t", "1", "-o", os.path.join(tmp, "stock")] + extra + args, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=900)
+    r = subprocess.run([emu_batch_binary, "-t", "1", "-o", os.path.join(tmp, "dev")] + extra + args, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, T4_STREAMS="1", T4_ANNOTATE="1"), text=True)
+    assert "rough annotation on the device" in r.stderr
+    for suf in SUFFIXES:
+        a = open(os.path.join(tmp, "stock" + suf), "rb").read()
+        assert len(a) > 0 and a == open(os.path.join(tmp, "dev" + suf), "rb").read(), (case, suf)
+
+
 def test_batch_emu_repseq_and_min_cov(emu_batch_binary, tmp_path):
     run_and_compare(emu_batch_binary, write_inputs(str(tmp_path), 800, 25, 22), str(tmp_path),
                     extra=("--trimLevel", "2", "--skipMateExtension", "--contigMinCov", "2"), env={"T4_STREAMS": "1"})
