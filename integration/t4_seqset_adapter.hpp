@@ -52,6 +52,7 @@
 #define t4_refset_set_hit_len_required t4emu_refset_set_hit_len_required
 #define t4_refset_set_radius t4emu_refset_set_radius
 #define t4_refset_annotate t4emu_refset_annotate
+#define t4_kmer_count_stats t4emu_kmer_count_stats
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
 #endif
@@ -500,6 +501,74 @@ public:
 		return true ;
 	}
 
+	// T4_BATCH_KMERSTATS() is the (opt-in, T4_KMERSTATS=1) line in front of the count-statistics loop (main.cpp:981:
+	// `if (threadCnt == 1) { ... GetCountStatsAndTrim ... } else { pthreads }`).  The driver has filled `kmerCount` with the
+	// 21-mers of every read it kept while loading (ProcessRead, main.cpp:401-440); the device counts the same reads again in
+	// one HBM table and returns minCnt / medianCnt / avgCnt and the quality trim per read (t4_kmer_count_stats), and the reads
+	// are cut / dropped exactly as the loop would have (main.cpp:985-1010).  Not applicable -- the CPU loop runs -- when the
+	// counts came from a file (-k) or reads were removed after counting (--contigMinCov with barcodes, main.cpp:951-978).
+	template <class Reads>
+	bool BatchKmerStats( Reads &sortedReads, int readCnt, int trimLevel, bool countMyself, bool readsRemovedAfterCounting )
+	{
+		const char *env = getenv( "T4_KMERSTATS" ) ;
+		if ( !gpu || env == NULL || atoi( env ) != 1 || getenv( "T4_STREAMS" ) == NULL || readCnt <= 0 || !countMyself || readsRemovedAfterCounting )
+			return false ;
+		std::string pool, qpool ;
+		std::vector<uint64_t> off( readCnt ) ;
+		std::vector<int32_t> len( readCnt ) ;
+		const bool useQual = trimLevel != 0 ;
+		bool allQual = true ;
+		for ( int i = 0 ; i < readCnt ; ++i )
+		{
+			off[i] = pool.size() ;
+			len[i] = (int)strlen( sortedReads[i].read ) ;
+			if ( len[i] > T4_MAX_READ_LEN )
+				return false ; // the CPU loop handles it (the assembly route will refuse such reads later)
+			pool.append( sortedReads[i].read, len[i] ) ;
+			if ( useQual )
+			{
+				if ( sortedReads[i].qual == NULL )
+					allQual = false ;
+				else
+					qpool.append( sortedReads[i].qual, len[i] ) ;
+			}
+		}
+		if ( useQual && !allQual )
+			return false ; // FASTA input mixed in: per-read qual == NULL cases stay on the CPU
+		pool.append( 16, '\0' ) ;
+		if ( useQual )
+			qpool.append( 16, '\0' ) ;
+		std::vector<int32_t> mn( readCnt ), med( readCnt ), nl( readCnt ) ;
+		std::vector<float> avg( readCnt ) ;
+		Check( t4_kmer_count_stats( pool.data(), useQual ? qpool.data() : NULL, pool.size(), off.data(), len.data(), readCnt, 21, mn.data(),
+			med.data(), avg.data(), nl.data() ) ) ;
+		int trimmed = 0 ;
+		for ( int i = 0 ; i < readCnt ; ++i )
+		{
+			sortedReads[i].minCnt = mn[i] ;
+			sortedReads[i].medianCnt = med[i] ;
+			sortedReads[i].avgCnt = avg[i] ;
+			if ( nl[i] < len[i] )
+			{
+				sortedReads[i].read[ nl[i] ] = '\0' ;
+				++trimmed ;
+			}
+			if ( sortedReads[i].qual != NULL ) // main.cpp:991-1000
+			{
+				free( sortedReads[i].qual ) ;
+				sortedReads[i].qual = NULL ;
+			}
+			if ( sortedReads[i].read[0] == '\0' ) // main.cpp:1004-1009
+			{
+				free( sortedReads[i].read ) ;
+				free( sortedReads[i].id ) ;
+				sortedReads[i].read = NULL ;
+			}
+		}
+		fprintf( stderr, "[trust4_b200] batch route: 21-mer statistics on the device, %d of %d reads trimmed\n", trimmed, readCnt ) ;
+		return true ;
+	}
+
 	// main.cpp:674 `refSet.InputRefFa( optarg )`: the CPU object loads the genes as always; the file name is kept so that the
 	// batch route can build the same gene set on the device (BatchAnnotate).
 	void InputRefFa( char *filename, bool isIMGT = false, const char *imgtAdditionalGap = NULL )
@@ -727,6 +796,9 @@ public:
 // The first line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
 #define T4_BATCH_PREPARE() seqSet.BatchPrepare( sortedReads, refSet, readCnt, hasBarcode, keepMissingBarcode, trimLevel, firstReadLen, \
 	constantGeneEnd, contigMinCov, changeKmerLengthThreshold )
+
+// Opt-in (T4_KMERSTATS=1), in front of the count-statistics loop (main.cpp:981); see BatchKmerStats.
+#define T4_BATCH_KMERSTATS() if ( !seqSet.BatchKmerStats( sortedReads, readCnt, trimLevel, countMyself, contigMinCov > 0 ) )
 
 // The third line (opt-in, T4_ANNOTATE=1), in front of the rough annotation loop (main.cpp:1084); see BatchAnnotate.
 #define T4_BATCH_ANNOTATE() if ( !seqSet.BatchAnnotate( sortedReads, refSet, readCnt ) )

@@ -145,6 +145,44 @@ def test_batch_emu_annotate_on_device(emu_batch_binary, tmp_path, case):
         assert len(a) > 0 and a == open(os.path.join(tmp, "dev" + suf), "rb").read(), (case, suf)
 
 
+def _degrade_qualities(prefix, seed=5):
+    """Give a fifth of the reads of <prefix>_1.fq / _2.fq a low-quality tail (Phred 2) so that the quality trimming of
+    GetCountStatsAndTrim (KmerCount.hpp:241-271, default --trimLevel 1) really cuts reads."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    for m in ("_1.fq", "_2.fq"):
+        lines = open(prefix + m).read().split("\n")
+        for i in range(3, len(lines), 4):
+            if lines[i] and rng.random() < 0.2:
+                q = int(rng.integers(len(lines[i]) // 2, len(lines[i])))
+                lines[i] = lines[i][:q] + "#" * (len(lines[i]) - q)
+                seq = list(lines[i - 2])             # bad bases are often wrong bases: the tail's k-mers become singletons
+                for x in range(q, len(seq)):
+                    if rng.random() < 0.3:
+                        seq[x] = "ACGT"[int(rng.integers(4))]
+                lines[i - 2] = "".join(seq)
+        open(prefix + m, "w").write("\n".join(lines))
+
+
+def test_batch_emu_all_passes_on_device(emu_batch_binary, tmp_path):
+    """Every pass the batch route can offload, together (T4_KMERSTATS=1 T4_ANNOTATE=1 on top of the defaults): 21-mer statistics
+    with quality trimming (main.cpp:981-1010), rough annotation (:1084-1120), AddRead loop + rescue (:1583-1940), AssignRead
+    (:2075-2116) -- on reads whose tails really get trimmed.  The three output files equal the stock binary's byte for byte."""
+    tmp = str(tmp_path)
+    args = write_inputs(tmp, 1500, 50, 35)
+    _degrade_qualities(os.path.join(tmp, "reads"))
+    subprocess.run([STOCK, "-t", "1", "-o", os.path.join(tmp, "stock")] + args, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=900)
+    r = subprocess.run([emu_batch_binary, "-t", "1", "-o", os.path.join(tmp, "dev")] + args, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, T4_STREAMS="1", T4_ANNOTATE="1", T4_KMERSTATS="1"), text=True)
+    m = [l for l in r.stderr.split("\n") if "21-mer statistics on the device" in l]
+    assert m and int(m[0].split(",")[1].split()[0]) > 100, r.stderr[-600:]       # reads were trimmed
+    assert "rough annotation on the device" in r.stderr and "AssignRead pass on the device" in r.stderr
+    for suf in SUFFIXES:
+        a = open(os.path.join(tmp, "stock" + suf), "rb").read()
+        assert len(a) > 0 and a == open(os.path.join(tmp, "dev" + suf), "rb").read(), suf
+
+
 def test_batch_emu_repseq_and_min_cov(emu_batch_binary, tmp_path):
     run_and_compare(emu_batch_binary, write_inputs(str(tmp_path), 800, 25, 22), str(tmp_path),
                     extra=("--trimLevel", "2", "--skipMateExtension", "--contigMinCov", "2"), env={"T4_STREAMS": "1"})
