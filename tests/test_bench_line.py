@@ -42,3 +42,14 @@ def test_reference_sample_order_is_a_fixed_uniform_permutation():
     assert (o == bench.sample_order(4096)).all()
     # any prefix covers the index range evenly: mean index of the first 256 within 10 % of the centre
     assert abs(np.mean(o[:256]) - 2048) < 205
+
+
+def test_bench_source_emits_the_separate_figures():
+    """The AssignRead pass and the k-mer statistics are separate figures of the line (outside value / e2e): their keys are
+    passed to build_line, are not hidden in a comment, and both legs are guarded so that they cannot break the headline."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for key in ('"assign_pass": assign_fig', '"preprocess_kmer_stats": kc_fig'):
+        assert any(key in ln.partition("#")[0] for ln in src.splitlines()), key
+    assert src.count("except Exception as ex:") >= 4
+    args = bench.parse([])
+    assert args.assign_pass == 1 and args.kmer_stats == 1
