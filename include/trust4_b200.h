@@ -382,6 +382,13 @@ int t4_refset_get_overlaps(t4_refset *r, const char *read, int32_t *overlaps, do
  * only so far (no GPU run yet). */
 int t4_refset_annotate(t4_refset *r, const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len,
                        int64_t n, int32_t *gene_overlaps, double *similarity);
+/* std::sort(sortedReads.begin(), sortedReads.end()) of the stage-1 driver (main.cpp:1078) with _sortRead::operator<
+ * (main.cpp:103-125: minCnt, medianCnt, avgCnt, length descending, then read string and id ascending): order[j] = index of
+ * the j-th record.  Host buffers; ids are id_pool[id_off[i] .. id_off[i+1]).  A merge sort of independent binary searches
+ * on the device.  Verified through the test emulation only so far (no GPU run yet). */
+int t4_sort_reads(const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, const char *id_pool,
+                  size_t id_pool_bytes, const uint64_t *id_off, const int32_t *min_cnt, const int32_t *median_cnt,
+                  const float *avg_cnt, int64_t n, int64_t *order);
 /* Test hook, host only: SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) exactly as the scan applies it to the
  * hits (a[i], b[i]) of a diagonal window sorted by b; returns the chain length, the chain in out_a / out_b (room for n). */
 int t4_test_lis(const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b);

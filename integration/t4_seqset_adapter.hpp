@@ -53,6 +53,7 @@
 #define t4_refset_set_radius t4emu_refset_set_radius
 #define t4_refset_annotate t4emu_refset_annotate
 #define t4_kmer_count_stats t4emu_kmer_count_stats
+#define t4_sort_reads t4emu_sort_reads
 #define t4_last_error t4emu_last_error
 #define t4_init t4emu_init
 #endif
@@ -569,6 +570,44 @@ public:
 		return true ;
 	}
 
+	// T4_BATCH_SORT() (opt-in, T4_SORT=1) in front of `std::sort( sortedReads.begin(), sortedReads.end() ) ;` (main.cpp:1078),
+	// which becomes the fall-back statement: the device returns the permutation of _sortRead::operator< (t4_sort_reads) and
+	// the records are moved accordingly.  Emulation-verified only so far.
+	template <class Reads>
+	bool BatchSort( Reads &sortedReads )
+	{
+		const char *env = getenv( "T4_SORT" ) ;
+		const int64_t n = (int64_t)sortedReads.size() ;
+		if ( !gpu || env == NULL || atoi( env ) != 1 || getenv( "T4_STREAMS" ) == NULL || n <= 1 )
+			return false ;
+		std::string pool, idPool ;
+		std::vector<uint64_t> off( n ), idOff( n + 1 ) ;
+		std::vector<int32_t> len( n ), mn( n ), med( n ) ;
+		std::vector<float> avg( n ) ;
+		for ( int64_t i = 0 ; i < n ; ++i )
+		{
+			off[i] = pool.size() ;
+			len[i] = (int32_t)strlen( sortedReads[i].read ) ;
+			pool.append( sortedReads[i].read, len[i] ) ;
+			idOff[i] = idPool.size() ;
+			idPool.append( sortedReads[i].id ) ;
+			mn[i] = sortedReads[i].minCnt ; med[i] = sortedReads[i].medianCnt ; avg[i] = sortedReads[i].avgCnt ;
+		}
+		idOff[n] = idPool.size() ;
+		pool.append( 16, '\0' ) ;
+		idPool.append( 16, '\0' ) ;
+		std::vector<int64_t> order( n ) ;
+		Check( t4_sort_reads( pool.data(), pool.size(), off.data(), len.data(), idPool.data(), idPool.size(), idOff.data(), mn.data(), med.data(),
+			avg.data(), n, order.data() ) ) ;
+		Reads sorted ;
+		sorted.reserve( n ) ;
+		for ( int64_t j = 0 ; j < n ; ++j )
+			sorted.push_back( sortedReads[ order[j] ] ) ;
+		sortedReads.swap( sorted ) ;
+		fprintf( stderr, "[trust4_b200] batch route: %lld reads sorted on the device\n", (long long)n ) ;
+		return true ;
+	}
+
 	// main.cpp:674 `refSet.InputRefFa( optarg )`: the CPU object loads the genes as always; the file name is kept so that the
 	// batch route can build the same gene set on the device (BatchAnnotate).
 	void InputRefFa( char *filename, bool isIMGT = false, const char *imgtAdditionalGap = NULL )
@@ -796,6 +835,9 @@ public:
 // The first line of the batch route, inserted in front of the AddRead loop of main.cpp (integration/make_batch_main.py).
 #define T4_BATCH_PREPARE() seqSet.BatchPrepare( sortedReads, refSet, readCnt, hasBarcode, keepMissingBarcode, trimLevel, firstReadLen, \
 	constantGeneEnd, contigMinCov, changeKmerLengthThreshold )
+
+// Opt-in (T4_SORT=1), in front of std::sort( sortedReads ) (main.cpp:1078); see BatchSort.
+#define T4_BATCH_SORT() if ( !seqSet.BatchSort( sortedReads ) )
 
 // Opt-in (T4_KMERSTATS=1), in front of the count-statistics loop (main.cpp:981); see BatchKmerStats.
 #define T4_BATCH_KMERSTATS() if ( !seqSet.BatchKmerStats( sortedReads, readCnt, trimLevel, countMyself, contigMinCov > 0 ) )

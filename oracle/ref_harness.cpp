@@ -21,6 +21,7 @@
 #include <assert.h>
 #include <limits.h>
 #include <map>
+#include <algorithm>
 #include <vector>
 #include <string>
 
@@ -725,6 +726,52 @@ int t4ref_annotate_read( void *h, const char *read, int32_t *out, double *sim )
 		sim[t] = geneOverlap[t].similarity ;
 	}
 	return ret ;
+}
+
+// std::sort( sortedReads ) of the stage-1 driver (main.cpp:1078).  `struct _sortRead` lives in main.cpp (which defines main
+// and cannot be included), so its operator< (main.cpp:103-125) is restated here line by line on the fields it reads.
+struct T4RefSortRead
+{
+	const char *id ;
+	const char *read ;
+	int minCnt, medianCnt ;
+	float avgCnt ;
+	int len ;
+	int64_t idx ;
+	bool operator<( const T4RefSortRead &b ) const
+	{
+		if ( minCnt != b.minCnt )
+			return minCnt > b.minCnt ;
+		else if ( medianCnt != b.medianCnt )
+			return medianCnt > b.medianCnt ;
+		else if ( avgCnt != b.avgCnt )
+			return avgCnt > b.avgCnt ;
+		else if ( len != b.len )
+			return len > b.len ;
+		else
+		{
+			int tmp = strcmp( read, b.read ) ;
+			if ( tmp != 0 )
+				return tmp < 0 ;
+			else
+				return strcmp( id, b.id ) < 0 ;
+		}
+	}
+} ;
+
+int t4ref_sort_reads( const char *const *reads, const char *const *ids, const int32_t *minCnt, const int32_t *medianCnt, const float *avgCnt,
+	int64_t n, int64_t *order )
+{
+	std::vector<T4RefSortRead> v( n ) ;
+	for ( int64_t i = 0 ; i < n ; ++i )
+	{
+		v[i].id = ids[i] ; v[i].read = reads[i] ; v[i].minCnt = minCnt[i] ; v[i].medianCnt = medianCnt[i] ; v[i].avgCnt = avgCnt[i] ;
+		v[i].len = (int)strlen( reads[i] ) ; v[i].idx = i ;
+	}
+	std::sort( v.begin(), v.end() ) ;
+	for ( int64_t i = 0 ; i < n ; ++i )
+		order[i] = v[i].idx ;
+	return 0 ;
 }
 
 } // extern "C"

@@ -35,7 +35,7 @@ def emu_lib():
     """TEST-ONLY single-thread emulation of the device code (g++ -DT4_EMU): lets the bit-exact logic of the
     engine be checked against the oracle without a GPU.  Exports t4emu_* symbols; never shipped."""
     from trust4_b200 import api
-    src = [os.path.join(ROOT, "trust4_b200", "csrc", f) for f in ("t4_api.cu", "t4_engine.h", "t4_common.h", "t4_shard.h", "t4_probe.cuh", "t4_assign.h", "t4_refscan.h", "t4_kcount.h", "t4_annot.h")]
+    src = [os.path.join(ROOT, "trust4_b200", "csrc", f) for f in ("t4_api.cu", "t4_engine.h", "t4_common.h", "t4_shard.h", "t4_probe.cuh", "t4_assign.h", "t4_refscan.h", "t4_kcount.h", "t4_annot.h", "t4_readsort.h")]
     src.append(os.path.join(ROOT, "include", "trust4_b200.h"))
     out = os.path.join(ROOT, "tests", "emu", "libt4emu.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)

@@ -1019,3 +1019,51 @@ def check_refset_annotate(lib, ref, tmp_path, seed=141, n=600, radius=None, hit_
     assert n_set[0] > n // 5 and n_set[2] > n // 20 and n_set[3] > n // 10, n_set
     g.close()
     return int(n_set.sum())
+
+
+def check_sort_reads(lib, ref, seed=151, n=5000):
+    """t4_sort_reads against std::sort with the driver's _sortRead::operator< (main.cpp:103-125, 1078): reads with their real
+    k-mer statistics plus adversarial ties -- equal statistics with different strings, prefixes of each other, identical
+    reads under different ids (mates, the '.1' copies), negative statistics, N's."""
+    rng = np.random.default_rng(seed)
+    cl = synth.make_clones(40, seed)
+    rd = synth.sample_pairs(cl, n // 4, 150, seed, sub_rate=0.01)
+    reads = [synth.decode(c) for c in rd.codes]
+    ids = ["r%d" % (i // 2) for i in range(len(reads))]                 # mates share an id (main.cpp:1069)
+    src = list(reads)
+    while len(reads) < n:
+        kind = int(rng.integers(0, 6))
+        s = src[int(rng.integers(len(src)))]
+        if kind == 0:
+            t = s[: int(rng.integers(20, 150))]
+        elif kind == 1:
+            t = s
+        elif kind == 2:
+            t = list(s)
+            t[int(rng.integers(len(t)))] = "N"
+            t = "".join(t)
+        elif kind == 3:
+            t = "".join("ACGT"[c] for c in rng.integers(0, 4, size=int(rng.integers(10, 160))))
+        elif kind == 4:
+            t = s[:75]
+        else:
+            t = s[10:]
+        reads.append(t)
+        ids.append(("r%d" % int(rng.integers(0, n))) + (".1" if rng.random() < 0.2 else ""))
+    lens = np.array([len(x) for x in reads], dtype=np.int32)
+    off = np.zeros(len(reads), dtype=np.uint64)
+    off[1:] = np.cumsum(lens[:-1])
+    pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    mn, med, avg, _ = ref.kmer_count_stats(pool, off, lens, 21)
+    # coarsen a part of the statistics so that long runs of equal (min, median, avg, len) must be decided by the strings
+    coarse = rng.random(len(reads)) < 0.5
+    mn = np.where(coarse, np.minimum(mn, 2), mn).astype(np.int32)
+    med = np.where(coarse, np.minimum(med, 3), med).astype(np.int32)
+    avg = np.where(coarse, np.float32(2.5), avg).astype(np.float32)
+    ro = ref.sort_reads(reads, ids, mn, med, avg)
+    go = api.sort_reads(pool, off, lens, ids, mn, med, avg, lib)
+    key = lambda i: (reads[i], ids[i], int(mn[i]), int(med[i]), float(avg[i]))
+    assert sorted(go.tolist()) == list(range(len(reads)))
+    # records that compare equal in every field may come in either order: compare the sorted RECORDS, not the indices
+    assert [key(i) for i in go] == [key(i) for i in ro], np.flatnonzero(np.array([key(i) != key(j) for i, j in zip(go, ro)]))[:5]
+    return len(reads)

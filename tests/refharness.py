@@ -68,6 +68,7 @@ def lib():
         l.t4ref_has_hit_in_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         l.t4ref_is_low_complexity.argtypes = [C.c_char_p]
         l.t4ref_annotate_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
+        l.t4ref_sort_reads.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.t4ref_lis.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.t4ref_input_seqset.restype = C.c_void_p
         l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]
@@ -259,6 +260,17 @@ def kmer_count_stats(pool, seq_off, lens, k=21, qual=None):
     lib().t4ref_kmer_count_stats(pool.ctypes.data, qual.ctypes.data if qual is not None else None, seq_off.ctypes.data, lens.ctypes.data, n, k,
                                  mn.ctypes.data, med.ctypes.data, avg.ctypes.data, nl.ctypes.data)
     return mn[:n], med[:n], avg[:n], nl[:n]
+
+
+def sort_reads(reads, ids, min_cnt, median_cnt, avg_cnt):
+    """std::sort with _sortRead::operator< (main.cpp:103-125): the permutation (order[j] = original index)."""
+    n = len(reads)
+    ra = (C.c_char_p * max(1, n))(*[r.encode() for r in reads])
+    ia = (C.c_char_p * max(1, n))(*[i.encode() for i in ids])
+    order = np.zeros(max(1, n), dtype=np.int64)
+    lib().t4ref_sort_reads(ra, ia, np.ascontiguousarray(min_cnt, dtype=np.int32).ctypes.data, np.ascontiguousarray(median_cnt, dtype=np.int32).ctypes.data,
+                           np.ascontiguousarray(avg_cnt, dtype=np.float32).ctypes.data, n, order.ctypes.data)
+    return order[:n]
 
 
 def assembled_list(ret, resc):

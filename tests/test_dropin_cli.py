@@ -165,8 +165,9 @@ def _degrade_qualities(prefix, seed=5):
 
 
 def test_batch_emu_all_passes_on_device(emu_batch_binary, tmp_path):
-    """Every pass the batch route can offload, together (T4_KMERSTATS=1 T4_ANNOTATE=1 on top of the defaults): 21-mer statistics
-    with quality trimming (main.cpp:981-1010), rough annotation (:1084-1120), AddRead loop + rescue (:1583-1940), AssignRead
+    """Every pass the batch route can offload, together (T4_KMERSTATS=1 T4_SORT=1 T4_ANNOTATE=1 on top of the defaults): 21-mer
+    statistics with quality trimming (main.cpp:981-1010), the read sort (:1078), rough annotation (:1084-1120), AddRead loop +
+    rescue (:1583-1940), AssignRead
     (:2075-2116) -- on reads whose tails really get trimmed.  The three output files equal the stock binary's byte for byte."""
     tmp = str(tmp_path)
     args = write_inputs(tmp, 1500, 50, 35)
@@ -174,7 +175,8 @@ def test_batch_emu_all_passes_on_device(emu_batch_binary, tmp_path):
     subprocess.run([STOCK, "-t", "1", "-o", os.path.join(tmp, "stock")] + args, check=True, stdout=subprocess.DEVNULL,
                    stderr=subprocess.DEVNULL, timeout=900)
     r = subprocess.run([emu_batch_binary, "-t", "1", "-o", os.path.join(tmp, "dev")] + args, check=True, stdout=subprocess.DEVNULL,
-                       stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, T4_STREAMS="1", T4_ANNOTATE="1", T4_KMERSTATS="1"), text=True)
+                       stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, T4_STREAMS="1", T4_ANNOTATE="1", T4_KMERSTATS="1", T4_SORT="1"), text=True)
+    assert "reads sorted on the device" in r.stderr
     m = [l for l in r.stderr.split("\n") if "21-mer statistics on the device" in l]
     assert m and int(m[0].split(",")[1].split()[0]) > 100, r.stderr[-600:]       # reads were trimmed
     assert "rough annotation on the device" in r.stderr and "AssignRead pass on the device" in r.stderr

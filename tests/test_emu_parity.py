@@ -120,3 +120,17 @@ def test_emu_refset_overlaps(emu_lib, ref, tmp_path, seed, radius, hit_len):
 def test_emu_refset_annotate(emu_lib, ref, tmp_path, seed, radius, hit_len):
     """SURVEY.md 8f-1: SeqSet::AnnotateRead(read, 0, ...) on the reference gene set (emulation only, see t4_annot.h)."""
     assert pc.check_refset_annotate(emu_lib, ref, tmp_path, seed=seed, radius=radius, hit_len=hit_len) > 300
+
+
+def test_emu_sort_reads(emu_lib, ref):
+    """SURVEY.md 8f-3, the sort: std::sort(sortedReads) with _sortRead::operator< (emulation only, see t4_readsort.h)."""
+    import numpy as np
+    from trust4_b200 import api
+    assert pc.check_sort_reads(emu_lib, ref) == 5000
+    assert pc.check_sort_reads(emu_lib, ref, seed=152, n=777) == 777          # not a power of two: ragged last runs
+    pool = np.frombuffer(b"ACGTACGTAC" + b"\0" * 16, dtype=np.uint8).copy()
+    for n in (0, 1, 2, 3):
+        order = api.sort_reads(pool, np.arange(n, dtype=np.uint64), np.full(n, 5, dtype=np.int32), ["r%d" % (9 - i) for i in range(n)],
+                               np.ones(n, np.int32), np.ones(n, np.int32), np.ones(n, np.float32), emu_lib)
+        reads = [bytes(pool[i:i + 5]).decode() for i in range(n)]
+        assert order.tolist() == ref.sort_reads(reads, ["r%d" % (9 - i) for i in range(n)], np.ones(n), np.ones(n), np.ones(n)).tolist()

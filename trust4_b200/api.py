@@ -37,7 +37,7 @@ EXPORTS = [
     "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
     "kmer_count_stats", "kmer_count_table_bytes", "kmer_count_stats_device", "kmer_count_table_stats",
     "refset_create_from_fa", "refset_free", "refset_size", "refset_name", "refset_seqset", "refset_set_hit_len_required",
-    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps", "refset_annotate",
+    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps", "refset_annotate", "sort_reads",
 ]
 
 
@@ -135,6 +135,7 @@ class Lib:
         f("test_lis", ci, [vp, vp, ci, vp, vp])
         f("refset_get_overlaps", ci, [vp, cs, vp, vp, ci])
         f("refset_annotate", ci, [vp, vp, C.c_size_t, vp, vp, C.c_int64, vp, vp])
+        f("sort_reads", ci, [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, C.c_int64, vp])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)
@@ -512,6 +513,25 @@ class RefSet:
         self.lib.check(self.lib.refset_scan(self.h, pool.ctypes.data, pool.nbytes, seq_off.ctypes.data, lens.ctypes.data, n,
                                             strand.ctypes.data, low.ctypes.data, st.ctypes.data))
         return strand[:n], low[:n], dict(with_hit=int(st[0]), low_complexity=int(st[1]))
+
+
+def sort_reads(pool, seq_off, lens, ids, min_cnt, median_cnt, avg_cnt, lib: Lib | None = None):
+    """t4_sort_reads: the permutation std::sort(sortedReads) applies (main.cpp:1078).  ids: list of bytes / str."""
+    lib = lib or default_lib()
+    pool = np.ascontiguousarray(pool)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    n = len(lens)
+    idb = [i if isinstance(i, bytes) else i.encode() for i in ids]
+    id_off = np.zeros(n + 1, dtype=np.uint64)
+    id_off[1:] = np.cumsum([len(i) for i in idb])
+    id_pool = np.frombuffer(b"".join(idb) + b"\0" * 16, dtype=np.uint8).copy()
+    order = np.zeros(max(1, n), dtype=np.int64)
+    lib.check(lib.sort_reads(pool.ctypes.data, pool.nbytes, seq_off.ctypes.data, lens.ctypes.data, id_pool.ctypes.data, id_pool.nbytes,
+                             id_off.ctypes.data, np.ascontiguousarray(min_cnt, dtype=np.int32).ctypes.data,
+                             np.ascontiguousarray(median_cnt, dtype=np.int32).ctypes.data,
+                             np.ascontiguousarray(avg_cnt, dtype=np.float32).ctypes.data, n, order.ctypes.data))
+    return order[:n]
 
 
 ASSIGN_NOT_LISTED = -2

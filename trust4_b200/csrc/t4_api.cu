@@ -20,6 +20,7 @@
 #include "t4_refscan.h"
 #include "t4_annot.h"
 #include "t4_kcount.h"
+#include "t4_readsort.h"
 
 #if T4_CUDA
 #include <cuda_runtime.h>
@@ -86,6 +87,13 @@ __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_aux_kernel( cha
 	cx.tid = threadIdx.x ;
 	cx.nt = blockDim.x ;
 	c_run_aux_op( cx, op ) ;
+}
+
+// one merge pass of the read sort (t4_readsort.h); emulation-verified only, like t4_annot_kernel
+__global__ void t4_readsort_kernel( T4SortParams P )
+{
+	for ( i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x ; i < P.n ; i += (i64)gridDim.x * blockDim.x )
+		t4_sort_merge_one( P, i ) ;
 }
 
 // GetOverlapsFromRead on a reference gene set (t4_annot.h): a kernel of its own, so that the kernels validated on the GPU
@@ -2728,6 +2736,75 @@ int T4_API( refset_annotate )( t4_refset *r, const char *read_pool, size_t pool_
 	if ( !rc ) rc = T4_API( streams_error )( r->workers.data(), nw ) ;
 	if ( !rc ) rc = d2h( gene_overlaps, b + oOut, (size_t)n * 4 * 8 * 4 ) ;
 	if ( !rc ) rc = d2h( similarity, b + oSim, (size_t)n * 4 * 8 ) ;
+	dfree( p ) ;
+	return rc ;
+}
+
+// `std::sort( sortedReads.begin(), sortedReads.end() )` of the stage-1 driver (main.cpp:1078; _sortRead::operator<, :103-125):
+// order[j] = index of the record that comes j-th.  Host buffers; record i: read_pool[seq_off[i] .. + len[i]), its id
+// id_pool[id_off[i] .. id_off[i + 1]), its count statistics.  NOTE: verified through the test emulation only (t4_readsort.h).
+int T4_API( sort_reads )( const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, const char *id_pool,
+	size_t id_pool_bytes, const uint64_t *id_off, const int32_t *min_cnt, const int32_t *median_cnt, const float *avg_cnt, int64_t n,
+	int64_t *order )
+{
+	int rc = ensure_up() ;
+	if ( rc ) return rc ;
+	if ( n < 0 || !read_pool || !seq_off || !len || !id_pool || !id_off || !min_cnt || !median_cnt || !avg_cnt || !order )
+	{
+		set_err( "t4_sort_reads: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	if ( n == 0 )
+		return 0 ;
+	std::vector<T4SortRec> recs( (size_t)n ) ;
+	std::vector<i64> idx( (size_t)n ) ;
+	for ( i64 i = 0 ; i < n ; ++i )
+	{
+		if ( len[i] < 0 || seq_off[i] + (u64)len[i] > pool_bytes || id_off[i + 1] < id_off[i] || id_off[i + 1] > id_pool_bytes )
+		{
+			set_err( "t4_sort_reads: record outside its pool" ) ;
+			return T4_E_INVAL ;
+		}
+		T4SortRec &r = recs[(size_t)i] ;
+		r.minCnt = min_cnt[i] ; r.medianCnt = median_cnt[i] ; r.avgCnt = avg_cnt[i] ; r.len = len[i] ;
+		r.readOff = seq_off[i] ; r.idOff = id_off[i] ; r.idLen = (int32_t)( id_off[i + 1] - id_off[i] ) ; r.pad = 0 ;
+		idx[(size_t)i] = i ;
+	}
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t oRec = 0, oPool = al( (size_t)n * sizeof( T4SortRec ) ), oId = oPool + al( pool_bytes + 16 ), oA = oId + al( id_pool_bytes + 16 ),
+		oB = oA + al( (size_t)n * 8 ), total = oB + al( (size_t)n * 8 ) ;
+	void *p = 0 ;
+	rc = dmalloc( &p, total ) ;
+	if ( rc ) return rc ;
+	char *b = (char *)p ;
+	rc = h2d( b + oRec, recs.data(), (size_t)n * sizeof( T4SortRec ) ) ;
+	if ( !rc ) rc = h2d( b + oPool, read_pool, pool_bytes ) ;
+	if ( !rc ) rc = h2d( b + oId, id_pool, id_pool_bytes ) ;
+	if ( !rc ) rc = h2d( b + oA, idx.data(), (size_t)n * 8 ) ;
+	T4SortParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	P.recs = (u64)(uintptr_t)( b + oRec ) ; P.pool = (u64)(uintptr_t)( b + oPool ) ; P.idPool = (u64)(uintptr_t)( b + oId ) ;
+	P.n = n ;
+	size_t from = oA, to = oB ;
+	for ( i64 w = 1 ; !rc && w < n ; w *= 2 )
+	{
+		P.src = (u64)(uintptr_t)( b + from ) ; P.dst = (u64)(uintptr_t)( b + to ) ; P.width = w ;
+#if T4_CUDA
+		const int threads = 256 ;
+		i64 blocks = ( n + threads - 1 ) / threads ;
+		if ( blocks > 148 * 16 )
+			blocks = 148 * 16 ;
+		t4_readsort_kernel<<<(int)blocks, threads>>>( P ) ;
+		if ( cudaGetLastError() != cudaSuccess )
+			rc = T4_E_CUDA ;
+#else
+		for ( i64 i = 0 ; i < n ; ++i )
+			t4_sort_merge_one( P, i ) ;
+#endif
+		const size_t t = from ; from = to ; to = t ;
+	}
+	if ( !rc ) rc = dsync() ;
+	if ( !rc ) rc = d2h( order, b + from, (size_t)n * 8 ) ;
 	dfree( p ) ;
 	return rc ;
 }
