@@ -389,6 +389,14 @@ int t4_refset_annotate(t4_refset *r, const char *read_pool, size_t pool_bytes, c
 int t4_sort_reads(const char *read_pool, size_t pool_bytes, const uint64_t *seq_off, const int32_t *len, const char *id_pool,
                   size_t id_pool_bytes, const uint64_t *id_off, const int32_t *min_cnt, const int32_t *median_cnt,
                   const float *avg_cnt, int64_t n, int64_t *order);
+/* AlignAlgo::IsMateOverlap(fr, flen, sr, slen, minOverlap, offset, bestMatchCnt, checkTandem) (AlignAlgo.hpp:1027-1096)
+ * for n read pairs, as ProcessRead calls it to detect read-through and overlapping mates (main.cpp:264, 291): overlap_size[i]
+ * is the return value (-1: no unambiguous overlap), offset[i] / best_match_cnt[i] the two outputs as the function leaves them
+ * (-1 when it never assigned them).  Host buffers.  Verified through the test emulation only so far (no GPU run yet). */
+int t4_mate_overlap_batch(const char *read_pool, size_t pool_bytes, const uint64_t *f_off, const int32_t *f_len,
+                          const uint64_t *s_off, const int32_t *s_len, const int32_t *min_overlap,
+                          const uint8_t *check_tandem, int64_t n, int32_t *overlap_size, int32_t *offset,
+                          int32_t *best_match_cnt);
 /* Test hook, host only: SeqSet::LongestIncreasingSubsequence (SeqSet.hpp:342-474) exactly as the scan applies it to the
  * hits (a[i], b[i]) of a diagonal window sorted by b; returns the chain length, the chain in out_a / out_b (room for n). */
 int t4_test_lis(const int32_t *a, const int32_t *b, int n, int32_t *out_a, int32_t *out_b);

@@ -774,4 +774,15 @@ int t4ref_sort_reads( const char *const *reads, const char *const *ids, const in
 	return 0 ;
 }
 
+// AlignAlgo::IsMateOverlap (AlignAlgo.hpp:1027); offset / bestMatchCnt start at -1 (the function only assigns offset when it
+// finds a candidate)
+int t4ref_is_mate_overlap( const char *fr, int flen, const char *sr, int slen, int minOverlap, int checkTandem, int32_t *offset, int32_t *bestMatchCnt )
+{
+	int off = -1, best = -1 ;
+	int ret = AlignAlgo::IsMateOverlap( (char *)fr, flen, (char *)sr, slen, minOverlap, off, best, checkTandem != 0 ) ;
+	*offset = off ;
+	*bestMatchCnt = best ;
+	return ret ;
+}
+
 } // extern "C"

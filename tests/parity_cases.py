@@ -1067,3 +1067,68 @@ def check_sort_reads(lib, ref, seed=151, n=5000):
     # records that compare equal in every field may come in either order: compare the sorted RECORDS, not the indices
     assert [key(i) for i in go] == [key(i) for i in ro], np.flatnonzero(np.array([key(i) != key(j) for i, j in zip(go, ro)]))[:5]
     return len(reads)
+
+
+def check_mate_overlap(lib, ref, seed=161, n=3000):
+    """t4_mate_overlap_batch against AlignAlgo::IsMateOverlap (AlignAlgo.hpp:1027-1096): return value, offset, bestMatchCnt
+    for overlapping mates (with mismatches), read-through pairs, unrelated pairs, tandem repeats, both checkTandem settings
+    and the two minOverlap formulas of ProcessRead (main.cpp:244-249)."""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+
+    def rnd(L):
+        return "".join("ACGT"[c] for c in rng.integers(0, 4, size=L))
+
+    fr, sr = [], []
+    for i in range(n):
+        kind = int(rng.integers(0, 6))
+        L1, L2 = int(rng.integers(30, 160)), int(rng.integers(30, 160))
+        if kind == 0:       # suffix of f = prefix of s
+            ov = int(rng.integers(5, min(L1, L2)))
+            f = rnd(L1)
+            s = f[L1 - ov:] + rnd(L2 - ov)
+        elif kind == 1:     # the same with a few mismatches
+            ov = int(rng.integers(10, min(L1, L2)))
+            f = rnd(L1)
+            t = list(f[L1 - ov:])
+            for q in rng.integers(0, ov, size=int(rng.integers(1, 5))):
+                t[int(q)] = "ACGT"[int(rng.integers(4))]
+            s = "".join(t) + rnd(L2 - ov)
+        elif kind == 2:     # read-through: s inside f
+            f = rnd(L1)
+            st = int(rng.integers(0, L1 // 2))
+            s = f[st:st + L2]
+        elif kind == 3:     # tandem repeats
+            u = rnd(int(rng.integers(1, 5)))
+            f = rnd(L1 // 2) + u * 20
+            s = u * 20 + rnd(L2 // 2)
+        elif kind == 4:
+            f, s = rnd(L1), rnd(L2)
+        else:               # two candidate offsets: ambiguous
+            core = rnd(25)
+            f = rnd(20) + core + rnd(15) + core
+            s = core + rnd(L2)
+        fr.append(f)
+        sr.append(s)
+    reads = fr + sr
+    lens = np.array([len(x) for x in reads], dtype=np.int32)
+    off = np.zeros(len(reads), dtype=np.uint64)
+    off[1:] = np.cumsum(lens[:-1])
+    pool = np.frombuffer(("".join(reads) + "\0" * 16).encode(), dtype=np.uint8).copy()
+    fo, so = off[:n].copy(), off[n:].copy()
+    fl, sl = lens[:n].copy(), lens[n:].copy()
+    tot = fl + sl
+    mo = np.where(rng.random(n) < 0.5, np.minimum(tot // 10, 31), np.minimum(tot // 20, 31)).astype(np.int32)
+    ct = (rng.random(n) < 0.6).astype(np.uint8)
+    gos, gof, gbm = (np.zeros(n, dtype=np.int32) for _ in range(3))
+    lib.check(lib.mate_overlap_batch(pool.ctypes.data, pool.nbytes, fo.ctypes.data, fl.ctypes.data, so.ctypes.data, sl.ctypes.data, mo.ctypes.data,
+                                     ct.ctypes.data, n, gos.ctypes.data, gof.ctypes.data, gbm.ctypes.data))
+    l = ref.lib()
+    n_pos = 0
+    for i in range(n):
+        o, b = C.c_int32(), C.c_int32()
+        r = l.t4ref_is_mate_overlap(fr[i].encode(), len(fr[i]), sr[i].encode(), len(sr[i]), int(mo[i]), int(ct[i]), C.byref(o), C.byref(b))
+        assert (r, o.value, b.value) == (int(gos[i]), int(gof[i]), int(gbm[i])), (i, r, o.value, b.value, gos[i], gof[i], gbm[i], fr[i], sr[i])
+        n_pos += r >= 0
+    assert n_pos > n // 5 and n_pos < n
+    return n_pos

@@ -69,6 +69,7 @@ def lib():
         l.t4ref_is_low_complexity.argtypes = [C.c_char_p]
         l.t4ref_annotate_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         l.t4ref_sort_reads.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        l.t4ref_is_mate_overlap.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         l.t4ref_lis.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.t4ref_input_seqset.restype = C.c_void_p
         l.t4ref_input_seqset.argtypes = [C.c_void_p, C.c_int]

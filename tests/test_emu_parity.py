@@ -134,3 +134,8 @@ def test_emu_sort_reads(emu_lib, ref):
                                np.ones(n, np.int32), np.ones(n, np.int32), np.ones(n, np.float32), emu_lib)
         reads = [bytes(pool[i:i + 5]).decode() for i in range(n)]
         assert order.tolist() == ref.sort_reads(reads, ["r%d" % (9 - i) for i in range(n)], np.ones(n), np.ones(n), np.ones(n)).tolist()
+
+
+def test_emu_mate_overlap(emu_lib, ref):
+    """SURVEY.md 8f-3, mate read-through / merge detection: AlignAlgo::IsMateOverlap per pair (emulation only)."""
+    assert pc.check_mate_overlap(emu_lib, ref) > 600

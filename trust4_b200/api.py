@@ -37,7 +37,7 @@ EXPORTS = [
     "streams_assign_reads", "assign_free", "assign_results", "assign_stats", "assign_extended_set", "assign_device_buffers",
     "kmer_count_stats", "kmer_count_table_bytes", "kmer_count_stats_device", "kmer_count_table_stats",
     "refset_create_from_fa", "refset_free", "refset_size", "refset_name", "refset_seqset", "refset_set_hit_len_required",
-    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps", "refset_annotate", "sort_reads",
+    "refset_set_radius", "refset_scan", "refset_scan_device", "test_lis", "refset_get_overlaps", "refset_annotate", "sort_reads", "mate_overlap_batch",
 ]
 
 
@@ -136,6 +136,7 @@ class Lib:
         f("refset_get_overlaps", ci, [vp, cs, vp, vp, ci])
         f("refset_annotate", ci, [vp, vp, C.c_size_t, vp, vp, C.c_int64, vp, vp])
         f("sort_reads", ci, [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, C.c_int64, vp])
+        f("mate_overlap_batch", ci, [vp, C.c_size_t, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.dll, self.prefix + name)

@@ -96,6 +96,12 @@ __global__ void t4_readsort_kernel( T4SortParams P )
 		t4_sort_merge_one( P, i ) ;
 }
 
+__global__ void t4_mate_overlap_kernel( T4MateParams P )
+{
+	for ( i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x ; i < P.n ; i += (i64)gridDim.x * blockDim.x )
+		t4_mate_overlap_one( P, i ) ;
+}
+
 // GetOverlapsFromRead on a reference gene set (t4_annot.h): a kernel of its own, so that the kernels validated on the GPU
 // keep their exact SASS while this one is verified through the emulation only
 __global__ void __launch_bounds__( T4_MAX_NT, T4_MIN_BLOCKS ) t4_annot_kernel( char *A, T4Op *ops )
@@ -2805,6 +2811,71 @@ int T4_API( sort_reads )( const char *read_pool, size_t pool_bytes, const uint64
 	}
 	if ( !rc ) rc = dsync() ;
 	if ( !rc ) rc = d2h( order, b + from, (size_t)n * 8 ) ;
+	dfree( p ) ;
+	return rc ;
+}
+
+// AlignAlgo::IsMateOverlap for n (first, second) read pairs of one pool (ProcessRead, main.cpp:264, 291): overlap_size[i] =
+// the return value (-1: no unambiguous overlap), offset[i] / best_match_cnt[i] the two reference outputs.  Host buffers.
+// NOTE: verified through the test emulation only (t4_readsort.h).
+int T4_API( mate_overlap_batch )( const char *read_pool, size_t pool_bytes, const uint64_t *f_off, const int32_t *f_len, const uint64_t *s_off,
+	const int32_t *s_len, const int32_t *min_overlap, const uint8_t *check_tandem, int64_t n, int32_t *overlap_size, int32_t *offset,
+	int32_t *best_match_cnt )
+{
+	int rc = ensure_up() ;
+	if ( rc ) return rc ;
+	if ( n < 0 || !read_pool || !f_off || !f_len || !s_off || !s_len || !min_overlap || !check_tandem || !overlap_size || !offset || !best_match_cnt )
+	{
+		set_err( "t4_mate_overlap_batch: bad argument" ) ;
+		return T4_E_INVAL ;
+	}
+	for ( i64 i = 0 ; i < n ; ++i )
+		if ( f_len[i] < 0 || s_len[i] < 0 || f_off[i] + (u64)f_len[i] > pool_bytes || s_off[i] + (u64)s_len[i] > pool_bytes )
+		{
+			set_err( "t4_mate_overlap_batch: record outside the pool" ) ;
+			return T4_E_INVAL ;
+		}
+	if ( n == 0 )
+		return 0 ;
+	auto al = []( size_t x ) { return ( x + 255 ) & ~(size_t)255 ; } ;
+	const size_t n8 = al( (size_t)n * 8 ), n4 = al( (size_t)n * 4 ), n1 = al( (size_t)n ) ;
+	const size_t oPool = 0, oFo = al( pool_bytes + 16 ), oSo = oFo + n8, oFl = oSo + n8, oSl = oFl + n4, oMo = oSl + n4, oCt = oMo + n4,
+		oOs = oCt + n1, oOf = oOs + n4, oBm = oOf + n4, total = oBm + n4 ;
+	void *p = 0 ;
+	rc = dmalloc( &p, total ) ;
+	if ( rc ) return rc ;
+	char *b = (char *)p ;
+	rc = h2d( b + oPool, read_pool, pool_bytes ) ;
+	if ( !rc ) rc = h2d( b + oFo, f_off, (size_t)n * 8 ) ;
+	if ( !rc ) rc = h2d( b + oSo, s_off, (size_t)n * 8 ) ;
+	if ( !rc ) rc = h2d( b + oFl, f_len, (size_t)n * 4 ) ;
+	if ( !rc ) rc = h2d( b + oSl, s_len, (size_t)n * 4 ) ;
+	if ( !rc ) rc = h2d( b + oMo, min_overlap, (size_t)n * 4 ) ;
+	if ( !rc ) rc = h2d( b + oCt, check_tandem, (size_t)n ) ;
+	T4MateParams P ;
+	memset( &P, 0, sizeof( P ) ) ;
+	auto dp = [&]( size_t off ) { return (u64)(uintptr_t)( b + off ) ; } ;
+	P.pool = dp( oPool ) ; P.fOff = dp( oFo ) ; P.sOff = dp( oSo ) ; P.fLen = dp( oFl ) ; P.sLen = dp( oSl ) ; P.minOverlap = dp( oMo ) ;
+	P.checkTandem = dp( oCt ) ; P.overlapSize = dp( oOs ) ; P.offset = dp( oOf ) ; P.bestMatchCnt = dp( oBm ) ;
+	P.n = n ;
+	if ( !rc )
+	{
+#if T4_CUDA
+		i64 blocks = ( n + 127 ) / 128 ;
+		if ( blocks > 148 * 16 )
+			blocks = 148 * 16 ;
+		t4_mate_overlap_kernel<<<(int)blocks, 128>>>( P ) ;
+		if ( cudaGetLastError() != cudaSuccess )
+			rc = T4_E_CUDA ;
+#else
+		for ( i64 i = 0 ; i < n ; ++i )
+			t4_mate_overlap_one( P, i ) ;
+#endif
+	}
+	if ( !rc ) rc = dsync() ;
+	if ( !rc ) rc = d2h( overlap_size, b + oOs, (size_t)n * 4 ) ;
+	if ( !rc ) rc = d2h( offset, b + oOf, (size_t)n * 4 ) ;
+	if ( !rc ) rc = d2h( best_match_cnt, b + oBm, (size_t)n * 4 ) ;
 	dfree( p ) ;
 	return rc ;
 }

@@ -106,4 +106,86 @@ T4_HD inline void t4_sort_merge_one( const T4SortParams &P, i64 i )
 	}
 }
 
+// ---- mate overlap detection ("mate read-through / merge") -------------------------------------------------
+// AlignAlgo::IsMateOverlap( fr, flen, sr, slen, minOverlap, offset, bestMatchCnt, checkTandem ) (AlignAlgo.hpp:1027-1096) as
+// ProcessRead calls it for every read pair (main.cpp:264, 291): does a suffix of `fr` match a prefix of `sr` at exactly one
+// offset (similarity threshold 0.85 ... 0.95 by length), and is the match not a tandem repeat?  One thread per pair.
+// Same emulation-only status as the sort above.
+struct T4MateParams
+{
+	u64 pool ;             // ASCII reads
+	u64 fOff, sOff ;       // u64[n]
+	u64 fLen, sLen ;       // i32[n]
+	u64 minOverlap ;       // i32[n]
+	u64 checkTandem ;      // u8[n]
+	u64 overlapSize, offset, bestMatchCnt ; // i32[n] out; offset / bestMatchCnt as the function leaves them (-1 / -1 untouched)
+	i64 n ;
+} ;
+
+T4_HD inline void t4_mate_overlap_one( const T4MateParams &P, i64 r )
+{
+	const char *fr = t4_x<char>( P.pool ) + t4_x<u64>( P.fOff )[r] ;
+	const char *sr = t4_x<char>( P.pool ) + t4_x<u64>( P.sOff )[r] ;
+	const int flen = t4_x<int32_t>( P.fLen )[r], slen = t4_x<int32_t>( P.sLen )[r] ;
+	const int minOverlap = t4_x<int32_t>( P.minOverlap )[r] ;
+	const bool checkTandem = t4_x<unsigned char>( P.checkTandem )[r] != 0 ;
+	int i, j, k = 0 ;
+	int bestMatchCnt = -1, offset = -1 ;
+	int offsetCnt = 0 ;
+	int overlapSize = -1 ;
+	for ( j = 0 ; j < flen - minOverlap ; ++j )
+	{
+		int matchCnt = 0 ;
+		bool flag = true ;
+		double similarityThreshold = 0.95 ;
+		if ( flen - j >= 100 )
+			similarityThreshold = 0.85 ;
+		else if ( flen - j >= 50 )
+			similarityThreshold = 0.85 + ( flen - j - 50 ) / 50.0 * 0.1 ;
+		for ( k = 0 ; j + k < flen && k < slen ; ++k )
+		{
+			if ( fr[j + k] == sr[k] )
+				++matchCnt ;
+			if ( matchCnt + ( flen - ( j + k ) - 1 ) < int( ( flen - j ) * similarityThreshold ) )
+			{
+				flag = false ;
+				break ;
+			}
+		}
+		if ( flag )
+		{
+			offset = j ;
+			++offsetCnt ;
+			overlapSize = k ;
+			bestMatchCnt = matchCnt ;
+		}
+	}
+	int ret = overlapSize ;
+	if ( offsetCnt != 1 )
+		ret = -1 ;
+	else if ( checkTandem && overlapSize <= minOverlap * 2 )
+	{
+		for ( i = 1 ; i <= overlapSize / 2 && ret >= 0 ; ++i )
+		{
+			bool tandem = true ;
+			for ( j = i ; j + i - 1 < overlapSize ; j += i )
+			{
+				for ( k = j ; k <= j + i - 1 ; ++k )
+					if ( sr[k - j] != sr[k] )
+						break ;
+				if ( k <= j + i - 1 )
+				{
+					tandem = false ;
+					break ;
+				}
+			}
+			if ( tandem )
+				ret = -1 ;
+		}
+	}
+	t4_x<int32_t>( P.overlapSize )[r] = ret ;
+	t4_x<int32_t>( P.offset )[r] = offset ;
+	t4_x<int32_t>( P.bestMatchCnt )[r] = bestMatchCnt ;
+}
+
 #endif
